@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- WKV-7 hot path, BASELINE.json config 2: RWKV-7 0.4B Spark layout, bf16,
+batch 8, seq_len 4096 per GPU (H=16 heads of 64, L=24 layers).
+
+A "step" is one pass of the hot path over one batch: the WKV-7 forward of all 24 layers followed
+by the WKV-7 backward of all 24 layers on [8,4096,16,64] synthetic inputs.
+metric = audio-tokens/s = B*T*n_gpus / step time.  Shards are independent (pure data parallel:
+each rank owns its own batch of 8 sequences, no data-path collective) -> "scaling": "weak".
+
+  python bench.py [--gpus N --steps K --warmup W]          our arm (device-resident `value`, `e2e`
+                                                           through the public API with host buffers)
+  python bench.py --impl reference ...                     the reference algorithm on the host cores
+                                                           (oracle C port, OpenMP), bounded sample
+
+Under torchrun (N > 1) every rank runs its shard; rank 0 prints the single JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, T, H, C, LAYERS = 8, 4096, 16, 64, 24
+FWD_BYTES, BWD_BYTES = 7 * C * 2, 13 * C * 2          # algorithmic bytes per token-head
+METRIC = "audio-tokens/sec (train fwd+bwd) RWKV-7 0.4B seq4096"
+WORKLOAD = "configs[1]: RWKV-7 0.4B Spark-layout bf16, batch 8/GPU, seq_len 4096, WKV-7 fwd+bwd x 24 layers"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(seconds_target=12.0):
+    """The reference algorithm (C port of forward_kernel/backward_kernel) on the host cores, on a
+    bounded sample: one layer-call of [b,4096,16,64]; tokens/s scaled to the 24-layer step."""
+    import torch
+    from oracle import c_oracle as CO
+    from oracle import wkv7_oracle as O
+    CO.build(ref=False)
+    cores = CO.num_threads()
+    b = min(B, max(1, -(-2 * cores // H)))      # at least 2 (b,h) units per thread
+    x = O.make_inputs(b, T, H, seed=42)
+    args = [x[n] for n in "wqkvab"]
+    t0 = time.perf_counter()
+    y, s, sa = CO.c_forward(*args)
+    CO.c_backward(*args, x["dy"], s, sa)
+    dt = time.perf_counter() - t0                       # warm-up + calibration
+    reps = max(1, min(8, int(seconds_target / max(dt, 1e-3))))
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y, s, sa = CO.c_forward(*args)
+        CO.c_backward(*args, x["dy"], s, sa)
+        best = min(best, time.perf_counter() - t0)
+    value = b * T / (best * LAYERS)
+    try:
+        model = [l.split(":")[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        model = "unknown"
+    return {"value": value, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"1 of {LAYERS} layers, batch {b} of {B}, T={T}, H={H}: fwd+bwd best of {reps} "
+                      f"= {best * 1e3:.0f} ms, scaled x{LAYERS} layers; C port of wkv7_cuda.cu "
+                      f"forward_kernel/backward_kernel, OpenMP over (b,h); cpu: {model}"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cb = cpu_reference(seconds_target=20.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": B * T / cb["value"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 in / fp32 state",
+            "data": "synthetic", "config": {"workload": WORKLOAD}, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import rwkvtts_b200 as R
+    from oracle import wkv7_oracle as O          # input generator only (SURVEY 8d recipe)
+    lib = R._lib.lib()
+
+    x = O.make_inputs(B, T, H, seed=42 + rank)
+    d = {n: t.to(dev) for n, t in x.items()}
+    ins = [d[n] for n in "wqkvab"]
+    y = torch.empty_like(d["v"])
+    s = torch.empty(B, H, T // 16, C, C, dtype=torch.float32, device=dev)
+    sa = torch.empty(B, T, H, C, dtype=torch.float32, device=dev)
+    grads = [torch.empty_like(d["v"]) for _ in range(6)]
+
+    def step(ev_mid=None):
+        for _ in range(LAYERS):
+            R.wkv7_forward_(*ins, y, s, sa)
+        if ev_mid is not None:
+            ev_mid.record()
+        for _ in range(LAYERS):
+            R.wkv7_backward_(*ins, d["dy"], s, sa, *grads)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.rwkvtts_kernel_launches()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step(ev[i][1])
+        ev[i][2].record()
+    barrier()
+    launches = lib.rwkvtts_kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0][0].elapsed_time(ev[-1][2])
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / (args.steps * LAYERS)
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / (args.steps * LAYERS)
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = B * T * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API (WindBackstepping autograd op) with pinned HOST buffers --------------
+    host_in = [x[n].pin_memory() for n in "wqkvab"] + [x["dy"].pin_memory()]
+    host_out = [torch.empty_like(x["v"]).pin_memory() for _ in range(7)]
+    h2d = sum(t_.numel() * t_.element_size() for t_ in host_in) * LAYERS
+    d2h = sum(t_.numel() * t_.element_size() for t_ in host_out) * LAYERS
+
+    def e2e_step():
+        for _ in range(LAYERS):
+            dv = [t_.to(dev, non_blocking=True) for t_ in host_in]
+            leaves = [t_.requires_grad_(True) for t_ in dv[:6]]
+            yy = R.WindBackstepping.apply(*leaves)
+            yy.backward(dv[6])
+            host_out[0].copy_(yy.detach(), non_blocking=True)
+            for o, l in zip(host_out[1:], leaves):
+                o.copy_(l.grad, non_blocking=True)
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * T * world / (float(t.item()) / args.e2e_steps * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- reference CUDA op on the same inputs (extra data point; oracle/_ref) --------------------
+    ref_gpu = None
+    if not args.no_ref_gpu:
+        try:
+            from oracle import c_oracle as CO
+            if CO.ref_available():
+                for _ in range(2):
+                    yr, sr, sar = CO.ref_forward(*ins)
+                    CO.ref_backward(*ins, d["dy"], sr, sar)
+                torch.cuda.synchronize()
+                r0, r1, r2 = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                n = 3
+                r0.record()
+                for _ in range(n):
+                    yr, sr, sar = CO.ref_forward(*ins)
+                r1.record()
+                for _ in range(n):
+                    CO.ref_backward(*ins, d["dy"], sr, sar)
+                r2.record()
+                torch.cuda.synchronize()
+                rf, rb = r0.elapsed_time(r1) / n, r1.elapsed_time(r2) / n
+                ref_gpu = {"what": "unmodified reference wind_backstepping kernels (oracle/_ref), same inputs, 1 GPU",
+                           "fwd_ms": rf, "bwd_ms": rb, "tokens_per_s": B * T / ((rf + rb) * LAYERS * 1e-3),
+                           "speedup_fwd": rf / fwd_ms, "speedup_bwd": rb / bwd_ms,
+                           "speedup_step": (rf + rb) / (fwd_ms + bwd_ms)}
+                del yr, sr, sar
+        except Exception as e:                                  # never let the extra leg kill the line
+            ref_gpu = {"error": repr(e)}
+
+    peak, peak_src = peaks()
+    th = B * T * H
+    dom = "bwd" if bwd_ms >= fwd_ms else "fwd"
+    dom_ms, dom_bytes = (bwd_ms, BWD_BYTES) if dom == "bwd" else (fwd_ms, FWD_BYTES)
+    ach = dom_bytes * th / (dom_ms * 1e-3) / 1e9
+    fwd_ach = FWD_BYTES * th / (fwd_ms * 1e-3) / 1e9
+    bwd_ach = BWD_BYTES * th / (bwd_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 in/out, fp32 state", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "B_per_gpu": B, "T": T, "H": H, "head": C, "layers": LAYERS,
+                   "l2": "inputs+outputs of one layer-call are 0.47-0.87 GB, larger than the 126 MB L2; "
+                         "no explicit flush"},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "rwkvtts_b200.WindBackstepping (autograd) with pinned host tensors", "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": f"wkv7 {dom}", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_token_head": dom_bytes, "token_heads_per_launch": th,
+                     "avg_launch_ms": dom_ms},
+        "kernels": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": fwd_ach, "bwd_GBps": bwd_ach,
+                    "fwd_frac": fwd_ach / peak, "bwd_frac": bwd_ach / peak},
+        "ref_gpu_op": ref_gpu,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,109 @@
+/* rwkvtts_wkv7.h -- C ABI of the B200-native WKV-7 hot path (librwkvtts_wkv7.so).
+ *
+ * Drop-in boundary for the native ops of yynil/RWKVTTS (reference paths relative to
+ * /root/reference).  Every entry point is what the reference's torch binding for the path
+ * would call instead of its own launcher:
+ *
+ *   rwkvtts_wkv7_forward        replaces cuda_forward   model/llm/cuda/wkv7_op.cpp:5-10
+ *                                                       (launcher wkv7_cuda.cu:132-134)
+ *   rwkvtts_wkv7_backward       replaces cuda_backward  model/llm/cuda/wkv7_op.cpp:12-19
+ *                                                       (launcher wkv7_cuda.cu:135-138)
+ *   rwkvtts_wkv7_state_forward  replaces cuda_forward   model/llm/cuda/wkv7s_op.cpp:7-11 and
+ *                                                       model/llm/cuda/rwkv7_state_fwd_fp16.cpp:6-10
+ *                                                       (launchers wkv7s.cu:59-64,
+ *                                                        rwkv7_state_fwd_fp16.cu:59-63)
+ *   rwkvtts_wkv7_forward_ex /   the same recurrence with an initial / final state, i.e. the
+ *   rwkvtts_wkv7_backward_ex    rwkvfla call chunk_rwkv7(..., initial_state, output_final_state)
+ *                               that model/llm/spark_llm.py reaches through RWKV7Attention
+ *                               
+ *
+ * Conventions (all from the reference):
+ *   - head size is compile-time 64 (-D_C_=64 / -D_N_=64, rwkv_s2s_single_ffn.py:10-12);
+ *   - w,q,k,v,z,a,y,dy and the six gradients are bf16, contiguous [B,T,H,64]
+ *     ([B,T,H*64] for the stateful op: same memory); argument order at the op boundary is
+ *     (w, q=r, k, v, z=a, a=b) (wkv7_op.cpp:7); `w` is the BlinkDL pre-activation,
+ *     decay = exp(-exp(w));
+ *   - recurrent state is fp32 [B,H,64,64], value-major S[b][h][value][key], updated in place;
+ *   - `s` and `sa` are the caller-allocated scratch tensors of WindBackstepping
+ *     (rwkv_s2s_single_ffn.py:22-25): s  = B*H*(T/16)*64*64 floats, sa = B*T*H*64 floats.
+ *     They are opaque: this library lays its own checkpoints out inside them and only
+ *     requires the reference's sizes (query them with rwkvtts_wkv7_scratch_floats).
+ *   - no allocation, no host synchronisation, no torch types; kernels are enqueued on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream, which is what
+ *     the reference uses, wkv7_cuda.cu:133).
+ *   - return value: 0 on success, a negative RWKVTTS_ERR_* otherwise (the reference aborts
+ *     via assert(), wkv7_cuda.cu:136; the Python mirror turns codes into exceptions).
+ */
+#ifndef RWKVTTS_WKV7_H_
+#define RWKVTTS_WKV7_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RWKVTTS_API __attribute__((visibility("default")))
+#else
+#define RWKVTTS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RWKVTTS_HEAD_SIZE 64
+#define RWKVTTS_CHUNK_LEN 16 /* T must be a multiple of this for the training ops */
+
+enum {
+    RWKVTTS_OK = 0,
+    RWKVTTS_ERR_SHAPE = -1,   /* B,T,H <= 0, T % 16 != 0, C != H*64 */
+    RWKVTTS_ERR_NULL = -2,    /* a required pointer is NULL */
+    RWKVTTS_ERR_ALIGN = -3,   /* a tensor pointer is not 16-byte aligned */
+    RWKVTTS_ERR_CUDA = -4,    /* launch failed; see rwkvtts_last_cuda_error() */
+    RWKVTTS_ERR_DEVICE = -5   /* current device is not sm_100 */
+};
+
+RWKVTTS_API int rwkvtts_version(void);
+RWKVTTS_API const char *rwkvtts_strerror(int code);
+/* cudaError_t of the last failed launch on the calling thread (0 if none). */
+RWKVTTS_API int rwkvtts_last_cuda_error(void);
+
+/* Process-wide count of CUDA kernels this library has launched (evidence for bench.py's
+ * "gpu_launches": every kernel of the path goes through the entry points below). */
+RWKVTTS_API long long rwkvtts_kernel_launches(void);
+
+/* Number of floats the caller must provide for the scratch tensors (reference sizes). */
+RWKVTTS_API size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_floats, size_t *sa_floats);
+
+/* Training forward.  y[b,t,h,:] = S_t q_t, state starts at 0. */
+RWKVTTS_API int rwkvtts_wkv7_forward(int B, int T, int H, const void *w, const void *q, const void *k,
+                         const void *v, const void *z, const void *a, void *y, float *s,
+                         float *sa, void *stream);
+
+/* Training backward: the exact adjoint of rwkvtts_wkv7_forward. */
+RWKVTTS_API int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const void *q, const void *k,
+                          const void *v, const void *z, const void *a, const void *dy,
+                          const float *s, const float *sa, void *dw, void *dq, void *dk,
+                          void *dv, void *dz, void *da, void *stream);
+
+/* Forward / backward with an initial state s0 (may be NULL = zeros) and optional final
+ * state sT / incoming final-state gradient dsT / outgoing initial-state gradient ds0
+ * (each may be NULL).  fp32 [B,H,64,64] value-major. */
+RWKVTTS_API int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, const void *k,
+                            const void *v, const void *z, const void *a, void *y, float *s,
+                            float *sa, const float *s0, float *sT, void *stream);
+RWKVTTS_API int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, const void *k,
+                             const void *v, const void *z, const void *a, const void *dy,
+                             const float *s, const float *sa, const float *s0,
+                             const float *dsT, void *dw, void *dq, void *dk, void *dv,
+                             void *dz, void *da, float *ds0, void *stream);
+
+/* Stateful forward (prefill for T > 1, the per-token decode op for T == 1).
+ * C must equal H*64.  `state` is read, advanced by T steps and written back. */
+RWKVTTS_API int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const void *r,
+                               const void *w, const void *k, const void *v, const void *a,
+                               const void *b, void *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RWKVTTS_WKV7_H_ */

@@ -1,0 +1,58 @@
+"""ctypes binding of librwkvtts_wkv7.so (include/rwkvtts_wkv7.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If the shared object is
+missing or a symbol of the header is absent, importing/calling fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librwkvtts_wkv7.so")
+
+_vp, _i, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+
+# every symbol include/rwkvtts_wkv7.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "rwkvtts_version": (_i, []),
+    "rwkvtts_strerror": (ctypes.c_char_p, [_i]),
+    "rwkvtts_last_cuda_error": (_i, []),
+    "rwkvtts_kernel_launches": (ctypes.c_longlong, []),
+    "rwkvtts_wkv7_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
+                                                      ctypes.POINTER(ctypes.c_size_t)]),
+    "rwkvtts_wkv7_forward": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
+    "rwkvtts_wkv7_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp] + [_vp] * 6 + [_vp]),
+    "rwkvtts_wkv7_forward_ex": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _fp, _fp, _vp]),
+    "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),
+    "rwkvtts_wkv7_state_forward": (_i, [_i, _i, _i, _i, _fp] + [_vp] * 6 + [_vp, _vp]),
+}
+
+_lib = None
+
+
+class RwkvttsError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RwkvttsError(
+                f"{LIB_PATH} not found: the CUDA extension is not built (run `python -m rwkvtts_b200.build`). "
+                "There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        L = lib()
+        msg = L.rwkvtts_strerror(rc).decode()
+        extra = f" (cudaError {L.rwkvtts_last_cuda_error()})" if rc == -4 else ""
+        raise RwkvttsError(f"{what}: {msg}{extra}")

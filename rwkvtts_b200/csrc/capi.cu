@@ -1,0 +1,121 @@
+// extern "C" entry points of librwkvtts_wkv7.so -- see include/rwkvtts_wkv7.h.
+// Argument validation mirrors the reference wrappers' asserts
+// (rwkv_s2s_single_ffn.py:19-21,30-31,52-54; wkv7_cuda.cu:136; wkv7s.cu:61).
+#include "../../include/rwkvtts_wkv7.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+namespace rwkvtts {
+std::atomic<long long> g_kernel_launches{0};
+cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                            const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
+                            float *sT, bool save, cudaStream_t st);
+cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                            const void *a, const void *b, const void *dy, const float *s, const float *sa,
+                            const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
+                            float *ds0, cudaStream_t st);
+}  // namespace rwkvtts
+
+namespace {
+thread_local int g_last_cuda_error = 0;
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_ptrs(std::initializer_list<const void *> ps) {
+    for (const void *p : ps) {
+        if (p == nullptr) return RWKVTTS_ERR_NULL;
+        if (!aligned16(p)) return RWKVTTS_ERR_ALIGN;
+    }
+    return RWKVTTS_OK;
+}
+
+int check_opt(std::initializer_list<const void *> ps) {
+    for (const void *p : ps)
+        if (p != nullptr && !aligned16(p)) return RWKVTTS_ERR_ALIGN;
+    return RWKVTTS_OK;
+}
+
+int finish(cudaError_t e) {
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return RWKVTTS_ERR_CUDA;
+    }
+    return RWKVTTS_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int rwkvtts_version(void) { return 100; }
+
+const char *rwkvtts_strerror(int code) {
+    switch (code) {
+        case RWKVTTS_OK: return "ok";
+        case RWKVTTS_ERR_SHAPE: return "bad shape (B,T,H must be > 0, T % 16 == 0 for training ops, C == H*64)";
+        case RWKVTTS_ERR_NULL: return "required pointer is NULL";
+        case RWKVTTS_ERR_ALIGN: return "tensor pointer is not 16-byte aligned";
+        case RWKVTTS_ERR_CUDA: return "CUDA launch failed (see rwkvtts_last_cuda_error)";
+        case RWKVTTS_ERR_DEVICE: return "current device is not sm_100";
+        default: return "unknown error";
+    }
+}
+
+int rwkvtts_last_cuda_error(void) { return g_last_cuda_error; }
+
+long long rwkvtts_kernel_launches(void) { return rwkvtts::g_kernel_launches.load(); }
+
+size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_floats, size_t *sa_floats) {
+    const size_t s = (size_t)B * H * (T / RWKVTTS_CHUNK_LEN) * RWKVTTS_HEAD_SIZE * RWKVTTS_HEAD_SIZE;
+    const size_t sa = (size_t)B * T * H * RWKVTTS_HEAD_SIZE;
+    if (s_floats) *s_floats = s;
+    if (sa_floats) *sa_floats = sa;
+    return s + sa;
+}
+
+int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                            const void *z, const void *a, void *y, float *s, float *sa, const float *s0,
+                            float *sT, void *stream) {
+    if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
+    if (int rc = check_opt({s0, sT})) return rc;
+    return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,
+                                           (cudaStream_t)stream));
+}
+
+int rwkvtts_wkv7_forward(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                         const void *z, const void *a, void *y, float *s, float *sa, void *stream) {
+    return rwkvtts_wkv7_forward_ex(B, T, H, w, q, k, v, z, a, y, s, sa, nullptr, nullptr, stream);
+}
+
+int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                             const void *z, const void *a, const void *dy, const float *s, const float *sa,
+                             const float *s0, const float *dsT, void *dw, void *dq, void *dk, void *dv,
+                             void *dz, void *da, float *ds0, void *stream) {
+    if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da})) return rc;
+    if (int rc = check_opt({s0, dsT, ds0})) return rc;
+    (void)s0;  // states are rebuilt from the snapshots in `s`; s0 is only part of the signature
+    return finish(rwkvtts::launch_scan_bwd(B, T, H, w, q, k, v, z, a, dy, s, sa, dsT, dw, dq, dk, dv, dz, da,
+                                           ds0, (cudaStream_t)stream));
+}
+
+int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                          const void *z, const void *a, const void *dy, const float *s, const float *sa,
+                          void *dw, void *dq, void *dk, void *dv, void *dz, void *da, void *stream) {
+    return rwkvtts_wkv7_backward_ex(B, T, H, w, q, k, v, z, a, dy, s, sa, nullptr, nullptr, dw, dq, dk, dv, dz,
+                                    da, nullptr, stream);
+}
+
+int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const void *r, const void *w,
+                               const void *k, const void *v, const void *a, const void *b, void *y,
+                               void *stream) {
+    if (B <= 0 || T <= 0 || H <= 0 || C != H * RWKVTTS_HEAD_SIZE) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({state, r, w, k, v, a, b, y})) return rc;
+    // op-boundary order of the scan kernel is (w, q=r, k, v, a, b)
+    return finish(rwkvtts::launch_scan_fwd(B, T, H, w, r, k, v, a, b, y, nullptr, nullptr, state, state, false,
+                                           (cudaStream_t)stream));
+}
+
+}  // extern "C"

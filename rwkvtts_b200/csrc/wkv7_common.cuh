@@ -1,0 +1,49 @@
+// Shared device helpers for the WKV-7 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+namespace rwkvtts {
+
+extern std::atomic<long long> g_kernel_launches;   // defined in capi.cu
+inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+
+constexpr int kC = 64;       // head size (reference: -D_C_=64)
+constexpr int kChunk = 16;   // snapshot spacing of the scan kernels (reference: _CHUNK_LEN_)
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// 8 bf16 (one uint4) -> 8 floats
+__device__ __forceinline__ void unpack8(const uint4 &u, float *f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+    f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+    f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// sum over the 4 lanes that share a row (lane bits 0..1)
+__device__ __forceinline__ float quad_sum(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    return x;
+}
+
+}  // namespace rwkvtts

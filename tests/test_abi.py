@@ -1,0 +1,72 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/rwkvtts_wkv7.h declares; the reference op schemas are registered; nothing falls back to CPU."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from rwkvtts_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built):
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "rwkvtts_wkv7.h")).read()
+    declared = re.findall(r"RWKVTTS_API\s+[\w\s\*]+?\b(rwkvtts_\w+)\s*\(", hdr)
+    assert len(declared) >= 10
+    L = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(L, name), name
+    from rwkvtts_b200 import _lib
+    assert set(declared) == set(_lib.SYMBOLS), set(declared) ^ set(_lib.SYMBOLS)
+    assert _lib.lib().rwkvtts_version() >= 100
+
+
+def test_argument_validation_without_gpu(built):
+    """Shape / pointer checks happen before any CUDA call, so they run on a CPU box."""
+    from rwkvtts_b200 import _lib
+    L = _lib.lib()
+    buf = torch.zeros(1 << 16, dtype=torch.float32)
+    p = buf.data_ptr()
+    ps = [p] * 6
+    assert L.rwkvtts_wkv7_forward(1, 15, 1, *ps, p, p, p, None) == -1          # T % 16 != 0
+    assert L.rwkvtts_wkv7_forward(0, 16, 1, *ps, p, p, p, None) == -1
+    assert L.rwkvtts_wkv7_forward(1, 16, 1, None, *ps[1:], p, p, p, None) == -2
+    assert L.rwkvtts_wkv7_forward(1, 16, 1, p + 2, *ps[1:], p, p, p, None) == -3
+    assert L.rwkvtts_wkv7_state_forward(1, 1, 100, 2, p, *ps, p, None) == -1   # C != H*64
+    assert b"16" in L.rwkvtts_strerror(-1)
+    s = torch.zeros(2, dtype=torch.int64)
+    import ctypes
+    a, b = ctypes.c_size_t(), ctypes.c_size_t()
+    tot = L.rwkvtts_wkv7_scratch_floats(8, 4096, 16, ctypes.byref(a), ctypes.byref(b))
+    assert a.value == 8 * 16 * 256 * 64 * 64 and b.value == 8 * 4096 * 16 * 64 and tot == a.value + b.value
+
+
+def test_reference_schemas_registered_and_no_cpu_fallback(built):
+    import rwkvtts_b200 as R
+    s = str(torch.ops.wind_backstepping.forward.default._schema)
+    assert "Tensor(a!) y" in s and "Tensor(c!) sa" in s
+    assert "Tensor(f!) da" in str(torch.ops.wind_backstepping.backward.default._schema)
+    for ns in ("wkv7s", "rwkv7_state_fwd_fp16"):
+        assert "int B, int T, int C, int H" in str(getattr(torch.ops, ns).forward.default._schema)
+    x = torch.zeros(1, 16, 64, dtype=torch.bfloat16)
+    with pytest.raises((NotImplementedError, R._lib.RwkvttsError)):
+        R.RUN_CUDA_RWKV7g(x, x, x, x, x, x)
+    with pytest.raises(R._lib.RwkvttsError):
+        R.wkv7_state_forward_(1, 16, 64, 1, torch.zeros(1, 64, 64), x, x, x, x, x, x, x.clone())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "rwkvtts_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "liboracle" not in src and "oracle/" not in src, f
