@@ -144,10 +144,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     import rwkvtts_b200 as R
-    from oracle import wkv7_oracle as O          # input generator only (SURVEY 8d recipe)
+    from rwkvtts_b200.synth import make_inputs
     lib = R._lib.lib()
 
-    x = O.make_inputs(B, T, H, seed=42 + rank)
+    x = make_inputs(B, T, H, seed=42 + rank)
     d = {n: t.to(dev) for n, t in x.items()}
     ins = [d[n] for n in "wqkvab"]
     y = torch.empty_like(d["v"])
