@@ -67,6 +67,12 @@ RWKVTTS_API const char *rwkvtts_strerror(int code);
 /* cudaError_t of the last failed launch on the calling thread (0 if none). */
 RWKVTTS_API int rwkvtts_last_cuda_error(void);
 
+/* Kernel family of the training ops: 0 = sequential scan on CUDA cores, 1 = chunked tensor-core
+ * kernels.  Forward and backward of one autograd node must run under the same setting (the
+ * layout inside `s`/`sa` differs).  Initial value from env RWKVTTS_WKV7_IMPL ("scan"/"chunk"). */
+RWKVTTS_API int rwkvtts_set_impl(int impl);
+RWKVTTS_API int rwkvtts_get_impl(void);
+
 /* Process-wide count of CUDA kernels this library has launched (evidence for bench.py's
  * "gpu_launches": every kernel of the path goes through the entry points below). */
 RWKVTTS_API long long rwkvtts_kernel_launches(void);

@@ -19,6 +19,8 @@ SYMBOLS = {
     "rwkvtts_strerror": (ctypes.c_char_p, [_i]),
     "rwkvtts_last_cuda_error": (_i, []),
     "rwkvtts_kernel_launches": (ctypes.c_longlong, []),
+    "rwkvtts_set_impl": (_i, [_i]),
+    "rwkvtts_get_impl": (_i, []),
     "rwkvtts_wkv7_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
                                                       ctypes.POINTER(ctypes.c_size_t)]),
     "rwkvtts_wkv7_forward": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),

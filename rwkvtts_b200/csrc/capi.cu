@@ -6,12 +6,16 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstdlib>
 
 namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
 cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
                             float *sT, bool save, cudaStream_t st);
+cudaError_t launch_chunk_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                             const void *a, const void *b, void *y, float *s, const float *s0, float *sT,
+                             cudaStream_t st);
 cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, const void *dy, const float *s, const float *sa,
                             const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
@@ -20,6 +24,16 @@ cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, c
 
 namespace {
 thread_local int g_last_cuda_error = 0;
+
+// Kernel family used by the training ops.  Forward and backward must use the same family because
+// the layout of the scratch tensor `s` differs (scan: state at chunk ends + `sa`; chunk: state at
+// chunk starts).  0 = sequential scan (CUDA cores), 1 = chunked tensor-core kernels.
+int initial_impl() {
+    const char *e = getenv("RWKVTTS_WKV7_IMPL");
+    if (e != nullptr && e[0] == 'c') return 1;
+    return 0;
+}
+std::atomic<int> g_impl{initial_impl()};
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -64,6 +78,13 @@ const char *rwkvtts_strerror(int code) {
 
 int rwkvtts_last_cuda_error(void) { return g_last_cuda_error; }
 
+int rwkvtts_set_impl(int impl) {
+    if (impl != 0 && impl != 1) return RWKVTTS_ERR_SHAPE;
+    g_impl.store(impl);
+    return RWKVTTS_OK;
+}
+int rwkvtts_get_impl(void) { return g_impl.load(); }
+
 long long rwkvtts_kernel_launches(void) { return rwkvtts::g_kernel_launches.load(); }
 
 size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_floats, size_t *sa_floats) {
@@ -80,6 +101,8 @@ int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, c
     if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
+    if (g_impl.load() == 1)
+        return finish(rwkvtts::launch_chunk_fwd(B, T, H, w, q, k, v, z, a, y, s, s0, sT, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,
                                            (cudaStream_t)stream));
 }

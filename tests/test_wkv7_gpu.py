@@ -163,3 +163,36 @@ def test_full_size_properties(R):
     sl = lambda t: t[3:4, :, 5:6].contiguous()
     y64, _ = O.wkv7_forward(*[sl(x[n]) for n in ORDER])
     _check("y[3,:,5]", sl(y.cpu()), y64)
+
+
+# ---------------------------------------------------------------------------------------------
+# chunked tensor-core kernels (impl 1)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture
+def chunk_impl(R):
+    L = R._lib.lib()
+    prev = L.rwkvtts_get_impl()
+    assert L.rwkvtts_set_impl(1) == 0
+    yield R
+    L.rwkvtts_set_impl(prev)
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 16, 1), (2, 512, 12), (3, 80, 2), (1, 1024, 4)])
+def test_chunk_forward_vs_oracle(chunk_impl, B, T, H):
+    R = chunk_impl
+    x = O.make_inputs(B, T, H, seed=B * 1000 + T)
+    d = _dev(x)
+    s0 = torch.randn(B, H, 64, 64) * 0.1 if T == 80 else None
+    y = torch.empty_like(d["v"])
+    s = torch.zeros(B, H, T // 16, 64, 64, device="cuda")
+    sa = torch.empty(B, T, H, 64, device="cuda")
+    sT = torch.empty(B, H, 64, 64, device="cuda")
+    R.wkv7_forward_(*[d[n] for n in ORDER], y, s, sa, s0=None if s0 is None else s0.cuda(), sT=sT)
+    torch.cuda.synchronize()
+    y64, sT64, states = O.wkv7_forward(*[x[n] for n in ORDER], s0=s0, return_states=True)
+    exc = _check("y", y, y64)
+    print(f"chunk fwd B{B} T{T} H{H}: excess {exc:.2e}")
+    assert O.rel_l2(sT, sT64) < 1e-3
+    # checkpoints: state at the START of every 16-token chunk, value-major
+    ck = states[:, 0:T:16].permute(0, 2, 1, 3, 4)          # [B,H,T/16,64,64]
+    assert O.rel_l2(s, ck) < 1e-3
