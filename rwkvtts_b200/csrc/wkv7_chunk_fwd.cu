@@ -50,7 +50,16 @@ struct Params {
     float *s;            // chunk-start states [B*H][T/16][64][64]
     const float *s0;     // may be null
     float *sT;           // may be null
+    long long *dbg;      // phase-cycle counters (profiling builds only), may be null
 };
+
+#ifdef RWKVTTS_PROFILE
+#define TICK(var) long long var = clock64()
+#define ACC(slot, t0, t1) do { if (P.dbg && blockIdx.x == 0 && (threadIdx.x & 127) == 0) P.dbg[slot] += (t1) - (t0); } while (0)
+#else
+#define TICK(var)
+#define ACC(slot, t0, t1)
+#endif
 
 __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
@@ -74,6 +83,7 @@ __device__ __forceinline__ void prep_load(const Params &P, size_t base, size_t t
 __device__ __forceinline__ void prep_chunk(const Params &P, Smem &sm, Stage &S, size_t base, size_t tok_stride,
                                            int c, int nC, int tp, uint4 (&raw)[6]) {
     const int t = tp >> 3, kg = tp & 7, wp = tp >> 5, lane = tp & 31, g = lane >> 2, tq = lane & 3;
+    TICK(tp0);
     // ---- P0: decay scan + scaling ---------------------------------------------------------
     float lw[8], gg[8];
     {
@@ -133,6 +143,7 @@ __device__ __forceinline__ void prep_chunk(const Params &P, Smem &sm, Stage &S, 
     }
     if (c + 1 < nC) prep_load(P, base, tok_stride, c + 1, tp, raw);   // in flight during P1/P2
     bar_sync(1, 128);
+    TICK(tp1); ACC(0, tp0, tp1);
     // ---- P1: Gram blocks, one 16x16 block per warp ------------------------------------------
     {
         const int rowsel = wp & 1, colsel = wp >> 1;
@@ -169,6 +180,7 @@ __device__ __forceinline__ void prep_chunk(const Params &P, Smem &sm, Stage &S, 
             }
     }
     bar_sync(1, 128);
+    TICK(tp2); ACC(1, tp1, tp2);
     // ---- P2: [M1 | W] = (I - N)^-1 [Aak | A~], one column per thread --------------------------
     if (tp < 16 + kC) {
         const int col = tp;
@@ -200,6 +212,7 @@ __device__ __forceinline__ void prep_chunk(const Params &P, Smem &sm, Stage &S, 
             for (int tt = 0; tt < L; tt++) S.W[tt * LD8 + col - 16] = tf32r(X[tt]);
         }
     }
+    TICK(tp3); ACC(2, tp2, tp3);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -209,6 +222,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
                                             size_t base, size_t tok_stride, int bh, int c, int nC, int tid) {
     const int wv = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
     const int r0 = 16 * wv + g;
+    TICK(ts0);
     {   // state at the start of this chunk -> checkpoint for the backward kernel
         float *ck = P.s + ((size_t)bh * nC + c) * (kC * kC);
 #pragma unroll
@@ -217,6 +231,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
             *reinterpret_cast<float2 *>(ck + (r0 + 8) * kC + 8 * nt + 2 * tq) = make_float2(Sacc[nt][2], Sacc[nt][3]);
         }
     }
+    TICK(ts1); ACC(4, ts0, ts1);
     float Uacc[2][4] = {}, Yacc[2][4] = {};
     // U^T = S W^T,  Y^T = S Q~^T        (A = S from the accumulators, k = key, permuted order)
 #pragma unroll
@@ -231,6 +246,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
             mma_tf32(Yacc[nt], af, bfr);
         }
     }
+    TICK(ts2); ACC(5, ts1, ts2);
     // + V^T M1^T, + V^T Aqk^T           (A[m=value][k=token] = V[token][value], permuted k)
     uint32_t Va[2][4];
 #pragma unroll
@@ -257,6 +273,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
             ldb_perm_k1(bfr, S.Aqb, LS, 8 * j, 8 * nt, g, tq);
             mma_tf32(Yacc[nt], Ua[j], bfr);
         }
+    TICK(ts3); ACC(6, ts2, ts3);
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
 #pragma unroll
@@ -272,6 +289,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
         const float2 d = *reinterpret_cast<const float2 *>(&S.DL[8 * nt + 2 * tq]);
         Sacc[nt][0] *= d.x; Sacc[nt][1] *= d.y; Sacc[nt][2] *= d.x; Sacc[nt][3] *= d.y;
     }
+    TICK(ts4); ACC(7, ts3, ts4);
     // y: transpose through shared memory, then 128-byte rows to HBM
 #pragma unroll
     for (int nt = 0; nt < 2; nt++)
@@ -286,6 +304,7 @@ __device__ __forceinline__ void state_chunk(const Params &P, Smem &sm, const Sta
         const uint4 v = *reinterpret_cast<const uint4 *>(&sm.y[tok][part * 8]);
         *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
     }
+    TICK(ts5); ACC(8, ts4, ts5);
 }
 
 __global__ void __launch_bounds__(256) wkv7_chunk_fwd_kernel(const Params P) {
@@ -320,12 +339,15 @@ __global__ void __launch_bounds__(256) wkv7_chunk_fwd_kernel(const Params P) {
     }
     __syncthreads();
     for (int c = 0; c < nC; c++) {
+        TICK(tl0);
         if (is_prep) {
             if (c + 1 < nC) prep_chunk(P, sm, sm.st[(c + 1) & 1], base, tok_stride, c + 1, nC, tid - 128, raw);
         } else {
             state_chunk(P, sm, sm.st[c & 1], Sacc, base, tok_stride, bh, c, nC, tid);
         }
+        TICK(tl1);
         __syncthreads();
+        TICK(tl2); ACC(is_prep ? 10 : 12, tl0, tl1); ACC(is_prep ? 11 : 13, tl1, tl2);
     }
     if (!is_prep && P.sT != nullptr) {
         const int wv = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3, r0 = 16 * wv + g;
@@ -340,6 +362,8 @@ __global__ void __launch_bounds__(256) wkv7_chunk_fwd_kernel(const Params P) {
 
 }  // namespace chunkfwd
 
+long long *g_dbg = nullptr;   // set by the profiling harness only
+
 cudaError_t launch_chunk_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                              const void *a, const void *b, void *y, float *s, const float *s0, float *sT,
                              cudaStream_t st) {
@@ -348,7 +372,7 @@ cudaError_t launch_chunk_fwd(int B, int T, int H, const void *w, const void *q, 
                                          (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
-             (const bf16 *)b, (bf16 *)y, s, s0, sT};
+             (const bf16 *)b, (bf16 *)y, s, s0, sT, g_dbg};
     count_launch();
     wkv7_chunk_fwd_kernel<<<dim3(B * H), dim3(256), sizeof(Smem), st>>>(P);
     return cudaGetLastError();
