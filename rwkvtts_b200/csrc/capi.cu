@@ -16,6 +16,9 @@ cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, c
 cudaError_t launch_chunk_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                              const void *a, const void *b, void *y, float *s, const float *s0, float *sT,
                              cudaStream_t st);
+cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                          const void *a, const void *b, void *y, float *ckpt, const float *s0, float *sT,
+                          cudaStream_t st);
 cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, const void *dy, const float *s, const float *sa,
                             const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
@@ -31,6 +34,7 @@ thread_local int g_last_cuda_error = 0;
 int initial_impl() {
     const char *e = getenv("RWKVTTS_WKV7_IMPL");
     if (e != nullptr && e[0] == 'c') return 1;
+    if (e != nullptr && e[0] == 't') return 2;
     return 0;
 }
 std::atomic<int> g_impl{initial_impl()};
@@ -79,7 +83,7 @@ const char *rwkvtts_strerror(int code) {
 int rwkvtts_last_cuda_error(void) { return g_last_cuda_error; }
 
 int rwkvtts_set_impl(int impl) {
-    if (impl != 0 && impl != 1) return RWKVTTS_ERR_SHAPE;
+    if (impl < 0 || impl > 2) return RWKVTTS_ERR_SHAPE;
     g_impl.store(impl);
     return RWKVTTS_OK;
 }
@@ -101,6 +105,8 @@ int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, c
     if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
+    if (g_impl.load() == 2)
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, s, s0, sT, (cudaStream_t)stream));
     if (g_impl.load() == 1)
         return finish(rwkvtts::launch_chunk_fwd(B, T, H, w, q, k, v, z, a, y, s, s0, sT, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,

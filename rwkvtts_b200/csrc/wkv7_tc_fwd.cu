@@ -1,0 +1,525 @@
+// WKV-7 training forward for sm_100a: chunked DPLR form on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators and the recurrent state in tensor memory).
+//
+// Reference operator: model/llm/cuda/wkv7_cuda.cu:17-42 (forward_kernel); same recurrence, evaluated
+// 16 tokens (one chunk) at a time.  S is the value-major state [64 values][64 keys].
+//
+// Frames.  Tokens are grouped in windows of 64 (4 chunks).  Inside a window every vector is scaled
+// by the decay accumulated since the window start, G_t = sum_{s<=t} log d_s (G < 0):
+//     Q~ = q e^{G_t}    A~ = a e^{G_{t-1}}    K~ = k e^{-G_t}    B~ = b e^{-G_t}
+// and the state is kept as S^ = S diag(e^{-G}) so that inside a window it is only ACCUMULATED:
+//     per chunk c:  N = stril(A~ B~^T)  Aak = stril(A~ K~^T)  Aqb = tril(Q~ B~^T)  Aqk = tril(Q~ K~^T)
+//                   T = (I - N)^-1,  W~ = T A~,  M1 = T Aak                          (CUDA cores / mma.sync)
+//         phase 1:  [U^T | Y^T] = S^ [W~ | Q~]^T + V^T [M1 | Aqk]^T                  (tcgen05, N = 32)
+//         phase 2:  S^ += U^T B~ + V^T K~ ;   Y^T += U^T Aqb^T                       (tcgen05, N = 64 / 16)
+// (U_t = S_{t-1} a_t is the reference's `sa`).  At a window end S^ is multiplied by e^{G_64}
+// (tensor memory -> registers -> tensor memory) and written to the checkpoint tensor for the
+// backward kernel.  |G| <= 64 * 1.35 stays inside the fp32 exponent range; log-decays below -1.35
+// per step (decay < 0.26; the model's range is (-0.6065, 0), rwkv_s2s_single_ffn.py:172) are clamped.
+//
+// tcgen05 facts this kernel relies on (measured with tests/csrc/umma_probe.cu on a B200):
+//   * M = 64 accumulators put row 16q+i in lane 32q+i; an M = 64 A operand in tensor memory uses the
+//     same lanes, so an accumulator (S^, U^T) is directly the A operand of the next product;
+//   * an MMA that reads tensor memory written by an MMA with a DIFFERENT accumulator is not ordered
+//     behind it: every phase boundary is a tcgen05.commit + mbarrier wait (~170 cycles);
+//   * tf32 operands in shared memory must be K-major (no-swizzle canonical layout, tc05.cuh).
+//
+// One CTA per (batch, head), 21 warps:
+//   warps  0-3   epilogue: Y^T tensor memory -> bf16 -> HBM, window-end rescale, checkpoints, s0 / sT
+//   warps  4-11  stage A: HBM loads, decay scan, scaled operands (natural + canonical layouts)
+//   warps 12-15  stage B (even chunks), warps 16-19 stage B (odd chunks): Gram blocks (mma.sync tf32),
+//                triangular solve, W~ / M1 / Aqk / Aqb into the canonical operand slot
+//   warp   20    MMA issuer (one elected lane), owns the tensor-memory allocation
+// All hand-offs are mbarriers; the operand slots form a ring of NSLOT chunks.
+#include "mma_tf32.cuh"
+#include "tc05.cuh"
+#include "wkv7_common.cuh"
+
+namespace rwkvtts {
+namespace tcfwd {
+using namespace tc05;
+
+constexpr int L = 16;        // chunk length
+constexpr int WIN = 4;       // chunks per window
+constexpr int NSLOT = 6;     // operand slots in flight
+constexpr int NNAT = 3;      // stage A -> stage B hand-off buffers
+constexpr int LDN = 68;      // row stride of the natural [token][channel] tiles
+constexpr float kMinLogDecay = -1.35f;
+
+// canonical K-major tiles, strides in floats (see tc05.cuh: off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4)
+constexpr int WQ_LBO = 132, WQ_SBO = 32;     // [32 rows: 0-15 W~ tokens, 16-31 Q~ tokens][64 channels]
+constexpr int T_SBO = 36, T_LBO = 288;       // [64 rows: channel / value][16 tokens]   (transposed tiles)
+constexpr int MA_LBO = 128, MA_SBO = 32;     // [32 rows: 0-15 M1, 16-31 Aqk][16]
+constexpr int QB_LBO = 64, QB_SBO = 32;      // [16][16]
+
+struct Slot {
+    float WQ[16 * WQ_LBO];
+    float Bt[4 * T_LBO], Kt[4 * T_LBO], Vt[4 * T_LBO];
+    float MA[4 * MA_LBO];
+    float Aqb[4 * QB_LBO];
+};
+struct Nat {
+    float At[L * LDN], Bn[L * LDN], Kn[L * LDN], Qn[L * LDN];
+};
+struct Smem {
+    Slot slot[NSLOT];
+    Nat nat[NNAT];
+    float NT[2][L * 20], Aak[2][L * 20];   // per stage-B group: N^T and Aak, fp32
+    float wtot[2][8][kC];                  // stage A scan partials, double buffered
+    __align__(16) bf16 ybuf[2][L][72];     // epilogue: Y tile [token][value], double buffered
+    float DLw[4][kC];                      // e^{G} at the end of a window (ring of 4 windows)
+    uint64_t empty[NSLOT], full[NSLOT], a_done[NNAT], nat_empty[NNAT];
+    uint64_t p_done, y_ready[2], y_free[2], win_scaled;
+    uint32_t tmem_base;
+};
+
+struct Params {
+    int T, H;
+    const bf16 *w, *q, *k, *v, *a, *b;
+    bf16 *y;
+    float *ckpt;         // state at the start of every window, [B*H][ceil(T/64)][64][64]
+    const float *s0;     // may be null
+    float *sT;           // may be null
+    long long *dbg;      // phase-cycle counters (profiling builds only), may be null
+};
+
+#ifdef RWKVTTS_PROFILE
+#define TICK(var) long long var = clock64()
+#define ACC(slot, t0, t1) do { if (P_dbg && blockIdx.x == 0) P_dbg[slot] += (t1) - (t0); } while (0)
+#else
+#define TICK(var)
+#define ACC(slot, t0, t1)
+#endif
+
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage A: tp in [0,256); token t = tp>>4, channels 4*k4 .. 4*k4+3; warp wp holds tokens 2wp, 2wp+1
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+}
+__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int tp,
+                                         uint2 (&raw)[6]) {
+    const int t = tp >> 4, k4 = tp & 15;
+    const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
+    raw[0] = ldg_nc_v2(P.w + off);
+    raw[1] = ldg_nc_v2(P.q + off);
+    raw[2] = ldg_nc_v2(P.k + off);
+    raw[3] = ldg_nc_v2(P.v + off);
+    raw[4] = ldg_nc_v2(P.a + off);
+    raw[5] = ldg_nc_v2(P.b + off);
+}
+
+__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int nC, int tp) {
+    long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
+    const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
+    uint2 raw[6], nxt[6], nx2[6];
+    float gpre[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) gpre[j] = 0.f;
+    load_raw(P, base, tok_stride, 0, tp, raw);
+    if (nC > 1) load_raw(P, base, tok_stride, 1, tp, nxt);
+    for (int c = 0; c < nC; c++) {
+        const int si = c % NSLOT, ni = c % NNAT;
+        Slot &S = sm.slot[si];
+        Nat &N = sm.nat[ni];
+        if (c + 2 < nC) load_raw(P, base, tok_stride, c + 2, tp, nx2);   // two chunks ahead
+        float lw[4], gg[4];
+        TICK(ta0);
+        {
+            float f[4];
+            unpack4(raw[0], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay); gg[j] = lw[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {   // inclusive scan over the 2 tokens of this warp (lane = (t&1)*16 + k4)
+            const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
+            if (t & 1) gg[j] += x;
+        }
+        float(&wt)[8][kC] = sm.wtot[c & 1];
+        if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
+        bar_sync(1, 256);
+        float tot[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { gg[j] += gpre[j]; tot[j] = gpre[j]; }
+#pragma unroll
+        for (int ww = 0; ww < 8; ww++) {
+            const float4 x0 = *reinterpret_cast<const float4 *>(&wt[ww][k4 * 4]);
+            const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                tot[j] += xs[j];
+                if (ww < wp) gg[j] += xs[j];
+            }
+        }
+        const bool win_end = (c % WIN == WIN - 1) || (c == nC - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) gpre[j] = win_end ? 0.f : tot[j];
+
+        // wait until the slot / hand-off buffer of this chunk have been released
+        TICK(ta1);
+        if (c >= NSLOT) mbar_wait(&sm.empty[si], ((c / NSLOT) - 1) & 1);
+        TICK(ta2);
+        if (c >= NNAT) mbar_wait(&sm.nat_empty[ni], ((c / NNAT) - 1) & 1);
+        TICK(ta3);
+        {
+            float D[4], Dp[4], iD[4], f[4], o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                D[j] = __expf(gg[j]);
+                Dp[j] = __expf(gg[j] - lw[j]);
+                iD[j] = __expf(-gg[j]);
+            }
+            const int on = t * LDN + k4 * 4;
+            // Q~: natural + canonical rows 16..31 of WQ
+            unpack4(raw[1], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = tf32r(f[j] * D[j]);
+            st4(&N.Qn[on], o[0], o[1], o[2], o[3]);
+            {
+                const int r = 16 + t;
+                st4(&S.WQ[(r >> 3) * WQ_SBO + k4 * WQ_LBO + (r & 7) * 4], o[0], o[1], o[2], o[3]);
+            }
+            // transposed tiles: row = channel 4*k4+j, column = token t
+            const int ot = (k4 >> 1) * T_SBO + (t >> 2) * T_LBO + (k4 & 1) * 16 + (t & 3);   // + 4*j
+            // K~
+            unpack4(raw[2], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = tf32r(f[j] * iD[j]);
+            st4(&N.Kn[on], o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Kt[ot + 4 * j] = o[j];
+            // V (bf16 values are exact in tf32)
+            unpack4(raw[3], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Vt[ot + 4 * j] = f[j];
+            // A~
+            unpack4(raw[4], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = tf32r(f[j] * Dp[j]);
+            st4(&N.At[on], o[0], o[1], o[2], o[3]);
+            // B~
+            unpack4(raw[5], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) o[j] = tf32r(f[j] * iD[j]);
+            st4(&N.Bn[on], o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Bt[ot + 4 * j] = o[j];
+            if (win_end && t == L - 1) st4(&sm.DLw[(c / WIN) & 3][k4 * 4], D[0], D[1], D[2], D[3]);
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.a_done[ni]);
+#pragma unroll
+        for (int i = 0; i < 6; i++) { raw[i] = nxt[i]; nxt[i] = nx2[i]; }
+        TICK(ta4); ACC(0, ta0, ta1); ACC(1, ta1, ta2); ACC(2, ta2, ta3); ACC(3, ta3, ta4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage B: tp in [0,128), group grp (0: even chunks, 1: odd chunks)
+// ---------------------------------------------------------------------------------------------
+__device__ void stage_b(const Params &P, Smem &sm, int nC, int tp, int grp) {
+    long long *P_dbg = (grp == 0 && tp == 0) ? P.dbg : nullptr; (void)P_dbg;
+    const int wp = tp >> 5, lane = tp & 31, g = lane >> 2, tq = lane & 3;
+    float *NT = sm.NT[grp], *AK = sm.Aak[grp];
+    for (int c = grp; c < nC; c += 2) {
+        const int si = c % NSLOT, ni = c % NNAT;
+        Slot &S = sm.slot[si];
+        const Nat &N = sm.nat[ni];
+        TICK(tb0);
+        mbar_wait(&sm.a_done[ni], (c / NNAT) & 1);
+        TICK(tb1);
+        // ---- Gram blocks, one 16x16 block per warp ------------------------------------------
+        {
+            const int rowsel = wp & 1, colsel = wp >> 1;
+            const float *Ar = rowsel ? N.Qn : N.At;
+            const float *Bc = colsel ? N.Kn : N.Bn;
+            float acc[2][4] = {};
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                uint32_t af[4], bfr[2];
+                lda(af, Ar, LDN, 1, 0, 8 * kb, g, tq);
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    ldb(bfr, Bc, 1, LDN, 8 * kb, 8 * nt, g, tq);
+                    mma_tf32(acc[nt], af, bfr);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int col = 8 * nt + 2 * tq + e;      // s
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int row = g + 8 * hh;           // t
+                        float x = acc[nt][2 * hh + e];
+                        if (rowsel) {   // Q~ rows: inclusive lower triangle, tensor-core operand
+                            x = (col <= row) ? tf32r(x) : 0.f;
+                            if (colsel) S.MA[kmajor_off(16 + row, col, MA_LBO, MA_SBO)] = x;
+                            else S.Aqb[kmajor_off(row, col, QB_LBO, QB_SBO)] = x;
+                        } else {        // A~ rows: strict lower triangle, fp32 for the solve
+                            x = (col < row) ? x : 0.f;
+                            if (colsel) AK[row * 20 + col] = x;
+                            else NT[col * 20 + row] = x;
+                        }
+                    }
+                }
+        }
+        bar_sync(2 + grp, 128);
+        TICK(tb2);
+        // ---- [M1 | W~] = (I - N)^-1 [Aak | A~], one column per thread, column-oriented ----------
+        if (tp < 16 + kC) {
+            const int col = tp;
+            float acc[L];
+#pragma unroll
+            for (int tt = 0; tt < L; tt++) acc[tt] = (col < 16) ? AK[tt * 20 + col] : N.At[tt * LDN + col - 16];
+#pragma unroll
+            for (int s = 0; s < L - 1; s++) {
+                const float x = acc[s];
+#pragma unroll
+                for (int q4 = (s + 1) / 4; q4 < 4; q4++) {
+                    const float4 n4 = *reinterpret_cast<const float4 *>(&NT[s * 20 + 4 * q4]);
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (4 * q4 + e > s) acc[4 * q4 + e] = fmaf(nn[e], x, acc[4 * q4 + e]);
+                }
+            }
+            if (col < 16) {
+#pragma unroll
+                for (int tt = 0; tt < L; tt++) S.MA[kmajor_off(tt, col, MA_LBO, MA_SBO)] = tf32r(acc[tt]);
+            } else {
+#pragma unroll
+                for (int tt = 0; tt < L; tt++) S.WQ[kmajor_off(tt, col - 16, WQ_LBO, WQ_SBO)] = tf32r(acc[tt]);
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.full[si]);
+        mbar_arrive(&sm.nat_empty[ni]);
+        TICK(tb3);
+        bar_sync(2 + grp, 128);     // NT / Aak are reused by the next chunk of this group
+        TICK(tb4); ACC(4, tb0, tb1); ACC(5, tb1, tb2); ACC(6, tb2, tb3); ACC(7, tb3, tb4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MMA issuer (one warp)
+// ---------------------------------------------------------------------------------------------
+__device__ void mma_warp(const Params &P, Smem &sm, int nC) {
+    long long *P_dbg = (threadIdx.x & 31) == 0 ? P.dbg : nullptr; (void)P_dbg;
+    const uint32_t tb = sm.tmem_base;
+    constexpr uint32_t I16 = idesc_tf32(64, 16, false, false);
+    constexpr uint32_t I32 = idesc_tf32(64, 32, false, false);
+    constexpr uint32_t I64 = idesc_tf32(64, 64, false, false);
+    uint32_t ph = 0;
+    for (int c = 0; c < nC; c++) {
+        const int si = c % NSLOT, u = c & 1;
+        const Slot &S = sm.slot[si];
+        const uint32_t uy = tb + 64 + 32 * u;
+        const uint64_t dWQ = smem_desc(smem_u32(S.WQ), WQ_LBO * 4, WQ_SBO * 4);
+        const uint64_t dVt = smem_desc(smem_u32(S.Vt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dBt = smem_desc(smem_u32(S.Bt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dKt = smem_desc(smem_u32(S.Kt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dMA = smem_desc(smem_u32(S.MA), MA_LBO * 4, MA_SBO * 4);
+        const uint64_t dQB = smem_desc(smem_u32(S.Aqb), QB_LBO * 4, QB_SBO * 4);
+        TICK(tm0);
+        mbar_wait(&sm.full[si], (c / NSLOT) & 1);
+        TICK(tm1);
+        if (c % WIN == 0) mbar_wait(&sm.win_scaled, (c / WIN) & 1);
+        TICK(tm2);
+        if (c >= 2) mbar_wait(&sm.y_free[u], ((c >> 1) - 1) & 1);
+        TICK(tm3);
+        fence_after_sync();
+        if (elect_one()) {
+            // phase 1: [U^T | Y^T] = S^ [W~ | Q~]^T + V^T [M1 | Aqk]^T
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+                mma_tf32_ts(uy, tb + 8 * kk, dWQ + (uint64_t)((kk * 2 * WQ_LBO * 4) >> 4), I32, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(uy, dVt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), dMA + (uint64_t)((kk * 2 * MA_LBO * 4) >> 4),
+                            I32, true);
+            mma_commit(&sm.p_done);
+        }
+        __syncwarp();
+        mbar_wait(&sm.p_done, ph); ph ^= 1;
+        TICK(tm4);
+        fence_after_sync();
+        if (elect_one()) {
+            // phase 2: S^ += U^T B~ + V^T K~ ;  Y^T += U^T Aqb^T
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ts(tb, uy + 8 * kk, dBt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), I64, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb, dVt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), dKt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4),
+                            I64, true);
+            mma_commit(&sm.p_done);       // the chain only needs S^
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ts(uy + 16, uy + 8 * kk, dQB + (uint64_t)((kk * 2 * QB_LBO * 4) >> 4), I16, true);
+            mma_commit(&sm.empty[si]);
+            mma_commit(&sm.y_ready[u]);
+        }
+        __syncwarp();
+        mbar_wait(&sm.p_done, ph); ph ^= 1;
+        TICK(tm5); ACC(8, tm0, tm1); ACC(9, tm1, tm2); ACC(10, tm2, tm3); ACC(11, tm3, tm4); ACC(12, tm4, tm5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = value rows 16q..16q+15
+// ---------------------------------------------------------------------------------------------
+__device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+    long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
+    const int q = tid >> 5, lane = tid & 31;
+    const bool act = lane < 16;
+    const int row = 16 * q + (lane & 15);
+    const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
+    const int nW = (nC + WIN - 1) / WIN;
+    float *ck = P.ckpt + (size_t)bh * nW * (kC * kC);
+    {   // initial state -> tensor memory and checkpoint 0
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) v[i] = 0.f;
+            if (P.s0 != nullptr) {
+                const float4 *sp = reinterpret_cast<const float4 *>(P.s0 + (size_t)bh * kC * kC + row * kC + 16 * cb);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 x = sp[i];
+                    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+                }
+            }
+            tmem_st16(tb + 16 * cb, v);
+            if (act) {
+                float4 *dp = reinterpret_cast<float4 *>(ck + row * kC + 16 * cb);
+#pragma unroll
+                for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        mbar_arrive(&sm.win_scaled);
+    }
+    for (int c = 0; c < nC; c++) {
+        const int u = c & 1;
+        const bool win_end = (c % WIN == WIN - 1) || (c == nC - 1);
+        TICK(te0);
+        mbar_wait(&sm.y_ready[u], (c >> 1) & 1);
+        TICK(te1);
+        fence_after_sync();
+        float yv[16];
+        tmem_ld16(tb + 64 + 32 * u + 16, yv);
+        tmem_wait_ld();
+        if (win_end) {
+            const int w = c / WIN;
+            const float *dl = sm.DLw[w & 3];
+            const bool last = (c == nC - 1);
+            float *dst = last ? (P.sT != nullptr ? P.sT + (size_t)bh * kC * kC : nullptr)
+                              : ck + (size_t)(w + 1) * (kC * kC);
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float v[16];
+                tmem_ld16(tb + 16 * cb, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] *= dl[16 * cb + i];
+                if (!last) tmem_st16(tb + 16 * cb, v);
+                if (act && dst != nullptr) {
+                    float4 *dp = reinterpret_cast<float4 *>(dst + row * kC + 16 * cb);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+            tmem_wait_st();
+        }
+        fence_before_sync();
+        mbar_arrive(&sm.y_free[u]);
+        if (win_end) mbar_arrive(&sm.win_scaled);
+        {   // Y tile: [value lanes][16 tokens] -> shared [token][value] bf16 -> 128-byte rows to HBM
+            bf16(&yb)[L][72] = sm.ybuf[u];
+            if (act) {
+#pragma unroll
+                for (int j = 0; j < 16; j++) yb[j][row] = __float2bfloat16_rn(yv[j]);
+            }
+            bar_sync(4, 128);
+            const int tok = tid >> 3, part = tid & 7;
+            const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
+            *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
+        }
+        TICK(te2); ACC(13, te0, te1); ACC(14, te1, te2);
+    }
+}
+
+constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1);
+
+__global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nC = P.T / L;
+    const size_t tok_stride = (size_t)P.H * kC;
+    const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
+
+    if (tid == 0) {
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.empty[i], 1); mbar_init(&sm.full[i], 128); }
+        for (int i = 0; i < NNAT; i++) { mbar_init(&sm.a_done[i], 256); mbar_init(&sm.nat_empty[i], 128); }
+        mbar_init(&sm.p_done, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 128); }
+        mbar_init(&sm.win_scaled, 128);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 128);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    if (warp < 4) epilogue(P, sm, base, tok_stride, bh, nC, tid);
+    else if (warp < 12) stage_a(P, sm, base, tok_stride, nC, tid - 128);
+    else if (warp < 16) stage_b(P, sm, nC, tid - 384, 0);
+    else if (warp < 20) stage_b(P, sm, nC, tid - 512, 1);
+    else mma_warp(P, sm, nC);
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 128);
+}
+
+}  // namespace tcfwd
+
+long long *g_tc_dbg = nullptr;   // set by the profiling harness only
+
+size_t tc_fwd_ckpt_floats(int B, int T, int H) {
+    const int nC = T / tcfwd::L, nW = (nC + tcfwd::WIN - 1) / tcfwd::WIN;
+    return (size_t)B * H * nW * kC * kC;
+}
+
+cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                          const void *a, const void *b, void *y, float *ckpt, const float *s0, float *sT,
+                          cudaStream_t st) {
+    using namespace tcfwd;
+    static_assert(sizeof(Smem) <= 232448, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
+             (const bf16 *)b, (bf16 *)y, ckpt, s0, sT, g_tc_dbg};
+    count_launch();
+    wkv7_tc_fwd_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace rwkvtts
