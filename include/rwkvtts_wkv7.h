@@ -67,9 +67,8 @@ RWKVTTS_API const char *rwkvtts_strerror(int code);
 /* cudaError_t of the last failed launch on the calling thread (0 if none). */
 RWKVTTS_API int rwkvtts_last_cuda_error(void);
 
-/* Kernel family of the training ops: 0 = sequential scan on CUDA cores, 1 = chunked tensor-core
- * kernels.  Forward and backward of one autograd node must run under the same setting (the
- * layout inside `s`/`sa` differs).  Initial value from env RWKVTTS_WKV7_IMPL ("scan"/"chunk"). */
+/* Kernel family of rwkvtts_wkv7_forward_infer: 1 = chunked tcgen05 tensor-core kernel (default),
+ * 0 = sequential scan on the CUDA cores.  Initial value from env RWKVTTS_WKV7_IMPL ("scan" -> 0). */
 RWKVTTS_API int rwkvtts_set_impl(int impl);
 RWKVTTS_API int rwkvtts_get_impl(void);
 
@@ -84,6 +83,13 @@ RWKVTTS_API size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_fl
 RWKVTTS_API int rwkvtts_wkv7_forward(int B, int T, int H, const void *w, const void *q, const void *k,
                          const void *v, const void *z, const void *a, void *y, float *s,
                          float *sa, void *stream);
+
+/* Forward without the backward's scratch tensors: what the reference runs under torch.no_grad()
+ * (evaluation, prefill of prompts through RWKV7Attention with T >= 64).
+ * y, optional initial state s0 and final state sT as in rwkvtts_wkv7_forward_ex. */
+RWKVTTS_API int rwkvtts_wkv7_forward_infer(int B, int T, int H, const void *w, const void *q, const void *k,
+                               const void *v, const void *z, const void *a, void *y, const float *s0,
+                               float *sT, void *stream);
 
 /* Training backward: the exact adjoint of rwkvtts_wkv7_forward. */
 RWKVTTS_API int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const void *q, const void *k,

@@ -24,6 +24,7 @@ SYMBOLS = {
     "rwkvtts_wkv7_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
                                                       ctypes.POINTER(ctypes.c_size_t)]),
     "rwkvtts_wkv7_forward": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
+    "rwkvtts_wkv7_forward_infer": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
     "rwkvtts_wkv7_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp] + [_vp] * 6 + [_vp]),
     "rwkvtts_wkv7_forward_ex": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _fp, _fp, _vp]),
     "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),

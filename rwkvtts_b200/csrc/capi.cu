@@ -13,9 +13,6 @@ std::atomic<long long> g_kernel_launches{0};
 cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
                             float *sT, bool save, cudaStream_t st);
-cudaError_t launch_chunk_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                             const void *a, const void *b, void *y, float *s, const float *s0, float *sT,
-                             cudaStream_t st);
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, void *y, float *ckpt, const float *s0, float *sT,
                           cudaStream_t st);
@@ -28,14 +25,14 @@ cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, c
 namespace {
 thread_local int g_last_cuda_error = 0;
 
-// Kernel family used by the training ops.  Forward and backward must use the same family because
-// the layout of the scratch tensor `s` differs (scan: state at chunk ends + `sa`; chunk: state at
-// chunk starts).  0 = sequential scan (CUDA cores), 1 = chunked tensor-core kernels.
+// Kernel family of the snapshot-free forward (rwkvtts_wkv7_forward_infer): 1 = chunked tcgen05 kernel
+// (default), 0 = sequential scan on the CUDA cores.  The training forward always runs the scan kernel:
+// the backward un-steps the state from its fp32 snapshots (as the reference does, wkv7_cuda.cu:91-94),
+// which amplifies the tf32-level differences of the chunked kernel by up to 1/decay^16.
 int initial_impl() {
     const char *e = getenv("RWKVTTS_WKV7_IMPL");
-    if (e != nullptr && e[0] == 'c') return 1;
-    if (e != nullptr && e[0] == 't') return 2;
-    return 0;
+    if (e != nullptr && e[0] == 's') return 0;
+    return 1;
 }
 std::atomic<int> g_impl{initial_impl()};
 
@@ -83,7 +80,7 @@ const char *rwkvtts_strerror(int code) {
 int rwkvtts_last_cuda_error(void) { return g_last_cuda_error; }
 
 int rwkvtts_set_impl(int impl) {
-    if (impl < 0 || impl > 2) return RWKVTTS_ERR_SHAPE;
+    if (impl != 0 && impl != 1) return RWKVTTS_ERR_SHAPE;
     g_impl.store(impl);
     return RWKVTTS_OK;
 }
@@ -105,11 +102,18 @@ int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, c
     if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
-    if (g_impl.load() == 2)
-        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, s, s0, sT, (cudaStream_t)stream));
-    if (g_impl.load() == 1)
-        return finish(rwkvtts::launch_chunk_fwd(B, T, H, w, q, k, v, z, a, y, s, s0, sT, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,
+                                           (cudaStream_t)stream));
+}
+
+int rwkvtts_wkv7_forward_infer(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                               const void *z, const void *a, void *y, const float *s0, float *sT, void *stream) {
+    if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({w, q, k, v, z, a, y})) return rc;
+    if (int rc = check_opt({s0, sT})) return rc;
+    if (g_impl.load() == 1)
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, s0, sT, (cudaStream_t)stream));
+    return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT, false,
                                            (cudaStream_t)stream));
 }
 

@@ -77,7 +77,7 @@ struct Params {
     int T, H;
     const bf16 *w, *q, *k, *v, *a, *b;
     bf16 *y;
-    float *ckpt;         // state at the start of every window, [B*H][ceil(T/64)][64][64]
+    float *ckpt;         // state at the start of every window, [B*H][ceil(T/64)][64][64]; may be null
     const float *s0;     // may be null
     float *sT;           // may be null
     long long *dbg;      // phase-cycle counters (profiling builds only), may be null
@@ -387,7 +387,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
     const int nW = (nC + WIN - 1) / WIN;
-    float *ck = P.ckpt + (size_t)bh * nW * (kC * kC);
+    float *ck = P.ckpt != nullptr ? P.ckpt + (size_t)bh * nW * (kC * kC) : nullptr;
     {   // initial state -> tensor memory and checkpoint 0
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
@@ -403,7 +403,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 }
             }
             tmem_st16(tb + 16 * cb, v);
-            if (act) {
+            if (act && ck != nullptr) {
                 float4 *dp = reinterpret_cast<float4 *>(ck + row * kC + 16 * cb);
 #pragma unroll
                 for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -428,7 +428,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
             const float *dl = sm.DLw[w & 3];
             const bool last = (c == nC - 1);
             float *dst = last ? (P.sT != nullptr ? P.sT + (size_t)bh * kC * kC : nullptr)
-                              : ck + (size_t)(w + 1) * (kC * kC);
+                              : (ck != nullptr ? ck + (size_t)(w + 1) * (kC * kC) : nullptr);
 #pragma unroll
             for (int cb = 0; cb < 4; cb++) {
                 float v[16];

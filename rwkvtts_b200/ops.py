@@ -53,6 +53,16 @@ def wkv7_forward_(w, q, k, v, z, a, y, s, sa, s0=None, sT=None):
     _lib.check(rc, "rwkvtts_wkv7_forward")
 
 
+def wkv7_forward_infer_(w, q, k, v, z, a, y, s0=None, sT=None):
+    """Snapshot-free forward (no backward possible): the chunked tcgen05 kernel."""
+    _need_cuda(w, q, k, v, z, a, y, s0, sT)
+    B, T, H, _ = w.shape
+    with torch.cuda.device(w.device):
+        rc = _lib.lib().rwkvtts_wkv7_forward_infer(B, T, H, _ptr(w), _ptr(q), _ptr(k), _ptr(v), _ptr(z), _ptr(a),
+                                                   _ptr(y), _ptr(s0), _ptr(sT), _stream())
+    _lib.check(rc, "rwkvtts_wkv7_forward_infer")
+
+
 def wkv7_backward_(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0=None, dsT=None, ds0=None):
     _need_cuda(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0, dsT, ds0)
     B, T, H, _ = w.shape
@@ -116,6 +126,9 @@ class WindBackstepping(torch.autograd.Function):
         assert all(i.dtype == torch.bfloat16 for i in [w, q, k, v, z, b])
         assert all(i.is_contiguous() for i in [w, q, k, v, z, b])
         y = torch.empty_like(v)
+        if not any(ctx.needs_input_grad):      # torch.no_grad() / frozen inputs: no scratch, tcgen05 kernel
+            wkv7_forward_infer_(w, q, k, v, z, b, y)
+            return y
         s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
         sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
         torch.ops.wind_backstepping.forward(w, q, k, v, z, b, y, s, sa)
@@ -189,9 +202,12 @@ class _Wkv7WithState(torch.autograd.Function):
     def forward(ctx, w, q, k, v, a, b, s0):
         B, T, H, C = w.shape
         y = torch.empty_like(v)
+        sT = torch.empty(B, H, C, C, dtype=torch.float32, device=w.device)
+        if not any(ctx.needs_input_grad):
+            wkv7_forward_infer_(w, q, k, v, a, b, y, s0=s0, sT=sT)
+            return y, sT
         s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
         sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
-        sT = torch.empty(B, H, C, C, dtype=torch.float32, device=w.device)
         wkv7_forward_(w, q, k, v, a, b, y, s, sa, s0=s0, sT=sT)
         ctx.save_for_backward(w, q, k, v, a, b, s, sa, s0)
         return y, sT

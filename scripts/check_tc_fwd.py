@@ -1,12 +1,12 @@
 """GPU check of one forward kernel family against the oracle, plus timing.
-usage: python scripts/check_tc_fwd.py [impl] (0 scan, 1 chunk mma.sync, 2 tcgen05)"""
+usage: python scripts/check_tc_fwd.py [impl] (0 scan, 1 tcgen05)"""
 import sys, time
 import torch
 import rwkvtts_b200 as R
 from rwkvtts_b200 import ops
 from oracle import wkv7_oracle as O
 
-impl = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+impl = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 lib = R._lib.lib()
 assert lib.rwkvtts_set_impl(impl) == 0
 ORDER = "wqkvab"
@@ -15,11 +15,9 @@ def run(B, T, H, seed, s0=None):
     x = O.make_inputs(B, T, H, seed=seed)
     d = {n: t.cuda() for n, t in x.items()}
     y = torch.empty_like(d["v"])
-    s = torch.empty(B, H, T // 16, 64, 64, dtype=torch.float32, device="cuda")
-    sa = torch.empty(B, T, H, 64, dtype=torch.float32, device="cuda")
     sT = torch.empty(B, H, 64, 64, dtype=torch.float32, device="cuda")
     s0d = None if s0 is None else s0.cuda()
-    ops.wkv7_forward_(*[d[n] for n in ORDER], y, s, sa, s0=s0d, sT=sT)
+    ops.wkv7_forward_infer_(*[d[n] for n in ORDER], y, s0=s0d, sT=sT)
     torch.cuda.synchronize()
     y64, sT64 = O.wkv7_forward(*[x[n] for n in ORDER], s0=s0)
     exc, err, floor = O.excess_rel_l2(y.cpu(), y64)
@@ -47,12 +45,12 @@ y = torch.empty_like(d["v"])
 s = torch.empty(B, H, T // 16, 64, 64, dtype=torch.float32, device="cuda")
 sa = torch.empty(B, T, H, 64, dtype=torch.float32, device="cuda")
 for _ in range(3):
-    ops.wkv7_forward_(*[d[n] for n in ORDER], y, s, sa)
+    ops.wkv7_forward_infer_(*[d[n] for n in ORDER], y)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(10):
-    ops.wkv7_forward_(*[d[n] for n in ORDER], y, s, sa)
+    ops.wkv7_forward_infer_(*[d[n] for n in ORDER], y)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f"impl {impl} fwd c2 [8,4096,16,64]: {ms:.3f} ms  -> {B*T*H*896/ms/1e6:.0f} GB/s algorithmic "
