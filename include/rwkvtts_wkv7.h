@@ -115,6 +115,17 @@ RWKVTTS_API int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *st
                                const void *w, const void *k, const void *v, const void *a,
                                const void *b, void *y, void *stream);
 
+/* Fused Adam / AdamW step on one contiguous shard of the flat parameter space (ZeRO-2 style: every
+ * rank updates only the slice it owns).  Replaces the deepspeed.ops.adam.FusedAdam / DeepSpeedCPUAdam
+ * step the reference's scripts run through engine.step() (train_spark_rwkv7speech_jsonl.py:195-199,
+ * :481-482).  master / exp_avg / exp_avg_sq: fp32 [n]; grad: bf16 or fp32 [n] (multiplied by
+ * grad_scale, e.g. the clipping coefficient); param: bf16 or fp32 [n] receives the updated weights.
+ * bias_correction1 = 1 - beta1^t, bias_correction2_sqrt = sqrt(1 - beta2^t) (pass 1.0 to disable). */
+RWKVTTS_API int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg_sq, const void *grad,
+                       int grad_is_bf16, void *param, int param_is_bf16, long long n, float lr, float beta1,
+                       float beta2, float eps, float weight_decay, int adamw_mode, float bias_correction1,
+                       float bias_correction2_sqrt, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

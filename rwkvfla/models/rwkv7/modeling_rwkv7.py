@@ -1,0 +1,337 @@
+"""`rwkvfla.models.rwkv7.modeling_rwkv7`: RWKV7Model / RWKV7ForCausalLM / RWKV7Block / RWKV7PreTrainedModel,
+plus the re-exports the reference imports from this module (Cache, FusedCrossEntropyLoss,
+FusedLinearCrossEntropyLoss; spark_llm.py:7-8).
+
+Parameter names follow rwkv-fla (`model.embeddings`, `model.layers.N.{pre_norm,attn_norm,attn.*,ffn_norm,
+ffn.{x_k,key,value}}`, `model.norm`, `lm_head`), so `from_pretrained` of the checkpoints the reference
+loads (README.md:140-142) and utils/convert_rwkv.py:17-41 keep working.  `generate` is a native loop
+(greedy / temperature / top-k / top-p, eos, left-padded batches) over the recurrent Cache: one
+prefill through the chunked kernels, then one stateful step per token.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch.utils.checkpoint import checkpoint
+from transformers.generation.utils import GenerationMixin
+from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutputWithPast
+from transformers.modeling_utils import PreTrainedModel
+
+from rwkvtts_b200 import core
+from ...layers.rwkv7 import RWKV7Attention
+from ...modules import FusedCrossEntropyLoss, FusedLinearCrossEntropyLoss, LayerNorm, l2_warp
+from ..utils import Cache
+from .configuration_rwkv7 import RWKV7Config
+
+
+class RWKV7FeedForward(nn.Module):
+    """Channel mix: value(relu(key(x + (shift(x) - x) * x_k))**2)  (rwkv_s2s_single_ffn.py:223-230)."""
+
+    def __init__(self, hidden_size: int, hidden_ratio: Optional[int] = None, intermediate_size: Optional[int] = None,
+                 hidden_act: str = "sqrelu", layer_idx: int = None, num_hidden_layers: int = None):
+        super().__init__()
+        assert hidden_act == "sqrelu"
+        self.hidden_size = hidden_size
+        if hidden_ratio is None:
+            hidden_ratio = 4
+        if intermediate_size is None:
+            intermediate_size = 32 * ((int(hidden_size * hidden_ratio) + 31) // 32)
+        self.hidden_ratio, self.intermediate_size = hidden_ratio, intermediate_size
+        self.layer_idx, self.num_hidden_layers = layer_idx, num_hidden_layers
+        self.x_k = nn.Parameter(torch.zeros(hidden_size))
+        self.key = nn.Linear(hidden_size, intermediate_size, bias=False)
+        self.value = nn.Linear(intermediate_size, hidden_size, bias=False)
+        with torch.no_grad():
+            if layer_idx is not None and num_hidden_layers is not None:
+                r10 = 1.0 - layer_idx / num_hidden_layers
+                ddd = torch.arange(hidden_size, dtype=torch.float32) / hidden_size
+                self.x_k.copy_(1.0 - torch.pow(ddd, r10 ** 4))
+            nn.init.orthogonal_(self.key.weight)
+            self.value.weight.zero_()
+
+    def forward(self, x: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, state: Optional[Cache] = None,
+                cu_seqlens=None, use_cache: bool = False, **kwargs):
+        am = None
+        if attention_mask is not None:
+            am = attention_mask.narrow(1, attention_mask.size(1) - x.shape[1], x.shape[1]).unsqueeze(-1).to(x.dtype)
+        shift = None
+        if state is not None and len(state) > self.layer_idx:
+            shift = state[self.layer_idx].get("ffn_state")
+        out, new_shift = core.cmix(self.x_k, self.key.weight, self.value.weight, x, mask=am, shift_state=shift,
+                                   need_state=state is not None and use_cache)
+        if state is not None and use_cache:
+            state.update(ffn_state=new_shift, layer_idx=self.layer_idx, offset=0)
+        return out, state
+
+
+class RWKV7Block(nn.Module):
+    def __init__(self, config: RWKV7Config, layer_idx: int):
+        super().__init__()
+        self.config, self.layer_idx = config, layer_idx
+        norm = lambda: LayerNorm(config.hidden_size, bias=config.norm_bias, eps=config.norm_eps)
+        if config.norm_first and layer_idx == 0:
+            self.pre_norm = norm()
+        self.attn_norm = norm()
+        self.attn = RWKV7Attention(
+            mode=config.attn_mode, hidden_size=config.hidden_size, head_dim=config.head_dim,
+            num_heads=config.num_heads, decay_low_rank_dim=config.decay_low_rank_dim,
+            gate_low_rank_dim=config.gate_low_rank_dim, a_low_rank_dim=config.a_low_rank_dim,
+            v_low_rank_dim=config.v_low_rank_dim, norm_eps=config.norm_eps, fuse_norm=config.fuse_norm,
+            layer_idx=layer_idx, value_dim=config.value_dim[layer_idx], num_hidden_layers=config.num_hidden_layers)
+        self.ffn_norm = norm()
+        self.ffn = RWKV7FeedForward(hidden_size=config.hidden_size, hidden_ratio=config.hidden_ratio,
+                                    intermediate_size=config.intermediate_size, hidden_act=config.hidden_act,
+                                    layer_idx=layer_idx, num_hidden_layers=config.num_hidden_layers)
+
+    def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                past_key_values: Optional[Cache] = None, use_cache: Optional[bool] = False,
+                output_attentions: Optional[bool] = False, v_first: torch.Tensor = None, cu_seqlens=None, **kwargs):
+        residual = self.pre_norm(hidden_states) if hasattr(self, "pre_norm") else hidden_states
+        hidden_states = self.attn_norm(residual)
+        hidden_states, attentions, past_key_values, v_first = self.attn(
+            hidden_states=hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
+            use_cache=use_cache, output_attentions=output_attentions, v_first=v_first, cu_seqlens=cu_seqlens)
+        hidden_states, residual = self.ffn_norm(hidden_states, residual, True)
+        hidden_states, past_key_values = self.ffn(hidden_states, attention_mask, past_key_values, cu_seqlens,
+                                                  use_cache=use_cache)
+        hidden_states = residual + hidden_states
+        return hidden_states, attentions, past_key_values, v_first
+
+
+class RWKV7PreTrainedModel(PreTrainedModel):
+    config_class = RWKV7Config
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = True
+    _no_split_modules = ["RWKV7Block"]
+    _supports_cache_class = True
+    _skip_keys_device_placement = ["past_key_values"]
+
+    def _init_weights(self, module: nn.Module, rescale_prenorm_residual: bool = True, num_residuals_per_layer: int = 2):
+        # time-mix / channel-mix modules initialise themselves (BlinkDL's layer-dependent init); only the
+        # embedding and the head are left (rwkv-fla: uniform embedding, orthogonal-ish head)
+        if isinstance(module, nn.Embedding):
+            nn.init.uniform_(module.weight, a=-1e-4, b=1e-4)
+        elif isinstance(module, nn.Linear) and getattr(module, "_is_lm_head", False):
+            nn.init.normal_(module.weight, mean=0.0, std=self.config.initializer_range)
+
+
+class RWKV7Model(RWKV7PreTrainedModel):
+    def __init__(self, config: RWKV7Config):
+        super().__init__(config)
+        self.padding_idx = config.pad_token_id
+        self.vocab_size = config.vocab_size
+        self.embeddings = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
+        self.layers = nn.ModuleList([RWKV7Block(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = LayerNorm(config.hidden_size, bias=config.norm_bias, eps=config.norm_eps)
+        self.gradient_checkpointing = False
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.embeddings
+
+    def set_input_embeddings(self, value):
+        self.embeddings = value
+
+    def forward(self, input_ids: Optional[torch.LongTensor] = None, attention_mask: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.FloatTensor] = None, past_key_values: Optional[Cache] = None,
+                use_cache: Optional[bool] = None, output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None,
+                cu_seqlens: Optional[torch.LongTensor] = None, **kwargs) -> Union[Tuple, BaseModelOutputWithPast]:
+        if output_attentions:
+            warnings.warn("`RWKV7Model` does not `output_attentions` now, setting it to `False`.")
+        output_attentions = False
+        output_hidden_states = output_hidden_states if output_hidden_states is not None else \
+            getattr(self.config, "output_hidden_states", False)
+        use_cache = use_cache if use_cache is not None else (self.config.use_cache if not self.training else False)
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if input_ids is None and inputs_embeds is None:
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        if inputs_embeds is None:
+            inputs_embeds = self.embeddings(input_ids)
+        hidden_states = inputs_embeds
+        if use_cache and not isinstance(past_key_values, Cache):
+            past_key_values = Cache.from_legacy_cache(past_key_values)
+        all_hidden_states = () if output_hidden_states else None
+        v_first = torch.zeros_like(hidden_states)
+        for layer in self.layers:
+            if output_hidden_states:
+                all_hidden_states += (hidden_states,)
+            if self.gradient_checkpointing and self.training:
+                hidden_states, _, past_key_values, v_first = checkpoint(
+                    layer, hidden_states, attention_mask, past_key_values, use_cache, False, v_first, cu_seqlens,
+                    use_reentrant=False)
+            else:
+                hidden_states, _, past_key_values, v_first = layer(
+                    hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
+                    use_cache=use_cache, output_attentions=False, v_first=v_first, cu_seqlens=cu_seqlens)
+        hidden_states = self.norm(hidden_states)
+        if output_hidden_states:
+            all_hidden_states += (hidden_states,)
+        if not return_dict:
+            return tuple(i for i in [hidden_states, past_key_values, all_hidden_states] if i is not None)
+        return BaseModelOutputWithPast(last_hidden_state=hidden_states, past_key_values=past_key_values,
+                                       hidden_states=all_hidden_states, attentions=None)
+
+
+def _filter_logits(logits: torch.Tensor, top_k: Optional[int], top_p: Optional[float]) -> torch.Tensor:
+    if top_k is not None and 0 < top_k < logits.shape[-1]:
+        kth = torch.topk(logits, top_k, dim=-1).values[..., -1, None]
+        logits = logits.masked_fill(logits < kth, float("-inf"))
+    if top_p is not None and 0.0 < top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(logits, descending=False, dim=-1)
+        cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        remove = cum <= (1 - top_p)
+        remove[..., -1:] = False
+        logits = logits.masked_fill(remove.scatter(-1, sorted_idx, remove), float("-inf"))
+    return logits
+
+
+class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
+    _tied_weights_keys = ["lm_head.weight"]
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.model = RWKV7Model(config)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.lm_head._is_lm_head = True
+        self.criterion = None
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embeddings
+
+    def set_input_embeddings(self, value):
+        self.model.embeddings = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, new_embeddings):
+        self.lm_head = new_embeddings
+
+    def set_decoder(self, decoder):
+        self.model = decoder
+
+    def get_decoder(self):
+        return self.model
+
+    def prepare_inputs_for_generation(self, input_ids=None, past_key_values=None, attention_mask=None,
+                                      inputs_embeds=None, use_cache=True, logits_to_keep=None, **kwargs):
+        if past_key_values is not None and len(past_key_values) > 0:
+            input_ids = input_ids[:, -1:]
+        if inputs_embeds is not None and (past_key_values is None or len(past_key_values) == 0):
+            model_inputs = {"inputs_embeds": inputs_embeds}
+        else:
+            model_inputs = {"input_ids": input_ids.contiguous()}
+        model_inputs.update({"past_key_values": past_key_values, "use_cache": use_cache,
+                             "attention_mask": attention_mask, "logits_to_keep": logits_to_keep})
+        return model_inputs
+
+    def forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                inputs_embeds: Optional[torch.Tensor] = None, past_key_values: Optional[Cache] = None,
+                labels: Optional[torch.LongTensor] = None, shift_labels: Optional[torch.LongTensor] = None,
+                use_cache: Optional[bool] = None, output_attentions: Optional[bool] = None,
+                output_hidden_states: Optional[bool] = None, return_dict: Optional[bool] = None,
+                logits_to_keep: Optional[int] = 0, **kwargs) -> Union[Tuple, CausalLMOutputWithPast]:
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "use_return_dict", True)
+        outputs = self.model(input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
+                             past_key_values=past_key_values, use_cache=use_cache,
+                             output_hidden_states=output_hidden_states, return_dict=True,
+                             cu_seqlens=kwargs.get("cu_seqlens"))
+        hidden_states = outputs.last_hidden_state
+        loss, logits = None, None
+        has_labels = labels is not None or shift_labels is not None
+        if not (self.config.fuse_linear_cross_entropy and has_labels):
+            h = hidden_states if not logits_to_keep else hidden_states[:, -logits_to_keep:]
+            logits = self.lm_head(h)
+        if has_labels:
+            criterion = self.criterion
+            if criterion is None:
+                if self.config.fuse_linear_cross_entropy:
+                    criterion = FusedLinearCrossEntropyLoss(use_l2warp=self.config.use_l2warp)
+                elif self.config.fuse_cross_entropy:
+                    criterion = FusedCrossEntropyLoss(inplace_backward=True)
+                else:
+                    criterion = nn.CrossEntropyLoss()
+            if shift_labels is None:
+                shift_labels = torch.cat((labels[..., 1:], torch.full_like(labels[:, :1], criterion.ignore_index)), 1)
+            shift_labels = shift_labels.to(hidden_states.device)
+            if self.config.fuse_linear_cross_entropy:
+                loss = criterion(hidden_states, shift_labels, self.lm_head.weight, self.lm_head.bias)
+            else:
+                loss = criterion(logits.view(shift_labels.numel(), -1), shift_labels.view(-1))
+                loss = l2_warp(loss, logits) if self.config.use_l2warp else loss
+        if not return_dict:
+            output = (logits, outputs.past_key_values)
+            return (loss,) + output if loss is not None else output
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=outputs.past_key_values,
+                                      hidden_states=outputs.hidden_states, attentions=None)
+
+    # ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids: Optional[torch.LongTensor] = None, inputs_embeds: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, max_new_tokens: Optional[int] = None,
+                 max_length: Optional[int] = None, min_new_tokens: int = 0, do_sample: bool = False,
+                 temperature: float = 1.0, top_k: Optional[int] = None, top_p: Optional[float] = None,
+                 eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
+                 use_cache: bool = True, generator: Optional[torch.Generator] = None,
+                 return_dict_in_generate: bool = False, **kwargs):
+        """Autoregressive decode over the recurrent Cache (the call inference/rwkv7speech_inference.py and
+        spark_llm.py:54-102 make).  Returns [B, prompt + new] token ids when `input_ids` is given and
+        [B, new] when only `inputs_embeds` is given (HF convention); finished rows are padded with
+        `pad_token_id`."""
+        if (input_ids is None) == (inputs_embeds is None):
+            raise ValueError("pass exactly one of input_ids / inputs_embeds")
+        prompt_len = input_ids.shape[1] if input_ids is not None else inputs_embeds.shape[1]
+        if max_new_tokens is None:
+            max_new_tokens = (max_length - prompt_len) if max_length is not None else 20
+        eos = eos_token_id if eos_token_id is not None else self.config.eos_token_id
+        eos = [] if eos is None else ([eos] if isinstance(eos, int) else list(eos))
+        pad = pad_token_id if pad_token_id is not None else (self.config.pad_token_id
+                                                             if self.config.pad_token_id is not None else (eos[0] if eos else 0))
+        if do_sample and top_k is None:
+            top_k = 50                                   # HF default
+        B = input_ids.shape[0] if input_ids is not None else inputs_embeds.shape[0]
+        dev = input_ids.device if input_ids is not None else inputs_embeds.device
+        cache = Cache()
+        out = self(input_ids=input_ids, inputs_embeds=inputs_embeds, attention_mask=attention_mask,
+                   past_key_values=cache, use_cache=True, logits_to_keep=1)
+        cache = out.past_key_values
+        eos_t = torch.tensor(eos, device=dev, dtype=torch.long) if eos else None
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        new_tokens = []
+        logits = out.logits[:, -1].float()
+        for step in range(max_new_tokens):
+            if eos_t is not None and step < min_new_tokens:
+                logits[:, eos_t] = float("-inf")
+            if do_sample:
+                lg = logits / max(temperature, 1e-6)
+                probs = _filter_logits(lg, top_k, top_p).softmax(dim=-1)
+                nxt = torch.multinomial(probs, 1, generator=generator).squeeze(-1)
+            else:
+                nxt = logits.argmax(dim=-1)
+            nxt = torch.where(done, torch.full_like(nxt, pad), nxt)
+            new_tokens.append(nxt)
+            if eos_t is not None:
+                done = done | torch.isin(nxt, eos_t)
+                if bool(done.all()):
+                    break
+            if step + 1 < max_new_tokens:
+                out = self(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, logits_to_keep=1)
+                cache = out.past_key_values
+                logits = out.logits[:, -1].float()
+        gen = torch.stack(new_tokens, dim=1) if new_tokens else torch.empty(B, 0, dtype=torch.long, device=dev)
+        seq = torch.cat([input_ids, gen], dim=1) if input_ids is not None else gen
+        if return_dict_in_generate:
+            return {"sequences": seq, "past_key_values": cache}
+        return seq
+
+
+__all__ = ["RWKV7Config", "RWKV7Model", "RWKV7ForCausalLM", "RWKV7PreTrainedModel", "RWKV7Block", "Cache",
+           "FusedLinearCrossEntropyLoss", "FusedCrossEntropyLoss", "RWKV7FeedForward"]

@@ -1,0 +1,152 @@
+"""RWKV-7 (x070) time-mix / channel-mix around the WKV-7 op, shared by the two module stacks.
+
+One functional restatement of
+
+  RWKV_Tmix_x070.forward      /root/reference/model/llm/rwkv_s2s_single_ffn.py:158-196   (training)
+  RWKV_x070_TMix_one / _seq   /root/reference/model/llm/rwkv_s2s_single_ffn.py:482-540   (stateful inference)
+  RWKV_CMix_x070.forward      :223-230,  RWKV_x070_CMix_one / _seq  :545-556
+  RWKV7Attention.forward      rwkv-fla (third party): same math with
+                              w = -0.6065*sigmoid(lora) == log(exp(-exp(w_pre))), w_pre = -softplus(-lora) - 0.5
+
+driven by a plain namespace of tensors (`TmixParams`), so the BlinkDL-named modules (x070.py) and the
+rwkvfla-named modules (rwkvfla/) are two thin parameter adapters over the same code.
+
+The recurrence itself always runs in the CUDA library (ops.py): WindBackstepping for training,
+the snapshot-free tcgen05 forward for no-grad prefill, the stateful scan for any-T / decode steps.
+Everything else here is torch (GEMMs through cuBLAS, elementwise through ATen): plumbing around the op.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+HEAD = ops.HEAD_SIZE
+
+
+@dataclass
+class TmixParams:
+    """Time-mix tensors.  Linear weights are [out, in] (nn.Linear); LoRA down/up are [in, low] / [low, out]
+    (BlinkDL layout; the rwkvfla adapter passes transposed views).  x_* / k_* / *0 broadcast over [.., C]."""
+    x_r: torch.Tensor
+    x_w: torch.Tensor
+    x_k: torch.Tensor
+    x_v: torch.Tensor
+    x_a: torch.Tensor
+    x_g: torch.Tensor
+    w0: torch.Tensor
+    w1: torch.Tensor
+    w2: torch.Tensor
+    a0: torch.Tensor
+    a1: torch.Tensor
+    a2: torch.Tensor
+    v0: Optional[torch.Tensor]
+    v1: Optional[torch.Tensor]
+    v2: Optional[torch.Tensor]
+    g1: torch.Tensor
+    g2: torch.Tensor
+    k_k: torch.Tensor
+    k_a: torch.Tensor
+    r_k: torch.Tensor          # [H, 64]
+    W_r: torch.Tensor
+    W_k: torch.Tensor
+    W_v: torch.Tensor
+    W_o: torch.Tensor
+    ln_w: torch.Tensor
+    ln_b: torch.Tensor
+    ln_eps: float = 64e-5      # 1e-5 * head_size_divisor**2 (:145) == head_dim * norm_eps (rwkvfla)
+
+
+def token_shift(x: torch.Tensor, prev: Optional[torch.Tensor]) -> torch.Tensor:
+    """time_shift(x) - x with time_shift = ZeroPad2d((0,0,1,-1)) (:162); `prev` [B,C] is the last
+    token of the previous call (:511), zeros if None."""
+    if prev is None:
+        shifted = F.pad(x, (0, 0, 1, -1))
+    else:
+        shifted = torch.cat((prev.unsqueeze(1).to(x.dtype), x[:, :-1]), dim=1)
+    return shifted - x
+
+
+def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
+    """Dispatch of the recurrence.  r,w,k,v,a,b: bf16 [B,T,C] contiguous; state fp32 [B,H,64,64] or None.
+    Returns y [B,T,C] and the final state (None unless need_state)."""
+    B, T, C = r.shape
+    H = C // HEAD
+    grad = torch.is_grad_enabled() and any(t.requires_grad for t in (r, w, k, v, a, b))
+    if T % ops.CHUNK_LEN == 0:
+        sh = lambda t: t.view(B, T, H, HEAD)
+        if state is None and not need_state:
+            return ops.RUN_CUDA_RWKV7g(r, w, k, v, a, b), None                     # :191 (training / no_grad)
+        y, sT = ops.wkv7_with_state(sh(w), sh(r), sh(k), sh(v), sh(a), sh(b), state)
+        return y.view(B, T, C), sT
+    if grad:
+        # ragged length under autograd: right-pad to a multiple of 16 with k=v=a=b=0 tokens (they leave
+        # every real output untouched; the state after them is not used)
+        assert not need_state, "final state with T % 16 != 0 is only available without autograd"
+        pad = (-T) % ops.CHUNK_LEN
+        pz = lambda t: F.pad(t, (0, 0, 0, pad))
+        sh = lambda t: pz(t).view(B, T + pad, H, HEAD)
+        y, _ = ops.wkv7_with_state(sh(w), sh(r), sh(k), sh(v), sh(a), sh(b), state)
+        return y.view(B, T + pad, C)[:, :T], None
+    # any T, no autograd: the stateful op (decode step for T == 1), state updated in place (:536)
+    if state is None:
+        st = torch.zeros(B, H, HEAD, HEAD, dtype=torch.float32, device=r.device)
+    else:
+        st = state if inplace_state else state.clone()
+    y = ops.RWKV7_BATCH_OP(st, r, w, k, v, a, b)
+    return y, st
+
+
+def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.Tensor],
+         mask: Optional[torch.Tensor] = None, mask_rwk: bool = True,
+         shift_state: Optional[torch.Tensor] = None, wkv_state: Optional[torch.Tensor] = None,
+         need_state: bool = False, inplace_state: bool = False):
+    """x [B,T,C] (bf16 on the GPU).  mask [B,T,1] of 0/1 or None.  Returns
+    (out [B,T,C], v_first, new_shift_state [B,C] | None, new_wkv_state | None).  With `inplace_state` the
+    stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536)."""
+    B, T, C = x.shape
+    H = C // HEAD
+    if mask is not None:
+        x = x * mask                                                            # :160
+    xx = token_shift(x, shift_state)                                            # :162
+    xr, xw, xk, xv, xa, xg = (torch.addcmul(x, xx, m) for m in (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g))
+    r = F.linear(xr, p.W_r)
+    w = -F.softplus(-(p.w0 + torch.tanh(xw @ p.w1) @ p.w2)) - 0.5               # :172
+    k = F.linear(xk, p.W_k)
+    v = F.linear(xv, p.W_v)
+    if mask is not None and mask_rwk:
+        r, w, k, v = r * mask, w * mask, k * mask, v * mask                     # :175-178
+    if layer_id == 0:
+        v_first = v                                                             # :180
+    else:
+        v = v + (v_first - v) * torch.sigmoid(p.v0 + (xv @ p.v1) @ p.v2)        # :182
+    a = torch.sigmoid(p.a0 + (xa @ p.a1) @ p.a2)                                # :183
+    g = torch.sigmoid(xg @ p.g1) @ p.g2                                         # :184
+    kk = F.normalize((k * p.k_k).view(B, T, H, HEAD), dim=-1, p=2.0).view(B, T, C)   # :186-187
+    if mask is not None:
+        kk = kk * mask                                                          # :188
+        v = v * mask                                                            # :190
+    k = k * (1 + (a - 1) * p.k_a)                                               # :189
+    c = lambda t: t.to(torch.bfloat16).contiguous()
+    y, new_state = _wkv(c(r), c(w), c(k), c(v), c(-kk), c(kk * a), wkv_state, need_state,
+                        inplace_state)                                                    # :191
+    y = F.group_norm(y.reshape(B * T, C).to(r.dtype), H, p.ln_w, p.ln_b, p.ln_eps).view(B, T, C)   # :192
+    y = y + ((r.view(B, T, H, HEAD) * k.view(B, T, H, HEAD) * p.r_k).sum(dim=-1, keepdim=True)
+             * v.view(B, T, H, HEAD)).view(B, T, C)                              # :194
+    out = F.linear(y * g, p.W_o)                                                 # :195
+    return out, v_first, (x[:, -1] if need_state else None), new_state
+
+
+def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch.Tensor,
+         mask: Optional[torch.Tensor] = None, shift_state: Optional[torch.Tensor] = None,
+         need_state: bool = False):
+    """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556)."""
+    if mask is not None:
+        x = x * mask
+    xx = token_shift(x, shift_state)
+    k = torch.relu(F.linear(torch.addcmul(x, xx, x_k), W_key)) ** 2
+    return F.linear(k, W_value), (x[:, -1] if need_state else None)

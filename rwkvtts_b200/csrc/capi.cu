@@ -20,6 +20,9 @@ cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, c
                             const void *a, const void *b, const void *dy, const float *s, const float *sa,
                             const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
                             float *ds0, cudaStream_t st);
+cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *grad, int grad_is_bf16, void *param,
+                              int param_is_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
+                              int adamw, float bc1, float bc2_sqrt, float gscale, cudaStream_t st);
 }  // namespace rwkvtts
 
 namespace {
@@ -149,6 +152,19 @@ int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const v
     // op-boundary order of the scan kernel is (w, q=r, k, v, a, b)
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, r, k, v, a, b, y, nullptr, nullptr, state, state, false,
                                            (cudaStream_t)stream));
+}
+
+int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg_sq, const void *grad, int grad_is_bf16,
+                       void *param, int param_is_bf16, long long n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int adamw_mode, float bias_correction1, float bias_correction2_sqrt,
+                       float grad_scale, void *stream) {
+    if (n < 0) return RWKVTTS_ERR_SHAPE;
+    if (n == 0) return RWKVTTS_OK;
+    if (master == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr || grad == nullptr || param == nullptr)
+        return RWKVTTS_ERR_NULL;
+    return finish(rwkvtts::launch_adam_shard(master, exp_avg, exp_avg_sq, grad, grad_is_bf16, param, param_is_bf16, n,
+                                             lr, beta1, beta2, eps, weight_decay, adamw_mode, bias_correction1,
+                                             bias_correction2_sqrt, grad_scale, (cudaStream_t)stream));
 }
 
 }  // extern "C"
