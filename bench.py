@@ -194,6 +194,26 @@ def main():
     ms_per_step = total_ms / args.steps
     value = B * T * world / (ms_per_step * 1e-3)
 
+    # ---- the other kernels of the path, same inputs (explain `value`; not part of it) -------------
+    def timed(fn, n=10):
+        fn(); torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b_.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b_) / n
+    infer_ms = timed(lambda: R.wkv7_forward_infer_(*ins, y))                 # chunked tcgen05 forward (no_grad)
+    DB, DSTEPS = 32, 64                                                       # config c4: 32 prompts, decode steps
+    dstate = torch.zeros(LAYERS, DB, H, C, C, dtype=torch.float32, device=dev)
+    dins = [d[n][:4, :DB // 4 * 1].reshape(DB, 1, H * C).contiguous() for n in "qwkvab"]
+    dy_ = torch.empty(DB, 1, H * C, dtype=torch.bfloat16, device=dev)
+    def decode_steps():
+        for _ in range(DSTEPS):
+            for l in range(LAYERS):
+                R.wkv7_state_forward_(DB, 1, H * C, H, dstate[l], *dins, dy_)
+    decode_ms = timed(decode_steps, n=2) / DSTEPS                            # WKV part of one decode step, 24 layers
+
     # ---- e2e: public API (WindBackstepping autograd op) with pinned HOST buffers --------------
     host_in = [x[n].pin_memory() for n in "wqkvab"] + [x["dy"].pin_memory()]
     host_out = [torch.empty_like(x["v"]).pin_memory() for _ in range(7)]
@@ -280,7 +300,14 @@ def main():
                      "algorithmic_bytes_per_token_head": dom_bytes, "token_heads_per_launch": th,
                      "avg_launch_ms": dom_ms},
         "kernels": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": fwd_ach, "bwd_GBps": bwd_ach,
-                    "fwd_frac": fwd_ach / peak, "bwd_frac": bwd_ach / peak},
+                    "fwd_frac": fwd_ach / peak, "bwd_frac": bwd_ach / peak,
+                    "fwd_infer_tcgen05_ms": infer_ms, "fwd_infer_GBps": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9,
+                    "fwd_infer_frac": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9 / peak,
+                    "decode_step_wkv_ms": decode_ms,
+                    "decode_step_GBps": (2 * C * C * 4 + FWD_BYTES) * DB * H * LAYERS / (decode_ms * 1e-3) / 1e9,
+                    "decode_wkv_tokens_per_s": DB / (decode_ms * 1e-3),
+                    "note": "fwd/bwd = training pair (scan kernels, exact snapshots); fwd_infer = chunked tcgen05 "
+                            "forward used under no_grad; decode = stateful op, T=1, B=32, 24 layers (config c4)"},
         "ref_gpu_op": ref_gpu,
     }
     if world == 1 and not args.no_cpu_baseline:

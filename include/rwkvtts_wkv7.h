@@ -67,8 +67,9 @@ RWKVTTS_API const char *rwkvtts_strerror(int code);
 /* cudaError_t of the last failed launch on the calling thread (0 if none). */
 RWKVTTS_API int rwkvtts_last_cuda_error(void);
 
-/* Kernel family of rwkvtts_wkv7_forward_infer: 1 = chunked tcgen05 tensor-core kernel (default),
- * 0 = sequential scan on the CUDA cores.  Initial value from env RWKVTTS_WKV7_IMPL ("scan" -> 0). */
+/* Kernel family: 1 = chunked tcgen05 tensor-core kernels (default), 0 = sequential scan on the CUDA
+ * cores.  The families lay `s`/`sa` out differently, so forward and backward of one autograd node must
+ * run under the same setting.  Initial value from env RWKVTTS_WKV7_IMPL ("scan" -> 0). */
 RWKVTTS_API int rwkvtts_set_impl(int impl);
 RWKVTTS_API int rwkvtts_get_impl(void);
 
@@ -99,13 +100,14 @@ RWKVTTS_API int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const 
 
 /* Forward / backward with an initial state s0 (may be NULL = zeros) and optional final
  * state sT / incoming final-state gradient dsT / outgoing initial-state gradient ds0
- * (each may be NULL).  fp32 [B,H,64,64] value-major. */
+ * (each may be NULL).  fp32 [B,H,64,64] value-major.  The backward takes the forward's final state
+ * sT when dsT is given (required by the tcgen05 family, ignored by the scan family). */
 RWKVTTS_API int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, const void *k,
                             const void *v, const void *z, const void *a, void *y, float *s,
                             float *sa, const float *s0, float *sT, void *stream);
 RWKVTTS_API int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, const void *k,
                              const void *v, const void *z, const void *a, const void *dy,
-                             const float *s, const float *sa, const float *s0,
+                             const float *s, const float *sa, const float *s0, const float *sT,
                              const float *dsT, void *dw, void *dq, void *dk, void *dv,
                              void *dz, void *da, float *ds0, void *stream);
 

@@ -27,7 +27,7 @@ SYMBOLS = {
     "rwkvtts_wkv7_forward_infer": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
     "rwkvtts_wkv7_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp] + [_vp] * 6 + [_vp]),
     "rwkvtts_wkv7_forward_ex": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _fp, _fp, _vp]),
-    "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),
+    "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),
     "rwkvtts_wkv7_state_forward": (_i, [_i, _i, _i, _i, _fp] + [_vp] * 6 + [_vp, _vp]),
     "rwkvtts_adam_shard": (_i, [_fp, _fp, _fp, _vp, _i, _vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_i]
                            + [ctypes.c_float] * 3 + [_vp]),

@@ -14,8 +14,12 @@ cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, c
                             const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
                             float *sT, bool save, cudaStream_t st);
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                          const void *a, const void *b, void *y, float *ckpt, const float *s0, float *sT,
+                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
                           cudaStream_t st);
+cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                          const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
+                          const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
+                          void *db, float *ds0, cudaStream_t st);
 cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, const void *dy, const float *s, const float *sa,
                             const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
@@ -28,10 +32,11 @@ cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *gra
 namespace {
 thread_local int g_last_cuda_error = 0;
 
-// Kernel family of the snapshot-free forward (rwkvtts_wkv7_forward_infer): 1 = chunked tcgen05 kernel
-// (default), 0 = sequential scan on the CUDA cores.  The training forward always runs the scan kernel:
-// the backward un-steps the state from its fp32 snapshots (as the reference does, wkv7_cuda.cu:91-94),
-// which amplifies the tf32-level differences of the chunked kernel by up to 1/decay^16.
+// Kernel family: 1 = chunked tcgen05 kernels (default), 0 = sequential scan on the CUDA cores.  The two
+// families lay the scratch tensors `s` / `sa` out differently (scan: state at chunk ends, the reference's
+// convention, un-stepped by the backward; tcgen05: transposed state at chunk starts in the window frame,
+// recomputed from by the backward), so the training forward records the family in `s` ... no: the caller
+// keeps forward and backward of one autograd node under the same setting (rwkvtts_set_impl).
 int initial_impl() {
     const char *e = getenv("RWKVTTS_WKV7_IMPL");
     if (e != nullptr && e[0] == 's') return 0;
@@ -105,6 +110,8 @@ int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, c
     if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
+    if (g_impl.load() == 1)
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,
                                            (cudaStream_t)stream));
 }
@@ -115,7 +122,8 @@ int rwkvtts_wkv7_forward_infer(int B, int T, int H, const void *w, const void *q
     if (int rc = check_ptrs({w, q, k, v, z, a, y})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
     if (g_impl.load() == 1)
-        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, s0, sT, (cudaStream_t)stream));
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT,
+                                             (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT, false,
                                            (cudaStream_t)stream));
 }
@@ -127,12 +135,17 @@ int rwkvtts_wkv7_forward(int B, int T, int H, const void *w, const void *q, cons
 
 int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                              const void *z, const void *a, const void *dy, const float *s, const float *sa,
-                             const float *s0, const float *dsT, void *dw, void *dq, void *dk, void *dv,
-                             void *dz, void *da, float *ds0, void *stream) {
+                             const float *s0, const float *sT, const float *dsT, void *dw, void *dq, void *dk,
+                             void *dv, void *dz, void *da, float *ds0, void *stream) {
     if (B <= 0 || T <= 0 || H <= 0 || T % RWKVTTS_CHUNK_LEN != 0) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da})) return rc;
-    if (int rc = check_opt({s0, dsT, ds0})) return rc;
+    if (int rc = check_opt({s0, sT, dsT, ds0})) return rc;
     (void)s0;  // states are rebuilt from the snapshots in `s`; s0 is only part of the signature
+    if (g_impl.load() == 1) {
+        if (dsT != nullptr && sT == nullptr) return RWKVTTS_ERR_NULL;   // the window-end term needs S_T
+        return finish(rwkvtts::launch_tc_bwd(B, T, H, w, q, k, v, z, a, dy, s, sa, sT, dsT, dw, dq, dk, dv, dz, da,
+                                             ds0, (cudaStream_t)stream));
+    }
     return finish(rwkvtts::launch_scan_bwd(B, T, H, w, q, k, v, z, a, dy, s, sa, dsT, dw, dq, dk, dv, dz, da,
                                            ds0, (cudaStream_t)stream));
 }
@@ -140,8 +153,8 @@ int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, 
 int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *z, const void *a, const void *dy, const float *s, const float *sa,
                           void *dw, void *dq, void *dk, void *dv, void *dz, void *da, void *stream) {
-    return rwkvtts_wkv7_backward_ex(B, T, H, w, q, k, v, z, a, dy, s, sa, nullptr, nullptr, dw, dq, dk, dv, dz,
-                                    da, nullptr, stream);
+    return rwkvtts_wkv7_backward_ex(B, T, H, w, q, k, v, z, a, dy, s, sa, nullptr, nullptr, nullptr, dw, dq, dk,
+                                    dv, dz, da, nullptr, stream);
 }
 
 int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const void *r, const void *w,

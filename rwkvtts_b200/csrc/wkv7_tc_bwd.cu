@@ -1,0 +1,723 @@
+// WKV-7 training backward for sm_100a: chunked DPLR adjoint on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32; dS, dS^T, the transposed forward state and all gradient tiles in tensor memory).
+//
+// Reference operator: the exact adjoint of model/llm/cuda/wkv7_cuda.cu:17-42 (backward_kernel :54-130).
+// Unlike the reference it never un-steps the state (no division by the decay): the forward
+// (wkv7_tc_fwd.cu, training variant) leaves, per 16-token chunk, the TRANSPOSED state at the chunk start
+// (window frame) and U_t = S_{t-1} a_t (`sa`); everything else is recomputed.  Algebra validated in f64
+// against the oracle in proto/tc_bwd_proto.py (1e-15) and with tf32 operand rounding (<= 6e-4).
+//
+// Frame: as in the forward (windows of 64 tokens, G = log-decay accumulated since the window start):
+//     Q~ = q e^{G}  A~ = a e^{G_{t-1}}  K~ = k e^{-G}  B~ = b e^{-G},   S^ = S diag(e^{-G}).
+// Per chunk (processed last to first), with S0 = state at the chunk start, dS = gradient w.r.t. the state
+// at the chunk end, N/Aak/Aqb/Aqk the forward's 16x16 Gram blocks and T = (I-N)^-1:
+//     B' = T^T B~,  Aqb' = Aqb T                                          (stage B: back substitution)
+//     Z^T  = dY^T Aqb' + dS B'^T                                          (R1)   Z = dL/dU after the solve
+//     dN = stril(Z U^T)  dAak = stril(Z V^T)  dAqb = tril(dY U^T)  dAqk = tril(dY V^T)   (mma.sync, 16x16)
+//     dQ~^T|dA~^T = S0^T [dY;Z]^T + B~^T [dAqb;dN]^T + K~^T [dAqk;dAak]^T  (P1)
+//     dB~^T|dK~^T = dS^T [U;V]^T  + A~^T [dN^T;dAak^T]^T + Q~^T [dAqb^T;dAqk^T]^T   (P2)
+//     dV^T        = dS K~^T + dY^T Aqk + Z^T Aak                           (P3)
+//     dS  += dY^T Q~ + Z^T A~ ;   dS^T += Q~^T dY + A~^T Z                  (R2)
+// then dq = dQ~ e^{G}, da = dA~ e^{G_{t-1}}, db = dB~ e^{-G}, dk = dK~ e^{-G} and, with
+//     g_t = dQ~.Q~ - dK~.K~ - dB~.B~ + (dA~.A~)_{t+1}  (+ sum_v dS.S at a window end),
+// dw_t = (-e^{w_t}) * sum_{s >= t in the window} g_s.   All M = 64 products put a channel / value index on
+// the tensor-memory lanes, so every gradient tile comes out as [channel][16 tokens] and the dw scan is
+// thread-local.
+//
+// One CTA per (batch, head), 21 warps:
+//   warps  0-3   group C: S0^T -> tensor memory, Z -> shared tiles, the four 16x16 gradient Grams (mma.sync),
+//                output epilogue (scaling, dw scan, bf16, coalesced stores), window-boundary rescale of dS
+//   warps  4-11  stage A: HBM loads (7 bf16 arrays + sa + checkpoint), decay scan, operand tiles
+//   warps 12-19  stage B (two groups on alternate chunks): forward Gram blocks, back substitution
+//   warp   20    MMA issuer
+#include "mma_tf32.cuh"
+#include "tc05.cuh"
+#include "wkv7_common.cuh"
+
+namespace rwkvtts {
+namespace tcbwd {
+using namespace tc05;
+
+constexpr int L = 16, WIN = 4, NS = 2;
+constexpr float kMinLogDecay = -1.35f;
+
+// canonical K-major tiles (floats): off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4
+constexpr int N32_LBO = 132, N16_LBO = 68, N_SBO = 32;   // [32|16 rows (tokens)][64 channels]
+constexpr int T_SBO = 36, T_LBO = 288;                   // [64 rows (channels)][16 tokens]
+constexpr int S32_LBO = 128, S16_LBO = 64, S_SBO = 32;   // [32|16 rows][16]
+
+struct Slot {
+    float UVn[16 * N32_LBO];      // rows 0-15 U (sa), 16-31 V          [.][value]
+    float DYZn[16 * N32_LBO];     // rows 0-15 dY, 16-31 Z (group C)     [.][value]
+    float Kn[16 * N16_LBO];       // K~ [s][key]
+    float Bpn[16 * N16_LBO];      // B' [s][key]                         (stage B)
+    float dYt[4 * T_LBO], Qt[4 * T_LBO], At[4 * T_LBO], Bt[4 * T_LBO], Kt[4 * T_LBO];   // [channel][token]
+    float Gt[4 * T_LBO];          // G (fp32, not an MMA operand), same layout
+    float AqbpT[4 * S16_LBO], AqkT[4 * S16_LBO], AakT[4 * S16_LBO];   // [n=s][k=t]          (stage B)
+    float Gs[kC];                 // G at the chunk start
+    float S0Ts[kC * 68];          // checkpoint S0^T [key][value], row stride 68
+};
+struct Smem {
+    Slot slot[NS];
+    float ZT[4 * T_LBO];          // Z^T [value][t]
+    float QB_N[4 * S32_LBO];      // rows 0-15 dAqb [t][s], 16-31 dN [t][s]
+    float QK_AK[4 * S32_LBO];     // rows 0-15 dAqk, 16-31 dAak
+    float NT_AKT[4 * S32_LBO];    // rows 0-15 dN^T [s][t], 16-31 dAak^T
+    float QBT_QKT[4 * S32_LBO];   // rows 0-15 dAqb^T, 16-31 dAqk^T
+    float Nn[2][L * 20], Aqbn[2][L * 20];   // stage B scratch: N and Aqb, natural [t][s], fp32
+    float wtot[2][8][kC];         // stage A scan partials
+    float wtotw[WIN][8][kC];      // stage A: per-chunk decay totals of the current window
+    float gst[WIN][kC];           // stage A: G at the start of each chunk of the current window
+    float elast[kC];              // group C: e^{G} at a window end
+    __align__(16) bf16 obuf[6][L][72];   // output staging [array][token][channel]
+    uint64_t full[NS], empty[NS], a_done[NS];
+    uint64_t s0t_ready, bar_z, c_done, out_ready;
+    uint32_t tmem_base;
+};
+
+struct Params {
+    int T, H;
+    const bf16 *w, *q, *k, *v, *a, *b, *dy;
+    const float *ckT, *sa;
+    const float *sT, *dsT;       // final state / its gradient (both or neither)
+    bf16 *dw, *dq, *dk, *dv, *da, *db;
+    float *ds0;                  // may be null
+};
+
+// tensor-memory columns
+constexpr uint32_t C_DS = 0, C_DST = 64, C_S0T = 128, C_Z = 256, C_OK = 272, C_OV = 336;
+
+__device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const void *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage A: tp in [0,256); token t = tp>>4, channels 4*k4 .. 4*k4+3
+// ---------------------------------------------------------------------------------------------
+struct Raw { uint2 x[7]; float4 u; };
+
+__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int tp, Raw &r) {
+    const int t = tp >> 4, k4 = tp & 15;
+    const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
+    r.x[0] = ldg_nc_v2(P.w + off); r.x[1] = ldg_nc_v2(P.q + off); r.x[2] = ldg_nc_v2(P.k + off);
+    r.x[3] = ldg_nc_v2(P.v + off); r.x[4] = ldg_nc_v2(P.a + off); r.x[5] = ldg_nc_v2(P.b + off);
+    r.x[6] = ldg_nc_v2(P.dy + off);
+    r.u = ldg_nc_f4(P.sa + off);
+}
+
+__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tp) {
+    const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
+    Raw raw, nxt;
+    load_raw(P, base, tok_stride, nC - 1, tp, raw);
+    for (int it = 0; it < nC; it++) {
+        const int c = nC - 1 - it, si = it % NS;
+        Slot &S = sm.slot[si];
+        if (c > 0) load_raw(P, base, tok_stride, c - 1, tp, nxt);
+        const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
+        if (win_last) {
+            // entering a window (from its end): G at the start of each of its chunks
+            const int c0 = (c / WIN) * WIN, nj = c - c0 + 1;
+            for (int j = 0; j < nj; j++) {
+                float f[4], s4[4];
+                unpack4(ldg_nc_v2(P.w + base + (size_t)((c0 + j) * L + t) * tok_stride + k4 * 4), f);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    s4[e] = fmaxf(-__expf(f[e]), kMinLogDecay);
+                    s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);
+                }
+                if (t & 1) st4(&sm.wtotw[j][wp][k4 * 4], s4[0], s4[1], s4[2], s4[3]);
+            }
+            bar_sync(1, 256);
+            if (tp < kC) {
+                float run = 0.f;
+                for (int j = 0; j < nj; j++) {
+                    sm.gst[j][tp] = run;
+#pragma unroll
+                    for (int ww = 0; ww < 8; ww++) run += sm.wtotw[j][ww][tp];
+                }
+            }
+            bar_sync(1, 256);
+        }
+        float lw[4], gg[4];
+        {
+            float f[4];
+            unpack4(raw.x[0], f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay); gg[j] = lw[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
+            if (t & 1) gg[j] += x;
+        }
+        float(&wt)[8][kC] = sm.wtot[it & 1];
+        if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
+        bar_sync(1, 256);
+        {
+            const float4 g0 = *reinterpret_cast<const float4 *>(&sm.gst[c % WIN][k4 * 4]);
+            gg[0] += g0.x; gg[1] += g0.y; gg[2] += g0.z; gg[3] += g0.w;
+        }
+#pragma unroll
+        for (int ww = 0; ww < 8; ww++) {
+            if (ww < wp) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(&wt[ww][k4 * 4]);
+                gg[0] += x0.x; gg[1] += x0.y; gg[2] += x0.z; gg[3] += x0.w;
+            }
+        }
+        if (it >= NS) mbar_wait(&sm.empty[si], ((it / NS) - 1) & 1);
+        {
+            float E[4], Ep[4], iE[4], f[4], o[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                E[j] = __expf(gg[j]);
+                Ep[j] = __expf(gg[j] - lw[j]);
+                iE[j] = __expf(-gg[j]);
+            }
+            // transposed tiles: row = channel 4*k4+j, column = token t
+            const int ot = (k4 >> 1) * T_SBO + (t >> 2) * T_LBO + (k4 & 1) * 16 + (t & 3);   // + 4*j
+            const int on32 = (t >> 3) * N_SBO + k4 * N32_LBO + (t & 7) * 4;                // 32-row tiles, row t
+            const int on16 = (t >> 3) * N_SBO + k4 * N16_LBO + (t & 7) * 4;
+            unpack4(raw.x[1], f);                                   // Q~
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Qt[ot + 4 * j] = tf32r(f[j] * E[j]);
+            unpack4(raw.x[2], f);                                   // K~
+#pragma unroll
+            for (int j = 0; j < 4; j++) { o[j] = tf32r(f[j] * iE[j]); S.Kt[ot + 4 * j] = o[j]; }
+            st4(&S.Kn[on16], o[0], o[1], o[2], o[3]);
+            unpack4(raw.x[3], f);                                   // V (exact in tf32)
+            st4(&S.UVn[on32 + 2 * N_SBO], f[0], f[1], f[2], f[3]);
+            unpack4(raw.x[4], f);                                   // A~
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.At[ot + 4 * j] = tf32r(f[j] * Ep[j]);
+            unpack4(raw.x[5], f);                                   // B~
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Bt[ot + 4 * j] = tf32r(f[j] * iE[j]);
+            unpack4(raw.x[6], f);                                   // dY (exact in tf32)
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.dYt[ot + 4 * j] = f[j];
+            st4(&S.DYZn[on32], f[0], f[1], f[2], f[3]);
+            st4(&S.UVn[on32], tf32r(raw.u.x), tf32r(raw.u.y), tf32r(raw.u.z), tf32r(raw.u.w));   // U
+#pragma unroll
+            for (int j = 0; j < 4; j++) S.Gt[ot + 4 * j] = gg[j];
+            if (t == 0) st4(&S.Gs[k4 * 4], gg[0] - lw[0], gg[1] - lw[1], gg[2] - lw[2], gg[3] - lw[3]);
+        }
+        {   // checkpoint S0^T of this chunk -> staging rows
+            const float *src = P.ckT + ((size_t)bh * nC + c) * (kC * kC);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int e = tp + 256 * i, r = e >> 4, c4 = (e & 15) * 4;
+                const float4 x = ldg_nc_f4(src + r * kC + c4);
+                st4(&S.S0Ts[r * 68 + c4], x.x, x.y, x.z, x.w);
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.a_done[si]);
+        mbar_arrive(&sm.full[si]);
+        raw = nxt;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage B: tp in [0,128), group grp handles iterations it = grp, grp+2, ...
+// ---------------------------------------------------------------------------------------------
+__device__ void stage_b(Smem &sm, int nC, int tp, int grp) {
+    const int wp = tp >> 5, lane = tp & 31, g = lane >> 2, tq = lane & 3;
+    float *Nn = sm.Nn[grp], *AQ = sm.Aqbn[grp];
+    for (int it = grp; it < nC; it += 2) {
+        const int si = it % NS;
+        Slot &S = sm.slot[si];
+        mbar_wait(&sm.a_done[si], (it / NS) & 1);
+        {   // forward Gram blocks from the transposed tiles: (A~|Q~)(B~|K~)^T, one 16x16 block per warp
+            const int rowsel = wp & 1, colsel = wp >> 1;
+            const float *Ar = rowsel ? S.Qt : S.At;
+            const float *Bc = colsel ? S.Kt : S.Bt;
+            float acc[2][4] = {};
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                uint32_t af[4], bfr[2];
+                const float *pa = Ar + kb * T_SBO + (g >> 2) * T_LBO + tq * 4 + (g & 3);
+                af[0] = __float_as_uint(pa[0]); af[1] = __float_as_uint(pa[2 * T_LBO]);
+                af[2] = __float_as_uint(pa[16]); af[3] = __float_as_uint(pa[2 * T_LBO + 16]);
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const float *pb = Bc + kb * T_SBO + (2 * nt + (g >> 2)) * T_LBO + tq * 4 + (g & 3);
+                    bfr[0] = __float_as_uint(pb[0]); bfr[1] = __float_as_uint(pb[16]);
+                    mma_tf32(acc[nt], af, bfr);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int col = 8 * nt + 2 * tq + e;      // s
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int row = g + 8 * hh;           // t
+                        float x = acc[nt][2 * hh + e];
+                        if (rowsel) {
+                            x = (col <= row) ? x : 0.f;
+                            if (colsel) S.AqkT[kmajor_off(col, row, S16_LBO, S_SBO)] = tf32r(x);
+                            else AQ[row * 20 + col] = x;
+                        } else {
+                            x = (col < row) ? x : 0.f;
+                            if (colsel) S.AakT[kmajor_off(col, row, S16_LBO, S_SBO)] = tf32r(x);
+                            else Nn[row * 20 + col] = x;
+                        }
+                    }
+                }
+        }
+        bar_sync(2 + grp, 128);
+        // [B' | Aqb'^T] = (I - N)^-T [B~ | Aqb^T]: back substitution, one column per thread
+        if (tp < kC + 16) {
+            float acc[L];
+            if (tp < kC) {
+                const float *pr = S.Bt + (tp >> 3) * T_SBO + (tp & 7) * 4;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(pr + q4 * T_LBO);
+                    acc[4 * q4] = x.x; acc[4 * q4 + 1] = x.y; acc[4 * q4 + 2] = x.z; acc[4 * q4 + 3] = x.w;
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < L; s++) acc[s] = AQ[(tp - kC) * 20 + s];
+            }
+#pragma unroll
+            for (int tt = L - 1; tt >= 1; tt--) {
+                const float x = acc[tt];
+#pragma unroll
+                for (int q4 = 0; q4 <= (tt - 1) / 4; q4++) {
+                    const float4 n4 = *reinterpret_cast<const float4 *>(&Nn[tt * 20 + 4 * q4]);
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        if (4 * q4 + e < tt) acc[4 * q4 + e] = fmaf(nn[e], x, acc[4 * q4 + e]);
+                }
+            }
+            if (tp < kC) {
+#pragma unroll
+                for (int s = 0; s < L; s++) S.Bpn[kmajor_off(s, tp, N16_LBO, N_SBO)] = tf32r(acc[s]);
+            } else {
+#pragma unroll
+                for (int s = 0; s < L; s++) S.AqbpT[kmajor_off(s, tp - kC, S16_LBO, S_SBO)] = tf32r(acc[s]);
+            }
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.full[si]);
+        bar_sync(2 + grp, 128);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MMA issuer
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t kadv(uint64_t d, int kk, int lbo_f) { return d + (uint64_t)((kk * 2 * lbo_f * 4) >> 4); }
+
+__device__ void mma_warp(Smem &sm, int nC) {
+    const uint32_t tb = sm.tmem_base;
+    constexpr uint32_t I16 = idesc_tf32(64, 16, false, false);
+    constexpr uint32_t I32 = idesc_tf32(64, 32, false, false);
+    constexpr uint32_t I64 = idesc_tf32(64, 64, false, false);
+    const uint64_t dZT = smem_desc(smem_u32(sm.ZT), T_LBO * 4, T_SBO * 4);
+    const uint64_t dQBN = smem_desc(smem_u32(sm.QB_N), S32_LBO * 4, S_SBO * 4);
+    const uint64_t dQKAK = smem_desc(smem_u32(sm.QK_AK), S32_LBO * 4, S_SBO * 4);
+    const uint64_t dNTAKT = smem_desc(smem_u32(sm.NT_AKT), S32_LBO * 4, S_SBO * 4);
+    const uint64_t dQBTQKT = smem_desc(smem_u32(sm.QBT_QKT), S32_LBO * 4, S_SBO * 4);
+    for (int it = 0; it < nC; it++) {
+        const int c = nC - 1 - it, si = it % NS;
+        const Slot &S = sm.slot[si];
+        const uint32_t s0t = tb + C_S0T + 64 * (it & 1);
+        const uint64_t dUV = smem_desc(smem_u32(S.UVn), N32_LBO * 4, N_SBO * 4);
+        const uint64_t dDYZ = smem_desc(smem_u32(S.DYZn), N32_LBO * 4, N_SBO * 4);
+        const uint64_t dKn = smem_desc(smem_u32(S.Kn), N16_LBO * 4, N_SBO * 4);
+        const uint64_t dBp = smem_desc(smem_u32(S.Bpn), N16_LBO * 4, N_SBO * 4);
+        const uint64_t dYt = smem_desc(smem_u32(S.dYt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dQt = smem_desc(smem_u32(S.Qt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dAt = smem_desc(smem_u32(S.At), T_LBO * 4, T_SBO * 4);
+        const uint64_t dBt = smem_desc(smem_u32(S.Bt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dKt = smem_desc(smem_u32(S.Kt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dAqbpT = smem_desc(smem_u32(S.AqbpT), S16_LBO * 4, S_SBO * 4);
+        const uint64_t dAqkT = smem_desc(smem_u32(S.AqkT), S16_LBO * 4, S_SBO * 4);
+        const uint64_t dAakT = smem_desc(smem_u32(S.AakT), S16_LBO * 4, S_SBO * 4);
+        mbar_wait(&sm.full[si], (it / NS) & 1);
+        // group C has finished with the previous chunk's tensor-memory results, has moved dS / dS^T into this
+        // window's frame if a boundary was crossed, and has put S0^T of this chunk into tensor memory
+        mbar_wait(&sm.s0t_ready, it & 1);
+        fence_after_sync();
+        if (elect_one()) {
+            // R1: Z^T = dY^T Aqb' + dS B'^T
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_Z, kadv(dYt, kk, T_LBO), kadv(dAqbpT, kk, S16_LBO), I16, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+                mma_tf32_ts(tb + C_Z, tb + C_DS + 8 * kk, kadv(dBp, kk, N16_LBO), I16, true);
+            mma_commit(&sm.bar_z);
+            // P3a: dV^T = dS K~^T ;  P2a: [dB~^T | dK~^T] = dS^T [U;V]^T     (dS, dS^T before this chunk's update)
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+                mma_tf32_ts(tb + C_OV, tb + C_DS + 8 * kk, kadv(dKn, kk, N16_LBO), I16, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+                mma_tf32_ts(tb + C_OK + 32, tb + C_DST + 8 * kk, kadv(dUV, kk, N32_LBO), I32, kk > 0);
+        }
+        __syncwarp();
+        mbar_wait(&sm.bar_z, it & 1);
+        fence_after_sync();
+        if (elect_one()) {
+            // R2 (dS): dS += dY^T Q~ + Z^T A~
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_DS, kadv(dYt, kk, T_LBO), kadv(dQt, kk, T_LBO), I64, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ts(tb + C_DS, tb + C_Z + 8 * kk, kadv(dAt, kk, T_LBO), I64, true);
+        }
+        __syncwarp();
+        mbar_wait(&sm.c_done, it & 1);            // group C: Z tiles and the gradient Gram tiles
+        fence_after_sync();
+        if (elect_one()) {
+            // R2 (dS^T): dS^T += Q~^T dY + A~^T Z
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_DST, kadv(dQt, kk, T_LBO), kadv(dYt, kk, T_LBO), I64, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_DST, kadv(dAt, kk, T_LBO), kadv(dZT, kk, T_LBO), I64, true);
+            // P1: [dQ~^T | dA~^T] = S0^T [dY;Z]^T + B~^T [dAqb;dN]^T + K~^T [dAqk;dAak]^T
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+                mma_tf32_ts(tb + C_OK, s0t + 8 * kk, kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_OK, kadv(dBt, kk, T_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_OK, kadv(dKt, kk, T_LBO), kadv(dQKAK, kk, S32_LBO), I32, true);
+            // P2b: [dB~^T | dK~^T] += A~^T [dN^T;dAak^T]^T + Q~^T [dAqb^T;dAqk^T]^T
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_OK + 32, kadv(dAt, kk, T_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_OK + 32, kadv(dQt, kk, T_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
+            // P3b: dV^T += dY^T Aqk + Z^T Aak
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ss(tb + C_OV, kadv(dYt, kk, T_LBO), kadv(dAqkT, kk, S16_LBO), I16, true);
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+                mma_tf32_ts(tb + C_OV, tb + C_Z + 8 * kk, kadv(dAakT, kk, S16_LBO), I16, true);
+            mma_commit(&sm.out_ready);
+        }
+        __syncwarp();
+        (void)c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// group C: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = rows 16q..16q+15
+// ---------------------------------------------------------------------------------------------
+__device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+    const int q = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    const bool act = lane < 16;
+    const int row = 16 * q + (lane & 15);
+    const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
+    float suffix = 0.f, carry_first = 0.f, gL = 0.f;     // per channel `row`
+    {   // dS, dS^T <- dsT (or 0); boundary term of the last window from sT
+        const bool have = P.dsT != nullptr && P.sT != nullptr;
+        const float *gs = have ? P.dsT + (size_t)bh * kC * kC : nullptr;
+        const float *st = have ? P.sT + (size_t)bh * kC * kC : nullptr;
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) {
+            float v[16], vt[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                v[i] = have ? gs[row * kC + 16 * cb + i] : 0.f;              // dS[row][.]
+                vt[i] = have ? gs[(16 * cb + i) * kC + row] : 0.f;           // dS^T[row][.] = dS[.][row]
+                if (have) gL = fmaf(vt[i], st[(16 * cb + i) * kC + row], gL);
+            }
+            tmem_st16(tb + C_DS + 16 * cb, v);
+            tmem_st16(tb + C_DST + 16 * cb, vt);
+        }
+        tmem_wait_st();
+    }
+    for (int it = 0; it < nC; it++) {
+        const int c = nC - 1 - it, si = it % NS;
+        Slot &S = sm.slot[si];
+        const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
+        mbar_wait(&sm.full[si], (it / NS) & 1);
+        if (win_last) {
+            // dS, dS^T arrive in the frame of the NEXT window (or true frame at the sequence end):
+            // move them into this window's frame, columns (keys) scaled by e^{G_last}
+            if (act) sm.elast[row] = __expf(S.Gt[(row >> 3) * T_SBO + 3 * T_LBO + (row & 7) * 4 + 3]);
+            bar_sync(4, 128);
+            const float er = sm.elast[row];
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float v[16];
+                tmem_ld16(tb + C_DS + 16 * cb, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] *= sm.elast[16 * cb + i];
+                tmem_st16(tb + C_DS + 16 * cb, v);
+                tmem_ld16(tb + C_DST + 16 * cb, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] *= er;
+                tmem_st16(tb + C_DST + 16 * cb, v);
+            }
+            suffix = 0.f; carry_first = 0.f;          // gL was computed when the boundary was reached
+        }
+        {   // S0^T of this chunk: staging rows -> tensor memory
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(&S.S0Ts[row * 68 + 16 * cb + 4 * i]);
+                    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+                }
+                tmem_st16(tb + C_S0T + 64 * (it & 1) + 16 * cb, v);
+            }
+        }
+        tmem_wait_st();
+        fence_before_sync();
+        mbar_arrive(&sm.s0t_ready);
+        // ---- Z^T -> shared tiles --------------------------------------------------------------
+        mbar_wait(&sm.bar_z, it & 1);
+        fence_after_sync();
+        {
+            float z[16];
+            tmem_ld16(tb + C_Z, z);
+            tmem_wait_ld();
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) z[i] = tf32r(z[i]);
+#pragma unroll
+                for (int i = 0; i < 16; i++) S.DYZn[kmajor_off(16 + i, row, N32_LBO, N_SBO)] = z[i];
+                float *pz = sm.ZT + (row >> 3) * T_SBO + (row & 7) * 4;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) st4(pz + q4 * T_LBO, z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+            }
+        }
+        bar_sync(4, 128);
+        {   // gradient Gram blocks over the value index: warp 0 dAqb=tril(dY U^T), 1 dN=stril(Z U^T),
+            // 2 dAqk=tril(dY V^T), 3 dAak=stril(Z V^T)
+            const int ar = (q & 1) * 16, br = (q >> 1) * 16;
+            float acc[2][4] = {};
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                uint32_t af[4], bfr[2];
+                const float *pa = S.DYZn + (ar >> 3) * N_SBO + 2 * kb * N32_LBO + g * 4 + tq;
+                af[0] = __float_as_uint(pa[0]); af[1] = __float_as_uint(pa[N_SBO]);
+                af[2] = __float_as_uint(pa[N32_LBO]); af[3] = __float_as_uint(pa[N32_LBO + N_SBO]);
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const float *pb = S.UVn + ((br >> 3) + nt) * N_SBO + 2 * kb * N32_LBO + g * 4 + tq;
+                    bfr[0] = __float_as_uint(pb[0]); bfr[1] = __float_as_uint(pb[N32_LBO]);
+                    mma_tf32(acc[nt], af, bfr);
+                }
+            }
+            float *nat = (q < 2) ? sm.QB_N : sm.QK_AK;            // [n=t][k=s], rows +16 for the Z grams
+            float *trn = (q == 0 || q == 2) ? sm.QBT_QKT : sm.NT_AKT;   // [n=s][k=t]
+            const int nrow = (q & 1) * 16, trow = (q >> 1) * 16;
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int col = 8 * nt + 2 * tq + e;      // s
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int r = g + 8 * hh;             // t
+                        float x = acc[nt][2 * hh + e];
+                        x = ((q & 1) ? (col < r) : (col <= r)) ? tf32r(x) : 0.f;
+                        nat[kmajor_off(nrow + r, col, S32_LBO, S_SBO)] = x;
+                        trn[kmajor_off(trow + col, r, S32_LBO, S_SBO)] = x;
+                    }
+                }
+        }
+        fence_proxy_async();
+        mbar_arrive(&sm.c_done);
+        // ---- outputs --------------------------------------------------------------------------
+        mbar_wait(&sm.out_ready, it & 1);
+        fence_after_sync();
+        {
+            float G[16], lwv[16];
+            {
+                const float *pg = S.Gt + (row >> 3) * T_SBO + (row & 7) * 4;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(pg + q4 * T_LBO);
+                    G[4 * q4] = x.x; G[4 * q4 + 1] = x.y; G[4 * q4 + 2] = x.z; G[4 * q4 + 3] = x.w;
+                }
+                const float gs = S.Gs[row];
+                lwv[0] = G[0] - gs;
+#pragma unroll
+                for (int i = 1; i < 16; i++) lwv[i] = G[i] - G[i - 1];
+            }
+            auto tile_row = [&](const float *T_, float (&o)[16]) {
+                const float *pr = T_ + (row >> 3) * T_SBO + (row & 7) * 4;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(pr + q4 * T_LBO);
+                    o[4 * q4] = x.x; o[4 * q4 + 1] = x.y; o[4 * q4 + 2] = x.z; o[4 * q4 + 3] = x.w;
+                }
+            };
+            float gsum[16], acc_[16], op[16];
+            // dQ~ -> dq
+            tmem_ld16(tb + C_OK, acc_); tmem_wait_ld();
+            tile_row(S.Qt, op);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                gsum[i] = acc_[i] * op[i];
+                if (act) sm.obuf[1][i][row] = __float2bfloat16_rn(acc_[i] * __expf(G[i]));
+            }
+            // dK~ -> dk
+            tmem_ld16(tb + C_OK + 48, acc_); tmem_wait_ld();
+            tile_row(S.Kt, op);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                gsum[i] = fmaf(-acc_[i], op[i], gsum[i]);
+                if (act) sm.obuf[2][i][row] = __float2bfloat16_rn(acc_[i] * __expf(-G[i]));
+            }
+            // dB~ -> db
+            tmem_ld16(tb + C_OK + 32, acc_); tmem_wait_ld();
+            tile_row(S.Bt, op);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                gsum[i] = fmaf(-acc_[i], op[i], gsum[i]);
+                if (act) sm.obuf[5][i][row] = __float2bfloat16_rn(acc_[i] * __expf(-G[i]));
+            }
+            // dA~ -> da ; (dA~.A~)_{t+1} joins g_t
+            tmem_ld16(tb + C_OK + 16, acc_); tmem_wait_ld();
+            tile_row(S.At, op);
+            float aa0 = acc_[0] * op[0];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (i > 0) gsum[i - 1] = fmaf(acc_[i], op[i], gsum[i - 1]);
+                if (act) sm.obuf[4][i][row] = __float2bfloat16_rn(acc_[i] * __expf(G[i] - lwv[i]));
+            }
+            gsum[15] += carry_first + (win_last ? gL : 0.f);
+            carry_first = aa0;
+            // dw: suffix sum over the window (chunks arrive last to first)
+#pragma unroll
+            for (int i = 15; i >= 0; i--) {
+                suffix += gsum[i];
+                if (act) sm.obuf[0][i][row] = __float2bfloat16_rn(suffix * lwv[i]);
+            }
+            // dV
+            tmem_ld16(tb + C_OV, acc_); tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                if (act) sm.obuf[3][i][row] = __float2bfloat16_rn(acc_[i]);
+        }
+        // window boundary below this chunk: boundary term for the previous window's last token
+        if (c % WIN == 0 && c > 0) {
+            gL = 0.f;
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float a_[16], b_[16];
+                tmem_ld16(tb + C_DST + 16 * cb, a_);
+                tmem_ld16(tb + C_S0T + 64 * (it & 1) + 16 * cb, b_);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; i++) gL = fmaf(a_[i], b_[i], gL);
+            }
+        }
+        if (c == 0 && P.ds0 != nullptr) {
+            float *dst = P.ds0 + (size_t)bh * kC * kC + row * kC;
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float v[16];
+                tmem_ld16(tb + C_DS + 16 * cb, v);
+                tmem_wait_ld();
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        *reinterpret_cast<float4 *>(dst + 16 * cb + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+        }
+        fence_before_sync();
+        mbar_arrive(&sm.empty[si]);
+        bar_sync(4, 128);
+        {   // six gradient tiles [token][channel] bf16 -> 128-byte rows
+            bf16 *dst[6] = {P.dw, P.dq, P.dk, P.dv, P.da, P.db};
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const int e = tid + 128 * i, arr = e >> 7, tok = (e >> 3) & 15, part = e & 7;
+                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.obuf[arr][tok][part * 8]);
+                *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
+            }
+        }
+        bar_sync(4, 128);
+    }
+}
+
+constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1);
+
+__global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nC = P.T / L;
+    const size_t tok_stride = (size_t)P.H * kC;
+    const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
+
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) { mbar_init(&sm.full[i], 256 + 128); mbar_init(&sm.empty[i], 128); mbar_init(&sm.a_done[i], 256); }
+        mbar_init(&sm.s0t_ready, 128); mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 128);
+        mbar_init(&sm.out_ready, 1);
+        mbar_fence_init();
+    }
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    if (warp < 4) group_c(P, sm, base, tok_stride, bh, nC, tid);
+    else if (warp < 12) stage_a(P, sm, base, tok_stride, bh, nC, tid - 128);
+    else if (warp < 16) stage_b(sm, nC, tid - 384, 0);
+    else if (warp < 20) stage_b(sm, nC, tid - 512, 1);
+    else mma_warp(sm, nC);
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace tcbwd
+
+cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                          const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
+                          const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
+                          void *db, float *ds0, cudaStream_t st) {
+    using namespace tcbwd;
+    static_assert(sizeof(Smem) <= 232448, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(wkv7_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
+             (const bf16 *)b, (const bf16 *)dy, ckT, sa, sT, dsT, (bf16 *)dw, (bf16 *)dq, (bf16 *)dk, (bf16 *)dv,
+             (bf16 *)da, (bf16 *)db, ds0};
+    count_launch();
+    wkv7_tc_bwd_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace rwkvtts

@@ -13,8 +13,9 @@
 //         phase 1:  [U^T | Y^T] = S^ [W~ | Q~]^T + V^T [M1 | Aqk]^T                  (tcgen05, N = 32)
 //         phase 2:  S^ += U^T B~ + V^T K~ ;   Y^T += U^T Aqb^T                       (tcgen05, N = 64 / 16)
 // (U_t = S_{t-1} a_t is the reference's `sa`).  At a window end S^ is multiplied by e^{G_64}
-// (tensor memory -> registers -> tensor memory) and written to the checkpoint tensor for the
-// backward kernel.  |G| <= 64 * 1.35 stays inside the fp32 exponent range; log-decays below -1.35
+// (tensor memory -> registers -> tensor memory).  The training variant also writes, per chunk, the
+// TRANSPOSED state at the chunk start (window frame) and `sa` for the chunked backward
+// (wkv7_tc_bwd.cu), into the caller's scratch tensors `s` / `sa` (reference sizes).  |G| <= 64 * 1.35 stays inside the fp32 exponent range; log-decays below -1.35
 // per step (decay < 0.26; the model's range is (-0.6065, 0), rwkv_s2s_single_ffn.py:172) are clamped.
 //
 // tcgen05 facts this kernel relies on (measured with tests/csrc/umma_probe.cu on a B200):
@@ -41,7 +42,7 @@ using namespace tc05;
 
 constexpr int L = 16;        // chunk length
 constexpr int WIN = 4;       // chunks per window
-constexpr int NSLOT = 6;     // operand slots in flight
+constexpr int NSLOT = 5;     // operand slots in flight
 constexpr int NNAT = 3;      // stage A -> stage B hand-off buffers
 constexpr int LDN = 68;      // row stride of the natural [token][channel] tiles
 constexpr float kMinLogDecay = -1.35f;
@@ -67,9 +68,10 @@ struct Smem {
     float NT[2][L * 20], Aak[2][L * 20];   // per stage-B group: N^T and Aak, fp32
     float wtot[2][8][kC];                  // stage A scan partials, double buffered
     __align__(16) bf16 ybuf[2][L][72];     // epilogue: Y tile [token][value], double buffered
+    __align__(16) float stg[kC * 68];      // training: transposed state tile [key][value] on its way to HBM
     float DLw[4][kC];                      // e^{G} at the end of a window (ring of 4 windows)
     uint64_t empty[NSLOT], full[NSLOT], a_done[NNAT], nat_empty[NNAT];
-    uint64_t p_done, y_ready[2], y_free[2], win_scaled;
+    uint64_t p_done, y_ready[2], y_free[2], win_scaled, s_free;
     uint32_t tmem_base;
 };
 
@@ -77,7 +79,9 @@ struct Params {
     int T, H;
     const bf16 *w, *q, *k, *v, *a, *b;
     bf16 *y;
-    float *ckpt;         // state at the start of every window, [B*H][ceil(T/64)][64][64]; may be null
+    float *ckT;          // training: TRANSPOSED state [key][value] at the start of every chunk, in the frame of
+                         // the chunk's window, [B*H][T/16][64][64]; null for the snapshot-free forward
+    float *sa;           // training: U_t = S_{t-1} a_t, fp32 [B,T,H,64]
     const float *s0;     // may be null
     float *sT;           // may be null
     long long *dbg;      // phase-cycle counters (profiling builds only), may be null
@@ -315,6 +319,7 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp, int grp) {
 // ---------------------------------------------------------------------------------------------
 // MMA issuer (one warp)
 // ---------------------------------------------------------------------------------------------
+template <bool kTrain>
 __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
     long long *P_dbg = (threadIdx.x & 31) == 0 ? P.dbg : nullptr; (void)P_dbg;
     const uint32_t tb = sm.tmem_base;
@@ -354,6 +359,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         __syncwarp();
         mbar_wait(&sm.p_done, ph); ph ^= 1;
         TICK(tm4);
+        if (kTrain && c > 0 && c % WIN != 0) mbar_wait(&sm.s_free, (c - 1) & 1);   // epilogue has read S^ of chunk c-1
         fence_after_sync();
         if (elect_one()) {
             // phase 2: S^ += U^T B~ + V^T K~ ;  Y^T += U^T Aqb^T
@@ -380,15 +386,30 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 // ---------------------------------------------------------------------------------------------
 // epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = value rows 16q..16q+15
 // ---------------------------------------------------------------------------------------------
+template <bool kTrain>
 __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
     long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int q = tid >> 5, lane = tid & 31;
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
-    const int nW = (nC + WIN - 1) / WIN;
-    float *ck = P.ckpt != nullptr ? P.ckpt + (size_t)bh * nW * (kC * kC) : nullptr;
-    {   // initial state -> tensor memory and checkpoint 0
+    float *ck = kTrain ? P.ckT + (size_t)bh * nC * (kC * kC) : nullptr;
+    // stage one 16-column block of this thread's state row, transposed, for the checkpoint
+    auto stage_T = [&](const float (&v)[16], int cb) {
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) sm.stg[(16 * cb + i) * 68 + row] = v[i];
+        }
+    };
+    // after a 128-thread barrier: [key][value] rows, 256 bytes each, coalesced
+    auto flush_T = [&](float *dst) {
+        const int k = tid >> 1, half = (tid & 1) * 32;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            *reinterpret_cast<float4 *>(dst + k * kC + half + 4 * i) =
+                *reinterpret_cast<const float4 *>(&sm.stg[k * 68 + half + 4 * i]);
+    };
+    {   // initial state -> tensor memory (and checkpoint 0)
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
             float v[16];
@@ -403,61 +424,75 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 }
             }
             tmem_st16(tb + 16 * cb, v);
-            if (act && ck != nullptr) {
-                float4 *dp = reinterpret_cast<float4 *>(ck + row * kC + 16 * cb);
-#pragma unroll
-                for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
+            if (kTrain) stage_T(v, cb);
         }
         tmem_wait_st();
         fence_before_sync();
         mbar_arrive(&sm.win_scaled);
+        if (kTrain) {
+            bar_sync(4, 128);
+            flush_T(ck);
+            bar_sync(4, 128);
+        }
     }
     for (int c = 0; c < nC; c++) {
         const int u = c & 1;
-        const bool win_end = (c % WIN == WIN - 1) || (c == nC - 1);
+        const bool last = (c == nC - 1);
+        const bool win_end = (c % WIN == WIN - 1) || last;
         TICK(te0);
         mbar_wait(&sm.y_ready[u], (c >> 1) & 1);
         TICK(te1);
         fence_after_sync();
-        float yv[16];
+        float yv[16], uv[16];
         tmem_ld16(tb + 64 + 32 * u + 16, yv);
+        if (kTrain) tmem_ld16(tb + 64 + 32 * u, uv);
         tmem_wait_ld();
-        if (win_end) {
-            const int w = c / WIN;
-            const float *dl = sm.DLw[w & 3];
-            const bool last = (c == nC - 1);
-            float *dst = last ? (P.sT != nullptr ? P.sT + (size_t)bh * kC * kC : nullptr)
-                              : (ck != nullptr ? ck + (size_t)(w + 1) * (kC * kC) : nullptr);
+        if (win_end || kTrain) {
+            // state after this chunk; at a window end it is rescaled (frame origin moves to the next window)
+            const float *dl = sm.DLw[(c / WIN) & 3];
+            float *dsT = (last && P.sT != nullptr) ? P.sT + (size_t)bh * kC * kC + row * kC : nullptr;
 #pragma unroll
             for (int cb = 0; cb < 4; cb++) {
                 float v[16];
                 tmem_ld16(tb + 16 * cb, v);
                 tmem_wait_ld();
+                if (win_end) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] *= dl[16 * cb + i];
-                if (!last) tmem_st16(tb + 16 * cb, v);
-                if (act && dst != nullptr) {
-                    float4 *dp = reinterpret_cast<float4 *>(dst + row * kC + 16 * cb);
+                    for (int i = 0; i < 16; i++) v[i] *= dl[16 * cb + i];
+                    if (!last) tmem_st16(tb + 16 * cb, v);
+                }
+                if (kTrain && !last) stage_T(v, cb);
+                if (act && dsT != nullptr) {
+                    float4 *dp = reinterpret_cast<float4 *>(dsT + 16 * cb);
 #pragma unroll
                     for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-            tmem_wait_st();
+            if (win_end) tmem_wait_st();
         }
         fence_before_sync();
         mbar_arrive(&sm.y_free[u]);
         if (win_end) mbar_arrive(&sm.win_scaled);
+        if (kTrain) mbar_arrive(&sm.s_free);
         {   // Y tile: [value lanes][16 tokens] -> shared [token][value] bf16 -> 128-byte rows to HBM
             bf16(&yb)[L][72] = sm.ybuf[u];
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) yb[j][row] = __float2bfloat16_rn(yv[j]);
+                if (kTrain) {
+                    float *sap = P.sa + base + (size_t)(c * L) * tok_stride + row;
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sap[(size_t)j * tok_stride] = uv[j];
+                }
             }
             bar_sync(4, 128);
             const int tok = tid >> 3, part = tid & 7;
             const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
             *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
+            if (kTrain && !last) {
+                flush_T(ck + (size_t)(c + 1) * (kC * kC));
+                bar_sync(4, 128);
+            }
         }
         TICK(te2); ACC(13, te0, te1); ACC(14, te1, te2);
     }
@@ -465,6 +500,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
 
 constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1);
 
+template <bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
@@ -479,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
         for (int i = 0; i < NNAT; i++) { mbar_init(&sm.a_done[i], 256); mbar_init(&sm.nat_empty[i], 128); }
         mbar_init(&sm.p_done, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 128); }
-        mbar_init(&sm.win_scaled, 128);
+        mbar_init(&sm.win_scaled, 128); mbar_init(&sm.s_free, 128);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 128);
@@ -487,11 +523,11 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
     __syncthreads();
     fence_after_sync();
 
-    if (warp < 4) epilogue(P, sm, base, tok_stride, bh, nC, tid);
+    if (warp < 4) epilogue<kTrain>(P, sm, base, tok_stride, bh, nC, tid);
     else if (warp < 12) stage_a(P, sm, base, tok_stride, nC, tid - 128);
     else if (warp < 16) stage_b(P, sm, nC, tid - 384, 0);
     else if (warp < 20) stage_b(P, sm, nC, tid - 512, 1);
-    else mma_warp(P, sm, nC);
+    else mma_warp<kTrain>(P, sm, nC);
 
     fence_before_sync();
     __syncthreads();
@@ -502,23 +538,27 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
 
 long long *g_tc_dbg = nullptr;   // set by the profiling harness only
 
-size_t tc_fwd_ckpt_floats(int B, int T, int H) {
-    const int nC = T / tcfwd::L, nW = (nC + tcfwd::WIN - 1) / tcfwd::WIN;
-    return (size_t)B * H * nW * kC * kC;
-}
-
+// ckT == nullptr: snapshot-free forward.  Otherwise the training forward: per-chunk transposed state
+// checkpoints (same size as the reference's `s`) and `sa`, consumed by wkv7_tc_bwd.cu.
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                          const void *a, const void *b, void *y, float *ckpt, const float *s0, float *sT,
+                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
                           cudaStream_t st) {
     using namespace tcfwd;
     static_assert(sizeof(Smem) <= 232448, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(Smem));
-    if (e != cudaSuccess) return e;
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
-             (const bf16 *)b, (bf16 *)y, ckpt, s0, sT, g_tc_dbg};
+             (const bf16 *)b, (bf16 *)y, ckT, sa, s0, sT, g_tc_dbg};
     count_launch();
-    wkv7_tc_fwd_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    if (ckT != nullptr) {
+        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        wkv7_tc_fwd_kernel<true><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        wkv7_tc_fwd_kernel<false><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    }
     return cudaGetLastError();
 }
 

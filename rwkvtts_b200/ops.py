@@ -63,12 +63,12 @@ def wkv7_forward_infer_(w, q, k, v, z, a, y, s0=None, sT=None):
     _lib.check(rc, "rwkvtts_wkv7_forward_infer")
 
 
-def wkv7_backward_(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0=None, dsT=None, ds0=None):
-    _need_cuda(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0, dsT, ds0)
+def wkv7_backward_(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0=None, dsT=None, ds0=None, sT=None):
+    _need_cuda(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0, dsT, ds0, sT)
     B, T, H, _ = w.shape
     with torch.cuda.device(w.device):
         rc = _lib.lib().rwkvtts_wkv7_backward_ex(B, T, H, _ptr(w), _ptr(q), _ptr(k), _ptr(v), _ptr(z), _ptr(a),
-                                                 _ptr(dy), _ptr(s), _ptr(sa), _ptr(s0), _ptr(dsT), _ptr(dw),
+                                                 _ptr(dy), _ptr(s), _ptr(sa), _ptr(s0), _ptr(sT), _ptr(dsT), _ptr(dw),
                                                  _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dz), _ptr(da), _ptr(ds0),
                                                  _stream())
     _lib.check(rc, "rwkvtts_wkv7_backward")
@@ -209,16 +209,16 @@ class _Wkv7WithState(torch.autograd.Function):
         s = torch.empty(B, H, T // CHUNK_LEN, C, C, dtype=torch.float32, device=w.device)
         sa = torch.empty(B, T, H, C, dtype=torch.float32, device=w.device)
         wkv7_forward_(w, q, k, v, a, b, y, s, sa, s0=s0, sT=sT)
-        ctx.save_for_backward(w, q, k, v, a, b, s, sa, s0)
+        ctx.save_for_backward(w, q, k, v, a, b, s, sa, s0, sT)
         return y, sT
 
     @staticmethod
     def backward(ctx, dy, dsT):
-        w, q, k, v, a, b, s, sa, s0 = ctx.saved_tensors
+        w, q, k, v, a, b, s, sa, s0, sT = ctx.saved_tensors
         grads = [torch.empty_like(x) for x in (w, q, k, v, a, b)]
-        ds0 = torch.empty_like(dsT) if s0 is not None else None
+        ds0 = torch.empty_like(sT) if s0 is not None else None
         wkv7_backward_(w, q, k, v, a, b, dy.contiguous(), s, sa, *grads, s0=s0,
-                       dsT=dsT.contiguous() if dsT is not None else None, ds0=ds0)
+                       dsT=dsT.contiguous() if dsT is not None else None, ds0=ds0, sT=sT.detach())
         return (*grads, ds0)
 
 

@@ -22,6 +22,15 @@ def R():
     return R
 
 
+@pytest.fixture(params=[0, 1], ids=["scan", "tcgen05"])
+def impl(R, request):
+    L = R._lib.lib()
+    prev = L.rwkvtts_get_impl()
+    assert L.rwkvtts_set_impl(request.param) == 0
+    yield R
+    L.rwkvtts_set_impl(prev)
+
+
 def _dev(x):
     return {n: t.cuda() for n, t in x.items()}
 
@@ -32,8 +41,9 @@ def _check(name, got, ref, tol=TOL):
     return exc
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 512, 12), (1, 16, 1), (3, 80, 2), (1, 1024, 4)])
-def test_forward_backward_vs_oracle(R, B, T, H):
+@pytest.mark.parametrize("B,T,H", [(2, 512, 12), (1, 16, 1), (3, 80, 2), (1, 1024, 4), (1, 208, 2)])
+def test_forward_backward_vs_oracle(impl, B, T, H):
+    R = impl
     x = O.make_inputs(B, T, H, seed=B * 1000 + T)
     d = _dev(x)
     leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
@@ -57,7 +67,8 @@ def test_run_cuda_rwkv7g_entry(R):
     _check("y", y.view(2, 64, 3, 64), y64)
 
 
-def test_initial_and_final_state(R):
+def test_initial_and_final_state(impl):
+    R = impl
     x = O.make_inputs(2, 96, 2, seed=9)
     d = _dev(x)
     s0 = torch.randn(2, 2, 64, 64) * 0.1
@@ -168,16 +179,7 @@ def test_full_size_properties(R):
 # ---------------------------------------------------------------------------------------------
 # snapshot-free forward (rwkvtts_wkv7_forward_infer): 1 = chunked tcgen05 kernel (default), 0 = scan
 # ---------------------------------------------------------------------------------------------
-@pytest.fixture(params=[0, 1], ids=["scan", "tcgen05"])
-def impl(R, request):
-    L = R._lib.lib()
-    prev = L.rwkvtts_get_impl()
-    assert L.rwkvtts_set_impl(request.param) == 0
-    yield R
-    L.rwkvtts_set_impl(prev)
-
-
-def test_default_infer_forward_is_tcgen05(R):
+def test_default_family_is_tcgen05(R):
     assert R._lib.lib().rwkvtts_get_impl() == 1
 
 
