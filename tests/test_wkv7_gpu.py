@@ -79,11 +79,13 @@ def test_initial_and_final_state(impl):
     torch.autograd.backward([y, sT], [d["dy"], dsT.cuda()])
     y64, sT64 = O.wkv7_forward(*[x[n] for n in ORDER], s0=s0)
     _check("y", y, y64)
-    assert O.rel_l2(sT, sT64) < 1e-5
+    # fp32 states: exact recurrence for the scan family, tf32 tensor-core operands for the tcgen05 family
+    tol = 1e-3 if R._lib.lib().rwkvtts_get_impl() == 1 else 1e-5
+    assert O.rel_l2(sT, sT64) < tol
     g64 = O.wkv7_backward(*[x[n] for n in ORDER], x["dy"], s0=s0, dsT=dsT)
     for n, leaf, g in zip(ORDER, leaves, g64[:6]):
         _check("d" + n, leaf.grad, g)
-    assert O.rel_l2(s0d.grad, g64[6]) < 1e-4
+    assert O.rel_l2(s0d.grad, g64[6]) < 10 * tol
 
 
 @pytest.mark.parametrize("B,T,H", [(1, 7, 2), (4, 1, 3), (32, 1, 16), (2, 45, 12)])
