@@ -17,11 +17,10 @@
 
 namespace rwkvtts {
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round to nearest (ties away) at bit 13 = cvt.rna.tf32.f32 for finite inputs (the cvt itself expands to ~5
+// instructions with its NaN/Inf handling).  The low bits are cleared although the tensor cores ignore them: the
+// CUDA cores read the same tiles (dw = sum of products with heavy cancellation) and must see the same values.
+__device__ __forceinline__ uint32_t f2tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ float tf32r(float x) { return __uint_as_float(f2tf32(x)); }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {

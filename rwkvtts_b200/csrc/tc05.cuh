@@ -123,6 +123,14 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// one arrival per warp: every arrival wakes all warps suspended on the barrier (they re-check the phase and go
+// back to sleep, 4 instructions each time), so per-thread arrivals on a 256-count barrier cost the waiters ~75
+// wake-ups per hand-off (measured with ncu: 17-40 % of all issued instructions).  Writers fence (proxy / tcgen05)
+// themselves before calling this; __syncwarp orders their writes before lane 0's release-arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t *bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires;
 // without a hint the default limit is short and 20+ waiting warps burn a third of the issue slots
 // re-polling (measured with ncu on the backward kernel).

@@ -258,8 +258,8 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
         }
         cp_async_wait<0>();
         fence_proxy_async();
-        mbar_arrive(&sm.a_done[si]);
-        mbar_arrive(&sm.full[si]);
+        mbar_arrive_warp(&sm.a_done[si]);
+        mbar_arrive_warp(&sm.full[si]);
         TICK(ta3); ACC(0, ta0, ta1); ACC(1, ta1, ta2); ACC(2, ta2, ta3);
     }
 }
@@ -352,7 +352,7 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp, int grp) {
             }
         }
         fence_proxy_async();
-        mbar_arrive(&sm.full[si]);
+        mbar_arrive_warp(&sm.full[si]);
         bar_sync(2 + grp, 128);
         TICK(tb2); ACC(3, tb0, tb1); ACC(4, tb1, tb2);
     }
@@ -551,7 +551,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&sm.s0t_ready);
+        mbar_arrive_warp(&sm.s0t_ready);
         TICK(tc2);
         // ---- Z^T -> shared tiles (tokens 8hf..8hf+7) ---------------------------------------------
         mbar_wait(&sm.bar_z, it & 1);
@@ -603,7 +603,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
         }
         fence_proxy_async();
-        mbar_arrive(&sm.c_done);
+        mbar_arrive_warp(&sm.c_done);
         TICK(tc4);
         // ---- outputs: this warp's 8 tokens (hf = 1 is later in time and feeds hf = 0) -------------
         mbar_wait(&sm.out_ready, it & 1);
@@ -728,7 +728,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
         }
         fence_before_sync();
-        mbar_arrive(&sm.empty[si]);
+        mbar_arrive_warp(&sm.empty[si]);
         bar_sync(4, 256);
         {   // six gradient tiles [token][channel] bf16 -> 128-byte rows
             bf16 *dst[6] = {P.dw, P.dq, P.dk, P.dv, P.da, P.db};
@@ -756,8 +756,8 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
     const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
 
     if (tid == 0) {
-        for (int i = 0; i < NS; i++) { mbar_init(&sm.full[i], 256 + 128); mbar_init(&sm.empty[i], 256); mbar_init(&sm.a_done[i], 256); }
-        mbar_init(&sm.s0t_ready, 256); mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 256);
+        for (int i = 0; i < NS; i++) { mbar_init(&sm.full[i], 8 + 4); mbar_init(&sm.empty[i], 8); mbar_init(&sm.a_done[i], 8); }
+        mbar_init(&sm.s0t_ready, 8); mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 8);
         mbar_init(&sm.out_ready, 1);
         mbar_fence_init();
     }

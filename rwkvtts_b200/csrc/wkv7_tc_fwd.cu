@@ -46,6 +46,7 @@ constexpr int NSLOT = 5;     // operand slots in flight
 constexpr int NNAT = 3;      // stage A -> stage B hand-off buffers
 constexpr int LDN = 68;      // row stride of the natural [token][channel] tiles
 constexpr float kMinLogDecay = -1.35f;
+constexpr float kLog2e = 1.4426950408889634f;   // decays are accumulated as log2 (ex2.approx needs no pre-scale)
 
 // canonical K-major tiles, strides in floats (see tc05.cuh: off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4)
 constexpr int WQ_LBO = 132, WQ_SBO = 32;     // [32 rows: 0-15 W~ tokens, 16-31 Q~ tokens][64 channels]
@@ -142,7 +143,10 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             float f[4];
             unpack4(raw[0], f);
 #pragma unroll
-            for (int j = 0; j < 4; j++) { lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay); gg[j] = lw[j]; }
+            for (int j = 0; j < 4; j++) {   // log2 of the decay: -e^w log2(e), clamped
+                lw[j] = fmaxf(-kLog2e * ex2f(f[j] * kLog2e), kMinLogDecay * kLog2e);
+                gg[j] = lw[j];
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) {   // inclusive scan over the 2 tokens of this warp (lane = (t&1)*16 + k4)
@@ -179,9 +183,9 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             float D[4], Dp[4], iD[4], f[4], o[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                D[j] = __expf(gg[j]);
-                Dp[j] = __expf(gg[j] - lw[j]);
-                iD[j] = __expf(-gg[j]);
+                D[j] = ex2f(gg[j]);
+                Dp[j] = ex2f(gg[j] - lw[j]);
+                iD[j] = ex2f(-gg[j]);
             }
             const int on = t * LDN + k4 * 4;
             // Q~: natural + canonical rows 16..31 of WQ
@@ -221,7 +225,7 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             if (win_end && t == L - 1) st4(&sm.DLw[(c / WIN) & 3][k4 * 4], D[0], D[1], D[2], D[3]);
         }
         fence_proxy_async();
-        mbar_arrive(&sm.a_done[ni]);
+        mbar_arrive_warp(&sm.a_done[ni]);
 #pragma unroll
         for (int i = 0; i < 6; i++) { raw[i] = nxt[i]; nxt[i] = nx2[i]; }
         TICK(ta4); ACC(0, ta0, ta1); ACC(1, ta1, ta2); ACC(2, ta2, ta3); ACC(3, ta3, ta4);
@@ -308,8 +312,8 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp, int grp) {
             }
         }
         fence_proxy_async();
-        mbar_arrive(&sm.full[si]);
-        mbar_arrive(&sm.nat_empty[ni]);
+        mbar_arrive_warp(&sm.full[si]);
+        mbar_arrive_warp(&sm.nat_empty[ni]);
         TICK(tb3);
         bar_sync(2 + grp, 128);     // NT / Aak are reused by the next chunk of this group
         TICK(tb4); ACC(4, tb0, tb1); ACC(5, tb1, tb2); ACC(6, tb2, tb3); ACC(7, tb3, tb4);
@@ -428,7 +432,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
         }
         tmem_wait_st();
         fence_before_sync();
-        mbar_arrive(&sm.win_scaled);
+        mbar_arrive_warp(&sm.win_scaled);
         if (kTrain) {
             bar_sync(4, 128);
             flush_T(ck);
@@ -471,9 +475,9 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
             if (win_end) tmem_wait_st();
         }
         fence_before_sync();
-        mbar_arrive(&sm.y_free[u]);
-        if (win_end) mbar_arrive(&sm.win_scaled);
-        if (kTrain) mbar_arrive(&sm.s_free);
+        mbar_arrive_warp(&sm.y_free[u]);
+        if (win_end) mbar_arrive_warp(&sm.win_scaled);
+        if (kTrain) mbar_arrive_warp(&sm.s_free);
         {   // Y tile: [value lanes][16 tokens] -> shared [token][value] bf16 -> 128-byte rows to HBM
             bf16(&yb)[L][72] = sm.ybuf[u];
             if (act) {
@@ -511,11 +515,11 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
     const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
 
     if (tid == 0) {
-        for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.empty[i], 1); mbar_init(&sm.full[i], 128); }
-        for (int i = 0; i < NNAT; i++) { mbar_init(&sm.a_done[i], 256); mbar_init(&sm.nat_empty[i], 128); }
+        for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.empty[i], 1); mbar_init(&sm.full[i], 4); }
+        for (int i = 0; i < NNAT; i++) { mbar_init(&sm.a_done[i], 8); mbar_init(&sm.nat_empty[i], 4); }
         mbar_init(&sm.p_done, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 128); }
-        mbar_init(&sm.win_scaled, 128); mbar_init(&sm.s_free, 128);
+        for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 4); }
+        mbar_init(&sm.win_scaled, 4); mbar_init(&sm.s_free, 4);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 128);

@@ -1,6 +1,8 @@
 """GPU check of the tcgen05 training pair (forward with checkpoints + chunked backward) against the oracle,
 plus timing at config c2."""
+import os
 import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import rwkvtts_b200 as R
 from rwkvtts_b200 import ops
