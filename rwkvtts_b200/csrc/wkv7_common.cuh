@@ -16,6 +16,15 @@ constexpr int kChunk = 16;   // snapshot spacing of the scan kernels (reference:
 
 using bf16 = __nv_bfloat16;
 
+// Scratch layout of the tcgen05 training pair inside the caller's `s` / `sa` tensors (reference sizes).
+// Both are stored per (batch*head, chunk) as dense tensor-core operand tiles (UMMA canonical K-major,
+// no swizzle: 8-row x 16-byte core matrices of 128 contiguous bytes), so the backward brings them into shared
+// memory with bulk copies and feeds them to tcgen05.mma without touching a register:
+//   checkpoint (4096 floats): S0^T, row = key, k = value    off = (value/4)*256 + (key/8)*32 + (key%8)*4 + value%4
+//   sa         (1024 floats): U,    row = token, k = value  off = (value/4)*64 + (token/8)*32 + (token%8)*4 + value%4
+constexpr int kCkFloats = 4096, kCkLbo = 256;
+constexpr int kUFloats = 1024, kULbo = 64;
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 

@@ -55,10 +55,10 @@ struct Slot {
     float Gt[4 * T_LBO];          // G (fp32, not an MMA operand), same layout
     float AqbpT[4 * S16_LBO], AqkT[4 * S16_LBO], AakT[4 * S16_LBO];   // [n=s][k=t]          (stage B)
     float Gs[kC];                 // G at the chunk start
-    float S0Ts[kC * 68];          // checkpoint S0^T [key][value], row stride 68
+    __align__(128) float S0c[kCkFloats];   // checkpoint S0^T as a K-major operand tile [key][value] (bulk copy)
 };
 constexpr int NRAW = 2;
-struct RawBuf { uint2 x[7][256]; __align__(16) float4 u[256]; };
+struct RawBuf { uint2 x[7][256]; };
 struct Smem {
     Slot slot[NS];
     float ZT[4 * T_LBO];          // Z^T [value][t]
@@ -74,7 +74,7 @@ struct Smem {
     float elast[kC];              // group C: e^{G} at a window end
     float glp[2][kC], suff[kC], cfirst[kC], xch[2][kC];   // group C: boundary-term partials, dw suffix, carries
     __align__(16) bf16 obuf[6][L][72];   // output staging [array][token][channel]
-    uint64_t full[NS], empty[NS], a_done[NS];
+    uint64_t full[NS], empty[NS], a_done[NS], blob_full[NS];
     uint64_t s0t_ready, bar_z, c_done, out_ready;
     uint32_t tmem_base;
 };
@@ -98,7 +98,7 @@ struct Params {
 #endif
 
 // tensor-memory columns
-constexpr uint32_t C_DS = 0, C_DST = 64, C_S0T = 128, C_Z = 256, C_OK = 272, C_OV = 336;
+constexpr uint32_t C_DS = 0, C_DST = 64, C_Z = 128, C_OK = 144, C_OV = 208;
 
 __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
@@ -130,7 +130,6 @@ __device__ __forceinline__ void issue_raw(const Params &P, RawBuf &rb, size_t ba
     cp_async8(&rb.x[0][tp], P.w + off); cp_async8(&rb.x[1][tp], P.q + off); cp_async8(&rb.x[2][tp], P.k + off);
     cp_async8(&rb.x[3][tp], P.v + off); cp_async8(&rb.x[4][tp], P.a + off); cp_async8(&rb.x[5][tp], P.b + off);
     cp_async8(&rb.x[6][tp], P.dy + off);
-    cp_async16(&rb.u[tp], P.sa + off);
 }
 
 __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tp) {
@@ -177,10 +176,9 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
         }
         cp_async_wait<1>();                       // this iteration's raw inputs have landed (own copies only)
         const RawBuf &rb = sm.raw[it % NRAW];
-        struct { uint2 x[7]; float4 u; } raw;
+        struct { uint2 x[7]; } raw;
 #pragma unroll
         for (int i = 0; i < 7; i++) raw.x[i] = rb.x[i][tp];
-        raw.u = rb.u[tp];
         float lw[4], gg[4];
         {
             float f[4];
@@ -210,14 +208,15 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
         TICK(ta1);
         if (it >= NS) mbar_wait(&sm.empty[si], ((it / NS) - 1) & 1);
         TICK(ta2);
-        {   // checkpoint S0^T of this chunk: HBM -> staging rows of the slot, asynchronously
-            const float *src = P.ckT + ((size_t)bh * nC + c) * (kC * kC);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int e = tp + 256 * i;
-                cp_async16(&S.S0Ts[(e >> 4) * 68 + (e & 15) * 4], src + (e >> 4) * kC + (e & 15) * 4);
-            }
-            cp_async_commit();
+        if (wp == 0) {   // checkpoint S0^T and U of this chunk: operand tiles, HBM -> slot, bulk copies
+            const int ln = tp & 31;
+            if (ln == 0) mbar_expect_tx(&sm.blob_full[si], (kCkFloats + kUFloats) * 4);
+            __syncwarp();
+            if (ln < 16)
+                bulk_g2s(&S.UVn[ln * N32_LBO], P.sa + ((size_t)bh * nC + c) * kUFloats + ln * kULbo, kULbo * 4,
+                         &sm.blob_full[si]);
+            else if (ln == 16)
+                bulk_g2s(S.S0c, P.ckT + ((size_t)bh * nC + c) * kCkFloats, kCkFloats * 4, &sm.blob_full[si]);
         }
         {
             float E[4], Ep[4], iE[4], f[4], o[4];
@@ -251,12 +250,10 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
 #pragma unroll
             for (int j = 0; j < 4; j++) S.dYt[ot + 4 * j] = f[j];
             st4(&S.DYZn[on32], f[0], f[1], f[2], f[3]);
-            st4(&S.UVn[on32], tf32r(raw.u.x), tf32r(raw.u.y), tf32r(raw.u.z), tf32r(raw.u.w));   // U
 #pragma unroll
             for (int j = 0; j < 4; j++) S.Gt[ot + 4 * j] = gg[j];
             if (t == 0) st4(&S.Gs[k4 * 4], gg[0] - lw[0], gg[1] - lw[1], gg[2] - lw[2], gg[3] - lw[3]);
         }
-        cp_async_wait<0>();
         fence_proxy_async();
         mbar_arrive_warp(&sm.a_done[si]);
         mbar_arrive_warp(&sm.full[si]);
@@ -377,7 +374,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
         const Slot &S = sm.slot[si];
-        const uint32_t s0t = tb + C_S0T + 64 * (it & 1);
+        const uint64_t dS0 = smem_desc(smem_u32(S.S0c), kCkLbo * 4, 32 * 4);
         const uint64_t dUV = smem_desc(smem_u32(S.UVn), N32_LBO * 4, N_SBO * 4);
         const uint64_t dDYZ = smem_desc(smem_u32(S.DYZn), N32_LBO * 4, N_SBO * 4);
         const uint64_t dKn = smem_desc(smem_u32(S.Kn), N16_LBO * 4, N_SBO * 4);
@@ -392,6 +389,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         const uint64_t dAakT = smem_desc(smem_u32(S.AakT), S16_LBO * 4, S_SBO * 4);
         TICK(tm0);
         mbar_wait(&sm.full[si], (it / NS) & 1);
+        mbar_wait(&sm.blob_full[si], (it / NS) & 1);     // U and S0^T operand tiles (bulk copies)
         TICK(tm1);
         // group C has finished with the previous chunk's tensor-memory results, has moved dS / dS^T into this
         // window's frame if a boundary was crossed, and has put S0^T of this chunk into tensor memory
@@ -429,7 +427,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
                 mma_tf32_ts(tb + C_DS, tb + C_Z + 8 * kk, kadv(dAt, kk, T_LBO), I64, true);
         }
         __syncwarp();
-        mbar_wait(&sm.c_done, it & 1);            // group C: Z tiles and the gradient Gram tiles
+        mbar_wait(&sm.c_done, it & 1);            // group C: Z tiles and the gradient Gram tiles (C has seen blob_full)
         TICK(tm4);
         fence_after_sync();
         if (elect_one()) {
@@ -443,7 +441,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
             // P1: [dQ~^T | dA~^T] = S0^T [dY;Z]^T + B~^T [dAqb;dN]^T + K~^T [dAqk;dAak]^T
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
-                mma_tf32_ts(tb + C_OK, s0t + 8 * kk, kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
+                mma_tf32_ss(tb + C_OK, kadv(dS0, kk, kCkLbo), kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
                 mma_tf32_ss(tb + C_OK, kadv(dBt, kk, T_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
@@ -536,22 +534,9 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 tmem_st16(tb + C_DST + 16 * cb, v);
             }
         }
-        {   // S0^T of this chunk: staging rows -> tensor memory
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int cb = 2 * hf + cc;
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 x = *reinterpret_cast<const float4 *>(&S.S0Ts[row * 68 + 16 * cb + 4 * i]);
-                    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
-                }
-                tmem_st16(tb + C_S0T + 64 * (it & 1) + 16 * cb, v);
-            }
-        }
-        tmem_wait_st();
+        if (win_last) tmem_wait_st();
         fence_before_sync();
-        mbar_arrive_warp(&sm.s0t_ready);
+        mbar_arrive_warp(&sm.s0t_ready);       // previous chunk's results consumed, dS / dS^T in this window's frame
         TICK(tc2);
         // ---- Z^T -> shared tiles (tokens 8hf..8hf+7) ---------------------------------------------
         mbar_wait(&sm.bar_z, it & 1);
@@ -572,6 +557,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
         }
         bar_sync(4, 256);
+        mbar_wait(&sm.blob_full[si], (it / NS) & 1);     // U (and S0^T) of this chunk have landed
         {   // gradient Gram blocks over the value index, one 16x8 tile per warp: q = 0 dAqb=tril(dY U^T),
             // 1 dN=stril(Z U^T), 2 dAqk=tril(dY V^T), 3 dAak=stril(Z V^T); hf = n-tile (s = 8hf..8hf+7)
             const int ar = (q & 1) * 16, br = (q >> 1) * 16;
@@ -703,12 +689,16 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
 #pragma unroll
             for (int cc = 0; cc < 2; cc++) {
                 const int cb = 2 * hf + cc;
-                float a_[16], b_[16];
+                float a_[16];
                 tmem_ld16(tb + C_DST + 16 * cb, a_);
-                tmem_ld16(tb + C_S0T + 64 * (it & 1) + 16 * cb, b_);
                 tmem_wait_ld();
+                const float *sp = S.S0c + (row >> 3) * 32 + (row & 7) * 4;      // S0^T[key = row][value]
 #pragma unroll
-                for (int i = 0; i < 16; i++) glp = fmaf(a_[i], b_[i], glp);
+                for (int i = 0; i < 4; i++) {
+                    const float4 x = *reinterpret_cast<const float4 *>(sp + (4 * cb + i) * kCkLbo);
+                    glp = fmaf(a_[4 * i], x.x, glp); glp = fmaf(a_[4 * i + 1], x.y, glp);
+                    glp = fmaf(a_[4 * i + 2], x.z, glp); glp = fmaf(a_[4 * i + 3], x.w, glp);
+                }
             }
             if (act) sm.glp[hf][row] = glp;
         }
@@ -756,12 +746,15 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
     const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
 
     if (tid == 0) {
-        for (int i = 0; i < NS; i++) { mbar_init(&sm.full[i], 8 + 4); mbar_init(&sm.empty[i], 8); mbar_init(&sm.a_done[i], 8); }
+        for (int i = 0; i < NS; i++) {
+            mbar_init(&sm.full[i], 8 + 4); mbar_init(&sm.empty[i], 8); mbar_init(&sm.a_done[i], 8);
+            mbar_init(&sm.blob_full[i], 1);
+        }
         mbar_init(&sm.s0t_ready, 8); mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 8);
         mbar_init(&sm.out_ready, 1);
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 256);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -774,7 +767,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
 
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 512);
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 256);
 }
 
 }  // namespace tcbwd

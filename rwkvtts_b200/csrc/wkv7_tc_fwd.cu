@@ -46,6 +46,7 @@ constexpr int NSLOT = 5;     // operand slots in flight
 constexpr int NNAT = 3;      // stage A -> stage B hand-off buffers
 constexpr int LDN = 68;      // row stride of the natural [token][channel] tiles
 constexpr float kMinLogDecay = -1.35f;
+constexpr uint32_t C_ST = 128;   // tensor-memory columns of the transposed state (training variant)
 constexpr float kLog2e = 1.4426950408889634f;   // decays are accumulated as log2 (ex2.approx needs no pre-scale)
 
 // canonical K-major tiles, strides in floats (see tc05.cuh: off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4)
@@ -69,10 +70,10 @@ struct Smem {
     float NT[2][L * 20], Aak[2][L * 20];   // per stage-B group: N^T and Aak, fp32
     float wtot[2][8][kC];                  // stage A scan partials, double buffered
     __align__(16) bf16 ybuf[2][L][72];     // epilogue: Y tile [token][value], double buffered
-    __align__(16) float stg[kC * 68];      // training: transposed state tile [key][value] on its way to HBM
+    __align__(16) float Ut[2][4 * T_LBO];  // training: U^T [value][token] operand tile of the transposed-state update
     float DLw[4][kC];                      // e^{G} at the end of a window (ring of 4 windows)
     uint64_t empty[NSLOT], full[NSLOT], a_done[NNAT], nat_empty[NNAT];
-    uint64_t p_done, y_ready[2], y_free[2], win_scaled, s_free;
+    uint64_t p_done, y_ready[2], y_free[2], win_scaled, ut_ready, st_ready, st_free;
     uint32_t tmem_base;
 };
 
@@ -80,9 +81,10 @@ struct Params {
     int T, H;
     const bf16 *w, *q, *k, *v, *a, *b;
     bf16 *y;
-    float *ckT;          // training: TRANSPOSED state [key][value] at the start of every chunk, in the frame of
-                         // the chunk's window, [B*H][T/16][64][64]; null for the snapshot-free forward
-    float *sa;           // training: U_t = S_{t-1} a_t, fp32 [B,T,H,64]
+    float *ckT;          // training: TRANSPOSED state at the start of every chunk, in the frame of the chunk's
+                         // window, [B*H][T/16] operand tiles of 4096 floats (wkv7_common.cuh); null for the
+                         // snapshot-free forward
+    float *sa;           // training: U_t = S_{t-1} a_t (tf32), [B*H][T/16] operand tiles of 1024 floats
     const float *s0;     // may be null
     float *sT;           // may be null
     long long *dbg;      // phase-cycle counters (profiling builds only), may be null
@@ -363,7 +365,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         __syncwarp();
         mbar_wait(&sm.p_done, ph); ph ^= 1;
         TICK(tm4);
-        if (kTrain && c > 0 && c % WIN != 0) mbar_wait(&sm.s_free, (c - 1) & 1);   // epilogue has read S^ of chunk c-1
+        if (kTrain && c > 0) {
+            mbar_wait(&sm.ut_ready, (c - 1) & 1);                      // U^T tile of chunk c-1 is in shared memory
+            if (c >= 2) mbar_wait(&sm.st_free, c & 1);                 // checkpoint c-1 has been read out of S^T
+        }
         fence_after_sync();
         if (elect_one()) {
             // phase 2: S^ += U^T B~ + V^T K~ ;  Y^T += U^T Aqb^T
@@ -378,8 +383,26 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
                 mma_tf32_ts(uy + 16, uy + 8 * kk, dQB + (uint64_t)((kk * 2 * QB_LBO * 4) >> 4), I16, true);
-            mma_commit(&sm.empty[si]);
+            if (!kTrain) mma_commit(&sm.empty[si]);
             mma_commit(&sm.y_ready[u]);
+            if (kTrain && c > 0) {
+                // transposed state, one chunk behind: S^T += B~^T U + K~^T V of chunk c-1 (checkpoint of chunk c)
+                const Slot &Sp = sm.slot[(c - 1) % NSLOT];
+                const uint64_t pBt = smem_desc(smem_u32(Sp.Bt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pKt = smem_desc(smem_u32(Sp.Kt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pVt = smem_desc(smem_u32(Sp.Vt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pUt = smem_desc(smem_u32(sm.Ut[(c - 1) & 1]), T_LBO * 4, T_SBO * 4);
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                    mma_tf32_ss(tb + C_ST, pBt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), pUt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4),
+                                I64, true);
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                    mma_tf32_ss(tb + C_ST, pKt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), pVt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4),
+                                I64, true);
+                mma_commit(&sm.st_ready);
+                mma_commit(&sm.empty[(c - 1) % NSLOT]);
+            }
         }
         __syncwarp();
         mbar_wait(&sm.p_done, ph); ph ^= 1;
@@ -388,7 +411,11 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = value rows 16q..16q+15
+// epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = rows 16q..16q+15 (values for S^, U^T,
+// Y^T; keys for S^T).  Training variant, per chunk: U goes to HBM in the backward's operand layout and to a
+// [value][token] shared tile from which the MMA warp keeps a TRANSPOSED copy of the state up to date
+// (S^T += B~^T U + K~^T V, one chunk behind the main chain); the chunk-start checkpoint is that copy, read
+// with keys on the lanes, so it leaves as 16-byte pieces of the backward's K-major operand tile.
 // ---------------------------------------------------------------------------------------------
 template <bool kTrain>
 __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
@@ -397,23 +424,18 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
-    float *ck = kTrain ? P.ckT + (size_t)bh * nC * (kC * kC) : nullptr;
-    // stage one 16-column block of this thread's state row, transposed, for the checkpoint
-    auto stage_T = [&](const float (&v)[16], int cb) {
+    float *ckg = kTrain ? P.ckT + (size_t)bh * nC * kCkFloats + (row >> 3) * 32 + (row & 7) * 4 : nullptr;   // key = row
+    float *sag = kTrain ? P.sa + (size_t)bh * nC * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
+    // 16 value columns (16cb ..) of this thread's key row of S^T -> checkpoint tile of chunk cc
+    auto store_ck = [&](const float (&v)[16], int cb, int cc) {
         if (act) {
+            float *dst = ckg + (size_t)cc * kCkFloats + (4 * cb) * kCkLbo;
 #pragma unroll
-            for (int i = 0; i < 16; i++) sm.stg[(16 * cb + i) * 68 + row] = v[i];
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4 *>(dst + i * kCkLbo) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         }
     };
-    // after a 128-thread barrier: [key][value] rows, 256 bytes each, coalesced
-    auto flush_T = [&](float *dst) {
-        const int k = tid >> 1, half = (tid & 1) * 32;
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-            *reinterpret_cast<float4 *>(dst + k * kC + half + 4 * i) =
-                *reinterpret_cast<const float4 *>(&sm.stg[k * 68 + half + 4 * i]);
-    };
-    {   // initial state -> tensor memory (and checkpoint 0)
+    {   // initial state -> tensor memory (S^, and S^T + checkpoint 0 when training)
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
             float v[16];
@@ -428,21 +450,24 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 }
             }
             tmem_st16(tb + 16 * cb, v);
-            if (kTrain) stage_T(v, cb);
+            if (kTrain) {
+                if (P.s0 != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = P.s0[(size_t)bh * kC * kC + (16 * cb + i) * kC + row];
+                }
+                tmem_st16(tb + C_ST + 16 * cb, v);
+                store_ck(v, cb, 0);
+            }
         }
         tmem_wait_st();
         fence_before_sync();
         mbar_arrive_warp(&sm.win_scaled);
-        if (kTrain) {
-            bar_sync(4, 128);
-            flush_T(ck);
-            bar_sync(4, 128);
-        }
     }
     for (int c = 0; c < nC; c++) {
         const int u = c & 1;
         const bool last = (c == nC - 1);
         const bool win_end = (c % WIN == WIN - 1) || last;
+        const float *dl = sm.DLw[(c / WIN) & 3];
         TICK(te0);
         mbar_wait(&sm.y_ready[u], (c >> 1) & 1);
         TICK(te1);
@@ -451,52 +476,73 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
         tmem_ld16(tb + 64 + 32 * u + 16, yv);
         if (kTrain) tmem_ld16(tb + 64 + 32 * u, uv);
         tmem_wait_ld();
-        if (win_end || kTrain) {
-            // state after this chunk; at a window end it is rescaled (frame origin moves to the next window)
-            const float *dl = sm.DLw[(c / WIN) & 3];
+        if (win_end) {
+            // state after this chunk, rescaled: the frame origin moves to the next window
             float *dsT = (last && P.sT != nullptr) ? P.sT + (size_t)bh * kC * kC + row * kC : nullptr;
 #pragma unroll
             for (int cb = 0; cb < 4; cb++) {
                 float v[16];
                 tmem_ld16(tb + 16 * cb, v);
                 tmem_wait_ld();
-                if (win_end) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] *= dl[16 * cb + i];
-                    if (!last) tmem_st16(tb + 16 * cb, v);
-                }
-                if (kTrain && !last) stage_T(v, cb);
+                for (int i = 0; i < 16; i++) v[i] *= dl[16 * cb + i];
+                if (!last) tmem_st16(tb + 16 * cb, v);
                 if (act && dsT != nullptr) {
                     float4 *dp = reinterpret_cast<float4 *>(dsT + 16 * cb);
 #pragma unroll
                     for (int i = 0; i < 4; i++) dp[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                 }
             }
-            if (win_end) tmem_wait_st();
+            tmem_wait_st();
         }
         fence_before_sync();
         mbar_arrive_warp(&sm.y_free[u]);
         if (win_end) mbar_arrive_warp(&sm.win_scaled);
-        if (kTrain) mbar_arrive_warp(&sm.s_free);
         {   // Y tile: [value lanes][16 tokens] -> shared [token][value] bf16 -> 128-byte rows to HBM
             bf16(&yb)[L][72] = sm.ybuf[u];
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) yb[j][row] = __float2bfloat16_rn(yv[j]);
                 if (kTrain) {
-                    float *sap = P.sa + base + (size_t)(c * L) * tok_stride + row;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) sap[(size_t)j * tok_stride] = uv[j];
+                    for (int j = 0; j < 16; j++) uv[j] = tf32r(uv[j]);
+                    float *ut = sm.Ut[u] + (row >> 3) * T_SBO + (row & 7) * 4;      // [value][token] operand tile
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st4(ut + i * T_LBO, uv[4 * i], uv[4 * i + 1], uv[4 * i + 2], uv[4 * i + 3]);
+                    float *sap = sag + (size_t)c * kUFloats;                         // [token][value] operand tile
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sap[(j >> 3) * 32 + (j & 7) * 4] = uv[j];
                 }
+            }
+            if (kTrain) {
+                fence_proxy_async();
+                mbar_arrive_warp(&sm.ut_ready);
             }
             bar_sync(4, 128);
             const int tok = tid >> 3, part = tid & 7;
             const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
             *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
-            if (kTrain && !last) {
-                flush_T(ck + (size_t)(c + 1) * (kC * kC));
-                bar_sync(4, 128);
+        }
+        if (kTrain && !last) {
+            // S^T after this chunk = checkpoint of chunk c+1 (rows = keys; at a window end rescaled per row)
+            mbar_wait(&sm.st_ready, c & 1);
+            fence_after_sync();
+            const float dr = win_end ? dl[row] : 1.f;
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                float v[16];
+                tmem_ld16(tb + C_ST + 16 * cb, v);
+                tmem_wait_ld();
+                if (win_end) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] *= dr;
+                    tmem_st16(tb + C_ST + 16 * cb, v);
+                }
+                store_ck(v, cb, c + 1);
             }
+            if (win_end) tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive_warp(&sm.st_free);
         }
         TICK(te2); ACC(13, te0, te1); ACC(14, te1, te2);
     }
@@ -519,10 +565,10 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
         for (int i = 0; i < NNAT; i++) { mbar_init(&sm.a_done[i], 8); mbar_init(&sm.nat_empty[i], 4); }
         mbar_init(&sm.p_done, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 4); }
-        mbar_init(&sm.win_scaled, 4); mbar_init(&sm.s_free, 4);
+        mbar_init(&sm.win_scaled, 4); mbar_init(&sm.ut_ready, 4); mbar_init(&sm.st_ready, 1); mbar_init(&sm.st_free, 4);
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 128);
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 256);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -535,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
 
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 128);
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 256);
 }
 
 }  // namespace tcfwd
