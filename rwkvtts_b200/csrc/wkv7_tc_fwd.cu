@@ -367,7 +367,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         TICK(tm4);
         if (kTrain && c > 0) {
             mbar_wait(&sm.ut_ready, (c - 1) & 1);                      // U^T tile of chunk c-1 is in shared memory
-            if (c >= 2) mbar_wait(&sm.st_free, c & 1);                 // checkpoint c-1 has been read out of S^T
+            mbar_wait(&sm.st_free, (c - 1) & 1);                       // checkpoint c-1 has been read out of S^T
         }
         fence_after_sync();
         if (elect_one()) {
@@ -424,18 +424,8 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
-    float *ckg = kTrain ? P.ckT + (size_t)bh * nC * kCkFloats + (row >> 3) * 32 + (row & 7) * 4 : nullptr;   // key = row
     float *sag = kTrain ? P.sa + (size_t)bh * nC * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
-    // 16 value columns (16cb ..) of this thread's key row of S^T -> checkpoint tile of chunk cc
-    auto store_ck = [&](const float (&v)[16], int cb, int cc) {
-        if (act) {
-            float *dst = ckg + (size_t)cc * kCkFloats + (4 * cb) * kCkLbo;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                *reinterpret_cast<float4 *>(dst + i * kCkLbo) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        }
-    };
-    {   // initial state -> tensor memory (S^, and S^T + checkpoint 0 when training)
+    {   // initial state -> tensor memory
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
             float v[16];
@@ -450,14 +440,6 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 }
             }
             tmem_st16(tb + 16 * cb, v);
-            if (kTrain) {
-                if (P.s0 != nullptr) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = P.s0[(size_t)bh * kC * kC + (16 * cb + i) * kC + row];
-                }
-                tmem_st16(tb + C_ST + 16 * cb, v);
-                store_ck(v, cb, 0);
-            }
         }
         tmem_wait_st();
         fence_before_sync();
@@ -523,35 +505,70 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
             const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
             *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
         }
-        if (kTrain && !last) {
-            // S^T after this chunk = checkpoint of chunk c+1 (rows = keys; at a window end rescaled per row)
-            mbar_wait(&sm.st_ready, c & 1);
-            fence_after_sync();
-            const float dr = win_end ? dl[row] : 1.f;
-#pragma unroll
-            for (int cb = 0; cb < 4; cb++) {
-                float v[16];
-                tmem_ld16(tb + C_ST + 16 * cb, v);
-                tmem_wait_ld();
-                if (win_end) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] *= dr;
-                    tmem_st16(tb + C_ST + 16 * cb, v);
-                }
-                store_ck(v, cb, c + 1);
-            }
-            if (win_end) tmem_wait_st();
-            fence_before_sync();
-            mbar_arrive_warp(&sm.st_free);
-        }
         TICK(te2); ACC(13, te0, te1); ACC(14, te1, te2);
     }
 }
 
-constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1);
+// ---------------------------------------------------------------------------------------------
+// checkpoint group (training variant only): warp q owns tensor-memory lanes 32q..32q+15 = KEY rows 16q..16q+15 of
+// the transposed state S^T.  After the MMA warp has added chunk c, S^T is the chunk-start checkpoint of chunk c+1:
+// 16-byte pieces of the backward's K-major operand tile, 256 contiguous bytes per warp store.
+// ---------------------------------------------------------------------------------------------
+__device__ void ckpt_group(const Params &P, Smem &sm, int bh, int nC, int tid) {
+    const int q = (tid >> 5) & 3, lane = tid & 31;
+    const bool act = lane < 16;
+    const int row = 16 * q + (lane & 15);
+    const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16) + C_ST;
+    float *ckg = P.ckT + (size_t)bh * nC * kCkFloats + (row >> 3) * 32 + (row & 7) * 4;   // key = row
+    auto store_ck = [&](const float (&v)[16], int cb, int cc) {
+        if (act) {
+            float *dst = ckg + (size_t)cc * kCkFloats + (4 * cb) * kCkLbo;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4 *>(dst + i * kCkLbo) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    };
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) {   // S^T <- s0^T (or 0) = checkpoint 0
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            v[i] = (P.s0 != nullptr) ? P.s0[(size_t)bh * kC * kC + (16 * cb + i) * kC + row] : 0.f;
+        tmem_st16(tb + 16 * cb, v);
+        store_ck(v, cb, 0);
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    mbar_arrive_warp(&sm.st_free);
+    for (int c = 0; c + 1 < nC; c++) {
+        const bool win_end = (c % WIN == WIN - 1);
+        mbar_wait(&sm.st_ready, c & 1);
+        fence_after_sync();
+        const float dr = win_end ? sm.DLw[(c / WIN) & 3][row] : 1.f;   // window end: rows move to the next window's frame
+        float v[4][16];
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) tmem_ld16(tb + 16 * cb, v[cb]);
+        tmem_wait_ld();
+        if (win_end) {
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[cb][i] *= dr;
+                tmem_st16(tb + 16 * cb, v[cb]);
+            }
+            tmem_wait_st();
+        }
+        fence_before_sync();
+        mbar_arrive_warp(&sm.st_free);
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) store_ck(v[cb], cb, c + 1);
+    }
+}
+
+constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1), kThreadsTrain = kThreads + 128;
 
 template <bool kTrain>
-__global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P) {
+__global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
@@ -577,7 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_kernel(const Params P
     else if (warp < 12) stage_a(P, sm, base, tok_stride, nC, tid - 128);
     else if (warp < 16) stage_b(P, sm, nC, tid - 384, 0);
     else if (warp < 20) stage_b(P, sm, nC, tid - 512, 1);
-    else mma_warp<kTrain>(P, sm, nC);
+    else if (warp == kMmaWarp) mma_warp<kTrain>(P, sm, nC);
+    else if (kTrain) ckpt_group(P, sm, bh, nC, tid);
 
     fence_before_sync();
     __syncthreads();
@@ -602,7 +620,7 @@ cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, con
         cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
-        wkv7_tc_fwd_kernel<true><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+        wkv7_tc_fwd_kernel<true><<<dim3(B * H), dim3(kThreadsTrain), sizeof(Smem), st>>>(P);
     } else {
         cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(Smem));
