@@ -75,7 +75,7 @@ struct Smem {
     float glp[2][kC], suff[kC], cfirst[kC], xch[2][kC];   // group C: boundary-term partials, dw suffix, carries
     __align__(16) bf16 obuf[6][L][72];   // output staging [array][token][channel]
     uint64_t full[NS], empty[NS], a_done[NS], blob_full[NS];
-    uint64_t s0t_ready, bar_z, c_done, out_ready;
+    uint64_t resc, glp_done, ok_free[2], bar_z, c_done, out_ready;
     uint32_t tmem_base;
 };
 
@@ -98,7 +98,7 @@ struct Params {
 #endif
 
 // tensor-memory columns
-constexpr uint32_t C_DS = 0, C_DST = 64, C_Z = 128, C_OK = 144, C_OV = 208;
+constexpr uint32_t C_DS = 0, C_DST = 64, C_Z = 128, C_OK = 144, C_OV = 208, C_OBUF = 80;   // OK/OV double buffered
 
 __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d) {
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
@@ -264,11 +264,12 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
 // ---------------------------------------------------------------------------------------------
 // stage B: tp in [0,128), group grp handles iterations it = grp, grp+2, ...
 // ---------------------------------------------------------------------------------------------
-__device__ void stage_b(const Params &P, Smem &sm, int nC, int tp, int grp) {
+__device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
+    constexpr int grp = 0;
     long long *P_dbg = (tp == 0 && grp == 0) ? P.dbg : nullptr; (void)P_dbg;
     const int wp = tp >> 5, lane = tp & 31, g = lane >> 2, tq = lane & 3;
     float *Nn = sm.Nn[grp], *AQ = sm.Aqbn[grp];
-    for (int it = grp; it < nC; it += 2) {
+    for (int it = 0; it < nC; it++) {
         const int si = it % NS;
         Slot &S = sm.slot[si];
         TICK(tb0);
@@ -371,8 +372,11 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
     const uint64_t dQKAK = smem_desc(smem_u32(sm.QK_AK), S32_LBO * 4, S_SBO * 4);
     const uint64_t dNTAKT = smem_desc(smem_u32(sm.NT_AKT), S32_LBO * 4, S_SBO * 4);
     const uint64_t dQBTQKT = smem_desc(smem_u32(sm.QBT_QKT), S32_LBO * 4, S_SBO * 4);
+    int nw = 0;
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
+        const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
+        const uint32_t ok = tb + C_OK + C_OBUF * (it & 1), ov = tb + C_OV + C_OBUF * (it & 1);
         const Slot &S = sm.slot[si];
         const uint64_t dS0 = smem_desc(smem_u32(S.S0c), kCkLbo * 4, 32 * 4);
         const uint64_t dUV = smem_desc(smem_u32(S.UVn), N32_LBO * 4, N_SBO * 4);
@@ -391,9 +395,12 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         mbar_wait(&sm.full[si], (it / NS) & 1);
         mbar_wait(&sm.blob_full[si], (it / NS) & 1);     // U and S0^T operand tiles (bulk copies)
         TICK(tm1);
-        // group C has finished with the previous chunk's tensor-memory results, has moved dS / dS^T into this
-        // window's frame if a boundary was crossed, and has put S0^T of this chunk into tensor memory
-        mbar_wait(&sm.s0t_ready, it & 1);
+        // every MMA of the previous chunk has completed (dS, dS^T are final; Z, the Gram tiles and the slot two
+        // iterations back are free); at a window boundary group C1 has moved dS / dS^T into this window's frame;
+        // group C2 has drained the gradient accumulators of two iterations back
+        if (it > 0) mbar_wait(&sm.out_ready, (it - 1) & 1);
+        if (win_last) { mbar_wait(&sm.resc, nw & 1); nw++; }
+        if (it >= 2) mbar_wait(&sm.ok_free[it & 1], ((it >> 1) - 1) & 1);
         TICK(tm2);
         fence_after_sync();
         if (elect_one()) {
@@ -408,10 +415,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
             // P3a: dV^T = dS K~^T ;  P2a: [dB~^T | dK~^T] = dS^T [U;V]^T     (dS, dS^T before this chunk's update)
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
-                mma_tf32_ts(tb + C_OV, tb + C_DS + 8 * kk, kadv(dKn, kk, N16_LBO), I16, kk > 0);
+                mma_tf32_ts(ov, tb + C_DS + 8 * kk, kadv(dKn, kk, N16_LBO), I16, kk > 0);
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
-                mma_tf32_ts(tb + C_OK + 32, tb + C_DST + 8 * kk, kadv(dUV, kk, N32_LBO), I32, kk > 0);
+                mma_tf32_ts(ok + 32, tb + C_DST + 8 * kk, kadv(dUV, kk, N32_LBO), I32, kk > 0);
         }
         __syncwarp();
         mbar_wait(&sm.bar_z, it & 1);
@@ -441,27 +448,27 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
             // P1: [dQ~^T | dA~^T] = S0^T [dY;Z]^T + B~^T [dAqb;dN]^T + K~^T [dAqk;dAak]^T
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
-                mma_tf32_ss(tb + C_OK, kadv(dS0, kk, kCkLbo), kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
+                mma_tf32_ss(ok, kadv(dS0, kk, kCkLbo), kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_OK, kadv(dBt, kk, T_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok, kadv(dBt, kk, T_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_OK, kadv(dKt, kk, T_LBO), kadv(dQKAK, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok, kadv(dKt, kk, T_LBO), kadv(dQKAK, kk, S32_LBO), I32, true);
             // P2b: [dB~^T | dK~^T] += A~^T [dN^T;dAak^T]^T + Q~^T [dAqb^T;dAqk^T]^T
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_OK + 32, kadv(dAt, kk, T_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dAt, kk, T_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_OK + 32, kadv(dQt, kk, T_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dQt, kk, T_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
             // P3b: dV^T += dY^T Aqk + Z^T Aak
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_OV, kadv(dYt, kk, T_LBO), kadv(dAqkT, kk, S16_LBO), I16, true);
+                mma_tf32_ss(ov, kadv(dYt, kk, T_LBO), kadv(dAqkT, kk, S16_LBO), I16, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ts(tb + C_OV, tb + C_Z + 8 * kk, kadv(dAakT, kk, S16_LBO), I16, true);
+                mma_tf32_ts(ov, tb + C_Z + 8 * kk, kadv(dAakT, kk, S16_LBO), I16, true);
             mma_commit(&sm.out_ready);
         }
         __syncwarp();
@@ -471,56 +478,51 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// group C: 8 warps.  Warp (q, hf): q = warp & 3 owns tensor-memory lanes 32q..32q+15 = rows 16q..16q+15,
-// hf = warp >> 2 takes one half of the columns / tokens of every step.
+// group C1: 4 warps, on the chain between the MMA batches of one chunk.  Warp q owns tensor-memory lanes
+// 32q..32q+15 = rows 16q..16q+15.  Per chunk: (window boundary) move dS / dS^T into the window's frame; Z^T ->
+// shared operand tiles; the four 16x16 gradient Gram blocks (mma.sync) -> operand tiles.
 // ---------------------------------------------------------------------------------------------
-__device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+__device__ void group_c1(const Params &P, Smem &sm, int bh, int nC, int tid) {
     long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
-    const int wq = tid >> 5, q = wq & 3, hf = wq >> 2, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    const int q = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
     const int trow = (row >> 3) * T_SBO + (row & 7) * 4;
-    {   // dS, dS^T <- dsT (or 0); boundary term of the last window from sT
+    {   // dS, dS^T <- dsT (or 0)
         const bool have = P.dsT != nullptr && P.sT != nullptr;
         const float *gs = have ? P.dsT + (size_t)bh * kC * kC : nullptr;
-        const float *st = have ? P.sT + (size_t)bh * kC * kC : nullptr;
-        float glp = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
-            const int cb = 2 * hf + cc;
+        for (int cb = 0; cb < 4; cb++) {
             float v[16], vt[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 v[i] = have ? gs[row * kC + 16 * cb + i] : 0.f;              // dS[row][.]
                 vt[i] = have ? gs[(16 * cb + i) * kC + row] : 0.f;           // dS^T[row][.] = dS[.][row]
-                if (have) glp = fmaf(vt[i], st[(16 * cb + i) * kC + row], glp);
             }
             tmem_st16(tb + C_DS + 16 * cb, v);
             tmem_st16(tb + C_DST + 16 * cb, vt);
         }
         tmem_wait_st();
-        if (act) { sm.glp[hf][row] = glp; if (hf == 0) { sm.suff[row] = 0.f; sm.cfirst[row] = 0.f; } }
     }
+    int nw = 0;
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
         Slot &S = sm.slot[si];
         const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
         TICK(tc0);
-        mbar_wait(&sm.full[si], (it / NS) & 1);
-        TICK(tc1);
         if (win_last) {
-            // dS, dS^T arrive in the frame of the NEXT window (or true frame at the sequence end):
-            // move them into this window's frame, columns (keys) scaled by e^{G_last}
-            if (act && hf == 0) {
-                sm.elast[row] = __expf(S.Gt[trow + 3 * T_LBO + 3]);
-                sm.suff[row] = 0.f; sm.cfirst[row] = 0.f;
-            }
-            bar_sync(4, 256);
+            // dS, dS^T arrive in the frame of the NEXT window (or true frame at the sequence end): move them into
+            // this window's frame, columns (keys) scaled by e^{G_last}.  Group C2 has taken the boundary term from
+            // dS^T first (which also means every MMA of the previous chunk has completed).
+            mbar_wait(&sm.full[si], (it / NS) & 1);
+            if (it > 0) mbar_wait(&sm.glp_done, (nw - 1) & 1);
+            fence_after_sync();
+            if (act) sm.elast[row] = __expf(S.Gt[trow + 3 * T_LBO + 3]);
+            bar_sync(4, 128);
             const float er = sm.elast[row];
 #pragma unroll
-            for (int cc = 0; cc < 2; cc++) {
-                const int cb = 2 * hf + cc;
+            for (int cb = 0; cb < 4; cb++) {
                 float v[16];
                 tmem_ld16(tb + C_DS + 16 * cb, v);
                 tmem_wait_ld();
@@ -533,63 +535,106 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 for (int i = 0; i < 16; i++) v[i] *= er;
                 tmem_st16(tb + C_DST + 16 * cb, v);
             }
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive_warp(&sm.resc);
+            nw++;
         }
-        if (win_last) tmem_wait_st();
-        fence_before_sync();
-        mbar_arrive_warp(&sm.s0t_ready);       // previous chunk's results consumed, dS / dS^T in this window's frame
         TICK(tc2);
-        // ---- Z^T -> shared tiles (tokens 8hf..8hf+7) ---------------------------------------------
+        // ---- Z^T -> shared tiles ----------------------------------------------------------------
         mbar_wait(&sm.bar_z, it & 1);
         TICK(tc3);
         fence_after_sync();
         {
-            float z[8];
-            tmem_ld8(tb + C_Z + 8 * hf, z);
+            float z[16];
+            tmem_ld16(tb + C_Z, z);
             tmem_wait_ld();
             if (act) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) z[i] = tf32r(z[i]);
+                for (int i = 0; i < 16; i++) z[i] = tf32r(z[i]);
 #pragma unroll
-                for (int i = 0; i < 8; i++) S.DYZn[kmajor_off(16 + 8 * hf + i, row, N32_LBO, N_SBO)] = z[i];
-                float *pz = sm.ZT + trow + 2 * hf * T_LBO;
-                st4(pz, z[0], z[1], z[2], z[3]);
-                st4(pz + T_LBO, z[4], z[5], z[6], z[7]);
+                for (int i = 0; i < 16; i++) S.DYZn[kmajor_off(16 + i, row, N32_LBO, N_SBO)] = z[i];
+                float *pz = sm.ZT + trow;
+#pragma unroll
+                for (int i = 0; i < 4; i++) st4(pz + i * T_LBO, z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
             }
         }
-        bar_sync(4, 256);
+        bar_sync(4, 128);
         mbar_wait(&sm.blob_full[si], (it / NS) & 1);     // U (and S0^T) of this chunk have landed
-        {   // gradient Gram blocks over the value index, one 16x8 tile per warp: q = 0 dAqb=tril(dY U^T),
-            // 1 dN=stril(Z U^T), 2 dAqk=tril(dY V^T), 3 dAak=stril(Z V^T); hf = n-tile (s = 8hf..8hf+7)
+        {   // gradient Gram blocks over the value index, one 16x16 block per warp: q = 0 dAqb=tril(dY U^T),
+            // 1 dN=stril(Z U^T), 2 dAqk=tril(dY V^T), 3 dAak=stril(Z V^T)
             const int ar = (q & 1) * 16, br = (q >> 1) * 16;
-            float acc[4] = {};
+            float acc[2][4] = {};
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
                 uint32_t af[4], bfr[2];
                 const float *pa = S.DYZn + (ar >> 3) * N_SBO + 2 * kb * N32_LBO + g * 4 + tq;
                 af[0] = __float_as_uint(pa[0]); af[1] = __float_as_uint(pa[N_SBO]);
                 af[2] = __float_as_uint(pa[N32_LBO]); af[3] = __float_as_uint(pa[N32_LBO + N_SBO]);
-                const float *pb = S.UVn + ((br >> 3) + hf) * N_SBO + 2 * kb * N32_LBO + g * 4 + tq;
-                bfr[0] = __float_as_uint(pb[0]); bfr[1] = __float_as_uint(pb[N32_LBO]);
-                mma_tf32(acc, af, bfr);
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const float *pb = S.UVn + ((br >> 3) + nt) * N_SBO + 2 * kb * N32_LBO + g * 4 + tq;
+                    bfr[0] = __float_as_uint(pb[0]); bfr[1] = __float_as_uint(pb[N32_LBO]);
+                    mma_tf32(acc[nt], af, bfr);
+                }
             }
             float *nat = (q < 2) ? sm.QB_N : sm.QK_AK;                  // [n=t][k=s], rows +16 for the Z grams
             float *trn = (q == 0 || q == 2) ? sm.QBT_QKT : sm.NT_AKT;   // [n=s][k=t]
             const int nrow = (q & 1) * 16, trow_ = (q >> 1) * 16;
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int col = 8 * hf + 2 * tq + e;      // s
+            for (int nt = 0; nt < 2; nt++)
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int r = g + 8 * hh;             // t
-                    float x = acc[2 * hh + e];
-                    x = ((q & 1) ? (col < r) : (col <= r)) ? tf32r(x) : 0.f;
-                    nat[kmajor_off(nrow + r, col, S32_LBO, S_SBO)] = x;
-                    trn[kmajor_off(trow_ + col, r, S32_LBO, S_SBO)] = x;
+                for (int e = 0; e < 2; e++) {
+                    const int col = 8 * nt + 2 * tq + e;      // s
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int r = g + 8 * hh;             // t
+                        float x = acc[nt][2 * hh + e];
+                        x = ((q & 1) ? (col < r) : (col <= r)) ? tf32r(x) : 0.f;
+                        nat[kmajor_off(nrow + r, col, S32_LBO, S_SBO)] = x;
+                        trn[kmajor_off(trow_ + col, r, S32_LBO, S_SBO)] = x;
+                    }
                 }
-            }
         }
         fence_proxy_async();
         mbar_arrive_warp(&sm.c_done);
+        TICK(tc4); ACC(10, tc0, tc2); ACC(12, tc2, tc3); ACC(13, tc3, tc4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// group C2: 8 warps, off the chain: the output epilogue of chunk `it` runs while the MMA warp and C1 work on
+// chunk it+1 (the gradient accumulators are double buffered in tensor memory).  Warp (q, hf): q = warp & 3 owns
+// lanes 32q..32q+15 = channel rows 16q..16q+15, hf = warp >> 2 takes tokens 8hf..8hf+7.
+// ---------------------------------------------------------------------------------------------
+__device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+    long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
+    const int wq = tid >> 5, q = wq & 3, hf = wq >> 2, lane = tid & 31;
+    const bool act = lane < 16;
+    const int row = 16 * q + (lane & 15);
+    const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
+    const int trow = (row >> 3) * T_SBO + (row & 7) * 4;
+    {   // boundary term of the last window from sT . dsT
+        const bool have = P.dsT != nullptr && P.sT != nullptr;
+        const float *gs = have ? P.dsT + (size_t)bh * kC * kC : nullptr;
+        const float *st = have ? P.sT + (size_t)bh * kC * kC : nullptr;
+        float glp = 0.f;
+        if (have) {
+#pragma unroll 4
+            for (int i = 0; i < 32; i++) glp = fmaf(gs[(32 * hf + i) * kC + row], st[(32 * hf + i) * kC + row], glp);
+        }
+        if (act) { sm.glp[hf][row] = glp; if (hf == 0) { sm.suff[row] = 0.f; sm.cfirst[row] = 0.f; } }
+        bar_sync(5, 256);
+    }
+    for (int it = 0; it < nC; it++) {
+        const int c = nC - 1 - it, si = it % NS;
+        Slot &S = sm.slot[si];
+        const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
+        const uint32_t ok = tb + C_OK + C_OBUF * (it & 1), ov = tb + C_OV + C_OBUF * (it & 1);
+        if (win_last && it > 0) {
+            if (act && hf == 0) { sm.suff[row] = 0.f; sm.cfirst[row] = 0.f; }
+            bar_sync(5, 256);
+        }
         TICK(tc4);
         // ---- outputs: this warp's 8 tokens (hf = 1 is later in time and feeds hf = 0) -------------
         mbar_wait(&sm.out_ready, it & 1);
@@ -619,7 +664,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 iE[i] = ex2f(-g2);
             }
             // dQ~ -> dq
-            tmem_ld8(tb + C_OK + 8 * hf, acc_); tmem_wait_ld();
+            tmem_ld8(ok + 8 * hf, acc_); tmem_wait_ld();
             tile8(S.Qt, op);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -627,7 +672,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 sm.obuf[1][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * E[i]);
             }
             // dK~ -> dk
-            tmem_ld8(tb + C_OK + 48 + 8 * hf, acc_); tmem_wait_ld();
+            tmem_ld8(ok + 48 + 8 * hf, acc_); tmem_wait_ld();
             tile8(S.Kt, op);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -635,7 +680,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 sm.obuf[2][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * iE[i]);
             }
             // dB~ -> db
-            tmem_ld8(tb + C_OK + 32 + 8 * hf, acc_); tmem_wait_ld();
+            tmem_ld8(ok + 32 + 8 * hf, acc_); tmem_wait_ld();
             tile8(S.Bt, op);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -643,7 +688,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 sm.obuf[5][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * iE[i]);
             }
             // dA~ -> da (e^{G_{t-1}} is the previous token's e^{G}); (dA~.A~)_{t+1} joins g_t
-            tmem_ld8(tb + C_OK + 16 + 8 * hf, acc_); tmem_wait_ld();
+            tmem_ld8(ok + 16 + 8 * hf, acc_); tmem_wait_ld();
             tile8(S.At, op);
             {
                 const float gprev2 = (G[0] - lwv[0]) * 1.4426950408889634f;
@@ -658,7 +703,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             const float aa0 = acc_[0] * op[0];
             {   // dV, this warp's 8 tokens
                 float dvv[8];
-                tmem_ld8(tb + C_OV + 8 * hf, dvv); tmem_wait_ld();
+                tmem_ld8(ov + 8 * hf, dvv); tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 8; i++) sm.obuf[3][8 * hf + i][orow] = __float2bfloat16_rn(dvv[i]);
             }
@@ -670,7 +715,7 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 for (int i = 0; i < 8; i++) tot += gsum[i];
                 if (act) { sm.xch[0][row] = aa0; sm.xch[1][row] = tot; }
             }
-            bar_sync(4, 256);
+            bar_sync(5, 256);
             float suffix = suffix_old;
             if (hf == 0) {
                 gsum[7] += sm.xch[0][row];
@@ -683,7 +728,8 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
             if (hf == 0 && act) { sm.suff[row] = suffix; sm.cfirst[row] = aa0; }
         }
-        // window boundary below this chunk: boundary term for the previous window's last token
+        // window boundary below this chunk: boundary term for the previous window's last token, taken from dS^T
+        // (after this chunk's update) before group C1 moves it into the next window's frame
         if (c % WIN == 0 && c > 0) {
             float glp = 0.f;
 #pragma unroll
@@ -701,6 +747,8 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 }
             }
             if (act) sm.glp[hf][row] = glp;
+            fence_before_sync();
+            mbar_arrive_warp(&sm.glp_done);
         }
         if (c == 0 && P.ds0 != nullptr) {
             float *dst = P.ds0 + (size_t)bh * kC * kC + row * kC;
@@ -718,8 +766,9 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
         }
         fence_before_sync();
+        mbar_arrive_warp(&sm.ok_free[it & 1]);
         mbar_arrive_warp(&sm.empty[si]);
-        bar_sync(4, 256);
+        bar_sync(5, 256);
         {   // six gradient tiles [token][channel] bf16 -> 128-byte rows
             bf16 *dst[6] = {P.dw, P.dq, P.dk, P.dv, P.da, P.db};
 #pragma unroll
@@ -729,8 +778,8 @@ __device__ void group_c(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
             }
         }
-        bar_sync(4, 256);
-        TICK(tc6); ACC(10, tc0, tc1); ACC(11, tc1, tc2); ACC(12, tc2, tc3); ACC(13, tc3, tc4); ACC(14, tc4, tc5); ACC(15, tc5, tc6);
+        bar_sync(5, 256);
+        TICK(tc6); ACC(14, tc4, tc5); ACC(15, tc5, tc6);
     }
 }
 
@@ -750,24 +799,25 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
             mbar_init(&sm.full[i], 8 + 4); mbar_init(&sm.empty[i], 8); mbar_init(&sm.a_done[i], 8);
             mbar_init(&sm.blob_full[i], 1);
         }
-        mbar_init(&sm.s0t_ready, 8); mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 8);
+        mbar_init(&sm.resc, 4); mbar_init(&sm.glp_done, 8); mbar_init(&sm.ok_free[0], 8); mbar_init(&sm.ok_free[1], 8);
+        mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 4);
         mbar_init(&sm.out_ready, 1);
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 256);
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
 
-    if (warp < 8) group_c(P, sm, base, tok_stride, bh, nC, tid);
-    else if (warp < 16) stage_a(P, sm, base, tok_stride, bh, nC, tid - 256);
-    else if (warp < 20) stage_b(P, sm, nC, tid - 512, 0);
-    else if (warp < 24) stage_b(P, sm, nC, tid - 640, 1);
+    if (warp < 4) group_c1(P, sm, bh, nC, tid);
+    else if (warp < 12) group_c2(P, sm, base, tok_stride, bh, nC, tid - 128);
+    else if (warp < 20) stage_a(P, sm, base, tok_stride, bh, nC, tid - 384);
+    else if (warp < 24) stage_b(P, sm, nC, tid - 640);
     else mma_warp(P, sm, nC);
 
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 256);
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, 512);
 }
 
 }  // namespace tcbwd
