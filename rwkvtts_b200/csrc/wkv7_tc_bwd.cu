@@ -38,7 +38,7 @@ namespace rwkvtts {
 namespace tcbwd {
 using namespace tc05;
 
-constexpr int L = 16, WIN = 4, NS = 2;
+constexpr int L = 16, WIN = 4, NS = 3;
 constexpr float kMinLogDecay = -1.35f;
 
 // canonical K-major tiles (floats): off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4
@@ -55,7 +55,6 @@ struct Slot {
     float Gt[4 * T_LBO];          // G (fp32, not an MMA operand), same layout
     float AqbpT[4 * S16_LBO], AqkT[4 * S16_LBO], AakT[4 * S16_LBO];   // [n=s][k=t]          (stage B)
     float Gs[kC];                 // G at the chunk start
-    __align__(128) float S0c[kCkFloats];   // checkpoint S0^T as a K-major operand tile [key][value] (bulk copy)
 };
 constexpr int NRAW = 2;
 struct RawBuf { uint2 x[7][256]; };
@@ -66,15 +65,14 @@ struct Smem {
     float QK_AK[4 * S32_LBO];     // rows 0-15 dAqk, 16-31 dAak
     float NT_AKT[4 * S32_LBO];    // rows 0-15 dN^T [s][t], 16-31 dAak^T
     float QBT_QKT[4 * S32_LBO];   // rows 0-15 dAqb^T, 16-31 dAqk^T
-    float Nn[2][L * 20], Aqbn[2][L * 20];   // stage B scratch: N and Aqb, natural [t][s], fp32
     RawBuf raw[NRAW];             // stage A: cp.async landing ring, thread-private
-    float wtot[2][8][kC];         // stage A scan partials
-    float wtotw[WIN][8][kC];      // stage A: per-chunk decay totals of the current window
+    __align__(128) float S0c[kCkFloats];   // checkpoint S0^T of the chunk in flight: K-major operand tile [key][value],
+                                           // brought in by the MMA warp with one bulk copy per chunk
+    // (the scan partials of stages A and B live in tiles of the slot they own that are written later)
     float gst[WIN][kC];           // stage A: G at the start of each chunk of the current window
     float elast[kC];              // group C: e^{G} at a window end
     float glp[2][kC], suff[kC], cfirst[kC], xch[2][kC];   // group C: boundary-term partials, dw suffix, carries
-    __align__(16) bf16 obuf[6][L][72];   // output staging [array][token][channel]
-    uint64_t full[NS], empty[NS], a_done[NS], blob_full[NS];
+    uint64_t full[NS], empty[NS], a_done[NS], blob_full[NS], s0_full;
     uint64_t resc, glp_done, ok_free[2], bar_z, c_done, out_ready;
     uint32_t tmem_base;
 };
@@ -135,8 +133,18 @@ __device__ __forceinline__ void issue_raw(const Params &P, RawBuf &rb, size_t ba
 __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tp) {
     long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
+    // w of every chunk of the window whose last chunk is c_last: needed when a window is entered from its end,
+    // fetched one window ahead
+    auto loadw = [&](int c_last, uint2 (&wr)[WIN]) {
+        const int c0 = (c_last / WIN) * WIN;
+#pragma unroll
+        for (int j = 0; j < WIN; j++)
+            if (c0 + j <= c_last) wr[j] = ldg_nc_v2(P.w + base + (size_t)((c0 + j) * L + t) * tok_stride + k4 * 4);
+    };
+    uint2 wr[WIN];
     issue_raw(P, sm.raw[0], base, tok_stride, nC - 1, tp);      // prologue: chunk of iteration 0
     cp_async_commit();
+    loadw(nC - 1, wr);
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
         Slot &S = sm.slot[si];
@@ -144,13 +152,14 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
         if (it + 1 < nC) issue_raw(P, sm.raw[(it + 1) % NRAW], base, tok_stride, c - 1, tp);   // one chunk ahead
         cp_async_commit();
         const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
+        TICK(ta1);
+        if (it >= NS) mbar_wait(&sm.empty[si], ((it / NS) - 1) & 1);
+        TICK(ta2);
+        float(&wt)[8][kC] = *reinterpret_cast<float(*)[8][kC]>(S.Bpn);          // scratch: stage B writes the tile later
         if (win_last) {
             // entering a window (from its end): G at the start of each of its chunks
+            float(&wtw)[WIN][8][kC] = *reinterpret_cast<float(*)[WIN][8][kC]>(S.DYZn);   // scratch: dY rows come below
             const int c0 = (c / WIN) * WIN, nj = c - c0 + 1;
-            uint2 wr[WIN];
-#pragma unroll
-            for (int j = 0; j < WIN; j++)
-                if (j < nj) wr[j] = ldg_nc_v2(P.w + base + (size_t)((c0 + j) * L + t) * tok_stride + k4 * 4);
 #pragma unroll
             for (int j = 0; j < WIN; j++) {
                 if (j >= nj) break;
@@ -161,15 +170,16 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
                     s4[e] = fmaxf(-__expf(f[e]), kMinLogDecay);
                     s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);
                 }
-                if (t & 1) st4(&sm.wtotw[j][wp][k4 * 4], s4[0], s4[1], s4[2], s4[3]);
+                if (t & 1) st4(&wtw[j][wp][k4 * 4], s4[0], s4[1], s4[2], s4[3]);
             }
+            if (c0 > 0) loadw(c0 - 1, wr);        // the window below
             bar_sync(1, 256);
             if (tp < kC) {
                 float run = 0.f;
                 for (int j = 0; j < nj; j++) {
                     sm.gst[j][tp] = run;
 #pragma unroll
-                    for (int ww = 0; ww < 8; ww++) run += sm.wtotw[j][ww][tp];
+                    for (int ww = 0; ww < 8; ww++) run += wtw[j][ww][tp];
                 }
             }
             bar_sync(1, 256);
@@ -191,7 +201,6 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
             if (t & 1) gg[j] += x;
         }
-        float(&wt)[8][kC] = sm.wtot[it & 1];
         if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
         bar_sync(1, 256);
         {
@@ -205,18 +214,13 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
                 gg[0] += x0.x; gg[1] += x0.y; gg[2] += x0.z; gg[3] += x0.w;
             }
         }
-        TICK(ta1);
-        if (it >= NS) mbar_wait(&sm.empty[si], ((it / NS) - 1) & 1);
-        TICK(ta2);
-        if (wp == 0) {   // checkpoint S0^T and U of this chunk: operand tiles, HBM -> slot, bulk copies
+        if (wp == 0) {   // U of this chunk: operand tile rows, HBM -> slot, bulk copies
             const int ln = tp & 31;
-            if (ln == 0) mbar_expect_tx(&sm.blob_full[si], (kCkFloats + kUFloats) * 4);
+            if (ln == 0) mbar_expect_tx(&sm.blob_full[si], kUFloats * 4);
             __syncwarp();
             if (ln < 16)
                 bulk_g2s(&S.UVn[ln * N32_LBO], P.sa + ((size_t)bh * nC + c) * kUFloats + ln * kULbo, kULbo * 4,
                          &sm.blob_full[si]);
-            else if (ln == 16)
-                bulk_g2s(S.S0c, P.ckT + ((size_t)bh * nC + c) * kCkFloats, kCkFloats * 4, &sm.blob_full[si]);
         }
         {
             float E[4], Ep[4], iE[4], f[4], o[4];
@@ -268,10 +272,11 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
     constexpr int grp = 0;
     long long *P_dbg = (tp == 0 && grp == 0) ? P.dbg : nullptr; (void)P_dbg;
     const int wp = tp >> 5, lane = tp & 31, g = lane >> 2, tq = lane & 3;
-    float *Nn = sm.Nn[grp], *AQ = sm.Aqbn[grp];
     for (int it = 0; it < nC; it++) {
         const int si = it % NS;
         Slot &S = sm.slot[si];
+        // scratch N and Aqb, natural [t][s] fp32, row stride N32_LBO: the Z-row pieces of DYZn (group C1 fills them later)
+        float *Nn = S.DYZn + 64, *AQ = S.DYZn + 96;
         TICK(tb0);
         mbar_wait(&sm.a_done[si], (it / NS) & 1);
         TICK(tb1);
@@ -305,11 +310,11 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
                         if (rowsel) {
                             x = (col <= row) ? x : 0.f;
                             if (colsel) S.AqkT[kmajor_off(col, row, S16_LBO, S_SBO)] = tf32r(x);
-                            else AQ[row * 20 + col] = x;
+                            else AQ[row * N32_LBO + col] = x;
                         } else {
                             x = (col < row) ? x : 0.f;
                             if (colsel) S.AakT[kmajor_off(col, row, S16_LBO, S_SBO)] = tf32r(x);
-                            else Nn[row * 20 + col] = x;
+                            else Nn[row * N32_LBO + col] = x;
                         }
                     }
                 }
@@ -327,14 +332,14 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
                 }
             } else {
 #pragma unroll
-                for (int s = 0; s < L; s++) acc[s] = AQ[(tp - kC) * 20 + s];
+                for (int s = 0; s < L; s++) acc[s] = AQ[(tp - kC) * N32_LBO + s];
             }
 #pragma unroll
             for (int tt = L - 1; tt >= 1; tt--) {
                 const float x = acc[tt];
 #pragma unroll
                 for (int q4 = 0; q4 <= (tt - 1) / 4; q4++) {
-                    const float4 n4 = *reinterpret_cast<const float4 *>(&Nn[tt * 20 + 4 * q4]);
+                    const float4 n4 = *reinterpret_cast<const float4 *>(&Nn[tt * N32_LBO + 4 * q4]);
                     const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
 #pragma unroll
                     for (int e = 0; e < 4; e++)
@@ -361,7 +366,7 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t kadv(uint64_t d, int kk, int lbo_f) { return d + (uint64_t)((kk * 2 * lbo_f * 4) >> 4); }
 
-__device__ void mma_warp(const Params &P, Smem &sm, int nC) {
+__device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
     long long *P_dbg = (threadIdx.x & 31) == 0 ? P.dbg : nullptr; (void)P_dbg;
     const uint32_t tb = sm.tmem_base;
     constexpr uint32_t I16 = idesc_tf32(64, 16, false, false);
@@ -378,7 +383,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
         const uint32_t ok = tb + C_OK + C_OBUF * (it & 1), ov = tb + C_OV + C_OBUF * (it & 1);
         const Slot &S = sm.slot[si];
-        const uint64_t dS0 = smem_desc(smem_u32(S.S0c), kCkLbo * 4, 32 * 4);
+        const uint64_t dS0 = smem_desc(smem_u32(sm.S0c), kCkLbo * 4, 32 * 4);
         const uint64_t dUV = smem_desc(smem_u32(S.UVn), N32_LBO * 4, N_SBO * 4);
         const uint64_t dDYZ = smem_desc(smem_u32(S.DYZn), N32_LBO * 4, N_SBO * 4);
         const uint64_t dKn = smem_desc(smem_u32(S.Kn), N16_LBO * 4, N_SBO * 4);
@@ -404,6 +409,9 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         TICK(tm2);
         fence_after_sync();
         if (elect_one()) {
+            // S0^T of this chunk (the previous chunk's MMAs and, at a window boundary, group C2 are done with the tile)
+            mbar_expect_tx(&sm.s0_full, kCkFloats * 4);
+            bulk_g2s(sm.S0c, P.ckT + ((size_t)bh * nC + c) * kCkFloats, kCkFloats * 4, &sm.s0_full);
             // R1: Z^T = dY^T Aqb' + dS B'^T
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
@@ -434,7 +442,8 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
                 mma_tf32_ts(tb + C_DS, tb + C_Z + 8 * kk, kadv(dAt, kk, T_LBO), I64, true);
         }
         __syncwarp();
-        mbar_wait(&sm.c_done, it & 1);            // group C: Z tiles and the gradient Gram tiles (C has seen blob_full)
+        mbar_wait(&sm.c_done, it & 1);            // group C1: Z tiles and the gradient Gram tiles
+        mbar_wait(&sm.s0_full, it & 1);           // S0^T operand tile
         TICK(tm4);
         fence_after_sync();
         if (elect_one()) {
@@ -472,7 +481,6 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
             mma_commit(&sm.out_ready);
         }
         __syncwarp();
-        (void)c;
         TICK(tm5); ACC(5, tm0, tm1); ACC(6, tm1, tm2); ACC(7, tm2, tm3); ACC(8, tm3, tm4); ACC(9, tm4, tm5);
     }
 }
@@ -631,6 +639,8 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
         Slot &S = sm.slot[si];
         const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
         const uint32_t ok = tb + C_OK + C_OBUF * (it & 1), ov = tb + C_OV + C_OBUF * (it & 1);
+        bf16(*obuf)[L][72] = reinterpret_cast<bf16(*)[L][72]>(S.UVn);      // 6 x 16 x 72 bf16 over UVn + DYZn
+        static_assert(6 * L * 72 * 2 <= 2 * 16 * N32_LBO * 4, "output staging fits in UVn + DYZn");
         if (win_last && it > 0) {
             if (act && hf == 0) { sm.suff[row] = 0.f; sm.cfirst[row] = 0.f; }
             bar_sync(5, 256);
@@ -655,7 +665,11 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 for (int i = 1; i < 8; i++) lwv[i] = G[i] - G[i - 1];
             }
             const float suffix_old = sm.suff[row];
+            // gradients are staged [array][token][channel] in tiles of this slot that are dead once the chunk's MMAs
+            // have completed (UVn + DYZn), then leave as 128-byte rows (2-byte global stores straight from the
+            // registers were measured 1.6x slower for the whole stage)
             const int orow = act ? row : 64 + (lane & 7);          // idle lanes write into the padding columns
+            auto put = [&](int arr, int i, float x) { obuf[arr][8 * hf + i][orow] = __float2bfloat16_rn(x); };
             float E[8], iE[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -669,7 +683,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 gsum[i] = acc_[i] * op[i];
-                sm.obuf[1][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * E[i]);
+                put(1, i, acc_[i] * E[i]);
             }
             // dK~ -> dk
             tmem_ld8(ok + 48 + 8 * hf, acc_); tmem_wait_ld();
@@ -677,7 +691,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 gsum[i] = fmaf(-acc_[i], op[i], gsum[i]);
-                sm.obuf[2][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * iE[i]);
+                put(2, i, acc_[i] * iE[i]);
             }
             // dB~ -> db
             tmem_ld8(ok + 32 + 8 * hf, acc_); tmem_wait_ld();
@@ -685,7 +699,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 gsum[i] = fmaf(-acc_[i], op[i], gsum[i]);
-                sm.obuf[5][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * iE[i]);
+                put(5, i, acc_[i] * iE[i]);
             }
             // dA~ -> da (e^{G_{t-1}} is the previous token's e^{G}); (dA~.A~)_{t+1} joins g_t
             tmem_ld8(ok + 16 + 8 * hf, acc_); tmem_wait_ld();
@@ -696,7 +710,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     if (i > 0) gsum[i - 1] = fmaf(acc_[i], op[i], gsum[i - 1]);
-                    sm.obuf[4][8 * hf + i][orow] = __float2bfloat16_rn(acc_[i] * ep);
+                    put(4, i, acc_[i] * ep);
                     ep = E[i];
                 }
             }
@@ -705,7 +719,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 float dvv[8];
                 tmem_ld8(ov + 8 * hf, dvv); tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 8; i++) sm.obuf[3][8 * hf + i][orow] = __float2bfloat16_rn(dvv[i]);
+                for (int i = 0; i < 8; i++) put(3, i, dvv[i]);
             }
             if (hf == 1) {
                 // token 15 also gets (dA~.A~) of the next chunk's first token and, at a window end, sum_v dS.S
@@ -724,7 +738,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
             for (int i = 7; i >= 0; i--) {
                 suffix += gsum[i];
-                sm.obuf[0][8 * hf + i][orow] = __float2bfloat16_rn(suffix * lwv[i]);
+                put(0, i, suffix * lwv[i]);
             }
             if (hf == 0 && act) { sm.suff[row] = suffix; sm.cfirst[row] = aa0; }
         }
@@ -738,7 +752,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
                 float a_[16];
                 tmem_ld16(tb + C_DST + 16 * cb, a_);
                 tmem_wait_ld();
-                const float *sp = S.S0c + (row >> 3) * 32 + (row & 7) * 4;      // S0^T[key = row][value]
+                const float *sp = sm.S0c + (row >> 3) * 32 + (row & 7) * 4;      // S0^T[key = row][value]
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 x = *reinterpret_cast<const float4 *>(sp + (4 * cb + i) * kCkLbo);
@@ -767,18 +781,22 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
         }
         fence_before_sync();
         mbar_arrive_warp(&sm.ok_free[it & 1]);
-        mbar_arrive_warp(&sm.empty[si]);
-        bar_sync(5, 256);
+        bar_sync(5, 256);       // staged tiles complete; suff / cfirst / xch / glp in place for the next chunk
         {   // six gradient tiles [token][channel] bf16 -> 128-byte rows
             bf16 *dst[6] = {P.dw, P.dq, P.dk, P.dv, P.da, P.db};
+            uint4 v[3];
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const int e = tid + 256 * i, arr = e >> 7, tok = (e >> 3) & 15, part = e & 7;
-                const uint4 v = *reinterpret_cast<const uint4 *>(&sm.obuf[arr][tok][part * 8]);
-                *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
+                v[i] = *reinterpret_cast<const uint4 *>(&obuf[arr][tok][part * 8]);
+            }
+            mbar_arrive_warp(&sm.empty[si]);            // the slot (tiles and staging) has been read
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                const int e = tid + 256 * i, arr = e >> 7, tok = (e >> 3) & 15, part = e & 7;
+                *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v[i];
             }
         }
-        bar_sync(5, 256);
         TICK(tc6); ACC(14, tc4, tc5); ACC(15, tc5, tc6);
     }
 }
@@ -799,6 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
             mbar_init(&sm.full[i], 8 + 4); mbar_init(&sm.empty[i], 8); mbar_init(&sm.a_done[i], 8);
             mbar_init(&sm.blob_full[i], 1);
         }
+        mbar_init(&sm.s0_full, 1);
         mbar_init(&sm.resc, 4); mbar_init(&sm.glp_done, 8); mbar_init(&sm.ok_free[0], 8); mbar_init(&sm.ok_free[1], 8);
         mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 4);
         mbar_init(&sm.out_ready, 1);
@@ -813,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
     else if (warp < 12) group_c2(P, sm, base, tok_stride, bh, nC, tid - 128);
     else if (warp < 20) stage_a(P, sm, base, tok_stride, bh, nC, tid - 384);
     else if (warp < 24) stage_b(P, sm, nC, tid - 640);
-    else mma_warp(P, sm, nC);
+    else mma_warp(P, sm, bh, nC);
 
     fence_before_sync();
     __syncthreads();
