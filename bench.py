@@ -220,15 +220,38 @@ def main():
     h2d = sum(t_.numel() * t_.element_size() for t_ in host_in) * LAYERS
     d2h = sum(t_.numel() * t_.element_size() for t_ in host_out) * LAYERS
 
+    # Copies of layer l+1 (H2D) and of layer l-1 (D2H) overlap the kernels of layer l: three streams, device input
+    # buffers double buffered, events for the hand-offs.  PCIe is full duplex, so the step is bound by the larger of
+    # the two copy directions (0.47 GB each way per layer), not by their sum.
+    s_comp = torch.cuda.current_stream()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    dev_in = [[torch.empty_like(d["v"]) for _ in range(7)] for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]          # inputs of buffer b have landed
+    ev_free = [torch.cuda.Event() for _ in range(2)]        # kernels are done with buffer b
+    ev_out = [torch.cuda.Event() for _ in range(2)]         # results of buffer b are in host memory
+
     def e2e_step():
-        for _ in range(LAYERS):
-            dv = [t_.to(dev, non_blocking=True) for t_ in host_in]
-            leaves = [t_.requires_grad_(True) for t_ in dv[:6]]
+        for l in range(LAYERS):
+            b = l % 2
+            with torch.cuda.stream(s_in):
+                if l >= 2:
+                    s_in.wait_event(ev_free[b])
+                for t_, h_ in zip(dev_in[b], host_in):
+                    t_.copy_(h_, non_blocking=True)
+                ev_in[b].record(s_in)
+            s_comp.wait_event(ev_in[b])
+            leaves = [t_.detach().requires_grad_(True) for t_ in dev_in[b][:6]]
             yy = R.WindBackstepping.apply(*leaves)
-            yy.backward(dv[6])
-            host_out[0].copy_(yy.detach(), non_blocking=True)
-            for o, l in zip(host_out[1:], leaves):
-                o.copy_(l.grad, non_blocking=True)
+            yy.backward(dev_in[b][6])
+            ev_free[b].record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[b])
+                outs = [yy.detach()] + [l_.grad for l_ in leaves]
+                for o, r_ in zip(host_out, outs):
+                    r_.record_stream(s_out)
+                    o.copy_(r_, non_blocking=True)
+                ev_out[b].record(s_out)
+        s_comp.wait_stream(s_out)
 
     e2e_step()
     barrier()
@@ -292,7 +315,7 @@ def main():
                    "l2": "inputs+outputs of one layer-call are 0.47-0.87 GB, larger than the 126 MB L2; "
                          "no explicit flush"},
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "rwkvtts_b200.WindBackstepping (autograd) with pinned host tensors", "steps": args.e2e_steps},
+                "api": "rwkvtts_b200.WindBackstepping (autograd) with pinned host tensors; H2D / kernels / D2H of consecutive layers overlapped on three streams", "steps": args.e2e_steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": f"wkv7 {dom}", "achieved": ach, "peak": peak, "unit": "GB/s",
@@ -306,8 +329,8 @@ def main():
                     "decode_step_wkv_ms": decode_ms,
                     "decode_step_GBps": (2 * C * C * 4 + FWD_BYTES) * DB * H * LAYERS / (decode_ms * 1e-3) / 1e9,
                     "decode_wkv_tokens_per_s": DB / (decode_ms * 1e-3),
-                    "note": "fwd/bwd = training pair (scan kernels, exact snapshots); fwd_infer = chunked tcgen05 "
-                            "forward used under no_grad; decode = stateful op, T=1, B=32, 24 layers (config c4)"},
+                    "note": "fwd/bwd = training pair (chunked tcgen05 kernels, default family); fwd_infer = snapshot-free "
+                            "tcgen05 forward used under no_grad; decode = stateful scan op, T=1, B=32, 24 layers (config c4)"},
         "ref_gpu_op": ref_gpu,
     }
     if world == 1 and not args.no_cpu_baseline:

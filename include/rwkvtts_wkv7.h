@@ -128,6 +128,54 @@ RWKVTTS_API int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg
                        float beta2, float eps, float weight_decay, int adamw_mode, float bias_correction1,
                        float bias_correction2_sqrt, float grad_scale, void *stream);
 
+/* ---- fused elementwise kernels of the time-mix around the WKV-7 op ---------------------------------------------
+ * Replace the ~30 ATen elementwise kernels RWKV_Tmix_x070.forward runs per layer between its GEMMs
+ * (model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226).
+ * Activations bf16 [B,T,C] contiguous, C = H*64; `mask` bf16 [B,T] of 0/1 or NULL (attention_mask, :160,:175-190);
+ * per-channel parameters fp32 [C]; parameter gradients fp32, summed deterministically through `scratch`
+ * (rwkvtts_tmix_scratch_floats floats, caller-allocated).  Each *_backward is the exact adjoint of its forward. */
+
+/* scratch floats for a backward with n_params per-channel parameter vectors (6 / 1 shift_mix, 5 prep, 3 out) */
+RWKVTTS_API size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params);
+
+/* out[i] = x + (shift(x) - x) * mix[i], i < n (n = 6: x_r,x_w,x_k,x_v,x_a,x_g :164-169; n = 1: x_k of channel-mix :226).
+ * shift(x)[t] = x[t-1], first token from `prev` [B,C] (NULL = zeros, ZeroPad2d :162); x is multiplied by mask first. */
+RWKVTTS_API int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask,
+                                               const void *prev, const float *mix, void *const *out, void *stream);
+RWKVTTS_API int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask,
+                                                const void *prev, const float *mix, const void *const *dout, void *dx,
+                                                float *dmix, float *scratch, void *stream);
+
+/* From the projections k, v and the LoRA outputs w_lo = tanh(xw@w1)@w2, a_lo = (xa@a1)@a2, v_lo = (xv@v1)@v2:
+ *   w = -softplus(-(w0 + w_lo)) - 0.5 (:172);  a = sigmoid(a0 + a_lo) (:183);
+ *   v' = v + (v_first - v) * sigmoid(v0 + v_lo) (:182; v_lo = v_first = NULL on layer 0, then v' = v);
+ *   kk = l2-normalise per head (k * k_k) (:186-187);  k' = k * (1 + (a - 1) * k_a) (:189);
+ *   WKV operands a_op = -kk, b_op = kk * a (:191);  w, k, v, kk masked as :175-190.
+ * v2 may be NULL when there is neither a mask nor a v residual (v' = v). */
+RWKVTTS_API int rwkvtts_tmix_prep_forward(int B, int T, int C, const void *k, const void *v, const void *w_lo,
+                                          const void *a_lo, const void *v_lo, const void *v_first, const void *mask,
+                                          const float *w0, const float *a0, const float *v0, const float *k_k,
+                                          const float *k_a, void *w, void *k2, void *v2, void *a_op, void *b_op,
+                                          void *stream);
+/* dparams: fp32 [5][C] = d w0, d a0, d v0, d k_k, d k_a.  dv / dv_lo / dv_first may be NULL together with dv2. */
+RWKVTTS_API int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v, const void *w_lo,
+                                           const void *a_lo, const void *v_lo, const void *v_first, const void *mask,
+                                           const float *w0, const float *a0, const float *v0, const float *k_k,
+                                           const float *k_a, const void *dw, const void *dk2, const void *dv2,
+                                           const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
+                                           void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch,
+                                           void *stream);
+
+/* o = (GroupNorm_H(y; ln_w, ln_b, eps) + (sum_head r * k' * r_k) * v') * g  (:192-195, the input of the output
+ * projection).  dparams: fp32 [3][C] = d r_k, d ln_w, d ln_b. */
+RWKVTTS_API int rwkvtts_tmix_out_forward(int B, int T, int C, const void *y, const void *r, const void *k2,
+                                         const void *v2, const void *g, const float *r_k, const float *ln_w,
+                                         const float *ln_b, float eps, void *o, void *stream);
+RWKVTTS_API int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, const void *r, const void *k2,
+                                          const void *v2, const void *g, const float *r_k, const float *ln_w,
+                                          const float *ln_b, float eps, const void *d_o, void *dy, void *dr, void *dk2,
+                                          void *dv2, void *dg, float *dparams, float *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

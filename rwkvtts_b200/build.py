@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librwkvtts_wkv7.so")
-SOURCES = ["capi.cu", "wkv7_scan.cu", "wkv7_tc_fwd.cu", "wkv7_tc_bwd.cu", "adam.cu"]
+SOURCES = ["capi.cu", "wkv7_scan.cu", "wkv7_tc_fwd.cu", "wkv7_tc_bwd.cu", "tmix_fused.cu", "adam.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

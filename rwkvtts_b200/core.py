@@ -13,7 +13,10 @@ rwkvfla-named modules (rwkvfla/) are two thin parameter adapters over the same c
 
 The recurrence itself always runs in the CUDA library (ops.py): WindBackstepping for training,
 the snapshot-free tcgen05 forward for no-grad prefill, the stateful scan for any-T / decode steps.
-Everything else here is torch (GEMMs through cuBLAS, elementwise through ATen): plumbing around the op.
+On CUDA bf16 activations the elementwise chain between the GEMMs runs in three fused kernels (fused.py:
+token-shift + lerps; decay / gates / kk / WKV operands; GroupNorm + bonus + gate), forward and backward; the
+GEMMs go through cuBLAS.  The ATen formulation below them is what the CPU oracle tests and fp32 callers use
+(`FUSED = False` or env RWKVTTS_FUSED=0 selects it on the GPU too).
 """
 from __future__ import annotations
 
@@ -23,9 +26,12 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-from . import ops
+import os
+
+from . import fused, ops
 
 HEAD = ops.HEAD_SIZE
+FUSED = os.environ.get("RWKVTTS_FUSED", "1") != "0"
 
 
 @dataclass
@@ -110,6 +116,8 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536)."""
     B, T, C = x.shape
     H = C // HEAD
+    if FUSED and fused.usable(x) and (mask is None or mask_rwk):
+        return _tmix_fused(p, layer_id, x, v_first, mask, shift_state, wkv_state, need_state, inplace_state)
     if mask is not None:
         x = x * mask                                                            # :160
     xx = token_shift(x, shift_state)                                            # :162
@@ -141,10 +149,43 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     return out, v_first, (x[:, -1] if need_state else None), new_state
 
 
+def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, shift_state, wkv_state, need_state, inplace_state):
+    """tmix() with the elementwise chain in the fused kernels (same reference lines, same results up to bf16
+    rounding of intermediates the fused kernels keep in fp32)."""
+    xr, xw, xk, xv, xa, xg = fused.shift_mix(x, (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g), mask, shift_state)  # :160-169
+    r = F.linear(xr, p.W_r)
+    k = F.linear(xk, p.W_k)
+    v = F.linear(xv, p.W_v)
+    w_lo = torch.tanh(xw @ p.w1) @ p.w2
+    a_lo = (xa @ p.a1) @ p.a2
+    g = torch.sigmoid(xg @ p.g1) @ p.g2                                         # :184
+    if mask is not None:
+        r = r * mask                                                            # :175
+    if layer_id == 0:
+        w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, None, None, p.w0, p.a0, None, p.k_k, p.k_a, mask)
+        v_first = v2                                                            # :180
+    else:
+        w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, (xv @ p.v1) @ p.v2, v_first, p.w0, p.a0, p.v0, p.k_k,
+                                           p.k_a, mask)                         # :172-190
+    y, new_state = _wkv(r.contiguous(), w, k2, v2.contiguous(), a_op, b_op, wkv_state, need_state, inplace_state)   # :191
+    o = fused.out(y, r, k2, v2, g, p.r_k, p.ln_w, p.ln_b, p.ln_eps)             # :192-195
+    shift_out = None
+    if need_state:
+        shift_out = x[:, -1] if mask is None else x[:, -1] * mask[:, -1]
+    return F.linear(o, p.W_o), v_first, shift_out, new_state
+
+
 def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch.Tensor,
          mask: Optional[torch.Tensor] = None, shift_state: Optional[torch.Tensor] = None,
          need_state: bool = False):
     """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556)."""
+    if FUSED and fused.usable(x):
+        (xk,) = fused.shift_mix(x, (x_k,), mask, shift_state)                   # :224-226
+        k = torch.relu(F.linear(xk, W_key)) ** 2
+        last = None
+        if need_state:
+            last = x[:, -1] if mask is None else x[:, -1] * mask[:, -1]
+        return F.linear(k, W_value), last
     if mask is not None:
         x = x * mask
     xx = token_shift(x, shift_state)

@@ -27,6 +27,28 @@ cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, c
 cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *grad, int grad_is_bf16, void *param,
                               int param_is_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
                               int adamw, float bc1, float bc2_sqrt, float gscale, cudaStream_t st);
+int tmix_grid(int B, int T, int C, int which);
+cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                 const float *mix, void *const *out, cudaStream_t st);
+cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                 const float *mix, const void *const *dout, void *dx, float *dmix, float *part,
+                                 cudaStream_t st);
+cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                            const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                            const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2, void *a_op,
+                            void *b_op, cudaStream_t st);
+cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                            const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                            const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
+                            const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
+                            void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *part, cudaStream_t st);
+cudaError_t launch_out_fwd(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                           const void *g_, const float *r_k, const float *ln_w, const float *ln_b, float eps, void *o,
+                           cudaStream_t st);
+cudaError_t launch_out_bwd(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                           const void *g_, const float *r_k, const float *ln_w, const float *ln_b, float eps,
+                           const void *d_o, void *dy, void *dr, void *dk2, void *dv2, void *dg, float *dparams,
+                           float *part, cudaStream_t st);
 }  // namespace rwkvtts
 
 namespace {
@@ -178,6 +200,86 @@ int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg_sq, const v
     return finish(rwkvtts::launch_adam_shard(master, exp_avg, exp_avg_sq, grad, grad_is_bf16, param, param_is_bf16, n,
                                              lr, beta1, beta2, eps, weight_decay, adamw_mode, bias_correction1,
                                              bias_correction2_sqrt, grad_scale, (cudaStream_t)stream));
+}
+
+// ---- fused time-mix elementwise kernels ------------------------------------------------------------------------
+static bool tmix_shape_ok(int B, int T, int C) { return B > 0 && T > 0 && C > 0 && C % RWKVTTS_HEAD_SIZE == 0 && C <= 4096; }
+
+size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params) {
+    if (!tmix_shape_ok(B, T, C) || n_params <= 0) return 0;
+    return (size_t)rwkvtts::tmix_grid(B, T, C, 0) * n_params * C;
+}
+
+int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                   const float *mix, void *const *out, void *stream) {
+    if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
+    if (out == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({x, mix})) return rc;
+    for (int i = 0; i < n; i++)
+        if (int rc = check_ptrs({out[i]})) return rc;
+    if (int rc = check_opt({prev})) return rc;
+    return finish(rwkvtts::launch_shift_mix_fwd(B, T, C, n, x, mask, prev, mix, out, (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                    const float *mix, const void *const *dout, void *dx, float *dmix, float *scratch,
+                                    void *stream) {
+    if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
+    if (dout == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({x, mix, dx, dmix, scratch})) return rc;
+    for (int i = 0; i < n; i++)
+        if (int rc = check_ptrs({dout[i]})) return rc;
+    if (int rc = check_opt({prev})) return rc;
+    return finish(rwkvtts::launch_shift_mix_bwd(B, T, C, n, x, mask, prev, mix, dout, dx, dmix, scratch,
+                                                (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_prep_forward(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                              const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                              const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2,
+                              void *a_op, void *b_op, void *stream) {
+    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({k, w_lo, a_lo, w0, a0, k_k, k_a, w, k2, a_op, b_op})) return rc;
+    if ((v_lo == nullptr) != (v_first == nullptr) || (v_lo != nullptr && v0 == nullptr)) return RWKVTTS_ERR_NULL;
+    if ((v_lo != nullptr || mask != nullptr) && (v == nullptr || v2 == nullptr)) return RWKVTTS_ERR_NULL;
+    if (int rc = check_opt({v, v_lo, v_first, v0, v2})) return rc;
+    return finish(rwkvtts::launch_prep_fwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, w, k2, v2,
+                                           a_op, b_op, (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                               const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                               const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
+                               const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
+                               void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch, void *stream) {
+    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({k, w_lo, a_lo, w0, a0, k_k, k_a, dw, dk2, da_op, db_op, dk, dw_lo, da_lo, dparams, scratch}))
+        return rc;
+    if ((v_lo == nullptr) != (v_first == nullptr) || (v_lo != nullptr && v0 == nullptr)) return RWKVTTS_ERR_NULL;
+    if (dv != nullptr && (dv2 == nullptr || v == nullptr)) return RWKVTTS_ERR_NULL;
+    if (v_lo != nullptr && (dv == nullptr || dv_lo == nullptr || dv_first == nullptr)) return RWKVTTS_ERR_NULL;
+    if (int rc = check_opt({v, v_lo, v_first, v0, dv2, dv, dv_lo, dv_first})) return rc;
+    return finish(rwkvtts::launch_prep_bwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, dw, dk2, dv2,
+                                           da_op, db_op, dk, dv, dw_lo, da_lo, dv_lo, dv_first, dparams, scratch,
+                                           (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_out_forward(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                             const void *g, const float *r_k, const float *ln_w, const float *ln_b, float eps, void *o,
+                             void *stream) {
+    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({y, r, k2, v2, g, r_k, ln_w, ln_b, o})) return rc;
+    return finish(rwkvtts::launch_out_fwd(B, T, C, y, r, k2, v2, g, r_k, ln_w, ln_b, eps, o, (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                              const void *g, const float *r_k, const float *ln_w, const float *ln_b, float eps,
+                              const void *d_o, void *dy, void *dr, void *dk2, void *dv2, void *dg, float *dparams,
+                              float *scratch, void *stream) {
+    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({y, r, k2, v2, g, r_k, ln_w, ln_b, d_o, dy, dr, dk2, dv2, dg, dparams, scratch})) return rc;
+    return finish(rwkvtts::launch_out_bwd(B, T, C, y, r, k2, v2, g, r_k, ln_w, ln_b, eps, d_o, dy, dr, dk2, dv2, dg, dparams,
+                                          scratch, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,621 @@
+// Fused elementwise kernels of the RWKV-7 time-mix around the WKV-7 op (sm_100a), forward and backward.
+//
+// Reference: RWKV_Tmix_x070.forward, model/llm/rwkv_s2s_single_ffn.py:158-196 (and RWKV_CMix_x070.forward :223-230 for
+// the single-output token-shift lerp).  Between its GEMMs the reference runs ~30 elementwise ATen kernels over
+// [B,T,C] activations per layer; here they are three kernels (each with its adjoint):
+//
+//   shift_mix   x -> x + (shift(x) - x) * mix_i, i < n          (:160-169; n = 6 time-mix, n = 1 channel-mix :226)
+//   prep        k, v, LoRA outputs -> w, k', v', -kk, kk*a       (:172, :175-190: decay transform, gates, v-residual,
+//                                                                 per-head l2-normalised kk, k update, WKV operands a, b)
+//   out         y (WKV), r, k', v', g -> (GroupNorm(y) + bonus) * g   (:192-195, input of the output projection)
+//
+// All are HBM-bound streaming kernels: one thread owns 8 adjacent channels (16-byte bf16 loads / stores) of a row
+// (= one token), a head (64 channels) is 8 adjacent lanes (reductions by shuffle), a CTA processes kRows rows at a time
+// and strides over the rows with a fixed thread <-> channel assignment, so per-channel parameters live in registers and
+// per-channel parameter gradients are accumulated in registers, reduced over the CTA's rows in shared memory and
+// written as one partial per CTA (summed by reduce_partials: deterministic, no atomics).
+// Arithmetic in fp32, one rounding to bf16 at the stores.
+#include "wkv7_common.cuh"
+
+namespace rwkvtts {
+namespace tmixf {
+
+constexpr int kVec = 8;          // channels per thread
+constexpr int kMaxThreads = 512;
+
+struct Row8 { float v[kVec]; };
+
+__device__ __forceinline__ Row8 ld8(const bf16 *p) {
+    Row8 r;
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    unpack8(u, r.v);
+    return r;
+}
+__device__ __forceinline__ Row8 ld8f(const float *p) {
+    Row8 r;
+    const float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ Row8 zero8() {
+    Row8 r;
+#pragma unroll
+    for (int i = 0; i < kVec; i++) r.v[i] = 0.f;
+    return r;
+}
+__device__ __forceinline__ void st8(bf16 *p, const Row8 &r, bool pred = true) {
+    if (!pred) return;
+    uint4 u;
+    u.x = pack2(r.v[0], r.v[1]); u.y = pack2(r.v[2], r.v[3]); u.z = pack2(r.v[4], r.v[5]); u.w = pack2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4 *>(p) = u;
+}
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// sum over the 8 lanes that hold one head
+__device__ __forceinline__ float head_sum(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    return x;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// CTA-level reduction of per-thread partial sums over the CTA's row lanes, written to part[blockIdx.x][slot][C]
+template <int N>
+__device__ __forceinline__ void write_partials(float (&acc)[N][kVec], float *part, int C, int tpr, int rl, int cl,
+                                               float *smem /* [kRows][N*C] */) {
+    const int nrl = blockDim.x / tpr;
+    float *mine = smem + (size_t)rl * N * C;
+#pragma unroll
+    for (int s = 0; s < N; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) mine[s * C + cl * kVec + i] = acc[s][i];
+    __syncthreads();
+    float *dst = part + (size_t)blockIdx.x * N * C;
+    for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
+        float x = 0.f;
+        for (int j = 0; j < nrl; j++) x += smem[(size_t)j * N * C + e];
+        dst[e] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// shift_mix
+// ------------------------------------------------------------------------------------------------------------------
+struct MixParams {
+    const bf16 *x;          // [B,T,C]
+    const bf16 *mask;       // [B,T] or null
+    const bf16 *prev;       // [B,C] or null (last token of the previous call)
+    const float *mix;       // [n][C]
+    bf16 *out[6];           // n outputs [B,T,C]
+    const bf16 *dout[6];    // backward: n output gradients
+    bf16 *dx;               // backward: [B,T,C]
+    float *part;            // backward: [grid][n][C] partial d mix
+    int B, T, C, n;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixParams P) {
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    float mix[N][kVec];
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+        const Row8 m = ld8f(P.mix + (size_t)s * P.C + c0);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) mix[s][i] = m.v[i];
+    }
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const int t = (int)(row % P.T), b = (int)(row / P.T);
+        Row8 x = ld8(P.x + row * P.C + c0), xp;
+        if (t > 0) xp = ld8(P.x + (row - 1) * P.C + c0);
+        else if (P.prev != nullptr) xp = ld8(P.prev + (size_t)b * P.C + c0);
+        else xp = zero8();
+        if (P.mask != nullptr) {
+            const float m = __bfloat162float(P.mask[row]), mp = (t > 0) ? __bfloat162float(P.mask[row - 1]) : 1.f;
+#pragma unroll
+            for (int i = 0; i < kVec; i++) { x.v[i] *= m; xp.v[i] *= mp; }
+        }
+        Row8 xx;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) xx.v[i] = rbf(xp.v[i] - x.v[i]);       // the reference rounds shift(x) - x to bf16
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            Row8 o;
+#pragma unroll
+            for (int i = 0; i < kVec; i++) o.v[i] = fmaf(xx.v[i], mix[s][i], x.v[i]);
+            st8(P.out[s] + row * P.C + c0, o, valid);
+        }
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kMaxThreads) shift_mix_bwd_kernel(const MixParams P) {
+    extern __shared__ float red[];
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    float mix[N][kVec], acc[N][kVec];
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+        const Row8 m = ld8f(P.mix + (size_t)s * P.C + c0);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { mix[s][i] = m.v[i]; acc[s][i] = 0.f; }
+    }
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const int t = (int)(row % P.T), b = (int)(row / P.T);
+        Row8 x = ld8(P.x + row * P.C + c0), xp;
+        if (t > 0) xp = ld8(P.x + (row - 1) * P.C + c0);
+        else if (P.prev != nullptr) xp = ld8(P.prev + (size_t)b * P.C + c0);
+        else xp = zero8();
+        float m = 1.f;
+        if (P.mask != nullptr) {
+            m = __bfloat162float(P.mask[row]);
+            const float mp = (t > 0) ? __bfloat162float(P.mask[row - 1]) : 1.f;
+#pragma unroll
+            for (int i = 0; i < kVec; i++) { x.v[i] *= m; xp.v[i] *= mp; }
+        }
+        Row8 dx = zero8();
+        const bool has_next = t + 1 < P.T;
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            Row8 d = zero8(), dn = zero8();
+            if (valid) d = ld8(P.dout[s] + row * P.C + c0);
+            if (valid && has_next) dn = ld8(P.dout[s] + (row + 1) * P.C + c0);
+#pragma unroll
+            for (int i = 0; i < kVec; i++) {
+                acc[s][i] = fmaf(d.v[i], rbf(xp.v[i] - x.v[i]), acc[s][i]);
+                dx.v[i] += d.v[i] * (1.f - mix[s][i]) + dn.v[i] * mix[s][i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; i++) dx.v[i] *= m;
+        st8(P.dx + row * P.C + c0, dx, valid);
+    }
+    write_partials<N>(acc, P.part, P.C, tpr, rl, cl, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const bf16 *k, *v, *w_lo, *a_lo, *v_lo, *v_first;   // [B,T,C]; v_lo / v_first null on layer 0
+    const bf16 *mask;                                     // [B,T] or null
+    const float *w0, *a0, *v0, *k_k, *k_a;                // [C]
+    bf16 *w, *k2, *v2, *a_op, *b_op;                      // outputs [B,T,C]  (v2 null on layer 0 without mask)
+    // backward
+    const bf16 *dw, *dk2, *dv2, *da_op, *db_op;
+    bf16 *dk, *dv, *dw_lo, *da_lo, *dv_lo, *dv_first;
+    float *part;                                          // [grid][5][C]: dw0, da0, dv0, dk_k, dk_a
+    int B, T, C;
+};
+
+__device__ __forceinline__ float neg_softplus_neg(float z) {   // -softplus(-z) with torch's threshold 20
+    const float y = -z;
+    return (y > 20.f) ? -y : -log1pf(__expf(y));
+}
+
+__global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams P) {
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    const Row8 w0 = ld8f(P.w0 + c0), a0 = ld8f(P.a0 + c0), kk_ = ld8f(P.k_k + c0), ka = ld8f(P.k_a + c0);
+    const bool has_v = P.v_lo != nullptr;
+    const Row8 v0 = has_v ? ld8f(P.v0 + c0) : zero8();
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const size_t off = row * P.C + c0;
+        const float m = (P.mask != nullptr) ? __bfloat162float(P.mask[row]) : 1.f;
+        Row8 k = ld8(P.k + off);
+        const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
+        Row8 w, a, u, o;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            k.v[i] *= m;
+            w.v[i] = (neg_softplus_neg(w0.v[i] + wl.v[i]) - 0.5f) * m;
+            a.v[i] = rbf(sigmoidf_(a0.v[i] + al.v[i]));
+            u.v[i] = k.v[i] * kk_.v[i];
+            ss = fmaf(u.v[i], u.v[i], ss);
+        }
+        st8(P.w + off, w, valid);
+        const float inv = m / fmaxf(sqrtf(head_sum(ss)), 1e-12f);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { u.v[i] = rbf(u.v[i] * inv); o.v[i] = -u.v[i]; }     // kk (masked)
+        st8(P.a_op + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = u.v[i] * a.v[i];
+        st8(P.b_op + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = k.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i]);
+        st8(P.k2 + off, o, valid);
+        if (P.v2 != nullptr) {
+            Row8 v = ld8(P.v + off);
+            if (has_v) {
+                const Row8 vl = ld8(P.v_lo + off), vf = ld8(P.v_first + off);
+#pragma unroll
+                for (int i = 0; i < kVec; i++) {
+                    const float vm = v.v[i] * m;          // the reference masks v before the residual mix (:178) ...
+                    v.v[i] = (vm + (vf.v[i] - vm) * sigmoidf_(v0.v[i] + vl.v[i])) * m;     // ... and after it (:190)
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kVec; i++) v.v[i] *= m;
+            }
+            st8(P.v2 + off, v, valid);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams P) {
+    extern __shared__ float red[];
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    const Row8 w0 = ld8f(P.w0 + c0), a0 = ld8f(P.a0 + c0), kk_ = ld8f(P.k_k + c0), ka = ld8f(P.k_a + c0);
+    const bool has_v = P.v_lo != nullptr;
+    const Row8 v0 = has_v ? ld8f(P.v0 + c0) : zero8();
+    float acc[5][kVec];
+#pragma unroll
+    for (int s = 0; s < 5; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const size_t off = row * P.C + c0;
+        const float m = (P.mask != nullptr) ? __bfloat162float(P.mask[row]) : 1.f;
+        Row8 k = ld8(P.k + off);
+        const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
+        Row8 dw = zero8(), dk2 = zero8(), da_op = zero8(), db_op = zero8();
+        if (valid) { dw = ld8(P.dw + off); dk2 = ld8(P.dk2 + off); da_op = ld8(P.da_op + off); db_op = ld8(P.db_op + off); }
+        Row8 a, u, o;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            k.v[i] *= m;
+            a.v[i] = sigmoidf_(a0.v[i] + al.v[i]);
+            u.v[i] = k.v[i] * kk_.v[i];
+            ss = fmaf(u.v[i], u.v[i], ss);
+        }
+        // w = (-softplus(-z) - 0.5) * m
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            o.v[i] = dw.v[i] * m * sigmoidf_(-(w0.v[i] + wl.v[i]));
+            acc[0][i] += o.v[i];
+        }
+        st8(P.dw_lo + off, o, valid);
+        // kk = u / n * m ;  a_op = -kk, b_op = kk * a
+        const float n = fmaxf(sqrtf(head_sum(ss)), 1e-12f), inv = 1.f / n;
+        Row8 kk, dkk;
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            kk.v[i] = u.v[i] * inv;
+            dkk.v[i] = (db_op.v[i] * a.v[i] - da_op.v[i]) * m;
+            dot = fmaf(kk.v[i], dkk.v[i], dot);
+        }
+        dot = head_sum(dot);
+        // a: b_op = kk*m*a, k2 = k (1 + (a-1) k_a)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            const float da = db_op.v[i] * kk.v[i] * m + dk2.v[i] * k.v[i] * ka.v[i];
+            o.v[i] = da * a.v[i] * (1.f - a.v[i]);
+            acc[1][i] += o.v[i];
+        }
+        st8(P.da_lo + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            const float du = (dkk.v[i] - kk.v[i] * dot) * inv;
+            acc[3][i] = fmaf(du, k.v[i], acc[3][i]);
+            acc[4][i] = fmaf(dk2.v[i] * k.v[i], a.v[i] - 1.f, acc[4][i]);
+            o.v[i] = (du * kk_.v[i] + dk2.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i])) * m;
+        }
+        st8(P.dk + off, o, valid);
+        if (P.dv != nullptr) {
+            const Row8 dv2 = valid ? ld8(P.dv2 + off) : zero8();
+            if (has_v) {
+                const Row8 v = ld8(P.v + off), vl = ld8(P.v_lo + off), vf = ld8(P.v_first + off);
+                Row8 dvl, dvf;
+#pragma unroll
+                for (int i = 0; i < kVec; i++) {
+                    const float s = sigmoidf_(v0.v[i] + vl.v[i]), g = dv2.v[i] * m, vm = v.v[i] * m;
+                    o.v[i] = g * (1.f - s) * m;
+                    dvf.v[i] = g * s;
+                    dvl.v[i] = g * (vf.v[i] - vm) * s * (1.f - s);
+                    acc[2][i] += dvl.v[i];
+                }
+                st8(P.dv + off, o, valid);
+                st8(P.dv_lo + off, dvl, valid);
+                st8(P.dv_first + off, dvf, valid);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kVec; i++) o.v[i] = dv2.v[i] * m;
+                st8(P.dv + off, o, valid);
+            }
+        }
+    }
+    write_partials<5>(acc, P.part, P.C, tpr, rl, cl, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// out
+// ------------------------------------------------------------------------------------------------------------------
+struct OutParams {
+    const bf16 *y, *r, *k2, *v2, *g;          // [B,T,C]
+    const float *r_k, *ln_w, *ln_b;           // [C]
+    bf16 *o;                                  // [B,T,C]
+    // backward
+    const bf16 *d_o;
+    bf16 *dy, *dr, *dk2, *dv2, *dg;
+    float *part;                              // [grid][3][C]: dr_k, dln_w, dln_b
+    float eps;
+    int B, T, C;
+};
+
+__global__ void __launch_bounds__(kMaxThreads) out_fwd_kernel(const OutParams P) {
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    const Row8 rk = ld8f(P.r_k + c0), lw = ld8f(P.ln_w + c0), lb = ld8f(P.ln_b + c0);
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const size_t off = row * P.C + c0;
+        const Row8 y = ld8(P.y + off), r = ld8(P.r + off), k = ld8(P.k2 + off), v = ld8(P.v2 + off), g = ld8(P.g + off);
+        float s1 = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { s1 += y.v[i]; sb = fmaf(r.v[i] * k.v[i], rk.v[i], sb); }
+        const float mu = head_sum(s1) * (1.f / kC);
+        sb = head_sum(sb);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { const float d = y.v[i] - mu; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(head_sum(s2) * (1.f / kC) + P.eps);
+        Row8 o;
+#pragma unroll
+        for (int i = 0; i < kVec; i++)
+            o.v[i] = (rbf((y.v[i] - mu) * rstd * lw.v[i] + lb.v[i]) + sb * v.v[i]) * g.v[i];
+        st8(P.o + off, o, valid);
+    }
+}
+
+__global__ void __launch_bounds__(kMaxThreads) out_bwd_kernel(const OutParams P) {
+    extern __shared__ float red[];
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int c0 = cl * kVec;
+    const Row8 rk = ld8f(P.r_k + c0), lw = ld8f(P.ln_w + c0), lb = ld8f(P.ln_b + c0);
+    float acc[3][kVec];
+#pragma unroll
+    for (int s = 0; s < 3; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
+    const long rows = (long)P.B * P.T;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
+        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
+        // the end are computed on the last row and not stored
+        long row = base_row + rl;
+        const bool valid = row < rows;
+        if (!valid) row = rows - 1;
+        const size_t off = row * P.C + c0;
+        const Row8 y = ld8(P.y + off), r = ld8(P.r + off), k = ld8(P.k2 + off), v = ld8(P.v2 + off), g = ld8(P.g + off);
+        const Row8 d_o = valid ? ld8(P.d_o + off) : zero8();
+        float s1 = 0.f, sb = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { s1 += y.v[i]; sb = fmaf(r.v[i] * k.v[i], rk.v[i], sb); }
+        const float mu = head_sum(s1) * (1.f / kC);
+        sb = head_sum(sb);
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { const float d = y.v[i] - mu; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(head_sum(s2) * (1.f / kC) + P.eps);
+        Row8 yh, dz, o;
+        float m1 = 0.f, m2 = 0.f, ds = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            yh.v[i] = (y.v[i] - mu) * rstd;
+            const float z = yh.v[i] * lw.v[i] + lb.v[i] + sb * v.v[i];
+            o.v[i] = d_o.v[i] * z;                                   // dg
+            dz.v[i] = d_o.v[i] * g.v[i];
+            acc[1][i] = fmaf(dz.v[i], yh.v[i], acc[1][i]);           // d ln_w
+            acc[2][i] += dz.v[i];                                    // d ln_b
+            const float dyh = dz.v[i] * lw.v[i];
+            m1 += dyh;
+            m2 = fmaf(dyh, yh.v[i], m2);
+            ds = fmaf(dz.v[i], v.v[i], ds);
+        }
+        st8(P.dg + off, o, valid);
+        m1 = head_sum(m1) * (1.f / kC);
+        m2 = head_sum(m2) * (1.f / kC);
+        ds = head_sum(ds);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = rstd * (dz.v[i] * lw.v[i] - m1 - yh.v[i] * m2);
+        st8(P.dy + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = dz.v[i] * sb;
+        st8(P.dv2 + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            o.v[i] = ds * k.v[i] * rk.v[i];
+            acc[0][i] = fmaf(ds * r.v[i], k.v[i], acc[0][i]);        // d r_k
+        }
+        st8(P.dr + off, o, valid);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = ds * r.v[i] * rk.v[i];
+        st8(P.dk2 + off, o, valid);
+    }
+    write_partials<3>(acc, P.part, P.C, tpr, rl, cl, red);
+}
+
+// part [G][n] -> out [n]
+__global__ void reduce_partials_kernel(const float *part, float *out, int G, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float x = 0.f;
+    for (int g = 0; g < G; g++) x += part[(size_t)g * n + e];
+    out[e] = x;
+}
+
+// launch geometry: threads per row = C/8; rows per CTA so that the CTA has <= 512 threads; grid = multiple of the SM count
+struct Geo { int threads, rows_per_cta, grid; size_t red_bytes(int n, int C) const { return (size_t)rows_per_cta * n * C * 4; } };
+inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm) {
+    Geo g;
+    const int tpr = C / kVec;
+    g.rows_per_cta = kMaxThreads / tpr;
+    if (g.rows_per_cta > max_rows) g.rows_per_cta = max_rows;
+    if (g.rows_per_cta < 1) g.rows_per_cta = 1;
+    g.threads = tpr * g.rows_per_cta;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const long rows = (long)B * T;
+    long need = (rows + g.rows_per_cta - 1) / g.rows_per_cta;
+    long cap = (long)sms * ctas_per_sm;
+    g.grid = (int)(need < cap ? need : cap);
+    return g;
+}
+
+}  // namespace tmixf
+
+using namespace tmixf;
+
+static bool shape_ok(int B, int T, int C) { return B > 0 && T > 0 && C > 0 && C % kC == 0 && C / kVec <= kMaxThreads; }
+
+int tmix_grid(int B, int T, int C, int which) {
+    if (!shape_ok(B, T, C)) return 0;
+    return geometry(B, T, C, which == 0 ? 4 : 4, 4).grid;
+}
+
+cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                 const float *mix, void *const *out, cudaStream_t st) {
+    MixParams P{};
+    P.x = (const bf16 *)x; P.mask = (const bf16 *)mask; P.prev = (const bf16 *)prev; P.mix = mix;
+    for (int i = 0; i < n; i++) P.out[i] = (bf16 *)out[i];
+    P.B = B; P.T = T; P.C = C; P.n = n;
+    const Geo g = geometry(B, T, C, 4, 4);
+    count_launch();
+    if (n == 6) shift_mix_fwd_kernel<6><<<g.grid, g.threads, 0, st>>>(P);
+    else if (n == 1) shift_mix_fwd_kernel<1><<<g.grid, g.threads, 0, st>>>(P);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                 const float *mix, const void *const *dout, void *dx, float *dmix, float *part,
+                                 cudaStream_t st) {
+    MixParams P{};
+    P.x = (const bf16 *)x; P.mask = (const bf16 *)mask; P.prev = (const bf16 *)prev; P.mix = mix;
+    for (int i = 0; i < n; i++) P.dout[i] = (const bf16 *)dout[i];
+    P.dx = (bf16 *)dx; P.part = part;
+    P.B = B; P.T = T; P.C = C; P.n = n;
+    const Geo g = geometry(B, T, C, 4, 4);
+    const size_t sh = g.red_bytes(n, C);
+    count_launch(2);
+    cudaError_t e;
+    if (n == 6) {
+        e = cudaFuncSetAttribute(shift_mix_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return e;
+        shift_mix_bwd_kernel<6><<<g.grid, g.threads, sh, st>>>(P);
+    } else if (n == 1) {
+        e = cudaFuncSetAttribute(shift_mix_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+        if (e != cudaSuccess) return e;
+        shift_mix_bwd_kernel<1><<<g.grid, g.threads, sh, st>>>(P);
+    } else return cudaErrorInvalidValue;
+    reduce_partials_kernel<<<(n * C + 255) / 256, 256, 0, st>>>(part, dmix, g.grid, n * C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                            const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                            const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2, void *a_op,
+                            void *b_op, cudaStream_t st) {
+    PrepParams P{};
+    P.k = (const bf16 *)k; P.v = (const bf16 *)v; P.w_lo = (const bf16 *)w_lo; P.a_lo = (const bf16 *)a_lo;
+    P.v_lo = (const bf16 *)v_lo; P.v_first = (const bf16 *)v_first; P.mask = (const bf16 *)mask;
+    P.w0 = w0; P.a0 = a0; P.v0 = v0; P.k_k = k_k; P.k_a = k_a;
+    P.w = (bf16 *)w; P.k2 = (bf16 *)k2; P.v2 = (bf16 *)v2; P.a_op = (bf16 *)a_op; P.b_op = (bf16 *)b_op;
+    P.B = B; P.T = T; P.C = C;
+    const Geo g = geometry(B, T, C, 4, 4);
+    count_launch();
+    prep_fwd_kernel<<<g.grid, g.threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
+                            const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
+                            const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
+                            const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
+                            void *da_lo, void *dv_lo, void *dv_first, float *dparams /* [5][C] */, float *part,
+                            cudaStream_t st) {
+    PrepParams P{};
+    P.k = (const bf16 *)k; P.v = (const bf16 *)v; P.w_lo = (const bf16 *)w_lo; P.a_lo = (const bf16 *)a_lo;
+    P.v_lo = (const bf16 *)v_lo; P.v_first = (const bf16 *)v_first; P.mask = (const bf16 *)mask;
+    P.w0 = w0; P.a0 = a0; P.v0 = v0; P.k_k = k_k; P.k_a = k_a;
+    P.dw = (const bf16 *)dw; P.dk2 = (const bf16 *)dk2; P.dv2 = (const bf16 *)dv2; P.da_op = (const bf16 *)da_op;
+    P.db_op = (const bf16 *)db_op;
+    P.dk = (bf16 *)dk; P.dv = (bf16 *)dv; P.dw_lo = (bf16 *)dw_lo; P.da_lo = (bf16 *)da_lo; P.dv_lo = (bf16 *)dv_lo;
+    P.dv_first = (bf16 *)dv_first; P.part = part;
+    P.B = B; P.T = T; P.C = C;
+    const Geo g = geometry(B, T, C, 4, 4);
+    const size_t sh = g.red_bytes(5, C);
+    cudaError_t e = cudaFuncSetAttribute(prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    count_launch(2);
+    prep_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
+    reduce_partials_kernel<<<(5 * C + 255) / 256, 256, 0, st>>>(part, dparams, g.grid, 5 * C);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_out_fwd(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                           const void *g_, const float *r_k, const float *ln_w, const float *ln_b, float eps, void *o,
+                           cudaStream_t st) {
+    OutParams P{};
+    P.y = (const bf16 *)y; P.r = (const bf16 *)r; P.k2 = (const bf16 *)k2; P.v2 = (const bf16 *)v2; P.g = (const bf16 *)g_;
+    P.r_k = r_k; P.ln_w = ln_w; P.ln_b = ln_b; P.eps = eps; P.o = (bf16 *)o;
+    P.B = B; P.T = T; P.C = C;
+    const Geo g = geometry(B, T, C, 4, 4);
+    count_launch();
+    out_fwd_kernel<<<g.grid, g.threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_out_bwd(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
+                           const void *g_, const float *r_k, const float *ln_w, const float *ln_b, float eps,
+                           const void *d_o, void *dy, void *dr, void *dk2, void *dv2, void *dg, float *dparams /* [3][C] */,
+                           float *part, cudaStream_t st) {
+    OutParams P{};
+    P.y = (const bf16 *)y; P.r = (const bf16 *)r; P.k2 = (const bf16 *)k2; P.v2 = (const bf16 *)v2; P.g = (const bf16 *)g_;
+    P.r_k = r_k; P.ln_w = ln_w; P.ln_b = ln_b; P.eps = eps;
+    P.d_o = (const bf16 *)d_o; P.dy = (bf16 *)dy; P.dr = (bf16 *)dr; P.dk2 = (bf16 *)dk2; P.dv2 = (bf16 *)dv2;
+    P.dg = (bf16 *)dg; P.part = part;
+    P.B = B; P.T = T; P.C = C;
+    const Geo g = geometry(B, T, C, 4, 4);
+    const size_t sh = g.red_bytes(3, C);
+    cudaError_t e = cudaFuncSetAttribute(out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    count_launch(2);
+    out_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
+    reduce_partials_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(part, dparams, g.grid, 3 * C);
+    return cudaGetLastError();
+}
+
+}  // namespace rwkvtts

@@ -1,0 +1,195 @@
+"""Fused elementwise kernels of the RWKV-7 time-mix around the WKV-7 op (autograd functions over the C ABI).
+
+They replace the ATen elementwise chain of RWKV_Tmix_x070.forward between its GEMMs
+(/root/reference/model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226):
+
+  shift_mix(x, mixes, mask, prev)                                  -> n tensors  x + (shift(x) - x) * mix_i      (:160-169, :226)
+  prep(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask) -> w, k', v', a_op, b_op                      (:172-190)
+  out(y, r, k', v', g, r_k, ln_w, ln_b, eps)                        -> (GroupNorm(y) + bonus) * g                 (:192-195)
+
+Kernels: rwkvtts_b200/csrc/tmix_fused.cu.  CUDA bf16 only; there is no CPU fallback (core.py keeps the ATen
+formulation for everything these kernels do not cover: CPU tensors in the oracle tests, fp32 activations).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .ops import _need_cuda, _ptr, _stream
+
+BF16 = torch.bfloat16
+
+
+def usable(x: torch.Tensor) -> bool:
+    """The fused kernels cover CUDA bf16 activations with C a multiple of 64 (one head = 8 lanes x 8 channels)."""
+    return x.is_cuda and x.dtype == BF16 and x.shape[-1] % 64 == 0 and x.shape[-1] <= 4096
+
+
+def _f32(p: Optional[torch.Tensor], C: int) -> Optional[torch.Tensor]:
+    if p is None:
+        return None
+    return p.detach().reshape(-1).to(torch.float32).contiguous()
+
+
+def _mask2d(mask: Optional[torch.Tensor], B: int, T: int) -> Optional[torch.Tensor]:
+    if mask is None:
+        return None
+    return mask.detach().reshape(B, T).to(BF16).contiguous()
+
+
+def _scratch(B, T, C, n, dev):
+    return torch.empty(_lib.lib().rwkvtts_tmix_scratch_floats(B, T, C, n), dtype=torch.float32, device=dev)
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+class _ShiftMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mixes, mask, prev):
+        # x [B,T,C] bf16; mixes [n,C] (any float dtype); mask [B,T] bf16 | None; prev [B,C] bf16 | None
+        _need_cuda(x, mixes, mask, prev)
+        B, T, C = x.shape
+        n = mixes.shape[0]
+        x = x.contiguous()
+        mix32 = mixes.detach().to(torch.float32).contiguous()
+        outs = [torch.empty_like(x) for _ in range(n)]
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().rwkvtts_tmix_shift_mix_forward(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
+                                                           _ptr_array(outs), _stream())
+        _lib.check(rc, "rwkvtts_tmix_shift_mix_forward")
+        ctx.save_for_backward(x, mix32, mask, prev)
+        ctx.mix_dtype = mixes.dtype
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        x, mix32, mask, prev = ctx.saved_tensors
+        B, T, C = x.shape
+        n = mix32.shape[0]
+        douts = [torch.zeros_like(x) if d is None else d.contiguous() for d in douts]
+        dx = torch.empty_like(x)
+        dmix = torch.empty_like(mix32)
+        scratch = _scratch(B, T, C, n, x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().rwkvtts_tmix_shift_mix_backward(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
+                                                            _ptr_array(douts), _ptr(dx), _ptr(dmix), _ptr(scratch), _stream())
+        _lib.check(rc, "rwkvtts_tmix_shift_mix_backward")
+        return dx, dmix.to(ctx.mix_dtype), None, None
+
+
+def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
+              prev: Optional[torch.Tensor] = None):
+    """[x + (shift(x*mask) - x*mask) * m for m in mixes]; mixes broadcastable to [C] (n = 1 or 6)."""
+    B, T, C = x.shape
+    m = torch.stack([p.reshape(-1) for p in mixes])
+    prev_ = None if prev is None else prev.detach().to(BF16).contiguous()
+    return _ShiftMix.apply(x, m, _mask2d(mask, B, T), prev_)
+
+
+class _Prep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask):
+        _need_cuda(k, v, w_lo, a_lo, v_lo, v_first)
+        B, T, C = k.shape
+        k, v, w_lo, a_lo = (t.contiguous() for t in (k, v, w_lo, a_lo))
+        has_v = v_lo is not None
+        if has_v:
+            v_lo, v_first = v_lo.contiguous(), v_first.contiguous()
+        p32 = [_f32(p, C) for p in (w0, a0, v0 if has_v else None, k_k, k_a)]
+        w, k2, a_op, b_op = (torch.empty_like(k) for _ in range(4))
+        need_v2 = has_v or mask is not None
+        v2 = torch.empty_like(v) if need_v2 else None
+        with torch.cuda.device(k.device):
+            rc = _lib.lib().rwkvtts_tmix_prep_forward(B, T, C, _ptr(k), _ptr(v), _ptr(w_lo), _ptr(a_lo), _ptr(v_lo),
+                                                      _ptr(v_first), _ptr(mask), *[_ptr(p) for p in p32], _ptr(w), _ptr(k2),
+                                                      _ptr(v2), _ptr(a_op), _ptr(b_op), _stream())
+        _lib.check(rc, "rwkvtts_tmix_prep_forward")
+        ctx.save_for_backward(k, v, w_lo, a_lo, v_lo, v_first, mask, *[p for p in p32 if p is not None])
+        ctx.has_v, ctx.need_v2 = has_v, need_v2
+        ctx.dtypes = [p.dtype for p in (w0, a0, k_k, k_a)] + [v0.dtype if has_v else None]
+        ctx.shapes = [p.shape for p in (w0, a0, k_k, k_a)] + [v0.shape if has_v else None]
+        return w, k2, (v2 if need_v2 else v), a_op, b_op
+
+    @staticmethod
+    def backward(ctx, dw, dk2, dv2, da_op, db_op):
+        saved = ctx.saved_tensors
+        k, v, w_lo, a_lo, v_lo, v_first, mask = saved[:7]
+        ps = list(saved[7:])
+        if ctx.has_v:
+            w0, a0, v0, k_k, k_a = ps
+        else:
+            (w0, a0, k_k, k_a), v0 = ps, None
+        B, T, C = k.shape
+        z = lambda d: torch.zeros_like(k) if d is None else d.contiguous()
+        dw, dk2, da_op, db_op = z(dw), z(dk2), z(da_op), z(db_op)
+        dv2 = z(dv2)
+        if not ctx.need_v2:                       # v' was v itself: its gradient passes straight through
+            dk, dw_lo, da_lo = (torch.empty_like(k) for _ in range(3))
+            dv_out, dv_lo, dv_first, dv_ptr, dv2_ptr = dv2, None, None, None, None
+        else:
+            dk, dw_lo, da_lo, dv_out = (torch.empty_like(k) for _ in range(4))
+            dv_lo = torch.empty_like(k) if ctx.has_v else None
+            dv_first = torch.empty_like(k) if ctx.has_v else None
+            dv_ptr, dv2_ptr = _ptr(dv_out), _ptr(dv2)
+        dparams = torch.empty(5, C, dtype=torch.float32, device=k.device)
+        scratch = _scratch(B, T, C, 5, k.device)
+        with torch.cuda.device(k.device):
+            rc = _lib.lib().rwkvtts_tmix_prep_backward(
+                B, T, C, _ptr(k), _ptr(v), _ptr(w_lo), _ptr(a_lo), _ptr(v_lo), _ptr(v_first), _ptr(mask), _ptr(w0), _ptr(a0),
+                _ptr(v0), _ptr(k_k), _ptr(k_a), _ptr(dw), _ptr(dk2), dv2_ptr, _ptr(da_op), _ptr(db_op), _ptr(dk), dv_ptr,
+                _ptr(dw_lo), _ptr(da_lo), _ptr(dv_lo), _ptr(dv_first), _ptr(dparams), _ptr(scratch), _stream())
+        _lib.check(rc, "rwkvtts_tmix_prep_backward")
+        g = lambda i, j: dparams[i].to(ctx.dtypes[j]).reshape(ctx.shapes[j])
+        dv0 = dparams[2].to(ctx.dtypes[4]).reshape(ctx.shapes[4]) if ctx.has_v else None
+        return (dk, dv_out, dw_lo, da_lo, dv_lo, dv_first, g(0, 0), g(1, 1), dv0, g(3, 2), g(4, 3), None)
+
+
+def prep(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask=None):
+    """-> (w, k', v', a_op, b_op): everything between the projections / LoRAs and the WKV-7 op.
+    v_lo / v_first / v0 are None on layer 0 (v' = v, masked)."""
+    B, T, C = k.shape
+    return _Prep.apply(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, _mask2d(mask, B, T))
+
+
+class _Out(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, r, k2, v2, g, r_k, ln_w, ln_b, eps):
+        _need_cuda(y, r, k2, v2, g)
+        B, T, C = y.shape
+        y, r, k2, v2, g = (t.contiguous() for t in (y, r, k2, v2, g))
+        p32 = [_f32(p, C) for p in (r_k, ln_w, ln_b)]
+        o = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            rc = _lib.lib().rwkvtts_tmix_out_forward(B, T, C, _ptr(y), _ptr(r), _ptr(k2), _ptr(v2), _ptr(g),
+                                                     *[_ptr(p) for p in p32], float(eps), _ptr(o), _stream())
+        _lib.check(rc, "rwkvtts_tmix_out_forward")
+        ctx.save_for_backward(y, r, k2, v2, g, *p32)
+        ctx.eps = float(eps)
+        ctx.meta = [(p.dtype, p.shape) for p in (r_k, ln_w, ln_b)]
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        y, r, k2, v2, g, r_k, ln_w, ln_b = ctx.saved_tensors
+        B, T, C = y.shape
+        d_o = d_o.contiguous()
+        dy, dr, dk2, dv2, dg = (torch.empty_like(y) for _ in range(5))
+        dparams = torch.empty(3, C, dtype=torch.float32, device=y.device)
+        scratch = _scratch(B, T, C, 3, y.device)
+        with torch.cuda.device(y.device):
+            rc = _lib.lib().rwkvtts_tmix_out_backward(B, T, C, _ptr(y), _ptr(r), _ptr(k2), _ptr(v2), _ptr(g), _ptr(r_k),
+                                                      _ptr(ln_w), _ptr(ln_b), ctx.eps, _ptr(d_o), _ptr(dy), _ptr(dr), _ptr(dk2),
+                                                      _ptr(dv2), _ptr(dg), _ptr(dparams), _ptr(scratch), _stream())
+        _lib.check(rc, "rwkvtts_tmix_out_backward")
+        dp = [dparams[i].to(dt).reshape(sh) for i, (dt, sh) in enumerate(ctx.meta)]
+        return dy, dr, dk2, dv2, dg, dp[0], dp[1], dp[2], None
+
+
+def out(y, r, k2, v2, g, r_k, ln_w, ln_b, eps):
+    """(GroupNorm_H(y) * ln_w + ln_b + (sum_head r*k'*r_k) * v') * g: the input of the output projection."""
+    return _Out.apply(y, r, k2, v2, g, r_k, ln_w, ln_b, eps)

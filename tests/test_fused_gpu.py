@@ -1,0 +1,183 @@
+"""GPU parity tests of the fused time-mix kernels (rwkvtts_b200/fused.py -> csrc/tmix_fused.cu) against a plain
+PyTorch fp32 restatement of the same reference lines (rwkv_s2s_single_ffn.py:160-195, :226), forward and backward.
+
+Tolerance: outputs / activation gradients are bf16 (rounding alone ~1.6e-3 relative-L2) -> 5e-3; per-channel
+parameter gradients are fp32 sums of products of bf16 tensors -> 1e-2.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ACT_TOL, PAR_TOL = 5e-3, 1e-2
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float(((a - b).norm() / b.norm().clamp_min(1e-20)).detach())
+
+
+@pytest.fixture(scope="module")
+def fused():
+    import rwkvtts_b200  # noqa: F401
+    from rwkvtts_b200 import fused
+    assert torch.cuda.is_available()
+    return fused
+
+
+def _mask(B, T, dev):
+    m = torch.ones(B, T, 1, device=dev, dtype=torch.bfloat16)
+    for b in range(B):
+        m[b, T - 1 - (b * 3) % max(T // 2, 1):] = 0
+    return m
+
+
+def ref_shift_mix(x, mixes, mask, prev):
+    x = x.float()
+    if mask is not None:
+        x = x * mask.float()
+    first = torch.zeros_like(x[:, :1]) if prev is None else prev.float().unsqueeze(1)
+    xx = torch.cat((first, x[:, :-1]), dim=1) - x
+    return [x + xx * m.float() for m in mixes]
+
+
+@pytest.mark.parametrize("B,T,C,n,use_mask,use_prev", [(2, 37, 192, 6, False, False), (2, 64, 1024, 6, True, False),
+                                                       (1, 5, 2048, 1, False, True), (3, 16, 768, 1, True, True),
+                                                       (1, 1, 64, 6, False, True)])
+def test_shift_mix(fused, B, T, C, n, use_mask, use_prev):
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + T)
+    x = torch.randn(B, T, C, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    mixes = [torch.rand(1, 1, C, device="cuda", generator=g).bfloat16().requires_grad_(True) for _ in range(n)]
+    mask = _mask(B, T, "cuda") if use_mask else None
+    prev = torch.randn(B, C, device="cuda", generator=g).bfloat16() if use_prev else None
+    outs = fused.shift_mix(x, mixes, mask, prev)
+    douts = [torch.randn(B, T, C, device="cuda", generator=g).bfloat16() for _ in range(n)]
+    torch.autograd.backward(outs, douts)
+    xr = x.detach().clone().requires_grad_(True)
+    mr = [m.detach().float().requires_grad_(True) for m in mixes]
+    refs = ref_shift_mix(xr, mr, mask, prev)
+    torch.autograd.backward(refs, [d.float() for d in douts])
+    for o, r in zip(outs, refs):
+        assert rel(o, r) < ACT_TOL
+    assert rel(x.grad, xr.grad) < ACT_TOL
+    for m, r in zip(mixes, mr):
+        assert rel(m.grad, r.grad) < PAR_TOL
+
+
+def ref_prep(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask, H):
+    f = lambda t: None if t is None else t.float()
+    k, v, w_lo, a_lo, v_lo, v_first = map(f, (k, v, w_lo, a_lo, v_lo, v_first))
+    B, T, C = k.shape
+    w = -F.softplus(-(w0.float() + w_lo)) - 0.5
+    if mask is not None:
+        m = mask.float()
+        w, k, v = w * m, k * m, v * m
+    if v_lo is not None:
+        v = v + (v_first - v) * torch.sigmoid(v0.float() + v_lo)
+    a = torch.sigmoid(a0.float() + a_lo)
+    kk = F.normalize((k * k_k.float()).view(B, T, H, 64), dim=-1, p=2.0).view(B, T, C)
+    if mask is not None:
+        kk, v = kk * m, v * m
+    k2 = k * (1 + (a - 1) * k_a.float())
+    return w, k2, v, -kk, kk * a
+
+
+@pytest.mark.parametrize("B,T,C,has_v,use_mask", [(2, 33, 192, True, False), (2, 64, 1024, True, True),
+                                                  (1, 16, 768, False, False), (2, 9, 128, False, True)])
+def test_prep(fused, B, T, C, has_v, use_mask):
+    H = C // 64
+    g = torch.Generator(device="cuda").manual_seed(C + T)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    acts = [rn(B, T, C) for _ in range(6)]                       # k, v, w_lo, a_lo, v_lo, v_first
+    if not has_v:
+        acts[4] = acts[5] = None
+    pars = [(0.5 * rn(1, 1, C)) for _ in range(5)]               # w0, a0, v0, k_k, k_a
+    pars[3] = pars[3] + 1
+    if not has_v:
+        pars[2] = None
+    mask = _mask(B, T, "cuda") if use_mask else None
+    leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)
+    a1, p1 = [leaf(t) for t in acts], [leaf(t) for t in pars]
+    outs = fused.prep(*a1, p1[0], p1[1], p1[2], p1[3], p1[4], mask)
+    douts = [rn(B, T, C) for _ in range(5)]
+    torch.autograd.backward(outs, douts)
+    a2, p2 = [leaf(t) for t in acts], [None if t is None else t.detach().float().requires_grad_(True) for t in pars]
+    refs = ref_prep(*a2, p2[0], p2[1], p2[2], p2[3], p2[4], mask, H)
+    torch.autograd.backward(refs, [d.float() for d in douts])
+    for name, o, r in zip(("w", "k2", "v2", "a_op", "b_op"), outs, refs):
+        assert rel(o, r) < ACT_TOL, name
+    for name, x1, x2 in zip(("k", "v", "w_lo", "a_lo", "v_lo", "v_first"), a1, a2):
+        if x1 is not None:
+            assert rel(x1.grad, x2.grad) < 2 * ACT_TOL, name
+    for name, x1, x2 in zip(("w0", "a0", "v0", "k_k", "k_a"), p1, p2):
+        if x1 is not None:
+            assert rel(x1.grad, x2.grad) < PAR_TOL, name
+
+
+def ref_out(y, r, k2, v2, g, r_k, ln_w, ln_b, eps, H):
+    y, r, k2, v2, g = (t.float() for t in (y, r, k2, v2, g))
+    B, T, C = y.shape
+    z = F.group_norm(y.reshape(B * T, C), H, ln_w.float(), ln_b.float(), eps).view(B, T, C)
+    z = z + ((r.view(B, T, H, 64) * k2.view(B, T, H, 64) * r_k.float().view(H, 64)).sum(-1, keepdim=True)
+             * v2.view(B, T, H, 64)).view(B, T, C)
+    return z * g
+
+
+@pytest.mark.parametrize("B,T,C", [(2, 33, 192), (2, 64, 1024), (1, 7, 2048)])
+def test_out(fused, B, T, C):
+    H = C // 64
+    g_ = torch.Generator(device="cuda").manual_seed(C)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g_).bfloat16()
+    acts = [rn(B, T, C) for _ in range(5)]
+    pars = [0.3 * rn(H, 64), 1 + 0.3 * rn(C), 0.3 * rn(C)]
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    a1, p1 = [leaf(t) for t in acts], [leaf(t) for t in pars]
+    o = fused.out(*a1, *p1, 64e-5)
+    d_o = rn(B, T, C)
+    o.backward(d_o)
+    a2, p2 = [leaf(t) for t in acts], [t.detach().float().requires_grad_(True) for t in pars]
+    ref = ref_out(*a2, *p2, 64e-5, H)
+    ref.backward(d_o.float())
+    assert rel(o, ref) < ACT_TOL
+    for name, x1, x2 in zip(("y", "r", "k2", "v2", "g"), a1, a2):
+        assert rel(x1.grad, x2.grad) < 2 * ACT_TOL, name
+    for name, x1, x2 in zip(("r_k", "ln_w", "ln_b"), p1, p2):
+        assert rel(x1.grad, x2.grad) < PAR_TOL, name
+
+
+@pytest.mark.parametrize("layer_id,use_mask", [(0, False), (1, False), (1, True)])
+def test_tmix_fused_matches_aten_path(fused, layer_id, use_mask):
+    """core.tmix with the fused kernels against the same function with the ATen chain (same weights, same WKV op)."""
+    from rwkvtts_b200 import core
+    from rwkvtts_b200.x070 import RWKV_Tmix_x070
+    import types
+    args = types.SimpleNamespace(n_embd=256, dim_att=256, n_layer=4, head_size_a=64, head_size_divisor=8)
+    torch.manual_seed(3)
+    mod = RWKV_Tmix_x070(args, layer_id).cuda().bfloat16()
+    with torch.no_grad():
+        for p in mod.parameters():                 # the reference zero-inits several tensors: make every path matter
+            if float(p.abs().sum()) == 0:
+                p.copy_(0.1 * torch.randn_like(p))
+    B, T = 2, 48
+    x = torch.randn(B, T, 256, device="cuda").bfloat16()
+    vf = torch.randn(B, T, 256, device="cuda").bfloat16() if layer_id else None
+    mask = _mask(B, T, "cuda") if use_mask else None
+    dout = torch.randn(B, T, 256, device="cuda").bfloat16()
+    res = {}
+    for flag in (True, False):
+        core.FUSED = flag
+        mod.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        vfi = None if vf is None else vf.clone().requires_grad_(True)
+        out, v_first, _, _ = core.tmix(mod.params(), layer_id, xi, vfi, mask)
+        out.backward(dout)
+        res[flag] = (out.detach(), xi.grad, None if vfi is None else vfi.grad,
+                     {n: p.grad.clone() for n, p in mod.named_parameters() if p.grad is not None})
+    core.FUSED = True
+    assert rel(res[True][0], res[False][0]) < 2e-2
+    assert rel(res[True][1], res[False][1]) < 5e-2      # both sides are bf16 chains; the ATen one rounds after every op
+    if vf is not None:
+        assert rel(res[True][2], res[False][2]) < 5e-2
+    for n, gr in res[False][3].items():
+        assert n in res[True][3], n
+        assert rel(res[True][3][n], gr) < 5e-2, n
