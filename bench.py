@@ -214,6 +214,42 @@ def main():
                 R.wkv7_state_forward_(DB, 1, H * C, H, dstate[l], *dins, dy_)
     decode_ms = timed(decode_steps, n=2) / DSTEPS                            # WKV part of one decode step, 24 layers
 
+    # ---- fused time-mix elementwise kernels at the same config ([8,4096,1024] activations; explain, not part of `value`)
+    from rwkvtts_b200 import fused as FU
+    CC = H * C
+    act = lambda: torch.randn(B, T, CC, device=dev).bfloat16()
+    par = lambda *sh: (0.5 * torch.randn(*sh, device=dev)).bfloat16()
+    fx, fdo = act(), [act() for _ in range(6)]
+    mixes = [par(1, 1, CC).requires_grad_(True) for _ in range(6)]
+    k_, v_, wl_, al_, vl_, vf_ = (act().requires_grad_(True) for _ in range(6))
+    pp = [par(1, 1, CC).requires_grad_(True) for _ in range(5)]
+    y_, r_, g_ = (act().requires_grad_(True) for _ in range(3))
+    rk_, lw_, lb_ = par(H, C).requires_grad_(True), par(CC).requires_grad_(True), par(CC).requires_grad_(True)
+    fxg = fx.clone().requires_grad_(True)
+
+    def fused_times():
+        res = {}
+        def fb(name, fwd, inputs, douts, n_fwd_arrays, n_bwd_arrays):
+            outs = fwd()
+            outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+            tf = timed(fwd, n=5)
+            # autograd.grad: no accumulation into .grad, so the timed region is the backward kernels + a few allocations
+            tb = timed(lambda: torch.autograd.grad(outs, inputs, douts[:len(outs)], retain_graph=True), n=5)
+            nbytes = B * T * CC * 2
+            res[name] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_GBps": n_fwd_arrays * nbytes / tf / 1e6,
+                         "bwd_GBps": n_bwd_arrays * nbytes / tb / 1e6,
+                         "fwd_frac": n_fwd_arrays * nbytes / tf / 1e6 / peak_, "bwd_frac": n_bwd_arrays * nbytes / tb / 1e6 / peak_}
+        peak_ = peaks()[0]
+        fb("shift_mix6", lambda: FU.shift_mix(fxg, mixes), [fxg] + mixes, fdo, 7, 8)     # fwd 1r+6w; bwd 6r+1r(x)+1w
+        fb("prep", lambda: FU.prep(k_, v_, wl_, al_, vl_, vf_, *pp), [k_, v_, wl_, al_, vl_, vf_] + pp, fdo, 11, 17)  # 6r+5w; 11r+6w
+        fb("out", lambda: FU.out(y_, r_, k_, v_, g_, rk_, lw_, lb_, 64e-5), [y_, r_, k_, v_, g_, rk_, lw_, lb_], fdo, 6, 11)  # 5r+1w; 6r+5w
+        res["note"] = ("algorithmic arrays of [B,T,C] bf16 moved per call / CUDA-event time of the autograd call (includes "
+                       "the partial-sum reduce kernel and output allocations)")
+        return res
+    fused_k = fused_times()
+    del fx, fdo, k_, v_, wl_, al_, vl_, vf_, y_, r_, g_, fxg
+    torch.cuda.empty_cache()
+
     # ---- e2e: public API (WindBackstepping autograd op) with pinned HOST buffers --------------
     host_in = [x[n].pin_memory() for n in "wqkvab"] + [x["dy"].pin_memory()]
     host_out = [torch.empty_like(x["v"]).pin_memory() for _ in range(7)]
@@ -331,6 +367,7 @@ def main():
                     "decode_wkv_tokens_per_s": DB / (decode_ms * 1e-3),
                     "note": "fwd/bwd = training pair (chunked tcgen05 kernels, default family); fwd_infer = snapshot-free "
                             "tcgen05 forward used under no_grad; decode = stateful scan op, T=1, B=32, 24 layers (config c4)"},
+        "fused_tmix_kernels": fused_k,
         "ref_gpu_op": ref_gpu,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -150,18 +150,19 @@ RWKVTTS_API int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, cons
  *   w = -softplus(-(w0 + w_lo)) - 0.5 (:172);  a = sigmoid(a0 + a_lo) (:183);
  *   v' = v + (v_first - v) * sigmoid(v0 + v_lo) (:182; v_lo = v_first = NULL on layer 0, then v' = v);
  *   kk = l2-normalise per head (k * k_k) (:186-187);  k' = k * (1 + (a - 1) * k_a) (:189);
- *   WKV operands a_op = -kk, b_op = kk * a (:191);  w, k, v, kk masked as :175-190.
+ *   WKV operands a_op = -kk, b_op = kk * a (:191);  mask_rwk = 1: w, k, v, kk masked as :175-190 (in-repo stack);
+ *   mask_rwk = 0: only kk and v' are masked (rwkvfla's RWKV7Attention masks its input and v).
  * v2 may be NULL when there is neither a mask nor a v residual (v' = v). */
 RWKVTTS_API int rwkvtts_tmix_prep_forward(int B, int T, int C, const void *k, const void *v, const void *w_lo,
                                           const void *a_lo, const void *v_lo, const void *v_first, const void *mask,
                                           const float *w0, const float *a0, const float *v0, const float *k_k,
-                                          const float *k_a, void *w, void *k2, void *v2, void *a_op, void *b_op,
-                                          void *stream);
+                                          const float *k_a, int mask_rwk, void *w, void *k2, void *v2, void *a_op,
+                                          void *b_op, void *stream);
 /* dparams: fp32 [5][C] = d w0, d a0, d v0, d k_k, d k_a.  dv / dv_lo / dv_first may be NULL together with dv2. */
 RWKVTTS_API int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v, const void *w_lo,
                                            const void *a_lo, const void *v_lo, const void *v_first, const void *mask,
                                            const float *w0, const float *a0, const float *v0, const float *k_k,
-                                           const float *k_a, const void *dw, const void *dk2, const void *dv2,
+                                           const float *k_a, int mask_rwk, const void *dw, const void *dk2, const void *dv2,
                                            const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
                                            void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch,
                                            void *stream);

@@ -116,8 +116,8 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536)."""
     B, T, C = x.shape
     H = C // HEAD
-    if FUSED and fused.usable(x) and (mask is None or mask_rwk):
-        return _tmix_fused(p, layer_id, x, v_first, mask, shift_state, wkv_state, need_state, inplace_state)
+    if FUSED and fused.usable(x):
+        return _tmix_fused(p, layer_id, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state)
     if mask is not None:
         x = x * mask                                                            # :160
     xx = token_shift(x, shift_state)                                            # :162
@@ -149,7 +149,8 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     return out, v_first, (x[:, -1] if need_state else None), new_state
 
 
-def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, shift_state, wkv_state, need_state, inplace_state):
+def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state,
+                inplace_state):
     """tmix() with the elementwise chain in the fused kernels (same reference lines, same results up to bf16
     rounding of intermediates the fused kernels keep in fp32)."""
     xr, xw, xk, xv, xa, xg = fused.shift_mix(x, (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g), mask, shift_state)  # :160-169
@@ -159,14 +160,14 @@ def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, shift_state, wkv
     w_lo = torch.tanh(xw @ p.w1) @ p.w2
     a_lo = (xa @ p.a1) @ p.a2
     g = torch.sigmoid(xg @ p.g1) @ p.g2                                         # :184
-    if mask is not None:
+    if mask is not None and mask_rwk:
         r = r * mask                                                            # :175
     if layer_id == 0:
-        w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, None, None, p.w0, p.a0, None, p.k_k, p.k_a, mask)
-        v_first = v2                                                            # :180
+        w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, None, None, p.w0, p.a0, None, p.k_k, p.k_a, mask, mask_rwk)
+        v_first = v2 if (mask is None or mask_rwk) else v                       # :180 (rwkvfla: the unmasked v)
     else:
         w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, (xv @ p.v1) @ p.v2, v_first, p.w0, p.a0, p.v0, p.k_k,
-                                           p.k_a, mask)                         # :172-190
+                                           p.k_a, mask, mask_rwk)               # :172-190
     y, new_state = _wkv(r.contiguous(), w, k2, v2.contiguous(), a_op, b_op, wkv_state, need_state, inplace_state)   # :191
     o = fused.out(y, r, k2, v2, g, p.r_k, p.ln_w, p.ln_b, p.ln_eps)             # :192-195
     shift_out = None

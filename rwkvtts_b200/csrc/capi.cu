@@ -35,13 +35,14 @@ cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, cons
                                  cudaStream_t st);
 cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                             const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                            const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2, void *a_op,
-                            void *b_op, cudaStream_t st);
+                            const float *v0, const float *k_k, const float *k_a, int mask_rwk, void *w, void *k2, void *v2,
+                            void *a_op, void *b_op, cudaStream_t st);
 cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                             const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                            const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
-                            const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
-                            void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *part, cudaStream_t st);
+                            const float *v0, const float *k_k, const float *k_a, int mask_rwk, const void *dw,
+                            const void *dk2, const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv,
+                            void *dw_lo, void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *part,
+                            cudaStream_t st);
 cudaError_t launch_out_fwd(int B, int T, int C, const void *y, const void *r, const void *k2, const void *v2,
                            const void *g_, const float *r_k, const float *ln_w, const float *ln_b, float eps, void *o,
                            cudaStream_t st);
@@ -236,22 +237,23 @@ int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, c
 
 int rwkvtts_tmix_prep_forward(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                               const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                              const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2,
-                              void *a_op, void *b_op, void *stream) {
+                              const float *v0, const float *k_k, const float *k_a, int mask_rwk, void *w, void *k2,
+                              void *v2, void *a_op, void *b_op, void *stream) {
     if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({k, w_lo, a_lo, w0, a0, k_k, k_a, w, k2, a_op, b_op})) return rc;
     if ((v_lo == nullptr) != (v_first == nullptr) || (v_lo != nullptr && v0 == nullptr)) return RWKVTTS_ERR_NULL;
     if ((v_lo != nullptr || mask != nullptr) && (v == nullptr || v2 == nullptr)) return RWKVTTS_ERR_NULL;
     if (int rc = check_opt({v, v_lo, v_first, v0, v2})) return rc;
-    return finish(rwkvtts::launch_prep_fwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, w, k2, v2,
-                                           a_op, b_op, (cudaStream_t)stream));
+    return finish(rwkvtts::launch_prep_fwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, mask_rwk, w, k2,
+                                           v2, a_op, b_op, (cudaStream_t)stream));
 }
 
 int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                                const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                               const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
-                               const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
-                               void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch, void *stream) {
+                               const float *v0, const float *k_k, const float *k_a, int mask_rwk, const void *dw,
+                               const void *dk2, const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv,
+                               void *dw_lo, void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch,
+                               void *stream) {
     if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({k, w_lo, a_lo, w0, a0, k_k, k_a, dw, dk2, da_op, db_op, dk, dw_lo, da_lo, dparams, scratch}))
         return rc;
@@ -259,8 +261,8 @@ int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v
     if (dv != nullptr && (dv2 == nullptr || v == nullptr)) return RWKVTTS_ERR_NULL;
     if (v_lo != nullptr && (dv == nullptr || dv_lo == nullptr || dv_first == nullptr)) return RWKVTTS_ERR_NULL;
     if (int rc = check_opt({v, v_lo, v_first, v0, dv2, dv, dv_lo, dv_first})) return rc;
-    return finish(rwkvtts::launch_prep_bwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, dw, dk2, dv2,
-                                           da_op, db_op, dk, dv, dw_lo, da_lo, dv_lo, dv_first, dparams, scratch,
+    return finish(rwkvtts::launch_prep_bwd(B, T, C, k, v, w_lo, a_lo, v_lo, v_first, mask, w0, a0, v0, k_k, k_a, mask_rwk, dw, dk2,
+                                           dv2, da_op, db_op, dk, dv, dw_lo, da_lo, dv_lo, dv_first, dparams, scratch,
                                            (cudaStream_t)stream));
 }
 

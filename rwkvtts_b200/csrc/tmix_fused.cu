@@ -22,6 +22,7 @@ namespace tmixf {
 
 constexpr int kVec = 8;          // channels per thread
 constexpr int kMaxThreads = 512;
+constexpr int kBwdThreads = 256;  // backward kernels hold the parameter-gradient accumulators: 2 CTAs of 256 threads per SM
 
 struct Row8 { float v[kVec]; };
 
@@ -57,7 +58,7 @@ __device__ __forceinline__ float head_sum(float x) {
     x += __shfl_xor_sync(0xffffffffu, x, 4);
     return x;
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // CTA-level reduction of per-thread partial sums over the CTA's row lanes, written to part[blockIdx.x][slot][C]
 template <int N>
@@ -135,17 +136,15 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixPar
 }
 
 template <int N>
-__global__ void __launch_bounds__(kMaxThreads) shift_mix_bwd_kernel(const MixParams P) {
+__global__ void __launch_bounds__(kBwdThreads, 2) shift_mix_bwd_kernel(const MixParams P) {
     extern __shared__ float red[];
     const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
     const int c0 = cl * kVec;
-    float mix[N][kVec], acc[N][kVec];
+    float acc[N][kVec];
 #pragma unroll
-    for (int s = 0; s < N; s++) {
-        const Row8 m = ld8f(P.mix + (size_t)s * P.C + c0);
+    for (int s = 0; s < N; s++)
 #pragma unroll
-        for (int i = 0; i < kVec; i++) { mix[s][i] = m.v[i]; acc[s][i] = 0.f; }
-    }
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
     const long rows = (long)P.B * P.T;
     for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
         // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
@@ -172,10 +171,11 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_bwd_kernel(const MixPar
             Row8 d = zero8(), dn = zero8();
             if (valid) d = ld8(P.dout[s] + row * P.C + c0);
             if (valid && has_next) dn = ld8(P.dout[s] + (row + 1) * P.C + c0);
+            const Row8 mix = ld8f(P.mix + (size_t)s * P.C + c0);      // L1-resident; keeps 8N registers free
 #pragma unroll
             for (int i = 0; i < kVec; i++) {
                 acc[s][i] = fmaf(d.v[i], rbf(xp.v[i] - x.v[i]), acc[s][i]);
-                dx.v[i] += d.v[i] * (1.f - mix[s][i]) + dn.v[i] * mix[s][i];
+                dx.v[i] += d.v[i] * (1.f - mix.v[i]) + dn.v[i] * mix.v[i];
             }
         }
 #pragma unroll
@@ -198,11 +198,12 @@ struct PrepParams {
     bf16 *dk, *dv, *dw_lo, *da_lo, *dv_lo, *dv_first;
     float *part;                                          // [grid][5][C]: dw0, da0, dv0, dk_k, dk_a
     int B, T, C;
+    int mask_rwk;   // 1: w, k, v are masked before use (in-repo stack, :175-178); 0: only kk and v' (rwkvfla)
 };
 
 __device__ __forceinline__ float neg_softplus_neg(float z) {   // -softplus(-z) with torch's threshold 20
     const float y = -z;
-    return (y > 20.f) ? -y : -log1pf(__expf(y));
+    return (y > 20.f) ? -y : -__logf(1.f + __expf(y));     // |error| <= 1e-7 absolute: the result is offset by -0.5
 }
 
 __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams P) {
@@ -220,14 +221,15 @@ __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams 
         if (!valid) row = rows - 1;
         const size_t off = row * P.C + c0;
         const float m = (P.mask != nullptr) ? __bfloat162float(P.mask[row]) : 1.f;
+        const float mk = P.mask_rwk ? m : 1.f;
         Row8 k = ld8(P.k + off);
         const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
         Row8 w, a, u, o;
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < kVec; i++) {
-            k.v[i] *= m;
-            w.v[i] = (neg_softplus_neg(w0.v[i] + wl.v[i]) - 0.5f) * m;
+            k.v[i] *= mk;
+            w.v[i] = (neg_softplus_neg(w0.v[i] + wl.v[i]) - 0.5f) * mk;
             a.v[i] = rbf(sigmoidf_(a0.v[i] + al.v[i]));
             u.v[i] = k.v[i] * kk_.v[i];
             ss = fmaf(u.v[i], u.v[i], ss);
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams 
                 const Row8 vl = ld8(P.v_lo + off), vf = ld8(P.v_first + off);
 #pragma unroll
                 for (int i = 0; i < kVec; i++) {
-                    const float vm = v.v[i] * m;          // the reference masks v before the residual mix (:178) ...
+                    const float vm = v.v[i] * mk;         // the reference masks v before the residual mix (:178) ...
                     v.v[i] = (vm + (vf.v[i] - vm) * sigmoidf_(v0.v[i] + vl.v[i])) * m;     // ... and after it (:190)
                 }
             } else {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams 
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams P) {
+__global__ void __launch_bounds__(kBwdThreads, 2) prep_bwd_kernel(const PrepParams P) {
     extern __shared__ float red[];
     const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
     const int c0 = cl * kVec;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams 
         if (!valid) row = rows - 1;
         const size_t off = row * P.C + c0;
         const float m = (P.mask != nullptr) ? __bfloat162float(P.mask[row]) : 1.f;
+        const float mk = P.mask_rwk ? m : 1.f;
         Row8 k = ld8(P.k + off);
         const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
         Row8 dw = zero8(), dk2 = zero8(), da_op = zero8(), db_op = zero8();
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams 
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < kVec; i++) {
-            k.v[i] *= m;
+            k.v[i] *= mk;
             a.v[i] = sigmoidf_(a0.v[i] + al.v[i]);
             u.v[i] = k.v[i] * kk_.v[i];
             ss = fmaf(u.v[i], u.v[i], ss);
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams 
         // w = (-softplus(-z) - 0.5) * m
 #pragma unroll
         for (int i = 0; i < kVec; i++) {
-            o.v[i] = dw.v[i] * m * sigmoidf_(-(w0.v[i] + wl.v[i]));
+            o.v[i] = dw.v[i] * mk * sigmoidf_(-(w0.v[i] + wl.v[i]));
             acc[0][i] += o.v[i];
         }
         st8(P.dw_lo + off, o, valid);
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams 
             const float du = (dkk.v[i] - kk.v[i] * dot) * inv;
             acc[3][i] = fmaf(du, k.v[i], acc[3][i]);
             acc[4][i] = fmaf(dk2.v[i] * k.v[i], a.v[i] - 1.f, acc[4][i]);
-            o.v[i] = (du * kk_.v[i] + dk2.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i])) * m;
+            o.v[i] = (du * kk_.v[i] + dk2.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i])) * mk;
         }
         st8(P.dk + off, o, valid);
         if (P.dv != nullptr) {
@@ -336,8 +339,8 @@ __global__ void __launch_bounds__(kMaxThreads) prep_bwd_kernel(const PrepParams 
                 Row8 dvl, dvf;
 #pragma unroll
                 for (int i = 0; i < kVec; i++) {
-                    const float s = sigmoidf_(v0.v[i] + vl.v[i]), g = dv2.v[i] * m, vm = v.v[i] * m;
-                    o.v[i] = g * (1.f - s) * m;
+                    const float s = sigmoidf_(v0.v[i] + vl.v[i]), g = dv2.v[i] * m, vm = v.v[i] * mk;
+                    o.v[i] = g * (1.f - s) * mk;
                     dvf.v[i] = g * s;
                     dvl.v[i] = g * (vf.v[i] - vm) * s * (1.f - s);
                     acc[2][i] += dvl.v[i];
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(kMaxThreads) out_fwd_kernel(const OutParams P)
     }
 }
 
-__global__ void __launch_bounds__(kMaxThreads) out_bwd_kernel(const OutParams P) {
+__global__ void __launch_bounds__(kBwdThreads, 2) out_bwd_kernel(const OutParams P) {
     extern __shared__ float red[];
     const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
     const int c0 = cl * kVec;
@@ -467,21 +470,29 @@ __global__ void __launch_bounds__(kMaxThreads) out_bwd_kernel(const OutParams P)
     write_partials<3>(acc, P.part, P.C, tpr, rl, cl, red);
 }
 
-// part [G][n] -> out [n]
-__global__ void reduce_partials_kernel(const float *part, float *out, int G, int n) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
+// part [G][n] -> out [n]: 32 columns x 8 slices of G per CTA (fixed summation order: deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *part, float *out, int G, int n) {
+    __shared__ float sh[8][33];
+    const int col = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
     float x = 0.f;
-    for (int g = 0; g < G; g++) x += part[(size_t)g * n + e];
-    out[e] = x;
+    if (col < n)
+        for (int g = gl; g < G; g += 8) x += part[(size_t)g * n + col];
+    sh[gl][threadIdx.x & 31] = x;
+    __syncthreads();
+    if (gl == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) t += sh[j][threadIdx.x & 31];
+        out[col] = t;
+    }
 }
 
 // launch geometry: threads per row = C/8; rows per CTA so that the CTA has <= 512 threads; grid = multiple of the SM count
 struct Geo { int threads, rows_per_cta, grid; size_t red_bytes(int n, int C) const { return (size_t)rows_per_cta * n * C * 4; } };
-inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm) {
+inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm, int max_threads = kMaxThreads) {
     Geo g;
     const int tpr = C / kVec;
-    g.rows_per_cta = kMaxThreads / tpr;
+    g.rows_per_cta = max_threads / tpr;
     if (g.rows_per_cta > max_rows) g.rows_per_cta = max_rows;
     if (g.rows_per_cta < 1) g.rows_per_cta = 1;
     g.threads = tpr * g.rows_per_cta;
@@ -502,7 +513,8 @@ static bool shape_ok(int B, int T, int C) { return B > 0 && T > 0 && C > 0 && C 
 
 int tmix_grid(int B, int T, int C, int which) {
     if (!shape_ok(B, T, C)) return 0;
-    return geometry(B, T, C, which == 0 ? 4 : 4, 4).grid;
+    (void)which;
+    return geometry(B, T, C, 4, 4, kBwdThreads).grid;
 }
 
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
@@ -527,7 +539,7 @@ cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, cons
     for (int i = 0; i < n; i++) P.dout[i] = (const bf16 *)dout[i];
     P.dx = (bf16 *)dx; P.part = part;
     P.B = B; P.T = T; P.C = C; P.n = n;
-    const Geo g = geometry(B, T, C, 4, 4);
+    const Geo g = geometry(B, T, C, 4, 4, kBwdThreads);
     const size_t sh = g.red_bytes(n, C);
     count_launch(2);
     cudaError_t e;
@@ -540,20 +552,20 @@ cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, cons
         if (e != cudaSuccess) return e;
         shift_mix_bwd_kernel<1><<<g.grid, g.threads, sh, st>>>(P);
     } else return cudaErrorInvalidValue;
-    reduce_partials_kernel<<<(n * C + 255) / 256, 256, 0, st>>>(part, dmix, g.grid, n * C);
+    reduce_partials_kernel<<<(n * C + 31) / 32, 256, 0, st>>>(part, dmix, g.grid, n * C);
     return cudaGetLastError();
 }
 
 cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                             const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                            const float *v0, const float *k_k, const float *k_a, void *w, void *k2, void *v2, void *a_op,
-                            void *b_op, cudaStream_t st) {
+                            const float *v0, const float *k_k, const float *k_a, int mask_rwk, void *w, void *k2, void *v2,
+                            void *a_op, void *b_op, cudaStream_t st) {
     PrepParams P{};
     P.k = (const bf16 *)k; P.v = (const bf16 *)v; P.w_lo = (const bf16 *)w_lo; P.a_lo = (const bf16 *)a_lo;
     P.v_lo = (const bf16 *)v_lo; P.v_first = (const bf16 *)v_first; P.mask = (const bf16 *)mask;
     P.w0 = w0; P.a0 = a0; P.v0 = v0; P.k_k = k_k; P.k_a = k_a;
     P.w = (bf16 *)w; P.k2 = (bf16 *)k2; P.v2 = (bf16 *)v2; P.a_op = (bf16 *)a_op; P.b_op = (bf16 *)b_op;
-    P.B = B; P.T = T; P.C = C;
+    P.B = B; P.T = T; P.C = C; P.mask_rwk = mask_rwk;
     const Geo g = geometry(B, T, C, 4, 4);
     count_launch();
     prep_fwd_kernel<<<g.grid, g.threads, 0, st>>>(P);
@@ -562,9 +574,9 @@ cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, c
 
 cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                             const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
-                            const float *v0, const float *k_k, const float *k_a, const void *dw, const void *dk2,
-                            const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv, void *dw_lo,
-                            void *da_lo, void *dv_lo, void *dv_first, float *dparams /* [5][C] */, float *part,
+                            const float *v0, const float *k_k, const float *k_a, int mask_rwk, const void *dw,
+                            const void *dk2, const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv,
+                            void *dw_lo, void *da_lo, void *dv_lo, void *dv_first, float *dparams /* [5][C] */, float *part,
                             cudaStream_t st) {
     PrepParams P{};
     P.k = (const bf16 *)k; P.v = (const bf16 *)v; P.w_lo = (const bf16 *)w_lo; P.a_lo = (const bf16 *)a_lo;
@@ -574,14 +586,14 @@ cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, c
     P.db_op = (const bf16 *)db_op;
     P.dk = (bf16 *)dk; P.dv = (bf16 *)dv; P.dw_lo = (bf16 *)dw_lo; P.da_lo = (bf16 *)da_lo; P.dv_lo = (bf16 *)dv_lo;
     P.dv_first = (bf16 *)dv_first; P.part = part;
-    P.B = B; P.T = T; P.C = C;
-    const Geo g = geometry(B, T, C, 4, 4);
+    P.B = B; P.T = T; P.C = C; P.mask_rwk = mask_rwk;
+    const Geo g = geometry(B, T, C, 4, 4, kBwdThreads);
     const size_t sh = g.red_bytes(5, C);
     cudaError_t e = cudaFuncSetAttribute(prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
     count_launch(2);
     prep_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
-    reduce_partials_kernel<<<(5 * C + 255) / 256, 256, 0, st>>>(part, dparams, g.grid, 5 * C);
+    reduce_partials_kernel<<<(5 * C + 31) / 32, 256, 0, st>>>(part, dparams, g.grid, 5 * C);
     return cudaGetLastError();
 }
 
@@ -608,13 +620,13 @@ cudaError_t launch_out_bwd(int B, int T, int C, const void *y, const void *r, co
     P.d_o = (const bf16 *)d_o; P.dy = (bf16 *)dy; P.dr = (bf16 *)dr; P.dk2 = (bf16 *)dk2; P.dv2 = (bf16 *)dv2;
     P.dg = (bf16 *)dg; P.part = part;
     P.B = B; P.T = T; P.C = C;
-    const Geo g = geometry(B, T, C, 4, 4);
+    const Geo g = geometry(B, T, C, 4, 4, kBwdThreads);
     const size_t sh = g.red_bytes(3, C);
     cudaError_t e = cudaFuncSetAttribute(out_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
     count_launch(2);
     out_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
-    reduce_partials_kernel<<<(3 * C + 255) / 256, 256, 0, st>>>(part, dparams, g.grid, 3 * C);
+    reduce_partials_kernel<<<(3 * C + 31) / 32, 256, 0, st>>>(part, dparams, g.grid, 3 * C);
     return cudaGetLastError();
 }
 

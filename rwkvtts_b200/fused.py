@@ -93,7 +93,7 @@ def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[tor
 
 class _Prep(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask):
+    def forward(ctx, k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask, mask_rwk):
         _need_cuda(k, v, w_lo, a_lo, v_lo, v_first)
         B, T, C = k.shape
         k, v, w_lo, a_lo = (t.contiguous() for t in (k, v, w_lo, a_lo))
@@ -106,11 +106,11 @@ class _Prep(torch.autograd.Function):
         v2 = torch.empty_like(v) if need_v2 else None
         with torch.cuda.device(k.device):
             rc = _lib.lib().rwkvtts_tmix_prep_forward(B, T, C, _ptr(k), _ptr(v), _ptr(w_lo), _ptr(a_lo), _ptr(v_lo),
-                                                      _ptr(v_first), _ptr(mask), *[_ptr(p) for p in p32], _ptr(w), _ptr(k2),
-                                                      _ptr(v2), _ptr(a_op), _ptr(b_op), _stream())
+                                                      _ptr(v_first), _ptr(mask), *[_ptr(p) for p in p32], int(mask_rwk), _ptr(w),
+                                                      _ptr(k2), _ptr(v2), _ptr(a_op), _ptr(b_op), _stream())
         _lib.check(rc, "rwkvtts_tmix_prep_forward")
         ctx.save_for_backward(k, v, w_lo, a_lo, v_lo, v_first, mask, *[p for p in p32 if p is not None])
-        ctx.has_v, ctx.need_v2 = has_v, need_v2
+        ctx.has_v, ctx.need_v2, ctx.mask_rwk = has_v, need_v2, int(mask_rwk)
         ctx.dtypes = [p.dtype for p in (w0, a0, k_k, k_a)] + [v0.dtype if has_v else None]
         ctx.shapes = [p.shape for p in (w0, a0, k_k, k_a)] + [v0.shape if has_v else None]
         return w, k2, (v2 if need_v2 else v), a_op, b_op
@@ -141,19 +141,20 @@ class _Prep(torch.autograd.Function):
         with torch.cuda.device(k.device):
             rc = _lib.lib().rwkvtts_tmix_prep_backward(
                 B, T, C, _ptr(k), _ptr(v), _ptr(w_lo), _ptr(a_lo), _ptr(v_lo), _ptr(v_first), _ptr(mask), _ptr(w0), _ptr(a0),
-                _ptr(v0), _ptr(k_k), _ptr(k_a), _ptr(dw), _ptr(dk2), dv2_ptr, _ptr(da_op), _ptr(db_op), _ptr(dk), dv_ptr,
+                _ptr(v0), _ptr(k_k), _ptr(k_a), ctx.mask_rwk, _ptr(dw), _ptr(dk2), dv2_ptr, _ptr(da_op), _ptr(db_op), _ptr(dk), dv_ptr,
                 _ptr(dw_lo), _ptr(da_lo), _ptr(dv_lo), _ptr(dv_first), _ptr(dparams), _ptr(scratch), _stream())
         _lib.check(rc, "rwkvtts_tmix_prep_backward")
         g = lambda i, j: dparams[i].to(ctx.dtypes[j]).reshape(ctx.shapes[j])
         dv0 = dparams[2].to(ctx.dtypes[4]).reshape(ctx.shapes[4]) if ctx.has_v else None
-        return (dk, dv_out, dw_lo, da_lo, dv_lo, dv_first, g(0, 0), g(1, 1), dv0, g(3, 2), g(4, 3), None)
+        return (dk, dv_out, dw_lo, da_lo, dv_lo, dv_first, g(0, 0), g(1, 1), dv0, g(3, 2), g(4, 3), None, None)
 
 
-def prep(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask=None):
+def prep(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask=None, mask_rwk=True):
     """-> (w, k', v', a_op, b_op): everything between the projections / LoRAs and the WKV-7 op.
-    v_lo / v_first / v0 are None on layer 0 (v' = v, masked)."""
+    v_lo / v_first / v0 are None on layer 0 (v' = v, masked).  mask_rwk: also mask w, k, v before use (the in-repo
+    stack, :175-178); False = rwkvfla's RWKV7Attention, which masks only its input, kk and v'."""
     B, T, C = k.shape
-    return _Prep.apply(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, _mask2d(mask, B, T))
+    return _Prep.apply(k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, _mask2d(mask, B, T), mask_rwk)
 
 
 class _Out(torch.autograd.Function):
