@@ -108,6 +108,11 @@ def cpu_reference(seconds_target=12.0):
 def run_reference(args, rank):
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use every host
+    # core (the other ranks exit without work), so undo that before the OpenMP runtime of the C port starts
+    if "LOCAL_RANK" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
+                                            else (os.cpu_count() or 1))
     cb = cpu_reference(seconds_target=20.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": B * T / cb["value"] * 1e3,
