@@ -105,6 +105,42 @@ def cpu_reference(seconds_target=12.0):
                       f"forward_kernel/backward_kernel, OpenMP over (b,h); cpu: {model}"}
 
 
+def decode_leg(dev, new_tokens=128):
+    """AR decode, BASELINE config c4: RWKV-7 0.4B (D=1024, L=24, H=16, vocab 8193), 32 prompts of 163 positions, greedy,
+    EOS suppressed, through RWKV7ForCausalLM.generate (CUDA-graph step).  tokens/s = 32 * steps / time after prefill."""
+    import torch
+    from rwkvfla.models.rwkv7 import RWKV7Config, RWKV7ForCausalLM
+    DB, PROMPT = 32, 163
+    torch.manual_seed(42)
+    cfg = RWKV7Config(hidden_size=1024, num_hidden_layers=24, head_dim=64, vocab_size=8193, decay_low_rank_dim=64,
+                      a_low_rank_dim=64, v_low_rank_dim=32, gate_low_rank_dim=128)
+    m = RWKV7ForCausalLM(cfg)
+    with torch.no_grad():
+        for _, p in m.named_parameters():
+            if p.abs().sum() == 0:
+                p.copy_(torch.randn_like(p) * 0.02)
+    m = m.to(dev).to(torch.bfloat16).eval()
+    ids = torch.randint(0, 8192, (DB, PROMPT), device=dev)
+    out = {}
+    for mode, steps in (("cuda_graph", new_tokens), ("eager", 24)):
+        kw = dict(input_ids=ids, do_sample=False, eos_token_id=None, use_cuda_graph=(mode == "cuda_graph"))
+        m.generate(max_new_tokens=10, **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); m.generate(max_new_tokens=1, **kw); torch.cuda.synchronize()
+        t_prefill = time.perf_counter() - t0
+        t0 = time.perf_counter(); seq = m.generate(max_new_tokens=steps, **kw); torch.cuda.synchronize()
+        dt = time.perf_counter() - t0 - t_prefill
+        out[mode] = {"tokens_per_s": DB * (steps - 1) / dt, "ms_per_step": dt / (steps - 1) * 1e3, "steps": steps,
+                     "prefill_ms": t_prefill * 1e3}
+        out[mode + "_ids"] = seq[:, PROMPT:PROMPT + 24]
+    same = bool(torch.equal(out.pop("cuda_graph_ids"), out.pop("eager_ids")))
+    out["greedy_ids_identical_graph_vs_eager"] = same
+    out["config"] = "configs[3]: RWKV-7 0.4B random init, batch 32, prompt 163, greedy, EOS suppressed; graph timing includes capture"
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -131,6 +167,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -375,6 +412,11 @@ def main():
         "fused_tmix_kernels": fused_k,
         "ref_gpu_op": ref_gpu,
     }
+    if world == 1 and not args.no_decode:
+        try:
+            line["decode"] = decode_leg(dev)
+        except Exception as e:                                  # never let the extra leg kill the line
+            line["decode"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference()
     print(json.dumps(line))

@@ -191,6 +191,56 @@ def _filter_logits(logits: torch.Tensor, top_k: Optional[int], top_p: Optional[f
     return logits
 
 
+class _GraphDecodeStep:
+    """One decode step of RWKV7ForCausalLM (token -> logits, every layer's state advanced in place) captured in a CUDA
+    graph: the step is ~25 small kernels per layer, so on the eager path it is bound by launch and Python overhead
+    (SURVEY section 8 row a12).  The recurrent state is already advanced in place by the stateful WKV op; the token-shift
+    states are copied into static buffers inside the graph so that every replay reads what the previous one wrote."""
+
+    def __init__(self, model: "RWKV7ForCausalLM", cache: Cache, batch: int, device):
+        self.model, self.cache = model, cache
+        self.tok = torch.zeros(batch, 1, dtype=torch.long, device=device)
+        self.logits = None
+        keys = ("conv_state", "ffn_state")
+        self.static = [{k: st[k].clone() for k in keys if torch.is_tensor(st.get(k))} for st in cache.states]
+        for st, sb in zip(cache.states, self.static):
+            st.update(sb)
+        # warm-up on a side stream (cuBLAS workspaces, lazy module state), then put the states back
+        saved = [{k: v.clone() for k, v in st.items() if torch.is_tensor(v)} for st in cache.states]
+        seen = cache._seen_tokens
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream(device).wait_stream(side)
+        for st, sv in zip(cache.states, saved):
+            for k, v in sv.items():
+                st[k].copy_(v)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        cache._seen_tokens = seen
+
+    def _step(self):
+        out = self.model(input_ids=self.tok, past_key_values=self.cache, use_cache=True, logits_to_keep=1)
+        for st, sb in zip(self.cache.states, self.static):
+            for k, buf in sb.items():
+                if st[k] is not buf:
+                    buf.copy_(st[k])
+                    st[k] = buf
+        lg = out.logits[:, -1].float()
+        if self.logits is None:
+            self.logits = torch.empty_like(lg)
+        self.logits.copy_(lg)
+
+    def __call__(self, nxt: torch.Tensor) -> torch.Tensor:
+        self.tok.copy_(nxt.view(-1, 1))
+        self.graph.replay()
+        self.cache._seen_tokens += 1
+        return self.logits
+
+
 class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
     _tied_weights_keys = ["lm_head.weight"]
 
@@ -281,11 +331,14 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
                  temperature: float = 1.0, top_k: Optional[int] = None, top_p: Optional[float] = None,
                  eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
                  use_cache: bool = True, generator: Optional[torch.Generator] = None,
-                 return_dict_in_generate: bool = False, **kwargs):
+                 return_dict_in_generate: bool = False, use_cuda_graph: Optional[bool] = None,
+                 eos_check_interval: int = 1, **kwargs):
         """Autoregressive decode over the recurrent Cache (the call inference/rwkv7speech_inference.py and
         spark_llm.py:54-102 make).  Returns [B, prompt + new] token ids when `input_ids` is given and
         [B, new] when only `inputs_embeds` is given (HF convention); finished rows are padded with
-        `pad_token_id`."""
+        `pad_token_id`.  On CUDA the per-token step runs as one CUDA graph (`use_cuda_graph`, default on when more than 8
+        tokens are requested); `eos_check_interval` > 1 polls the all-finished flag (a host sync) only every that many
+        steps (finished rows are padded either way, so the result does not change)."""
         if (input_ids is None) == (inputs_embeds is None):
             raise ValueError("pass exactly one of input_ids / inputs_embeds")
         prompt_len = input_ids.shape[1] if input_ids is not None else inputs_embeds.shape[1]
@@ -307,6 +360,9 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         new_tokens = []
         logits = out.logits[:, -1].float()
+        if use_cuda_graph is None:
+            use_cuda_graph = dev.type == "cuda" and max_new_tokens > 8
+        graph_step = _GraphDecodeStep(self, cache, B, dev) if (use_cuda_graph and max_new_tokens > 1) else None
         for step in range(max_new_tokens):
             if eos_t is not None and step < min_new_tokens:
                 logits[:, eos_t] = float("-inf")
@@ -320,12 +376,15 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
             new_tokens.append(nxt)
             if eos_t is not None:
                 done = done | torch.isin(nxt, eos_t)
-                if bool(done.all()):
+                if (step + 1) % max(eos_check_interval, 1) == 0 and bool(done.all()):
                     break
             if step + 1 < max_new_tokens:
-                out = self(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, logits_to_keep=1)
-                cache = out.past_key_values
-                logits = out.logits[:, -1].float()
+                if graph_step is not None:
+                    logits = graph_step(nxt).clone()
+                else:
+                    out = self(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, logits_to_keep=1)
+                    cache = out.past_key_values
+                    logits = out.logits[:, -1].float()
         gen = torch.stack(new_tokens, dim=1) if new_tokens else torch.empty(B, 0, dtype=torch.long, device=dev)
         seq = torch.cat([input_ids, gen], dim=1) if input_ids is not None else gen
         if return_dict_in_generate:

@@ -13,6 +13,7 @@ formulation for everything these kernels do not cover: CPU tensors in the oracle
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional, Sequence
 
 import torch
@@ -28,10 +29,37 @@ def usable(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype == BF16 and x.shape[-1] % 64 == 0 and x.shape[-1] <= 4096
 
 
+# fp32 copies of per-channel parameters.  Under no_grad (prefill / decode: ~14 tiny conversion kernels per layer and
+# token otherwise) they are cached per parameter OBJECT (weak references: a freed parameter's address can be reused by
+# another tensor) and version counter.
+_PCACHE: dict = {}       # id(parameter) -> (weakref to it, version key, fp32 copy)
+
+
+def _cached(p: torch.Tensor, ver, make):
+    k = id(p)
+    hit = _PCACHE.get(k)
+    if hit is not None and hit[0]() is p and hit[1] == ver and hit[2].device == p.device:
+        return hit[2]
+    val = make()
+    _PCACHE[k] = (weakref.ref(p, lambda _r, k=k: _PCACHE.pop(k, None)), ver, val)
+    return val
+
+
 def _f32(p: Optional[torch.Tensor], C: int) -> Optional[torch.Tensor]:
     if p is None:
         return None
-    return p.detach().reshape(-1).to(torch.float32).contiguous()
+    make = lambda: p.detach().reshape(-1).to(torch.float32).contiguous()
+    if torch.is_grad_enabled():
+        return make()
+    return _cached(p, ("f32", p._version), make)
+
+
+def _stack32(mixes: Sequence[torch.Tensor]) -> torch.Tensor:
+    """[n, C] stack of the lerp coefficients (fp32 under no_grad, cached on the first coefficient like _f32)."""
+    if torch.is_grad_enabled():
+        return torch.stack([p.reshape(-1) for p in mixes])
+    ver = ("stack",) + tuple((id(p), p._version) for p in mixes)
+    return _cached(mixes[0], ver, lambda: torch.stack([p.detach().reshape(-1) for p in mixes]).to(torch.float32).contiguous())
 
 
 def _mask2d(mask: Optional[torch.Tensor], B: int, T: int) -> Optional[torch.Tensor]:
@@ -86,7 +114,7 @@ def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[tor
               prev: Optional[torch.Tensor] = None):
     """[x + (shift(x*mask) - x*mask) * m for m in mixes]; mixes broadcastable to [C] (n = 1 or 6)."""
     B, T, C = x.shape
-    m = torch.stack([p.reshape(-1) for p in mixes])
+    m = _stack32(mixes)
     prev_ = None if prev is None else prev.detach().to(BF16).contiguous()
     return _ShiftMix.apply(x, m, _mask2d(mask, B, T), prev_)
 
