@@ -52,7 +52,7 @@ constexpr float kLog2e = 1.4426950408889634f;   // decays are accumulated as log
 // canonical K-major tiles, strides in floats (see tc05.cuh: off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4)
 constexpr int WQ_LBO = 132, WQ_SBO = 32;     // [32 rows: 0-15 W~ tokens, 16-31 Q~ tokens][64 channels]
 constexpr int T_SBO = 36, T_LBO = 288;       // [64 rows: channel / value][16 tokens]   (transposed tiles)
-constexpr int MA_LBO = 128, MA_SBO = 32;     // [32 rows: 0-15 M1, 16-31 Aqk][16]
+constexpr int MA_LBO = 132, MA_SBO = 32;     // [32 rows: 0-15 M1, 16-31 Aqk][16]; +4: stage B writes columns conflict-free
 constexpr int QB_LBO = 64, QB_SBO = 32;      // [16][16]
 
 struct Slot {
@@ -68,7 +68,7 @@ struct Smem {
     Slot slot[NSLOT];
     Nat nat[NNAT];
     float NT[2][L * 20], Aak[2][L * 20];   // per stage-B group: N^T and Aak, fp32
-    float wtot[2][8][kC];                  // stage A scan partials, double buffered
+    float wtot[9][kC];                     // stage A scan: per-warp totals -> exclusive prefixes, chunk total
     __align__(16) bf16 ybuf[2][L][72];     // epilogue: Y tile [token][value], double buffered
     __align__(16) float Ut[2][4 * T_LBO];  // training: U^T [value][token] operand tile of the transposed-state update
     float DLw[4][kC];                      // e^{G} at the end of a window (ring of 4 windows)
@@ -155,22 +155,31 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
             if (t & 1) gg[j] += x;
         }
-        float(&wt)[8][kC] = sm.wtot[c & 1];
+        // cross-warp prefix in two stages: 8 per-warp totals per channel -> 64 threads turn them into exclusive
+        // prefixes (+ the chunk total in row 8) -> every thread reads two rows (the one-stage version had every thread
+        // read all 8 rows: 256 of the kernel's ~1660 shared-memory wavefronts per chunk)
+        float(&wt)[9][kC] = sm.wtot;
         if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
         bar_sync(1, 256);
-        float tot[4];
+        if (tp < kC) {
+            float run = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) { gg[j] += gpre[j]; tot[j] = gpre[j]; }
-#pragma unroll
-        for (int ww = 0; ww < 8; ww++) {
-            const float4 x0 = *reinterpret_cast<const float4 *>(&wt[ww][k4 * 4]);
-            const float xs[4] = {x0.x, x0.y, x0.z, x0.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                tot[j] += xs[j];
-                if (ww < wp) gg[j] += xs[j];
+            for (int ww = 0; ww < 8; ww++) {
+                const float x = wt[ww][tp];
+                wt[ww][tp] = run;
+                run += x;
             }
+            wt[8][tp] = run;
         }
+        bar_sync(1, 256);
+        float tot[4];
+        {
+            const float4 pre = *reinterpret_cast<const float4 *>(&wt[wp][k4 * 4]);
+            const float4 all = *reinterpret_cast<const float4 *>(&wt[8][k4 * 4]);
+            gg[0] += gpre[0] + pre.x; gg[1] += gpre[1] + pre.y; gg[2] += gpre[2] + pre.z; gg[3] += gpre[3] + pre.w;
+            tot[0] = gpre[0] + all.x; tot[1] = gpre[1] + all.y; tot[2] = gpre[2] + all.z; tot[3] = gpre[3] + all.w;
+        }
+        bar_sync(1, 256);       // rows are rewritten by the next chunk
         const bool win_end = (c % WIN == WIN - 1) || (c == nC - 1);
 #pragma unroll
         for (int j = 0; j < 4; j++) gpre[j] = win_end ? 0.f : tot[j];
