@@ -44,6 +44,8 @@ constexpr float kMinLogDecay = -1.35f;
 // canonical K-major tiles (floats): off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4
 constexpr int N32_LBO = 132, N16_LBO = 68, N_SBO = 32;   // [32|16 rows (tokens)][64 channels]
 constexpr int T_SBO = 36, T_LBO = 288;                   // [64 rows (channels)][16 tokens]
+constexpr int G_LBO = 296;   // same tiles when stage B also reads them as mma.sync fragments (Q~, A~, B~, K~): = 8 mod 32, so the
+                             // 64-bit fragment loads of a half-warp hit 32 different banks
 constexpr int S32_LBO = 128, S16_LBO = 64, S_SBO = 32;   // [32|16 rows][16]
 
 struct Slot {
@@ -51,7 +53,7 @@ struct Slot {
     float DYZn[16 * N32_LBO];     // rows 0-15 dY, 16-31 Z (group C)     [.][value]
     float Kn[16 * N16_LBO];       // K~ [s][key]
     float Bpn[16 * N16_LBO];      // B' [s][key]                         (stage B)
-    float dYt[4 * T_LBO], Qt[4 * T_LBO], At[4 * T_LBO], Bt[4 * T_LBO], Kt[4 * T_LBO];   // [channel][token]
+    float dYt[4 * T_LBO], Qt[4 * G_LBO], At[4 * G_LBO], Bt[4 * G_LBO], Kt[4 * G_LBO];   // [channel][token]
     float Gt[4 * T_LBO];          // G (fp32, not an MMA operand), same layout
     float AqbpT[4 * S16_LBO], AqkT[4 * S16_LBO], AakT[4 * S16_LBO];   // [n=s][k=t]          (stage B)
     float Gs[kC];                 // G at the chunk start
@@ -233,23 +235,24 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
             // transposed tiles: row = channel 4*k4+j, column = token t
             const int ot = (k4 >> 1) * T_SBO + (t >> 2) * T_LBO + (k4 & 1) * 16 + (t & 3);   // + 4*j
+            const int og = (k4 >> 1) * T_SBO + (t >> 2) * G_LBO + (k4 & 1) * 16 + (t & 3);   // Q~, A~, B~, K~ tiles
             const int on32 = (t >> 3) * N_SBO + k4 * N32_LBO + (t & 7) * 4;                // 32-row tiles, row t
             const int on16 = (t >> 3) * N_SBO + k4 * N16_LBO + (t & 7) * 4;
             unpack4(raw.x[1], f);                                   // Q~
 #pragma unroll
-            for (int j = 0; j < 4; j++) S.Qt[ot + 4 * j] = tf32r(f[j] * E[j]);
+            for (int j = 0; j < 4; j++) S.Qt[og + 4 * j] = tf32r(f[j] * E[j]);
             unpack4(raw.x[2], f);                                   // K~
 #pragma unroll
-            for (int j = 0; j < 4; j++) { o[j] = tf32r(f[j] * iE[j]); S.Kt[ot + 4 * j] = o[j]; }
+            for (int j = 0; j < 4; j++) { o[j] = tf32r(f[j] * iE[j]); S.Kt[og + 4 * j] = o[j]; }
             st4(&S.Kn[on16], o[0], o[1], o[2], o[3]);
             unpack4(raw.x[3], f);                                   // V (exact in tf32)
             st4(&S.UVn[on32 + 2 * N_SBO], f[0], f[1], f[2], f[3]);
             unpack4(raw.x[4], f);                                   // A~
 #pragma unroll
-            for (int j = 0; j < 4; j++) S.At[ot + 4 * j] = tf32r(f[j] * Ep[j]);
+            for (int j = 0; j < 4; j++) S.At[og + 4 * j] = tf32r(f[j] * Ep[j]);
             unpack4(raw.x[5], f);                                   // B~
 #pragma unroll
-            for (int j = 0; j < 4; j++) S.Bt[ot + 4 * j] = tf32r(f[j] * iE[j]);
+            for (int j = 0; j < 4; j++) S.Bt[og + 4 * j] = tf32r(f[j] * iE[j]);
             unpack4(raw.x[6], f);                                   // dY (exact in tf32)
 #pragma unroll
             for (int j = 0; j < 4; j++) S.dYt[ot + 4 * j] = f[j];
@@ -268,6 +271,8 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
 // ---------------------------------------------------------------------------------------------
 // stage B: tp in [0,128), group grp handles iterations it = grp, grp+2, ...
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int perm8(int g) { return (g & 1) | ((g & 2) << 1) | ((g & 4) >> 1); }
+
 __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
     constexpr int grp = 0;
     long long *P_dbg = (tp == 0 && grp == 0) ? P.dbg : nullptr; (void)P_dbg;
@@ -280,32 +285,36 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
         TICK(tb0);
         mbar_wait(&sm.a_done[si], (it / NS) & 1);
         TICK(tb1);
-        {   // forward Gram blocks from the transposed tiles: (A~|Q~)(B~|K~)^T, one 16x16 block per warp
+        {   // forward Gram blocks from the transposed tiles: (A~|Q~)(B~|K~)^T, one 16x16 block per warp.  Fragment rows
+            // (g, g+8) are tokens (2p, 2p+1) and column g of n-tile nt is token 2p+nt, p = perm8(g): every fragment
+            // register pair is one 64-bit load (two adjacent tokens of one channel), conflict-free with G_LBO = 8 mod 32
             const int rowsel = wp & 1, colsel = wp >> 1;
-            const float *Ar = rowsel ? S.Qt : S.At;
-            const float *Bc = colsel ? S.Kt : S.Bt;
+            const int pg = perm8(g);
+            const int ofrag = (pg >> 1) * G_LBO + 2 * (pg & 1) + tq * 4;
+            const float *Ar = (rowsel ? S.Qt : S.At) + ofrag;
+            const float *Bc = (colsel ? S.Kt : S.Bt) + ofrag;
             float acc[2][4] = {};
 #pragma unroll
             for (int kb = 0; kb < 8; kb++) {
-                uint32_t af[4], bfr[2];
-                const float *pa = Ar + kb * T_SBO + (g >> 2) * T_LBO + tq * 4 + (g & 3);
-                af[0] = __float_as_uint(pa[0]); af[1] = __float_as_uint(pa[2 * T_LBO]);
-                af[2] = __float_as_uint(pa[16]); af[3] = __float_as_uint(pa[2 * T_LBO + 16]);
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) {
-                    const float *pb = Bc + kb * T_SBO + (2 * nt + (g >> 2)) * T_LBO + tq * 4 + (g & 3);
-                    bfr[0] = __float_as_uint(pb[0]); bfr[1] = __float_as_uint(pb[16]);
-                    mma_tf32(acc[nt], af, bfr);
-                }
+                const float2 a01 = *reinterpret_cast<const float2 *>(Ar + kb * T_SBO);
+                const float2 a23 = *reinterpret_cast<const float2 *>(Ar + kb * T_SBO + 16);
+                const float2 b0 = *reinterpret_cast<const float2 *>(Bc + kb * T_SBO);        // k = tq:   n-tiles 0, 1
+                const float2 b1 = *reinterpret_cast<const float2 *>(Bc + kb * T_SBO + 16);   // k = tq+4
+                const uint32_t af[4] = {__float_as_uint(a01.x), __float_as_uint(a01.y), __float_as_uint(a23.x),
+                                        __float_as_uint(a23.y)};
+                const uint32_t bf0[2] = {__float_as_uint(b0.x), __float_as_uint(b1.x)};
+                const uint32_t bf1[2] = {__float_as_uint(b0.y), __float_as_uint(b1.y)};
+                mma_tf32(acc[0], af, bf0);
+                mma_tf32(acc[1], af, bf1);
             }
 #pragma unroll
             for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
-                    const int col = 8 * nt + 2 * tq + e;      // s
+                    const int col = 2 * perm8(2 * tq + e) + nt;   // s
 #pragma unroll
                     for (int hh = 0; hh < 2; hh++) {
-                        const int row = g + 8 * hh;           // t
+                        const int row = 2 * pg + hh;              // t
                         float x = acc[nt][2 * hh + e];
                         if (rowsel) {
                             x = (col <= row) ? x : 0.f;
@@ -327,7 +336,7 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
                 const float *pr = S.Bt + (tp >> 3) * T_SBO + (tp & 7) * 4;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; q4++) {
-                    const float4 x = *reinterpret_cast<const float4 *>(pr + q4 * T_LBO);
+                    const float4 x = *reinterpret_cast<const float4 *>(pr + q4 * G_LBO);
                     acc[4 * q4] = x.x; acc[4 * q4 + 1] = x.y; acc[4 * q4 + 2] = x.z; acc[4 * q4 + 3] = x.w;
                 }
             } else {
@@ -389,10 +398,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
         const uint64_t dKn = smem_desc(smem_u32(S.Kn), N16_LBO * 4, N_SBO * 4);
         const uint64_t dBp = smem_desc(smem_u32(S.Bpn), N16_LBO * 4, N_SBO * 4);
         const uint64_t dYt = smem_desc(smem_u32(S.dYt), T_LBO * 4, T_SBO * 4);
-        const uint64_t dQt = smem_desc(smem_u32(S.Qt), T_LBO * 4, T_SBO * 4);
-        const uint64_t dAt = smem_desc(smem_u32(S.At), T_LBO * 4, T_SBO * 4);
-        const uint64_t dBt = smem_desc(smem_u32(S.Bt), T_LBO * 4, T_SBO * 4);
-        const uint64_t dKt = smem_desc(smem_u32(S.Kt), T_LBO * 4, T_SBO * 4);
+        const uint64_t dQt = smem_desc(smem_u32(S.Qt), G_LBO * 4, T_SBO * 4);
+        const uint64_t dAt = smem_desc(smem_u32(S.At), G_LBO * 4, T_SBO * 4);
+        const uint64_t dBt = smem_desc(smem_u32(S.Bt), G_LBO * 4, T_SBO * 4);
+        const uint64_t dKt = smem_desc(smem_u32(S.Kt), G_LBO * 4, T_SBO * 4);
         const uint64_t dAqbpT = smem_desc(smem_u32(S.AqbpT), S16_LBO * 4, S_SBO * 4);
         const uint64_t dAqkT = smem_desc(smem_u32(S.AqkT), S16_LBO * 4, S_SBO * 4);
         const uint64_t dAakT = smem_desc(smem_u32(S.AakT), S16_LBO * 4, S_SBO * 4);
@@ -436,10 +445,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
             // R2 (dS): dS += dY^T Q~ + Z^T A~
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_DS, kadv(dYt, kk, T_LBO), kadv(dQt, kk, T_LBO), I64, true);
+                mma_tf32_ss(tb + C_DS, kadv(dYt, kk, T_LBO), kadv(dQt, kk, G_LBO), I64, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ts(tb + C_DS, tb + C_Z + 8 * kk, kadv(dAt, kk, T_LBO), I64, true);
+                mma_tf32_ts(tb + C_DS, tb + C_Z + 8 * kk, kadv(dAt, kk, G_LBO), I64, true);
         }
         __syncwarp();
         mbar_wait(&sm.c_done, it & 1);            // group C1: Z tiles and the gradient Gram tiles
@@ -450,27 +459,27 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
             // R2 (dS^T): dS^T += Q~^T dY + A~^T Z
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_DST, kadv(dQt, kk, T_LBO), kadv(dYt, kk, T_LBO), I64, true);
+                mma_tf32_ss(tb + C_DST, kadv(dQt, kk, G_LBO), kadv(dYt, kk, T_LBO), I64, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(tb + C_DST, kadv(dAt, kk, T_LBO), kadv(dZT, kk, T_LBO), I64, true);
+                mma_tf32_ss(tb + C_DST, kadv(dAt, kk, G_LBO), kadv(dZT, kk, T_LBO), I64, true);
             // P1: [dQ~^T | dA~^T] = S0^T [dY;Z]^T + B~^T [dAqb;dN]^T + K~^T [dAqk;dAak]^T
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
                 mma_tf32_ss(ok, kadv(dS0, kk, kCkLbo), kadv(dDYZ, kk, N32_LBO), I32, kk > 0);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok, kadv(dBt, kk, T_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok, kadv(dBt, kk, G_LBO), kadv(dQBN, kk, S32_LBO), I32, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok, kadv(dKt, kk, T_LBO), kadv(dQKAK, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok, kadv(dKt, kk, G_LBO), kadv(dQKAK, kk, S32_LBO), I32, true);
             // P2b: [dB~^T | dK~^T] += A~^T [dN^T;dAak^T]^T + Q~^T [dAqb^T;dAqk^T]^T
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok + 32, kadv(dAt, kk, T_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dAt, kk, G_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok + 32, kadv(dQt, kk, T_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dQt, kk, G_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
             // P3b: dV^T += dY^T Aqk + Z^T Aak
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
@@ -651,13 +660,13 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
         TICK(tc5);
         fence_after_sync();
         {
-            auto tile8 = [&](const float *T_, float (&o)[8]) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(T_ + trow + (2 * hf) * T_LBO);
-                const float4 x1 = *reinterpret_cast<const float4 *>(T_ + trow + (2 * hf + 1) * T_LBO);
+            auto tile8 = [&](const float *T_, float (&o)[8], int lbo = G_LBO) {
+                const float4 x0 = *reinterpret_cast<const float4 *>(T_ + trow + (2 * hf) * lbo);
+                const float4 x1 = *reinterpret_cast<const float4 *>(T_ + trow + (2 * hf + 1) * lbo);
                 o[0] = x0.x; o[1] = x0.y; o[2] = x0.z; o[3] = x0.w; o[4] = x1.x; o[5] = x1.y; o[6] = x1.z; o[7] = x1.w;
             };
             float G[8], lwv[8], gsum[8], acc_[8], op[8];
-            tile8(S.Gt, G);
+            tile8(S.Gt, G, T_LBO);
             {
                 const float gprev = (hf == 0) ? S.Gs[row] : S.Gt[trow + T_LBO + 3];   // G of token 7
                 lwv[0] = G[0] - gprev;
