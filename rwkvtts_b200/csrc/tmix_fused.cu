@@ -94,6 +94,15 @@ struct MixParams {
     int B, T, C, n;
 };
 
+// Each row lane (C/8 threads) walks a CONTIGUOUS range of rows, so the neighbour row a token needs (t-1 in the forward,
+// t+1 and t-1 in the backward) is the row it handled one step earlier / handles next: every element is loaded once.
+__device__ __forceinline__ Row8 masked(const Row8 &x, float m) {
+    Row8 r;
+#pragma unroll
+    for (int i = 0; i < kVec; i++) r.v[i] = x.v[i] * m;
+    return r;
+}
+
 template <int N>
 __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixParams P) {
     const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
@@ -106,22 +115,20 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixPar
         for (int i = 0; i < kVec; i++) mix[s][i] = m.v[i];
     }
     const long rows = (long)P.B * P.T;
-    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
-        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
-        // the end are computed on the last row and not stored
-        long row = base_row + rl;
-        const bool valid = row < rows;
-        if (!valid) row = rows - 1;
-        const int t = (int)(row % P.T), b = (int)(row / P.T);
-        Row8 x = ld8(P.x + row * P.C + c0), xp;
-        if (t > 0) xp = ld8(P.x + (row - 1) * P.C + c0);
-        else if (P.prev != nullptr) xp = ld8(P.prev + (size_t)b * P.C + c0);
-        else xp = zero8();
-        if (P.mask != nullptr) {
-            const float m = __bfloat162float(P.mask[row]), mp = (t > 0) ? __bfloat162float(P.mask[row - 1]) : 1.f;
-#pragma unroll
-            for (int i = 0; i < kVec; i++) { x.v[i] *= m; xp.v[i] *= mp; }
-        }
+    const long lanes = (long)gridDim.x * nrl, per = (rows + lanes - 1) / lanes;
+    const long r0 = ((long)blockIdx.x * nrl + rl) * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    auto mask_of = [&](long row) { return P.mask != nullptr ? __bfloat162float(P.mask[row]) : 1.f; };
+    Row8 xp = zero8(), x = zero8(), xn = zero8();
+    if (r0 < r1) {
+        x = masked(ld8(P.x + r0 * P.C + c0), mask_of(r0));
+        if (r0 % P.T != 0) xp = masked(ld8(P.x + (r0 - 1) * P.C + c0), mask_of(r0 - 1));
+        if (r0 + 1 < r1) xn = masked(ld8(P.x + (r0 + 1) * P.C + c0), mask_of(r0 + 1));
+    }
+    for (long row = r0; row < r1; row++) {
+        const int t = (int)(row % P.T);
+        if (t == 0) xp = (P.prev != nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
+        Row8 xn2 = zero8();
+        if (row + 2 < r1) xn2 = masked(ld8(P.x + (row + 2) * P.C + c0), mask_of(row + 2));     // two rows ahead, in flight
         Row8 xx;
 #pragma unroll
         for (int i = 0; i < kVec; i++) xx.v[i] = rbf(xp.v[i] - x.v[i]);       // the reference rounds shift(x) - x to bf16
@@ -130,8 +137,11 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixPar
             Row8 o;
 #pragma unroll
             for (int i = 0; i < kVec; i++) o.v[i] = fmaf(xx.v[i], mix[s][i], x.v[i]);
-            st8(P.out[s] + row * P.C + c0, o, valid);
+            st8(P.out[s] + row * P.C + c0, o);
         }
+        xp = x;
+        x = xn;
+        xn = xn2;
     }
 }
 
@@ -146,41 +156,52 @@ __global__ void __launch_bounds__(kBwdThreads, 2) shift_mix_bwd_kernel(const Mix
 #pragma unroll
         for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
     const long rows = (long)P.B * P.T;
-    for (long base_row = (long)blockIdx.x * nrl; base_row < rows; base_row += (long)gridDim.x * nrl) {
-        // warp-uniform trip count (lanes of different rows share a warp when C/8 is not a multiple of 32): rows past
-        // the end are computed on the last row and not stored
-        long row = base_row + rl;
-        const bool valid = row < rows;
-        if (!valid) row = rows - 1;
-        const int t = (int)(row % P.T), b = (int)(row / P.T);
-        Row8 x = ld8(P.x + row * P.C + c0), xp;
-        if (t > 0) xp = ld8(P.x + (row - 1) * P.C + c0);
-        else if (P.prev != nullptr) xp = ld8(P.prev + (size_t)b * P.C + c0);
-        else xp = zero8();
-        float m = 1.f;
-        if (P.mask != nullptr) {
-            m = __bfloat162float(P.mask[row]);
-            const float mp = (t > 0) ? __bfloat162float(P.mask[row - 1]) : 1.f;
+    const long lanes = (long)gridDim.x * nrl, per = (rows + lanes - 1) / lanes;
+    const long r0 = ((long)blockIdx.x * nrl + rl) * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    auto mask_of = [&](long row) { return P.mask != nullptr ? __bfloat162float(P.mask[row]) : 1.f; };
+    // descending walk: d[s][row+1] is what this lane loaded one step earlier, x[row-1] is the next step's x[row]
+    uint4 dn[N];
 #pragma unroll
-            for (int i = 0; i < kVec; i++) { x.v[i] *= m; xp.v[i] *= mp; }
+    for (int s = 0; s < N; s++) dn[s] = make_uint4(0, 0, 0, 0);
+    Row8 x = zero8();
+    if (r0 < r1) {
+        const long last = r1 - 1;
+        x = masked(ld8(P.x + last * P.C + c0), mask_of(last));
+        if ((last + 1) % P.T != 0) {        // the row after the range belongs to the same sequence
+#pragma unroll
+            for (int s = 0; s < N; s++) dn[s] = *reinterpret_cast<const uint4 *>(P.dout[s] + (last + 1) * P.C + c0);
+        }
+    }
+    for (long row = r1 - 1; row >= r0; row--) {
+        const int t = (int)(row % P.T);
+        const float m = mask_of(row);
+        Row8 xb = zero8();                    // the row below: this token's shift source and the next step's x
+        if (row > 0) xb = masked(ld8(P.x + (row - 1) * P.C + c0), mask_of(row - 1));
+        Row8 xp = xb;
+        if (t == 0) xp = (P.prev != nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
+        if (t == P.T - 1) {
+#pragma unroll
+            for (int s = 0; s < N; s++) dn[s] = make_uint4(0, 0, 0, 0);
         }
         Row8 dx = zero8();
-        const bool has_next = t + 1 < P.T;
 #pragma unroll
         for (int s = 0; s < N; s++) {
-            Row8 d = zero8(), dn = zero8();
-            if (valid) d = ld8(P.dout[s] + row * P.C + c0);
-            if (valid && has_next) dn = ld8(P.dout[s] + (row + 1) * P.C + c0);
+            const uint4 du = *reinterpret_cast<const uint4 *>(P.dout[s] + row * P.C + c0);
+            Row8 d, dnx;
+            unpack8(du, d.v);
+            unpack8(dn[s], dnx.v);
+            dn[s] = du;
             const Row8 mix = ld8f(P.mix + (size_t)s * P.C + c0);      // L1-resident; keeps 8N registers free
 #pragma unroll
             for (int i = 0; i < kVec; i++) {
                 acc[s][i] = fmaf(d.v[i], rbf(xp.v[i] - x.v[i]), acc[s][i]);
-                dx.v[i] += d.v[i] * (1.f - mix.v[i]) + dn.v[i] * mix.v[i];
+                dx.v[i] += d.v[i] * (1.f - mix.v[i]) + dnx.v[i] * mix.v[i];
             }
         }
 #pragma unroll
         for (int i = 0; i < kVec; i++) dx.v[i] *= m;
-        st8(P.dx + row * P.C + c0, dx, valid);
+        st8(P.dx + row * P.C + c0, dx);
+        x = xb;
     }
     write_partials<N>(acc, P.part, P.C, tpr, rl, cl, red);
 }

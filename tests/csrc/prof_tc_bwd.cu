@@ -37,8 +37,8 @@ int main() {
                           "B end barrier", "M wait full", "M wait win_scaled", "M wait y_free", "M phase 1", "M phase 2 (+s_free)", "E wait y_ready", "E work", ""};
     printf("-- forward (training variant), cycles/chunk\n");
     for (int i = 0; i < 15; i++) printf("%-22s %8.0f\n", nm[i], (double)hd[i] / (T / 16));
-    const char *nb[16] = {"A load+prescan+scan", "A wait slot empty", "A tiles+ckpt", "B wait a_done (x2)", "B gram+solve (x2)", "M wait full", "M wait C ready (s0t)",
-                          "M R1 (+P2a,P3a issue)", "M R2a + wait C grams", "M late products", "C wait full", "C rescale + S0T", "C wait Z", "C Z tiles + grams", "C wait out_ready", "C outputs"};
+    const char *nb[16] = {"A issue loads", "A wait slot empty", "A prescan+scan+tiles", "B wait a_done", "B gram+solve", "M wait full+blob", "M wait prev done / resc / ok_free",
+                          "M R1 (+P2a,P3a issue) + wait Z", "M R2a + wait C1 grams + S0", "M late products issue", "C1 window rescale", "(unused)", "C1 wait Z", "C1 Z tiles + grams", "C2 wait out_ready", "C2 outputs"};
     printf("-- backward, cycles/chunk\n");
     for (int i = 0; i < 16; i++) printf("%-24s %8.0f\n", nb[i], (double)hb[i] / (T / 16));
 }
