@@ -119,6 +119,30 @@ def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[tor
     return _ShiftMix.apply(x, m, _mask2d(mask, B, T), prev_)
 
 
+@torch.no_grad()
+def shift_mix_stacked(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
+                      prev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """shift_mix without autograd, outputs as one [n, B, T, C] buffer (inputs of batched projections on the decode path)."""
+    _need_cuda(x, mask, prev)
+    B, T, C = x.shape
+    n = len(mixes)
+    x = x.contiguous()
+    mix32 = _stack32(mixes)
+    out = torch.empty(n, B, T, C, dtype=x.dtype, device=x.device)
+    prev_ = None if prev is None else prev.to(BF16).contiguous()
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().rwkvtts_tmix_shift_mix_forward(B, T, C, n, _ptr(x), _ptr(_mask2d(mask, B, T)), _ptr(prev_), _ptr(mix32),
+                                                       _ptr_array([out[i] for i in range(n)]), _stream())
+    _lib.check(rc, "rwkvtts_tmix_shift_mix_forward")
+    return out
+
+
+def cached(anchor: torch.Tensor, tensors: Sequence[torch.Tensor], tag: str, make):
+    """make() cached on `anchor` until any of `tensors` is modified in place (no_grad paths only)."""
+    base = lambda t: t._base if t._base is not None else t        # .t() views are rebuilt per call: key on their parameter
+    return _cached(base(anchor), (tag,) + tuple((id(base(t)), t._version) for t in tensors), make)
+
+
 class _Prep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, k, v, w_lo, a_lo, v_lo, v_first, w0, a0, v0, k_k, k_a, mask, mask_rwk):
