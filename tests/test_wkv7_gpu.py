@@ -236,3 +236,35 @@ def test_long_sequence_property(impl):
     assert O.rel_l2(y_cat.float().cpu(), y_full.float().cpu()) < 4e-3      # two independent bf16 roundings
     assert O.rel_l2(sT_b.cpu(), sT_full.cpu()) < 1e-3
     assert torch.isfinite(y_full.float()).all()
+
+
+def test_kernel_families_agree_at_c5_shape(R):
+    """BASELINE config c5 per-GPU shape [2,8192,32,64] (H = 32, T = 8192): the chunked tcgen05 pair against the
+    sequential scan pair on the same inputs, outputs and all six gradients -- two independent implementations of the
+    same operator, compared where the oracle would take an hour.  Also: linearity of the backward in dy (exact for a
+    power of two)."""
+    B, T, H = 2, 8192, 32
+    x = O.make_inputs(B, T, H, seed=8192)
+    d = _dev(x)
+    L = R._lib.lib()
+    prev = L.rwkvtts_get_impl()
+    res = {}
+    try:
+        for impl in (1, 0):
+            assert L.rwkvtts_set_impl(impl) == 0
+            leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
+            y = R.WindBackstepping.apply(*leaves)
+            y.backward(d["dy"])
+            torch.cuda.synchronize()
+            res[impl] = [y.detach()] + [l.grad for l in leaves]
+            if impl == 1:
+                leaves2 = [d[n].clone().requires_grad_(True) for n in ORDER]
+                R.WindBackstepping.apply(*leaves2).backward(d["dy"] * 2)
+                for l, l2 in zip(leaves, leaves2):
+                    assert torch.equal(l2.grad, l.grad * 2)
+    finally:
+        L.rwkvtts_set_impl(prev)
+    for name, a, b in zip(["y"] + ["d" + n for n in ORDER], res[1], res[0]):
+        assert torch.isfinite(a.float()).all(), name
+        # both sides are bf16-rounded (1.6e-3 each); the scan backward un-steps the state, which costs it accuracy on dw
+        assert O.rel_l2(a.float().cpu(), b.float().cpu()) < (2e-2 if name == "dw" else 6e-3), name
