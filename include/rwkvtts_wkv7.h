@@ -177,6 +177,11 @@ RWKVTTS_API int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, co
                                           const float *ln_b, float eps, const void *d_o, void *dy, void *dr, void *dk2,
                                           void *dv2, void *dg, float *dparams, float *scratch, void *stream);
 
+/* Channel-mix activation y = relu(x)^2 on n bf16 elements (n % 8 == 0) and its adjoint dx = 2 relu(x) dy
+ * (RWKV_CMix_x070.forward, model/llm/rwkv_s2s_single_ffn.py:228: `torch.relu(self.key(k)) ** 2`). */
+RWKVTTS_API int rwkvtts_sqrelu_forward(long long n, const void *x, void *y, void *stream);
+RWKVTTS_API int rwkvtts_sqrelu_backward(long long n, const void *x, const void *dy, void *dx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

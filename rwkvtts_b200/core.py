@@ -218,7 +218,8 @@ def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch
     """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556)."""
     if FUSED and fused.usable(x):
         (xk,) = fused.shift_mix(x, (x_k,), mask, shift_state)                   # :224-226
-        k = torch.relu(F.linear(xk, W_key)) ** 2
+        k = F.linear(xk, W_key)
+        k = fused.sqrelu(k) if k.numel() % 8 == 0 else torch.relu(k) ** 2        # :228
         last = None
         if need_state:
             last = x[:, -1] if mask is None else x[:, -1] * mask[:, -1]

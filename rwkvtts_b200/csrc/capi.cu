@@ -28,6 +28,7 @@ cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *gra
                               int param_is_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
                               int adamw, float bc1, float bc2_sqrt, float gscale, cudaStream_t st);
 int tmix_grid(int B, int T, int C, int which);
+cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                  const float *mix, void *const *out, cudaStream_t st);
 cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
@@ -282,6 +283,18 @@ int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, const void *r,
     if (int rc = check_ptrs({y, r, k2, v2, g, r_k, ln_w, ln_b, d_o, dy, dr, dk2, dv2, dg, dparams, scratch})) return rc;
     return finish(rwkvtts::launch_out_bwd(B, T, C, y, r, k2, v2, g, r_k, ln_w, ln_b, eps, d_o, dy, dr, dk2, dv2, dg, dparams,
                                           scratch, (cudaStream_t)stream));
+}
+
+int rwkvtts_sqrelu_forward(long long n, const void *x, void *y, void *stream) {
+    if (n <= 0 || n % 8 != 0) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({x, y})) return rc;
+    return finish(rwkvtts::launch_sqrelu(x, nullptr, y, (long)n, (cudaStream_t)stream));
+}
+
+int rwkvtts_sqrelu_backward(long long n, const void *x, const void *dy, void *dx, void *stream) {
+    if (n <= 0 || n % 8 != 0) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({x, dy, dx})) return rc;
+    return finish(rwkvtts::launch_sqrelu(x, dy, dx, (long)n, (cudaStream_t)stream));
 }
 
 }  // extern "C"

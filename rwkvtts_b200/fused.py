@@ -246,3 +246,31 @@ class _Out(torch.autograd.Function):
 def out(y, r, k2, v2, g, r_k, ln_w, ln_b, eps):
     """(GroupNorm_H(y) * ln_w + ln_b + (sum_head r*k'*r_k) * v') * g: the input of the output projection."""
     return _Out.apply(y, r, k2, v2, g, r_k, ln_w, ln_b, eps)
+
+
+class _SqRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().rwkvtts_sqrelu_forward(x.numel(), _ptr(x), _ptr(y), _stream())
+        _lib.check(rc, "rwkvtts_sqrelu_forward")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().rwkvtts_sqrelu_backward(x.numel(), _ptr(x), _ptr(dy), _ptr(dx), _stream())
+        _lib.check(rc, "rwkvtts_sqrelu_backward")
+        return dx
+
+
+def sqrelu(x: torch.Tensor) -> torch.Tensor:
+    """relu(x) ** 2, the channel-mix activation (:228), one pass forward and one backward."""
+    return _SqRelu.apply(x)

@@ -145,6 +145,18 @@ def test_out(fused, B, T, C):
         assert rel(x1.grad, x2.grad) < PAR_TOL, name
 
 
+def test_sqrelu(fused):
+    x = torch.randn(3, 17, 512, device="cuda").bfloat16().requires_grad_(True)
+    dy = torch.randn(3, 17, 512, device="cuda").bfloat16()
+    y = fused.sqrelu(x)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_(True)
+    yr = torch.relu(xr) ** 2
+    yr.backward(dy)
+    assert torch.equal(y, yr)                      # same roundings as ATen: relu is exact, one rounding in the square
+    assert rel(x.grad, xr.grad) < ACT_TOL
+
+
 @pytest.mark.parametrize("layer_id,use_mask,mask_rwk", [(0, False, True), (1, False, True), (1, True, True),
                                                         (1, True, False), (0, True, False)])
 def test_tmix_fused_matches_aten_path(fused, layer_id, use_mask, mask_rwk):
