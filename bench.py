@@ -387,9 +387,9 @@ def main():
     fwd_ach = FWD_BYTES * th / (fwd_ms * 1e-3) / 1e9
     bwd_ach = BWD_BYTES * th / (bwd_ms * 1e-3) / 1e9
     # DRAM bytes per launch of the two training kernels: dram__bytes_read.sum + dram__bytes_write.sum from the ncu
-    # `--set full` capture of this same configuration (profiles/r01_tc_pair_full_v3.txt); the excess over the algorithmic
+    # `--set full` capture of this same configuration (profiles/r01_tc_pair_full_v5.txt); the excess over the algorithmic
     # bytes is the checkpoint / U scratch the pair exchanges (537 + 134 MB written by the forward, read by the backward)
-    NCU_TRAFFIC = {"fwd": 0.402714e9 + 0.678875e9, "bwd": 1.200751e9 + 0.379588e9}
+    NCU_TRAFFIC = {"fwd": 0.402706e9 + 0.679393e9, "bwd": 1.201027e9 + 0.380507e9}
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -403,7 +403,7 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": f"wkv7 {dom}", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": NCU_TRAFFIC[dom],
-                     "traffic_source": "ncu --set full capture, profiles/r01_tc_pair_full_v3.txt", "peak_source": peak_src,
+                     "traffic_source": "ncu --set full capture, profiles/r01_tc_pair_full_v5.txt", "peak_source": peak_src,
                      "algorithmic_bytes_per_token_head": dom_bytes, "token_heads_per_launch": th,
                      "avg_launch_ms": dom_ms},
         "kernels": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": fwd_ach, "bwd_GBps": bwd_ach,
