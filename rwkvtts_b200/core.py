@@ -181,26 +181,31 @@ def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift_
 
 def _tmix_decode(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state):
     """One decode step (T = 1, no autograd, layer > 0) of _tmix_fused with the 11 skinny GEMMs between the fused
-    kernels batched into 5: at 32 rows every GEMM is a ~5 us launch that reads 0.1-2 MB of weights, so the step is bound
+    kernels batched into 3 (+ output projection): at 32 rows every GEMM is a ~5 us launch that reads 0.1-2 MB of weights, so the step is bound
     by their count.  Weights are stacked once and cached until modified in place."""
     B, T, C = x.shape
     # order (r, k, v | w, a, g): two contiguous groups of projection inputs
     X = fused.shift_mix_stacked(x, (p.x_r, p.x_k, p.x_v, p.x_w, p.x_a, p.x_g), mask, shift_state)      # [6,B,1,C]
     X = X.view(6, B, C)
     W3 = fused.cached(p.W_r, (p.W_r, p.W_k, p.W_v), "rkv", lambda: torch.stack((p.W_r.t(), p.W_k.t(), p.W_v.t())).contiguous())
-    D = max(p.w1.shape[1], p.a1.shape[1], p.g1.shape[1])
+    D = max(p.v1.shape[1], p.w1.shape[1], p.a1.shape[1], p.g1.shape[1])
     padc = lambda m: F.pad(m, (0, D - m.shape[1]))
     padr = lambda m: F.pad(m, (0, 0, 0, D - m.shape[0]))
-    L1 = fused.cached(p.w1, (p.w1, p.a1, p.g1), "lora1", lambda: torch.stack((padc(p.w1), padc(p.a1), padc(p.g1))).contiguous())
-    L2 = fused.cached(p.w2, (p.w2, p.a2, p.g2), "lora2", lambda: torch.stack((padr(p.w2), padr(p.a2), padr(p.g2))).contiguous())
+    # the four LoRAs read X[2:6] = (xv, xw, xa, xg): one batched down- and one batched up-projection, ranks zero-padded
+    L1 = fused.cached(p.w1, (p.v1, p.w1, p.a1, p.g1), "lora1",
+                      lambda: torch.stack((padc(p.v1), padc(p.w1), padc(p.a1), padc(p.g1))).contiguous())
+    L2 = fused.cached(p.w2, (p.v2, p.w2, p.a2, p.g2), "lora2",
+                      lambda: torch.stack((padr(p.v2), padr(p.w2), padr(p.a2), padr(p.g2))).contiguous())
     rkv = torch.bmm(X[0:3], W3)                                                  # [3,B,C]
-    h = torch.bmm(X[3:6], L1)                                                    # [3,B,D]
-    h[0].tanh_()
-    h[2].sigmoid_()
-    lo = torch.bmm(h, L2)                                                        # [3,B,C]: w_lo, a_lo, g
+    h = torch.bmm(X[2:6], L1)                                                    # [4,B,D]
+    h[1].tanh_()
+    if p.g1.shape[1] == D:
+        h[3].sigmoid_()
+    else:                                                                        # sigmoid(0) != 0: keep the padding at zero
+        h[3, :, :p.g1.shape[1]].sigmoid_()
+    lo = torch.bmm(h, L2)                                                        # [4,B,C]: v_lo, w_lo, a_lo, g
     r, k, v = (rkv[i].view(B, 1, C) for i in range(3))
-    w_lo, a_lo, g = (lo[i].view(B, 1, C) for i in range(3))
-    v_lo = ((X[2] @ p.v1) @ p.v2).view(B, 1, C)
+    v_lo, w_lo, a_lo, g = (lo[i].view(B, 1, C) for i in range(4))
     if mask is not None and mask_rwk:
         r = r * mask
     w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, v_lo, v_first, p.w0, p.a0, p.v0, p.k_k, p.k_a, mask, mask_rwk)
