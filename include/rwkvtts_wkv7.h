@@ -139,9 +139,12 @@ RWKVTTS_API int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg
 RWKVTTS_API size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params);
 
 /* out[i] = x + (shift(x) - x) * mix[i], i < n (n = 6: x_r,x_w,x_k,x_v,x_a,x_g :164-169; n = 1: x_k of channel-mix :226).
- * shift(x)[t] = x[t-1], first token from `prev` [B,C] (NULL = zeros, ZeroPad2d :162); x is multiplied by mask first. */
+ * shift(x)[t] = x[t-1], first token from `prev` [B,C] (NULL = zeros, ZeroPad2d :162); x is multiplied by mask first.
+ * prev_out [B,C] (or NULL) receives the masked last token = the shift state of the next call (:511); it may be the
+ * same buffer as `prev` only for T == 1 (the decode step updates its state in place). */
 RWKVTTS_API int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask,
-                                               const void *prev, const float *mix, void *const *out, void *stream);
+                                               const void *prev, const float *mix, void *const *out, void *prev_out,
+                                               void *stream);
 RWKVTTS_API int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask,
                                                 const void *prev, const float *mix, const void *const *dout, void *dx,
                                                 float *dmix, float *scratch, void *stream);

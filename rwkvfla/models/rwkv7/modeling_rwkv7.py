@@ -61,7 +61,8 @@ class RWKV7FeedForward(nn.Module):
         if state is not None and len(state) > self.layer_idx:
             shift = state[self.layer_idx].get("ffn_state")
         out, new_shift = core.cmix(self.x_k, self.key.weight, self.value.weight, x, mask=am, shift_state=shift,
-                                   need_state=state is not None and use_cache)
+                                   need_state=state is not None and use_cache,
+                                   inplace_state=not torch.is_grad_enabled())
         if state is not None and use_cache:
             state.update(ffn_state=new_shift, layer_idx=self.layer_idx, offset=0)
         return out, state

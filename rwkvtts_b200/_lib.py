@@ -30,7 +30,7 @@ SYMBOLS = {
     "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),
     "rwkvtts_wkv7_state_forward": (_i, [_i, _i, _i, _i, _fp] + [_vp] * 6 + [_vp, _vp]),
     "rwkvtts_tmix_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, _i]),
-    "rwkvtts_tmix_shift_mix_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp]),
+    "rwkvtts_tmix_shift_mix_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _vp]),
     "rwkvtts_tmix_shift_mix_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _fp, _fp, _vp]),
     "rwkvtts_tmix_prep_forward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp] * 5 + [_i] + [_vp] * 5 + [_vp]),
     "rwkvtts_tmix_prep_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp] * 5 + [_i] + [_vp] * 5 + [_vp] * 6 + [_fp, _fp, _vp]),

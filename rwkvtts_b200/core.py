@@ -185,7 +185,10 @@ def _tmix_decode(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift
     by their count.  Weights are stacked once and cached until modified in place."""
     B, T, C = x.shape
     # order (r, k, v | w, a, g): two contiguous groups of projection inputs
-    X = fused.shift_mix_stacked(x, (p.x_r, p.x_k, p.x_v, p.x_w, p.x_a, p.x_g), mask, shift_state)      # [6,B,1,C]
+    inplace_shift = (need_state and inplace_state and shift_state is not None and shift_state.dtype == torch.bfloat16
+                     and shift_state.is_contiguous())
+    X = fused.shift_mix_stacked(x, (p.x_r, p.x_k, p.x_v, p.x_w, p.x_a, p.x_g), mask, shift_state,
+                                update_prev=inplace_shift)                      # [6,B,1,C]
     X = X.view(6, B, C)
     W3 = fused.cached(p.W_r, (p.W_r, p.W_k, p.W_v), "rkv", lambda: torch.stack((p.W_r.t(), p.W_k.t(), p.W_v.t())).contiguous())
     D = max(p.v1.shape[1], p.w1.shape[1], p.a1.shape[1], p.g1.shape[1])
@@ -213,14 +216,21 @@ def _tmix_decode(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift
     o = fused.out(y, r, k2, v2, g, p.r_k, p.ln_w, p.ln_b, p.ln_eps)
     shift_out = None
     if need_state:
-        shift_out = x[:, -1] if mask is None else x[:, -1] * mask[:, -1]
+        shift_out = shift_state if inplace_shift else (x[:, -1] if mask is None else x[:, -1] * mask[:, -1])
     return F.linear(o, p.W_o), v_first, shift_out, new_state
 
 
 def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch.Tensor,
          mask: Optional[torch.Tensor] = None, shift_state: Optional[torch.Tensor] = None,
-         need_state: bool = False):
+         need_state: bool = False, inplace_state: bool = False):
     """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556)."""
+    if (FUSED and fused.usable(x) and not torch.is_grad_enabled() and x.shape[1] == 1 and need_state and inplace_state
+            and shift_state is not None and shift_state.dtype == torch.bfloat16 and shift_state.is_contiguous()):
+        # decode step: the kernel also writes the new shift state into the caller's buffer
+        xk = fused.shift_mix_stacked(x, (x_k,), mask, shift_state, update_prev=True)[0]
+        k = F.linear(xk, W_key)
+        k = fused.sqrelu(k) if k.numel() % 8 == 0 else torch.relu(k) ** 2
+        return F.linear(k, W_value), shift_state
     if FUSED and fused.usable(x):
         (xk,) = fused.shift_mix(x, (x_k,), mask, shift_state)                   # :224-226
         k = F.linear(xk, W_key)

@@ -30,7 +30,7 @@ cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *gra
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                 const float *mix, void *const *out, cudaStream_t st);
+                                 const float *mix, void *const *out, void *prev_out, cudaStream_t st);
 cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                  const float *mix, const void *const *dout, void *dx, float *dmix, float *part,
                                  cudaStream_t st);
@@ -213,14 +213,15 @@ size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params) {
 }
 
 int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                   const float *mix, void *const *out, void *stream) {
+                                   const float *mix, void *const *out, void *prev_out, void *stream) {
     if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
     if (out == nullptr) return RWKVTTS_ERR_NULL;
     if (int rc = check_ptrs({x, mix})) return rc;
     for (int i = 0; i < n; i++)
         if (int rc = check_ptrs({out[i]})) return rc;
-    if (int rc = check_opt({prev})) return rc;
-    return finish(rwkvtts::launch_shift_mix_fwd(B, T, C, n, x, mask, prev, mix, out, (cudaStream_t)stream));
+    if (int rc = check_opt({prev, prev_out})) return rc;
+    if (prev_out != nullptr && prev_out == prev && T != 1) return RWKVTTS_ERR_SHAPE;   // in-place state update: decode only
+    return finish(rwkvtts::launch_shift_mix_fwd(B, T, C, n, x, mask, prev, mix, out, prev_out, (cudaStream_t)stream));
 }
 
 int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,

@@ -86,6 +86,7 @@ struct MixParams {
     const bf16 *x;          // [B,T,C]
     const bf16 *mask;       // [B,T] or null
     const bf16 *prev;       // [B,C] or null (last token of the previous call)
+    bf16 *prev_out;         // [B,C] or null: receives the (masked) last token; may alias `prev` only when T == 1
     const float *mix;       // [n][C]
     bf16 *out[6];           // n outputs [B,T,C]
     const bf16 *dout[6];    // backward: n output gradients
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixPar
             for (int i = 0; i < kVec; i++) o.v[i] = fmaf(xx.v[i], mix[s][i], x.v[i]);
             st8(P.out[s] + row * P.C + c0, o);
         }
+        if (P.prev_out != nullptr && t == P.T - 1) st8(P.prev_out + (size_t)(row / P.T) * P.C + c0, x);
         xp = x;
         x = xn;
         xn = xn2;
@@ -572,9 +574,10 @@ cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cuda
 }
 
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                 const float *mix, void *const *out, cudaStream_t st) {
+                                 const float *mix, void *const *out, void *prev_out, cudaStream_t st) {
     MixParams P{};
     P.x = (const bf16 *)x; P.mask = (const bf16 *)mask; P.prev = (const bf16 *)prev; P.mix = mix;
+    P.prev_out = (bf16 *)prev_out;
     for (int i = 0; i < n; i++) P.out[i] = (bf16 *)out[i];
     P.B = B; P.T = T; P.C = C; P.n = n;
     const Geo g = geometry(B, T, C, 4, 4);

@@ -88,7 +88,7 @@ class _ShiftMix(torch.autograd.Function):
         outs = [torch.empty_like(x) for _ in range(n)]
         with torch.cuda.device(x.device):
             rc = _lib.lib().rwkvtts_tmix_shift_mix_forward(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
-                                                           _ptr_array(outs), _stream())
+                                                           _ptr_array(outs), None, _stream())
         _lib.check(rc, "rwkvtts_tmix_shift_mix_forward")
         ctx.save_for_backward(x, mix32, mask, prev)
         ctx.mix_dtype = mixes.dtype
@@ -121,8 +121,9 @@ def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[tor
 
 @torch.no_grad()
 def shift_mix_stacked(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
-                      prev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """shift_mix without autograd, outputs as one [n, B, T, C] buffer (inputs of batched projections on the decode path)."""
+                      prev: Optional[torch.Tensor] = None, update_prev: bool = False) -> torch.Tensor:
+    """shift_mix without autograd, outputs as one [n, B, T, C] buffer (inputs of batched projections on the decode path).
+    update_prev (T == 1 only): `prev` [B,C] bf16 contiguous is overwritten with the new shift state by the same kernel."""
     _need_cuda(x, mask, prev)
     B, T, C = x.shape
     n = len(mixes)
@@ -130,9 +131,12 @@ def shift_mix_stacked(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Opti
     mix32 = _stack32(mixes)
     out = torch.empty(n, B, T, C, dtype=x.dtype, device=x.device)
     prev_ = None if prev is None else prev.to(BF16).contiguous()
+    if update_prev:
+        assert T == 1 and prev_ is prev, "in-place shift state: T == 1 and a contiguous bf16 [B,C] buffer"
     with torch.cuda.device(x.device):
         rc = _lib.lib().rwkvtts_tmix_shift_mix_forward(B, T, C, n, _ptr(x), _ptr(_mask2d(mask, B, T)), _ptr(prev_), _ptr(mix32),
-                                                       _ptr_array([out[i] for i in range(n)]), _stream())
+                                                       _ptr_array([out[i] for i in range(n)]),
+                                                       _ptr(prev_) if update_prev else None, _stream())
     _lib.check(rc, "rwkvtts_tmix_shift_mix_forward")
     return out
 
