@@ -13,6 +13,8 @@ std::atomic<long long> g_kernel_launches{0};
 cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
                             float *sT, bool save, cudaStream_t st);
+cudaError_t launch_step(int B, int H, const void *w, const void *q, const void *k, const void *v, const void *a,
+                        const void *b, void *y, float *state, cudaStream_t st);
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
                           cudaStream_t st);
@@ -186,7 +188,9 @@ int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const v
                                void *stream) {
     if (B <= 0 || T <= 0 || H <= 0 || C != H * RWKVTTS_HEAD_SIZE) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({state, r, w, k, v, a, b, y})) return rc;
-    // op-boundary order of the scan kernel is (w, q=r, k, v, a, b)
+    // op-boundary order of the kernels is (w, q=r, k, v, a, b)
+    if (T == 1)   // the decode step: dedicated streaming kernel
+        return finish(rwkvtts::launch_step(B, H, w, r, k, v, a, b, y, state, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, r, k, v, a, b, y, nullptr, nullptr, state, state, false,
                                            (cudaStream_t)stream));
 }

@@ -333,6 +333,62 @@ wkv7_scan_bwd_kernel(int T, int H, const bf16 *__restrict__ w_, const bf16 *__re
 }
 
 // ---------------------------------------------------------------------------------------
+// single decode step (T = 1): the per-token op of the AR loop (rwkv7_state_fwd_fp16.cu:9-57 with T = 1;
+// RWKV_x070_TMix_one, rwkv_s2s_single_ffn.py:497-502).  33.7 KB per (b,h) -- state read + write -- is all it moves, so
+// it is a pure streaming kernel: thread (i, p) owns value row i and keys 16m+4p..16m+4p+3, m < 4 (the scan kernel's
+// ownership and summation order, so T single steps are bit-identical to one T-step call); four 16-byte state accesses
+// each way, 64 contiguous bytes per quad and access; the six 64-vectors come in through shared memory once per CTA.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wkv7_step_kernel(int H, const bf16 *__restrict__ w, const bf16 *__restrict__ q,
+                                                        const bf16 *__restrict__ k, const bf16 *__restrict__ v,
+                                                        const bf16 *__restrict__ a, const bf16 *__restrict__ b,
+                                                        bf16 *__restrict__ y, float *__restrict__ state) {
+    __shared__ float vec[6][kC];     // d, q, k, v, a, b
+    const int bh = blockIdx.x, tid = threadIdx.x, i = tid >> 2, p = tid & 3;
+    const size_t off = (size_t)bh * kC;                      // [B,1,H,64]: (b*H + h)*64
+    float4 *srow = reinterpret_cast<float4 *>(state + (size_t)bh * kC * kC + i * kC + 4 * p);
+    float4 s4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) s4[j] = srow[4 * j];         // state first: the long-latency loads
+    if (tid < 6 * kC / 2) {                                  // 192 threads x 2 elements
+        const int arr = tid / (kC / 2), c = (tid % (kC / 2)) * 2;
+        const bf16 *src = arr == 0 ? w : arr == 1 ? q : arr == 2 ? k : arr == 3 ? v : arr == 4 ? a : b;
+        const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162 *>(src + off + c);
+        float x0 = __bfloat162float(x.x), x1 = __bfloat162float(x.y);
+        if (arr == 0) { x0 = expf(-expf(x0)); x1 = expf(-expf(x1)); }              // decay (wkv7_cuda.cu:24)
+        vec[arr][c] = x0; vec[arr][c + 1] = x1;
+    }
+    __syncthreads();
+    float S[16];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { S[4 * j] = s4[j].x; S[4 * j + 1] = s4[j].y; S[4 * j + 2] = s4[j].z; S[4 * j + 3] = s4[j].w; }
+    float sa = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) sa = fmaf(S[j], vec[4][16 * (j >> 2) + 4 * p + (j & 3)], sa);
+    sa = quad_sum(sa);
+    const float vi = vec[3][i];
+    float yy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int c = 16 * (j >> 2) + 4 * p + (j & 3);
+        S[j] = fmaf(S[j], vec[0][c], fmaf(sa, vec[5][c], vec[2][c] * vi));
+        yy = fmaf(S[j], vec[1][c], yy);
+    }
+    yy = quad_sum(yy);
+#pragma unroll
+    for (int j = 0; j < 4; j++) srow[4 * j] = make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]);
+    if (p == 0) y[off + i] = __float2bfloat16_rn(yy);
+}
+
+cudaError_t launch_step(int B, int H, const void *w, const void *q, const void *k, const void *v, const void *a,
+                        const void *b, void *y, float *state, cudaStream_t st) {
+    count_launch();
+    wkv7_step_kernel<<<dim3(B * H), dim3(256), 0, st>>>(H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k,
+                                                         (const bf16 *)v, (const bf16 *)a, (const bf16 *)b, (bf16 *)y, state);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------
 // launchers (called from capi.cu)
 // ---------------------------------------------------------------------------------------
 cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
