@@ -142,6 +142,49 @@ def decode_leg(dev, new_tokens=128):
     return out
 
 
+def model_step_leg(dev, steps=2):
+    """Whole-model training step (forward + backward) at BASELINE config c2: RWKV-7 0.4B (D=1024, L=24, H=16, vocab 8193),
+    batch 8 x 4096, bf16, random init, synthetic ids: tokens/s with the fused time-mix kernels and with the ATen elementwise
+    chain around the same WKV kernels (what the kernels outside the recurrence buy end to end)."""
+    import torch
+    from rwkvtts_b200 import core
+    from rwkvfla.models.rwkv7 import RWKV7Config, RWKV7ForCausalLM
+    torch.manual_seed(42)
+    cfg = RWKV7Config(hidden_size=1024, num_hidden_layers=24, head_dim=64, vocab_size=8193, decay_low_rank_dim=64,
+                      a_low_rank_dim=64, v_low_rank_dim=32, gate_low_rank_dim=128, fuse_cross_entropy=True)
+    m = RWKV7ForCausalLM(cfg)
+    with torch.no_grad():
+        for _, p in m.named_parameters():
+            if p.abs().sum() == 0:
+                p.copy_(torch.randn_like(p) * 0.02)
+    m = m.to(dev).to(torch.bfloat16).train()
+    ids = torch.randint(0, 8192, (B, T), device=dev)
+    out = {}
+    try:
+        for name, flag in (("fused", True), ("aten", False)):
+            core.FUSED = flag
+            for _ in range(2):
+                m.zero_grad(set_to_none=True)
+                m(input_ids=ids, labels=ids).loss.backward()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                m.zero_grad(set_to_none=True)
+                loss = m(input_ids=ids, labels=ids).loss
+                loss.backward()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "tokens_per_s": B * T / ms * 1e3, "loss": float(loss.detach())}
+    finally:
+        core.FUSED = True
+    out["config"] = "configs[1] whole model: RWKV-7 0.4B, batch 8 x 4096, fwd+bwd, 1 GPU; fused = csrc/tmix_fused.cu, aten = ATen chain"
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -169,6 +212,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-model-step", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -423,6 +467,11 @@ def main():
             line["decode"] = decode_leg(dev)
         except Exception as e:                                  # never let the extra leg kill the line
             line["decode"] = {"error": repr(e)}
+    if world == 1 and not args.no_model_step:
+        try:
+            line["model_train_step"] = model_step_leg(dev)
+        except Exception as e:
+            line["model_train_step"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference()
     print(json.dumps(line))
