@@ -15,12 +15,14 @@ from typing import Dict, List, Optional, Tuple, Union
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 from transformers.generation.utils import GenerationMixin
 from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from rwkvtts_b200 import core
+from rwkvtts_b200.fused import cached as fused_cached
 from ...layers.rwkv7 import RWKV7Attention
 from ...modules import FusedCrossEntropyLoss, FusedLinearCrossEntropyLoss, LayerNorm, l2_warp
 from ..utils import Cache
@@ -300,7 +302,15 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
         has_labels = labels is not None or shift_labels is not None
         if not (self.config.fuse_linear_cross_entropy and has_labels):
             h = hidden_states if not logits_to_keep else hidden_states[:, -logits_to_keep:]
-            logits = self.lm_head(h)
+            W = self.lm_head.weight
+            if W.is_cuda and W.dtype == torch.bfloat16 and W.shape[0] % 8 != 0 and self.lm_head.bias is None:
+                # an odd vocabulary (Spark: 8193) sends cuBLAS to an unaligned legacy kernel, 5x slower on B200:
+                # multiply by the weight zero-padded to a multiple of 8 rows and return the view without the padding
+                pad = lambda: F.pad(W, (0, 0, 0, 8 - W.shape[0] % 8))
+                Wp = pad() if torch.is_grad_enabled() else fused_cached(W, (W,), "lm_head_pad8", lambda: pad().detach())
+                logits = F.linear(h, Wp)[..., :W.shape[0]]
+            else:
+                logits = self.lm_head(h)
         if has_labels:
             criterion = self.criterion
             if criterion is None:
