@@ -180,6 +180,17 @@ RWKVTTS_API int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, co
                                           const float *ln_b, float eps, const void *d_o, void *dy, void *dr, void *dk2,
                                           void *dv2, void *dg, float *dparams, float *scratch, void *stream);
 
+/* Residual add + LayerNorm of the block (Block.forward, model/llm/rwkv_s2s_single_ffn.py:251-259; rwkvfla's
+ * LayerNorm(x, residual, prenorm=True)): s = x + res (bf16; res / s may be NULL), y = (s - mean) * rstd * w + b (b may be
+ * NULL).  rows = B*T, C % 256 == 0.  stats fp32 [rows][2] = (mean, rstd) is what the backward needs besides s (NULL for
+ * inference).  Backward: dx (= d res) = LayerNorm adjoint of dy (+ ds, the gradient flowing into the sum directly);
+ * dparams fp32 [2][C] = d w, d b; scratch = rwkvtts_tmix_scratch_floats(1, rows, C, 2) floats. */
+RWKVTTS_API int rwkvtts_add_layernorm_forward(long long rows, int C, const void *x, const void *res, const float *w,
+                                              const float *b, float eps, void *y, void *s, float *stats, void *stream);
+RWKVTTS_API int rwkvtts_add_layernorm_backward(long long rows, int C, const void *sum, const float *stats, const float *w,
+                                               const void *dy, const void *ds, void *dx, float *dparams, float *scratch,
+                                               void *stream);
+
 /* Channel-mix activation y = relu(x)^2 on n bf16 elements (n % 8 == 0) and its adjoint dx = 2 relu(x) dy
  * (RWKV_CMix_x070.forward, model/llm/rwkv_s2s_single_ffn.py:228: `torch.relu(self.key(k)) ** 2`). */
 RWKVTTS_API int rwkvtts_sqrelu_forward(long long n, const void *x, void *y, void *stream);

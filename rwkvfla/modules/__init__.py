@@ -6,6 +6,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 
+from rwkvtts_b200 import core, fused
+
 from .l2warp import l2_warp
 
 
@@ -18,6 +20,10 @@ class LayerNorm(nn.LayerNorm):
         super().__init__(hidden_size, eps=eps, elementwise_affine=elementwise_affine, bias=bias)
 
     def forward(self, x, residual=None, prenorm: bool = False):
+        if core.FUSED and self.elementwise_affine and fused.ln_usable(x) and (residual is None or residual.shape == x.shape):
+            # one kernel for the residual add and the norm (and one for their adjoint): csrc/tmix_fused.cu
+            y, total = fused.add_layernorm(x, residual, self.weight, self.bias, self.eps)
+            return (y, total) if prenorm else y
         if residual is not None:
             x = x + residual
         y = super().forward(x)

@@ -36,6 +36,8 @@ SYMBOLS = {
     "rwkvtts_tmix_prep_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp] * 5 + [_i] + [_vp] * 5 + [_vp] * 6 + [_fp, _fp, _vp]),
     "rwkvtts_tmix_out_forward": (_i, [_i, _i, _i] + [_vp] * 5 + [_fp] * 3 + [ctypes.c_float, _vp, _vp]),
     "rwkvtts_tmix_out_backward": (_i, [_i, _i, _i] + [_vp] * 5 + [_fp] * 3 + [ctypes.c_float] + [_vp] * 6 + [_fp, _fp, _vp]),
+    "rwkvtts_add_layernorm_forward": (_i, [ctypes.c_longlong, _i, _vp, _vp, _fp, _fp, ctypes.c_float, _vp, _vp, _fp, _vp]),
+    "rwkvtts_add_layernorm_backward": (_i, [ctypes.c_longlong, _i, _vp, _fp, _fp, _vp, _vp, _vp, _fp, _fp, _vp]),
     "rwkvtts_sqrelu_forward": (_i, [ctypes.c_longlong, _vp, _vp, _vp]),
     "rwkvtts_sqrelu_backward": (_i, [ctypes.c_longlong, _vp, _vp, _vp, _vp]),
     "rwkvtts_adam_shard": (_i, [_fp, _fp, _fp, _vp, _i, _vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_i]

@@ -31,6 +31,10 @@ cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *gra
                               int adamw, float bc1, float bc2_sqrt, float gscale, cudaStream_t st);
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
+cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
+                              void *y, void *s, float *stats, cudaStream_t st);
+cudaError_t launch_add_ln_bwd(long rows, int C, const void *sum, const float *stats, const float *w, const void *dy,
+                              const void *ds, void *dx, float *dparams, float *part, cudaStream_t st);
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                  const float *mix, void *const *out, void *prev_out, cudaStream_t st);
 cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
@@ -288,6 +292,22 @@ int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, const void *r,
     if (int rc = check_ptrs({y, r, k2, v2, g, r_k, ln_w, ln_b, d_o, dy, dr, dk2, dv2, dg, dparams, scratch})) return rc;
     return finish(rwkvtts::launch_out_bwd(B, T, C, y, r, k2, v2, g, r_k, ln_w, ln_b, eps, d_o, dy, dr, dk2, dv2, dg, dparams,
                                           scratch, (cudaStream_t)stream));
+}
+
+int rwkvtts_add_layernorm_forward(long long rows, int C, const void *x, const void *res, const float *w, const float *b,
+                                  float eps, void *y, void *s, float *stats, void *stream) {
+    if (rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 256 != 0 || C > 4096) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({x, w, y})) return rc;
+    if (int rc = check_opt({res, b, s, stats})) return rc;
+    return finish(rwkvtts::launch_add_ln_fwd((long)rows, C, x, res, w, b, eps, y, s, stats, (cudaStream_t)stream));
+}
+
+int rwkvtts_add_layernorm_backward(long long rows, int C, const void *sum, const float *stats, const float *w,
+                                   const void *dy, const void *ds, void *dx, float *dparams, float *scratch, void *stream) {
+    if (rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 256 != 0 || C > 4096) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({sum, stats, w, dy, dx, dparams, scratch})) return rc;
+    if (int rc = check_opt({ds})) return rc;
+    return finish(rwkvtts::launch_add_ln_bwd((long)rows, C, sum, stats, w, dy, ds, dx, dparams, scratch, (cudaStream_t)stream));
 }
 
 int rwkvtts_sqrelu_forward(long long n, const void *x, void *y, void *stream) {

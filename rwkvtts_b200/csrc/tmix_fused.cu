@@ -531,6 +531,126 @@ __global__ void __launch_bounds__(256) sqrelu_bwd_kernel(const bf16 *x, const bf
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// residual add + LayerNorm (Block.forward, rwkv_s2s_single_ffn.py:251-259: x + att(ln1(x)), x + ffn(ln2(x)); rwkvfla's
+// fused add+norm): s = x + res, y = (s - mean) * rstd * w + b.  One row = C/8 threads = whole warps (C % 256 == 0), the
+// two row reductions go warp shuffle -> shared memory -> every thread.  stats [rows][2] = (mean, rstd) for the backward.
+// ------------------------------------------------------------------------------------------------------------------
+struct LnParams {
+    const bf16 *x, *res;          // [rows, C]; res may be null
+    const float *w, *b;           // [C]; b may be null
+    bf16 *y, *s;                  // [rows, C]; s (the sum) may be null when res is null
+    float *stats;                 // [rows][2] or null
+    // backward
+    const bf16 *dy, *ds, *sum;    // ds may be null; sum = the forward's s (or x when there was no residual)
+    bf16 *dx;                     // = d res
+    float *part;                  // [grid][2][C]: dw, db
+    float eps;
+    long rows;
+    int C;
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+// sum over the C/8 threads of a row lane: red [nrl][wpr] floats, two barriers (uniform trip counts in the callers)
+__device__ __forceinline__ float row_sum(float x, float *red, int rl, int wpr, int wil) {
+    x = warp_sum(x);
+    if ((threadIdx.x & 31) == 0) red[rl * wpr + wil] = x;
+    __syncthreads();
+    float t = 0.f;
+    for (int j = 0; j < wpr; j++) t += red[rl * wpr + j];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kMaxThreads) add_ln_fwd_kernel(const LnParams P) {
+    __shared__ float red[kMaxThreads / 32];
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int wpr = tpr / 32, wil = cl / 32, c0 = cl * kVec;
+    const Row8 w = ld8f(P.w + c0), b = P.b != nullptr ? ld8f(P.b + c0) : zero8();
+    const float invC = 1.f / P.C;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < P.rows; base_row += (long)gridDim.x * nrl) {
+        long row = base_row + rl;
+        const bool valid = row < P.rows;
+        if (!valid) row = P.rows - 1;
+        const size_t off = row * P.C + c0;
+        Row8 x = ld8(P.x + off);
+        if (P.res != nullptr) {
+            const Row8 r = ld8(P.res + off);
+#pragma unroll
+            for (int i = 0; i < kVec; i++) x.v[i] = rbf(x.v[i] + r.v[i]);      // the sum is a bf16 tensor in the reference
+            if (P.s != nullptr) st8(P.s + off, x, valid);
+        }
+        float s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) s1 += x.v[i];
+        const float mu = row_sum(s1, red, rl, wpr, wil) * invC;
+        float s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) { const float d = x.v[i] - mu; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(row_sum(s2, red, rl, wpr, wil) * invC + P.eps);
+        Row8 o;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = (x.v[i] - mu) * rstd * w.v[i] + b.v[i];
+        st8(P.y + off, o, valid);
+        if (P.stats != nullptr && valid && cl == 0) { P.stats[2 * row] = mu; P.stats[2 * row + 1] = rstd; }
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 2) add_ln_bwd_kernel(const LnParams P) {
+    extern __shared__ float redp[];
+    __shared__ float red[2 * kBwdThreads / 32];
+    const int tpr = P.C / kVec, rl = threadIdx.x / tpr, cl = threadIdx.x % tpr, nrl = blockDim.x / tpr;
+    const int wpr = tpr / 32, wil = cl / 32, c0 = cl * kVec;
+    const Row8 w = ld8f(P.w + c0);
+    const float invC = 1.f / P.C;
+    float acc[2][kVec];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
+    for (long base_row = (long)blockIdx.x * nrl; base_row < P.rows; base_row += (long)gridDim.x * nrl) {
+        long row = base_row + rl;
+        const bool valid = row < P.rows;
+        if (!valid) row = P.rows - 1;
+        const size_t off = row * P.C + c0;
+        const Row8 sm_ = ld8(P.sum + off), dy = valid ? ld8(P.dy + off) : zero8();
+        const float mu = P.stats[2 * row], rstd = P.stats[2 * row + 1];
+        Row8 sh, g;
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            sh.v[i] = (sm_.v[i] - mu) * rstd;
+            g.v[i] = dy.v[i] * w.v[i];
+            acc[0][i] = fmaf(dy.v[i], sh.v[i], acc[0][i]);
+            acc[1][i] += dy.v[i];
+            m1 += g.v[i];
+            m2 = fmaf(g.v[i], sh.v[i], m2);
+        }
+        // both row means in one pass over the shared scratch
+        m1 = warp_sum(m1); m2 = warp_sum(m2);
+        if ((threadIdx.x & 31) == 0) { red[2 * (rl * wpr + wil)] = m1; red[2 * (rl * wpr + wil) + 1] = m2; }
+        __syncthreads();
+        m1 = 0.f; m2 = 0.f;
+        for (int j = 0; j < wpr; j++) { m1 += red[2 * (rl * wpr + j)]; m2 += red[2 * (rl * wpr + j) + 1]; }
+        __syncthreads();
+        m1 *= invC; m2 *= invC;
+        Row8 o;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = rstd * (g.v[i] - m1 - sh.v[i] * m2);
+        if (P.ds != nullptr && valid) {
+            const Row8 d2 = ld8(P.ds + off);
+#pragma unroll
+            for (int i = 0; i < kVec; i++) o.v[i] += d2.v[i];
+        }
+        st8(P.dx + off, o, valid);
+    }
+    write_partials<2>(acc, P.part, P.C, tpr, rl, cl, redp);
+}
+
 // launch geometry: threads per row = C/8; rows per CTA so that the CTA has <= 512 threads; grid = multiple of the SM count
 struct Geo { int threads, rows_per_cta, grid; size_t red_bytes(int n, int C) const { return (size_t)rows_per_cta * n * C * 4; } };
 inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm, int max_threads = kMaxThreads) {
@@ -559,6 +679,32 @@ int tmix_grid(int B, int T, int C, int which) {
     if (!shape_ok(B, T, C)) return 0;
     (void)which;
     return geometry(B, T, C, 4, 4, kBwdThreads).grid;
+}
+
+cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
+                              void *y, void *s, float *stats, cudaStream_t st) {
+    LnParams P{};
+    P.x = (const bf16 *)x; P.res = (const bf16 *)res; P.w = w; P.b = b; P.y = (bf16 *)y; P.s = (bf16 *)s; P.stats = stats;
+    P.eps = eps; P.rows = rows; P.C = C;
+    const Geo g = geometry(1, (int)rows, C, 4, 4);
+    count_launch();
+    add_ln_fwd_kernel<<<g.grid, g.threads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_add_ln_bwd(long rows, int C, const void *sum, const float *stats, const float *w, const void *dy,
+                              const void *ds, void *dx, float *dparams /* [2][C] */, float *part, cudaStream_t st) {
+    LnParams P{};
+    P.sum = (const bf16 *)sum; P.stats = const_cast<float *>(stats); P.w = w; P.dy = (const bf16 *)dy; P.ds = (const bf16 *)ds;
+    P.dx = (bf16 *)dx; P.part = part; P.rows = rows; P.C = C;
+    const Geo g = geometry(1, (int)rows, C, 4, 4, kBwdThreads);
+    const size_t sh = g.red_bytes(2, C);
+    cudaError_t e = cudaFuncSetAttribute(add_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return e;
+    count_launch(2);
+    add_ln_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
+    reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, dparams, g.grid, 2 * C);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st) {

@@ -278,3 +278,55 @@ class _SqRelu(torch.autograd.Function):
 def sqrelu(x: torch.Tensor) -> torch.Tensor:
     """relu(x) ** 2, the channel-mix activation (:228), one pass forward and one backward."""
     return _SqRelu.apply(x)
+
+
+def ln_usable(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype == BF16 and x.shape[-1] % 256 == 0 and x.shape[-1] <= 4096
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, w, b, eps):
+        _need_cuda(x, res, w, b)
+        C = x.shape[-1]
+        rows = x.numel() // C
+        x = x.contiguous()
+        res = None if res is None else res.contiguous()
+        w32, b32 = _f32(w, C), _f32(b, C)
+        y = torch.empty_like(x)
+        s = torch.empty_like(x) if res is not None else None
+        need_bwd = any(ctx.needs_input_grad[:4])     # (grad mode is off inside forward: ask the context)
+        stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device) if need_bwd else None
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().rwkvtts_add_layernorm_forward(rows, C, _ptr(x), _ptr(res), _ptr(w32), _ptr(b32), float(eps),
+                                                          _ptr(y), _ptr(s), _ptr(stats), _stream())
+        _lib.check(rc, "rwkvtts_add_layernorm_forward")
+        total = s if res is not None else x
+        ctx.save_for_backward(total, stats, w32)
+        ctx.meta = (w.dtype, w.shape, None if b is None else (b.dtype, b.shape), res is not None)
+        return y, total
+
+    @staticmethod
+    def backward(ctx, dy, ds):
+        total, stats, w32 = ctx.saved_tensors
+        C = total.shape[-1]
+        rows = total.numel() // C
+        dy = torch.zeros_like(total) if dy is None else dy.contiguous()
+        ds = None if ds is None else ds.contiguous()
+        dx = torch.empty_like(total)
+        dparams = torch.empty(2, C, dtype=torch.float32, device=total.device)
+        scratch = _scratch(1, rows, C, 2, total.device)
+        with torch.cuda.device(total.device):
+            rc = _lib.lib().rwkvtts_add_layernorm_backward(rows, C, _ptr(total), _ptr(stats), _ptr(w32), _ptr(dy), _ptr(ds),
+                                                           _ptr(dx), _ptr(dparams), _ptr(scratch), _stream())
+        _lib.check(rc, "rwkvtts_add_layernorm_backward")
+        wdt, wsh, bmeta, has_res = ctx.meta
+        dw = dparams[0].to(wdt).reshape(wsh)
+        db = None if bmeta is None else dparams[1].to(bmeta[0]).reshape(bmeta[1])
+        return dx, (dx if has_res else None), dw, db, None
+
+
+def add_layernorm(x, residual, weight, bias, eps):
+    """(LayerNorm(x + residual) * weight + bias, x + residual); residual may be None (then the second result is x).
+    forward stats are kept only when a backward can follow (no_grad: inference / decode)."""
+    return _AddLayerNorm.apply(x, residual, weight, bias, eps)

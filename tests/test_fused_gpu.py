@@ -145,6 +145,36 @@ def test_out(fused, B, T, C):
         assert rel(x1.grad, x2.grad) < PAR_TOL, name
 
 
+@pytest.mark.parametrize("B,T,C,use_res,use_bias", [(2, 33, 256, True, True), (8, 64, 1024, True, True), (1, 7, 2048, False, True),
+                                                    (3, 5, 512, True, False)])
+def test_add_layernorm(fused, B, T, C, use_res, use_bias):
+    g = torch.Generator(device="cuda").manual_seed(C + T)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
+    x, res = rn(B, T, C), (rn(B, T, C) if use_res else None)
+    w, b = 1 + 0.3 * rn(C), (0.3 * rn(C) if use_bias else None)
+    dy, ds = rn(B, T, C), rn(B, T, C)
+    leaf = lambda t: None if t is None else t.detach().clone().requires_grad_(True)
+    x1, r1, w1, b1 = leaf(x), leaf(res), leaf(w), leaf(b)
+    y, tot = fused.add_layernorm(x1, r1, w1, b1, 1e-5)
+    torch.autograd.backward([y, tot], [dy, ds])
+    f = lambda t: None if t is None else t.detach().float().requires_grad_(True)
+    x2, r2, w2, b2 = f(x), f(res), f(w), f(b)
+    tot2 = x2 if r2 is None else (x2 + r2).bfloat16().float() + 0 * (x2 + r2)      # the sum is a bf16 tensor in the model
+    tot2 = x2 if r2 is None else x2 + r2
+    y2 = F.layer_norm(tot2, (C,), w2, b2, 1e-5)
+    torch.autograd.backward([y2, tot2], [dy.float(), ds.float()])
+    assert rel(y, y2) < ACT_TOL and rel(tot, tot2) < ACT_TOL
+    assert rel(x1.grad, x2.grad) < 2 * ACT_TOL
+    if use_res:
+        assert rel(r1.grad, r2.grad) < 2 * ACT_TOL
+    assert rel(w1.grad, w2.grad) < PAR_TOL
+    if use_bias:
+        assert rel(b1.grad, b2.grad) < PAR_TOL
+    with torch.no_grad():                          # inference path (no stats)
+        y3, _ = fused.add_layernorm(x, res, w, b, 1e-5)
+    assert torch.equal(y3, y)
+
+
 def test_sqrelu(fused):
     x = torch.randn(3, 17, 512, device="cuda").bfloat16().requires_grad_(True)
     dy = torch.randn(3, 17, 512, device="cuda").bfloat16()
