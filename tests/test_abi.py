@@ -48,6 +48,30 @@ def test_argument_validation_without_gpu(built):
     assert a.value == 8 * 16 * 256 * 64 * 64 and b.value == 8 * 4096 * 16 * 64 and tot == a.value + b.value
 
 
+def test_fused_kernel_argument_validation_without_gpu(built):
+    """The fused time-mix / LayerNorm / activation entry points validate shapes and pointers before any CUDA call."""
+    import ctypes
+    from rwkvtts_b200 import _lib, fused
+    L = _lib.lib()
+    buf = torch.zeros(1 << 16, dtype=torch.float32)
+    p = buf.data_ptr()
+    outs = (ctypes.c_void_p * 6)(*[p] * 6)
+    assert L.rwkvtts_tmix_shift_mix_forward(1, 4, 100, 6, p, None, None, p, outs, None, None) == -1      # C % 64 != 0
+    assert L.rwkvtts_tmix_shift_mix_forward(1, 4, 64, 3, p, None, None, p, outs, None, None) == -1       # n must be 1 or 6
+    assert L.rwkvtts_tmix_shift_mix_forward(1, 4, 64, 6, None, None, None, p, outs, None, None) == -2
+    assert L.rwkvtts_tmix_shift_mix_forward(1, 4, 64, 6, p, None, p, p, outs, p, None) == -1             # in-place state: T == 1 only
+    assert L.rwkvtts_add_layernorm_forward(8, 100, p, None, p, None, 1e-5, p, None, None, None) == -1    # C % 256 != 0
+    assert L.rwkvtts_add_layernorm_forward(8, 256, p, None, None, None, 1e-5, p, None, None, None) == -2
+    assert L.rwkvtts_sqrelu_forward(12, p, p, None) == -1                                                 # n % 8 != 0
+    assert L.rwkvtts_tmix_out_forward(1, 4, 64, p, p, p, p, p, p, p, None, 1e-5, p, None) == -2           # ln_b missing
+    assert L.rwkvtts_tmix_scratch_floats(1, 4, 100, 5) == 0
+    # host side: CPU tensors never reach the fused kernels (the ATen formulation serves the CPU oracle tests)
+    x = torch.zeros(1, 4, 64, dtype=torch.bfloat16)
+    assert not fused.usable(x) and not fused.ln_usable(x)
+    with pytest.raises(_lib.RwkvttsError):
+        fused.sqrelu(x)
+
+
 def test_reference_schemas_registered_and_no_cpu_fallback(built):
     import rwkvtts_b200 as R
     s = str(torch.ops.wind_backstepping.forward.default._schema)
