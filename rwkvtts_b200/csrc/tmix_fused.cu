@@ -245,8 +245,15 @@ __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams 
         const size_t off = row * P.C + c0;
         const float m = (P.mask != nullptr) ? __bfloat162float(P.mask[row]) : 1.f;
         const float mk = P.mask_rwk ? m : 1.f;
-        Row8 k = ld8(P.k + off);
-        const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
+        // all of the row's loads are issued before the first use (one memory round trip per iteration, not two)
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        const uint4 rk = *reinterpret_cast<const uint4 *>(P.k + off), rwl = *reinterpret_cast<const uint4 *>(P.w_lo + off),
+                    ral = *reinterpret_cast<const uint4 *>(P.a_lo + off);
+        const uint4 rv = (P.v2 != nullptr) ? *reinterpret_cast<const uint4 *>(P.v + off) : zero4;
+        const uint4 rvl = has_v ? *reinterpret_cast<const uint4 *>(P.v_lo + off) : zero4;
+        const uint4 rvf = has_v ? *reinterpret_cast<const uint4 *>(P.v_first + off) : zero4;
+        Row8 k, wl, al;
+        unpack8(rk, k.v); unpack8(rwl, wl.v); unpack8(ral, al.v);
         Row8 w, a, u, o;
         float ss = 0.f;
 #pragma unroll
@@ -269,9 +276,11 @@ __global__ void __launch_bounds__(kMaxThreads) prep_fwd_kernel(const PrepParams 
         for (int i = 0; i < kVec; i++) o.v[i] = k.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i]);
         st8(P.k2 + off, o, valid);
         if (P.v2 != nullptr) {
-            Row8 v = ld8(P.v + off);
+            Row8 v;
+            unpack8(rv, v.v);
             if (has_v) {
-                const Row8 vl = ld8(P.v_lo + off), vf = ld8(P.v_first + off);
+                Row8 vl, vf;
+                unpack8(rvl, vl.v); unpack8(rvf, vf.v);
 #pragma unroll
                 for (int i = 0; i < kVec; i++) {
                     const float vm = v.v[i] * mk;         // the reference masks v before the residual mix (:178) ...
@@ -312,6 +321,12 @@ __global__ void __launch_bounds__(kBwdThreads, 2) prep_bwd_kernel(const PrepPara
         const Row8 wl = ld8(P.w_lo + off), al = ld8(P.a_lo + off);
         Row8 dw = zero8(), dk2 = zero8(), da_op = zero8(), db_op = zero8();
         if (valid) { dw = ld8(P.dw + off); dk2 = ld8(P.dk2 + off); da_op = ld8(P.da_op + off); db_op = ld8(P.db_op + off); }
+        // the v branch's loads are issued with the others (one memory round trip per iteration)
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        const uint4 rdv2 = (P.dv != nullptr && valid) ? *reinterpret_cast<const uint4 *>(P.dv2 + off) : zero4;
+        const uint4 rv = has_v ? *reinterpret_cast<const uint4 *>(P.v + off) : zero4;
+        const uint4 rvl = has_v ? *reinterpret_cast<const uint4 *>(P.v_lo + off) : zero4;
+        const uint4 rvf = has_v ? *reinterpret_cast<const uint4 *>(P.v_first + off) : zero4;
         Row8 a, u, o;
         float ss = 0.f;
 #pragma unroll
@@ -356,9 +371,11 @@ __global__ void __launch_bounds__(kBwdThreads, 2) prep_bwd_kernel(const PrepPara
         }
         st8(P.dk + off, o, valid);
         if (P.dv != nullptr) {
-            const Row8 dv2 = valid ? ld8(P.dv2 + off) : zero8();
+            Row8 dv2;
+            unpack8(rdv2, dv2.v);
             if (has_v) {
-                const Row8 v = ld8(P.v + off), vl = ld8(P.v_lo + off), vf = ld8(P.v_first + off);
+                Row8 v, vl, vf;
+                unpack8(rv, v.v); unpack8(rvl, vl.v); unpack8(rvf, vf.v);
                 Row8 dvl, dvf;
 #pragma unroll
                 for (int i = 0; i < kVec; i++) {
