@@ -1,5 +1,5 @@
 // WKV-7 training backward for sm_100a: chunked DPLR adjoint on the 5th-generation tensor cores
-// (tcgen05.mma kind::tf32; dS, dS^T, the transposed forward state and all gradient tiles in tensor memory).
+// (tcgen05.mma kind::tf32; dS, dS^T and all gradient tiles in tensor memory, S0^T as a shared-memory operand).
 //
 // Reference operator: the exact adjoint of model/llm/cuda/wkv7_cuda.cu:17-42 (backward_kernel :54-130).
 // Unlike the reference it never un-steps the state (no division by the decay): the forward
@@ -24,12 +24,18 @@
 // the tensor-memory lanes, so every gradient tile comes out as [channel][16 tokens] and the dw scan is
 // thread-local.
 //
-// One CTA per (batch, head), 25 warps:
-//   warps  0-7   group C: S0^T -> tensor memory, Z -> shared tiles, the four 16x16 gradient Grams (mma.sync),
-//                output epilogue (scaling, dw scan, bf16, coalesced stores), window-boundary rescale of dS
-//   warps  8-15  stage A: HBM loads (7 bf16 arrays + sa + checkpoint), decay scan, operand tiles
-//   warps 16-23  stage B (two groups on alternate chunks): forward Gram blocks, back substitution
-//   warp   24    MMA issuer
+// One CTA per (batch, head), 25 warps, every hand-off an mbarrier with one arrival per warp:
+//   warps  0-3   group C1 (on the chain): window-boundary rescale of dS / dS^T in tensor memory, Z^T -> shared operand
+//                tiles, the four 16x16 gradient Gram blocks (mma.sync)
+//   warps  4-11  group C2 (off the chain): output epilogue of chunk `it` while chunk `it+1` is in flight -- gradient
+//                accumulators double buffered in tensor memory; scaling, dw suffix scan, bf16, staging in slot tiles
+//                that are dead by then, 128-byte rows; window-boundary term sum_v dS.S
+//   warps 12-19  stage A: cp.async ring of the 7 bf16 inputs (one chunk ahead), the window's decays (one window ahead),
+//                decay scan, ten operand tiles; U (`sa`) arrives by bulk copy straight into its operand tile
+//   warps 20-23  stage B: forward Gram blocks (64-bit conflict-free fragment loads), back substitution
+//   warp   24    MMA issuer; also brings S0^T (the checkpoint, already in operand layout) in with one bulk copy per chunk
+// Three operand slots; scan scratch, stage-B scratch and the output staging alias slot tiles that are written later /
+// already consumed.  Bound by the shared-memory data pipe (~80 % of peak on the SMs that hold a CTA, ncu).
 #include "mma_tf32.cuh"
 #include "tc05.cuh"
 #include "wkv7_common.cuh"

@@ -14,8 +14,10 @@
 //         phase 2:  S^ += U^T B~ + V^T K~ ;   Y^T += U^T Aqb^T                       (tcgen05, N = 64 / 16)
 // (U_t = S_{t-1} a_t is the reference's `sa`).  At a window end S^ is multiplied by e^{G_64}
 // (tensor memory -> registers -> tensor memory).  The training variant also writes, per chunk, the
-// TRANSPOSED state at the chunk start (window frame) and `sa` for the chunked backward
-// (wkv7_tc_bwd.cu), into the caller's scratch tensors `s` / `sa` (reference sizes).  |G| <= 64 * 1.35 stays inside the fp32 exponent range; log-decays below -1.35
+// TRANSPOSED state at the chunk start (window frame) and `sa` for the chunked backward (wkv7_tc_bwd.cu), as dense
+// tensor-core operand tiles (wkv7_common.cuh) inside the caller's scratch tensors `s` / `sa` (reference sizes); the
+// transposed state is kept up to date by the tensor core itself (S^T += B~^T U + K~^T V, one chunk behind).
+// |G| <= 64 * 1.35 stays inside the fp32 exponent range; log-decays below -1.35
 // per step (decay < 0.26; the model's range is (-0.6065, 0), rwkv_s2s_single_ffn.py:172) are clamped.
 //
 // tcgen05 facts this kernel relies on (measured with tests/csrc/umma_probe.cu on a B200):
@@ -25,13 +27,17 @@
 //     behind it: every phase boundary is a tcgen05.commit + mbarrier wait (~170 cycles);
 //   * tf32 operands in shared memory must be K-major (no-swizzle canonical layout, tc05.cuh).
 //
-// One CTA per (batch, head), 21 warps:
-//   warps  0-3   epilogue: Y^T tensor memory -> bf16 -> HBM, window-end rescale, checkpoints, s0 / sT
-//   warps  4-11  stage A: HBM loads, decay scan, scaled operands (natural + canonical layouts)
+// One CTA per (batch, head), 21 warps (25 in the training variant), one mbarrier arrival per warp at every hand-off:
+//   warps  0-3   epilogue: Y^T tensor memory -> bf16 -> HBM, window-end rescale of S^, s0 / sT; training: U to HBM in
+//                the backward's operand layout and as the [value][token] operand tile of the transposed-state update
+//   warps  4-11  stage A: HBM loads, decay scan (log2 domain, two-stage cross-warp prefix), scaled operands in both
+//                orientations
 //   warps 12-15  stage B (even chunks), warps 16-19 stage B (odd chunks): Gram blocks (mma.sync tf32),
 //                triangular solve, W~ / M1 / Aqk / Aqb into the canonical operand slot
-//   warp   20    MMA issuer (one elected lane), owns the tensor-memory allocation
-// All hand-offs are mbarriers; the operand slots form a ring of NSLOT chunks.
+//   warp   20    MMA issuer (one elected lane), owns the tensor-memory allocation; training: also S^T += B~^T U + K~^T V
+//   warps 21-24  (training) checkpoint group: reads S^T with keys on the lanes -> 16-byte pieces of the backward's
+//                K-major S0^T operand tile, 256 contiguous bytes per warp store
+// The operand slots form a ring of NSLOT chunks.  Bound by the shared-memory data pipe (~75-80 % of peak, ncu).
 #include "mma_tf32.cuh"
 #include "tc05.cuh"
 #include "wkv7_common.cuh"
