@@ -373,7 +373,13 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
         logits = out.logits[:, -1].float()
         if use_cuda_graph is None:
             use_cuda_graph = dev.type == "cuda" and max_new_tokens > 8
-        graph_step = _GraphDecodeStep(self, cache, B, dev) if (use_cuda_graph and max_new_tokens > 1) else None
+        graph_step = None
+        if use_cuda_graph and max_new_tokens > 1:
+            try:
+                graph_step = _GraphDecodeStep(self, cache, B, dev)
+            except RuntimeError as e:                  # e.g. an op that cannot be captured in a user subclass: decode eagerly
+                warnings.warn(f"CUDA-graph decode step unavailable ({e}); falling back to the eager step")
+                torch.cuda.synchronize(dev)
         for step in range(max_new_tokens):
             if eos_t is not None and step < min_new_tokens:
                 logits[:, eos_t] = float("-inf")
