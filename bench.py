@@ -31,6 +31,44 @@ METRIC = "audio-tokens/sec (train fwd+bwd) RWKV-7 0.4B seq4096"
 WORKLOAD = "configs[1]: RWKV-7 0.4B Spark-layout bf16, batch 8/GPU, seq_len 4096, WKV-7 fwd+bwd x 24 layers"
 
 
+def dist_init(world):
+    """Control plane of a multi-GPU run.  The path shards by batch with no data-path collective, so
+    the only exchanges of the bench are its barriers and the max over ranks of two scalars: they go over gloo (CPU
+    tensors).  The process group is created with NCCL registered for CUDA tensors, as a training job would have it
+    (the ZeRO-2 engine's reduce-scatter / all-gather), but the NCCL communicator is only built on the first CUDA
+    collective -- which this bench never issues -- so an 8-rank start does not pay (or hang in) NVLS / fabric set-up."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    import torch
+    try:
+        dist.init_process_group("cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo")
+    except Exception:                      # mixed registration unavailable: the control plane only needs gloo
+        if dist.is_initialized():
+            dist.destroy_process_group()
+        dist.init_process_group("gloo")
+
+
+def dist_barrier(world):
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(torch.zeros(1))          # CPU tensor -> gloo
+
+
+def dist_max(x, world):
+    import torch
+    if world <= 1:
+        return float(x)
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -227,9 +265,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    dist_init(world)
+    extras = world == 1          # the explanatory legs (other kernels, fused kernels, reference CUDA op) run at N = 1 only
     import rwkvtts_b200 as R
     from rwkvtts_b200.synth import make_inputs
     lib = R._lib.lib()
@@ -251,9 +288,7 @@ def main():
             R.wkv7_backward_(*ins, d["dy"], s, sa, *grads)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        dist_barrier(world)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -274,10 +309,7 @@ def main():
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / (args.steps * LAYERS)
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / (args.steps * LAYERS)
-    t = torch.tensor([total_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = dist_max(total_ms, world)
     ms_per_step = total_ms / args.steps
     value = B * T * world / (ms_per_step * 1e-3)
 
@@ -290,52 +322,62 @@ def main():
             fn()
         b_.record(); torch.cuda.synchronize()
         return a.elapsed_time(b_) / n
-    infer_ms = timed(lambda: R.wkv7_forward_infer_(*ins, y))                 # chunked tcgen05 forward (no_grad)
-    DB, DSTEPS = 32, 64                                                       # config c4: 32 prompts, decode steps
-    dstate = torch.zeros(LAYERS, DB, H, C, C, dtype=torch.float32, device=dev)
-    dins = [d[n][:4, :DB // 4 * 1].reshape(DB, 1, H * C).contiguous() for n in "qwkvab"]
-    dy_ = torch.empty(DB, 1, H * C, dtype=torch.bfloat16, device=dev)
-    def decode_steps():
-        for _ in range(DSTEPS):
-            for l in range(LAYERS):
-                R.wkv7_state_forward_(DB, 1, H * C, H, dstate[l], *dins, dy_)
-    decode_ms = timed(decode_steps, n=2) / DSTEPS                            # WKV part of one decode step, 24 layers
+    def other_kernels():
+        infer_ms = timed(lambda: R.wkv7_forward_infer_(*ins, y))                 # chunked tcgen05 forward (no_grad)
+        DB, DSTEPS = 32, 64                                                       # config c4: 32 prompts, decode steps
+        dstate = torch.zeros(LAYERS, DB, H, C, C, dtype=torch.float32, device=dev)
+        dins = [d[n][:4, :DB // 4 * 1].reshape(DB, 1, H * C).contiguous() for n in "qwkvab"]
+        dy_ = torch.empty(DB, 1, H * C, dtype=torch.bfloat16, device=dev)
+        def decode_steps():
+            for _ in range(DSTEPS):
+                for l in range(LAYERS):
+                    R.wkv7_state_forward_(DB, 1, H * C, H, dstate[l], *dins, dy_)
+        decode_ms = timed(decode_steps, n=2) / DSTEPS                            # WKV part of one decode step, 24 layers
 
-    # ---- fused time-mix elementwise kernels at the same config ([8,4096,1024] activations; explain, not part of `value`)
-    from rwkvtts_b200 import fused as FU
-    CC = H * C
-    act = lambda: torch.randn(B, T, CC, device=dev).bfloat16()
-    par = lambda *sh: (0.5 * torch.randn(*sh, device=dev)).bfloat16()
-    fx, fdo = act(), [act() for _ in range(6)]
-    mixes = [par(1, 1, CC).requires_grad_(True) for _ in range(6)]
-    k_, v_, wl_, al_, vl_, vf_ = (act().requires_grad_(True) for _ in range(6))
-    pp = [par(1, 1, CC).requires_grad_(True) for _ in range(5)]
-    y_, r_, g_ = (act().requires_grad_(True) for _ in range(3))
-    rk_, lw_, lb_ = par(H, C).requires_grad_(True), par(CC).requires_grad_(True), par(CC).requires_grad_(True)
-    fxg = fx.clone().requires_grad_(True)
+        return infer_ms, decode_ms, DB
 
-    def fused_times():
-        res = {}
-        def fb(name, fwd, inputs, douts, n_fwd_arrays, n_bwd_arrays):
-            outs = fwd()
-            outs = outs if isinstance(outs, (tuple, list)) else (outs,)
-            tf = timed(fwd, n=5)
-            # autograd.grad: no accumulation into .grad, so the timed region is the backward kernels + a few allocations
-            tb = timed(lambda: torch.autograd.grad(outs, inputs, douts[:len(outs)], retain_graph=True), n=5)
-            nbytes = B * T * CC * 2
-            res[name] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_GBps": n_fwd_arrays * nbytes / tf / 1e6,
-                         "bwd_GBps": n_bwd_arrays * nbytes / tb / 1e6,
-                         "fwd_frac": n_fwd_arrays * nbytes / tf / 1e6 / peak_, "bwd_frac": n_bwd_arrays * nbytes / tb / 1e6 / peak_}
-        peak_ = peaks()[0]
-        fb("shift_mix6", lambda: FU.shift_mix(fxg, mixes), [fxg] + mixes, fdo, 7, 8)     # fwd 1r+6w; bwd 6r+1r(x)+1w
-        fb("prep", lambda: FU.prep(k_, v_, wl_, al_, vl_, vf_, *pp), [k_, v_, wl_, al_, vl_, vf_] + pp, fdo, 11, 17)  # 6r+5w; 11r+6w
-        fb("out", lambda: FU.out(y_, r_, k_, v_, g_, rk_, lw_, lb_, 64e-5), [y_, r_, k_, v_, g_, rk_, lw_, lb_], fdo, 6, 11)  # 5r+1w; 6r+5w
-        res["note"] = ("algorithmic arrays of [B,T,C] bf16 moved per call / CUDA-event time of the autograd call (includes "
-                       "the partial-sum reduce kernel and output allocations)")
-        return res
-    fused_k = fused_times()
-    del fx, fdo, k_, v_, wl_, al_, vl_, vf_, y_, r_, g_, fxg
-    torch.cuda.empty_cache()
+    def fused_leg():
+        # ---- fused time-mix elementwise kernels at the same config ([8,4096,1024] activations; explain, not part of `value`)
+        from rwkvtts_b200 import fused as FU
+        CC = H * C
+        act = lambda: torch.randn(B, T, CC, device=dev).bfloat16()
+        par = lambda *sh: (0.5 * torch.randn(*sh, device=dev)).bfloat16()
+        fx, fdo = act(), [act() for _ in range(6)]
+        mixes = [par(1, 1, CC).requires_grad_(True) for _ in range(6)]
+        k_, v_, wl_, al_, vl_, vf_ = (act().requires_grad_(True) for _ in range(6))
+        pp = [par(1, 1, CC).requires_grad_(True) for _ in range(5)]
+        y_, r_, g_ = (act().requires_grad_(True) for _ in range(3))
+        rk_, lw_, lb_ = par(H, C).requires_grad_(True), par(CC).requires_grad_(True), par(CC).requires_grad_(True)
+        fxg = fx.clone().requires_grad_(True)
+
+        def fused_times():
+            res = {}
+            def fb(name, fwd, inputs, douts, n_fwd_arrays, n_bwd_arrays):
+                outs = fwd()
+                outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+                tf = timed(fwd, n=5)
+                # autograd.grad: no accumulation into .grad, so the timed region is the backward kernels + a few allocations
+                tb = timed(lambda: torch.autograd.grad(outs, inputs, douts[:len(outs)], retain_graph=True), n=5)
+                nbytes = B * T * CC * 2
+                res[name] = {"fwd_ms": tf, "bwd_ms": tb, "fwd_GBps": n_fwd_arrays * nbytes / tf / 1e6,
+                             "bwd_GBps": n_bwd_arrays * nbytes / tb / 1e6,
+                             "fwd_frac": n_fwd_arrays * nbytes / tf / 1e6 / peak_, "bwd_frac": n_bwd_arrays * nbytes / tb / 1e6 / peak_}
+            peak_ = peaks()[0]
+            fb("shift_mix6", lambda: FU.shift_mix(fxg, mixes), [fxg] + mixes, fdo, 7, 8)     # fwd 1r+6w; bwd 6r+1r(x)+1w
+            fb("prep", lambda: FU.prep(k_, v_, wl_, al_, vl_, vf_, *pp), [k_, v_, wl_, al_, vl_, vf_] + pp, fdo, 11, 17)  # 6r+5w; 11r+6w
+            fb("out", lambda: FU.out(y_, r_, k_, v_, g_, rk_, lw_, lb_, 64e-5), [y_, r_, k_, v_, g_, rk_, lw_, lb_], fdo, 6, 11)  # 5r+1w; 6r+5w
+            res["note"] = ("algorithmic arrays of [B,T,C] bf16 moved per call / CUDA-event time of the autograd call (includes "
+                           "the partial-sum reduce kernel and output allocations)")
+            return res
+        return fused_times()
+
+
+    infer_ms = decode_ms = fused_k = None
+    DB = 32
+    if extras:
+        infer_ms, decode_ms, DB = other_kernels()
+        fused_k = fused_leg()
+        torch.cuda.empty_cache()
 
     # ---- e2e: public API (WindBackstepping autograd op) with pinned HOST buffers --------------
     host_in = [x[n].pin_memory() for n in "wqkvab"] + [x["dy"].pin_memory()]
@@ -352,13 +394,14 @@ def main():
     ev_in = [torch.cuda.Event() for _ in range(2)]          # inputs of buffer b have landed
     ev_free = [torch.cuda.Event() for _ in range(2)]        # kernels are done with buffer b
     ev_out = [torch.cuda.Event() for _ in range(2)]         # results of buffer b are in host memory
+    used = [False, False]
 
     def e2e_step():
         for l in range(LAYERS):
             b = l % 2
             with torch.cuda.stream(s_in):
-                if l >= 2:
-                    s_in.wait_event(ev_free[b])
+                if l >= 2 or used[b]:
+                    s_in.wait_event(ev_free[b])     # the kernels of the layer that last used this buffer are done
                 for t_, h_ in zip(dev_in[b], host_in):
                     t_.copy_(h_, non_blocking=True)
                 ev_in[b].record(s_in)
@@ -367,6 +410,7 @@ def main():
             yy = R.WindBackstepping.apply(*leaves)
             yy.backward(dev_in[b][6])
             ev_free[b].record(s_comp)
+            used[b] = True
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_free[b])
                 outs = [yy.detach()] + [l_.grad for l_ in leaves]
@@ -384,10 +428,8 @@ def main():
         e2e_step()
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * T * world / (float(t.item()) / args.e2e_steps * 1e-3)
+    e2e_ms = dist_max(e0.elapsed_time(e1), world)
+    e2e_value = B * T * world / (e2e_ms / args.e2e_steps * 1e-3)
 
     if rank != 0:
         if world > 1:
@@ -396,7 +438,7 @@ def main():
 
     # ---- reference CUDA op on the same inputs (extra data point; oracle/_ref) --------------------
     ref_gpu = None
-    if not args.no_ref_gpu:
+    if extras and not args.no_ref_gpu:
         try:
             from oracle import c_oracle as CO
             if CO.ref_available():
@@ -430,6 +472,18 @@ def main():
     ach = dom_bytes * th / (dom_ms * 1e-3) / 1e9
     fwd_ach = FWD_BYTES * th / (fwd_ms * 1e-3) / 1e9
     bwd_ach = BWD_BYTES * th / (bwd_ms * 1e-3) / 1e9
+    kernels = {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": fwd_ach, "bwd_GBps": bwd_ach,
+               "fwd_frac": fwd_ach / peak, "bwd_frac": bwd_ach / peak,
+               "note": "fwd/bwd = training pair (chunked tcgen05 kernels, default family)"}
+    if extras:
+        kernels.update({
+            "fwd_infer_tcgen05_ms": infer_ms, "fwd_infer_GBps": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9,
+            "fwd_infer_frac": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9 / peak,
+            "decode_step_wkv_ms": decode_ms,
+            "decode_step_GBps": (2 * C * C * 4 + FWD_BYTES) * DB * H * LAYERS / (decode_ms * 1e-3) / 1e9,
+            "decode_wkv_tokens_per_s": DB / (decode_ms * 1e-3),
+            "note": "fwd/bwd = training pair (chunked tcgen05 kernels, default family); fwd_infer = snapshot-free tcgen05 "
+                    "forward used under no_grad; decode = single-step kernel called eagerly, T=1, B=32, 24 layers (launch-bound)"})
     # DRAM bytes per launch of the two training kernels: dram__bytes_read.sum + dram__bytes_write.sum from the ncu
     # `--set full` capture of this same configuration (profiles/r01_tc_pair_full_v5.txt); the excess over the algorithmic
     # bytes is the checkpoint / U scratch the pair exchanges (537 + 134 MB written by the forward, read by the backward)
@@ -450,15 +504,7 @@ def main():
                      "traffic_source": "ncu --set full capture, profiles/r01_tc_pair_full_v5.txt", "peak_source": peak_src,
                      "algorithmic_bytes_per_token_head": dom_bytes, "token_heads_per_launch": th,
                      "avg_launch_ms": dom_ms},
-        "kernels": {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "fwd_GBps": fwd_ach, "bwd_GBps": bwd_ach,
-                    "fwd_frac": fwd_ach / peak, "bwd_frac": bwd_ach / peak,
-                    "fwd_infer_tcgen05_ms": infer_ms, "fwd_infer_GBps": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9,
-                    "fwd_infer_frac": FWD_BYTES * th / (infer_ms * 1e-3) / 1e9 / peak,
-                    "decode_step_wkv_ms": decode_ms,
-                    "decode_step_GBps": (2 * C * C * 4 + FWD_BYTES) * DB * H * LAYERS / (decode_ms * 1e-3) / 1e9,
-                    "decode_wkv_tokens_per_s": DB / (decode_ms * 1e-3),
-                    "note": "fwd/bwd = training pair (chunked tcgen05 kernels, default family); fwd_infer = snapshot-free "
-                            "tcgen05 forward used under no_grad; decode = stateful scan op, T=1, B=32, 24 layers (config c4)"},
+        "kernels": kernels,
         "fused_tmix_kernels": fused_k,
         "ref_gpu_op": ref_gpu,
     }
