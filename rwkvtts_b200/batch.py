@@ -74,3 +74,60 @@ def create_inputs_and_labels(batch: Dict[str, Any], tokenizer, model, eos_token_
         emb = first if k == "semantic" else tables[k](part[j])
         out = out.index_copy(0, part[4 + j], emb)
     return {"input_embs": out.view(B, Tmax, -1), "labels": part[8].view(B, Tmax), "attention_mask": part[9].view(B, Tmax)}
+
+
+def process_single_batch(batch: Dict[str, torch.Tensor], rwkv7speech_model, eos_token_id: int = 8192) -> Dict[str, torch.Tensor]:
+    """Same signature and result as the reference's process_single_batch (/root/reference/data/utils/spark_dataset.py:
+    165-239), the collator of train_spark_rwkv7speech.py: the batch holds LEFT-padded id matrices with their masks
+    (`input_ids`, `global_tokens_ids`, `semantic_tokens_ids` + `*attention_mask*`); the result is the LEFT-padded
+    [tag2, text, tag0, global, tag1, semantic] embedding batch, its attention mask, and labels that are already shifted
+    (`labels[i, -S-1:-1] = semantic ids, labels[i, -1] = eos`, :231-232).
+
+    The reference reads six lengths per sample with `.item()` (host syncs) and launches ~25 kernels per sample; here the
+    three length vectors come back in one transfer, the layout is computed on the host, and the batch is assembled with
+    one id gather, one embedding lookup and one scatter per table."""
+    model = rwkv7speech_model
+    device = model.device
+    ids_t, ids_g, ids_s = batch["input_ids"], batch["global_tokens_ids"], batch["semantic_tokens_ids"]
+    B = ids_t.shape[0]
+    lens = torch.stack([batch["attention_mask_input_ids"].sum(1), batch["global_tokens_attention_mask"].sum(1),
+                        batch["semantic_tokens_attention_mask"].sum(1)]).tolist()          # the only host sync
+    tl, gl, sl = ([int(v) for v in row] for row in lens)
+    total = [tl[i] + gl[i] + sl[i] + 3 for i in range(B)]
+    Tmax = max(total)
+    src = {k: [] for k in ("text", "global", "semantic")}       # flat positions inside the padded id matrices
+    dst = {k: [] for k in ("tag", "text", "global", "semantic")}
+    lab_dst, mask = [], np.zeros((B, Tmax), dtype=np.int64)
+    for i in range(B):
+        pad = Tmax - total[i]
+        base = i * Tmax + pad
+        mask[i, pad:] = 1
+        p_text, p_tag0 = 1, 1 + tl[i]
+        p_glob, p_tag1 = p_tag0 + 1, p_tag0 + 1 + gl[i]
+        p_sem = p_tag1 + 1
+        dst["tag"] += [base, base + p_tag0, base + p_tag1]
+        for k, ids, n, p in (("text", ids_t, tl[i], p_text), ("global", ids_g, gl[i], p_glob), ("semantic", ids_s, sl[i], p_sem)):
+            L = ids.shape[1]
+            src[k] += range(i * L + L - n, i * L + L)              # the last n entries of row i (left padding)
+            dst[k] += range(base + p, base + p + n)
+        lab_dst += range(i * Tmax + Tmax - sl[i] - 1, i * Tmax + Tmax - 1)
+    order = ("text", "global", "semantic")
+    arrays = [np.asarray(src[k], dtype=np.int64) for k in order] + [np.asarray(dst[k], dtype=np.int64) for k in ("tag",) + order] \
+        + [np.asarray(lab_dst, dtype=np.int64), np.asarray([i * Tmax + Tmax - 1 for i in range(B)], dtype=np.int64), mask.reshape(-1)]
+    cuts = np.cumsum([0] + [len(a) for a in arrays])
+    packed = torch.from_numpy(np.concatenate(arrays))
+    packed = packed.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else packed.to(device)
+    part = [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
+    s_text, s_glob, s_sem, d_tag, d_text, d_glob, d_sem, d_lab, d_eos, m_flat = part
+    tok = {"text": ids_t.to(device).reshape(-1)[s_text], "global": ids_g.to(device).reshape(-1)[s_glob],
+           "semantic": ids_s.to(device).reshape(-1)[s_sem]}
+    tables = {"text": model.text_embedder, "global": model.global_embedder, "semantic": model.model.embeddings}
+    tag = model.tts_tag_embedder(torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(B))
+    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=device).index_copy(0, d_tag, tag)
+    for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
+        if tok[k].numel():
+            out = out.index_copy(0, d_k, tables[k](tok[k]))
+    labels = torch.full((B * Tmax,), -100, dtype=torch.long, device=device)
+    labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
+    labels.index_fill_(0, d_eos, eos_token_id)
+    return {"input_embs": out.view(B, Tmax, -1), "attention_mask": m_flat.view(B, Tmax), "labels": labels.view(B, Tmax)}

@@ -82,3 +82,58 @@ def test_embedding_tables_receive_gradients():
     assert torch.allclose(model.model.embeddings.weight.grad, ref_grad, atol=1e-6)
     for emb in (model.text_embedder, model.global_embedder, model.tts_tag_embedder):
         assert emb.weight.grad is not None and float(emb.weight.grad.abs().sum()) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# process_single_batch (data/utils/spark_dataset.py:165-239): the reference module imports `datasets` and its inference
+# package at the top, so the function's own source is extracted with ast and executed on its own (it only needs torch)
+# ---------------------------------------------------------------------------------------------------------------
+REF2 = "/root/reference/data/utils/spark_dataset.py"
+GOLD2 = os.path.join(ROOT, "tests", "golden", "process_single_batch.pt")
+
+
+def _reference_process_single_batch():
+    if not os.path.exists(REF2):
+        return None
+    import ast
+    src = open(REF2).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "process_single_batch"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF2, "exec"), ns)
+    return ns["process_single_batch"]
+
+
+def _padded_batch():
+    g = torch.Generator().manual_seed(5)
+    B, Lt, Lg, Ls = 4, 12, 6, 20
+    tl, gl, sl = [12, 3, 7, 1], [6, 6, 2, 4], [20, 5, 11, 1]
+    def left(L, lens, hi):
+        ids = torch.randint(0, hi, (B, L), generator=g)
+        m = torch.zeros(B, L, dtype=torch.long)
+        for i, n in enumerate(lens):
+            m[i, L - n:] = 1
+        return ids * m, m
+    it, mt = left(Lt, tl, 500)
+    ig, mg = left(Lg, gl, 64)
+    is_, ms = left(Ls, sl, 128)
+    return {"input_ids": it, "attention_mask_input_ids": mt, "global_tokens_ids": ig, "global_tokens_attention_mask": mg,
+            "semantic_tokens_ids": is_, "semantic_tokens_attention_mask": ms}
+
+
+def test_process_single_batch_matches_reference_and_golden():
+    from rwkvtts_b200.batch import process_single_batch
+    model = make_model(seed=7)
+    model.device = torch.device("cpu")
+    batch = _padded_batch()
+    got = process_single_batch(batch, model, eos_token_id=129)
+    ref_fn = _reference_process_single_batch()
+    if ref_fn is not None:
+        ref = ref_fn(batch, model, eos_token_id=129)
+        if not os.path.exists(GOLD2):
+            torch.save({k: v.detach() for k, v in ref.items()}, GOLD2)
+    else:
+        ref = torch.load(GOLD2)
+    for k in ("input_embs", "attention_mask", "labels"):
+        assert torch.equal(got[k], ref[k].to(got[k].dtype)), k
+    gold = torch.load(GOLD2)
+    assert torch.equal(got["labels"], gold["labels"]) and torch.equal(got["input_embs"].detach(), gold["input_embs"])
