@@ -131,3 +131,50 @@ def process_single_batch(batch: Dict[str, torch.Tensor], rwkv7speech_model, eos_
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)
     return {"input_embs": out.view(B, Tmax, -1), "attention_mask": m_flat.view(B, Tmax), "labels": labels.view(B, Tmax)}
+
+
+def create_inputs(texts, global_tokens_ids, semantic_tokens_ids, tokenizer, llm, pad_token_id: int = 0):
+    """Same signature and result as the reference's create_inputs (/root/reference/inference/rwkv7speech_inference.py:
+    35-67), the prompt builder of the AR decode loop and of collate_fn_for_rwkv7speech: LEFT-padded
+    [tag2, text, tag0, global, tag1, semantic] embeddings [B, Tmax, D] and their attention mask [B, Tmax].  One host ->
+    device copy of the index arrays, one lookup + one scatter per embedding table (the reference: 6 lookups, 2 cats and 6
+    small copies per sample)."""
+    assert len(texts) == len(global_tokens_ids) == len(semantic_tokens_ids), \
+        f"input lists differ in length: texts({len(texts)}), global_tokens_ids({len(global_tokens_ids)}), " \
+        f"semantic_tokens_ids({len(semantic_tokens_ids)})"
+    device = llm.device
+    B = len(texts)
+    text_ids = [tokenizer.encode(t) for t in texts]
+    total = [len(text_ids[i]) + len(global_tokens_ids[i]) + len(semantic_tokens_ids[i]) + 3 for i in range(B)]
+    Tmax = max(total)
+    ids = {k: [] for k in ("tag", "text", "global", "semantic")}
+    dst = {k: [] for k in ("tag", "text", "global", "semantic")}
+    mask = np.zeros((B, Tmax), dtype=np.int64)
+    for i in range(B):
+        pad = Tmax - total[i]
+        base = i * Tmax + pad
+        mask[i, pad:] = 1
+        nt, ng, ns = len(text_ids[i]), len(global_tokens_ids[i]), len(semantic_tokens_ids[i])
+        p_tag0 = 1 + nt
+        p_tag1 = p_tag0 + 1 + ng
+        ids["tag"] += [2, 0, 1]
+        dst["tag"] += [base, base + p_tag0, base + p_tag1]
+        for k, seq, n, p in (("text", text_ids[i], nt, 1), ("global", global_tokens_ids[i], ng, p_tag0 + 1),
+                             ("semantic", semantic_tokens_ids[i], ns, p_tag1 + 1)):
+            ids[k] += list(seq)
+            dst[k] += range(base + p, base + p + n)
+    order = ("tag", "text", "global", "semantic")
+    arrays = [np.asarray(ids[k], dtype=np.int64) for k in order] + [np.asarray(dst[k], dtype=np.int64) for k in order] \
+        + [mask.reshape(-1)]
+    cuts = np.cumsum([0] + [len(a) for a in arrays])
+    packed = torch.from_numpy(np.concatenate(arrays))
+    packed = packed.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else packed.to(device)
+    part = [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
+    tables = {"tag": llm.tts_tag_embedder, "text": llm.text_embedder, "global": llm.global_embedder,
+              "semantic": llm.model.embeddings}
+    tag = tables["tag"](part[0])
+    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=tag.device).index_copy(0, part[4], tag)
+    for j, k in enumerate(order[1:], start=1):
+        if len(ids[k]):
+            out = out.index_copy(0, part[4 + j], tables[k](part[j]))
+    return out.view(B, Tmax, -1), part[8].view(B, Tmax)

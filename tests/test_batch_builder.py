@@ -137,3 +137,40 @@ def test_process_single_batch_matches_reference_and_golden():
         assert torch.equal(got[k], ref[k].to(got[k].dtype)), k
     gold = torch.load(GOLD2)
     assert torch.equal(got["labels"], gold["labels"]) and torch.equal(got["input_embs"].detach(), gold["input_embs"])
+
+
+REF3 = "/root/reference/inference/rwkv7speech_inference.py"
+GOLD3 = os.path.join(ROOT, "tests", "golden", "create_inputs.pt")
+
+
+def _reference_create_inputs():
+    if not os.path.exists(REF3):
+        return None
+    import ast
+    from typing import List
+    src = open(REF3).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "create_inputs"][0]
+    ns = {"torch": torch, "List": List}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF3, "exec"), ns)
+    return ns["create_inputs"]
+
+
+def test_create_inputs_matches_reference_and_golden():
+    """inference/rwkv7speech_inference.py:35-67, including the empty semantic prompt the decode loop starts from (:95)"""
+    from rwkvtts_b200.batch import create_inputs
+    model = make_model(seed=11)
+    model.device = torch.device("cpu")
+    b = make_batch()
+    sem = [b["semantic_tokens"][0], [], b["semantic_tokens"][2]]
+    got_e, got_m = create_inputs(b["text"], b["global_tokens"], sem, Tok(), model)
+    ref_fn = _reference_create_inputs()
+    if ref_fn is not None:
+        ref_e, ref_m = ref_fn(b["text"], b["global_tokens"], sem, Tok(), model)
+        if not os.path.exists(GOLD3):
+            torch.save({"embs": ref_e.detach(), "mask": ref_m}, GOLD3)
+    else:
+        g_ = torch.load(GOLD3)
+        ref_e, ref_m = g_["embs"], g_["mask"]
+    assert torch.equal(got_e, ref_e.to(got_e.dtype)) and torch.equal(got_m, ref_m)
+    gold = torch.load(GOLD3)
+    assert torch.equal(got_e.detach(), gold["embs"].to(got_e.dtype))
