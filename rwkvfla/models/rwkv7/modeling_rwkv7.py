@@ -121,6 +121,29 @@ class RWKV7PreTrainedModel(PreTrainedModel):
             nn.init.normal_(module.weight, mean=0.0, std=self.config.initializer_range)
 
 
+def unpack_varlen(x: torch.Tensor, cu_seqlens: torch.Tensor):
+    """Packed varlen batch [1, total, D] + cu_seqlens [N+1] (rwkvfla's `cu_seqlens` convention, produced by the reference's
+    `*_culens` collators, utils/multiple_jsonl.py:78-135) -> RIGHT-padded [N, Tmax, D] and the flat row index of every packed
+    token.  The recurrence, both token shifts and the norms are causal and per sequence, so the padded tail never
+    influences a real position and no mask is needed; every sequence starts from a zero state, which is exactly what
+    `cu_seqlens` means.  One host read of cu_seqlens (rwkvfla's own chunk index preparation does the same)."""
+    if x.shape[0] != 1:
+        raise ValueError("cu_seqlens expects a packed batch of size 1")
+    cu = [int(v) for v in cu_seqlens.tolist()]
+    lens = [b - a for a, b in zip(cu[:-1], cu[1:])]
+    if cu[0] != 0 or cu[-1] != x.shape[1] or min(lens) <= 0:
+        raise ValueError(f"cu_seqlens {cu} does not partition a packed sequence of length {x.shape[1]}")
+    n, tmax = len(lens), max(lens)
+    idx = torch.cat([torch.arange(i * tmax, i * tmax + l) for i, l in enumerate(lens)]).to(x.device)
+    padded = x.new_zeros(n * tmax, x.shape[-1]).index_copy(0, idx, x[0])
+    return padded.view(n, tmax, -1), idx
+
+
+def repack_varlen(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """[N, Tmax, D] -> packed [1, total, D] (inverse of unpack_varlen)."""
+    return x.reshape(-1, x.shape[-1]).index_select(0, idx).unsqueeze(0)
+
+
 class RWKV7Model(RWKV7PreTrainedModel):
     def __init__(self, config: RWKV7Config):
         super().__init__(config)
@@ -157,6 +180,14 @@ class RWKV7Model(RWKV7PreTrainedModel):
         if inputs_embeds is None:
             inputs_embeds = self.embeddings(input_ids)
         hidden_states = inputs_embeds
+        packed_idx = None
+        if cu_seqlens is not None:
+            # packed varlen input: run it as the equivalent right-padded batch (see unpack_varlen)
+            if attention_mask is not None or (past_key_values is not None and len(past_key_values) > 0):
+                raise NotImplementedError("cu_seqlens together with attention_mask / a filled cache")
+            use_cache = False                  # a packed batch carries no per-sequence state out
+            hidden_states, packed_idx = unpack_varlen(hidden_states, cu_seqlens)
+            cu_seqlens = None
         if use_cache and not isinstance(past_key_values, Cache):
             past_key_values = Cache.from_legacy_cache(past_key_values)
         all_hidden_states = () if output_hidden_states else None
@@ -173,6 +204,10 @@ class RWKV7Model(RWKV7PreTrainedModel):
                     hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
                     use_cache=use_cache, output_attentions=False, v_first=v_first, cu_seqlens=cu_seqlens)
         hidden_states = self.norm(hidden_states)
+        if packed_idx is not None:
+            hidden_states = repack_varlen(hidden_states, packed_idx)
+            if output_hidden_states:
+                all_hidden_states = tuple(repack_varlen(h, packed_idx) for h in all_hidden_states)
         if output_hidden_states:
             all_hidden_states += (hidden_states,)
         if not return_dict:

@@ -96,3 +96,41 @@ def test_layernorm_prenorm_form():
     x, r = torch.randn(2, 3, 8), torch.randn(2, 3, 8)
     y, res = ln(x, r, True)
     assert torch.allclose(res, x + r) and torch.allclose(y, torch.nn.functional.layer_norm(x + r, (8,), ln.weight, ln.bias))
+
+
+def test_cu_seqlens_packed_input_runs_as_the_equivalent_padded_batch(monkeypatch):
+    """RWKV7Model.forward(cu_seqlens=...) (what the reference's *_culens collators feed, utils/multiple_jsonl.py:78-135):
+    packed [1, total, D] must give, per sequence, what the sequence gives on its own.  The blocks are replaced by a
+    causal stand-in (running mean over time) so that the wiring is checked on CPU; the real blocks see an ordinary
+    right-padded batch."""
+    import torch
+    from rwkvfla.models.rwkv7 import RWKV7Config, RWKV7Model
+    from rwkvfla.models.rwkv7 import modeling_rwkv7 as M
+
+    def fake_block(self, hidden_states, attention_mask=None, past_key_values=None, use_cache=False,
+                   output_attentions=False, v_first=None, cu_seqlens=None, **kw):
+        assert cu_seqlens is None and attention_mask is None
+        t = torch.arange(1, hidden_states.shape[1] + 1, dtype=hidden_states.dtype).view(1, -1, 1)
+        return hidden_states.cumsum(1) / t + 0.1 * (self.layer_idx + 1), None, past_key_values, v_first
+
+    monkeypatch.setattr(M.RWKV7Block, "forward", fake_block)
+    torch.manual_seed(0)
+    cfg = RWKV7Config(hidden_size=64, num_hidden_layers=2, vocab_size=50, decay_low_rank_dim=32, a_low_rank_dim=32,
+                      v_low_rank_dim=32, gate_low_rank_dim=32)
+    m = RWKV7Model(cfg).eval()
+    lens = [5, 1, 9, 3]
+    cu = torch.tensor([0, 5, 6, 15, 18])
+    x = torch.randn(1, 18, 64, requires_grad=True)
+    out = m(inputs_embeds=x, cu_seqlens=cu, output_hidden_states=True)
+    assert out.last_hidden_state.shape == (1, 18, 64) and all(h.shape == (1, 18, 64) for h in out.hidden_states)
+    for a, b in zip(cu[:-1].tolist(), cu[1:].tolist()):
+        single = m(inputs_embeds=x[:, a:b]).last_hidden_state
+        assert torch.allclose(out.last_hidden_state[:, a:b], single, atol=1e-6)
+    out.last_hidden_state.sum().backward()
+    assert x.grad is not None and bool(torch.isfinite(x.grad).all())
+    # helpers are inverse of each other and reject a cu_seqlens that does not partition the sequence
+    padded, idx = M.unpack_varlen(x.detach(), cu)
+    assert padded.shape == (4, 9, 64) and torch.equal(M.repack_varlen(padded, idx), x.detach())
+    import pytest
+    with pytest.raises(ValueError):
+        M.unpack_varlen(x.detach(), torch.tensor([0, 5, 17]))
