@@ -178,3 +178,46 @@ def create_inputs(texts, global_tokens_ids, semantic_tokens_ids, tokenizer, llm,
         if len(ids[k]):
             out = out.index_copy(0, part[4 + j], tables[k](part[j]))
     return out.view(B, Tmax, -1), part[8].view(B, Tmax)
+
+
+def create_inputs_and_labels_culens(batch: Dict[str, Any], tokenizer, model, eos_token_id: int, device) -> Dict[str, torch.Tensor]:
+    """Packed-varlen variant (/root/reference/utils/multiple_jsonl.py:77-135): the samples of
+    create_inputs_and_labels back to back as one sequence, `input_embs` [1, total, D], `labels` [1, total] and
+    `cu_seqlens` [B+1].  Same host-side layout pass; the destination rows are simply consecutive."""
+    texts, glob, sem = batch["text"], batch["global_tokens"], batch["semantic_tokens"]
+    text_ids = [tokenizer.encode(t, add_special_tokens=False) for t in texts]
+    B = len(texts)
+    order = ("tag", "text", "global", "semantic")
+    ids = {k: [] for k in order}
+    dst = {k: [] for k in order}
+    labels, cu = [], [0]
+    for i in range(B):
+        base, nt, ng = cu[-1], len(text_ids[i]), len(glob[i])
+        sem_ids = list(sem[i]) + [eos_token_id]
+        p_tag0 = 1 + nt
+        p_tag1 = p_tag0 + 1 + ng
+        p_sem = p_tag1 + 1
+        ids["tag"] += [2, 0, 1]
+        dst["tag"] += [base, base + p_tag0, base + p_tag1]
+        ids["text"] += text_ids[i]
+        dst["text"] += range(base + 1, base + 1 + nt)
+        ids["global"] += list(glob[i])
+        dst["global"] += range(base + p_tag0 + 1, base + p_tag0 + 1 + ng)
+        ids["semantic"] += sem_ids
+        dst["semantic"] += range(base + p_sem, base + p_sem + len(sem_ids))
+        labels += [-100] * p_sem + sem_ids
+        cu.append(base + p_sem + len(sem_ids))
+    arrays = [np.asarray(ids[k], dtype=np.int64) for k in order] + [np.asarray(dst[k], dtype=np.int64) for k in order] \
+        + [np.asarray(labels, dtype=np.int64), np.asarray(cu, dtype=np.int64)]
+    cuts = np.cumsum([0] + [len(a) for a in arrays])
+    packed = torch.from_numpy(np.concatenate(arrays))
+    packed = packed.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else packed.to(device)
+    part = [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
+    tables = {"tag": model.tts_tag_embedder, "text": model.text_embedder, "global": model.global_embedder,
+              "semantic": model.model.embeddings}
+    first = tables["semantic"](part[3])
+    out = torch.zeros(cu[-1], first.shape[-1], dtype=first.dtype, device=first.device)
+    for j, k in enumerate(order):
+        if len(ids[k]):
+            out = out.index_copy(0, part[4 + j], first if k == "semantic" else tables[k](part[j]))
+    return {"input_embs": out.unsqueeze(0), "labels": part[8].unsqueeze(0), "cu_seqlens": part[9]}

@@ -174,3 +174,29 @@ def test_create_inputs_matches_reference_and_golden():
     assert torch.equal(got_e, ref_e.to(got_e.dtype)) and torch.equal(got_m, ref_m)
     gold = torch.load(GOLD3)
     assert torch.equal(got_e.detach(), gold["embs"].to(got_e.dtype))
+
+
+def test_culens_builder_matches_reference_and_feeds_unpack_varlen():
+    from rwkvtts_b200.batch import create_inputs_and_labels, create_inputs_and_labels_culens
+    model, batch = make_model(seed=13), make_batch()
+    got = create_inputs_and_labels_culens(batch, Tok(), model, 128, "cpu")
+    if os.path.exists(REF):
+        import importlib
+        _reference_fn()                                   # loads utils.multiple_jsonl
+        ref = sys.modules["utils.multiple_jsonl"] if "utils.multiple_jsonl" in sys.modules else None
+        spec = importlib.util.spec_from_file_location("utils.multiple_jsonl", REF)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        r = mod.create_inputs_and_labels_culens(batch, Tok(), model, 128, "cpu")
+        for k in ("input_embs", "labels", "cu_seqlens"):
+            assert torch.equal(got[k], r[k]), k
+    # consistency with the padded builder (which is pinned to the reference and its golden) through the model's own
+    # varlen unpacking: sample i of the padded batch == rows cu[i]:cu[i+1] of the packed one
+    from rwkvfla.models.rwkv7.modeling_rwkv7 import unpack_varlen
+    pad = create_inputs_and_labels(batch, Tok(), model, 128, "cpu")
+    padded, _ = unpack_varlen(got["input_embs"], got["cu_seqlens"])
+    assert torch.equal(padded, pad["input_embs"])
+    cu = got["cu_seqlens"].tolist()
+    for i, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
+        assert torch.equal(got["labels"][0, a:b], pad["labels"][i, :b - a])
+        assert int(pad["attention_mask"][i].sum()) == b - a
