@@ -17,7 +17,7 @@ m = bench.dist_max(10.0 + r, w)
 bench.dist_barrier(w)
 import torch.distributed as dist
 assert dist.get_world_size() == w
-print("rank", r, "max", m, flush=True)
+sys.stdout.write(f"rank {r} max {m}\n"); sys.stdout.flush()     # one write per rank: lines do not interleave
 dist.destroy_process_group()
 """
 
@@ -39,3 +39,27 @@ def test_bench_single_process_helpers_are_noops():
     import bench
     bench.dist_init(1)
     assert bench.dist_max(3.5, 1) == 3.5
+
+
+def test_reference_arm_line_has_the_contract_keys(capsys):
+    """`bench.py --impl reference`: the reference algorithm (C port of the reference kernels) on the host cores, bounded
+    sample; the line carries the contract keys (impl, metric, value, unit, cpu_baseline{kind, cores, sample}, e2e{...})."""
+    import json
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    cb = bench.cpu_reference(seconds_target=0.5)
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "T=4096" in cb["sample"]
+    orig = bench.cpu_reference
+    bench.cpu_reference = lambda seconds_target=20.0: cb          # keep the test short: reuse the measured sample
+    try:
+        bench.run_reference(types.SimpleNamespace(gpus=2, steps=2, warmup=1), rank=1)     # other ranks: no work, no line
+        assert capsys.readouterr().out == ""
+        bench.run_reference(types.SimpleNamespace(gpus=2, steps=2, warmup=1), rank=0)
+    finally:
+        bench.cpu_reference = orig
+    line = json.loads(capsys.readouterr().out)
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "tokens/s"
+    assert line["higher_is_better"] is True and line["value"] == line["cpu_baseline"]["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"] == bench.WORKLOAD and line["n_gpus"] == 2
