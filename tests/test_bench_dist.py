@@ -17,7 +17,7 @@ m = bench.dist_max(10.0 + r, w)
 bench.dist_barrier(w)
 import torch.distributed as dist
 assert dist.get_world_size() == w
-sys.stdout.write(f"rank {r} max {m}\n"); sys.stdout.flush()     # one write per rank: lines do not interleave
+sys.stdout.write("rank %d max %s\n" % (r, m)); sys.stdout.flush()     # one write per rank: lines do not interleave
 dist.destroy_process_group()
 """
 
