@@ -221,3 +221,168 @@ def create_inputs_and_labels_culens(batch: Dict[str, Any], tokenizer, model, eos
         if len(ids[k]):
             out = out.index_copy(0, part[4 + j], first if k == "semantic" else tables[k](part[j]))
     return {"input_embs": out.unsqueeze(0), "labels": part[8].unsqueeze(0), "cu_seqlens": part[9]}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Generic row assembler for the remaining layouts: a row is a list of segments (table, ids, predict); the embedding
+# of segment ids comes from `table`, and the label of each position is its id when `predict` else -100.
+# ---------------------------------------------------------------------------------------------------------------
+_ORDER = ("tag", "text", "global", "semantic")
+
+
+def _tables(model):
+    return {"tag": model.tts_tag_embedder, "text": model.text_embedder, "global": model.global_embedder,
+            "semantic": model.model.embeddings}
+
+
+def _to_device(arrays, device):
+    arrays = [np.asarray(a, dtype=np.int64).reshape(-1) for a in arrays]
+    cuts = np.cumsum([0] + [a.size for a in arrays])
+    packed = torch.from_numpy(np.concatenate(arrays))
+    packed = packed.pin_memory().to(device, non_blocking=True) if torch.device(device).type == "cuda" else packed.to(device)
+    return [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
+
+
+def _assemble_rows(rows, model, device, packed: bool):
+    """rows -> (embeddings, labels, mask-or-cu_seqlens).  Padded ([R, Tmax, D], right padding, labels -100 / embeddings
+    0.0 outside the row) or packed ([1, total, D] with cu_seqlens [R+1]).  One host pass, one host -> device copy, one
+    lookup + one scatter per embedding table."""
+    R = len(rows)
+    lens = [sum(len(s[1]) for s in row) for row in rows]
+    if packed:
+        starts = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        total = int(starts[-1])
+    else:
+        Tmax = max(lens)
+        starts = np.arange(R, dtype=np.int64) * Tmax
+        total = R * Tmax
+    ids = {k: [] for k in _ORDER}
+    dst = {k: [] for k in _ORDER}
+    labels = np.full(total, -100, dtype=np.int64)
+    for r, row in enumerate(rows):
+        p = int(starts[r])
+        for table, seg, predict in row:
+            n = len(seg)
+            ids[table] += list(seg)
+            dst[table] += range(p, p + n)
+            if predict and n:
+                labels[p:p + n] = seg
+            p += n
+    if packed:
+        tail = starts
+    else:
+        tail = (np.arange(Tmax)[None, :] < np.asarray(lens)[:, None]).astype(np.int64)
+    part = _to_device([ids[k] for k in _ORDER] + [dst[k] for k in _ORDER] + [labels, tail], device)
+    tables = _tables(model)
+    out = None
+    for j, k in enumerate(_ORDER):
+        if not len(ids[k]):
+            continue
+        emb = tables[k](part[j])
+        if out is None:
+            out = torch.zeros(total, emb.shape[-1], dtype=emb.dtype, device=emb.device)
+        out = out.index_copy(0, part[4 + j], emb)
+    if packed:
+        return out.unsqueeze(0), part[8].unsqueeze(0), part[9]
+    return out.view(R, Tmax, -1), part[8].view(R, Tmax), part[9].view(R, Tmax)
+
+
+def _properties_tokens(batch, i, tokenizer):
+    from .properties import convert_properties_to_tokens
+    s = convert_properties_to_tokens(batch["age"][i], batch["gender"][i], batch["emotion"][i], batch["pitch"][i], batch["speed"][i])
+    return tokenizer.encode(s, add_special_tokens=False)
+
+
+def _property_rows(batch, tokenizer, eos_token_id, plain: bool, predict_semantic: bool):
+    """Rows of the controllable-TTS layouts (/root/reference/utils/multiple_jsonl.py:139-233, :313-400): per sample an
+    optional plain row [tag2, text, tag0, global, tag1, semantic+eos] predicting the semantic ids, then the row with the
+    property tokens (text table) in front, predicting the global ids and, optionally, the semantic ids."""
+    rows = []
+    for i, text in enumerate(batch["text"]):
+        t = tokenizer.encode(text, add_special_tokens=False)
+        g = list(batch["global_tokens"][i])
+        s = list(batch["semantic_tokens"][i]) + [eos_token_id]
+        if plain:
+            rows.append([("tag", [2], False), ("text", t, False), ("tag", [0], False), ("global", g, False),
+                         ("tag", [1], False), ("semantic", s, True)])
+        rows.append([("text", _properties_tokens(batch, i, tokenizer), False), ("tag", [2], False), ("text", t, False),
+                     ("tag", [0], False), ("global", g, True), ("tag", [1], False), ("semantic", s, predict_semantic)])
+    return rows
+
+
+def _padded(rows, model, device):
+    e, l, m = _assemble_rows(rows, model, device, packed=False)
+    return {"input_embs": e, "labels": l, "attention_mask": m}
+
+
+def _packed(rows, model, device):
+    e, l, cu = _assemble_rows(rows, model, device, packed=True)
+    return {"input_embs": e, "labels": l, "cu_seqlens": cu}
+
+
+def create_inputs_and_labels_with_properties(batch, tokenizer, model, eos_token_id, device):
+    """/root/reference/utils/multiple_jsonl.py:139-233: 2 rows per sample (plain, then with properties)."""
+    return _padded(_property_rows(batch, tokenizer, eos_token_id, plain=True, predict_semantic=True), model, device)
+
+
+def create_inputs_and_labels_with_properties_culens(batch, tokenizer, model, eos_token_id, device):
+    """/root/reference/utils/multiple_jsonl.py:236-311: the same rows packed back to back."""
+    return _packed(_property_rows(batch, tokenizer, eos_token_id, plain=True, predict_semantic=True), model, device)
+
+
+def create_inputs_and_labels_with_properties_global_tokens(batch, tokenizer, model, eos_token_id, device):
+    """/root/reference/utils/multiple_jsonl.py:313-400: only the row with properties, only the global ids predicted."""
+    return _padded(_property_rows(batch, tokenizer, eos_token_id, plain=False, predict_semantic=False), model, device)
+
+
+def create_inputs_and_labels_with_properties_global_tokens_culens(batch, tokenizer, model, eos_token_id, device):
+    """/root/reference/utils/multiple_jsonl.py:403-476."""
+    return _packed(_property_rows(batch, tokenizer, eos_token_id, plain=False, predict_semantic=False), model, device)
+
+
+def process_single_batch_culens(batch, rwkv7speech_model, eos_token_id: int = 8192, max_cu_seqlens: int = 8192):
+    """/root/reference/data/utils/spark_dataset.py:111-162: the packed form of process_single_batch, cut at
+    `max_cu_seqlens` tokens.  As in the reference (:153-156) the sample that crosses the limit is still part of
+    `input_embs` / `labels` but gets no entry in `cu_seqlens`, and nothing after it is read."""
+    model = rwkv7speech_model
+    device = model.device
+    ids_t, ids_g, ids_s = batch["input_ids"], batch["global_tokens_ids"], batch["semantic_tokens_ids"]
+    B = ids_t.shape[0]
+    lens = torch.stack([batch["attention_mask_input_ids"].sum(1), batch["global_tokens_attention_mask"].sum(1),
+                        batch["semantic_tokens_attention_mask"].sum(1)]).tolist()          # the only host sync
+    tl, gl, sl = ([int(v) for v in row] for row in lens)
+    src = {k: [] for k in ("text", "global", "semantic")}
+    dst = {k: [] for k in _ORDER}
+    lab_dst, eos_dst, cu = [], [], [0]
+    base = 0
+    for i in range(B):
+        n_i = tl[i] + gl[i] + sl[i] + 3
+        p_tag0 = 1 + tl[i]
+        p_tag1 = p_tag0 + 1 + gl[i]
+        dst["tag"] += [base, base + p_tag0, base + p_tag1]
+        for k, ids, n, p in (("text", ids_t, tl[i], 1), ("global", ids_g, gl[i], p_tag0 + 1), ("semantic", ids_s, sl[i], p_tag1 + 1)):
+            L = ids.shape[1]
+            src[k] += range(i * L + L - n, i * L + L)
+            dst[k] += range(base + p, base + p + n)
+        lab_dst += range(base + n_i - sl[i] - 1, base + n_i - 1)
+        eos_dst.append(base + n_i - 1)
+        base += n_i
+        if cu[-1] + n_i > max_cu_seqlens:
+            break
+        cu.append(cu[-1] + n_i)
+    n_rows = len(eos_dst)
+    order = ("text", "global", "semantic")
+    part = _to_device([src[k] for k in order] + [dst[k] for k in _ORDER] + [lab_dst, eos_dst, cu], device)
+    s_text, s_glob, s_sem, d_tag, d_text, d_glob, d_sem, d_lab, d_eos, cu_t = part
+    tok = {"text": ids_t.to(device).reshape(-1)[s_text], "global": ids_g.to(device).reshape(-1)[s_glob],
+           "semantic": ids_s.to(device).reshape(-1)[s_sem]}
+    tables = _tables(model)
+    tag = tables["tag"](torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(n_rows))
+    out = torch.zeros(base, tag.shape[-1], dtype=tag.dtype, device=device).index_copy(0, d_tag, tag)
+    for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
+        if tok[k].numel():
+            out = out.index_copy(0, d_k, tables[k](tok[k]))
+    labels = torch.full((base,), -100, dtype=torch.long, device=device)
+    labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
+    labels.index_fill_(0, d_eos, eos_token_id)
+    return {"input_embs": out.unsqueeze(0), "labels": labels.unsqueeze(0), "cu_seqlens": cu_t}

@@ -200,3 +200,142 @@ def test_culens_builder_matches_reference_and_feeds_unpack_varlen():
     for i, (a, b) in enumerate(zip(cu[:-1], cu[1:])):
         assert torch.equal(got["labels"][0, a:b], pad["labels"][i, :b - a])
         assert int(pad["attention_mask"][i].sum()) == b - a
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# controllable-TTS layouts (utils/multiple_jsonl.py:139-476) and the property tokens (utils/properties_util.py)
+# ---------------------------------------------------------------------------------------------------------------
+REF4 = "/root/reference/utils/properties_util.py"
+GOLD4 = os.path.join(ROOT, "tests", "golden", "properties_tokens.json")
+GOLD5 = os.path.join(ROOT, "tests", "golden", "batch_builder_properties.pt")
+
+
+def _property_grid():
+    ages = ["child", "teenager", "youth-adult", "middle-aged", "elderly", "Elderly"]
+    genders = ["female", "male", "Male"]
+    emotions = ["NEUTRAL", "happy", "NO-AGREEMENT", "CONTEMPT"]
+    pitches = [0.0, 109.9, 110, 114, 115, 121, 125, 128, 130, 131, 142, 143, 147, 151, 153, 166, 170, 176, 187, 189.99, 190,
+               191, 195, 208, 209, 211, 213, 215, 232, 238, 249.99, 250, 270, 289, 290, 400.5]
+    speeds = [0.0, 3.5, 3.51, 3.99, 4.0, 4.01, 4.5, 4.51, 5.0, 5.01, 9.0]
+    for a in ages:
+        for g in genders:
+            for e in emotions:
+                for p in pitches:
+                    for s in (speeds if e == "NEUTRAL" else speeds[3:6]):
+                        yield a, g, e, p, s
+
+
+def _load_reference_properties():
+    if not os.path.exists(REF4):
+        return None
+    spec = importlib.util.spec_from_file_location("_ref_properties_util", REF4)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_property_tokens_match_reference_and_golden():
+    import hashlib
+    import json
+    from rwkvtts_b200 import properties as P
+    grid = list(_property_grid())
+    got = [P.convert_properties_to_tokens(*x) for x in grid]
+    ref = _load_reference_properties()
+    if ref is not None:
+        assert got == [ref.convert_properties_to_tokens(*x) for x in grid]
+        for g in ("female", "male", "unknown", "other"):
+            for a in ("child", "teenager", "youth-adult", "middle-aged", "elderly", "n/a"):
+                for p in (0, 100, 113.9, 114, 129.9, 130, 150, 179.9, 180, 219.9, 220, 251, 300):
+                    assert P.classify_pitch(p, g, a) == ref.classify_pitch(p, g, a), (p, g, a)
+        assert P.convert_standard_properties_to_tokens("child", "FEMALE", "sad", "HIGH_PITCH", "Fast") == \
+            ref.convert_standard_properties_to_tokens("child", "FEMALE", "sad", "HIGH_PITCH", "Fast")
+        for name in ("SPEED_MAP", "PITCH_MAP", "AGE_MAP", "GENDER_MAP", "EMOTION_MAP"):
+            assert getattr(P, name) == getattr(ref, name), name
+        if not os.path.exists(GOLD4):
+            json.dump({"n": len(grid), "sha256": hashlib.sha256("\n".join(got).encode()).hexdigest(),
+                       "first": got[:5], "speed_4.0": P.classify_speed(4.0)}, open(GOLD4, "w"), indent=1)
+    gold = json.load(open(GOLD4))
+    assert gold["n"] == len(got) and gold["sha256"] == hashlib.sha256("\n".join(got).encode()).hexdigest()
+    assert got[:5] == gold["first"] and P.classify_speed(4.0) == gold["speed_4.0"] == "very_fast"
+    # error behaviour of the reference: unknown categories raise KeyError (the second GENDER_MAP has no "unknown")
+    for bad in (("adult", "male", "SAD", 100.0, 4.2), ("child", "unknown", "SAD", 100.0, 4.2), ("child", "male", "BORED", 100.0, 4.2)):
+        with pytest.raises(KeyError):
+            P.convert_properties_to_tokens(*bad)
+
+
+def _property_batch():
+    b = make_batch()
+    b.update({"age": ["child", "elderly", "youth-adult"], "gender": ["female", "male", "male"],
+              "emotion": ["HAPPY", "sad", "NEUTRAL"], "pitch": [251.0, 120.5, 131.0], "speed": [4.0, 3.2, 4.7]})
+    return b
+
+
+PROP_FNS = ("create_inputs_and_labels_with_properties", "create_inputs_and_labels_with_properties_culens",
+            "create_inputs_and_labels_with_properties_global_tokens", "create_inputs_and_labels_with_properties_global_tokens_culens")
+
+
+def test_property_builders_match_reference_and_golden(capsys):
+    import rwkvtts_b200.batch as mine
+    model, batch = make_model(seed=17), _property_batch()
+    got = {n: getattr(mine, n)(batch, Tok(), model, 128, "cpu") for n in PROP_FNS}
+    if os.path.exists(REF):
+        _reference_fn()
+        spec = importlib.util.spec_from_file_location("utils.multiple_jsonl", REF)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        ref = {n: getattr(mod, n)(batch, Tok(), model, 128, "cpu") for n in PROP_FNS}
+        capsys.readouterr()                          # the reference prints its first property string once
+        if not os.path.exists(GOLD5):
+            torch.save({n: {k: v.detach() for k, v in d.items()} for n, d in ref.items()}, GOLD5)
+    else:
+        ref = torch.load(GOLD5)
+    gold = torch.load(GOLD5)
+    for n in PROP_FNS:
+        assert set(got[n]) == set(ref[n]) == set(gold[n])
+        for k in got[n]:
+            assert torch.equal(got[n][k], ref[n][k].to(got[n][k].dtype)), (n, k)
+            assert torch.equal(got[n][k].detach(), gold[n][k].to(got[n][k].dtype)), (n, k)
+    # 2 rows per sample (plain, with properties); the global-token variant has 1 and predicts no semantic id
+    assert got[PROP_FNS[0]]["input_embs"].shape[0] == 6 and got[PROP_FNS[2]]["input_embs"].shape[0] == 3
+    assert got[PROP_FNS[1]]["cu_seqlens"].numel() == 7 and got[PROP_FNS[3]]["cu_seqlens"].numel() == 4
+    lab = got[PROP_FNS[2]]["labels"]
+    assert int((lab >= 0).sum()) == sum(len(g) for g in batch["global_tokens"])
+
+
+def _reference_process_single_batch_culens():
+    if not os.path.exists(REF2):
+        return None
+    import ast
+    src = open(REF2).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "process_single_batch_culens"][0]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF2, "exec"), ns)
+    return ns["process_single_batch_culens"]
+
+
+@pytest.mark.parametrize("limit", [8192, 60, 30, 5])
+def test_process_single_batch_culens_matches_reference_and_padded_collator(limit):
+    from rwkvtts_b200.batch import process_single_batch, process_single_batch_culens
+    model = make_model(seed=19)
+    model.device = torch.device("cpu")
+    batch = _padded_batch()
+    got = process_single_batch_culens(batch, model, eos_token_id=129, max_cu_seqlens=limit)
+    ref_fn = _reference_process_single_batch_culens()
+    if ref_fn is not None:
+        ref = ref_fn(batch, model, eos_token_id=129, max_cu_seqlens=limit)
+        for k in ("input_embs", "labels", "cu_seqlens"):
+            assert torch.equal(got[k], ref[k]), k
+    # against the padded collator, which is pinned to the reference and to its golden: row i of the left-padded batch
+    # (its last n_i positions) is segment i of the packed one, for every sample the limit let through
+    pad = process_single_batch(batch, model, eos_token_id=129)
+    n = pad["attention_mask"].sum(1).tolist()
+    cu = got["cu_seqlens"].tolist()
+    assert cu[0] == 0 and all(b - a == n[i] for i, (a, b) in enumerate(zip(cu[:-1], cu[1:])))
+    assert len(cu) - 1 == sum(1 for i in range(len(n)) if sum(n[:i + 1]) <= limit and all(sum(n[:j + 1]) <= limit for j in range(i)))
+    rows = min(len(cu), len(n))                    # the sample that crossed the limit is still in the buffers
+    assert got["input_embs"].shape[1] == sum(n[:rows]) == got["labels"].shape[1]
+    off = 0
+    for i in range(rows):
+        assert torch.equal(got["input_embs"][0, off:off + n[i]], pad["input_embs"][i, -n[i]:])
+        assert torch.equal(got["labels"][0, off:off + n[i]], pad["labels"][i, -n[i]:])
+        off += n[i]
