@@ -386,3 +386,125 @@ def process_single_batch_culens(batch, rwkv7speech_model, eos_token_id: int = 81
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)
     return {"input_embs": out.unsqueeze(0), "labels": labels.unsqueeze(0), "cu_seqlens": cu_t}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Cosy layout (/root/reference/model/llm/cosy_llm.py:64-73, :86-88; same code in model/llm/llm.py:73-83, :101-103)
+# ---------------------------------------------------------------------------------------------------------------
+def pad_unpad_sequence(sos_eos_emb, text_token, text_token_len, task_id_emb, speech_token, speech_token_len,
+                       padding_value: float = -1):
+    """Same arguments and result as the reference's method of that name (without `self`): `text_token` [B, Lt, D] and
+    `speech_token` [B, Ls, D] are right-padded EMBEDDINGS with their lengths; the result is the right-padded
+    [sos, text_i, task_id, speech_i] batch [B, Tmax, D] (padding value IGNORE_ID = -1, as the reference pads its
+    embeddings, :71) and an int32 attention mask [B, Tmax].  The reference unpads to 2B tensors, concatenates per sample
+    and pads again; here it is one length read-back, one index array and one gather + scatter per source."""
+    device = text_token.device
+    B, Lt, D = text_token.shape
+    Ls = speech_token.shape[1]
+    tl = [int(v) for v in text_token_len.tolist()]
+    sl = [int(v) for v in speech_token_len.tolist()]
+    n = [2 + tl[i] + sl[i] for i in range(B)]
+    Tmax = max(n)
+    src_t, dst_t, src_s, dst_s, dst_sos, dst_task = [], [], [], [], [], []
+    for i in range(B):
+        base = i * Tmax
+        dst_sos.append(base)
+        src_t += range(i * Lt, i * Lt + tl[i])
+        dst_t += range(base + 1, base + 1 + tl[i])
+        dst_task.append(base + 1 + tl[i])
+        src_s += range(i * Ls, i * Ls + sl[i])
+        dst_s += range(base + 2 + tl[i], base + n[i])
+    mask = (np.arange(Tmax)[None, :] < np.asarray(n)[:, None]).astype(np.int64)
+    s_t, d_t, s_s, d_s, d_sos, d_task, m = _to_device([src_t, dst_t, src_s, dst_s, dst_sos, dst_task, mask], device)
+    out = torch.full((B * Tmax, D), padding_value, dtype=text_token.dtype, device=device)
+    out = out.index_copy(0, d_sos, sos_eos_emb.reshape(1, D).to(out.dtype).expand(B, D))
+    out = out.index_copy(0, d_task, task_id_emb.reshape(1, D).to(out.dtype).expand(B, D))
+    if len(src_t):
+        out = out.index_copy(0, d_t, text_token.reshape(B * Lt, D).index_select(0, s_t))
+    if len(src_s):
+        out = out.index_copy(0, d_s, speech_token.reshape(B * Ls, D).to(out.dtype).index_select(0, s_s))
+    return out.view(B, Tmax, D), m.view(B, Tmax).to(torch.int32)
+
+
+def cosy_lm_target(text_token_len, speech_token, speech_token_len, speech_token_size: int, ignore_id: int = -1):
+    """The reference's `lm_target` (/root/reference/model/llm/cosy_llm.py:86-88): per sample
+    [ignore] * (2 + text_len) + speech ids + [speech_token_size], right-padded with `ignore_id`, int64 on the device of
+    `speech_token` (the caller takes `[:, 1:]` as labels, :111).  The reference converts every row to a Python list
+    (`.tolist()`, one sync per sample); here the lengths come back once and the ids never leave the device."""
+    device = speech_token.device
+    B, Ls = speech_token.shape
+    tl = [int(v) for v in text_token_len.tolist()]
+    sl = [int(v) for v in speech_token_len.tolist()]
+    n = [2 + tl[i] + sl[i] + 1 for i in range(B)]
+    Tmax = max(n)
+    src, dst, eos = [], [], []
+    for i in range(B):
+        src += range(i * Ls, i * Ls + sl[i])
+        dst += range(i * Tmax + 2 + tl[i], i * Tmax + 2 + tl[i] + sl[i])
+        eos.append(i * Tmax + n[i] - 1)
+    s, d, e = _to_device([src, dst, eos], device)
+    out = torch.full((B * Tmax,), ignore_id, dtype=torch.long, device=device)
+    if len(src):
+        out.index_copy_(0, d, speech_token.reshape(-1).to(torch.long).index_select(0, s))
+    out.index_fill_(0, e, speech_token_size)
+    return out.view(B, Tmax)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# XY layout (/root/reference/train_scripts/train_xy_llm.py:91-216): 8 codebook channels in a staircase
+# ---------------------------------------------------------------------------------------------------------------
+def xy_staircase_batch(processed_features, num_channels: int, speech_vocab_size: int, text_pad_token_id: int,
+                       ignore_id: int = -100) -> Dict[str, torch.Tensor]:
+    """The layout half of the reference's `process_batch` (:121-216).  Each feature holds `text` ids [T1] and `speech`
+    codes [num_channels, T2] (channel 0 already shifted into the text vocabulary).  Per sample, T1 + T2 + channels - 1
+    steps: channel 0 = text then the text pad id, every other cell the audio pad id (speech_vocab_size - 1), and channel
+    c's codes start c steps late (:146-153).  Labels are the inputs shifted by one step (:156), ignored on the text part
+    except its last step (:159), ignored wherever they equal either pad id (:162-163), then each channel gets its pad id
+    as the end-of-stream target right after its last code (:164-166).  Samples are padded to the longest with pad ids /
+    ignore / mask 0.  CPU int64 tensors, as in the reference.
+
+    The reference fills the staircase cell by cell (8 * (T2 + 7) tensor writes per sample, about a second per sample at
+    T2 = 8192); here it is one strided copy per channel."""
+    audio_pad = speech_vocab_size - 1
+    n = [int(f["text"].shape[0]) + int(f["speech"].shape[1]) + num_channels - 1 for f in processed_features]
+    B, Tmax = len(n), max(n)
+    ids = np.full((B, Tmax, num_channels), audio_pad, dtype=np.int64)
+    ids[:, :, 0] = text_pad_token_id
+    labels = np.full((B, Tmax, num_channels), ignore_id, dtype=np.int64)
+    mask = np.zeros((B, Tmax), dtype=np.int64)
+    for i, f in enumerate(processed_features):
+        text = np.asarray(f["text"].cpu() if torch.is_tensor(f["text"]) else f["text"], dtype=np.int64)
+        speech = np.asarray(f["speech"].cpu() if torch.is_tensor(f["speech"]) else f["speech"], dtype=np.int64)
+        T1, T2 = text.shape[0], speech.shape[1]
+        ids[i, :T1, 0] = text
+        for ch in range(num_channels):
+            ids[i, T1 + ch:T1 + ch + T2, ch] = speech[ch]
+        lab = labels[i, :n[i]]
+        lab[:-1] = ids[i, 1:n[i]]
+        lab[:T1 - 1] = ignore_id
+        lab[(lab == audio_pad) | (lab == text_pad_token_id)] = ignore_id
+        for ch in range(num_channels):
+            lab[T1 + T2 - 1 + ch, ch] = text_pad_token_id if ch == 0 else audio_pad
+        mask[i, :n[i]] = 1
+    return {"input_ids": torch.from_numpy(ids), "labels": torch.from_numpy(labels), "attention_mask": torch.from_numpy(mask)}
+
+
+def process_batch(features, text_tokenizer, xy_tokenizer, num_channels, text_shift_size, speech_vocab_size, device):
+    """Same signature and result as the reference's `process_batch` (/root/reference/train_scripts/train_xy_llm.py:91-216):
+    tokenises the text ("[S0]...[CTL0]", :100), runs the caller's audio codec (`xy_tokenizer.encode`, not part of this
+    repo), shifts channel 0 by `text_shift_size` (:116) and lays the batch out with `xy_staircase_batch`.  Samples without
+    text or audio are skipped; an empty batch gives {} (:120-121)."""
+    processed = []
+    for feature in features:
+        text = f"[S0]{feature.get('json', {}).get('text', '')}[CTL0]"
+        audio_np = feature.get("audio", {}).get("array")
+        if not text or audio_np is None:
+            continue
+        text_tokens = text_tokenizer(text, return_tensors="pt").input_ids.squeeze(0)
+        with torch.no_grad():
+            codes = xy_tokenizer.encode([torch.from_numpy(audio_np).to(device)], device=device)["codes_list"][0].clone()
+            codes[0, :] = codes[0, :] + text_shift_size
+        processed.append({"text": text_tokens, "speech": codes})
+    if not processed:
+        return {}
+    return xy_staircase_batch(processed, num_channels, speech_vocab_size, text_tokenizer.vocab_size - 1)

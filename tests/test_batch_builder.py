@@ -339,3 +339,125 @@ def test_process_single_batch_culens_matches_reference_and_padded_collator(limit
         assert torch.equal(got["input_embs"][0, off:off + n[i]], pad["input_embs"][i, -n[i]:])
         assert torch.equal(got["labels"][0, off:off + n[i]], pad["labels"][i, -n[i]:])
         off += n[i]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Cosy layout: RWKV7CosyLM.pad_unpad_sequence and the lm_target lines of its forward (model/llm/cosy_llm.py:64-88)
+# ---------------------------------------------------------------------------------------------------------------
+REF5 = "/root/reference/model/llm/cosy_llm.py"
+GOLD6 = os.path.join(ROOT, "tests", "golden", "cosy_pad_unpad.pt")
+
+
+def _reference_pad_unpad_sequence():
+    if not os.path.exists(REF5):
+        return None
+    import ast
+    from torch.nn.utils.rnn import pad_sequence, unpad_sequence
+    cls = [n for n in ast.parse(open(REF5).read()).body if isinstance(n, ast.ClassDef) and n.name == "RWKV7CosyLM"][0]
+    fn = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "pad_unpad_sequence"][0]
+    ns = {"torch": torch, "pad_sequence": pad_sequence, "unpad_sequence": unpad_sequence, "IGNORE_ID": -1}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF5, "exec"), ns)
+    return lambda *a: ns["pad_unpad_sequence"](None, *a)
+
+
+def test_cosy_pad_unpad_sequence_and_target_match_reference_and_golden():
+    from torch.nn.utils.rnn import pad_sequence
+    from rwkvtts_b200.batch import cosy_lm_target, pad_unpad_sequence
+    g = torch.Generator().manual_seed(23)
+    B, Lt, Ls, D, V = 4, 9, 14, 8, 6561
+    tl, sl = torch.tensor([9, 1, 4, 7]), torch.tensor([3, 14, 8, 1])
+    text_ids = torch.randint(0, 100, (B, Lt), generator=g)
+    speech_ids = torch.randint(0, V, (B, Ls), generator=g)
+    text_emb = torch.randn(B, Lt, D, generator=g, requires_grad=True)
+    speech_emb = torch.randn(B, Ls, D, generator=g, requires_grad=True)
+    sos, task = torch.randn(1, 1, D, generator=g, requires_grad=True), torch.randn(1, 1, D, generator=g)
+    got_x, got_m = pad_unpad_sequence(sos, text_emb, tl, task, speech_emb, sl)
+    got_t = cosy_lm_target(tl, speech_ids, sl, V)
+    ref_fn = _reference_pad_unpad_sequence()
+    if ref_fn is not None:
+        ref_x, ref_m = ref_fn(sos, text_emb, tl, task, speech_emb, sl)
+        # cosy_llm.py:86-88
+        ref_t = pad_sequence([torch.tensor([-1] * (2 + tl[i]) + speech_ids[i, :sl[i]].tolist() + [V]) for i in range(B)],
+                             batch_first=True, padding_value=-1)
+        if not os.path.exists(GOLD6):
+            torch.save({"x": ref_x.detach(), "mask": ref_m, "target": ref_t}, GOLD6)
+    else:
+        g_ = torch.load(GOLD6)
+        ref_x, ref_m, ref_t = g_["x"], g_["mask"], g_["target"]
+    gold = torch.load(GOLD6)
+    assert torch.equal(got_x, ref_x) and torch.equal(got_x.detach(), gold["x"])
+    assert got_m.dtype == ref_m.dtype == torch.int32 and torch.equal(got_m, ref_m)
+    assert got_t.dtype == ref_t.dtype and torch.equal(got_t, ref_t) and torch.equal(got_t, gold["target"])
+    # gradients flow to the three sources; padding positions get none
+    w = torch.randn(got_x.shape, generator=g)
+    (got_x * w).sum().backward()
+    assert torch.equal(sos.grad.reshape(-1), w[:, 0].sum(0))
+    for i in range(B):
+        assert torch.equal(text_emb.grad[i, :tl[i]], w[i, 1:1 + tl[i]]) and float(text_emb.grad[i, tl[i]:].abs().sum()) == 0
+        assert torch.equal(speech_emb.grad[i, :sl[i]], w[i, 2 + tl[i]:2 + tl[i] + sl[i]])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# XY layout: process_batch of train_scripts/train_xy_llm.py:91-216 (staircase over 8 codebook channels)
+# ---------------------------------------------------------------------------------------------------------------
+REF6 = "/root/reference/train_scripts/train_xy_llm.py"
+GOLD7 = os.path.join(ROOT, "tests", "golden", "xy_process_batch.pt")
+
+
+class _XYTextTok:
+    vocab_size = 300                                   # pad id 299
+
+    def __call__(self, text, return_tensors="pt"):
+        ids = torch.tensor([[(ord(c) * 11 + i) % 299 for i, c in enumerate(text)]])
+        return types.SimpleNamespace(input_ids=ids)
+
+
+class _XYCodec:
+    """stand-in audio codec: 8 x T2 codes derived from the samples; some codes equal the pad ids on purpose
+    (speech_vocab_size - 1 in any channel, text pad - shift in channel 0) to hit the reference's label masking"""
+    def encode(self, wavs, device="cpu"):
+        a = wavs[0]
+        T2 = a.numel() // 4
+        g = torch.Generator().manual_seed(int(a.numel()))
+        codes = torch.randint(0, 40, (8, T2), generator=g)
+        codes[3, T2 // 2] = 39
+        codes[0, min(2, T2 - 1)] = 299 - 256
+        return {"codes_list": [codes]}
+
+
+def _reference_process_batch():
+    if not os.path.exists(REF6):
+        return None
+    import ast
+    import logging
+    fn = [n for n in ast.parse(open(REF6).read()).body if isinstance(n, ast.FunctionDef) and n.name == "process_batch"][0]
+    ns = {"torch": torch, "logger": logging.getLogger("xy")}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF6, "exec"), ns)
+    return ns["process_batch"]
+
+
+def test_xy_process_batch_matches_reference_and_golden():
+    import numpy as np
+    from rwkvtts_b200.batch import process_batch
+    feats = [{"json": {"text": "hello"}, "audio": {"array": np.zeros(44, dtype=np.float32)}},
+             {"json": {"text": "a much longer line of text"}, "audio": {"array": np.zeros(8, dtype=np.float32)}},
+             {"json": {"text": "no audio"}, "audio": {}},
+             {"json": {}, "audio": {"array": np.zeros(100, dtype=np.float32)}}]
+    args = (_XYTextTok(), _XYCodec(), 8, 256, 40, "cpu")
+    got = process_batch(feats, *args)
+    ref_fn = _reference_process_batch()
+    if ref_fn is not None:
+        ref = ref_fn(feats, *args)
+        if not os.path.exists(GOLD7):
+            torch.save(ref, GOLD7)
+        assert ref_fn([feats[2]], *args) == {}
+    else:
+        ref = torch.load(GOLD7)
+    gold = torch.load(GOLD7)
+    assert process_batch([feats[2]], *args) == {}
+    assert got["input_ids"].shape[0] == 3 and got["input_ids"].shape[2] == 8
+    for k in ("input_ids", "labels", "attention_mask"):
+        assert got[k].dtype == ref[k].dtype and torch.equal(got[k], ref[k]), k
+        assert torch.equal(got[k], gold[k]), k
+    # the masking quirk is exercised: a real code equal to a pad id is not a target
+    assert int((got["labels"] == 39).sum()) == 7 * 3 and int((got["labels"] == 299).sum()) == 3
