@@ -27,10 +27,11 @@ def mm_3x(a, b):
 
 
 def doubling(N, mm):
-    I = torch.eye(16, dtype=torch.float64).expand_as(N)
+    L = N.shape[-1]
+    I = torch.eye(L, dtype=torch.float64).expand_as(N)
     T = I + N
     P = N
-    for _ in range(3):
+    for _ in range(L.bit_length() - 2):                 # 3 squarings for L = 16, 5 for L = 64
         P = mm(P, P)
         T = T + mm(T, P)
     return T
@@ -40,21 +41,28 @@ x = make_inputs(2, 256, 4, seed=1)
 w, a, b = (x[n].double() for n in "wab")
 lw = (-torch.exp(w)).clamp(min=-1.35)                    # log decay per step
 B, T, H, C = w.shape
-res = {"fp32 solve + tf32 round": [], "tf32 doubling": [], "3xtf32 doubling": []}
-for c0 in range(0, T, 16):
-    win0 = (c0 // 64) * 64
-    G = lw[:, win0:c0 + 16].cumsum(1)[:, c0 - win0:]      # [B,16,H,C] decay since the window start
-    Gm1 = G - lw[:, c0:c0 + 16]
-    At = (a[:, c0:c0 + 16] * torch.exp(Gm1)).permute(0, 2, 1, 3)      # [B,H,16,C]
-    Bt = (b[:, c0:c0 + 16] * torch.exp(-G)).permute(0, 2, 1, 3)
-    N = torch.tril(tf32(At) @ tf32(Bt).transpose(-1, -2), diagonal=-1)
-    I = torch.eye(16, dtype=torch.float64)
-    W_ref = torch.linalg.solve_triangular(I - N, tf32(At), upper=False)
-    W_now = tf32(torch.linalg.solve_triangular((I - N).float(), tf32(At).float(), upper=False))
-    rel = lambda y: float((y - W_ref).norm() / W_ref.norm())
-    res["fp32 solve + tf32 round"].append(rel(W_now))
-    res["tf32 doubling"].append(rel(tf32(mm_tf32(doubling(N, mm_tf32), At))))
-    res["3xtf32 doubling"].append(rel(tf32(mm_tf32(doubling(N, mm_3x), At))))
-for k, v in res.items():
-    t = torch.tensor(v)
-    print(f"{k:28s} rel err of W~: mean {t.mean():.2e}  max {t.max():.2e}")
+
+
+def run(L):
+    res = {"fp32 solve + tf32 round": [], "tf32 doubling": [], "3xtf32 doubling": []}
+    for c0 in range(0, T, L):
+        win0 = (c0 // 64) * 64
+        G = lw[:, win0:c0 + L].cumsum(1)[:, c0 - win0:]      # [B,L,H,C] decay since the window start
+        Gm1 = G - lw[:, c0:c0 + L]
+        At = (a[:, c0:c0 + L] * torch.exp(Gm1)).permute(0, 2, 1, 3)      # [B,H,L,C]
+        Bt = (b[:, c0:c0 + L] * torch.exp(-G)).permute(0, 2, 1, 3)
+        N = torch.tril(tf32(At) @ tf32(Bt).transpose(-1, -2), diagonal=-1)
+        I = torch.eye(L, dtype=torch.float64)
+        W_ref = torch.linalg.solve_triangular(I - N, tf32(At), upper=False)
+        W_now = tf32(torch.linalg.solve_triangular((I - N).float(), tf32(At).float(), upper=False))
+        rel = lambda y: float((y - W_ref).norm() / W_ref.norm())
+        res["fp32 solve + tf32 round"].append(rel(W_now))
+        res["tf32 doubling"].append(rel(tf32(mm_tf32(doubling(N, mm_tf32), At))))
+        res["3xtf32 doubling"].append(rel(tf32(mm_tf32(doubling(N, mm_3x), At))))
+    for k, v in res.items():
+        t = torch.tensor(v)
+        print(f"L={L:3d}  {k:28s} rel err of W~: mean {t.mean():.2e}  max {t.max():.2e}")
+
+
+run(16)      # today's chunk
+run(64)      # a whole window as one chunk: every product is a single M = 64, N = 64, K = 64 tensor-core instruction
