@@ -35,6 +35,11 @@ from . import _lib
 ALIGN = 256     # elements; keeps every shard boundary 512-byte aligned for bf16
 
 
+def _invalidate_param_cache():
+    from . import fused              # late: fused pulls in the op registrations
+    fused.invalidate_param_cache()
+
+
 # ---------------------------------------------------------------------------------------------
 # optimizers (deepspeed.ops.adam)
 # ---------------------------------------------------------------------------------------------
@@ -83,6 +88,7 @@ def adam_update(master, m, v, grad, param, group: Dict[str, Any], step: int, ada
     n = master.numel()
     if n == 0:
         return
+    _invalidate_param_cache()        # `param` is rewritten below without any parameter's version counter moving
     if master.is_cuda:
         for t, dt in ((grad, (torch.bfloat16, torch.float32)), (param, (torch.bfloat16, torch.float32))):
             if t.dtype not in dt:
@@ -284,6 +290,7 @@ class Engine:
                 dist.all_gather_into_tensor(self.flat_param, pshard)          # in place: pshard is rank's slice
             else:
                 dist.all_gather(list(self.flat_param.chunk(self.world_size)), pshard.clone())
+        _invalidate_param_cache()     # the all-gather rewrote the other ranks' shards of the flat parameter buffer
         self.flat_grad.zero_()
         self.global_steps += 1
         if self.lr_scheduler is not None:

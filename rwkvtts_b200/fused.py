@@ -33,10 +33,20 @@ def usable(x: torch.Tensor) -> bool:
 # token otherwise) they are cached per parameter OBJECT (weak references: a freed parameter's address can be reused by
 # another tensor) and version counter.
 _PCACHE: dict = {}       # id(parameter) -> (weakref to it, version key, fp32 copy)
+_EPOCH = [0]
+
+
+def invalidate_param_cache() -> None:
+    """Called by whatever rewrites parameter storage behind autograd's back: the Adam kernel writes through raw
+    pointers and the engine's all-gather lands in the flat buffer the parameters alias, so no parameter's `_version`
+    moves.  Without this a generate() after a training step would run on the cached copies of the old weights."""
+    _EPOCH[0] += 1
+    _PCACHE.clear()
 
 
 def _cached(p: torch.Tensor, ver, make):
     k = id(p)
+    ver = (_EPOCH[0], ver)
     hit = _PCACHE.get(k)
     if hit is not None and hit[0]() is p and hit[1] == ver and hit[2].device == p.device:
         return hit[2]

@@ -142,3 +142,38 @@ def test_world_size_2_gloo_matches_single_process():
         got = torch.load(out)
     for a, b in zip(got, _reference_steps(4)):
         assert torch.allclose(a, b, atol=2e-6), (a - b).abs().max()
+
+
+def test_optimizer_step_invalidates_the_no_grad_parameter_cache():
+    """The Adam kernel writes parameters through raw pointers and the engine's parameters alias a flat buffer, so an
+    optimizer step moves no parameter's autograd version counter; the cached fp32 / stacked copies that the no_grad
+    paths (prefill, decode) keep must be dropped by the step itself."""
+    import deepspeed
+    from deepspeed.ops.adam import FusedAdam
+    from rwkvtts_b200 import fused
+    m = _model()
+    opt = FusedAdam(_groups(m), lr=1e-2, betas=(0.9, 0.95), eps=1e-18)
+    eng, _, _, _ = deepspeed.initialize(model=m, config={"train_batch_size": 16, "bf16": {"enabled": False},
+                                                         "zero_optimization": {"stage": 2}},
+                                        model_parameters=m.parameters(), optimizer=opt)
+    w = m[0].weight
+    calls = []
+    def copy():
+        calls.append(1)
+        return w.detach().double().clone()
+    with torch.no_grad():
+        c0 = fused.cached(w, (w,), "test", copy)
+        assert fused.cached(w, (w,), "test", copy) is c0 and len(calls) == 1          # hit
+    ver = w._version
+    x, y = _data()
+    eng.backward(torch.nn.functional.mse_loss(eng(x), y))
+    eng.step()
+    assert w._version == ver                       # the hazard: nothing autograd-visible happened to the parameter
+    with torch.no_grad():
+        c1 = fused.cached(w, (w,), "test", copy)
+    assert len(calls) == 2 and not torch.equal(c0, c1) and torch.equal(c1, w.detach().double())
+    # in-place edits that do move the version counter are still seen without a step
+    with torch.no_grad():
+        w.mul_(2.0)
+        c2 = fused.cached(w, (w,), "test", copy)
+    assert len(calls) == 3 and torch.equal(c2, 2.0 * c1)
