@@ -41,6 +41,8 @@ def dist_init(world):
         return
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if os.environ["MASTER_ADDR"] in ("127.0.0.1", "localhost"):
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")     # one node: do not depend on the hostname resolving
     import torch
     try:
         dist.init_process_group("cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo")
