@@ -31,25 +31,71 @@ METRIC = "audio-tokens/sec (train fwd+bwd) RWKV-7 0.4B seq4096"
 WORKLOAD = "configs[1]: RWKV-7 0.4B Spark-layout bf16, batch 8/GPU, seq_len 4096, WKV-7 fwd+bwd x 24 layers"
 
 
+_CTL = {"mode": "single", "dir": None, "seq": 0, "rank": 0}
+
+
 def dist_init(world):
     """Control plane of a multi-GPU run.  The path shards by batch with no data-path collective, so
     the only exchanges of the bench are its barriers and the max over ranks of two scalars: they go over gloo (CPU
     tensors).  The process group is created with NCCL registered for CUDA tensors, as a training job would have it
     (the ZeRO-2 engine's reduce-scatter / all-gather), but the NCCL communicator is only built on the first CUDA
-    collective -- which this bench never issues -- so an 8-rank start does not pay (or hang in) NVLS / fabric set-up."""
+    collective -- which this bench never issues -- so an 8-rank start does not pay (or hang in) NVLS / fabric set-up.
+    If the process group cannot be created within two minutes (or RWKVTTS_BENCH_CONTROL=fs), the same two exchanges run
+    over files in /tmp: the ranks of one torchrun launch share a node and a parent process."""
     if world <= 1:
         return
+    import datetime
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     if os.environ["MASTER_ADDR"] in ("127.0.0.1", "localhost"):
         os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")     # one node: do not depend on the hostname resolving
+    _CTL["rank"] = int(os.environ.get("RANK", "0"))
+    _CTL["dir"] = os.path.join("/tmp", "rwkvtts_bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
     import torch
-    try:
-        dist.init_process_group("cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo")
-    except Exception:                      # mixed registration unavailable: the control plane only needs gloo
-        if dist.is_initialized():
-            dist.destroy_process_group()
-        dist.init_process_group("gloo")
+    if os.environ.get("RWKVTTS_BENCH_CONTROL") != "fs":
+        tmo = datetime.timedelta(seconds=120)
+        for backend in (("cpu:gloo,cuda:nccl",) if torch.cuda.is_available() else ()) + ("gloo",):
+            try:
+                dist.init_process_group(backend, timeout=tmo)
+                dist.all_reduce(torch.zeros(1))               # proves the gloo ring before anything is timed
+                _CTL["mode"] = "dist"
+                return
+            except Exception as e:                            # mixed registration unavailable / rendezvous failed
+                sys.stderr.write("bench: process group %r failed (%r)\n" % (backend, e))
+                if dist.is_initialized():
+                    dist.destroy_process_group()
+    os.makedirs(_CTL["dir"], exist_ok=True)
+    _CTL["mode"] = "fs"
+
+
+def dist_finish(world):
+    if world > 1 and _CTL["mode"] == "dist":
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def _fs_exchange(x, world, timeout_s=900.0):
+    """Every rank publishes one float for this sequence number and reads everybody's (atomic rename, polling)."""
+    seq, _CTL["seq"] = _CTL["seq"], _CTL["seq"] + 1
+    d, r = _CTL["dir"], _CTL["rank"]
+    tmp = os.path.join(d, ".%d.%d.tmp" % (seq, r))
+    with open(tmp, "w") as f:
+        f.write(repr(float(x)))
+    os.replace(tmp, os.path.join(d, "%d.%d" % (seq, r)))
+    vals, t0 = {}, time.time()
+    while len(vals) < world:
+        for k in range(world):
+            if k not in vals:
+                try:
+                    vals[k] = float(open(os.path.join(d, "%d.%d" % (seq, k))).read())
+                except (OSError, ValueError):
+                    pass
+        if len(vals) < world:
+            if time.time() - t0 > timeout_s:
+                raise RuntimeError("bench control plane: rank(s) %s never reached exchange %d"
+                                   % (sorted(set(range(world)) - set(vals)), seq))
+            time.sleep(0.002)
+    return [vals[k] for k in range(world)]
 
 
 def dist_barrier(world):
@@ -57,6 +103,9 @@ def dist_barrier(world):
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     if world > 1:
+        if _CTL["mode"] == "fs":
+            _fs_exchange(0.0, world)
+            return
         import torch.distributed as dist
         dist.all_reduce(torch.zeros(1))          # CPU tensor -> gloo
 
@@ -65,6 +114,8 @@ def dist_max(x, world):
     import torch
     if world <= 1:
         return float(x)
+    if _CTL["mode"] == "fs":
+        return max(_fs_exchange(x, world))
     import torch.distributed as dist
     t = torch.tensor([float(x)], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -263,7 +314,6 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -434,8 +484,7 @@ def main():
     e2e_value = B * T * world / (e2e_ms / args.e2e_steps * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        dist_finish(world)
         return
 
     # ---- reference CUDA op on the same inputs (extra data point; oracle/_ref) --------------------
@@ -523,8 +572,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference()
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dist_finish(world)
 
 
 if __name__ == "__main__":

@@ -12,26 +12,38 @@ sys.path.insert(0, {root!r})
 import bench
 w, r = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
 bench.dist_init(w)
+assert bench._CTL["mode"] == os.environ["EXPECT_MODE"], bench._CTL
 bench.dist_barrier(w)
 m = bench.dist_max(10.0 + r, w)
 bench.dist_barrier(w)
-import torch.distributed as dist
-assert dist.get_world_size() == w
-sys.stdout.write("rank %d max %s\n" % (r, m)); sys.stdout.flush()     # one write per rank: lines do not interleave
-dist.destroy_process_group()
+m2 = bench.dist_max(-1.0 - r, w)
+if bench._CTL["mode"] == "dist":
+    import torch.distributed as dist
+    assert dist.get_world_size() == w
+sys.stdout.write("rank %d max %s %s\n" % (r, m, m2)); sys.stdout.flush()     # one write per rank: lines do not interleave
+bench.dist_finish(w)
 """
 
 
-def test_bench_control_plane_world_size_2(tmp_path):
+def _run_world2(tmp_path, port, extra_env, mode):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", EXPECT_MODE=mode, **extra_env)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=180, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("rank")]
-    assert sorted(lines) == ["rank 0 max 11.0", "rank 1 max 11.0"], out.stdout
+    assert sorted(lines) == ["rank 0 max 11.0 -1.0", "rank 1 max 11.0 -1.0"], out.stdout
+
+
+def test_bench_control_plane_world_size_2(tmp_path):
+    _run_world2(tmp_path, 29577, {}, "dist")
+
+
+def test_bench_control_plane_file_fallback_world_size_2(tmp_path):
+    """the fallback the bench takes when no process group can be created: same barrier / max over files in /tmp"""
+    _run_world2(tmp_path, 29578, {"RWKVTTS_BENCH_CONTROL": "fs"}, "fs")
 
 
 def test_bench_single_process_helpers_are_noops():
