@@ -9,7 +9,7 @@ lookups, two `torch.cat` and two `torch.full` (about 20 kernels and as many smal
 then `pad_sequence` over the list).  Here the layout of the whole batch is computed once on the host as flat index
 arrays, shipped to the device in one copy, and the batch is assembled with one gather per embedding table and one
 scatter per table into the zero-initialised padded result (8 kernels for any batch size, autograd-friendly: the
-embedding tables receive their gradients through `index_copy`).
+embedding tables receive their gradients through the in-place `index_copy_` into a fresh buffer).
 
 Layout per sample (`:34-41`): [tag2, text..., tag0, global..., tag1, semantic..., eos]; labels are -100 on the prefix and
 the semantic ids (+ eos) after it (`:46-53`), padding value -100 / 0.0, attention_mask 1 on real positions (`:66-69`).
@@ -72,7 +72,7 @@ def create_inputs_and_labels(batch: Dict[str, Any], tokenizer, model, eos_token_
         if sizes[j] == 0:
             continue
         emb = first if k == "semantic" else tables[k](part[j])
-        out = out.index_copy(0, part[4 + j], emb)
+        out.index_copy_(0, part[4 + j], emb)
     return {"input_embs": out.view(B, Tmax, -1), "labels": part[8].view(B, Tmax), "attention_mask": part[9].view(B, Tmax)}
 
 
@@ -123,10 +123,10 @@ def process_single_batch(batch: Dict[str, torch.Tensor], rwkv7speech_model, eos_
            "semantic": ids_s.to(device).reshape(-1)[s_sem]}
     tables = {"text": model.text_embedder, "global": model.global_embedder, "semantic": model.model.embeddings}
     tag = model.tts_tag_embedder(torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(B))
-    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=device).index_copy(0, d_tag, tag)
+    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=device).index_copy_(0, d_tag, tag)
     for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
         if tok[k].numel():
-            out = out.index_copy(0, d_k, tables[k](tok[k]))
+            out.index_copy_(0, d_k, tables[k](tok[k]))
     labels = torch.full((B * Tmax,), -100, dtype=torch.long, device=device)
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)
@@ -173,10 +173,10 @@ def create_inputs(texts, global_tokens_ids, semantic_tokens_ids, tokenizer, llm,
     tables = {"tag": llm.tts_tag_embedder, "text": llm.text_embedder, "global": llm.global_embedder,
               "semantic": llm.model.embeddings}
     tag = tables["tag"](part[0])
-    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=tag.device).index_copy(0, part[4], tag)
+    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=tag.device).index_copy_(0, part[4], tag)
     for j, k in enumerate(order[1:], start=1):
         if len(ids[k]):
-            out = out.index_copy(0, part[4 + j], tables[k](part[j]))
+            out.index_copy_(0, part[4 + j], tables[k](part[j]))
     return out.view(B, Tmax, -1), part[8].view(B, Tmax)
 
 
@@ -219,7 +219,7 @@ def create_inputs_and_labels_culens(batch: Dict[str, Any], tokenizer, model, eos
     out = torch.zeros(cu[-1], first.shape[-1], dtype=first.dtype, device=first.device)
     for j, k in enumerate(order):
         if len(ids[k]):
-            out = out.index_copy(0, part[4 + j], first if k == "semantic" else tables[k](part[j]))
+            out.index_copy_(0, part[4 + j], first if k == "semantic" else tables[k](part[j]))
     return {"input_embs": out.unsqueeze(0), "labels": part[8].unsqueeze(0), "cu_seqlens": part[9]}
 
 
@@ -281,7 +281,7 @@ def _assemble_rows(rows, model, device, packed: bool):
         emb = tables[k](part[j])
         if out is None:
             out = torch.zeros(total, emb.shape[-1], dtype=emb.dtype, device=emb.device)
-        out = out.index_copy(0, part[4 + j], emb)
+        out.index_copy_(0, part[4 + j], emb)
     if packed:
         return out.unsqueeze(0), part[8].unsqueeze(0), part[9]
     return out.view(R, Tmax, -1), part[8].view(R, Tmax), part[9].view(R, Tmax)
@@ -378,10 +378,10 @@ def process_single_batch_culens(batch, rwkv7speech_model, eos_token_id: int = 81
            "semantic": ids_s.to(device).reshape(-1)[s_sem]}
     tables = _tables(model)
     tag = tables["tag"](torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(n_rows))
-    out = torch.zeros(base, tag.shape[-1], dtype=tag.dtype, device=device).index_copy(0, d_tag, tag)
+    out = torch.zeros(base, tag.shape[-1], dtype=tag.dtype, device=device).index_copy_(0, d_tag, tag)
     for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
         if tok[k].numel():
-            out = out.index_copy(0, d_k, tables[k](tok[k]))
+            out.index_copy_(0, d_k, tables[k](tok[k]))
     labels = torch.full((base,), -100, dtype=torch.long, device=device)
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)
@@ -417,12 +417,12 @@ def pad_unpad_sequence(sos_eos_emb, text_token, text_token_len, task_id_emb, spe
     mask = (np.arange(Tmax)[None, :] < np.asarray(n)[:, None]).astype(np.int64)
     s_t, d_t, s_s, d_s, d_sos, d_task, m = _to_device([src_t, dst_t, src_s, dst_s, dst_sos, dst_task, mask], device)
     out = torch.full((B * Tmax, D), padding_value, dtype=text_token.dtype, device=device)
-    out = out.index_copy(0, d_sos, sos_eos_emb.reshape(1, D).to(out.dtype).expand(B, D))
-    out = out.index_copy(0, d_task, task_id_emb.reshape(1, D).to(out.dtype).expand(B, D))
+    out.index_copy_(0, d_sos, sos_eos_emb.reshape(1, D).to(out.dtype).expand(B, D))
+    out.index_copy_(0, d_task, task_id_emb.reshape(1, D).to(out.dtype).expand(B, D))
     if len(src_t):
-        out = out.index_copy(0, d_t, text_token.reshape(B * Lt, D).index_select(0, s_t))
+        out.index_copy_(0, d_t, text_token.reshape(B * Lt, D).index_select(0, s_t))
     if len(src_s):
-        out = out.index_copy(0, d_s, speech_token.reshape(B * Ls, D).to(out.dtype).index_select(0, s_s))
+        out.index_copy_(0, d_s, speech_token.reshape(B * Ls, D).to(out.dtype).index_select(0, s_s))
     return out.view(B, Tmax, D), m.view(B, Tmax).to(torch.int32)
 
 
