@@ -1,0 +1,126 @@
+"""the reference's OWN layout wrappers (model/llm/spark_llm.py, cosy_llm.py, xy_llm.py) run,
+unmodified, on this repo's `rwkvfla` package and batch builders.  They are imported from /root/reference, so these tests
+only run in the build container (the GPU box has no reference tree); the recurrent blocks are replaced by a causal
+stand-in because the real ones need the CUDA library -- what is checked is the seam: construction through
+PreTrainedModel / post_init, parameter registration, `self.model(inputs_embeds=..., attention_mask=...)`, the loss
+modules the wrappers import from `rwkvfla`, and gradients reaching the wrappers' own embedding tables and heads."""
+import importlib.util
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model", "llm")), reason="reference tree not mounted")
+
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _load(name, rel):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    third = os.path.join(REF, "third_party")
+    if third not in sys.path:
+        sys.path.append(third)                      # cosy_llm.py imports cosyvoice.* from the reference's third_party
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod                          # transformers looks the defining module up by name
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture
+def stand_in_blocks(monkeypatch):
+    from rwkvfla.models.rwkv7 import modeling_rwkv7 as M
+
+    def fake_block(self, hidden_states, attention_mask=None, past_key_values=None, use_cache=False,
+                   output_attentions=False, v_first=None, cu_seqlens=None, **kw):
+        t = torch.arange(1, hidden_states.shape[1] + 1, dtype=hidden_states.dtype).view(1, -1, 1)
+        return hidden_states.cumsum(1) / t + 0.1 * (self.layer_idx + 1), None, past_key_values, v_first
+
+    monkeypatch.setattr(M.RWKV7Block, "forward", fake_block)
+    return M
+
+
+SMALL = dict(hidden_size=64, num_hidden_layers=2, decay_low_rank_dim=32, a_low_rank_dim=32, v_low_rank_dim=32,
+             gate_low_rank_dim=32)
+
+
+def test_reference_spark_wrapper_trains_on_the_seam(stand_in_blocks):
+    import test_batch_builder as tb
+    from rwkvtts_b200.batch import create_inputs_and_labels
+    mod = _load("ref_spark_llm", "model/llm/spark_llm.py")
+    torch.manual_seed(0)
+    cfg = mod.RWKV7SpeechConfig(vocab_size=131, text_vocab_size=500, audio_global_vocab_size=64, fuse_cross_entropy=True, **SMALL)
+    m = mod.RWKV7ForSpeech(cfg)
+    assert isinstance(m, stand_in_blocks.RWKV7ForCausalLM) and isinstance(m.model, stand_in_blocks.RWKV7Model)
+    names = dict(m.named_parameters())
+    for n in ("model.embeddings.weight", "lm_head.weight", "text_embedder.weight", "global_embedder.weight",
+              "tts_tag_embedder.weight", "model.layers.1.attn.w_lora.lora.2.bias", "model.layers.0.ffn.key.weight"):
+        assert n in names, n
+    out = create_inputs_and_labels(tb.make_batch(), tb.Tok(), m, 130, "cpu")          # this repo's builder feeds it
+    m.train()
+    m.dropout.p = 0.0                                                                   # make train == eval comparable
+    r = m(inputs_embeds=out["input_embs"], attention_mask=out["attention_mask"], labels=out["labels"], return_dict=True)
+    assert r.logits is None                           # training + fuse_cross_entropy: rwkvfla's FusedLinearCrossEntropyLoss
+    r.loss.backward()
+    for n in ("lm_head.weight", "text_embedder.weight", "global_embedder.weight", "tts_tag_embedder.weight",
+              "model.embeddings.weight", "model.norm.weight"):
+        assert names[n].grad is not None and float(names[n].grad.abs().sum()) > 0, n
+    m.eval()
+    with torch.no_grad():
+        e = m(inputs_embeds=out["input_embs"], attention_mask=out["attention_mask"], labels=out["labels"], return_dict=True)
+    assert e.logits.shape == (3, out["labels"].shape[1], 131)
+    # the wrapper shifts the labels itself (spark_llm.py:156); both loss modules must agree with plain torch
+    lab = torch.cat((out["labels"][:, 1:], torch.full_like(out["labels"][:, :1], -100)), 1)
+    want = torch.nn.functional.cross_entropy(e.logits.reshape(-1, 131).float(), lab.reshape(-1), ignore_index=-100)
+    assert abs(float(e.loss) - float(want)) < 1e-5 and abs(float(r.loss.detach()) - float(want)) < 1e-5
+
+
+def test_reference_xy_wrapper_trains_on_the_seam(stand_in_blocks):
+    import numpy as np
+    import test_batch_builder as tb
+    from rwkvtts_b200.batch import process_batch
+    mod = _load("ref_xy_llm", "model/llm/xy_llm.py")
+    torch.manual_seed(0)
+    cfg = mod.RWKV7XYConfig(vocab_size=300, speech_vocab_size=40, num_channels=8, text_shift_size=256, **SMALL)
+    m = mod.RWKV7XYLM(cfg)
+    feats = [{"json": {"text": "hello"}, "audio": {"array": np.zeros(44, dtype=np.float32)}},
+             {"json": {"text": "a longer line"}, "audio": {"array": np.zeros(20, dtype=np.float32)}}]
+    b = process_batch(feats, tb._XYTextTok(), tb._XYCodec(), 8, 256, 40, "cpu")       # this repo's staircase builder
+    m.train()
+    r = m(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"], return_dict=True)
+    assert len(r.logits) == 8 and r.logits[0].shape[-1] == 300 and r.logits[1].shape[-1] == 40
+    want = sum(torch.nn.functional.cross_entropy(r.logits[i].reshape(-1, r.logits[i].shape[-1]), b["labels"][:, :, i].reshape(-1))
+               for i in range(8))
+    assert abs(float(r.loss.detach()) - float(want)) < 1e-5
+    r.loss.backward()
+    assert all(h.weight.grad is not None for h in m.heads) and all(e.weight.grad is not None for e in m.embs)
+
+
+def test_reference_cosy_wrapper_runs_on_the_seam(stand_in_blocks):
+    from rwkvtts_b200.batch import cosy_lm_target, pad_unpad_sequence
+    mod = _load("ref_cosy_llm", "model/llm/cosy_llm.py")
+    torch.manual_seed(0)
+    cfg = mod.RWKV7CosyConfig(vocab_size=51, speech_token_size=50, **SMALL)
+    m = mod.RWKV7CosyLM(cfg)
+    # the attributes the reference's training script attaches before calling forward(batch=...)
+    m.text_embedding = torch.nn.Embedding(100, 64)
+    m.llm_embedding = torch.nn.Embedding(2, 64)
+    m.speech_embedding = torch.nn.Embedding(51, 64)
+    m.sos_eos, m.task_id, m.dropout = 0, 1, None
+    m.criterion_ce = mod.LabelSmoothingLoss(size=51, padding_idx=-1, smoothing=0.0, normalize_length=True)
+    g = torch.Generator().manual_seed(3)
+    batch = {"text_token": torch.randint(0, 100, (3, 7), generator=g), "text_token_len": torch.tensor([7, 2, 5]),
+             "speech_token": torch.randint(0, 50, (3, 11), generator=g), "speech_token_len": torch.tensor([4, 11, 9])}
+    m.train()
+    ref = m(batch=batch, return_dict=True)                 # the wrapper's own pad_unpad_sequence and lm_target lines
+    # the same forward fed by this repo's builders
+    x, mask = pad_unpad_sequence(m.llm_embedding.weight[0].reshape(1, 1, -1), m.text_embedding(batch["text_token"]),
+                                 batch["text_token_len"], m.llm_embedding.weight[1].reshape(1, 1, -1),
+                                 m.speech_embedding(batch["speech_token"]), batch["speech_token_len"])
+    labels = cosy_lm_target(batch["text_token_len"], batch["speech_token"], batch["speech_token_len"], 50)[:, 1:].contiguous()
+    mine = m(inputs_embeds=x, attention_mask=mask, labels=labels, return_dict=True)
+    assert torch.equal(mine.logits, ref.logits) and torch.equal(mine.loss, ref.loss) and bool(torch.isfinite(ref.loss))
