@@ -124,3 +124,71 @@ def test_reference_cosy_wrapper_runs_on_the_seam(stand_in_blocks):
     labels = cosy_lm_target(batch["text_token_len"], batch["speech_token"], batch["speech_token_len"], 50)[:, 1:].contiguous()
     mine = m(inputs_embeds=x, attention_mask=mask, labels=labels, return_dict=True)
     assert torch.equal(mine.logits, ref.logits) and torch.equal(mine.loss, ref.loss) and bool(torch.isfinite(ref.loss))
+
+
+def _script_functions(rel, names, ns):
+    """functions of a reference training script, without running its top-level imports (datasets, wandb, ...)"""
+    import ast
+    path = os.path.join(REF, rel)
+    tree = ast.parse(open(path).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(body) == len(names)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def test_reference_training_script_functions_run_on_the_engine(stand_in_blocks, tmp_path, capsys):
+    """train_scripts/train_spark_rwkv7speech_jsonl.py: its own configure_optimizer (:161-199), update_learning_rate
+    (:223-243), train_step (:271-285) and save_checkpoint (:201-221), on its own RWKV7ForSpeech, this repo's `deepspeed`
+    shim (engine.py), and this repo's batch builders -- padded and packed (cu_seqlens) steps, with the script's default
+    ZeRO-3 + offload config (:365-397), which the engine must accept."""
+    import logging
+    import types
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import deepspeed
+    import test_batch_builder as tb
+    from rwkvtts_b200.batch import create_inputs_and_labels, create_inputs_and_labels_culens
+    mod = _load("ref_spark_llm", "model/llm/spark_llm.py")
+    configure_optimizer, update_learning_rate, train_step, save_checkpoint = _script_functions(
+        "train_scripts/train_spark_rwkv7speech_jsonl.py",
+        ["configure_optimizer", "update_learning_rate", "train_step", "save_checkpoint"],
+        {"torch": torch, "os": os, "deepspeed": deepspeed})
+    torch.manual_seed(0)
+    cfg = mod.RWKV7SpeechConfig(vocab_size=131, text_vocab_size=500, audio_global_vocab_size=64, fuse_cross_entropy=True, **SMALL)
+    model = mod.RWKV7ForSpeech(cfg)
+    model.dropout.p = 0.0
+    model.train()
+    args = types.SimpleNamespace(weight_decay=0.01, ds_optimizer_offload=True, learning_rate=1e-3, learning_rate_final=1e-5)
+    optimizer = configure_optimizer(model, args)
+    groups = {g["name"]: g for g in optimizer.param_groups}
+    assert set(groups) == {"lr_1x", "lr_2x", "lr_decay"} and len(groups["lr_2x"]["params"]) == 2     # one decay bias per layer
+    ds_config = {"distributed_backend": "nccl", "train_batch_size": 3, "bf16": {"enabled": False},
+                 "zero_optimization": {"stage": 3, "stage3_max_live_parameters": 1e9, "stage3_max_reuse_distance": 1e9,
+                                       "stage3_prefetch_bucket_size": 5e6, "memory_efficient_linear": True,
+                                       "stage3_param_persistence_threshold": 1e4,
+                                       "offload_param": {"device": "cpu", "pin_memory": True, "buffer_count": 4, "buffer_size": 1e8},
+                                       "offload_optimizer": {"device": "cpu", "pin_memory": True, "buffer_count": 4},
+                                       "allgather_partitions": True, "reduce_scatter": True, "reduce_bucket_size": 5e6,
+                                       "overlap_comm": False, "contiguous_gradients": True},
+                 "zero_force_ds_cpu_initialization": True, "gradient_checkpointing": False, "dump_state": False}
+    engine, opt2, _, _ = deepspeed.initialize(model=model, config=ds_config, model_parameters=model.parameters(), optimizer=optimizer)
+    assert opt2 is optimizer and engine.local_rank == 0
+    before = {n: p.detach().clone() for n, p in engine.module.named_parameters()}
+    batch = tb.make_batch()
+    losses = []
+    for step, builder in enumerate((create_inputs_and_labels, create_inputs_and_labels_culens, create_inputs_and_labels)):
+        update_learning_rate(optimizer, step, 100, 2, args.learning_rate, args.learning_rate_final, args, True)
+        assert abs(groups["lr_2x"]["lr"] - 2.0 * groups["lr_1x"]["lr"]) < 1e-12 and groups["lr_decay"]["weight_decay"] == 0.01
+        out = train_step(engine, **builder(batch, tb.Tok(), engine, 130, engine.device))     # the script passes the engine as `model`
+        assert bool(torch.isfinite(out["loss"]))
+        engine.backward(out["loss"])
+        engine.step()
+        losses.append(float(out["loss"].detach()))
+    assert losses[2] < losses[0]                                  # the same batch again after two updates
+    changed = [n for n, p in engine.module.named_parameters() if not torch.equal(p.detach(), before[n])]
+    assert {"lm_head.weight", "text_embedder.weight", "tts_tag_embedder.weight", "model.embeddings.weight"} <= set(changed)
+    save_checkpoint(engine, str(tmp_path / "ckpt"), 0, 3, logging.getLogger("t"))
+    capsys.readouterr()
+    saved = tmp_path / "ckpt" / "epoch_0_step_3"
+    assert (saved / "latest").exists() and any(f.name.startswith("mp_rank_00") for f in saved.rglob("*.pt"))
