@@ -111,13 +111,14 @@ def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
 def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.Tensor],
          mask: Optional[torch.Tensor] = None, mask_rwk: bool = True,
          shift_state: Optional[torch.Tensor] = None, wkv_state: Optional[torch.Tensor] = None,
-         need_state: bool = False, inplace_state: bool = False):
+         need_state: bool = False, inplace_state: bool = False, mask_kk: bool = True):
     """x [B,T,C] (bf16 on the GPU).  mask [B,T,1] of 0/1 or None.  Returns
     (out [B,T,C], v_first, new_shift_state [B,C] | None, new_wkv_state | None).  With `inplace_state` the
-    stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536)."""
+    stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536).  `mask_kk=False` is the
+    masking of the reference's inference-only `forward_batch` (rwkv_asr_cuda_whisper.py:184, :209: x and v only)."""
     B, T, C = x.shape
     H = C // HEAD
-    if FUSED and fused.usable(x):
+    if FUSED and fused.usable(x) and (mask is None or mask_kk):
         return _tmix_fused(p, layer_id, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state)
     if mask is not None:
         x = x * mask                                                            # :160
@@ -137,7 +138,8 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     g = torch.sigmoid(xg @ p.g1) @ p.g2                                         # :184
     kk = F.normalize((k * p.k_k).view(B, T, H, HEAD), dim=-1, p=2.0).view(B, T, C)   # :186-187
     if mask is not None:
-        kk = kk * mask                                                          # :188
+        if mask_kk:
+            kk = kk * mask                                                      # :188
         v = v * mask                                                            # :190
     k = k * (1 + (a - 1) * p.k_a)                                               # :189
     c = lambda t: t.to(torch.bfloat16).contiguous()

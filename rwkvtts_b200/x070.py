@@ -95,6 +95,20 @@ class RWKV_Tmix_x070(nn.Module):
         out, v_first, _, _ = core.tmix(self.params(), self.layer_id, x, v_first, mask=attention_mask)
         return out, v_first
 
+    @torch.inference_mode()
+    def forward_batch(self, x, attention_mask=None, v_first=None, x_prev=None, state=None):
+        """Stateful inference over a batch (/root/reference/model/llm/rwkv_asr_cuda_whisper.py:181-215): `x_prev` [B,C] is
+        the token-shift state, `state` fp32 [B,H,64,64] is advanced IN PLACE (RWKV7_BATCH_OP, :210).  Only x and v are
+        masked (:184, :209).  Returns (out, v_first, out[:, -1], state): the third value is the last row of the OUTPUT, as
+        in the reference (:215 returns `x[:,-1,:]` after `x` has been reassigned to the projection)."""
+        out, v_first, _, new_state = core.tmix(self.params(), self.layer_id, x, v_first, mask=attention_mask, mask_rwk=False,
+                                               mask_kk=False, shift_state=x_prev, wkv_state=state, need_state=True,
+                                               inplace_state=True)
+        if state is not None and new_state is not state:
+            state.copy_(new_state)
+            new_state = state
+        return out, v_first, out[:, -1, :], new_state
+
 
 class RWKV_CMix_x070(nn.Module):
     def __init__(self, args, layer_id):
@@ -115,6 +129,12 @@ class RWKV_CMix_x070(nn.Module):
 
     def forward(self, x, attention_mask):
         return core.cmix(self.x_k, self.key.weight, self.value.weight, x, mask=attention_mask)[0]
+
+    @torch.inference_mode()
+    def forward_batch(self, x, attention_mask=None, x_prev=None):
+        """rwkv_asr_cuda_whisper.py:277-285: returns (out, last masked input row = the next call's x_prev)."""
+        return core.cmix(self.x_k, self.key.weight, self.value.weight, x, mask=attention_mask, shift_state=x_prev,
+                         need_state=True)
 
 
 class Block(nn.Module):
@@ -138,6 +158,17 @@ class Block(nn.Module):
         x = x + x_attn
         x = x + self.ffn(self.ln2(x), attention_mask)
         return x, v_first
+
+    @torch.inference_mode()
+    def forward_batch(self, x, attention_mask=None, v_first=None, tx_prev=None, state=None, cx_prev=None):
+        """rwkv_asr_cuda_whisper.py:318-326."""
+        if self.layer_id == 0:
+            x = self.ln0(x)
+        x_attn, v_first, tx_prev, state = self.att.forward_batch(self.ln1(x), attention_mask, v_first, tx_prev, state)
+        x = x + x_attn
+        x_ffn, cx_prev = self.ffn.forward_batch(self.ln2(x), attention_mask, cx_prev)
+        x = x + x_ffn
+        return x, v_first, tx_prev, state, cx_prev
 
 
 class L2Wrap(torch.autograd.Function):
