@@ -1,7 +1,7 @@
 // SKETCH, NOT BUILT INTO THE LIBRARY, NEVER RUN ON A GPU (written after the round's GPU budget was spent; it only
 // has to compile: nvcc -c -I rwkvtts_b200/csrc proto/wkv7_tc_fwd_v2.cu).  Starting point for round 2.
 //
-// "Forward v2" of DESIGN.md section 7 (inference variant only): the shipped forward (csrc/wkv7_tc_fwd.cu) with
+// "Forward v2" of DESIGN.md section 7 (both variants): the shipped forward (csrc/wkv7_tc_fwd.cu) with
 //   * the U-form: phase 1 gives Z^T = S^ A~^T + V^T Aak^T (and Y^T), a new phase 1b applies the triangular factor on the
 //     tensor core, U^T = Z^T T^T, so W~ = T A~ and M1 = T Aak are never formed on the CUDA cores;
 //   * the four Gram blocks as ONE tcgen05 instruction chain per chunk, G[64 x 32] = [A~ ; Q~ ; - ; -] [B~ ; K~]^T
@@ -26,6 +26,7 @@ constexpr int NSLOT = 5;     // operand slots in flight
 constexpr float kMinLogDecay = -1.35f;
 // tensor-memory columns: S^ 0-63 | per chunk parity u: Z^T 64+48u, Y^T +16, U^T +32 | Gram blocks 160+32u (0-15: x B~, 16-31: x K~)
 constexpr uint32_t C_ZY = 64, C_ZY_STRIDE = 48, C_G = 160, kTmemCols = 256;
+constexpr uint32_t C_ST = 256, kTmemColsTrain = 512;   // training variant: transposed state S^T in columns 256-319
 constexpr float kLog2e = 1.4426950408889634f;   // decays are accumulated as log2 (ex2.approx needs no pre-scale)
 
 // canonical K-major tiles, strides in floats (see tc05.cuh: off = (r/8)*SBO + (k/4)*LBO + (r%8)*4 + k%4)
@@ -46,9 +47,10 @@ struct Smem {
     float NT[2][L * 20];                   // per Gram group: N^T, fp32, for the column solve
     float wtot[9][kC];                     // stage A scan: per-warp totals -> exclusive prefixes, chunk total
     __align__(16) bf16 ybuf[2][L][72];     // epilogue: Y tile [token][value], double buffered
+    __align__(16) float Ut[2][4 * T_LBO];  // training: U^T [value][token] operand tile of the transposed-state update
     float DLw[4][kC];                      // e^{G} at the end of a window (ring of 4 windows)
     uint64_t empty[NSLOT], full[NSLOT], a_done[NSLOT], g_ready[2];
-    uint64_t p_done, y_ready[2], y_free[2], win_scaled;
+    uint64_t p_done, y_ready[2], y_free[2], win_scaled, ut_ready, st_ready, st_free;
     uint32_t tmem_base;
 };
 
@@ -56,6 +58,9 @@ struct Params {
     int T, H;
     const bf16 *w, *q, *k, *v, *a, *b;
     bf16 *y;
+    float *ckT;          // training: TRANSPOSED state at the start of every chunk (window frame), operand tiles of 4096
+                         // floats per chunk (wkv7_common.cuh); null for the snapshot-free forward
+    float *sa;           // training: U_t = S_{t-1} a_t (tf32), operand tiles of 1024 floats per chunk
     const float *s0;     // may be null
     float *sT;           // may be null
     long long *dbg;      // phase-cycle counters (profiling builds only), may be null
@@ -302,6 +307,7 @@ __device__ __forceinline__ void issue_gram(Smem &sm, uint32_t tb, int c) {   // 
     mma_commit(&sm.g_ready[c & 1]);
 }
 
+template <bool kTrain>
 __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
     long long *P_dbg = (threadIdx.x & 31) == 0 ? P.dbg : nullptr; (void)P_dbg;
     const uint32_t tb = sm.tmem_base;
@@ -362,6 +368,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
         __syncwarp();
         mbar_wait(&sm.p_done, ph); ph ^= 1;
         TICK(tm4);
+        if (kTrain && c > 0) {
+            mbar_wait(&sm.ut_ready, (c - 1) & 1);                      // U^T tile of chunk c-1 is in shared memory
+            mbar_wait(&sm.st_free, (c - 1) & 1);                       // checkpoint c-1 has been read out of S^T
+        }
         fence_after_sync();
         if (elect_one()) {
             // phase 2: S^ += U^T B~ + V^T K~ ;  Y^T += U^T Aqb^T
@@ -376,8 +386,26 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
                 mma_tf32_ts(uy, uu + 8 * kk, dQB + (uint64_t)((kk * 2 * QB_LBO * 4) >> 4), I16, true);
-            mma_commit(&sm.empty[si]);
+            if (!kTrain) mma_commit(&sm.empty[si]);
             mma_commit(&sm.y_ready[u]);
+            if (kTrain && c > 0) {
+                // transposed state, one chunk behind: S^T += B~^T U + K~^T V of chunk c-1 (checkpoint of chunk c)
+                const Slot &Sp = sm.slot[(c - 1) % NSLOT];
+                const uint64_t pBt = smem_desc(smem_u32(Sp.Bt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pKt = smem_desc(smem_u32(Sp.Kt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pVt = smem_desc(smem_u32(Sp.Vt), T_LBO * 4, T_SBO * 4);
+                const uint64_t pUt = smem_desc(smem_u32(sm.Ut[(c - 1) & 1]), T_LBO * 4, T_SBO * 4);
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                    mma_tf32_ss(tb + C_ST, pBt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), pUt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4),
+                                I64, true);
+#pragma unroll
+                for (int kk = 0; kk < 2; kk++)
+                    mma_tf32_ss(tb + C_ST, pKt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4), pVt + (uint64_t)((kk * 2 * T_LBO * 4) >> 4),
+                                I64, true);
+                mma_commit(&sm.st_ready);
+                mma_commit(&sm.empty[(c - 1) % NSLOT]);
+            }
         }
         __syncwarp();
         mbar_wait(&sm.p_done, ph); ph ^= 1;
@@ -386,14 +414,18 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = value rows 16q..16q+15 of S^ and Y^T
+// epilogue group: warp q in [0,4) owns tensor-memory lanes 32q..32q+15 = value rows 16q..16q+15 of S^, U^T and Y^T.
+// Training variant (as shipped): U goes to HBM in the backward's operand layout and to a [value][token] shared tile for
+// the transposed-state update.
 // ---------------------------------------------------------------------------------------------
+template <bool kTrain>
 __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
     long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int q = tid >> 5, lane = tid & 31;
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
+    float *sag = kTrain ? P.sa + (size_t)bh * nC * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
     {   // initial state -> tensor memory
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
@@ -423,8 +455,9 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
         mbar_wait(&sm.y_ready[u], (c >> 1) & 1);
         TICK(te1);
         fence_after_sync();
-        float yv[16];
+        float yv[16], uv[16];
         tmem_ld16(tb + C_ZY + C_ZY_STRIDE * u + 16, yv);
+        if (kTrain) tmem_ld16(tb + C_ZY + C_ZY_STRIDE * u + 32, uv);
         tmem_wait_ld();
         if (win_end) {
             // state after this chunk, rescaled: the frame origin moves to the next window
@@ -453,6 +486,20 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
             if (act) {
 #pragma unroll
                 for (int j = 0; j < 16; j++) yb[j][row] = __float2bfloat16_rn(yv[j]);
+                if (kTrain) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) uv[j] = tf32r(uv[j]);
+                    float *ut = sm.Ut[u] + (row >> 3) * T_SBO + (row & 7) * 4;      // [value][token] operand tile
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st4(ut + i * T_LBO, uv[4 * i], uv[4 * i + 1], uv[4 * i + 2], uv[4 * i + 3]);
+                    float *sap = sag + (size_t)c * kUFloats;                         // [token][value] operand tile
+#pragma unroll
+                    for (int j = 0; j < 16; j++) sap[(j >> 3) * 32 + (j & 7) * 4] = uv[j];
+                }
+            }
+            if (kTrain) {
+                fence_proxy_async();
+                mbar_arrive_warp(&sm.ut_ready);
             }
             bar_sync(4, 128);
             const int tok = tid >> 3, part = tid & 7;
@@ -463,9 +510,66 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
     }
 }
 
-constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1);
+// ---------------------------------------------------------------------------------------------
+// checkpoint group (training variant only): warp q owns tensor-memory lanes 32q..32q+15 = KEY rows 16q..16q+15 of
+// the transposed state S^T.  After the MMA warp has added chunk c, S^T is the chunk-start checkpoint of chunk c+1:
+// 16-byte pieces of the backward's K-major operand tile, 256 contiguous bytes per warp store.
+// ---------------------------------------------------------------------------------------------
+__device__ void ckpt_group(const Params &P, Smem &sm, int bh, int nC, int tid) {
+    const int q = (tid >> 5) & 3, lane = tid & 31;
+    const bool act = lane < 16;
+    const int row = 16 * q + (lane & 15);
+    const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16) + C_ST;
+    float *ckg = P.ckT + (size_t)bh * nC * kCkFloats + (row >> 3) * 32 + (row & 7) * 4;   // key = row
+    auto store_ck = [&](const float (&v)[16], int cb, int cc) {
+        if (act) {
+            float *dst = ckg + (size_t)cc * kCkFloats + (4 * cb) * kCkLbo;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                *reinterpret_cast<float4 *>(dst + i * kCkLbo) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+    };
+#pragma unroll
+    for (int cb = 0; cb < 4; cb++) {   // S^T <- s0^T (or 0) = checkpoint 0
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            v[i] = (P.s0 != nullptr) ? P.s0[(size_t)bh * kC * kC + (16 * cb + i) * kC + row] : 0.f;
+        tmem_st16(tb + 16 * cb, v);
+        store_ck(v, cb, 0);
+    }
+    tmem_wait_st();
+    fence_before_sync();
+    mbar_arrive_warp(&sm.st_free);
+    for (int c = 0; c + 1 < nC; c++) {
+        const bool win_end = (c % WIN == WIN - 1);
+        mbar_wait(&sm.st_ready, c & 1);
+        fence_after_sync();
+        const float dr = win_end ? sm.DLw[(c / WIN) & 3][row] : 1.f;   // window end: rows move to the next window's frame
+        float v[4][16];
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) tmem_ld16(tb + 16 * cb, v[cb]);
+        tmem_wait_ld();
+        if (win_end) {
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[cb][i] *= dr;
+                tmem_st16(tb + 16 * cb, v[cb]);
+            }
+            tmem_wait_st();
+        }
+        fence_before_sync();
+        mbar_arrive_warp(&sm.st_free);
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) store_ck(v[cb], cb, c + 1);
+    }
+}
 
-__global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_v2_kernel(const Params P) {
+constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1), kThreadsTrain = kThreads + 128;
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_v2_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
@@ -473,43 +577,53 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_fwd_v2_kernel(const Param
     const int nC = P.T / L;
     const size_t tok_stride = (size_t)P.H * kC;
     const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
+    constexpr uint32_t kCols = kTrain ? kTmemColsTrain : kTmemCols;
 
     if (tid == 0) {
         for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.empty[i], 1); mbar_init(&sm.full[i], 2); mbar_init(&sm.a_done[i], 8); }
         mbar_init(&sm.p_done, 1);
         for (int i = 0; i < 2; i++) { mbar_init(&sm.y_ready[i], 1); mbar_init(&sm.y_free[i], 4); mbar_init(&sm.g_ready[i], 1); }
-        mbar_init(&sm.win_scaled, 4);
+        mbar_init(&sm.win_scaled, 4); mbar_init(&sm.ut_ready, 4); mbar_init(&sm.st_ready, 1); mbar_init(&sm.st_free, 4);
         mbar_fence_init();
     }
-    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, kCols);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
 
     // tensor-memory lane quadrants follow warp % 4: the Gram groups need one warp on lanes 0-31 and one on lanes 32-63
-    if (warp < 4) epilogue(P, sm, base, tok_stride, bh, nC, tid);
+    if (warp < 4) epilogue<kTrain>(P, sm, base, tok_stride, bh, nC, tid);
     else if (warp < 12) stage_a(P, sm, base, tok_stride, nC, tid - 128);
     else if (warp == 12 || warp == 13) stage_g(P, sm, nC, tid - 384, 0);
     else if (warp == 16 || warp == 17) stage_g(P, sm, nC, tid - 512, 1);
-    else if (warp == kMmaWarp) mma_warp(P, sm, nC);
+    else if (warp == kMmaWarp) mma_warp<kTrain>(P, sm, nC);
+    else if (kTrain && warp > kMmaWarp) ckpt_group(P, sm, bh, nC, tid);
     // warps 14, 15, 18, 19 only keep the warp numbering aligned (to be dropped with a renumbering)
 
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, kTmemCols);
+    if (warp == kMmaWarp) tmem_dealloc(sm.tmem_base, kCols);
 }
 
 }  // namespace tcfwd2
 
+// ckT == nullptr: snapshot-free forward; otherwise the training forward (same scratch contract as launch_tc_fwd)
 cudaError_t launch_tc_fwd_v2(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                             const void *a, const void *b, void *y, const float *s0, float *sT, cudaStream_t st) {
+                             const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
+                             cudaStream_t st) {
     using namespace tcfwd2;
     static_assert(sizeof(Smem) <= 232448, "shared memory budget");
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
-             (const bf16 *)b, (bf16 *)y, s0, sT, nullptr};
-    cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    if (e != cudaSuccess) return e;
-    wkv7_tc_fwd_v2_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+             (const bf16 *)b, (bf16 *)y, ckT, sa, s0, sT, nullptr};
+    if (ckT != nullptr) {
+        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        wkv7_tc_fwd_v2_kernel<true><<<dim3(B * H), dim3(kThreadsTrain), sizeof(Smem), st>>>(P);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return e;
+        wkv7_tc_fwd_v2_kernel<false><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    }
     return cudaGetLastError();
 }
 

@@ -32,12 +32,13 @@ def main():
     from rwkvtts_b200 import ops
     lib = ctypes.CDLL(LIB)
     lib.fwd_v2.restype = ctypes.c_int
-    lib.fwd_v2.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 10
+    lib.fwd_v2.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 12
     ORDER = "wqkvab"
 
-    def fwd(d, y, s0=None, sT=None):
+    def fwd(d, y, s0=None, sT=None, ck=None, sa=None):
         B, T, H, _ = d["w"].shape
         rc = lib.fwd_v2(B, T, H, *[d[n].data_ptr() for n in ORDER], y.data_ptr(),
+                        None if ck is None else ck.data_ptr(), None if sa is None else sa.data_ptr(),
                         None if s0 is None else s0.data_ptr(), None if sT is None else sT.data_ptr(),
                         torch.cuda.current_stream().cuda_stream)
         assert rc == 0, f"launch failed: cudaError {rc}"
@@ -58,6 +59,26 @@ def main():
               f"sT rel {O.rel_l2(sT.cpu(), sT64):.2e}; nan={bool(torch.isnan(y.float()).any())}", flush=True)
         worst = max(worst, exc)
     print("worst excess", worst, "(bar 1e-3)")
+
+    # training variant: its checkpoints and `sa` must drive the SHIPPED backward to the oracle's gradients
+    import rwkvtts_b200 as R
+    for (B, T, H) in [(1, 64, 1), (2, 208, 2), (1, 1024, 4)]:
+        x = O.make_inputs(B, T, H, seed=7 * B + T)
+        d = {n: t.cuda() for n, t in x.items()}
+        y = torch.empty_like(d["v"])
+        ck = torch.empty(B, H, T // 16, 64, 64, dtype=torch.float32, device="cuda")
+        sa = torch.empty(B, T, H, 64, dtype=torch.float32, device="cuda")
+        fwd(d, y, ck=ck, sa=sa)
+        grads = [torch.empty_like(d["v"]) for _ in range(6)]
+        R.wkv7_backward_(*[d[n] for n in ORDER], d["dy"], ck, sa, *grads)
+        torch.cuda.synchronize()
+        g64 = O.wkv7_backward(*[x[n] for n in ORDER], x["dy"])
+        y64 = O.wkv7_forward(*[x[n] for n in ORDER])
+        y64 = y64[0] if isinstance(y64, tuple) else y64
+        errs = {"y": O.excess_rel_l2(y.cpu(), y64)[0]}
+        for i, n in enumerate(ORDER):
+            errs["d" + n] = O.excess_rel_l2(grads[i].cpu(), g64[i])[0]
+        print(f"v2 training B{B} T{T} H{H}: " + "  ".join(f"{n} {e:.1e}" for n, e in errs.items()), flush=True)
 
     B, T, H = 8, 4096, 16
     xs = O.make_inputs(1, T, H, seed=3)
