@@ -1,0 +1,155 @@
+"""Index-level emulation of the forward-v2 sketch (proto/wkv7_tc_fwd_v2.cu) on the CPU: every shared-memory tile is a
+flat float array written and read with the SAME offset expressions as the .cu file, tensor memory is a [64 rows][256
+columns] array, and each tcgen05 instruction chain is modelled as D[m][n] (+)= sum_k A[m][k] * B[n][k] with K-major
+canonical operands (tc05.cuh).  Products are exact fp32 -> f64 here (no tf32 rounding), so any disagreement with the f64
+oracle beyond ~1e-6 is an indexing / orientation / masking / window-frame mistake in the sketch, not numerics.
+What it cannot check: barriers, proxy fences, tensor-memory lane quadrants, instruction descriptors."""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import wkv7_oracle as O  # noqa: E402
+
+L, WIN, kC = 16, 4, 64
+WQ_LBO, WQ_SBO = 132, 32
+T_SBO, T_LBO = 36, 288
+MA_LBO, MA_SBO = 132, 32
+QB_LBO, QB_SBO = 64, 32
+C_ZY, C_ZY_STRIDE, C_G = 64, 48, 160
+kMinLogDecay = -1.35
+
+
+def kmajor_off(r, k, lbo, sbo):
+    return (r >> 3) * sbo + (k >> 2) * lbo + (r & 7) * 4 + (k & 3)
+
+
+class Slot:
+    def __init__(self):
+        self.WQ = np.full(16 * WQ_LBO, np.nan); self.BK = np.full(16 * WQ_LBO, np.nan)
+        self.Bt = np.full(4 * T_LBO, np.nan); self.Kt = np.full(4 * T_LBO, np.nan); self.Vt = np.full(4 * T_LBO, np.nan)
+        self.MA = np.full(4 * MA_LBO, np.nan); self.Aqb = np.full(4 * QB_LBO, np.nan); self.Tt = np.full(4 * QB_LBO, np.nan)
+
+
+def smem_operand(tile, rows, K, lbo, sbo):
+    """what the tensor core reads: X[r][k] for r < rows, k < K"""
+    return np.array([[tile[kmajor_off(r, k, lbo, sbo)] for k in range(K)] for r in range(rows)])
+
+
+def stage_a(S, w, q, k, v, a, b, gpre):
+    """one chunk; inputs [16][64] float64 (bf16 values); gpre = log2 decay accumulated since the window start.  Returns
+    the chunk total (for the next chunk's gpre) and e^{G} of the last token (DLw)."""
+    lw = np.maximum(-np.exp(w), kMinLogDecay)                  # natural log here; the kernel works in log2, same values
+    gg = np.cumsum(lw, 0) + gpre
+    D, Dp, iD = np.exp(gg), np.exp(gg - lw), np.exp(-gg)
+    for tp in range(256):
+        t, k4 = tp >> 4, tp & 15
+        ch = slice(4 * k4, 4 * k4 + 4)
+        oa = (t >> 3) * WQ_SBO + k4 * WQ_LBO + (t & 7) * 4
+        oq = oa + 2 * WQ_SBO
+        ot = (k4 >> 1) * T_SBO + (t >> 2) * T_LBO + (k4 & 1) * 16 + (t & 3)
+        S.WQ[oq:oq + 4] = q[t, ch] * D[t, ch]
+        o = k[t, ch] * iD[t, ch]
+        S.BK[oq:oq + 4] = o
+        for j in range(4):
+            S.Kt[ot + 4 * j] = o[j]
+            S.Vt[ot + 4 * j] = v[t, 4 * k4 + j]
+        S.WQ[oa:oa + 4] = a[t, ch] * Dp[t, ch]
+        o = b[t, ch] * iD[t, ch]
+        S.BK[oa:oa + 4] = o
+        for j in range(4):
+            S.Bt[ot + 4 * j] = o[j]
+    return gg[-1], D[-1]
+
+
+def stage_g(S, tm, u):
+    NT = np.zeros(16 * 20)
+    for wq in range(2):
+        for row in range(16):
+            g = tm[16 * wq + row, C_G + 32 * u:C_G + 32 * u + 32]      # lanes 0-15 (wq = 0) / 32-47 (wq = 1) = rows 0-15 / 16-31
+            gb, gk = g[:16].copy(), g[16:].copy()
+            if wq == 0:
+                for s_ in range(16):
+                    NT[s_ * 20 + row] = gb[s_] if s_ < row else 0.0
+                    gk[s_] = gk[s_] if s_ < row else 0.0
+                for j in range(4):
+                    o = kmajor_off(row, 4 * j, MA_LBO, MA_SBO)
+                    S.MA[o:o + 4] = gk[4 * j:4 * j + 4]
+            else:
+                for s_ in range(16):
+                    gb[s_] = gb[s_] if s_ <= row else 0.0
+                    gk[s_] = gk[s_] if s_ <= row else 0.0
+                for j in range(4):
+                    o = kmajor_off(row, 4 * j, QB_LBO, QB_SBO)
+                    S.Aqb[o:o + 4] = gb[4 * j:4 * j + 4]
+                    o = kmajor_off(16 + row, 4 * j, MA_LBO, MA_SBO)
+                    S.MA[o:o + 4] = gk[4 * j:4 * j + 4]
+    for col in range(16):
+        acc = [1.0 if tt == col else 0.0 for tt in range(L)]
+        for s_ in range(L - 1):
+            x = acc[s_]
+            for q4 in range((s_ + 1) // 4, 4):
+                nn = NT[s_ * 20 + 4 * q4:s_ * 20 + 4 * q4 + 4]
+                for e in range(4):
+                    if 4 * q4 + e > s_:
+                        acc[4 * q4 + e] += nn[e] * x
+        for tt in range(L):
+            S.Tt[kmajor_off(tt, col, QB_LBO, QB_SBO)] = acc[tt]
+
+
+def forward(w, q, k, v, a, b, s0=None):
+    """one (batch, head): inputs [T][64]; returns y [T][64], S_T [64][64] value-major"""
+    T = w.shape[0]
+    nC = T // L
+    tm = np.zeros((64, 256))
+    if s0 is not None:
+        tm[:, 0:64] = s0
+    slots = [Slot() for _ in range(nC)]          # the ring is not modelled (barriers are out of scope)
+    gpre, DL = np.zeros(kC), [None] * nC
+    for c in range(nC):
+        sl = slice(c * L, (c + 1) * L)
+        tot, dl = stage_a(slots[c], w[sl], q[sl], k[sl], v[sl], a[sl], b[sl], gpre)
+        win_end = (c % WIN == WIN - 1) or (c == nC - 1)
+        gpre = np.zeros(kC) if win_end else tot
+        DL[c] = dl
+    y = np.zeros((T, kC))
+    for c in range(nC):
+        S, u = slots[c], c & 1
+        uz = C_ZY + C_ZY_STRIDE * u
+        uy, uu = uz + 16, uz + 32
+        # Gram instruction: A = WQ (M = 64, rows 0-31 live), B = BK (N = 32), K = 64
+        A, B = smem_operand(S.WQ, 32, 64, WQ_LBO, WQ_SBO), smem_operand(S.BK, 32, 64, WQ_LBO, WQ_SBO)
+        tm[0:32, C_G + 32 * u:C_G + 32 * u + 32] = A @ B.T
+        stage_g(S, tm, u)
+        # phase 1: [Z^T | Y^T] = S^ [A~ | Q~]^T + V^T [Aak | Aqk]^T
+        Sst = tm[:, 0:64].copy()
+        tm[:, uz:uz + 32] = Sst @ smem_operand(S.WQ, 32, 64, WQ_LBO, WQ_SBO).T \
+            + smem_operand(S.Vt, 64, 16, T_LBO, T_SBO) @ smem_operand(S.MA, 32, 16, MA_LBO, MA_SBO).T
+        # phase 1b: U^T = Z^T T^T   (A = tensor-memory columns uz .. uz+15, B = Tt [n = t][k = s])
+        tm[:, uu:uu + 16] = tm[:, uz:uz + 16] @ smem_operand(S.Tt, 16, 16, QB_LBO, QB_SBO).T
+        # phase 2: S^ += U^T B~ + V^T K~ ;  Y^T += U^T Aqb^T
+        Ut = tm[:, uu:uu + 16].copy()
+        tm[:, 0:64] += Ut @ smem_operand(S.Bt, 64, 16, T_LBO, T_SBO).T \
+            + smem_operand(S.Vt, 64, 16, T_LBO, T_SBO) @ smem_operand(S.Kt, 64, 16, T_LBO, T_SBO).T
+        tm[:, uy:uy + 16] += Ut @ smem_operand(S.Aqb, 16, 16, QB_LBO, QB_SBO).T
+        # epilogue
+        y[c * L:(c + 1) * L] = tm[:, uy:uy + 16].T
+        if (c % WIN == WIN - 1) or (c == nC - 1):
+            tm[:, 0:64] *= DL[c][None, :]
+    return y, tm[:, 0:64].copy()
+
+
+if __name__ == "__main__":
+    x = O.make_inputs(1, 208, 2, seed=5)          # 13 chunks: full windows and a ragged last one
+    names = "wqkvab"
+    s0 = torch.randn(1, 2, 64, 64, dtype=torch.float64) * 0.1
+    y64, sT64 = O.wkv7_forward(*[x[n] for n in names], s0=s0)
+    for h in range(2):
+        y, sT = forward(*[x[n][0, :, h].double().numpy() for n in names], s0=s0[0, h].numpy())
+        ey = float(np.linalg.norm(y - y64[0, :, h].numpy()) / np.linalg.norm(y64[0, :, h].numpy()))
+        es = float(np.linalg.norm(sT - sT64[0, h].numpy()) / np.linalg.norm(sT64[0, h].numpy()))
+        print(f"head {h}: y rel-l2 {ey:.2e}   S_T rel-l2 {es:.2e}   nan in y: {bool(np.isnan(y).any())}")

@@ -11,7 +11,9 @@
 //   * a Gram group of two warps per parity (warp % 4 == 0 reads lanes 0-15 = N | Aak, warp % 4 == 1 reads lanes 32-47 =
 //     Aqb | Aqk): mask, round, 16-byte operand-tile stores, and the column solve of T only (16 identity columns).
 // Expected shared-memory wavefronts per chunk ~650 against 1455 (profiles/r01_tc_pair_smem_lines_v5.txt); numerics of the
-// form: proto/uform_numerics_proto.py.  Everything not mentioned is the shipped kernel's code.
+// form: proto/uform_numerics_proto.py; tile offsets, operand orientations, masks, tensor-memory columns and window frames
+// of THIS file replayed on the CPU against the f64 oracle: proto/fwd_v2_index_emulator.py (1e-15).  Not checked by
+// anything: barriers, proxy fences, lane quadrants, descriptors.  Everything not mentioned is the shipped kernel's code.
 #include "mma_tf32.cuh"
 #include "tc05.cuh"
 #include "wkv7_common.cuh"
