@@ -1,7 +1,8 @@
 """Model check of the forward-v2 sketch's synchronisation (proto/wkv7_tc_fwd_v2.cu, inference variant): the warp roles are
 coroutines that execute the kernel's mbarrier waits / arrivals / commits in program order, the tensor pipe is an in-order
 queue whose commits arrive when everything issued before them has executed, and a random scheduler interleaves them.
-Every access carries an assertion about WHAT it must find (which chunk's data a tile / tensor-memory buffer holds, and
+Both variants (the training one adds the U^T tile hand-off, the lagged transposed-state update and the checkpoint
+group).  Every access carries an assertion about WHAT it must find (which chunk's data a tile / tensor-memory buffer holds, and
 that its previous contents have been consumed), so the run fails on a lost hand-off, an overwrite-before-read, a wrong
 parity or a deadlock.  Barrier counts, parities and the issue order are transcribed from the .cu file.
 `--mutations` seeds known protocol bugs into a copy of the model and reports which ones it catches (its sensitivity).
@@ -29,8 +30,13 @@ class Bar:
 
 
 class Kernel:
-    def __init__(self, nC):
-        self.nC = nC
+    def __init__(self, nC, train=False):
+        self.nC, self.train = nC, train
+        self.ut_ready, self.st_ready, self.st_free = Bar(4), Bar(1), Bar(4)
+        self.Ut = [-1, -1]                  # chunk whose U^T tile is in shared memory
+        self.Ut_read = [-1, -1]
+        self.ST = 0                         # chunks accumulated into the transposed state
+        self.ck_out = 0                     # checkpoints read out of S^T (checkpoint 0 = initial state)
         self.empty = [Bar(1) for _ in range(NSLOT)]
         self.full = [Bar(2) for _ in range(NSLOT)]
         self.a_done = [Bar(8) for _ in range(NSLOT)]
@@ -83,6 +89,12 @@ class Kernel:
             assert self.U[u] == c and self.Y[u] == (c, "partial") and self.slot_g[si] == c
             self.Y[u] = c
             self.slot_reads_left[si] -= 1
+        elif kind == "st":                  # S^T += B~^T U + K~^T V of chunk c (issued in iteration c + 1)
+            assert self.slot_a[si] == c and self.Ut[u] == c, ("st", c, self.slot_a[si], self.Ut[u])
+            assert self.ST == c and self.ck_out == c + 1, ("st overwrites checkpoint", self.ST, self.ck_out, c)
+            self.ST = c + 1
+            self.Ut_read[u] = c
+            self.slot_reads_left[si] -= 1
 
     # ---- roles (generators yield a predicate to wait on, or None to just yield the processor) --------------
     def stage_a(self):
@@ -93,7 +105,7 @@ class Kernel:
             assert self.slot_reads_left[si] == 0, ("stage A overwrites a slot still being read", c)
             assert self.slot_g[si] in (-1, c - NSLOT), ("slot", si, "holds Gram tiles of", self.slot_g[si])
             self.slot_a[si] = c
-            self.slot_reads_left[si] = 5          # gram, p1, p1b, p2s, p2y
+            self.slot_reads_left[si] = 5 + (1 if self.train and c + 1 < self.nC else 0)   # gram, p1, p1b, p2s, p2y (+ st)
             yield None
             self.a_done[si].arrive(8)
 
@@ -131,8 +143,15 @@ class Kernel:
             self.pipe += [("p1b", c), ("commit", c, self.p_done)]
             yield lambda ph=ph: self.p_done.done(ph)
             ph ^= 1
-            self.pipe += [("p2s", c), ("commit", c, self.p_done), ("p2y", c), ("commit", c, self.empty[si]),
-                          ("commit", c, self.y_ready[u])]
+            if self.train and c > 0:
+                yield lambda: self.ut_ready.done((c - 1) & 1)
+                yield lambda: self.st_free.done((c - 1) & 1)
+            self.pipe += [("p2s", c), ("commit", c, self.p_done), ("p2y", c)]
+            if not self.train:
+                self.pipe += [("commit", c, self.empty[si])]
+            self.pipe += [("commit", c, self.y_ready[u])]
+            if self.train and c > 0:
+                self.pipe += [("st", c - 1), ("commit", c, self.st_ready), ("commit", c, self.empty[(c - 1) % NSLOT])]
             yield lambda ph=ph: self.p_done.done(ph)
             ph ^= 1
 
@@ -147,6 +166,7 @@ class Kernel:
             yield lambda: self.y_ready[u].done((c >> 1) & 1)
             assert self.Y[u] == c, ("epilogue reads Y of", self.Y[u], "for", c)
             self.Y_read[u] = c
+            assert self.U[u] == c
             if win_end:
                 assert self.S == c + 1, ("window-end rescale sees", self.S, "chunks at", c)
                 if not last:
@@ -155,13 +175,31 @@ class Kernel:
             self.y_free[u].arrive(4)
             if win_end:
                 self.win_scaled.arrive(4)
+            if self.train:
+                assert self.Ut_read[u] == self.Ut[u], ("epilogue overwrites an unread U^T tile", self.Ut[u])
+                self.Ut[u] = c
+                yield None
+                self.ut_ready.arrive(4)
             self.y_out += 1
 
+    def ckpt_group(self):
+        self.ck_out = 1                             # checkpoint 0 = the initial state
+        yield None
+        self.st_free.arrive(4)
+        for c in range(self.nC - 1):
+            yield lambda c=c: self.st_ready.done(c & 1)
+            assert self.ST == c + 1, ("checkpoint", c + 1, "reads S^T after", self.ST, "chunks")
+            self.ck_out = c + 2
+            yield None
+            self.st_free.arrive(4)
 
-def run(nC, seed):
+
+def run(nC, seed, train=False):
     rng = random.Random(seed)
-    k = Kernel(nC)
+    k = Kernel(nC, train)
     roles = {"A": k.stage_a(), "G0": k.gram_group(0), "G1": k.gram_group(1), "M": k.mma_warp(), "E": k.epilogue()}
+    if train:
+        roles["C"] = k.ckpt_group()
     waiting = {n: None for n in roles}
     alive = set(roles)
     steps = 0
@@ -183,7 +221,7 @@ def run(nC, seed):
             except StopIteration:
                 alive.discard(n)
         steps += 1
-    assert k.y_out == nC and k.S == nC
+    assert k.y_out == nC and k.S == nC and (not train or (k.ck_out == nC and k.ST == nC - 1))
     return steps
 
 
@@ -199,7 +237,11 @@ MUTATIONS = [
     ("g_ready parity off by one", "self.g_ready[grp].done((c >> 1) & 1)", "self.g_ready[grp].done(((c >> 1) + 1) & 1)"),
     ("no a_done wait for chunk c+2",
      "            if c + 2 < self.nC:\n                yield lambda: self.a_done[(c + 2) % NSLOT].done(((c + 2) // NSLOT) & 1)\n", ""),
-    ("slot never released", '("p2y", c), ("commit", c, self.empty[si]),', '("p2y", c),'),
+    ("slot never released (inference)", '                self.pipe += [("commit", c, self.empty[si])]\n', "                pass\n"),
+    ("training: no st_free wait", "                yield lambda: self.st_free.done((c - 1) & 1)\n", ""),
+    ("training: no ut_ready wait", "                yield lambda: self.ut_ready.done((c - 1) & 1)\n", ""),
+    ("training: slot released in phase 2 as in inference", "            if not self.train:\n                self.pipe += [(\"commit\", c, self.empty[si])]\n",
+     "            self.pipe += [(\"commit\", c, self.empty[si])]\n"),
 ]
 
 
@@ -215,6 +257,7 @@ def mutations():
             for nC in (4, 7, 13):
                 for seed in range(200):
                     ns["run"](nC, seed)
+                    ns["run"](nC, seed, train=True)
         except AssertionError as e:
             caught = str(e)[:100]
         print(f"  {name:46s} {'caught: ' + caught if caught else 'NOT caught'}")
@@ -227,5 +270,5 @@ if __name__ == "__main__":
     total = 0
     for nC in (1, 2, 3, 4, 5, 6, 7, 9, 13, 16, 23, 64):
         for seed in range(300 if nC < 30 else 40):
-            total += run(nC, seed)
+            total += run(nC, seed) + run(nC, seed, train=True)
     print("forward-v2 synchronisation model: no deadlock, no hazard over", total, "scheduled steps")

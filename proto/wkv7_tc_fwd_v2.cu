@@ -13,7 +13,7 @@
 // Expected shared-memory wavefronts per chunk ~650 against 1455 (profiles/r01_tc_pair_smem_lines_v5.txt); numerics of the
 // form: proto/uform_numerics_proto.py; tile offsets, operand orientations, masks, tensor-memory columns and window frames
 // of THIS file replayed on the CPU against the f64 oracle: proto/fwd_v2_index_emulator.py (1e-15); mbarrier protocol
-// (counts, parities, issue order of the inference variant) model-checked in proto/fwd_v2_sync_model.py.  Not checked by
+// (counts, parities, issue order, both variants) model-checked in proto/fwd_v2_sync_model.py.  Not checked by
 // anything: proxy / tcgen05 fences, lane quadrants, descriptors, the different-accumulator ordering rule.  Everything not mentioned is the shipped kernel's code.
 #include "mma_tf32.cuh"
 #include "tc05.cuh"
