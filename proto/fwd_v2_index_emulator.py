@@ -40,30 +40,92 @@ def smem_operand(tile, rows, K, lbo, sbo):
     return np.array([[tile[kmajor_off(r, k, lbo, sbo)] for k in range(K)] for r in range(rows)])
 
 
+WAVES = {"st4": [0, 0], "scalar": [0, 0]}       # [warp instructions, wavefronts] of stage A's tile stores
+
+
+def _count(kind, word_addrs, width):
+    """shared-memory wavefronts of one warp store instruction: `width` consecutive 32-bit words per lane; 32 banks;
+    128-bit accesses are served a quarter-warp at a time, 64-bit a half-warp, 32-bit the whole warp"""
+    per = {1: 32, 2: 16, 4: 8}[width]
+    waves = 0
+    for g0 in range(0, 32, per):
+        banks = {}
+        for a0 in word_addrs[g0:g0 + per]:
+            for wd in range(width):
+                banks.setdefault((a0 + wd) % 32, set()).add(a0 + wd)
+        waves += max(len(v) for v in banks.values())
+    WAVES[kind][0] += 1
+    WAVES[kind][1] += waves
+
+
 def stage_a(S, w, q, k, v, a, b, gpre):
-    """one chunk; inputs [16][64] float64 (bf16 values); gpre = log2 decay accumulated since the window start.  Returns
-    the chunk total (for the next chunk's gpre) and e^{G} of the last token (DLw)."""
-    lw = np.maximum(-np.exp(w), kMinLogDecay)                  # natural log here; the kernel works in log2, same values
-    gg = np.cumsum(lw, 0) + gpre
-    D, Dp, iD = np.exp(gg), np.exp(gg - lw), np.exp(-gg)
+    """one chunk, thread by thread as in the .cu file: 256 threads, lane = (t & 3) * 8 + (k4 & 7), warp = (t >> 2) * 2 +
+    (k4 >> 3); the decay scan with its two warp shuffles and the two-stage cross-warp prefix; every tile store with the
+    file's offset expression (and its bank conflicts counted).  Inputs [16][64] float64; gpre [64] = log decay
+    accumulated since the window start.  Returns the chunk total and e^{G} of the last token (DLw)."""
+    T_ = np.zeros(256, dtype=int); K4 = np.zeros(256, dtype=int)
+    gg = np.zeros((256, 4)); lw = np.zeros((256, 4))
     for tp in range(256):
-        t, k4 = tp >> 4, tp & 15
-        ch = slice(4 * k4, 4 * k4 + 4)
-        oa = (t >> 3) * WQ_SBO + k4 * WQ_LBO + (t & 7) * 4
-        oq = oa + 2 * WQ_SBO
-        ot = (k4 >> 1) * T_SBO + (t >> 2) * T_LBO + (k4 & 1) * 16 + (t & 3)
-        S.WQ[oq:oq + 4] = q[t, ch] * D[t, ch]
-        o = k[t, ch] * iD[t, ch]
-        S.BK[oq:oq + 4] = o
+        wp, lane = tp >> 5, tp & 31
+        tt, tg = lane >> 3, wp >> 1
+        T_[tp], K4[tp] = 4 * tg + tt, 8 * (wp & 1) + (lane & 7)
+        lw[tp] = np.maximum(-np.exp(w[T_[tp], 4 * K4[tp]:4 * K4[tp] + 4]), kMinLogDecay)
+        gg[tp] = lw[tp]
+
+    def shfl_up(x, delta):
+        y = x.copy()
+        for tp in range(256):
+            if (tp & 31) >= delta:
+                y[tp] = x[tp - delta]
+        return y
+    for delta, need in ((8, 1), (16, 2)):
+        x = shfl_up(gg, delta)
+        for tp in range(256):
+            if ((tp & 31) >> 3) >= need:
+                gg[tp] += x[tp]
+    wt = np.full((9, kC), np.nan)
+    for tp in range(256):
+        if ((tp & 31) >> 3) == 3:
+            wt[(tp >> 5) >> 1, 4 * K4[tp]:4 * K4[tp] + 4] = gg[tp]
+    for ch in range(kC):                                   # threads tp < 64
+        run = 0.0
+        for ww in range(4):
+            x = wt[ww, ch]; wt[ww, ch] = run; run += x
+        wt[4, ch] = run
+    tot = np.zeros(kC)
+    for tp in range(256):
+        tg, ch = (tp >> 5) >> 1, slice(4 * K4[tp], 4 * K4[tp] + 4)
+        gg[tp] += gpre[ch] + wt[tg, ch]
+        tot[ch] = gpre[ch] + wt[4, ch]
+    D, Dp, iD = np.exp(gg), np.exp(gg - lw), np.exp(-gg)
+    dl = np.zeros(kC)
+    for wp in range(8):                                    # one warp instruction at a time, for the conflict count
+        tps = range(32 * wp, 32 * wp + 32)
+        oa = [(T_[tp] >> 3) * WQ_SBO + K4[tp] * WQ_LBO + (T_[tp] & 7) * 4 for tp in tps]
+        oq = [o + 2 * WQ_SBO for o in oa]
+        ot = [(K4[tp] >> 1) * T_SBO + (T_[tp] >> 2) * T_LBO + (K4[tp] & 1) * 16 + (T_[tp] & 3) for tp in tps]
+        for _ in range(2):
+            _count("st4", oq, 4); _count("st4", oa, 4)   # WQ and BK, rows t and 16 + t
         for j in range(4):
-            S.Kt[ot + 4 * j] = o[j]
-            S.Vt[ot + 4 * j] = v[t, 4 * k4 + j]
-        S.WQ[oa:oa + 4] = a[t, ch] * Dp[t, ch]
-        o = b[t, ch] * iD[t, ch]
-        S.BK[oa:oa + 4] = o
-        for j in range(4):
-            S.Bt[ot + 4 * j] = o[j]
-    return gg[-1], D[-1]
+            for _ in range(3):
+                _count("scalar", [o + 4 * j for o in ot], 1)   # Kt, Vt, Bt
+        for i, tp in enumerate(tps):
+            t, k4 = T_[tp], K4[tp]
+            ch = slice(4 * k4, 4 * k4 + 4)
+            S.WQ[oq[i]:oq[i] + 4] = q[t, ch] * D[tp]
+            o = k[t, ch] * iD[tp]
+            S.BK[oq[i]:oq[i] + 4] = o
+            for j in range(4):
+                S.Kt[ot[i] + 4 * j] = o[j]
+                S.Vt[ot[i] + 4 * j] = v[t, 4 * k4 + j]
+            S.WQ[oa[i]:oa[i] + 4] = a[t, ch] * Dp[tp]
+            o = b[t, ch] * iD[tp]
+            S.BK[oa[i]:oa[i] + 4] = o
+            for j in range(4):
+                S.Bt[ot[i] + 4 * j] = o[j]
+            if t == L - 1:
+                dl[ch] = D[tp]
+    return tot, dl
 
 
 def stage_g(S, tm, u):
@@ -153,3 +215,5 @@ if __name__ == "__main__":
         ey = float(np.linalg.norm(y - y64[0, :, h].numpy()) / np.linalg.norm(y64[0, :, h].numpy()))
         es = float(np.linalg.norm(sT - sT64[0, h].numpy()) / np.linalg.norm(sT64[0, h].numpy()))
         print(f"head {h}: y rel-l2 {ey:.2e}   S_T rel-l2 {es:.2e}   nan in y: {bool(np.isnan(y).any())}")
+    for kind, (n, wv) in WAVES.items():
+        print(f"stage A {kind} tile stores: {wv / n:.2f} wavefronts per warp instruction (1.00 = conflict-free; 16-byte stores: 4.00)")

@@ -82,7 +82,11 @@ __device__ __forceinline__ void st4(float *p, float a, float b, float c, float d
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage A: tp in [0,256); token t = tp>>4, channels 4*k4 .. 4*k4+3; warp wp holds tokens 2wp, 2wp+1
+// stage A: tp in [0,256).  A warp holds 4 tokens x 8 channel groups (the shipped kernel: 2 tokens x 16 groups), lane =
+// (t & 3) * 8 + (k4 & 7), warp = (t >> 2) * 2 + (k4 >> 3): a scalar store into a transposed [channel][token] tile then covers
+// all four token columns of 8 core-matrix rows = 32 different banks (2 x 16 covers 16 banks twice: 192 instead of 96
+// wavefronts per chunk, profiles/r01_tc_pair_smem_lines_v5.txt), and the 16-byte row stores stay one quarter-warp per
+// 128-byte row piece.  Thread = token t, channels 4*k4 .. 4*k4+3.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
     uint2 r;
@@ -92,9 +96,8 @@ __device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
 __device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
 }
-__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int tp,
+__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int t, int k4,
                                          uint2 (&raw)[6]) {
-    const int t = tp >> 4, k4 = tp & 15;
     const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
     raw[0] = ldg_nc_v2(P.w + off);
     raw[1] = ldg_nc_v2(P.q + off);
@@ -106,17 +109,18 @@ __device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t to
 
 __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int nC, int tp) {
     long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
-    const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
+    const int wp = tp >> 5, lane = tp & 31, tt = lane >> 3, tg = wp >> 1;
+    const int t = 4 * tg + tt, k4 = 8 * (wp & 1) + (lane & 7);
     uint2 raw[6], nxt[6], nx2[6];
     float gpre[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) gpre[j] = 0.f;
-    load_raw(P, base, tok_stride, 0, tp, raw);
-    if (nC > 1) load_raw(P, base, tok_stride, 1, tp, nxt);
+    load_raw(P, base, tok_stride, 0, t, k4, raw);
+    if (nC > 1) load_raw(P, base, tok_stride, 1, t, k4, nxt);
     for (int c = 0; c < nC; c++) {
         const int si = c % NSLOT;
         Slot &S = sm.slot[si];
-        if (c + 2 < nC) load_raw(P, base, tok_stride, c + 2, tp, nx2);   // two chunks ahead
+        if (c + 2 < nC) load_raw(P, base, tok_stride, c + 2, t, k4, nx2);   // two chunks ahead
         float lw[4], gg[4];
         TICK(ta0);
         {
@@ -129,31 +133,32 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {   // inclusive scan over the 2 tokens of this warp (lane = (t&1)*16 + k4)
-            const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
-            if (t & 1) gg[j] += x;
+        for (int j = 0; j < 4; j++) {   // inclusive scan over the 4 tokens of this warp (token = lane >> 3)
+            float x = __shfl_up_sync(0xffffffffu, gg[j], 8);
+            if (tt >= 1) gg[j] += x;
+            x = __shfl_up_sync(0xffffffffu, gg[j], 16);
+            if (tt >= 2) gg[j] += x;
         }
-        // cross-warp prefix in two stages: 8 per-warp totals per channel -> 64 threads turn them into exclusive
-        // prefixes (+ the chunk total in row 8) -> every thread reads two rows (the one-stage version had every thread
-        // read all 8 rows: 256 of the kernel's ~1660 shared-memory wavefronts per chunk)
+        // cross-warp prefix in two stages: 4 token-group totals per channel (two warps each cover half the channels) ->
+        // 64 threads turn them into exclusive prefixes (+ the chunk total in row 4) -> every thread reads two rows
         float(&wt)[9][kC] = sm.wtot;
-        if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
+        if (tt == 3) st4(&wt[tg][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
         bar_sync(1, 256);
         if (tp < kC) {
             float run = 0.f;
 #pragma unroll
-            for (int ww = 0; ww < 8; ww++) {
+            for (int ww = 0; ww < 4; ww++) {
                 const float x = wt[ww][tp];
                 wt[ww][tp] = run;
                 run += x;
             }
-            wt[8][tp] = run;
+            wt[4][tp] = run;
         }
         bar_sync(1, 256);
         float tot[4];
         {
-            const float4 pre = *reinterpret_cast<const float4 *>(&wt[wp][k4 * 4]);
-            const float4 all = *reinterpret_cast<const float4 *>(&wt[8][k4 * 4]);
+            const float4 pre = *reinterpret_cast<const float4 *>(&wt[tg][k4 * 4]);
+            const float4 all = *reinterpret_cast<const float4 *>(&wt[4][k4 * 4]);
             gg[0] += gpre[0] + pre.x; gg[1] += gpre[1] + pre.y; gg[2] += gpre[2] + pre.z; gg[3] += gpre[3] + pre.w;
             tot[0] = gpre[0] + all.x; tot[1] = gpre[1] + all.y; tot[2] = gpre[2] + all.z; tot[3] = gpre[3] + all.w;
         }
@@ -572,7 +577,7 @@ __device__ void ckpt_group(const Params &P, Smem &sm, int bh, int nC, int tid) {
 constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1), kThreadsTrain = kThreads + 128;
 
 template <bool kTrain>
-__global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_v2_kernel(const Params P) {
+__global__ void __launch_bounds__(kTrain ? kThreadsTrain : kThreads, 1) wkv7_tc_fwd_v2_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
