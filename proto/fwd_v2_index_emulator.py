@@ -19,7 +19,7 @@ L, WIN, kC = 16, 4, 64
 WQ_LBO, WQ_SBO = 132, 32
 T_SBO, T_LBO = 36, 288
 MA_LBO, MA_SBO = 132, 32
-QB_LBO, QB_SBO = 64, 32
+QB_LBO, QB_SBO = 68, 32
 C_ZY, C_ZY_STRIDE, C_G = 64, 48, 160
 kMinLogDecay = -1.35
 
@@ -40,7 +40,8 @@ def smem_operand(tile, rows, K, lbo, sbo):
     return np.array([[tile[kmajor_off(r, k, lbo, sbo)] for k in range(K)] for r in range(rows)])
 
 
-WAVES = {"st4": [0, 0], "scalar": [0, 0]}       # [warp instructions, wavefronts] of stage A's tile stores
+WAVES = {"st4": [0, 0], "scalar": [0, 0], "gram group st4": [0, 0], "gram group NT stores": [0, 0], "T tile stores": [0, 0]}
+# [warp instructions, wavefronts] per kind of shared-memory store
 
 
 def _count(kind, word_addrs, width):
@@ -48,7 +49,7 @@ def _count(kind, word_addrs, width):
     128-bit accesses are served a quarter-warp at a time, 64-bit a half-warp, 32-bit the whole warp"""
     per = {1: 32, 2: 16, 4: 8}[width]
     waves = 0
-    for g0 in range(0, 32, per):
+    for g0 in range(0, len(word_addrs), per):
         banks = {}
         for a0 in word_addrs[g0:g0 + per]:
             for wd in range(width):
@@ -130,6 +131,15 @@ def stage_a(S, w, q, k, v, a, b, gpre):
 
 def stage_g(S, tm, u):
     NT = np.zeros(16 * 20)
+    # bank conflicts of the group's stores: lanes 0-15 active (rows), one warp instruction each
+    for j in range(4):
+        _count("gram group st4", [kmajor_off(r, 4 * j, MA_LBO, MA_SBO) for r in range(16)], 4)          # Aak
+        _count("gram group st4", [kmajor_off(r, 4 * j, QB_LBO, QB_SBO) for r in range(16)], 4)          # Aqb
+        _count("gram group st4", [kmajor_off(16 + r, 4 * j, MA_LBO, MA_SBO) for r in range(16)], 4)     # Aqk
+    for s_ in range(16):
+        _count("gram group NT stores", [s_ * 20 + r for r in range(16)], 1)
+    for tt in range(L):
+        _count("T tile stores", [kmajor_off(tt, col, QB_LBO, QB_SBO) for col in range(16)], 1)
     for wq in range(2):
         for row in range(16):
             g = tm[16 * wq + row, C_G + 32 * u:C_G + 32 * u + 32]      # lanes 0-15 (wq = 0) / 32-47 (wq = 1) = rows 0-15 / 16-31
@@ -216,4 +226,5 @@ if __name__ == "__main__":
         es = float(np.linalg.norm(sT - sT64[0, h].numpy()) / np.linalg.norm(sT64[0, h].numpy()))
         print(f"head {h}: y rel-l2 {ey:.2e}   S_T rel-l2 {es:.2e}   nan in y: {bool(np.isnan(y).any())}")
     for kind, (n, wv) in WAVES.items():
-        print(f"stage A {kind} tile stores: {wv / n:.2f} wavefronts per warp instruction (1.00 = conflict-free; 16-byte stores: 4.00)")
+        print(f"{kind:24s}: {wv / n:.2f} wavefronts per warp instruction (conflict-free: 1.00 for 4-byte stores, 4.00 / 2.00 for "
+              f"16-byte stores of 32 / 16 lanes)")

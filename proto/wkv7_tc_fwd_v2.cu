@@ -36,7 +36,7 @@ constexpr float kLog2e = 1.4426950408889634f;   // decays are accumulated as log
 constexpr int WQ_LBO = 132, WQ_SBO = 32;     // [32 rows: 0-15 A~ tokens, 16-31 Q~ tokens][64 channels]; same strides for BK
 constexpr int T_SBO = 36, T_LBO = 288;       // [64 rows: channel / value][16 tokens]   (transposed tiles)
 constexpr int MA_LBO = 132, MA_SBO = 32;     // [32 rows: 0-15 Aak, 16-31 Aqk][16]
-constexpr int QB_LBO = 64, QB_SBO = 32;      // [16][16]: Aqb and T
+constexpr int QB_LBO = 68, QB_SBO = 32;      // [16][16]: Aqb and T; 68 = 4 mod 32: the column-per-lane stores of T are conflict-free (64: 4-way)
 
 struct Slot {
     float WQ[16 * WQ_LBO];   // as the M = 64 A operand of the Gram instruction it is read 32 rows past its end (into BK:
