@@ -461,3 +461,93 @@ def test_xy_process_batch_matches_reference_and_golden():
         assert torch.equal(got[k], gold[k]), k
     # the masking quirk is exercised: a real code equal to a pad id is not a target
     assert int((got["labels"] == 39).sum()) == 7 * 3 and int((got["labels"] == 299).sum()) == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# randomised ragged batches (including empty text / global / semantic lists and a single sample) against the
+# reference's own functions; build container only
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")
+def test_random_ragged_batches_match_reference(capsys):
+    import random
+    import rwkvtts_b200.batch as mine
+    _reference_fn()
+    spec = importlib.util.spec_from_file_location("utils.multiple_jsonl", REF)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    ref_psb, ref_psb_cu = _reference_process_single_batch(), _reference_process_single_batch_culens()
+    ref_ci = _reference_create_inputs()
+    model = make_model(seed=29)
+    model.device = torch.device("cpu")
+    rng = random.Random(1234)
+    ages, genders, emos = ["child", "teenager", "youth-adult", "middle-aged", "elderly"], ["male", "female"], ["HAPPY", "sad", "NEUTRAL", "WHISPER"]
+    for trial in range(25):
+        B = rng.choice([1, 1, 2, 3, 5])
+        lo = 0 if trial % 2 else 1                      # every other trial allows empty pieces
+        batch = {"text": ["".join(rng.choice("abc xyz") for _ in range(rng.randint(lo, 9))) for _ in range(B)],
+                 "global_tokens": [[rng.randrange(64) for _ in range(rng.randint(lo, 5))] for _ in range(B)],
+                 "semantic_tokens": [[rng.randrange(128) for _ in range(rng.randint(lo, 14))] for _ in range(B)],
+                 "age": [rng.choice(ages) for _ in range(B)], "gender": [rng.choice(genders) for _ in range(B)],
+                 "emotion": [rng.choice(emos) for _ in range(B)], "pitch": [rng.uniform(60, 330) for _ in range(B)],
+                 "speed": [rng.choice([3.0, 3.5, 3.9, 4.0, 4.2, 4.5, 4.8, 5.0, 6.0]) for _ in range(B)]}
+        for name in ("create_inputs_and_labels", "create_inputs_and_labels_culens") + PROP_FNS:
+            got = getattr(mine, name)(batch, Tok(), model, 128, "cpu")
+            want = getattr(ref, name)(batch, Tok(), model, 128, "cpu")
+            assert set(got) == set(want), name
+            for k in got:
+                assert got[k].shape == want[k].shape and torch.equal(got[k], want[k].to(got[k].dtype)), (trial, name, k)
+        ge, gm = mine.create_inputs(batch["text"], batch["global_tokens"], batch["semantic_tokens"], Tok(), model)
+        we, wm = ref_ci(batch["text"], batch["global_tokens"], batch["semantic_tokens"], Tok(), model)
+        assert torch.equal(ge, we.to(ge.dtype)) and torch.equal(gm, wm), trial
+        # left-padded id matrices (lengths >= 1: with a zero length the reference's `[i, -0:]` slice takes the whole row)
+        Lt, Lg, Ls = rng.randint(3, 9), rng.randint(2, 5), rng.randint(4, 14)
+        def left(L, hi):
+            lens = [rng.randint(1, L) for _ in range(B)]
+            ids = torch.tensor([[rng.randrange(hi) for _ in range(L)] for _ in range(B)])
+            m = torch.zeros(B, L, dtype=torch.long)
+            for i, n in enumerate(lens):
+                m[i, L - n:] = 1
+            return ids * m, m
+        it, mt = left(Lt, 500); ig, mg = left(Lg, 64); is_, ms = left(Ls, 128)
+        pb = {"input_ids": it, "attention_mask_input_ids": mt, "global_tokens_ids": ig, "global_tokens_attention_mask": mg,
+              "semantic_tokens_ids": is_, "semantic_tokens_attention_mask": ms}
+        got, want = mine.process_single_batch(pb, model, eos_token_id=129), ref_psb(pb, model, eos_token_id=129)
+        for k in got:
+            assert torch.equal(got[k], want[k].to(got[k].dtype)), (trial, "process_single_batch", k)
+        limit = rng.choice([8192, 40, 25, 12])
+        got = mine.process_single_batch_culens(pb, model, eos_token_id=129, max_cu_seqlens=limit)
+        want = ref_psb_cu(pb, model, eos_token_id=129, max_cu_seqlens=limit)
+        for k in got:
+            assert torch.equal(got[k], want[k]), (trial, "process_single_batch_culens", limit, k)
+    capsys.readouterr()
+
+
+@pytest.mark.skipif(not os.path.exists(REF5), reason="reference tree not mounted")
+def test_random_cosy_and_xy_batches_match_reference():
+    import random
+    import numpy as np
+    from torch.nn.utils.rnn import pad_sequence
+    from rwkvtts_b200.batch import cosy_lm_target, pad_unpad_sequence, process_batch
+    ref_pad, ref_xy = _reference_pad_unpad_sequence(), _reference_process_batch()
+    rng = random.Random(99)
+    g = torch.Generator().manual_seed(99)
+    for trial in range(15):
+        B, Lt, Ls, D, V = rng.choice([1, 2, 4]), rng.randint(1, 8), rng.randint(1, 12), 8, 50
+        tl = torch.tensor([rng.randint(1, Lt) for _ in range(B)])
+        sl = torch.tensor([rng.randint(0 if trial % 3 == 0 else 1, Ls) for _ in range(B)])
+        text_emb, speech_emb = torch.randn(B, Lt, D, generator=g), torch.randn(B, Ls, D, generator=g)
+        speech_ids = torch.randint(0, V, (B, Ls), generator=g)
+        sos, task = torch.randn(1, 1, D, generator=g), torch.randn(1, 1, D, generator=g)
+        gx, gm = pad_unpad_sequence(sos, text_emb, tl, task, speech_emb, sl)
+        wx, wm = ref_pad(sos, text_emb, tl, task, speech_emb, sl)
+        assert torch.equal(gx, wx) and torch.equal(gm, wm) and gm.dtype == wm.dtype, trial
+        want_t = pad_sequence([torch.tensor([-1] * (2 + int(tl[i])) + speech_ids[i, :int(sl[i])].tolist() + [V]) for i in range(B)],
+                              batch_first=True, padding_value=-1)
+        assert torch.equal(cosy_lm_target(tl, speech_ids, sl, V), want_t), trial
+    args = (_XYTextTok(), _XYCodec(), 8, 256, 40, "cpu")
+    for trial in range(6):
+        feats = [{"json": {"text": "".join(rng.choice("ab c") for _ in range(rng.randint(0, 12)))},
+                  "audio": {"array": np.zeros(4 * rng.randint(1, 9), dtype=np.float32)}} for _ in range(rng.choice([1, 2, 3]))]
+        got, want = process_batch(feats, *args), ref_xy(feats, *args)
+        for k in ("input_ids", "labels", "attention_mask"):
+            assert torch.equal(got[k], want[k]), (trial, k)
