@@ -134,3 +134,22 @@ def test_cu_seqlens_packed_input_runs_as_the_equivalent_padded_batch(monkeypatch
     import pytest
     with pytest.raises(ValueError):
         M.unpack_varlen(x.detach(), torch.tensor([0, 5, 17]))
+
+
+def test_sampling_filters_match_hf_warpers():
+    """generate()'s top-k / top-p filter keeps exactly the tokens Hugging Face's warpers keep (the reference decodes
+    through HF generate, spark_llm.py:54-102), for random logits, k and p."""
+    import torch
+    from transformers.generation.logits_process import TopKLogitsWarper, TopPLogitsWarper
+    from rwkvfla.models.rwkv7.modeling_rwkv7 import _filter_logits
+    g = torch.Generator().manual_seed(0)
+    ids = torch.zeros(3, 1, dtype=torch.long)
+    for _ in range(60):
+        V = int(torch.randint(5, 300, (1,), generator=g))
+        lg = torch.randn(3, V, generator=g) * 3
+        k = int(torch.randint(1, V + 5, (1,), generator=g))
+        p = float(torch.rand(1, generator=g)) * 0.98 + 0.01
+        want = TopPLogitsWarper(top_p=p)(ids, TopKLogitsWarper(top_k=min(k, V))(ids, lg.clone()))
+        got = _filter_logits(lg.clone(), k, p)
+        assert torch.equal(torch.isinf(want), torch.isinf(got))
+        assert torch.equal(want[~torch.isinf(want)], got[~torch.isinf(got)])
