@@ -508,3 +508,27 @@ def process_batch(features, text_tokenizer, xy_tokenizer, num_channels, text_shi
     if not processed:
         return {}
     return xy_staircase_batch(processed, num_channels, speech_vocab_size, text_tokenizer.vocab_size - 1)
+
+
+def collate_fn_for_rwkv7speech(batch, tokenizer, rwkv7speech_model, max_length=2048, pad_to_max_length=True, vocab_size=8193):
+    """Same signature and result as the reference's collator of that name (/root/reference/data/utils/spark_dataset.py:41-52):
+    a list of samples {text, global_tokens, semantic_tokens} -> LEFT-padded `input_embs` / `attention_mask` (create_inputs
+    with the eos id `vocab_size - 1` appended to every semantic sequence) and `labels` = the semantic ids + eos placed one
+    step early at the end of each row (`labels[i, -(n+1):-1]`, :50), -100 elsewhere.  `max_length` / `pad_to_max_length` are
+    accepted and, as in the reference, unused.  One host index array and one scatter for the labels instead of a tensor
+    construction and a slice assignment per sample."""
+    device = rwkv7speech_model.device
+    texts = [sample["text"] for sample in batch]
+    global_tokens_ids = [sample["global_tokens"] for sample in batch]
+    semantic_tokens_ids = [list(sample["semantic_tokens"]) + [vocab_size - 1] for sample in batch]
+    input_ids_embs, attention_mask = create_inputs(texts, global_tokens_ids, semantic_tokens_ids, tokenizer, rwkv7speech_model)
+    B, Tmax = input_ids_embs.shape[0], input_ids_embs.shape[1]
+    dst, ids = [], []
+    for i, sem in enumerate(semantic_tokens_ids):
+        n = len(sem)
+        dst += range(i * Tmax + Tmax - n - 1, i * Tmax + Tmax - 1)
+        ids += sem
+    d, v = _to_device([dst, ids], device)
+    labels = torch.full((B * Tmax,), -100, dtype=torch.long, device=device)
+    labels.index_copy_(0, d, v)
+    return {"input_embs": input_ids_embs, "attention_mask": attention_mask, "labels": labels.view(B, Tmax)}

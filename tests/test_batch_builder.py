@@ -551,3 +551,26 @@ def test_random_cosy_and_xy_batches_match_reference():
         got, want = process_batch(feats, *args), ref_xy(feats, *args)
         for k in ("input_ids", "labels", "attention_mask"):
             assert torch.equal(got[k], want[k]), (trial, k)
+
+
+@pytest.mark.skipif(not os.path.exists(REF2), reason="reference tree not mounted")
+def test_collate_fn_for_rwkv7speech_matches_reference():
+    """data/utils/spark_dataset.py:41-52 (it calls the reference's own create_inputs)"""
+    import ast
+    import random
+    from rwkvtts_b200.batch import collate_fn_for_rwkv7speech
+    fn = [n for n in ast.parse(open(REF2).read()).body if isinstance(n, ast.FunctionDef) and n.name == "collate_fn_for_rwkv7speech"][0]
+    ns = {"torch": torch, "create_inputs": _reference_create_inputs()}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), REF2, "exec"), ns)
+    model = make_model(seed=31)
+    model.device = torch.device("cpu")
+    rng = random.Random(3)
+    for trial in range(10):
+        batch = [{"text": "".join(rng.choice("abc xyz") for _ in range(rng.randint(1, 9))),
+                  "global_tokens": [rng.randrange(64) for _ in range(rng.randint(1, 5))],
+                  "semantic_tokens": [rng.randrange(128) for _ in range(rng.randint(1, 14))]} for _ in range(rng.choice([1, 2, 4]))]
+        got = collate_fn_for_rwkv7speech(batch, Tok(), model, vocab_size=130)
+        want = ns["collate_fn_for_rwkv7speech"](batch, Tok(), model, vocab_size=130)
+        assert set(got) == set(want)
+        for k in got:
+            assert torch.equal(got[k], want[k].to(got[k].dtype)), (trial, k)
