@@ -532,3 +532,7 @@ def collate_fn_for_rwkv7speech(batch, tokenizer, rwkv7speech_model, max_length=2
     labels = torch.full((B * Tmax,), -100, dtype=torch.long, device=device)
     labels.index_copy_(0, d, v)
     return {"input_embs": input_ids_embs, "attention_mask": attention_mask, "labels": labels.view(B, Tmax)}
+
+
+# /root/reference/data/utils/collator.py:8-130 is the same collator under another name
+xy_data_collator = process_batch

@@ -574,3 +574,21 @@ def test_collate_fn_for_rwkv7speech_matches_reference():
         assert set(got) == set(want)
         for k in got:
             assert torch.equal(got[k], want[k].to(got[k].dtype)), (trial, k)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/utils/collator.py"), reason="reference tree not mounted")
+def test_xy_data_collator_alias_matches_reference():
+    import ast
+    import logging
+    import numpy as np
+    from rwkvtts_b200.batch import xy_data_collator
+    path = "/root/reference/data/utils/collator.py"
+    fn = [n for n in ast.parse(open(path).read()).body if isinstance(n, ast.FunctionDef) and n.name == "xy_data_collator"][0]
+    ns = {"torch": torch, "logger": logging.getLogger("xy")}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    feats = [{"json": {"text": "one"}, "audio": {"array": np.zeros(24, dtype=np.float32)}},
+             {"json": {"text": "another sample"}, "audio": {"array": np.zeros(12, dtype=np.float32)}}]
+    args = (_XYTextTok(), _XYCodec(), 8, 256, 40, "cpu")
+    got, want = xy_data_collator(feats, *args), ns["xy_data_collator"](feats, *args)
+    for k in ("input_ids", "labels", "attention_mask"):
+        assert torch.equal(got[k], want[k]), k
