@@ -40,3 +40,22 @@ class LabelSmoothingLoss(nn.Module):
         total = row.masked_fill(ignore, 0.0).sum()
         denom = (~ignore).sum() if self.normalize_length else batch_size
         return (total / denom).to(x.dtype)
+
+
+def xy_channel_losses(hidden_states: torch.Tensor, heads, labels: torch.Tensor, label_smoothing: float = 0.0,
+                      ignore_index: int = -100, num_chunks: int = 8) -> torch.Tensor:
+    """Sum over the codebook channels of the mean cross entropy of `heads[i](hidden_states)` against `labels[:, :, i]`
+    -- the loss loop of RWKV7XYLM.forward (/root/reference/model/llm/xy_llm.py:233-240) -- without ever holding a
+    channel's logits: channel 0 has 66.7 k classes, [2, 8192, 66.7 k] bf16 = 2.2 GB per GPU at config c5, and the
+    reference keeps all eight logit tensors alive for the backward.  Each head goes through the chunked linear +
+    cross-entropy of the `rwkvfla` package (token chunks recomputed in the backward).  A channel without a valid label
+    gives NaN, as `nn.CrossEntropyLoss` does."""
+    from rwkvfla.modules import FusedLinearCrossEntropyLoss
+    crit = FusedLinearCrossEntropyLoss(ignore_index=ignore_index, label_smoothing=label_smoothing, num_chunks=num_chunks,
+                                       reduction="sum")
+    total = None
+    for i, head in enumerate(heads):
+        y = labels[:, :, i]
+        loss = crit(hidden_states, y, head.weight, head.bias) / (y != ignore_index).sum()
+        total = loss if total is None else total + loss
+    return total

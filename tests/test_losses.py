@@ -38,3 +38,29 @@ def test_label_smoothing_loss_matches_reference_value_and_gradient():
     y = torch.randint(0, 11, (2, 5), generator=g); y[1, 3:] = -1
     ce = torch.nn.functional.cross_entropy(x.view(-1, 11), y.view(-1), ignore_index=-1)
     assert abs(float(LabelSmoothingLoss(11, -1, 0.0, True)(x, y)) - float(ce)) < 1e-6
+
+
+def test_xy_channel_losses_equal_the_reference_loss_loop():
+    """xy_llm.py:233-240: eight heads, eight nn.CrossEntropyLoss, summed; value and gradients (hidden states, head weights
+    and biases) from the logit-free path."""
+    from rwkvtts_b200.losses import xy_channel_losses
+    g = torch.Generator().manual_seed(1)
+    B, T, D = 2, 13, 16
+    sizes = [97] + [23] * 7
+    heads = torch.nn.ModuleList([torch.nn.Linear(D, v) for v in sizes])
+    for lsm in (0.0, 0.1):
+        h = torch.randn(B, T, D, generator=g, requires_grad=True)
+        labels = torch.stack([torch.randint(0, v, (B, T), generator=g) for v in sizes], dim=-1)
+        labels[0, :4, :] = -100
+        labels[1, 7:, 3] = -100
+        crits = [torch.nn.CrossEntropyLoss(label_smoothing=lsm) for _ in sizes]
+        want = 0
+        for i in range(8):                                            # the reference's loop
+            logits = heads[i](h)
+            want = want + crits[i](logits.view(-1, logits.shape[-1]), labels[:, :, i].reshape(-1))
+        params = [h] + [p for hd in heads for p in hd.parameters()]
+        gw = torch.autograd.grad(want, params)
+        got = xy_channel_losses(h, heads, labels, label_smoothing=lsm, num_chunks=3)
+        gg = torch.autograd.grad(got, params)
+        assert abs(float(want.detach()) - float(got.detach())) < 1e-5
+        assert max(float((a - b).abs().max()) for a, b in zip(gw, gg)) < 1e-5
