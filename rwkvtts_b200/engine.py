@@ -294,6 +294,7 @@ class Engine:
         self.flat_grad.zero_()
         self.global_steps += 1
         if self.lr_scheduler is not None:
+            self.optimizer._opt_called = True     # the update ran above (on the shard): torch's scheduler order check looks here
             self.lr_scheduler.step()
 
     # -- checkpoints (DeepSpeed directory layout) --------------------------------------------------

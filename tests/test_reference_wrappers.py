@@ -192,3 +192,41 @@ def test_reference_training_script_functions_run_on_the_engine(stand_in_blocks, 
     capsys.readouterr()
     saved = tmp_path / "ckpt" / "epoch_0_step_3"
     assert (saved / "latest").exists() and any(f.name.startswith("mp_rank_00") for f in saved.rglob("*.pt"))
+
+
+def test_reference_lr_scheduler_path_on_the_engine(stand_in_blocks):
+    """train_scripts/train_spark_rwkv7speech.py: its configure_optimizer (:178-197), get_lr_scheduler (:219-232, a LambdaLR
+    handed to deepspeed.initialize(lr_scheduler=...), :566-572) and process_single_batch-style collated batches."""
+    import types
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import deepspeed
+    import test_batch_builder as tb
+    from rwkvtts_b200.batch import process_single_batch
+    mod = _load("ref_spark_llm", "model/llm/spark_llm.py")
+    configure_optimizer, get_lr_scheduler, train_step = _script_functions(
+        "train_scripts/train_spark_rwkv7speech.py", ["configure_optimizer", "get_lr_scheduler", "train_step"],
+        {"torch": torch, "os": os, "deepspeed": deepspeed})
+    torch.manual_seed(0)
+    cfg = mod.RWKV7SpeechConfig(vocab_size=131, text_vocab_size=500, audio_global_vocab_size=64, fuse_cross_entropy=True, **SMALL)
+    model = mod.RWKV7ForSpeech(cfg)
+    model.dropout.p = 0.0
+    model.train()
+    args = types.SimpleNamespace(weight_decay=0.01, ds_optimizer_offload=False, learning_rate=1e-3, learning_rate_final=1e-5)
+    optimizer = configure_optimizer(model, args)
+    sched = get_lr_scheduler(optimizer, 10, 2, args.learning_rate, args.learning_rate_final)
+    engine, opt2, _, sched2 = deepspeed.initialize(model=model, config={"train_batch_size": 4, "bf16": {"enabled": False},
+                                                                        "zero_optimization": {"stage": 2}},
+                                                   model_parameters=model.parameters(), optimizer=optimizer, lr_scheduler=sched)
+    assert opt2 is optimizer and sched2 is sched
+    lrs, losses = [], []
+    for step in range(4):
+        batch = process_single_batch(tb._padded_batch(), engine, eos_token_id=130)      # engine passed where a model is expected
+        out = train_step(engine, **batch)
+        engine.backward(out["loss"])
+        engine.step()                                   # steps the scheduler as DeepSpeed does
+        lrs.append(optimizer.param_groups[0]["lr"])
+        losses.append(float(out["loss"].detach()))
+    want = [args.learning_rate * f for f in (0.5, 1.0, 1.0 - (1 / 8) * (1 - 0.01), 1.0 - (2 / 8) * (1 - 0.01))]
+    assert all(abs(a - b) < 1e-12 for a, b in zip(lrs, want)), (lrs, want)
+    assert losses[-1] < losses[1]                       # the first step runs at lr = 0 (warm-up from zero)
