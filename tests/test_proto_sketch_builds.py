@@ -19,3 +19,35 @@ def test_forward_v2_sketch_compiles(tmp_path):
     log = out.stdout + out.stderr
     assert log.count("Compiling entry function") == 2          # inference and training variants
     assert "bytes spill stores" in log and " 0 bytes spill stores" in log
+
+
+def _run(script, *args):
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "proto", script), *args], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return out.stdout
+
+
+def test_forward_v2_index_emulation_matches_oracle():
+    """tile offsets / operand orientations / masks / tensor-memory columns / stage-A thread mapping of the sketch, replayed on
+    the CPU (proto/fwd_v2_index_emulator.py), against the f64 oracle; all tile stores conflict-free in its bank model"""
+    import re
+    txt = _run("fwd_v2_index_emulator.py")
+    errs = [float(x) for x in re.findall(r"rel-l2 ([0-9.e+-]+)", txt)]
+    assert len(errs) == 4 and max(errs) < 1e-12, txt
+    assert "nan in y: True" not in txt
+    per_instr = {m[0].strip(): float(m[1]) for m in re.findall(r"^(.+?)\s*: ([0-9.]+) wavefronts per warp instruction", txt, re.M)}
+    assert per_instr == {"st4": 4.0, "scalar": 1.0, "gram group st4": 2.0, "gram group NT stores": 1.0, "T tile stores": 1.0}, per_instr
+
+
+def test_forward_v2_sync_model_has_no_deadlock_or_hazard_and_catches_seeded_bugs():
+    assert "no deadlock, no hazard" in _run("fwd_v2_sync_model.py")
+    txt = _run("fwd_v2_sync_model.py", "--mutations")
+    assert txt.count("caught:") == 11 and "NOT caught" not in txt, txt
+
+
+def test_backward_v2_blueprint_matches_oracle():
+    import re
+    txt = _run("bwd_v2_blueprint.py")
+    errs = [float(x) for x in re.findall(r"d\w+ ([0-9.e+-]+)", txt)]
+    assert len(errs) == 7 and max(errs) < 1e-12, txt
