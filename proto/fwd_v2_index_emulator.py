@@ -215,7 +215,35 @@ def forward(w, q, k, v, a, b, s0=None):
     return y, tm[:, 0:64].copy()
 
 
+def check_sa_quad_transpose():
+    """training variant: the epilogue's 4x4 quad transposes (two __shfl_xor rounds per block of 4 tokens) followed by
+    16-byte stores must produce the backward's `sa` operand tile, element (token, value) at (value/4)*64 + (token/8)*32 +
+    (token%8)*4 + value%4 (wkv7_common.cuh), for the 64 value rows of the four epilogue warps"""
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal((16, 64))                      # [token][value]
+    blob = np.full(1024, np.nan)
+    for q in range(4):                                     # warp q: lanes 0-15 hold value rows 16q .. 16q+15
+        uv = np.array([[U[tok, 16 * q + lane] for tok in range(16)] for lane in range(16)])      # uv[lane][token]
+        for blk in range(4):
+            for delta, pairs in ((1, ((0, 1), (2, 3))), (2, ((0, 2), (1, 3)))):
+                for j0, j1 in pairs:
+                    snd = np.array([uv[l, 4 * blk + (j0 if (l & 3) & delta else j1)] for l in range(16)])
+                    rcv = np.array([snd[l ^ delta] for l in range(16)])
+                    for l in range(16):
+                        uv[l, 4 * blk + (j0 if (l & 3) & delta else j1)] = rcv[l]
+        for lane in range(16):
+            row, vi = 16 * q + lane, lane & 3
+            for blk in range(4):
+                tok = 4 * blk + vi
+                o = (row >> 2) * 64 + (tok >> 3) * 32 + (tok & 7) * 4
+                blob[o:o + 4] = uv[lane, 4 * blk:4 * blk + 4]
+    want = np.array([U[(o % 64) // 32 * 8 + (o % 32) // 4, (o // 64) * 4 + o % 4] for o in range(1024)])
+    assert np.array_equal(blob, want), "sa blob layout"
+    return True
+
+
 if __name__ == "__main__":
+    print("sa quad transpose (training epilogue):", "ok" if check_sa_quad_transpose() else "MISMATCH")
     x = O.make_inputs(1, 208, 2, seed=5)          # 13 chunks: full windows and a ragged last one
     names = "wqkvab"
     s0 = torch.randn(1, 2, 64, 64, dtype=torch.float64) * 0.1

@@ -433,7 +433,6 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
-    float *sag = kTrain ? P.sa + (size_t)bh * nC * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
     {   // initial state -> tensor memory
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
@@ -500,9 +499,34 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                     float *ut = sm.Ut[u] + (row >> 3) * T_SBO + (row & 7) * 4;      // [value][token] operand tile
 #pragma unroll
                     for (int i = 0; i < 4; i++) st4(ut + i * T_LBO, uv[4 * i], uv[4 * i + 1], uv[4 * i + 2], uv[4 * i + 3]);
-                    float *sap = sag + (size_t)c * kUFloats;                         // [token][value] operand tile
+                    // `sa` blob ([token][value] operand tile of the backward): element (token, value) at (value/4)*64 +
+                    // (token/8)*32 + (token%8)*4 + value%4, i.e. the four values of a lane quad are adjacent for one token.
+                    // 4x4 transposes inside the quad (two shuffle rounds per block of 4 tokens) give every lane the four
+                    // values of ONE token: 4 x 16-byte stores per lane instead of 16 x 4-byte (256 -> 64 requests per chunk)
+                    const int vi = lane & 3;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) sap[(j >> 3) * 32 + (j & 7) * 4] = uv[j];
+                    for (int blk = 0; blk < 4; blk++) {
+                        float *r = &uv[4 * blk];
+#pragma unroll
+                        for (int j = 0; j < 4; j += 2) {
+                            const float snd = (vi & 1) ? r[j] : r[j + 1];
+                            const float rcv = __shfl_xor_sync(0x0000ffffu, snd, 1);
+                            if (vi & 1) r[j] = rcv; else r[j + 1] = rcv;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            const float snd = (vi & 2) ? r[j] : r[j + 2];
+                            const float rcv = __shfl_xor_sync(0x0000ffffu, snd, 2);
+                            if (vi & 2) r[j] = rcv; else r[j + 2] = rcv;
+                        }
+                    }
+                    // now uv[4*blk + j] = U[token 4*blk + vi][value 4*(row/4) + j]
+                    float *sap = P.sa + ((size_t)bh * nC + c) * kUFloats + (row >> 2) * kULbo;
+#pragma unroll
+                    for (int blk = 0; blk < 4; blk++) {
+                        const int tok = 4 * blk + vi;
+                        st4(sap + (tok >> 3) * 32 + (tok & 7) * 4, uv[4 * blk], uv[4 * blk + 1], uv[4 * blk + 2], uv[4 * blk + 3]);
+                    }
                 }
             }
             if (kTrain) {
