@@ -51,3 +51,11 @@ def test_backward_v2_blueprint_matches_oracle():
     txt = _run("bwd_v2_blueprint.py")
     errs = [float(x) for x in re.findall(r"d\w+ ([0-9.e+-]+)", txt)]
     assert len(errs) == 7 and max(errs) < 1e-12, txt
+
+
+def test_backward_v2_sync_design_has_no_deadlock_or_hazard_and_catches_seeded_bugs():
+    assert "no deadlock, no hazard" in _run("bwd_v2_sync_model.py")
+    txt = _run("bwd_v2_sync_model.py", "--mutations")
+    # the one seeded bug the model cannot see is the missing commit + wait between two MMAs with different accumulators
+    # (its tensor pipe completes instructions in issue order)
+    assert txt.count("caught:") == 10 and txt.count("NOT caught") == 1 and "no bar_r wait before B2" in txt, txt
