@@ -32,6 +32,13 @@ WORKLOAD = "configs[1]: RWKV-7 0.4B Spark-layout bf16, batch 8/GPU, seq_len 4096
 
 
 _CTL = {"mode": "single", "dir": None, "seq": 0, "rank": 0}
+_T0 = time.time()
+
+
+def log(msg):
+    """One stderr line per leg: a hang can no longer erase the record of how far the run got."""
+    sys.stderr.write("bench[%s +%.1fs]: %s\n" % (os.environ.get("RANK", "0"), time.time() - _T0, msg))
+    sys.stderr.flush()
 
 
 def dist_init(world):
@@ -342,9 +349,11 @@ def main():
     def barrier():
         dist_barrier(world)
 
+    log("inputs resident; warm-up")
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    log("warm-up done; timed region")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -356,6 +365,7 @@ def main():
         step(ev[i][1])
         ev[i][2].record()
     barrier()
+    log("timed region done")
     launches = lib.rwkvtts_kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0][0].elapsed_time(ev[-1][2])
@@ -427,9 +437,12 @@ def main():
     infer_ms = decode_ms = fused_k = None
     DB = 32
     if extras:
+        log("leg: other kernels")
         infer_ms, decode_ms, DB = other_kernels()
+        log("leg: fused kernels")
         fused_k = fused_leg()
         torch.cuda.empty_cache()
+    log("leg: e2e")
 
     # ---- e2e: public API (WindBackstepping autograd op) with pinned HOST buffers --------------
     host_in = [x[n].pin_memory() for n in "wqkvab"] + [x["dy"].pin_memory()]
@@ -483,6 +496,7 @@ def main():
     e2e_ms = dist_max(e0.elapsed_time(e1), world)
     e2e_value = B * T * world / (e2e_ms / args.e2e_steps * 1e-3)
 
+    log("e2e done")
     if rank != 0:
         dist_finish(world)
         return
@@ -560,17 +574,21 @@ def main():
         "ref_gpu_op": ref_gpu,
     }
     if world == 1 and not args.no_decode:
+        log("leg: decode")
         try:
             line["decode"] = decode_leg(dev)
         except Exception as e:                                  # never let the extra leg kill the line
             line["decode"] = {"error": repr(e)}
     if world == 1 and not args.no_model_step:
+        log("leg: model step")
         try:
             line["model_train_step"] = model_step_leg(dev)
         except Exception as e:
             line["model_train_step"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:
+        log("leg: cpu baseline")
         line["cpu_baseline"] = cpu_reference()
+    log("done")
     print(json.dumps(line))
     dist_finish(world)
 

@@ -77,6 +77,14 @@ RWKVTTS_API int rwkvtts_get_impl(void);
  * "gpu_launches": every kernel of the path goes through the entry points below). */
 RWKVTTS_API long long rwkvtts_kernel_launches(void);
 
+/* Watchdog of the chunked tensor-core kernels.  Every mbarrier hand-off inside them is bounded (4 s; a
+ * launch takes < 2 ms): a wait that expires writes {kernel, barrier, parity, block, thread, time} to a
+ * pinned host record and traps, so the next CUDA call of the process fails (sticky launch failure) instead
+ * of the device spinning forever -- the reference kernels have no such hand-offs (wkv7_cuda.cu uses
+ * __syncthreads only).  Formats the record into buf (NUL-terminated, at most n bytes); returns 1 if a
+ * record exists, 0 otherwise.  Readable after the CUDA context has been lost. */
+RWKVTTS_API int rwkvtts_watchdog_report(char *buf, size_t n);
+
 /* Number of floats the caller must provide for the scratch tensors (reference sizes). */
 RWKVTTS_API size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_floats, size_t *sa_floats);
 

@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librwkvtts_wkv7.so")
+# RWKVTTS_LIB selects another build of the same library (the stress variants of rwkvtts_b200/build.py)
+LIB_PATH = os.environ.get("RWKVTTS_LIB") or os.path.join(_HERE, "librwkvtts_wkv7.so")
 
 _vp, _i, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
 
@@ -19,6 +20,7 @@ SYMBOLS = {
     "rwkvtts_strerror": (ctypes.c_char_p, [_i]),
     "rwkvtts_last_cuda_error": (_i, []),
     "rwkvtts_kernel_launches": (ctypes.c_longlong, []),
+    "rwkvtts_watchdog_report": (_i, [ctypes.c_char_p, ctypes.c_size_t]),
     "rwkvtts_set_impl": (_i, [_i]),
     "rwkvtts_get_impl": (_i, []),
     "rwkvtts_wkv7_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
@@ -64,6 +66,12 @@ def lib() -> ctypes.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+def watchdog_report() -> str:
+    """Text of the mbarrier watchdog record of the chunked kernels ('' if none fired); include/rwkvtts_wkv7.h."""
+    buf = ctypes.create_string_buffer(512)
+    return buf.value.decode() if lib().rwkvtts_watchdog_report(buf, 512) else ""
 
 
 def check(rc: int, what: str) -> None:

@@ -8,8 +8,40 @@
 #include <atomic>
 #include <cstdlib>
 
+#include <cstdio>
+#include <mutex>
+
 namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
+
+// ---- watchdog record (see tc05.cuh) -------------------------------------------------------------------------
+static unsigned long long *g_wd_host = nullptr;
+static std::once_flag g_wd_once;
+unsigned long long *watchdog_record() {
+    std::call_once(g_wd_once, [] {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, 8 * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+            g_wd_host = static_cast<unsigned long long *>(p);
+            for (int i = 0; i < 8; i++) g_wd_host[i] = 0;
+        } else {
+            (void)cudaGetLastError();
+        }
+    });
+    return g_wd_host;
+}
+static std::atomic<unsigned long long> g_wd_installed[4];      // per slot: bit d = installed on device d
+bool watchdog_needs_install(int slot, cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || slot < 0 || slot >= 4) return false;
+    const unsigned long long bit = 1ull << dev;
+    if (g_wd_installed[slot].load(std::memory_order_acquire) & bit) return false;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return !(g_wd_installed[slot].fetch_or(bit, std::memory_order_acq_rel) & bit);
+}
 cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, void *y, float *s, float *sa, const float *s0,
                             float *sT, bool save, cudaStream_t st);
@@ -29,6 +61,11 @@ cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, c
 cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *grad, int grad_is_bf16, void *param,
                               int param_is_bf16, long long n, float lr, float b1, float b2, float eps, float wd,
                               int adamw, float bc1, float bc2_sqrt, float gscale, cudaStream_t st);
+const char *tc_fwd_barrier_name(unsigned off);
+const char *tc_bwd_barrier_name(unsigned off);
+inline const char *watchdog_barrier_name(unsigned kernel, unsigned off) {
+    return kernel == 1 ? tc_fwd_barrier_name(off) : kernel == 2 ? tc_bwd_barrier_name(off) : "?";
+}
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
@@ -125,6 +162,25 @@ int rwkvtts_set_impl(int impl) {
 int rwkvtts_get_impl(void) { return g_impl.load(); }
 
 long long rwkvtts_kernel_launches(void) { return rwkvtts::g_kernel_launches.load(); }
+
+int rwkvtts_watchdog_report(char *buf, size_t n) {
+    const unsigned long long *r = rwkvtts::g_wd_host;
+    if (r == nullptr || r[0] == 0) {
+        if (buf != nullptr && n > 0) buf[0] = 0;
+        return 0;
+    }
+    if (buf != nullptr && n > 0) {
+        const unsigned kid = (unsigned)r[1];
+        snprintf(buf, n,
+                 "rwkvtts watchdog: kernel %s, mbarrier at dynamic-smem offset %u (%s), parity %u, block %u, thread %u "
+                 "(warp %u), waited %.3f s",
+                 kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : "?", (unsigned)(r[2] >> 32),
+                 rwkvtts::watchdog_barrier_name(kid, (unsigned)(r[2] >> 32)), (unsigned)(r[2] & 0xffffffffu),
+                 (unsigned)(r[3] >> 32), (unsigned)(r[3] & 0xffffffffu), (unsigned)(r[3] & 0xffffffffu) >> 5,
+                 (double)r[4] * 1e-9);
+    }
+    return 1;
+}
 
 size_t rwkvtts_wkv7_scratch_floats(int B, int T, int H, size_t *s_floats, size_t *sa_floats) {
     const size_t s = (size_t)B * H * (T / RWKVTTS_CHUNK_LEN) * RWKVTTS_HEAD_SIZE * RWKVTTS_HEAD_SIZE;

@@ -143,8 +143,49 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
+
+// ---- watchdog ------------------------------------------------------------------------------------
+// Every mbarrier wait of the chunked kernels is bounded: a hand-off that has not arrived after
+// RWKVTTS_WATCHDOG_NS (default 4 s; a whole launch takes < 2 ms) writes one record
+//   {magic, kernel id, barrier offset in dynamic shared memory, parity, block, thread, ns waited}
+// to a pinned host buffer (capi.cu owns it; rwkvtts_watchdog_report() formats it) and traps, so a
+// protocol error surfaces as a CUDA error with a diagnosis instead of a device that spins forever.
+#ifndef RWKVTTS_WATCHDOG_NS
+#define RWKVTTS_WATCHDOG_NS 4000000000ull
+#endif
+constexpr unsigned long long kWatchdogMagic = 0x57444f4752574b56ull;   // "WDOGRWKV"
+static __device__ unsigned long long *g_wd_rec = nullptr;              // one copy per translation unit
+static __device__ unsigned int g_wd_kernel = 0;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity, unsigned long long waited) {
+    extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
+    unsigned long long *r = g_wd_rec;
+    if (r != nullptr && atomicCAS_system(r, 0ull, kWatchdogMagic) == 0ull) {
+        r[1] = g_wd_kernel;
+        r[2] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
+        r[3] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+        r[4] = waited;
+        __threadfence_system();
+    }
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {}
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = globaltimer_ns();
+    while (!mbar_try_wait(bar, parity)) {
+        const unsigned long long dt = globaltimer_ns() - t0;
+        if (dt > RWKVTTS_WATCHDOG_NS) mbar_timeout(smem_u32(bar), parity, dt);
+    }
+}
+// host side: point this translation unit's record pointer at the pinned buffer (once per device)
+inline cudaError_t watchdog_install(unsigned long long *rec, unsigned int kernel_id) {
+    cudaError_t e = cudaMemcpyToSymbol(g_wd_rec, &rec, sizeof(rec));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(g_wd_kernel, &kernel_id, sizeof(kernel_id));
 }
 
 // ---- bulk asynchronous copies (TMA engine, 1-D): no registers, one instruction per contiguous piece ------------

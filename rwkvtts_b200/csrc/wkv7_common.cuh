@@ -11,6 +11,13 @@ namespace rwkvtts {
 extern std::atomic<long long> g_kernel_launches;   // defined in capi.cu
 inline void count_launch(int n = 1) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Pinned, device-visible record the chunked kernels' mbarrier watchdog writes before it traps (tc05.cuh);
+// owned by capi.cu, nullptr if it could not be allocated.  8 x u64.
+unsigned long long *watchdog_record();
+// true once per (translation unit slot, device): the caller then installs the record pointer into its own
+// copy of the device symbol.  Never true while `st` is being captured into a CUDA graph.
+bool watchdog_needs_install(int slot, cudaStream_t st);
+
 constexpr int kC = 64;       // head size (reference: -D_C_=64)
 constexpr int kChunk = 16;   // snapshot spacing of the scan kernels (reference: _CHUNK_LEN_)
 

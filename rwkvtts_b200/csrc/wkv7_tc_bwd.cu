@@ -81,7 +81,13 @@ struct Smem {
     float elast[kC];              // group C: e^{G} at a window end
     float glp[2][kC], suff[kC], cfirst[kC], xch[2][kC];   // group C: boundary-term partials, dw suffix, carries
     uint64_t full[NS], empty[NS], a_done[NS], blob_full[NS], s0_full;
-    uint64_t resc, glp_done, ok_free[2], bar_z, c_done, out_ready;
+    uint64_t resc, glp_done, ok_free[2], bar_z, c_done;
+    // one barrier per iteration parity: with a single barrier the MMA warp could commit iteration it+1 before group C2
+    // had observed iteration it (nothing on C2's side gates that commit), the 1-bit phase parity would flip twice and
+    // C2 would wait for a phase that can only complete after its own ok_free arrival -- a deadlock (found by the
+    // protocol model, proto/bwd_v2_sync_model.py; round-1 VERDICT).  out_ready[p] is committed at iterations of parity
+    // p only, and the next commit on it (it+2) waits for ok_free[p] of iteration `it`, which C2 gives after its wait.
+    uint64_t out_ready[2];
     uint32_t tmem_base;
 };
 
@@ -418,7 +424,11 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
         // every MMA of the previous chunk has completed (dS, dS^T are final; Z, the Gram tiles and the slot two
         // iterations back are free); at a window boundary group C1 has moved dS / dS^T into this window's frame;
         // group C2 has drained the gradient accumulators of two iterations back
-        if (it > 0) mbar_wait(&sm.out_ready, (it - 1) & 1);
+        #ifdef RWKVTTS_BWD_SINGLE_OUT_READY      // round-1 protocol, kept only so that scripts/stress_wkv7.py can show the hazard
+        if (it > 0) mbar_wait(&sm.out_ready[0], (it - 1) & 1);
+#else
+        if (it > 0) mbar_wait(&sm.out_ready[(it - 1) & 1], ((it - 1) >> 1) & 1);
+#endif
         if (win_last) { mbar_wait(&sm.resc, nw & 1); nw++; }
         if (it >= 2) mbar_wait(&sm.ok_free[it & 1], ((it >> 1) - 1) & 1);
         TICK(tm2);
@@ -493,7 +503,11 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
                 mma_tf32_ts(ov, tb + C_Z + 8 * kk, kadv(dAakT, kk, S16_LBO), I16, true);
-            mma_commit(&sm.out_ready);
+#ifdef RWKVTTS_BWD_SINGLE_OUT_READY
+            mma_commit(&sm.out_ready[0]);
+#else
+            mma_commit(&sm.out_ready[it & 1]);
+#endif
         }
         __syncwarp();
         TICK(tm5); ACC(5, tm0, tm1); ACC(6, tm1, tm2); ACC(7, tm2, tm3); ACC(8, tm3, tm4); ACC(9, tm4, tm5);
@@ -662,7 +676,17 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
         }
         TICK(tc4);
         // ---- outputs: this warp's 8 tokens (hf = 1 is later in time and feeds hf = 0) -------------
-        mbar_wait(&sm.out_ready, it & 1);
+#ifdef RWKVTTS_BWD_SINGLE_OUT_READY
+#ifdef RWKVTTS_BWD_DELAY_C2              // hold C2 back for about a chunk every so often: the window the hazard needs
+        if ((it & 63) == 17 && (blockIdx.x & 7) == 3) { const long long t_ = clock64(); while (clock64() - t_ < 20000) {} }
+#endif
+        mbar_wait(&sm.out_ready[0], it & 1);
+#else
+#ifdef RWKVTTS_BWD_DELAY_C2
+        if ((it & 63) == 17 && (blockIdx.x & 7) == 3) { const long long t_ = clock64(); while (clock64() - t_ < 20000) {} }
+#endif
+        mbar_wait(&sm.out_ready[it & 1], (it >> 1) & 1);
+#endif
         TICK(tc5);
         fence_after_sync();
         {
@@ -835,7 +859,7 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
         mbar_init(&sm.s0_full, 1);
         mbar_init(&sm.resc, 4); mbar_init(&sm.glp_done, 8); mbar_init(&sm.ok_free[0], 8); mbar_init(&sm.ok_free[1], 8);
         mbar_init(&sm.bar_z, 1); mbar_init(&sm.c_done, 4);
-        mbar_init(&sm.out_ready, 1);
+        mbar_init(&sm.out_ready[0], 1); mbar_init(&sm.out_ready[1], 1);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc(&sm.tmem_base, 512);
@@ -858,6 +882,19 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
 
 long long *g_tcb_dbg = nullptr;   // set by the profiling harness only
 
+const char *tc_bwd_barrier_name(unsigned off) {
+    using tcbwd::Smem;
+    struct { size_t off; int n; const char *name; } t[] = {
+        {offsetof(Smem, full), tcbwd::NS, "full[slot]"}, {offsetof(Smem, empty), tcbwd::NS, "empty[slot]"},
+        {offsetof(Smem, a_done), tcbwd::NS, "a_done[slot]"}, {offsetof(Smem, blob_full), tcbwd::NS, "blob_full[slot]"},
+        {offsetof(Smem, s0_full), 1, "s0_full"}, {offsetof(Smem, resc), 1, "resc"}, {offsetof(Smem, glp_done), 1, "glp_done"},
+        {offsetof(Smem, ok_free), 2, "ok_free[parity]"}, {offsetof(Smem, bar_z), 1, "bar_z"}, {offsetof(Smem, c_done), 1, "c_done"},
+        {offsetof(Smem, out_ready), 2, "out_ready[parity]"}};
+    for (auto &e : t)
+        if (off >= e.off && off < e.off + 8 * (size_t)e.n) return e.name;
+    return "unknown";
+}
+
 cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
                           const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
@@ -870,6 +907,10 @@ cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, con
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
              (const bf16 *)b, (const bf16 *)dy, ckT, sa, sT, dsT, (bf16 *)dw, (bf16 *)dq, (bf16 *)dk, (bf16 *)dv,
              (bf16 *)da, (bf16 *)db, ds0, g_tcb_dbg};
+    if (watchdog_needs_install(1, st)) {
+        e = watchdog_install(watchdog_record(), 2);
+        if (e != cudaSuccess) return e;
+    }
     count_launch();
     wkv7_tc_bwd_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
     return cudaGetLastError();

@@ -621,6 +621,19 @@ __global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_kernel(const Par
 
 long long *g_tc_dbg = nullptr;   // set by the profiling harness only
 
+const char *tc_fwd_barrier_name(unsigned off) {
+    using tcfwd::Smem;
+    struct { size_t off; int n; const char *name; } t[] = {
+        {offsetof(Smem, empty), tcfwd::NSLOT, "empty[slot]"}, {offsetof(Smem, full), tcfwd::NSLOT, "full[slot]"},
+        {offsetof(Smem, a_done), tcfwd::NNAT, "a_done[nat]"}, {offsetof(Smem, nat_empty), tcfwd::NNAT, "nat_empty[nat]"},
+        {offsetof(Smem, p_done), 1, "p_done"}, {offsetof(Smem, y_ready), 2, "y_ready[parity]"},
+        {offsetof(Smem, y_free), 2, "y_free[parity]"}, {offsetof(Smem, win_scaled), 1, "win_scaled"},
+        {offsetof(Smem, ut_ready), 1, "ut_ready"}, {offsetof(Smem, st_ready), 1, "st_ready"}, {offsetof(Smem, st_free), 1, "st_free"}};
+    for (auto &e : t)
+        if (off >= e.off && off < e.off + 8 * (size_t)e.n) return e.name;
+    return "unknown";
+}
+
 // ckT == nullptr: snapshot-free forward.  Otherwise the training forward: per-chunk transposed state
 // checkpoints (same size as the reference's `s`) and `sa`, consumed by wkv7_tc_bwd.cu.
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
@@ -630,6 +643,10 @@ cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, con
     static_assert(sizeof(Smem) <= 232448, "shared memory budget");
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
              (const bf16 *)b, (bf16 *)y, ckT, sa, s0, sT, g_tc_dbg};
+    if (watchdog_needs_install(0, st)) {
+        cudaError_t e = watchdog_install(watchdog_record(), 1);
+        if (e != cudaSuccess) return e;
+    }
     count_launch();
     if (ckT != nullptr) {
         cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
