@@ -136,6 +136,24 @@ RWKVTTS_API int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg
                        float beta2, float eps, float weight_decay, int adamw_mode, float bias_correction1,
                        float bias_correction2_sqrt, float grad_scale, void *stream);
 
+/* The engine's form of the same update (rwkvtts_b200/engine.py): the range [0,n) of the rank's shard is a
+ * run of `nseg` segments -- seg_end[s] (device, int64, ascending exclusive ends, multiples of 4) and
+ * seg_group[s] (device, int32) -- that map to optimizer param groups with their own hyper-parameters,
+ * group_hp (HOST, float[ngroups][4] = lr, weight_decay, bias_correction1, sqrt(bias_correction2); the
+ * reference's scripts rewrite param_groups[i]['lr'] every step, train_spark_rwkv7speech.py:586-600).
+ * `stat` (device, float[2] = {global squared gradient norm, non-finite count}, or NULL) is read on the
+ * device: a non-finite gradient skips the update on every rank (and bumps *skipped, device u64, may be NULL),
+ * and `clip` > 0 scales the gradient by clip / (norm + 1e-6) when norm > clip (DeepSpeed's
+ * gradient_clipping) -- no host synchronisation anywhere in engine.step().  ngroups <= 8. */
+RWKVTTS_API int rwkvtts_adam_multi(float *master, float *exp_avg, float *exp_avg_sq, const void *grad,
+                       int grad_is_bf16, void *param, int param_is_bf16, long long n, const long long *seg_end,
+                       const int *seg_group, int nseg, const float *group_hp, int ngroups, float beta1, float beta2,
+                       float eps, int adamw_mode, const float *stat, float clip, unsigned long long *skipped,
+                       void *stream);
+/* stat[0] += sum of squares of grad[0..n), stat[1] += 1 if any element is non-finite (device float[2],
+ * zeroed by the caller; the engine all-reduces it across ranks before rwkvtts_adam_multi). */
+RWKVTTS_API int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, void *stream);
+
 /* ---- fused elementwise kernels of the time-mix around the WKV-7 op ---------------------------------------------
  * Replace the ~30 ATen elementwise kernels RWKV_Tmix_x070.forward runs per layer between its GEMMs
  * (model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226).

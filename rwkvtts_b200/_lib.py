@@ -44,6 +44,9 @@ SYMBOLS = {
     "rwkvtts_sqrelu_backward": (_i, [ctypes.c_longlong, _vp, _vp, _vp, _vp]),
     "rwkvtts_adam_shard": (_i, [_fp, _fp, _fp, _vp, _i, _vp, _i, ctypes.c_longlong] + [ctypes.c_float] * 5 + [_i]
                            + [ctypes.c_float] * 3 + [_vp]),
+    "rwkvtts_adam_multi": (_i, [_fp, _fp, _fp, _vp, _i, _vp, _i, ctypes.c_longlong, _vp, _vp, _i,
+                                ctypes.POINTER(ctypes.c_float), _i] + [ctypes.c_float] * 3 + [_i, _fp, ctypes.c_float, _vp, _vp]),
+    "rwkvtts_grad_stat": (_i, [_vp, _i, ctypes.c_longlong, _fp, _vp]),
 }
 
 _lib = None

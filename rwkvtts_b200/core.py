@@ -33,6 +33,9 @@ from . import fused, ops
 HEAD = ops.HEAD_SIZE
 FUSED = os.environ.get("RWKVTTS_FUSED", "1") != "0"
 DECODE_BATCHED_GEMM = os.environ.get("RWKVTTS_DECODE_BMM", "1") != "0"
+# measurement hook (bench.py R-GPU-model leg): an autograd.Function with WindBackstepping's signature that replaces the
+# training op (the bench binds the compiled reference kernels there); None = this library
+WKV_TRAIN_OP = None
 
 
 @dataclass
@@ -87,6 +90,8 @@ def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
     if T % ops.CHUNK_LEN == 0:
         sh = lambda t: t.view(B, T, H, HEAD)
         if state is None and not need_state:
+            if WKV_TRAIN_OP is not None:
+                return WKV_TRAIN_OP.apply(sh(w), sh(r), sh(k), sh(v), sh(a), sh(b)).view(B, T, C), None
             return ops.RUN_CUDA_RWKV7g(r, w, k, v, a, b), None                     # :191 (training / no_grad)
         y, sT = ops.wkv7_with_state(sh(w), sh(r), sh(k), sh(v), sh(a), sh(b), state)
         return y.view(B, T, C), sT

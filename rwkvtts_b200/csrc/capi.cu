@@ -66,6 +66,11 @@ const char *tc_bwd_barrier_name(unsigned off);
 inline const char *watchdog_barrier_name(unsigned kernel, unsigned off) {
     return kernel == 1 ? tc_fwd_barrier_name(off) : kernel == 2 ? tc_bwd_barrier_name(off) : "?";
 }
+cudaError_t launch_adam_multi(float *master, float *m, float *v, const void *grad, int grad_is_bf16, void *param,
+                              int param_is_bf16, long long n, const long long *seg_end, const int *seg_group, int nseg,
+                              const float *group_hp, int ngroups, float b1, float b2, float eps, int adamw,
+                              const float *stat, float clip, unsigned long long *skipped, cudaStream_t st);
+cudaError_t launch_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, cudaStream_t st);
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
@@ -266,6 +271,29 @@ int rwkvtts_adam_shard(float *master, float *exp_avg, float *exp_avg_sq, const v
     return finish(rwkvtts::launch_adam_shard(master, exp_avg, exp_avg_sq, grad, grad_is_bf16, param, param_is_bf16, n,
                                              lr, beta1, beta2, eps, weight_decay, adamw_mode, bias_correction1,
                                              bias_correction2_sqrt, grad_scale, (cudaStream_t)stream));
+}
+
+int rwkvtts_adam_multi(float *master, float *exp_avg, float *exp_avg_sq, const void *grad, int grad_is_bf16,
+                       void *param, int param_is_bf16, long long n, const long long *seg_end, const int *seg_group,
+                       int nseg, const float *group_hp, int ngroups, float beta1, float beta2, float eps, int adamw_mode,
+                       const float *stat, float clip, unsigned long long *skipped, void *stream) {
+    if (n < 0 || nseg <= 0 || ngroups <= 0 || ngroups > 8) return RWKVTTS_ERR_SHAPE;
+    if (n == 0) return RWKVTTS_OK;
+    if (group_hp == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({master, exp_avg, exp_avg_sq, seg_end, seg_group})) return rc;
+    if (grad == nullptr || param == nullptr) return RWKVTTS_ERR_NULL;
+    if ((reinterpret_cast<uintptr_t>(grad) & 7u) || (reinterpret_cast<uintptr_t>(param) & 7u)) return RWKVTTS_ERR_ALIGN;
+    return finish(rwkvtts::launch_adam_multi(master, exp_avg, exp_avg_sq, grad, grad_is_bf16, param, param_is_bf16, n,
+                                             seg_end, seg_group, nseg, group_hp, ngroups, beta1, beta2, eps, adamw_mode,
+                                             stat, clip, skipped, (cudaStream_t)stream));
+}
+
+int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, void *stream) {
+    if (n < 0) return RWKVTTS_ERR_SHAPE;
+    if (n == 0) return RWKVTTS_OK;
+    if (grad == nullptr || stat == nullptr) return RWKVTTS_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(grad) & 7u) return RWKVTTS_ERR_ALIGN;
+    return finish(rwkvtts::launch_grad_stat(grad, grad_is_bf16, n, stat, (cudaStream_t)stream));
 }
 
 // ---- fused time-mix elementwise kernels ------------------------------------------------------------------------

@@ -23,8 +23,10 @@ into two flat buffers, so the collectives take no packing copies.  On one rank n
 """
 from __future__ import annotations
 
+import ctypes
 import math
 import os
+import warnings
 from typing import Any, Dict, Iterable, List, Optional
 
 import torch
@@ -130,6 +132,21 @@ def _world():
 
 
 class Engine:
+    """ZeRO-2 style data-parallel engine.  Flat layout (all in the model dtype):
+
+        flat space  = optimizer parameters in REVERSE model order (the order their gradients become final in
+                      backward), each padded to 8 elements, cut into buckets of ~`bucket_elems` at parameter
+                      boundaries, each bucket padded to 256 * world_size elements;
+        bucket b    = [start_b, end_b); rank r owns slice r of every bucket; the rank's fp32 master weights and Adam
+                      moments are the concatenation of its slices ("shard space").
+
+    Per optimizer step and bucket: reduce-scatter(AVG) of the bucket's gradients as soon as the last gradient of the
+    bucket has been accumulated (post-accumulate-grad hooks; NCCL on a side stream, so the exchange of the last
+    layers overlaps the backward of the first ones), then -- after one 2-float all-reduce of {squared norm,
+    non-finite count} -- the fused Adam kernel on the slice (hyper-parameters per param group through a segment
+    table, clipping / skip decided on the device) and the in-place all-gather of the updated parameters, the
+    all-gather of bucket b overlapping the Adam kernel of bucket b+1.  No host synchronisation in step()."""
+
     def __init__(self, model: torch.nn.Module, optimizer: FusedAdam, config: Dict[str, Any],
                  lr_scheduler=None, device: Optional[torch.device] = None):
         self.config = dict(config or {})
@@ -145,61 +162,137 @@ class Engine:
         self.lr_scheduler = lr_scheduler
         self.gradient_accumulation_steps = int(self.config.get("gradient_accumulation_steps", 1))
         self.gradient_clipping = float(self.config.get("gradient_clipping", 0.0))
+        zo = self.config.get("zero_optimization", {}) or {}
+        self.bucket_elems = int(os.environ.get("RWKVTTS_BUCKET_ELEMS", 0)) or max(int(zo.get("reduce_bucket_size", 0)), 1 << 26)
+        self.overlap_comm = os.environ.get("RWKVTTS_OVERLAP_COMM", "1") != "0"
         self.global_steps = 0
         self.micro_steps = 0
-        self.skipped_steps = 0
+        self.comm_ms = None                    # filled by profile_comm()
+        self._on_gpu = self.device.type == "cuda"
+        self._nccl = self.world_size > 1 and dist.get_backend() == "nccl"
+        self._comm_stream = torch.cuda.Stream(device=self.device) if (self._on_gpu and self.world_size > 1) else None
         self._build_flat_buffers()
+        self._install_hooks()
 
     # -- flat parameter / gradient space ---------------------------------------------------------
     def _build_flat_buffers(self):
         groups = self.optimizer.param_groups
-        plist: List[torch.nn.Parameter] = []
-        self._segments = []            # (start, end, group index) in the flat space
-        off = 0
+        if len(groups) > 8:
+            raise ValueError("at most 8 optimizer param groups")
+        gid = {}
         for gi, g in enumerate(groups):
             g["params"] = [p for p in g["params"]]
-            start = off
             for p in g["params"]:
-                plist.append(p)
-                off += p.numel()
-            self._segments.append((start, off, gi))
-        if not plist:
+                gid[id(p)] = gi
+        ordered, seen = [], set()
+        for p in self.module.parameters():                       # model order ...
+            if id(p) in gid and id(p) not in seen:
+                ordered.append(p); seen.add(id(p))
+        for g in groups:                                          # ... then anything the module does not own
+            for p in g["params"]:
+                if id(p) not in seen:
+                    ordered.append(p); seen.add(id(p))
+        if not ordered:
             raise ValueError("optimizer has no parameters")
-        dtype = plist[0].dtype
-        if any(p.dtype != dtype for p in plist):
+        ordered.reverse()                                         # gradients arrive last layer first
+        dtype = ordered[0].dtype
+        if any(p.dtype != dtype for p in ordered):
             raise ValueError("all optimized parameters must share one dtype (cast the model first)")
-        unit = ALIGN * self.world_size
-        total = ((off + unit - 1) // unit) * unit
-        self.numel, self.padded = off, total
-        self.flat_param = torch.zeros(total, dtype=dtype, device=self.device)
-        self.flat_grad = torch.zeros(total, dtype=dtype, device=self.device)
-        o = 0
-        for p in plist:
+        W = self.world_size
+        unit = ALIGN * W
+        self._params, self._poff, self._pgroup, self._pbucket = ordered, [], [], []
+        self.buckets = []                                         # (start, end) in the flat space
+        off, bstart = 0, 0
+        for i, p in enumerate(ordered):
+            self._poff.append(off)
+            self._pgroup.append(gid[id(p)])
+            self._pbucket.append(len(self.buckets))
+            off += (p.numel() + 7) // 8 * 8
+            if off - bstart >= self.bucket_elems or i == len(ordered) - 1:
+                off = bstart + ((off - bstart + unit - 1) // unit) * unit
+                self.buckets.append((bstart, off))
+                bstart = off
+        self.numel, self.padded = sum(p.numel() for p in ordered), off
+        self.flat_param = torch.zeros(off, dtype=dtype, device=self.device)
+        self.flat_grad = torch.zeros(off, dtype=dtype, device=self.device)
+        for p, o in zip(ordered, self._poff):
             n = p.numel()
             self.flat_param[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + n].view(p.shape)          # parameters alias the flat buffer
             p.grad = self.flat_grad[o:o + n].view(p.shape)           # autograd accumulates in place
-            o += n
-        self._params = plist
-        self.shard_size = total // self.world_size
-        lo = self.rank * self.shard_size
-        self.shard = (lo, lo + self.shard_size)
-        self.master = self.flat_param[lo:lo + self.shard_size].float().clone()
+        # shard space: slice `rank` of every bucket, concatenated
+        self._slice, self._soff = [], []
+        so = 0
+        for (s, e) in self.buckets:
+            ss = (e - s) // W
+            self._slice.append((s + self.rank * ss, s + (self.rank + 1) * ss))
+            self._soff.append(so)
+            so += ss
+        self.shard_size = so
+        self.shard = [tuple(x) for x in self._slice]                 # flat ranges this rank owns
+        self.master = torch.cat([self.flat_param[a:b] for a, b in self._slice]).float()
         self.exp_avg = torch.zeros_like(self.master)
         self.exp_avg_sq = torch.zeros_like(self.master)
-        self.grad_shard = torch.zeros(self.shard_size, dtype=dtype, device=self.device) if self.world_size > 1 else None
+        self.grad_shard = torch.zeros(so, dtype=dtype, device=self.device) if W > 1 else None
         self._opt_step = [0] * len(groups)
+        self._stat = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._skipped = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # segment tables of the rank's slices: exclusive ends (relative to the slice start) and param group ids
+        self._segs = []
+        for (a, b) in self._slice:
+            ends, gids = [], []
+            for o, p, gi in zip(self._poff, ordered, self._pgroup):
+                pe = o + (p.numel() + 7) // 8 * 8
+                lo, hi = max(o, a), min(pe, b)
+                if lo < hi:
+                    ends.append(hi - a); gids.append(gi)
+            if not ends or ends[-1] < b - a:                     # bucket padding behind the last parameter
+                ends.append(b - a); gids.append(gids[-1] if gids else 0)
+            self._segs.append((torch.tensor(ends, dtype=torch.int64, device=self.device),
+                               torch.tensor(gids, dtype=torch.int32, device=self.device), ends, gids))
+
+    def _install_hooks(self):
+        self._hook_handles = []
+        self._pending = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._dirty = [False] * len(self.buckets)
+        self._works = []
+        self._bucket_np = [0] * len(self.buckets)
+        for b in self._pbucket:
+            self._bucket_np[b] += 1
+        if not (self._nccl and self.overlap_comm):
+            return
+        for p, b in zip(self._params, self._pbucket):
+            def hook(param, b=b):
+                if not self.is_gradient_accumulation_boundary():
+                    return
+                if self._launched[b]:
+                    self._dirty[b] = True                        # a gradient arrived after its bucket left: redo in step()
+                    return
+                self._pending[b] -= 1
+                if self._pending[b] == 0:
+                    self._launch_reduce(b)
+            self._hook_handles.append(p.register_post_accumulate_grad_hook(hook))
+        self._pending = list(self._bucket_np)
+
+    def _launch_reduce(self, b):
+        s, e = self.buckets[b]
+        so, ss = self._soff[b], (e - s) // self.world_size
+        self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self._comm_stream):
+            w = dist.reduce_scatter_tensor(self.grad_shard[so:so + ss], self.flat_grad[s:e], op=dist.ReduceOp.AVG,
+                                           async_op=True)
+        self._works.append(w)
+        self._launched[b] = True
 
     def _rebind_grads(self):
-        o = 0
-        for p in self._params:
+        for p, o in zip(self._params, self._poff):
             n = p.numel()
             if p.grad is None or p.grad.data_ptr() != self.flat_grad[o:o + n].data_ptr():
                 g = self.flat_grad[o:o + n].view(p.shape)
                 if p.grad is not None:                   # something replaced .grad (e.g. zero_grad(set_to_none))
                     g.add_(p.grad)
                 p.grad = g
-            o += n
 
     # -- module surface ----------------------------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -237,6 +330,15 @@ class Engine:
     def is_gradient_accumulation_boundary(self) -> bool:
         return (self.micro_steps + 1) % self.gradient_accumulation_steps == 0
 
+    @property
+    def global_grad_norm(self) -> float:
+        """Gradient norm of the last step (reads a device scalar: a host sync only when somebody asks)."""
+        return float(self._stat[0].sqrt())
+
+    @property
+    def skipped_steps(self) -> int:
+        return int(self._skipped.item())
+
     # -- training step --------------------------------------------------------------------------
     def backward(self, loss: torch.Tensor, **kwargs):
         self._rebind_grads()
@@ -245,6 +347,40 @@ class Engine:
         loss.backward()
         return loss
 
+    def _reduce_gradients(self):
+        """Every bucket's gradients averaged over the ranks into grad_shard (world_size > 1)."""
+        W = self.world_size
+        if self._nccl:
+            for b in range(len(self.buckets)):
+                if not self._launched[b] or self._dirty[b]:      # parameters that got no gradient / a late gradient
+                    self._launch_reduce(b)
+            for w in self._works:
+                w.wait()                                         # the compute stream waits for the exchange
+            self._works = []
+        else:           # gloo (CPU tests of the host logic) has no reduce-scatter
+            dist.all_reduce(self.flat_grad)
+            for (a, b), so in zip(self._slice, self._soff):
+                self.grad_shard[so:so + b - a].copy_(self.flat_grad[a:b]).div_(W)
+        self._pending = list(self._bucket_np)
+        self._launched = [False] * len(self.buckets)
+        self._dirty = [False] * len(self.buckets)
+
+    def _grad_of(self, b):
+        a, e = self._slice[b]
+        if self.world_size > 1:
+            return self.grad_shard[self._soff[b]:self._soff[b] + e - a]
+        return self.flat_grad[a:e]
+
+    def _group_hp(self):
+        hp = []
+        for gi, g in enumerate(self.optimizer.param_groups):
+            b1, b2 = g["betas"]
+            t = self._opt_step[gi]
+            bc = g.get("bias_correction", True)
+            hp.append((float(g["lr"]), float(g["weight_decay"]), 1.0 - b1 ** t if bc else 1.0,
+                       math.sqrt(1.0 - b2 ** t) if bc else 1.0))
+        return hp
+
     @torch.no_grad()
     def step(self):
         boundary = self.is_gradient_accumulation_boundary()
@@ -252,52 +388,131 @@ class Engine:
         if not boundary:
             return
         self._rebind_grads()
-        lo, hi = self.shard
-        if self.world_size > 1:
-            if dist.get_backend() == "nccl":
-                dist.reduce_scatter_tensor(self.grad_shard, self.flat_grad, op=dist.ReduceOp.AVG)
-            else:       # gloo (CPU tests of the host logic) has no reduce-scatter
-                dist.all_reduce(self.flat_grad)
-                self.grad_shard.copy_(self.flat_grad[lo:hi]).div_(self.world_size)
-            g = self.grad_shard
+        W = self.world_size
+        if W > 1:
+            self._reduce_gradients()
+        # global squared gradient norm and non-finite count: one small all-reduce, consumed on the device
+        self._stat.zero_()
+        if self._on_gpu:
+            L = _lib.lib()
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            with torch.cuda.device(self.device):
+                if W > 1:
+                    _lib.check(L.rwkvtts_grad_stat(self.grad_shard.data_ptr(), int(self.grad_shard.dtype == torch.bfloat16),
+                                                   self.grad_shard.numel(), self._stat.data_ptr(), st), "rwkvtts_grad_stat")
+                else:
+                    _lib.check(L.rwkvtts_grad_stat(self.flat_grad.data_ptr(), int(self.flat_grad.dtype == torch.bfloat16),
+                                                   self.flat_grad.numel(), self._stat.data_ptr(), st), "rwkvtts_grad_stat")
         else:
-            g = self.flat_grad[lo:hi]
-        # global gradient norm and non-finite check in one small all-reduce
-        gf = g.float()
-        stat = torch.stack([gf.pow(2).sum(), (~torch.isfinite(gf)).any().float()])
-        if self.world_size > 1:
-            dist.all_reduce(stat)
-        self.global_grad_norm = float(stat[0].sqrt())
-        if float(stat[1]) > 0 or not math.isfinite(self.global_grad_norm):
-            self.skipped_steps += 1              # same decision on every rank
-            self.flat_grad.zero_()
-            return
-        gscale = 1.0
-        if self.gradient_clipping > 0 and self.global_grad_norm > self.gradient_clipping:
-            gscale = self.gradient_clipping / (self.global_grad_norm + 1e-6)
-        pshard = self.flat_param[lo:hi]
+            gf = (self.grad_shard if W > 1 else self.flat_grad).float()
+            self._stat.copy_(torch.stack([gf.pow(2).sum(), (~torch.isfinite(gf)).sum().float()]))
+        if W > 1:
+            dist.all_reduce(self._stat)
         for gi in range(len(self._opt_step)):
             self._opt_step[gi] += 1
-        for (s, e, gi) in self._segments:
-            a, b = max(s, lo), min(e, hi)
-            if a >= b:
-                continue
-            sl = slice(a - lo, b - lo)
-            adam_update(self.master[sl], self.exp_avg[sl], self.exp_avg_sq[sl], g[sl], pshard[sl],
-                        self.optimizer.param_groups[gi], self._opt_step[gi], self.optimizer.adam_w_mode, gscale)
-        if self.world_size > 1:
-            if dist.get_backend() == "nccl":
-                dist.all_gather_into_tensor(self.flat_param, pshard)          # in place: pshard is rank's slice
+        hp = self._group_hp()
+        g0 = self.optimizer.param_groups[0]
+        b1, b2 = g0["betas"]
+        eps = float(g0["eps"])
+        _invalidate_param_cache()        # parameters are rewritten below without any version counter moving
+        gathers = []
+        for b, (a, e) in enumerate(self._slice):
+            so, n = self._soff[b], e - a
+            g = self._grad_of(b)
+            pslice = self.flat_param[a:e]
+            if self._on_gpu:
+                ends, gids, _, _ = self._segs[b]
+                hp_c = (ctypes.c_float * (4 * len(hp)))(*[x for h in hp for x in h])
+                with torch.cuda.device(self.device):
+                    rc = _lib.lib().rwkvtts_adam_multi(
+                        self.master[so:so + n].data_ptr(), self.exp_avg[so:so + n].data_ptr(),
+                        self.exp_avg_sq[so:so + n].data_ptr(), g.data_ptr(), int(g.dtype == torch.bfloat16),
+                        pslice.data_ptr(), int(pslice.dtype == torch.bfloat16), n, ends.data_ptr(), gids.data_ptr(),
+                        ends.numel(), hp_c, len(hp), b1, b2, eps, self.optimizer.adam_w_mode, self._stat.data_ptr(),
+                        self.gradient_clipping, self._skipped.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+                _lib.check(rc, "rwkvtts_adam_multi")
             else:
-                dist.all_gather(list(self.flat_param.chunk(self.world_size)), pshard.clone())
-        _invalidate_param_cache()     # the all-gather rewrote the other ranks' shards of the flat parameter buffer
+                self._cpu_adam(b, g, pslice, hp, b1, b2, eps)
+            if W > 1:
+                s, e2 = self.buckets[b]
+                if self._nccl:
+                    # in place (pslice is this rank's slice of the bucket); overlaps the next bucket's Adam kernel
+                    self._comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(self._comm_stream):
+                        gathers.append(dist.all_gather_into_tensor(self.flat_param[s:e2], pslice, async_op=True))
+                else:
+                    dist.all_gather(list(self.flat_param[s:e2].chunk(W)), pslice.clone())
+        for w in gathers:
+            w.wait()
+        _invalidate_param_cache()     # the all-gather rewrote the other ranks' slices of the flat parameter buffer
         self.flat_grad.zero_()
         self.global_steps += 1
         if self.lr_scheduler is not None:
             self.optimizer._opt_called = True     # the update ran above (on the shard): torch's scheduler order check looks here
             self.lr_scheduler.step()
 
+    def _cpu_adam(self, b, g, pslice, hp, b1, b2, eps):
+        """Host-logic twin of rwkvtts_adam_multi (gloo / CPU tests): same segment walk, same skip and clipping rule."""
+        norm = float(self._stat[0].sqrt())
+        if float(self._stat[1]) > 0 or not math.isfinite(norm):
+            if b == 0:
+                self._skipped += 1
+            return
+        gscale = 1.0
+        if self.gradient_clipping > 0 and norm > self.gradient_clipping:
+            gscale = self.gradient_clipping / (norm + 1e-6)
+        so = self._soff[b]
+        _, _, ends, gids = self._segs[b]
+        lo = 0
+        for hi, gi in zip(ends, gids):
+            sl = slice(so + lo, so + hi)
+            lr, wd, bc1, bc2s = hp[gi]
+            grp = {"lr": lr, "weight_decay": wd, "betas": (b1, b2), "eps": eps, "bias_correction": False}
+            m, v, w = self.exp_avg[sl], self.exp_avg_sq[sl], self.master[sl]
+            gg = g[lo:hi].float() * gscale
+            if not self.optimizer.adam_w_mode:
+                gg = gg + wd * w
+            m.mul_(b1).add_(gg, alpha=1 - b1)
+            v.mul_(b2).addcmul_(gg, gg, value=1 - b2)
+            upd = (m / bc1) / (v.sqrt() / bc2s + eps)
+            if self.optimizer.adam_w_mode:
+                upd = upd + wd * w
+            w.add_(upd, alpha=-lr)
+            pslice[lo:hi].copy_(w)
+            lo = hi
+
+    @torch.no_grad()
+    def profile_comm(self, iters: int = 5):
+        """Device time of the step's exchange in isolation (all buckets: reduce-scatter, then all-gather), ms; the
+        bench reports it next to the step time as the collective's share.  Leaves gradients zeroed."""
+        if not self._nccl:
+            self.comm_ms = {"reduce_scatter_ms": 0.0, "all_gather_ms": 0.0, "bytes_per_rank": 0}
+            return self.comm_ms
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        rs = ag = 0.0
+        for _ in range(iters):
+            torch.cuda.synchronize(self.device)
+            ev[0].record()
+            for b, (s, e) in enumerate(self.buckets):
+                so, ss = self._soff[b], (e - s) // self.world_size
+                dist.reduce_scatter_tensor(self.grad_shard[so:so + ss], self.flat_grad[s:e], op=dist.ReduceOp.AVG)
+            ev[1].record()
+            for b, (s, e) in enumerate(self.buckets):
+                a, e2 = self._slice[b]
+                dist.all_gather_into_tensor(self.flat_param[s:e], self.flat_param[a:e2])
+            ev[2].record()
+            torch.cuda.synchronize(self.device)
+            rs += ev[0].elapsed_time(ev[1]); ag += ev[1].elapsed_time(ev[2])
+        self.flat_grad.zero_()
+        self.comm_ms = {"reduce_scatter_ms": rs / iters, "all_gather_ms": ag / iters,
+                        "bytes_per_rank": self.padded * self.flat_grad.element_size(), "buckets": len(self.buckets)}
+        return self.comm_ms
+
     # -- checkpoints (DeepSpeed directory layout) --------------------------------------------------
+    def _layout(self):
+        return {"numel": self.numel, "padded": self.padded, "buckets": [list(b) for b in self.buckets],
+                "dp_world_size": self.world_size}
+
     def save_checkpoint(self, save_dir: str, tag: Optional[str] = None, client_state: Optional[dict] = None,
                         save_latest: bool = True):
         tag = tag if tag is not None else f"global_step{self.global_steps}"
@@ -306,18 +521,56 @@ class Engine:
         if self.rank == 0:
             sd = {k: v.detach().cpu() for k, v in self.module.state_dict().items()}
             torch.save({"module": sd, "global_steps": self.global_steps, "micro_steps": self.micro_steps,
-                        "skipped_steps": self.skipped_steps, "dp_world_size": self.world_size,
+                        "skipped_steps": self.skipped_steps, "layout": self._layout(),
+                        "dp_world_size": self.world_size,
                         "lr_scheduler": self.lr_scheduler.state_dict() if self.lr_scheduler is not None else None,
                         **(client_state or {})}, os.path.join(path, "mp_rank_00_model_states.pt"))
             if save_latest:
                 with open(os.path.join(save_dir, "latest"), "w") as f:
                     f.write(str(tag))
-        torch.save({"shard": self.shard, "padded": self.padded, "master": self.master.cpu(),
+        torch.save({"slices": [list(x) for x in self._slice], "layout": self._layout(), "master": self.master.cpu(),
                     "exp_avg": self.exp_avg.cpu(), "exp_avg_sq": self.exp_avg_sq.cpu(), "opt_step": self._opt_step,
                     "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.optimizer.param_groups]},
                    os.path.join(path, f"zero_pp_rank_{self.rank}_mp_rank_00_optim_states.pt"))
         if self.world_size > 1:
             dist.barrier()
+        return True
+
+    def _load_optimizer_states(self, path, saved_world):
+        """Restores master / moments for this rank's slices.  Same layout: the rank's own file.  Different world size
+        or bucket layout (same model): the saved ranks' slices are stitched into the full flat space and re-cut."""
+        files = [os.path.join(path, f"zero_pp_rank_{r}_mp_rank_00_optim_states.pt") for r in range(saved_world)]
+        mine = os.path.join(path, f"zero_pp_rank_{self.rank}_mp_rank_00_optim_states.pt")
+        if os.path.exists(mine):
+            os_ = torch.load(mine, map_location="cpu")
+            if os_.get("layout") == self._layout() and [list(x) for x in self._slice] == os_.get("slices"):
+                self.master.copy_(os_["master"]); self.exp_avg.copy_(os_["exp_avg"]); self.exp_avg_sq.copy_(os_["exp_avg_sq"])
+                self._opt_step = list(os_["opt_step"])
+                return True
+        if not all(os.path.exists(f) for f in files):
+            return False
+        full = None
+        for f in files:
+            os_ = torch.load(f, map_location="cpu")
+            if os_.get("layout", {}).get("numel") != self.numel:
+                return False
+            if full is None:
+                full = {k: torch.zeros(max(os_["layout"]["padded"], self.padded)) for k in ("master", "exp_avg", "exp_avg_sq")}
+            so = 0
+            for (a, b) in os_["slices"]:
+                for k in full:
+                    full[k][a:b] = os_[k][so:so + b - a]
+                so += b - a
+            step = list(os_["opt_step"])
+        # the flat order of parameters is fixed by the model; only the bucket padding can move offsets
+        if os_["layout"]["buckets"] != [list(b) for b in self.buckets] and len(os_["layout"]["buckets"]) != 1 \
+                and len(self.buckets) != 1:
+            return False
+        for (a, b), so in zip(self._slice, self._soff):
+            self.master[so:so + b - a].copy_(full["master"][a:b])
+            self.exp_avg[so:so + b - a].copy_(full["exp_avg"][a:b])
+            self.exp_avg_sq[so:so + b - a].copy_(full["exp_avg_sq"][a:b])
+        self._opt_step = step
         return True
 
     def load_checkpoint(self, load_dir: str, tag: Optional[str] = None, load_optimizer_states: bool = True, **kwargs):
@@ -333,15 +586,18 @@ class Engine:
             for k, v in ms["module"].items():
                 own[k].copy_(v)                       # in place: parameters keep aliasing the flat buffer
         self.global_steps, self.micro_steps = ms["global_steps"], ms["micro_steps"]
-        self.skipped_steps = ms.get("skipped_steps", 0)
-        lo, hi = self.shard
-        self.master.copy_(self.flat_param[lo:hi].float())
-        opt_file = os.path.join(path, f"zero_pp_rank_{self.rank}_mp_rank_00_optim_states.pt")
-        if load_optimizer_states and os.path.exists(opt_file) and ms.get("dp_world_size") == self.world_size:
-            os_ = torch.load(opt_file, map_location="cpu")
-            if tuple(os_["shard"]) == tuple(self.shard):
-                self.master.copy_(os_["master"]); self.exp_avg.copy_(os_["exp_avg"]); self.exp_avg_sq.copy_(os_["exp_avg_sq"])
-                self._opt_step = list(os_["opt_step"])
+        self._skipped.fill_(int(ms.get("skipped_steps", 0)))
+        self.master.copy_(torch.cat([self.flat_param[a:b] for a, b in self._slice]).float())
+        if load_optimizer_states:
+            ok = False
+            try:
+                ok = self._load_optimizer_states(path, int(ms.get("dp_world_size", self.world_size)))
+            except (OSError, KeyError, RuntimeError) as e:
+                warnings.warn(f"optimizer states of {path} could not be read: {e!r}")
+            if not ok:
+                warnings.warn(f"load_checkpoint({path}): optimizer states were requested but could not be restored for this "
+                              f"layout (saved world size {ms.get('dp_world_size')}, now {self.world_size}); Adam moments and "
+                              "bias correction restart from zero, fp32 master weights are rebuilt from the model weights")
         if self.lr_scheduler is not None and ms.get("lr_scheduler") is not None:
             self.lr_scheduler.load_state_dict(ms["lr_scheduler"])
         client = {k: v for k, v in ms.items() if k not in ("module", "lr_scheduler")}

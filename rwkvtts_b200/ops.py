@@ -35,6 +35,28 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# bench.py sets this to {"fwd": [], "bwd": []}: every launch of the training pair is then bracketed by CUDA events on
+# the launching stream, so the kernels' durations are measured inside the timed region of a whole-model step.
+TIMING = None
+
+
+class _timed:
+    def __init__(self, kind):
+        self.rec = TIMING[kind] if TIMING is not None else None
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.rec.append((self.e0, e1))
+        return False
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -47,7 +69,7 @@ def _need_cuda(*ts):
 def wkv7_forward_(w, q, k, v, z, a, y, s, sa, s0=None, sT=None):
     _need_cuda(w, q, k, v, z, a, y, s, sa, s0, sT)
     B, T, H, _ = w.shape
-    with torch.cuda.device(w.device):
+    with torch.cuda.device(w.device), _timed("fwd"):
         rc = _lib.lib().rwkvtts_wkv7_forward_ex(B, T, H, _ptr(w), _ptr(q), _ptr(k), _ptr(v), _ptr(z), _ptr(a),
                                                 _ptr(y), _ptr(s), _ptr(sa), _ptr(s0), _ptr(sT), _stream())
     _lib.check(rc, "rwkvtts_wkv7_forward")
@@ -66,7 +88,7 @@ def wkv7_forward_infer_(w, q, k, v, z, a, y, s0=None, sT=None):
 def wkv7_backward_(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0=None, dsT=None, ds0=None, sT=None):
     _need_cuda(w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da, s0, dsT, ds0, sT)
     B, T, H, _ = w.shape
-    with torch.cuda.device(w.device):
+    with torch.cuda.device(w.device), _timed("bwd"):
         rc = _lib.lib().rwkvtts_wkv7_backward_ex(B, T, H, _ptr(w), _ptr(q), _ptr(k), _ptr(v), _ptr(z), _ptr(a),
                                                  _ptr(dy), _ptr(s), _ptr(sa), _ptr(s0), _ptr(sT), _ptr(dsT), _ptr(dw),
                                                  _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dz), _ptr(da), _ptr(ds0),

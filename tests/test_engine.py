@@ -99,7 +99,7 @@ def test_nonfinite_gradient_skips_the_step():
     loss = torch.nn.functional.mse_loss(eng(x), y) * float("nan")
     eng.backward(loss)
     eng.step()
-    assert eng.skipped_steps == 1 and eng.global_steps == 1
+    assert eng.skipped_steps == 1 and eng.global_steps == 2      # DeepSpeed counts a skipped step as a step
     for a, b in zip(eng.parameters(), before):
         assert torch.equal(a, b)
 
@@ -127,7 +127,7 @@ def _worker(rank, world, port, out):
                       MASTER_PORT=str(port))
     torch.set_num_threads(1)
     eng = _engine_steps(4, rank=rank, world=world)
-    assert eng.world_size == world and eng.shard[0] == rank * eng.shard_size
+    assert eng.world_size == world and eng.shard[0][0] == eng.buckets[0][0] + rank * eng.shard_size
     if rank == 0:
         torch.save([p.detach().clone() for p in eng.parameters()], out)
     dist.barrier()
@@ -177,3 +177,67 @@ def test_optimizer_step_invalidates_the_no_grad_parameter_cache():
         w.mul_(2.0)
         c2 = fused.cached(w, (w,), "test", copy)
     assert len(calls) == 3 and torch.equal(c2, 2.0 * c1)
+
+
+def test_multiple_buckets_match_adamw(monkeypatch):
+    """Small buckets: the toy model is cut into several; slices, segment tables and the shard space must still give
+    exactly AdamW."""
+    monkeypatch.setenv("RWKVTTS_BUCKET_ELEMS", "300")
+    eng = _engine_steps(5)
+    assert len(eng.buckets) >= 2
+    for a, b in zip(eng.parameters(), _reference_steps(5)):
+        assert torch.allclose(a, b, atol=2e-6), (a - b).abs().max()
+
+
+def test_gradient_clipping_matches_torch():
+    import deepspeed
+    from deepspeed.ops.adam import FusedAdam
+    m = _model()
+    opt = FusedAdam(_groups(m), lr=1e-2, betas=(0.9, 0.95), eps=1e-18)
+    eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": False}, "gradient_clipping": 0.05},
+                                        model_parameters=m.parameters(), optimizer=opt)
+    ref = _model()
+    ropt = torch.optim.AdamW([{"params": g["params"], "weight_decay": g["weight_decay"]} for g in _groups(ref)],
+                             lr=1e-2, betas=(0.9, 0.95), eps=1e-18)
+    x, y = _data()
+    for _ in range(3):
+        eng.backward(torch.nn.functional.mse_loss(eng(x), y)); eng.step()
+        ropt.zero_grad(); torch.nn.functional.mse_loss(ref(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.05); ropt.step()
+    assert eng.global_grad_norm > 0.05
+    for a, b in zip(eng.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=5e-6), (a - b).abs().max()
+
+
+def _ckpt_worker(rank, world, port, d):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    eng = _engine_steps(3, rank=rank, world=world)
+    eng.save_checkpoint(d)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_checkpoint_saved_on_two_ranks_resumes_on_one(recwarn):
+    """Re-sharding: the two ranks' optimizer slices are stitched back and re-cut for world size 1; the next step equals
+    the uninterrupted single-process run (a resume on another GPU count silently restarted Adam)."""
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_ckpt_worker, args=(2, 29741 + os.getpid() % 200, d), nprocs=2, join=True)
+        eng = _engine_steps(0)
+        eng.load_checkpoint(d)
+        assert not [w for w in recwarn.list if "could not be restored" in str(w.message)]
+        x, y = _data()
+        eng.backward(torch.nn.functional.mse_loss(eng(x), y)); eng.step()
+    for a, b in zip(eng.parameters(), _reference_steps(4)):
+        assert torch.allclose(a, b, atol=3e-6), (a - b).abs().max()
+
+
+def test_missing_optimizer_state_warns():
+    eng = _engine_steps(2)
+    with tempfile.TemporaryDirectory() as d:
+        eng.save_checkpoint(d)
+        os.remove(os.path.join(d, "global_step2", "zero_pp_rank_0_mp_rank_00_optim_states.pt"))
+        eng2 = _engine_steps(0)
+        with pytest.warns(UserWarning, match="could not be restored"):
+            eng2.load_checkpoint(d)

@@ -1,0 +1,198 @@
+"""GPU side of the engine (round-1 VERDICT: csrc/adam.cu had no GPU test, the NCCL path had never run):
+
+* rwkvtts_adam_shard / rwkvtts_adam_multi / rwkvtts_grad_stat against torch.optim.AdamW with the reference's
+  hyper-parameters (betas (0.9, 0.95), eps 1e-18, train_spark_rwkv7speech_jsonl.py:195-199), fp32 and bf16 gradients;
+* the engine on one GPU (several buckets, several param groups, clipping, the device-side skip on non-finite gradients);
+* two ranks over NCCL (needs 2 GPUs; the driver's 8-GPU box runs it): reduce-scatter -> Adam -> all-gather equals the
+  single-process full-batch AdamW, with the bucketed exchange overlapping the backward.
+"""
+import math
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+B1, B2, EPS = 0.9, 0.95, 1e-18
+
+
+def _ref_adamw(w, grads, lr, wd, steps):
+    p = torch.nn.Parameter(w.clone().float())
+    opt = torch.optim.AdamW([p], lr=lr, betas=(B1, B2), eps=EPS, weight_decay=wd)
+    for g in grads[:steps]:
+        p.grad = g.float()
+        opt.step()
+    return p.detach()
+
+
+@pytest.mark.parametrize("gdt,pdt", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("n", [1, 7, 4096, 100003])
+def test_adam_shard_matches_torch_adamw(gdt, pdt, n):
+    from rwkvtts_b200.engine import adam_update
+    torch.manual_seed(n)
+    dev = "cuda"
+    w0 = torch.randn(n, device=dev)
+    grads = [(torch.randn(n, device=dev) * 0.1).to(gdt) for _ in range(4)]
+    master, m, v = w0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    param = w0.to(pdt)
+    grp = {"lr": 3e-3, "betas": (B1, B2), "eps": EPS, "weight_decay": 0.1, "bias_correction": True}
+    for t, g in enumerate(grads, 1):
+        adam_update(master, m, v, g, param, grp, t, 1, 1.0)
+    want = _ref_adamw(w0, grads, 3e-3, 0.1, 4)
+    assert torch.allclose(master, want, rtol=2e-5, atol=2e-6), (master - want).abs().max()
+    assert torch.equal(param, master.to(pdt))
+
+
+def test_adam_multi_segments_groups_clip_and_skip():
+    import ctypes
+    from rwkvtts_b200 import _lib
+    L = _lib.lib()
+    dev = "cuda"
+    torch.manual_seed(3)
+    sizes, gids = [1000, 24, 4096 * 3 + 8, 520], [0, 1, 0, 2]                  # multiples of 4 (the engine pads to 8)
+    hp = [(1e-2, 0.0), (2e-2, 0.0), (1e-2, 0.1)]
+    n = sum(sizes)
+    ends = torch.tensor([sum(sizes[:i + 1]) for i in range(len(sizes))], dtype=torch.int64, device=dev)
+    gid_t = torch.tensor(gids, dtype=torch.int32, device=dev)
+    w0 = torch.randn(n, device=dev)
+    grads = [(torch.randn(n, device=dev) * 0.3).bfloat16() for _ in range(3)]
+    master, m, v = w0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    param = w0.bfloat16()
+    stat = torch.zeros(2, device=dev)
+    skipped = torch.zeros(1, dtype=torch.int64, device=dev)
+    clip = 5.0
+    want = w0.clone()
+    refs = []
+    o = 0
+    for sz, gi in zip(sizes, gids):
+        refs.append((o, o + sz, gi)); o += sz
+    st = torch.cuda.current_stream().cuda_stream
+    ref_state = [(w0[a:b].clone(), torch.zeros(b - a, device=dev), torch.zeros(b - a, device=dev)) for a, b, _ in refs]
+    for t, g in enumerate(grads, 1):
+        stat.zero_()
+        assert L.rwkvtts_grad_stat(g.data_ptr(), 1, n, stat.data_ptr(), st) == 0
+        norm = float(g.float().norm())
+        assert abs(float(stat[0].sqrt()) - norm) < 1e-3 * norm and float(stat[1]) == 0
+        hp_c = (ctypes.c_float * 12)(*[x for (lr, wd) in hp for x in (lr, wd, 1 - B1 ** t, math.sqrt(1 - B2 ** t))])
+        assert L.rwkvtts_adam_multi(master.data_ptr(), m.data_ptr(), v.data_ptr(), g.data_ptr(), 1, param.data_ptr(), 1, n,
+                                    ends.data_ptr(), gid_t.data_ptr(), len(sizes), hp_c, 3, B1, B2, EPS, 1, stat.data_ptr(),
+                                    clip, skipped.data_ptr(), st) == 0
+        gs = clip / (norm + 1e-6) if norm > clip else 1.0
+        for (a, b, gi), (rw, rm, rv) in zip(refs, ref_state):
+            gg = g[a:b].float() * gs
+            rm.mul_(B1).add_(gg, alpha=1 - B1)
+            rv.mul_(B2).addcmul_(gg, gg, value=1 - B2)
+            upd = (rm / (1 - B1 ** t)) / (rv.sqrt() / math.sqrt(1 - B2 ** t) + EPS) + hp[gi][1] * rw
+            rw.add_(upd, alpha=-hp[gi][0])
+    want = torch.cat([rw for rw, _, _ in ref_state])
+    assert torch.allclose(master, want, rtol=3e-5, atol=3e-6), (master - want).abs().max()
+    assert torch.equal(param, master.bfloat16()) and int(skipped) == 0
+    # a non-finite gradient: nothing moves, the skip counter does
+    bad = grads[0].clone(); bad[17] = float("nan")
+    stat.zero_()
+    L.rwkvtts_grad_stat(bad.data_ptr(), 1, n, stat.data_ptr(), st)
+    before = master.clone()
+    L.rwkvtts_adam_multi(master.data_ptr(), m.data_ptr(), v.data_ptr(), bad.data_ptr(), 1, param.data_ptr(), 1, n,
+                         ends.data_ptr(), gid_t.data_ptr(), len(sizes), hp_c, 3, B1, B2, EPS, 1, stat.data_ptr(), clip,
+                         skipped.data_ptr(), st)
+    assert float(stat[1]) > 0 and torch.equal(master, before) and int(skipped) == 1
+
+
+def _toy(seed=0):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.Tanh(), torch.nn.Linear(200, 64), torch.nn.Tanh(),
+                               torch.nn.Linear(64, 8))
+
+
+def _groups(m):
+    dec = [p for n, p in m.named_parameters() if n.endswith("weight")]
+    nod = [p for n, p in m.named_parameters() if not n.endswith("weight")]
+    return [{"params": nod, "weight_decay": 0.0, "my_lr_scale": 2.0}, {"params": dec, "weight_decay": 0.1, "my_lr_scale": 1.0}]
+
+
+def test_engine_on_one_gpu_matches_adamw(monkeypatch):
+    import deepspeed
+    from deepspeed.ops.adam import FusedAdam
+    monkeypatch.setenv("RWKVTTS_BUCKET_ELEMS", "6000")
+    m = _toy()
+    opt = FusedAdam(_groups(m), lr=1e-2, betas=(B1, B2), eps=EPS)
+    eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": False}, "gradient_clipping": 0.5,
+                                                         "zero_optimization": {"stage": 2}},
+                                        model_parameters=m.parameters(), optimizer=opt)
+    assert eng.device.type == "cuda" and len(eng.buckets) >= 3
+    ref = _toy().cuda()
+    ropt = torch.optim.AdamW([{"params": g["params"], "weight_decay": g["weight_decay"]} for g in _groups(ref)], lr=1e-2,
+                             betas=(B1, B2), eps=EPS)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x, y = torch.randn(32, 96, device="cuda", generator=g), torch.randn(32, 8, device="cuda", generator=g)
+    for _ in range(4):
+        eng.backward(torch.nn.functional.mse_loss(eng(x), y)); eng.step()
+        ropt.zero_grad(); torch.nn.functional.mse_loss(ref(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.5); ropt.step()
+    for a, b in zip(eng.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+    assert eng.skipped_steps == 0
+    before = [p.detach().clone() for p in eng.parameters()]
+    eng.backward(torch.nn.functional.mse_loss(eng(x), y) * float("nan")); eng.step()
+    assert eng.skipped_steps == 1 and all(torch.equal(a, b) for a, b in zip(eng.parameters(), before))
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+os.environ["RWKVTTS_BUCKET_ELEMS"] = "6000"
+import deepspeed
+from deepspeed.ops.adam import FusedAdam
+import test_engine_gpu as T
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+deepspeed.init_distributed("nccl")
+m = T._toy().to(torch.bfloat16)
+opt = FusedAdam(T._groups(m), lr=1e-2, betas=(T.B1, T.B2), eps=T.EPS)
+eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": True}, "zero_optimization": {"stage": 2}},
+                                    model_parameters=m.parameters(), optimizer=opt)
+assert eng.world_size == world and eng._nccl and len(eng.buckets) >= 3
+g = torch.Generator(device="cuda").manual_seed(1)
+x, y = torch.randn(32, 96, device="cuda", generator=g).bfloat16(), torch.randn(32, 8, device="cuda", generator=g).bfloat16()
+n = 32 // world
+for _ in range(4):
+    eng.backward(torch.nn.functional.mse_loss(eng(x[rank * n:(rank + 1) * n]).float(), y[rank * n:(rank + 1) * n].float()))
+    eng.step()
+comm = eng.profile_comm(2)
+if rank == 0:
+    torch.save({"params": [p.detach().float().cpu() for p in eng.parameters()], "master": eng.master.cpu(), "comm": comm}, sys.argv[1])
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_over_nccl_match_single_process():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    with tempfile.TemporaryDirectory() as d:
+        script, out = os.path.join(d, "w.py"), os.path.join(d, "o.pt")
+        open(script, "w").write(WORKER % {"root": ROOT})
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), script, out],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        got = torch.load(out)
+    # the same 4 steps on one process with the full batch, bf16 model / fp32 master weights like the engine
+    import deepspeed
+    from deepspeed.ops.adam import FusedAdam
+    m = _toy().to(torch.bfloat16)
+    opt = FusedAdam(_groups(m), lr=1e-2, betas=(B1, B2), eps=EPS)
+    eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": True}, "zero_optimization": {"stage": 2}},
+                                        model_parameters=m.parameters(), optimizer=opt)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x, y = torch.randn(32, 96, device="cuda", generator=g).bfloat16(), torch.randn(32, 8, device="cuda", generator=g).bfloat16()
+    for _ in range(4):
+        eng.backward(torch.nn.functional.mse_loss(eng(x).float(), y.float())); eng.step()
+    for a, b in zip(got["params"], eng.parameters()):
+        assert torch.allclose(a, b.detach().float().cpu(), atol=2e-2, rtol=2e-2), (a - b.detach().float().cpu()).abs().max()
+    assert got["comm"]["reduce_scatter_ms"] > 0 and got["comm"]["all_gather_ms"] > 0
