@@ -154,6 +154,24 @@ RWKVTTS_API int rwkvtts_adam_multi(float *master, float *exp_avg, float *exp_avg
  * zeroed by the caller; the engine all-reduces it across ranks before rwkvtts_adam_multi). */
 RWKVTTS_API int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, void *stream);
 
+/* ---- caller side of the path: batch assembly and the loss head -------------------
+ * rwkvtts_embed_rows: the padded [rows, D] bf16 embedding batch of a speech layout in one kernel.  Replaces the
+ * per-sample nn.Embedding lookups + torch.cat + pad_sequence of the reference's batch builders
+ * (data/utils/spark_dataset.py:163-239, utils/multiple_jsonl.py:4-75, inference/rwkv7speech_inference.py:35-67,
+ * model/llm/cosy_llm.py:64-73).  tables: HOST array of ntab (<= 8) device pointers to bf16 [n_i, D] tables;
+ * row_src (device, int64 [rows]): (table << 40) | row for every output position, negative = padding (zeros).
+ * D % 8 == 0. */
+RWKVTTS_API int rwkvtts_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows,
+                                   int D, void *out, void *stream);
+/* rwkvtts_ce_forward_backward: cross-entropy of a chunk of bf16 logits [rows, ld] (V valid columns, ld % 8 == 0),
+ * loss and gradient in one pass, IN PLACE: loss_rows[r] (fp32) and logits[r,:] <- d loss / d logits * *scale_dev.
+ * Rows with labels[r] == ignore_index give loss 0 and a zero gradient row.  The middle piece of the fused
+ * linear + CE head the reference reaches through rwkvfla's FusedLinearCrossEntropyLoss (model/llm/spark_llm.py:139-158;
+ * label_smoothing as third_party/cosyvoice/transformer/label_smoothing_loss.py:68-96 in closed form). */
+RWKVTTS_API int rwkvtts_ce_forward_backward(void *logits, long long rows, int V, long long ld, const long long *labels,
+                                            long long ignore_index, float label_smoothing, const float *scale_dev,
+                                            float *loss_rows, void *stream);
+
 /* ---- fused elementwise kernels of the time-mix around the WKV-7 op ---------------------------------------------
  * Replace the ~30 ATen elementwise kernels RWKV_Tmix_x070.forward runs per layer between its GEMMs
  * (model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226).

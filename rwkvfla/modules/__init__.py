@@ -52,21 +52,29 @@ class FusedLinearCrossEntropyLoss(nn.Module):
         self.ignore_index, self.label_smoothing = ignore_index, label_smoothing
         self.num_chunks, self.reduction, self.use_l2warp = num_chunks, reduction, use_l2warp
 
-    def _chunk(self, h, y, weight, bias):
+    def _chunk(self, h, y, weight, bias, l2_factor=0.0):
         logits = F.linear(h, weight, bias).float()
-        return F.cross_entropy(logits, y, ignore_index=self.ignore_index, reduction="sum",
+        loss = F.cross_entropy(logits, y, ignore_index=self.ignore_index, reduction="sum",
                                label_smoothing=self.label_smoothing)
+        if l2_factor:
+            loss = l2_warp(loss, logits.unsqueeze(0), l2_factor)       # [1, n, V]: l2_warp divides by the first two dims
+        return loss
 
     def forward(self, x, target, weight, bias=None):
         h = x.reshape(-1, x.shape[-1])
         y = target.reshape(-1)
+        if core.FUSED and not self.use_l2warp and self.reduction in ("mean", "sum") and fused.linear_ce_usable(h, weight, bias):
+            # CUDA bf16: logits GEMM -> CE kernel (loss + gradient in place) -> gradient GEMMs, chunk by chunk
+            return fused.linear_cross_entropy(h, y, weight, self.ignore_index, self.label_smoothing, self.reduction)
         n = max(1, min(self.num_chunks, h.shape[0]))
         total = h.new_zeros((), dtype=torch.float32)
         for hc, yc in zip(h.chunk(n), y.chunk(n)):
+            # l2_warp (rwkvfla.modules.l2warp): gradient 1e-4 / tokens on each row's max logit
+            l2f = 1e-4 * hc.shape[0] / max(1, h.shape[0]) if self.use_l2warp else 0.0
             if torch.is_grad_enabled() and (hc.requires_grad or weight.requires_grad):
-                total = total + checkpoint(self._chunk, hc, yc, weight, bias, use_reentrant=False)
+                total = total + checkpoint(self._chunk, hc, yc, weight, bias, l2f, use_reentrant=False)
             else:
-                total = total + self._chunk(hc, yc, weight, bias)
+                total = total + self._chunk(hc, yc, weight, bias, l2f)
         if self.reduction == "sum":
             return total
         return total / (y != self.ignore_index).sum().clamp(min=1)

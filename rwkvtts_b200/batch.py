@@ -22,6 +22,38 @@ import numpy as np
 import torch
 
 
+def _gather(tables, order, ids, dst, total, row_src=None):
+    """The [total, D] batch from per-table (ids, destination rows).  CUDA bf16 tables: ONE kernel writes every row once
+    (csrc/gather.cu through fused.embed_rows; `row_src` = (table << 40) | id per row, -1 = padding, built on the device
+    when the caller has no host copy).  Otherwise one lookup and one scatter per table into a zero-filled buffer."""
+    from . import core, fused
+    weights = [tables[k].weight for k in order]
+    used = [j for j, k in enumerate(order) if ids[j].numel()]
+    if core.FUSED and fused.gather_usable(weights):
+        if row_src is None:
+            row_src = torch.full((total,), -1, dtype=torch.long, device=weights[0].device)
+            for j in used:
+                row_src.index_copy_(0, dst[j], ids[j].to(torch.long) + (j << fused.TABLE_SHIFT))
+        return fused.embed_rows(weights, row_src, [ids[j] for j in range(len(order))], [dst[j] for j in range(len(order))])
+    out = None
+    for j in used:
+        emb = tables[order[j]](ids[j])
+        if out is None:
+            out = torch.zeros(total, emb.shape[-1], dtype=emb.dtype, device=emb.device)
+        out.index_copy_(0, dst[j], emb)
+    return out
+
+
+def _row_src(order, ids, dst, total):
+    """Host twin of the device construction in _gather: int64 [total], (table << 40) | id, -1 for padding."""
+    from . import fused
+    rs = np.full(total, -1, dtype=np.int64)
+    for j, k in enumerate(order):
+        if len(ids[k]):
+            rs[np.asarray(dst[k], dtype=np.int64)] = np.asarray(ids[k], dtype=np.int64) + (j << fused.TABLE_SHIFT)
+    return rs
+
+
 def create_inputs_and_labels(batch: Dict[str, Any], tokenizer, model, eos_token_id: int, device) -> Dict[str, torch.Tensor]:
     texts = batch["text"]
     glob = batch["global_tokens"]
@@ -56,23 +88,17 @@ def create_inputs_and_labels(batch: Dict[str, Any], tokenizer, model, eos_token_
     sizes = [len(ids[k]) for k in order]
     packed = np.concatenate([np.asarray(ids[k], dtype=np.int64) for k in order]
                             + [np.asarray(dst[k], dtype=np.int64) for k in order]
-                            + [labels.reshape(-1), mask.reshape(-1)])
+                            + [labels.reshape(-1), mask.reshape(-1), _row_src(order, ids, dst, B * Tmax)])
     packed_t = torch.from_numpy(packed)
     if torch.device(device).type == "cuda":
         packed_t = packed_t.pin_memory().to(device, non_blocking=True)
     else:
         packed_t = packed_t.to(device)
-    cuts = np.cumsum([0] + sizes + sizes + [B * Tmax, B * Tmax])
+    cuts = np.cumsum([0] + sizes + sizes + [B * Tmax, B * Tmax, B * Tmax])
     part = [packed_t[cuts[j]:cuts[j + 1]] for j in range(len(cuts) - 1)]
     tables = {"tag": model.tts_tag_embedder, "text": model.text_embedder, "global": model.global_embedder,
               "semantic": model.model.embeddings}
-    first = tables["semantic"](part[3])
-    out = torch.zeros(B * Tmax, first.shape[-1], dtype=first.dtype, device=first.device)
-    for j, k in enumerate(order):
-        if sizes[j] == 0:
-            continue
-        emb = first if k == "semantic" else tables[k](part[j])
-        out.index_copy_(0, part[4 + j], emb)
+    out = _gather(tables, order, part[0:4], part[4:8], B * Tmax, row_src=part[10])
     return {"input_embs": out.view(B, Tmax, -1), "labels": part[8].view(B, Tmax), "attention_mask": part[9].view(B, Tmax)}
 
 
@@ -121,12 +147,11 @@ def process_single_batch(batch: Dict[str, torch.Tensor], rwkv7speech_model, eos_
     s_text, s_glob, s_sem, d_tag, d_text, d_glob, d_sem, d_lab, d_eos, m_flat = part
     tok = {"text": ids_t.to(device).reshape(-1)[s_text], "global": ids_g.to(device).reshape(-1)[s_glob],
            "semantic": ids_s.to(device).reshape(-1)[s_sem]}
-    tables = {"text": model.text_embedder, "global": model.global_embedder, "semantic": model.model.embeddings}
-    tag = model.tts_tag_embedder(torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(B))
-    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=device).index_copy_(0, d_tag, tag)
-    for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
-        if tok[k].numel():
-            out.index_copy_(0, d_k, tables[k](tok[k]))
+    tables = {"tag": model.tts_tag_embedder, "text": model.text_embedder, "global": model.global_embedder,
+              "semantic": model.model.embeddings}
+    tag_ids = torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(B)
+    out = _gather(tables, ("tag", "text", "global", "semantic"), [tag_ids, tok["text"], tok["global"], tok["semantic"]],
+                  [d_tag, d_text, d_glob, d_sem], B * Tmax)
     labels = torch.full((B * Tmax,), -100, dtype=torch.long, device=device)
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)
@@ -172,11 +197,7 @@ def create_inputs(texts, global_tokens_ids, semantic_tokens_ids, tokenizer, llm,
     part = [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
     tables = {"tag": llm.tts_tag_embedder, "text": llm.text_embedder, "global": llm.global_embedder,
               "semantic": llm.model.embeddings}
-    tag = tables["tag"](part[0])
-    out = torch.zeros(B * Tmax, tag.shape[-1], dtype=tag.dtype, device=tag.device).index_copy_(0, part[4], tag)
-    for j, k in enumerate(order[1:], start=1):
-        if len(ids[k]):
-            out.index_copy_(0, part[4 + j], tables[k](part[j]))
+    out = _gather(tables, order, part[0:4], part[4:8], B * Tmax)
     return out.view(B, Tmax, -1), part[8].view(B, Tmax)
 
 
@@ -215,11 +236,7 @@ def create_inputs_and_labels_culens(batch: Dict[str, Any], tokenizer, model, eos
     part = [packed[cuts[j]:cuts[j + 1]] for j in range(len(arrays))]
     tables = {"tag": model.tts_tag_embedder, "text": model.text_embedder, "global": model.global_embedder,
               "semantic": model.model.embeddings}
-    first = tables["semantic"](part[3])
-    out = torch.zeros(cu[-1], first.shape[-1], dtype=first.dtype, device=first.device)
-    for j, k in enumerate(order):
-        if len(ids[k]):
-            out.index_copy_(0, part[4 + j], first if k == "semantic" else tables[k](part[j]))
+    out = _gather(tables, order, part[0:4], part[4:8], cu[-1])
     return {"input_embs": out.unsqueeze(0), "labels": part[8].unsqueeze(0), "cu_seqlens": part[9]}
 
 
@@ -272,16 +289,9 @@ def _assemble_rows(rows, model, device, packed: bool):
         tail = starts
     else:
         tail = (np.arange(Tmax)[None, :] < np.asarray(lens)[:, None]).astype(np.int64)
-    part = _to_device([ids[k] for k in _ORDER] + [dst[k] for k in _ORDER] + [labels, tail], device)
-    tables = _tables(model)
-    out = None
-    for j, k in enumerate(_ORDER):
-        if not len(ids[k]):
-            continue
-        emb = tables[k](part[j])
-        if out is None:
-            out = torch.zeros(total, emb.shape[-1], dtype=emb.dtype, device=emb.device)
-        out.index_copy_(0, part[4 + j], emb)
+    part = _to_device([ids[k] for k in _ORDER] + [dst[k] for k in _ORDER] + [labels, tail, _row_src(_ORDER, ids, dst, total)],
+                      device)
+    out = _gather(_tables(model), _ORDER, part[0:4], part[4:8], total, row_src=part[10])
     if packed:
         return out.unsqueeze(0), part[8].unsqueeze(0), part[9]
     return out.view(R, Tmax, -1), part[8].view(R, Tmax), part[9].view(R, Tmax)
@@ -376,12 +386,9 @@ def process_single_batch_culens(batch, rwkv7speech_model, eos_token_id: int = 81
     s_text, s_glob, s_sem, d_tag, d_text, d_glob, d_sem, d_lab, d_eos, cu_t = part
     tok = {"text": ids_t.to(device).reshape(-1)[s_text], "global": ids_g.to(device).reshape(-1)[s_glob],
            "semantic": ids_s.to(device).reshape(-1)[s_sem]}
-    tables = _tables(model)
-    tag = tables["tag"](torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(n_rows))
-    out = torch.zeros(base, tag.shape[-1], dtype=tag.dtype, device=device).index_copy_(0, d_tag, tag)
-    for k, d_k in (("text", d_text), ("global", d_glob), ("semantic", d_sem)):
-        if tok[k].numel():
-            out.index_copy_(0, d_k, tables[k](tok[k]))
+    tag_ids = torch.tensor([2, 0, 1], dtype=torch.long, device=device).repeat(n_rows)
+    out = _gather(_tables(model), _ORDER, [tag_ids, tok["text"], tok["global"], tok["semantic"]],
+                  [d_tag, d_text, d_glob, d_sem], base)
     labels = torch.full((base,), -100, dtype=torch.long, device=device)
     labels.index_copy_(0, d_lab, tok["semantic"].to(torch.long))
     labels.index_fill_(0, d_eos, eos_token_id)

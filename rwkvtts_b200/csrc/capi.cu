@@ -71,6 +71,11 @@ cudaError_t launch_adam_multi(float *master, float *m, float *v, const void *gra
                               const float *group_hp, int ngroups, float b1, float b2, float eps, int adamw,
                               const float *stat, float clip, unsigned long long *skipped, cudaStream_t st);
 cudaError_t launch_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, cudaStream_t st);
+cudaError_t launch_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows, int D,
+                              void *out, cudaStream_t st);
+cudaError_t launch_ce_fwd_bwd(void *logits, long long rows, int V, long long ld, const long long *labels,
+                              long long ignore_index, float label_smoothing, const float *scale_dev, float *loss_rows,
+                              cudaStream_t st);
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
@@ -294,6 +299,30 @@ int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *st
     if (grad == nullptr || stat == nullptr) return RWKVTTS_ERR_NULL;
     if (reinterpret_cast<uintptr_t>(grad) & 7u) return RWKVTTS_ERR_ALIGN;
     return finish(rwkvtts::launch_grad_stat(grad, grad_is_bf16, n, stat, (cudaStream_t)stream));
+}
+
+int rwkvtts_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows, int D, void *out,
+                       void *stream) {
+    if (ntab <= 0 || ntab > 8 || rows < 0 || D <= 0 || D % 8 != 0) return RWKVTTS_ERR_SHAPE;
+    if (rows == 0) return RWKVTTS_OK;
+    if (tables == nullptr) return RWKVTTS_ERR_NULL;
+    for (int i = 0; i < ntab; i++)
+        if (int rc = check_ptrs({tables[i]})) return rc;
+    if (int rc = check_ptrs({out})) return rc;
+    if (row_src == nullptr) return RWKVTTS_ERR_NULL;
+    return finish(rwkvtts::launch_embed_rows(tables, ntab, row_src, rows, D, out, (cudaStream_t)stream));
+}
+
+int rwkvtts_ce_forward_backward(void *logits, long long rows, int V, long long ld, const long long *labels,
+                                long long ignore_index, float label_smoothing, const float *scale_dev, float *loss_rows,
+                                void *stream) {
+    if (rows < 0 || V <= 0 || ld < V || ld % 8 != 0 || label_smoothing < 0.f || label_smoothing >= 1.f)
+        return RWKVTTS_ERR_SHAPE;
+    if (rows == 0) return RWKVTTS_OK;
+    if (int rc = check_ptrs({logits})) return rc;
+    if (labels == nullptr || scale_dev == nullptr || loss_rows == nullptr) return RWKVTTS_ERR_NULL;
+    return finish(rwkvtts::launch_ce_fwd_bwd(logits, rows, V, ld, labels, ignore_index, label_smoothing, scale_dev,
+                                             loss_rows, (cudaStream_t)stream));
 }
 
 // ---- fused time-mix elementwise kernels ------------------------------------------------------------------------

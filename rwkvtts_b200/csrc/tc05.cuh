@@ -158,13 +158,21 @@ static __device__ unsigned long long *g_wd_rec = nullptr;              // one co
 static __device__ unsigned int g_wd_kernel = 0;
 static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity, unsigned long long waited) {
     extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
-    unsigned long long *r = g_wd_rec;
-    if (r != nullptr && atomicCAS_system(r, 0ull, kWatchdogMagic) == 0ull) {
-        r[1] = g_wd_kernel;
-        r[2] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
-        r[3] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
-        r[4] = waited;
-        __threadfence_system();
+    volatile unsigned long long *r = g_wd_rec;
+    if (r != nullptr) {
+        if (atomicCAS_system(g_wd_rec, 0ull, kWatchdogMagic) == 0ull) {
+            r[1] = g_wd_kernel;
+            r[2] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
+            r[3] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+            r[4] = waited;
+            __threadfence_system();
+            r[5] = 1ull;                       // record complete
+            __threadfence_system();
+        }
+        // nobody traps before the record is in host memory: a trap aborts the whole grid, stores in flight included
+        // (first version: the record came back with only one field written)
+        const long long t0 = clock64();
+        while (r[5] == 0ull && clock64() - t0 < 200000000ll) {}
     }
     __trap();
 }

@@ -340,3 +340,112 @@ def add_layernorm(x, residual, weight, bias, eps):
     """(LayerNorm(x + residual) * weight + bias, x + residual); residual may be None (then the second result is x).
     forward stats are kept only when a backward can follow (no_grad: inference / decode)."""
     return _AddLayerNorm.apply(x, residual, weight, bias, eps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# caller side of the path: embedding gather / concat of a speech layout, and the fused linear + cross-entropy head
+# (kernels: csrc/gather.cu, csrc/linear_ce.cu; SURVEY.md section 8 rows a13 / f2)
+# ---------------------------------------------------------------------------------------------------------------
+TABLE_SHIFT = 40                      # row_src = (table << 40) | row, negative = padding
+
+
+def gather_usable(weights) -> bool:
+    w0 = weights[0]
+    return (w0.is_cuda and all(w.dtype == BF16 and w.is_contiguous() and w.shape[1] == w0.shape[1] for w in weights)
+            and w0.shape[1] % 8 == 0 and len(weights) <= 8)
+
+
+class _EmbedRows(torch.autograd.Function):
+    """out[r] = weights[table(r)][row(r)] for every position of the padded / packed batch, zeros where row_src < 0: one
+    kernel instead of a lookup and a scatter per table into a zero-filled buffer.  Backward: what nn.Embedding does,
+    per table, on the rows that came from it (aten::embedding_dense_backward, so the numerics of the tables' gradients
+    are the reference's)."""
+
+    @staticmethod
+    def forward(ctx, row_src, n_tables, *rest):
+        weights, ids, dst = rest[:n_tables], rest[n_tables:2 * n_tables], rest[2 * n_tables:]
+        rows, D = row_src.numel(), weights[0].shape[1]
+        out = torch.empty(rows, D, dtype=BF16, device=row_src.device)
+        tabs = _ptr_array(weights)
+        with torch.cuda.device(row_src.device):
+            rc = _lib.lib().rwkvtts_embed_rows(tabs, n_tables, _ptr(row_src), rows, D, _ptr(out), _stream())
+        _lib.check(rc, "rwkvtts_embed_rows")
+        ctx.n_tables, ctx.sizes = n_tables, [w.shape[0] for w in weights]
+        ctx.save_for_backward(*ids, *dst)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        n = ctx.n_tables
+        ids, dst = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        grads = []
+        for k in range(n):
+            if not ctx.needs_input_grad[2 + k] or ids[k].numel() == 0:
+                grads.append(None)
+                continue
+            g = d_out.index_select(0, dst[k])
+            grads.append(torch.ops.aten.embedding_dense_backward(g, ids[k], ctx.sizes[k], -1, False))
+        return (None, None, *grads, *([None] * (2 * n)))
+
+
+def embed_rows(weights, row_src, ids, dst):
+    """weights: embedding tables [n_k, D] bf16; row_src int64 [rows] on the device; ids[k] / dst[k]: the rows taken from
+    table k and where they went (for the tables' gradients).  Returns [rows, D]."""
+    _need_cuda(row_src, *weights)
+    return _EmbedRows.apply(row_src, len(weights), *weights, *ids, *dst)
+
+
+def linear_ce_usable(h, weight, bias) -> bool:
+    return (h.is_cuda and h.dtype == BF16 and weight.dtype == BF16 and bias is None and h.shape[-1] % 8 == 0
+            and weight.shape[0] <= (1 << 20))
+
+
+class _LinearCE(torch.autograd.Function):
+    """mean / sum cross-entropy of h @ W^T against labels without the [tokens, V] logits: per token chunk one cuBLAS
+    GEMM for the logits, the CE kernel (loss and d logits in one in-place pass), and the two gradient GEMMs -- all in
+    the forward; the backward only scales by the incoming gradient.  dW accumulates in fp32 across the chunks."""
+
+    @staticmethod
+    def forward(ctx, h, labels, weight, ignore_index, label_smoothing, reduction, chunk_rows):
+        N, D = h.shape
+        V = weight.shape[0]
+        Vp = (V + 7) // 8 * 8
+        Wp = weight if Vp == V else torch.nn.functional.pad(weight, (0, 0, 0, Vp - V))       # aligned tensor-core GEMMs
+        valid = labels != ignore_index
+        if reduction == "mean":
+            scale = (1.0 / valid.sum().clamp(min=1).to(torch.float32)).reshape(1)
+        else:
+            scale = torch.ones(1, dtype=torch.float32, device=h.device)
+        loss_rows = torch.empty(N, dtype=torch.float32, device=h.device)
+        need = torch.is_grad_enabled() or h.requires_grad or weight.requires_grad
+        dh = torch.empty_like(h) if need else None
+        dW = torch.zeros(Vp, D, dtype=torch.float32, device=h.device) if need else None
+        L = _lib.lib()
+        for s in range(0, N, chunk_rows):
+            e = min(N, s + chunk_rows)
+            hc = h[s:e]
+            logits = torch.mm(hc, Wp.t())
+            with torch.cuda.device(h.device):
+                rc = L.rwkvtts_ce_forward_backward(_ptr(logits), e - s, V, Vp, _ptr(labels[s:e]), int(ignore_index),
+                                                   float(label_smoothing), _ptr(scale), _ptr(loss_rows[s:e]), _stream())
+            _lib.check(rc, "rwkvtts_ce_forward_backward")
+            if need:
+                torch.mm(logits, Wp, out=dh[s:e])
+                dW += torch.mm(logits.t(), hc, out_dtype=torch.float32)
+        loss = loss_rows.sum() * scale[0]
+        if need:
+            ctx.save_for_backward(dh, dW[:V].to(BF16))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dh, dW = ctx.saved_tensors
+        g = g.to(torch.float32)
+        return (dh * g).to(dh.dtype), None, (dW * g).to(dW.dtype), None, None, None, None
+
+
+def linear_cross_entropy(h, labels, weight, ignore_index=-100, label_smoothing=0.0, reduction="mean", chunk_rows=4096):
+    """h [N, D] bf16, labels [N] int64, weight [V, D] bf16 -> scalar fp32 loss (see _LinearCE)."""
+    _need_cuda(h, labels, weight)
+    return _LinearCE.apply(h.contiguous(), labels.contiguous(), weight.contiguous(), ignore_index, label_smoothing,
+                           reduction, chunk_rows)

@@ -268,3 +268,32 @@ def test_kernel_families_agree_at_c5_shape(R):
         assert torch.isfinite(a.float()).all(), name
         # both sides are bf16-rounded (1.6e-3 each); the scan backward un-steps the state, which costs it accuracy on dw
         assert O.rel_l2(a.float().cpu(), b.float().cpu()) < (2e-2 if name == "dw" else 6e-3), name
+
+
+@pytest.mark.parametrize("B,T,H,slices", [(8, 4096, 16, [(3, 5), (7, 15), (0, 0)]), (2, 8192, 32, [(1, 31), (0, 7)])],
+                         ids=["c2", "c5"])
+def test_full_size_forward_and_backward_slices_vs_oracle(impl, B, T, H, slices):
+    """BASELINE configs c2 / c5 at FULL size, both kernel families: y and all six gradients of sampled (batch, head)
+    slices against the f64 oracle (the recurrence of one (b,h) does not depend on the others, so a slice of the full
+    launch is the oracle's single-head problem; round-1 VERDICT: the backward had no oracle check at c2).  The raw
+    relative-L2 error is printed next to the excess over the bf16 floor the bar is applied to."""
+    R = impl
+    x = O.make_inputs(B, T, H, seed=T + H)
+    d = _dev(x)
+    leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
+    y = R.WindBackstepping.apply(*leaves)
+    y.backward(d["dy"])
+    torch.cuda.synchronize()
+    scan = R._lib.lib().rwkvtts_get_impl() == 0
+    for (b, h) in slices:
+        sl = lambda t: t[b:b + 1, :, h:h + 1].contiguous()
+        y64, _ = O.wkv7_forward(*[sl(x[n]) for n in ORDER])
+        g64 = O.wkv7_backward(*[sl(x[n]) for n in ORDER], sl(x["dy"]))
+        rows = [("y", sl(y.detach().cpu()), y64)] + [("d" + n, sl(l.grad.cpu()), g) for n, l, g in zip(ORDER, leaves, g64)]
+        for name, got, ref in rows:
+            exc, err, floor = O.excess_rel_l2(got, ref)
+            print(f"[{'scan' if scan else 'tcgen05'} {B}x{T}x{H} b={b} h={h}] {name}: rel-L2 {err:.3e}, bf16 floor {floor:.3e}, excess {exc:.3e}")
+            # the scan family un-steps the state by dividing by the decay (the reference's scheme, wkv7_cuda.cu:91-94):
+            # over 4096+ tokens that costs its dw accuracy, exactly as it does the reference kernel
+            tol = 5e-3 if (scan and name == "dw") else TOL
+            assert exc <= tol, f"{name} b={b} h={h}: excess {exc:.3e} (err {err:.3e}, floor {floor:.3e})"
