@@ -518,7 +518,19 @@ def leg_decode():
     try:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import decode_parity
-        out["greedy_ids_identical_vs_reference"] = decode_parity.compare(m, ids, seq[:, PROMPT:], NEW)
+        # exact mode (the reference's operations one for one, csrc/wkv7_step_exact.cu): must be identical
+        kwx = dict(kw, exact=True)
+        m.generate(max_new_tokens=short, **kwx); torch.cuda.synchronize()
+        t0 = time.perf_counter(); m.generate(max_new_tokens=short, **kwx); torch.cuda.synchronize()
+        tx_short = time.perf_counter() - t0
+        t0 = time.perf_counter(); seqx = m.generate(max_new_tokens=NEW, **kwx); torch.cuda.synchronize()
+        dtx = time.perf_counter() - t0 - tx_short
+        out["exact_mode"] = {"tokens_per_s": DB * (NEW - short) / dtx, "ms_per_step": dtx / (NEW - short) * 1e3}
+        out["greedy_ids_identical_vs_reference"] = decode_parity.compare(m, ids, seqx[:, PROMPT:], NEW)
+        out["greedy_ids_identical_vs_reference"]["path"] = "generate(exact=True)"
+        # the default fast path (fused kernels, fp32 intermediates): agreement rate and how close the reference's own
+        # top-2 logits are wherever it picks another id
+        out["fast_path_vs_reference"] = decode_parity.compare(m, ids, seq[:, PROMPT:], NEW)
     except Exception as e:
         out["greedy_ids_identical_vs_reference"] = {"error": repr(e)}
     return out

@@ -73,6 +73,14 @@ RWKVTTS_API int rwkvtts_last_cuda_error(void);
 RWKVTTS_API int rwkvtts_set_impl(int impl);
 RWKVTTS_API int rwkvtts_get_impl(void);
 
+/* Arithmetic of the stateful forward / decode step (rwkvtts_wkv7_state_forward): 0 = fast (default: four lanes per
+ * state row, fused-multiply-add forms chosen for speed; outputs agree with the reference kernel to fp32 rounding),
+ * 1 = the reference's operation order (rwkv7_state_fwd_fp16.cu:36-52, wkv7s.cu same lines): y and the state are
+ * bit-identical to the reference kernels, which is what "identical greedy token ids" needs.  Initial value from env
+ * RWKVTTS_STEP_MODE ("exact" -> 1). */
+RWKVTTS_API int rwkvtts_set_step_mode(int mode);
+RWKVTTS_API int rwkvtts_get_step_mode(void);
+
 /* Process-wide count of CUDA kernels this library has launched (evidence for bench.py's
  * "gpu_launches": every kernel of the path goes through the entry points below). */
 RWKVTTS_API long long rwkvtts_kernel_launches(void);

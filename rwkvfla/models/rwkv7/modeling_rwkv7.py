@@ -378,13 +378,24 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
                  eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
                  use_cache: bool = True, generator: Optional[torch.Generator] = None,
                  return_dict_in_generate: bool = False, use_cuda_graph: Optional[bool] = None,
-                 eos_check_interval: int = 1, **kwargs):
+                 eos_check_interval: int = 1, exact: bool = False, **kwargs):
         """Autoregressive decode over the recurrent Cache (the call inference/rwkv7speech_inference.py and
         spark_llm.py:54-102 make).  Returns [B, prompt + new] token ids when `input_ids` is given and
         [B, new] when only `inputs_embeds` is given (HF convention); finished rows are padded with
         `pad_token_id`.  On CUDA the per-token step runs as one CUDA graph (`use_cuda_graph`, default on when more than 8
         tokens are requested); `eos_check_interval` > 1 polls the all-finished flag (a host sync) only every that many
         steps (finished rows are padded either way, so the result does not change)."""
+        if exact:
+            # the reference decode step operation for operation (core.exact_mode): greedy ids bit-identical to the
+            # reference loop (rwkv_asr_cuda_whisper.py:694-717), at the reference's eager speed plus the CUDA graph
+            from rwkvtts_b200 import core as _core
+            with _core.exact_mode():
+                return self.generate(input_ids=input_ids, inputs_embeds=inputs_embeds, attention_mask=attention_mask,
+                                     max_new_tokens=max_new_tokens, max_length=max_length, min_new_tokens=min_new_tokens,
+                                     do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p,
+                                     eos_token_id=eos_token_id, pad_token_id=pad_token_id, use_cache=use_cache,
+                                     generator=generator, return_dict_in_generate=return_dict_in_generate,
+                                     use_cuda_graph=use_cuda_graph, eos_check_interval=eos_check_interval, **kwargs)
         if (input_ids is None) == (inputs_embeds is None):
             raise ValueError("pass exactly one of input_ids / inputs_embeds")
         prompt_len = input_ids.shape[1] if input_ids is not None else inputs_embeds.shape[1]

@@ -23,6 +23,8 @@ SYMBOLS = {
     "rwkvtts_watchdog_report": (_i, [ctypes.c_char_p, ctypes.c_size_t]),
     "rwkvtts_set_impl": (_i, [_i]),
     "rwkvtts_get_impl": (_i, []),
+    "rwkvtts_set_step_mode": (_i, [_i]),
+    "rwkvtts_get_step_mode": (_i, []),
     "rwkvtts_wkv7_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
                                                       ctypes.POINTER(ctypes.c_size_t)]),
     "rwkvtts_wkv7_forward": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
@@ -76,8 +78,8 @@ def lib() -> ctypes.CDLL:
 
 def watchdog_report() -> str:
     """Text of the mbarrier watchdog record of the chunked kernels ('' if none fired); include/rwkvtts_wkv7.h."""
-    buf = ctypes.create_string_buffer(512)
-    return buf.value.decode() if lib().rwkvtts_watchdog_report(buf, 512) else ""
+    buf = ctypes.create_string_buffer(4096)
+    return buf.value.decode() if lib().rwkvtts_watchdog_report(buf, 4096) else ""
 
 
 def check(rc: int, what: str) -> None:

@@ -26,7 +26,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "librwkvtts_wkv7.so")
 SOURCES = ["capi.cu", "wkv7_scan.cu", "wkv7_tc_fwd.cu", "wkv7_tc_bwd.cu", "tmix_fused.cu", "adam.cu", "gather.cu",
-           "linear_ce.cu"]
+           "linear_ce.cu", "wkv7_step_exact.cu"]
+# per-file flags: the reference-order step kernel must come out with the reference build's flush-to-zero fast-math
+# instructions (model/llm/rwkv_asr_cuda_whisper.py:50) to be bit-identical to it
+FILE_FLAGS = {"wkv7_step_exact.cu": ["--use_fast_math"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 VARIANTS = {
@@ -46,7 +49,7 @@ def _digest(extra) -> str:
     for d in deps:
         h.update(os.path.basename(d).encode())
         h.update(open(d, "rb").read())
-    h.update(" ".join(NVCC_FLAGS + list(extra) + _sources()).encode())
+    h.update(" ".join(NVCC_FLAGS + list(extra) + _sources() + [repr(sorted(FILE_FLAGS.items()))]).encode())
     return h.hexdigest()
 
 
@@ -86,7 +89,7 @@ def build(force: bool = False, verbose: bool = False, variant=None) -> str:
         objs.append(o)
         if t == tag or not os.path.exists(o):
             ex = extra if s in special and variant else []
-            jobs.append([nvcc, *NVCC_FLAGS, *ex, *(["-Xptxas", "-v"] if verbose else []), "-c",
+            jobs.append([nvcc, *NVCC_FLAGS, *FILE_FLAGS.get(s, []), *ex, *(["-Xptxas", "-v"] if verbose else []), "-c",
                          os.path.join(CSRC, s), "-o", o])
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))

@@ -36,6 +36,30 @@ DECODE_BATCHED_GEMM = os.environ.get("RWKVTTS_DECODE_BMM", "1") != "0"
 # measurement hook (bench.py R-GPU-model leg): an autograd.Function with WindBackstepping's signature that replaces the
 # training op (the bench binds the compiled reference kernels there); None = this library
 WKV_TRAIN_OP = None
+# "exact" inference: the reference's decode step operation for operation -- the ATen elementwise chain (bf16
+# intermediates, as RWKV_Tmix_x070.forward_batch, rwkv_asr_cuda_whisper.py:181-215) around the stateful kernel in the
+# reference's summation order (csrc/wkv7_step_exact.cu), prompt included.  Greedy token ids are then bit-identical to
+# the reference loop's (north_star); the default path trades that for speed (fused kernels keep fp32 intermediates).
+EXACT = False
+
+
+class exact_mode:
+    """with core.exact_mode(): ...   (what generate(..., exact=True) enters)"""
+
+    def __enter__(self):
+        global FUSED, EXACT
+        from . import _lib
+        self.prev = (FUSED, EXACT, _lib.lib().rwkvtts_get_step_mode())
+        FUSED, EXACT = False, True
+        _lib.lib().rwkvtts_set_step_mode(1)
+        return self
+
+    def __exit__(self, *exc):
+        global FUSED, EXACT
+        from . import _lib
+        FUSED, EXACT = self.prev[0], self.prev[1]
+        _lib.lib().rwkvtts_set_step_mode(self.prev[2])
+        return False
 
 
 @dataclass
@@ -87,7 +111,7 @@ def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
     B, T, C = r.shape
     H = C // HEAD
     grad = torch.is_grad_enabled() and any(t.requires_grad for t in (r, w, k, v, a, b))
-    if T % ops.CHUNK_LEN == 0:
+    if T % ops.CHUNK_LEN == 0 and not (EXACT and not grad):
         sh = lambda t: t.view(B, T, H, HEAD)
         if state is None and not need_state:
             if WKV_TRAIN_OP is not None:
@@ -128,7 +152,9 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     if mask is not None:
         x = x * mask                                                            # :160
     xx = token_shift(x, shift_state)                                            # :162
-    xr, xw, xk, xv, xa, xg = (torch.addcmul(x, xx, m) for m in (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g))
+    # EXACT: two roundings per lerp like the reference's `x + xx * self.x_r` (:164-169); addcmul rounds once
+    lerp = (lambda m: x + xx * m) if EXACT else (lambda m: torch.addcmul(x, xx, m))
+    xr, xw, xk, xv, xa, xg = (lerp(m) for m in (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g))
     r = F.linear(xr, p.W_r)
     w = -F.softplus(-(p.w0 + torch.tanh(xw @ p.w1) @ p.w2)) - 0.5               # :172
     k = F.linear(xk, p.W_k)
@@ -249,5 +275,5 @@ def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch
     if mask is not None:
         x = x * mask
     xx = token_shift(x, shift_state)
-    k = torch.relu(F.linear(torch.addcmul(x, xx, x_k), W_key)) ** 2
+    k = torch.relu(F.linear((x + xx * x_k) if EXACT else torch.addcmul(x, xx, x_k), W_key)) ** 2
     return F.linear(k, W_value), (x[:, -1] if need_state else None)

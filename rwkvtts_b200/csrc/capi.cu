@@ -15,14 +15,15 @@ namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
 
 // ---- watchdog record (see tc05.cuh) -------------------------------------------------------------------------
+constexpr int kWdEntries = 24, kWdWords = 8 + 4 * kWdEntries;      // tc05.cuh: kWatchdogEntries / kWatchdogWords
 static unsigned long long *g_wd_host = nullptr;
 static std::once_flag g_wd_once;
 unsigned long long *watchdog_record() {
     std::call_once(g_wd_once, [] {
         void *p = nullptr;
-        if (cudaHostAlloc(&p, 8 * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+        if (cudaHostAlloc(&p, kWdWords * sizeof(unsigned long long), cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
             g_wd_host = static_cast<unsigned long long *>(p);
-            for (int i = 0; i < 8; i++) g_wd_host[i] = 0;
+            for (int i = 0; i < kWdWords; i++) g_wd_host[i] = 0;
         } else {
             (void)cudaGetLastError();
         }
@@ -47,6 +48,8 @@ cudaError_t launch_scan_fwd(int B, int T, int H, const void *w, const void *q, c
                             float *sT, bool save, cudaStream_t st);
 cudaError_t launch_step(int B, int H, const void *w, const void *q, const void *k, const void *v, const void *a,
                         const void *b, void *y, float *state, cudaStream_t st);
+cudaError_t launch_state_exact(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
+                               const void *a, const void *b, void *y, float *state, cudaStream_t st);
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
                           cudaStream_t st);
@@ -120,6 +123,11 @@ int initial_impl() {
     return 1;
 }
 std::atomic<int> g_impl{initial_impl()};
+int initial_step_mode() {
+    const char *e = getenv("RWKVTTS_STEP_MODE");
+    return (e != nullptr && e[0] == 'e') ? 1 : 0;       // "exact"
+}
+std::atomic<int> g_step_mode{initial_step_mode()};
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -171,6 +179,13 @@ int rwkvtts_set_impl(int impl) {
 }
 int rwkvtts_get_impl(void) { return g_impl.load(); }
 
+int rwkvtts_set_step_mode(int mode) {
+    if (mode != 0 && mode != 1) return RWKVTTS_ERR_SHAPE;
+    g_step_mode.store(mode);
+    return RWKVTTS_OK;
+}
+int rwkvtts_get_step_mode(void) { return g_step_mode.load(); }
+
 long long rwkvtts_kernel_launches(void) { return rwkvtts::g_kernel_launches.load(); }
 
 int rwkvtts_watchdog_report(char *buf, size_t n) {
@@ -180,14 +195,23 @@ int rwkvtts_watchdog_report(char *buf, size_t n) {
         return 0;
     }
     if (buf != nullptr && n > 0) {
-        const unsigned kid = (unsigned)r[1];
-        snprintf(buf, n,
-                 "rwkvtts watchdog: kernel %s, mbarrier at dynamic-smem offset %u (%s), parity %u, block %u, thread %u "
-                 "(warp %u), waited %.3f s",
-                 kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : "?", (unsigned)(r[2] >> 32),
-                 rwkvtts::watchdog_barrier_name(kid, (unsigned)(r[2] >> 32)), (unsigned)(r[2] & 0xffffffffu),
-                 (unsigned)(r[3] >> 32), (unsigned)(r[3] & 0xffffffffu), (unsigned)(r[3] & 0xffffffffu) >> 5,
-                 (double)r[4] * 1e-9);
+        size_t off = 0;
+        int shown = 0;
+        off += (size_t)snprintf(buf + off, n - off, "rwkvtts watchdog: %llu stuck warp(s) recorded:", r[1]);
+        for (int i = 0; i < rwkvtts::kWdEntries && off + 1 < n; i++) {
+            const unsigned long long *e = r + 8 + 4 * i;
+            if ((e[0] >> 32) == 0) continue;
+            const unsigned kid = (unsigned)(e[0] & 0xffffffffu);
+            off += (size_t)snprintf(buf + off, n - off,
+                                    "%s %s: %s (smem +%u) parity %u, block %u warp %u, %.2f Gcycles;", shown ? "" : "",
+                                    kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : "?",
+                                    rwkvtts::watchdog_barrier_name(kid, (unsigned)(e[1] >> 32)), (unsigned)(e[1] >> 32),
+                                    (unsigned)(e[1] & 0xffffffffu), (unsigned)(e[2] >> 32),
+                                    (unsigned)(e[2] & 0xffffffffu) >> 5, (double)e[3] * 2e-9);
+            if (off >= n) { off = n - 1; break; }
+            shown++;
+        }
+        buf[off < n ? off : n - 1] = 0;
     }
     return 1;
 }
@@ -259,6 +283,8 @@ int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const v
     if (B <= 0 || T <= 0 || H <= 0 || C != H * RWKVTTS_HEAD_SIZE) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({state, r, w, k, v, a, b, y})) return rc;
     // op-boundary order of the kernels is (w, q=r, k, v, a, b)
+    if (g_step_mode.load() == 1)   // the reference's operation order, bit for bit (wkv7_step_exact.cu)
+        return finish(rwkvtts::launch_state_exact(B, T, H, w, r, k, v, a, b, y, state, (cudaStream_t)stream));
     if (T == 1)   // the decode step: dedicated streaming kernel
         return finish(rwkvtts::launch_step(B, H, w, r, k, v, a, b, y, state, (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, r, k, v, a, b, y, nullptr, nullptr, state, state, false,

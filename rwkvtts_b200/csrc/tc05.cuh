@@ -147,7 +147,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // ---- watchdog ------------------------------------------------------------------------------------
 // Every mbarrier wait of the chunked kernels is bounded: a hand-off that has not arrived after
 // RWKVTTS_WATCHDOG_NS (default 4 s at a nominal 2 GHz SM clock; a whole launch takes < 2 ms) writes one record
-//   {magic, kernel id, barrier offset in dynamic shared memory, parity, block, thread, ns waited}
+//   {kernel id, barrier offset in dynamic shared memory, parity, block, thread, time waited}   (one per stuck warp)
 // to a pinned host buffer (capi.cu owns it; rwkvtts_watchdog_report() formats it) and traps, so a
 // protocol error surfaces as a CUDA error with a diagnosis instead of a device that spins forever.
 #ifndef RWKVTTS_WATCHDOG_NS
@@ -156,23 +156,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 constexpr unsigned long long kWatchdogMagic = 0x57444f4752574b56ull;   // "WDOGRWKV"
 static __device__ unsigned long long *g_wd_rec = nullptr;              // one copy per translation unit
 static __device__ unsigned int g_wd_kernel = 0;
+// record layout (u64 words): [0] magic once any entry exists, [1] number of entries claimed, entries of 4 words from
+// word 8: {kernel id | valid << 32, (barrier offset << 32) | parity, (block << 32) | thread, cycles waited / 2}
+constexpr int kWatchdogEntries = 24, kWatchdogWords = 8 + 4 * kWatchdogEntries;
 static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity, unsigned long long waited) {
     extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
     volatile unsigned long long *r = g_wd_rec;
     if (r != nullptr) {
-        if (atomicCAS_system(g_wd_rec, 0ull, kWatchdogMagic) == 0ull) {
-            r[1] = g_wd_kernel;
-            r[2] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
-            r[3] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
-            r[4] = waited;
+        // every stuck warp (one lane each) appends what it was waiting for: a deadlock is a cycle of waits and the
+        // first warp to run out of patience is usually a bystander (first version reported only that one)
+        const unsigned long long idx = atomicAdd_system(g_wd_rec + 1, 1ull);
+        if (idx < (unsigned long long)kWatchdogEntries) {
+            volatile unsigned long long *e = r + 8 + 4 * idx;
+            e[1] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
+            e[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+            e[3] = waited;
             __threadfence_system();
-            r[5] = 1ull;                       // record complete
+            e[0] = (unsigned long long)g_wd_kernel | (1ull << 32);          // valid: written last
+            r[0] = kWatchdogMagic;
             __threadfence_system();
         }
-        // nobody traps before the record is in host memory: a trap aborts the whole grid, stores in flight included
-        // (first version: the record came back with only one field written)
+        // nobody traps at once: a trap aborts the whole grid, stores in flight included (first version: the record came
+        // back with one field written), and the other stuck warps time out within a few ms of this one
         const long long t0 = clock64();
-        while (r[5] == 0ull && clock64() - t0 < 200000000ll) {}
+        while (clock64() - t0 < 100000000ll) {}
     }
     __trap();
 }
@@ -186,7 +193,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         const long long dt = clock64() - t0;
-        if (dt > (long long)(RWKVTTS_WATCHDOG_NS) * 2) mbar_timeout(smem_u32(bar), parity, (unsigned long long)dt / 2);
+        if (dt > (long long)(RWKVTTS_WATCHDOG_NS) * 2) {
+            if ((threadIdx.x & 31) == 0 || __activemask() != 0xffffffffu) mbar_timeout(smem_u32(bar), parity, (unsigned long long)dt / 2);
+            else { const long long t1 = clock64(); while (clock64() - t1 < 400000000ll) {} __trap(); }
+        }
     }
 }
 // host side: point this translation unit's record pointer at the pinned buffer (once per device)

@@ -123,7 +123,7 @@ def test_engine_on_one_gpu_matches_adamw(monkeypatch):
     eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": False}, "gradient_clipping": 0.5,
                                                          "zero_optimization": {"stage": 2}},
                                         model_parameters=m.parameters(), optimizer=opt)
-    assert eng.device.type == "cuda" and len(eng.buckets) >= 3
+    assert eng.device.type == "cuda" and len(eng.buckets) >= 2
     ref = _toy().cuda()
     ropt = torch.optim.AdamW([{"params": g["params"], "weight_decay": g["weight_decay"]} for g in _groups(ref)], lr=1e-2,
                              betas=(B1, B2), eps=EPS)
@@ -156,7 +156,7 @@ m = T._toy().to(torch.bfloat16)
 opt = FusedAdam(T._groups(m), lr=1e-2, betas=(T.B1, T.B2), eps=T.EPS)
 eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": True}, "zero_optimization": {"stage": 2}},
                                     model_parameters=m.parameters(), optimizer=opt)
-assert eng.world_size == world and eng._nccl and len(eng.buckets) >= 3
+assert eng.world_size == world and eng._nccl and len(eng.buckets) >= 2
 g = torch.Generator(device="cuda").manual_seed(1)
 x, y = torch.randn(32, 96, device="cuda", generator=g).bfloat16(), torch.randn(32, 8, device="cuda", generator=g).bfloat16()
 n = 32 // world

@@ -86,3 +86,55 @@ def test_forward_batch_matches_reference_classes(monkeypatch):
         for n, a, b in zip(names, r2, m2):
             err = float((a.float() - b.float()).norm() / a.float().norm().clamp(min=1e-9))
             assert err < 1e-4, (layer_id, "step", n, err)
+
+
+def test_exact_mode_chain_is_operation_for_operation_the_reference_chain(monkeypatch):
+    """bf16 on both sides, bit-for-bit: with core.EXACT the ATen chain around the op performs the reference's operations
+    in the reference's order (same roundings), which is what makes greedy token ids of generate(exact=True) identical to
+    the reference decode loop once the op itself is bit-identical (csrc/wkv7_step_exact.cu, checked on the GPU)."""
+    from rwkvtts_b200 import core, x070
+    ref = _reference_classes()
+
+    def op_bf16(state, r, w, k, v, a, b):
+        from oracle.wkv7_oracle import wkv7_state_forward
+        y, sT = wkv7_state_forward(state.double(), *(t.double() for t in (r, w, k, v, a, b)))
+        state.copy_(sT.to(state.dtype))
+        return y.to(torch.bfloat16)
+
+    ref["RWKV_Tmix_x070"].forward_batch.__globals__["RWKV7_BATCH_OP"] = op_bf16
+
+    def wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
+        st = state if inplace_state else state.clone()
+        return op_bf16(st, r, w, k, v, a, b), st
+
+    monkeypatch.setattr(core, "_wkv", wkv)
+    monkeypatch.setattr(core, "EXACT", True)
+    monkeypatch.setattr(core, "FUSED", False)
+    args = Namespace(n_embd=128, n_layer=3, head_size_a=64, head_size_divisor=8, dim_att=128, dim_ffn=512, dropout=0.0,
+                     need_init_tmix=True, need_init_cmix=True)
+    torch.manual_seed(1)
+    B, T, C = 3, 5, 128
+    for layer_id in (0, 1):
+        rb = ref["Block"](args, layer_id)
+        with torch.no_grad():
+            for p in rb.parameters():
+                if float(p.abs().sum()) == 0:
+                    p.normal_(0, 0.05)
+        rb = rb.to(torch.bfloat16)
+        mb = x070.Block(args, layer_id).to(torch.bfloat16)
+        mb.load_state_dict(rb.state_dict(), strict=True)
+        x = torch.randn(B, T, C).bfloat16()
+        mask = torch.ones(B, T, 1, dtype=torch.bfloat16)
+        v_first = torch.randn(B, T, C).bfloat16()
+        st_r = [(torch.randn(B, C) * 0.1).bfloat16(), torch.randn(B, 2, 64, 64) * 0.1, (torch.randn(B, C) * 0.1).bfloat16()]
+        st_m = [t.clone() for t in st_r]
+        out_r = rb.forward_batch(x, mask, v_first.clone(), st_r[0], st_r[1], st_r[2])
+        out_m = mb.forward_batch(x, mask, v_first.clone(), st_m[0], st_m[1], st_m[2])
+        for n, a, b in zip(("x", "v_first", "tx_prev", "state", "cx_prev"), out_r, out_m):
+            assert torch.equal(a, b), (layer_id, n, float((a.float() - b.float()).abs().max()))
+        x1 = torch.randn(B, 1, C).bfloat16()
+        m1 = torch.ones(B, 1, 1, dtype=torch.bfloat16)
+        r2 = rb.forward_batch(x1, m1, out_r[1][:, -1:], out_r[2], out_r[3], out_r[4])
+        m2 = mb.forward_batch(x1, m1, out_m[1][:, -1:], out_m[2], out_m[3], out_m[4])
+        for n, a, b in zip(("x", "v_first", "tx_prev", "state", "cx_prev"), r2, m2):
+            assert torch.equal(a, b), (layer_id, "step", n)
