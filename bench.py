@@ -134,8 +134,10 @@ def train_arm(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG", "INFO")            # leave NCCL's log on: communicator size is checkable
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"                  # leave NCCL's log on: communicator size is checkable
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line
         import deepspeed
         log("joining the NCCL process group")
         deepspeed.init_distributed("nccl")

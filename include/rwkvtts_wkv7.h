@@ -127,6 +127,23 @@ RWKVTTS_API int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, con
                              const float *dsT, void *dw, void *dq, void *dk, void *dv,
                              void *dz, void *da, float *ds0, void *stream);
 
+/* Packed variable-length launches: the sequences of a batch back to back as ONE [1, T_total, H, 64] tensor with
+ * cu_seqlens (the `_culens` collators the reference's operating points use: data/utils/spark_dataset.py:111-162,
+ * utils/multiple_jsonl.py:77-135, :236-311; rwkvfla's chunk_rwkv7(..., cu_seqlens=), SURVEY.md section 8 rows a10 / b).
+ * The recurrent state restarts from zero at every boundary; no padding token is computed or moved, sequence lengths
+ * need not be multiples of 16.  cu_seqlens: device int32 [N+1] (0 ... T_total); chunk_base: device int32 [N+1], the
+ * exclusive prefix sum of ceil(len_i / 16) (where sequence i's checkpoints start inside `s` / `sa`).  Scratch sizes
+ * from rwkvtts_wkv7_varlen_scratch_floats (T_total/16 + N chunk slots per head); s = sa = NULL selects the
+ * snapshot-free forward.  Chunked tensor-core family only. */
+RWKVTTS_API size_t rwkvtts_wkv7_varlen_scratch_floats(int T_total, int H, int N, size_t *s_floats, size_t *sa_floats);
+RWKVTTS_API int rwkvtts_wkv7_forward_varlen(int T_total, int H, int N, const int *cu_seqlens, const int *chunk_base,
+                                const void *w, const void *q, const void *k, const void *v, const void *z,
+                                const void *a, void *y, float *s, float *sa, void *stream);
+RWKVTTS_API int rwkvtts_wkv7_backward_varlen(int T_total, int H, int N, const int *cu_seqlens, const int *chunk_base,
+                                 const void *w, const void *q, const void *k, const void *v, const void *z,
+                                 const void *a, const void *dy, const float *s, const float *sa, void *dw, void *dq,
+                                 void *dk, void *dv, void *dz, void *da, void *stream);
+
 /* Stateful forward (prefill for T > 1, the per-token decode op for T == 1).
  * C must equal H*64.  `state` is read, advanced by T steps and written back. */
 RWKVTTS_API int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const void *r,
@@ -200,6 +217,16 @@ RWKVTTS_API int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const
 RWKVTTS_API int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask,
                                                 const void *prev, const float *mix, const void *const *dout, void *dx,
                                                 float *dmix, float *scratch, void *stream);
+/* The same pair for packed (cu_seqlens) batches: seq_first (device, uint8 [B*T], 1 on the first token of every
+ * sequence, or NULL = dense) cuts the shift at sequence boundaries -- shift(x)[t] = 0 where seq_first[t] -- so a
+ * packed batch gives what the per-sample runs give (no state is carried: prev / prev_out must be NULL with it). */
+RWKVTTS_API int rwkvtts_tmix_shift_mix_forward_varlen(int B, int T, int C, int n, const void *x, const void *mask,
+                                                      const void *prev, const float *mix, void *const *out,
+                                                      void *prev_out, const unsigned char *seq_first, void *stream);
+RWKVTTS_API int rwkvtts_tmix_shift_mix_backward_varlen(int B, int T, int C, int n, const void *x, const void *mask,
+                                                       const void *prev, const float *mix, const void *const *dout,
+                                                       void *dx, float *dmix, float *scratch,
+                                                       const unsigned char *seq_first, void *stream);
 
 /* From the projections k, v and the LoRA outputs w_lo = tanh(xw@w1)@w2, a_lo = (xa@a1)@a2, v_lo = (xv@v1)@v2:
  *   w = -softplus(-(w0 + w_lo)) - 0.5 (:172);  a = sigmoid(a0 + a_lo) (:183);

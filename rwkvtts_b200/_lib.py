@@ -32,10 +32,16 @@ SYMBOLS = {
     "rwkvtts_wkv7_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp] + [_vp] * 6 + [_vp]),
     "rwkvtts_wkv7_forward_ex": (_i, [_i, _i, _i] + [_vp] * 6 + [_vp, _fp, _fp, _fp, _fp, _vp]),
     "rwkvtts_wkv7_backward_ex": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp, _fp, _fp, _fp, _fp] + [_vp] * 6 + [_fp, _vp]),
+    "rwkvtts_wkv7_varlen_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, ctypes.POINTER(ctypes.c_size_t),
+                                                             ctypes.POINTER(ctypes.c_size_t)]),
+    "rwkvtts_wkv7_forward_varlen": (_i, [_i, _i, _i, _vp, _vp] + [_vp] * 6 + [_vp, _fp, _fp, _vp]),
+    "rwkvtts_wkv7_backward_varlen": (_i, [_i, _i, _i, _vp, _vp] + [_vp] * 7 + [_fp, _fp] + [_vp] * 6 + [_vp]),
     "rwkvtts_wkv7_state_forward": (_i, [_i, _i, _i, _i, _fp] + [_vp] * 6 + [_vp, _vp]),
     "rwkvtts_tmix_scratch_floats": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "rwkvtts_tmix_shift_mix_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _vp]),
     "rwkvtts_tmix_shift_mix_backward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _fp, _fp, _vp]),
+    "rwkvtts_tmix_shift_mix_forward_varlen": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _vp, _vp]),
+    "rwkvtts_tmix_shift_mix_backward_varlen": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _fp, ctypes.POINTER(_vp), _vp, _fp, _fp, _vp, _vp]),
     "rwkvtts_tmix_prep_forward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp] * 5 + [_i] + [_vp] * 5 + [_vp]),
     "rwkvtts_tmix_prep_backward": (_i, [_i, _i, _i] + [_vp] * 7 + [_fp] * 5 + [_i] + [_vp] * 5 + [_vp] * 6 + [_fp, _fp, _vp]),
     "rwkvtts_tmix_out_forward": (_i, [_i, _i, _i] + [_vp] * 5 + [_fp] * 3 + [ctypes.c_float, _vp, _vp]),

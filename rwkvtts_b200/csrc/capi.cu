@@ -52,11 +52,11 @@ cudaError_t launch_state_exact(int B, int T, int H, const void *w, const void *q
                                const void *a, const void *b, void *y, float *state, cudaStream_t st);
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
-                          cudaStream_t st);
+                          const int *cu, const int *cbase, cudaStream_t st);
 cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
                           const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
-                          void *db, float *ds0, cudaStream_t st);
+                          void *db, float *ds0, const int *cu, const int *cbase, cudaStream_t st);
 cudaError_t launch_scan_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                             const void *a, const void *b, const void *dy, const float *s, const float *sa,
                             const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da, void *db,
@@ -86,10 +86,11 @@ cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, 
 cudaError_t launch_add_ln_bwd(long rows, int C, const void *sum, const float *stats, const float *w, const void *dy,
                               const void *ds, void *dx, float *dparams, float *part, cudaStream_t st);
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                 const float *mix, void *const *out, void *prev_out, cudaStream_t st);
+                                 const float *mix, void *const *out, void *prev_out, const unsigned char *first,
+                                 cudaStream_t st);
 cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                  const float *mix, const void *const *dout, void *dx, float *dmix, float *part,
-                                 cudaStream_t st);
+                                 const unsigned char *first, cudaStream_t st);
 cudaError_t launch_prep_fwd(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,
                             const void *v_lo, const void *v_first, const void *mask, const float *w0, const float *a0,
                             const float *v0, const float *k_k, const float *k_a, int mask_rwk, void *w, void *k2, void *v2,
@@ -231,7 +232,8 @@ int rwkvtts_wkv7_forward_ex(int B, int T, int H, const void *w, const void *q, c
     if (int rc = check_ptrs({w, q, k, v, z, a, y, s, sa})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
     if (g_impl.load() == 1)
-        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, (cudaStream_t)stream));
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, nullptr, nullptr,
+                                             (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, s, sa, s0, sT, true,
                                            (cudaStream_t)stream));
 }
@@ -242,7 +244,7 @@ int rwkvtts_wkv7_forward_infer(int B, int T, int H, const void *w, const void *q
     if (int rc = check_ptrs({w, q, k, v, z, a, y})) return rc;
     if (int rc = check_opt({s0, sT})) return rc;
     if (g_impl.load() == 1)
-        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT,
+        return finish(rwkvtts::launch_tc_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT, nullptr, nullptr,
                                              (cudaStream_t)stream));
     return finish(rwkvtts::launch_scan_fwd(B, T, H, w, q, k, v, z, a, y, nullptr, nullptr, s0, sT, false,
                                            (cudaStream_t)stream));
@@ -264,7 +266,7 @@ int rwkvtts_wkv7_backward_ex(int B, int T, int H, const void *w, const void *q, 
     if (g_impl.load() == 1) {
         if (dsT != nullptr && sT == nullptr) return RWKVTTS_ERR_NULL;   // the window-end term needs S_T
         return finish(rwkvtts::launch_tc_bwd(B, T, H, w, q, k, v, z, a, dy, s, sa, sT, dsT, dw, dq, dk, dv, dz, da,
-                                             ds0, (cudaStream_t)stream));
+                                             ds0, nullptr, nullptr, (cudaStream_t)stream));
     }
     return finish(rwkvtts::launch_scan_bwd(B, T, H, w, q, k, v, z, a, dy, s, sa, dsT, dw, dq, dk, dv, dz, da,
                                            ds0, (cudaStream_t)stream));
@@ -275,6 +277,39 @@ int rwkvtts_wkv7_backward(int B, int T, int H, const void *w, const void *q, con
                           void *dw, void *dq, void *dk, void *dv, void *dz, void *da, void *stream) {
     return rwkvtts_wkv7_backward_ex(B, T, H, w, q, k, v, z, a, dy, s, sa, nullptr, nullptr, nullptr, dw, dq, dk,
                                     dv, dz, da, nullptr, stream);
+}
+
+// ---- packed (cu_seqlens) launches of the chunked kernels -----------------------------------------------------------
+size_t rwkvtts_wkv7_varlen_scratch_floats(int T_total, int H, int N, size_t *s_floats, size_t *sa_floats) {
+    // every sequence may end in a partial chunk: at most T_total/16 + N chunk slots per head
+    const size_t slots = ((size_t)T_total / RWKVTTS_CHUNK_LEN + (size_t)N) * (size_t)H;
+    const size_t s = slots * RWKVTTS_HEAD_SIZE * RWKVTTS_HEAD_SIZE, sa = slots * RWKVTTS_CHUNK_LEN * RWKVTTS_HEAD_SIZE;
+    if (s_floats) *s_floats = s;
+    if (sa_floats) *sa_floats = sa;
+    return s + sa;
+}
+
+int rwkvtts_wkv7_forward_varlen(int T_total, int H, int N, const int *cu_seqlens, const int *chunk_base, const void *w,
+                                const void *q, const void *k, const void *v, const void *z, const void *a, void *y,
+                                float *s, float *sa, void *stream) {
+    if (T_total <= 0 || H <= 0 || N <= 0) return RWKVTTS_ERR_SHAPE;
+    if (cu_seqlens == nullptr || chunk_base == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({w, q, k, v, z, a, y})) return rc;
+    if ((s == nullptr) != (sa == nullptr)) return RWKVTTS_ERR_NULL;          // both (training) or neither (no-grad)
+    if (int rc = check_opt({s, sa})) return rc;
+    return finish(rwkvtts::launch_tc_fwd(N, T_total, H, w, q, k, v, z, a, y, s, sa, nullptr, nullptr, cu_seqlens, chunk_base,
+                                         (cudaStream_t)stream));
+}
+
+int rwkvtts_wkv7_backward_varlen(int T_total, int H, int N, const int *cu_seqlens, const int *chunk_base, const void *w,
+                                 const void *q, const void *k, const void *v, const void *z, const void *a, const void *dy,
+                                 const float *s, const float *sa, void *dw, void *dq, void *dk, void *dv, void *dz,
+                                 void *da, void *stream) {
+    if (T_total <= 0 || H <= 0 || N <= 0) return RWKVTTS_ERR_SHAPE;
+    if (cu_seqlens == nullptr || chunk_base == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({w, q, k, v, z, a, dy, s, sa, dw, dq, dk, dv, dz, da})) return rc;
+    return finish(rwkvtts::launch_tc_bwd(N, T_total, H, w, q, k, v, z, a, dy, s, sa, nullptr, nullptr, dw, dq, dk, dv, dz,
+                                         da, nullptr, cu_seqlens, chunk_base, (cudaStream_t)stream));
 }
 
 int rwkvtts_wkv7_state_forward(int B, int T, int C, int H, float *state, const void *r, const void *w,
@@ -359,8 +394,9 @@ size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params) {
     return (size_t)rwkvtts::tmix_grid(B, T, C, 0) * n_params * C;
 }
 
-int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                   const float *mix, void *const *out, void *prev_out, void *stream) {
+int rwkvtts_tmix_shift_mix_forward_varlen(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                          const float *mix, void *const *out, void *prev_out,
+                                          const unsigned char *seq_first, void *stream) {
     if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
     if (out == nullptr) return RWKVTTS_ERR_NULL;
     if (int rc = check_ptrs({x, mix})) return rc;
@@ -368,20 +404,34 @@ int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, co
         if (int rc = check_ptrs({out[i]})) return rc;
     if (int rc = check_opt({prev, prev_out})) return rc;
     if (prev_out != nullptr && prev_out == prev && T != 1) return RWKVTTS_ERR_SHAPE;   // in-place state update: decode only
-    return finish(rwkvtts::launch_shift_mix_fwd(B, T, C, n, x, mask, prev, mix, out, prev_out, (cudaStream_t)stream));
+    if (seq_first != nullptr && (prev != nullptr || prev_out != nullptr)) return RWKVTTS_ERR_SHAPE;   // packed: no carried state
+    return finish(rwkvtts::launch_shift_mix_fwd(B, T, C, n, x, mask, prev, mix, out, prev_out, seq_first,
+                                                (cudaStream_t)stream));
 }
 
-int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                    const float *mix, const void *const *dout, void *dx, float *dmix, float *scratch,
-                                    void *stream) {
+int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                   const float *mix, void *const *out, void *prev_out, void *stream) {
+    return rwkvtts_tmix_shift_mix_forward_varlen(B, T, C, n, x, mask, prev, mix, out, prev_out, nullptr, stream);
+}
+
+int rwkvtts_tmix_shift_mix_backward_varlen(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                           const float *mix, const void *const *dout, void *dx, float *dmix, float *scratch,
+                                           const unsigned char *seq_first, void *stream) {
     if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
     if (dout == nullptr) return RWKVTTS_ERR_NULL;
     if (int rc = check_ptrs({x, mix, dx, dmix, scratch})) return rc;
     for (int i = 0; i < n; i++)
         if (int rc = check_ptrs({dout[i]})) return rc;
     if (int rc = check_opt({prev})) return rc;
-    return finish(rwkvtts::launch_shift_mix_bwd(B, T, C, n, x, mask, prev, mix, dout, dx, dmix, scratch,
+    if (seq_first != nullptr && prev != nullptr) return RWKVTTS_ERR_SHAPE;
+    return finish(rwkvtts::launch_shift_mix_bwd(B, T, C, n, x, mask, prev, mix, dout, dx, dmix, scratch, seq_first,
                                                 (cudaStream_t)stream));
+}
+
+int rwkvtts_tmix_shift_mix_backward(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
+                                    const float *mix, const void *const *dout, void *dx, float *dmix, float *scratch,
+                                    void *stream) {
+    return rwkvtts_tmix_shift_mix_backward_varlen(B, T, C, n, x, mask, prev, mix, dout, dx, dmix, scratch, nullptr, stream);
 }
 
 int rwkvtts_tmix_prep_forward(int B, int T, int C, const void *k, const void *v, const void *w_lo, const void *a_lo,

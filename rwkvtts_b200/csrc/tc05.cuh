@@ -229,6 +229,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
+// the same copy with a source size: 0 bytes are read and the 8 destination bytes are zero-filled when !valid (tokens
+// beyond the end of a packed sequence)
+__device__ __forceinline__ void cp_async8_zfill(void *smem, const void *gmem, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(smem)), "l"(gmem), "r"(valid ? 8u : 0u) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
 }

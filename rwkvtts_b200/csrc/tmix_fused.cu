@@ -92,8 +92,17 @@ struct MixParams {
     const bf16 *dout[6];    // backward: n output gradients
     bf16 *dx;               // backward: [B,T,C]
     float *part;            // backward: [grid][n][C] partial d mix
+    const unsigned char *first;   // packed (cu_seqlens) batches: [B*T], 1 on the first token of every sequence; null = dense
     int B, T, C, n;
 };
+// sequence boundaries: every T rows (dense) or where the caller's flags say so (packed: the shift must not reach across
+// two sequences, utils/multiple_jsonl.py:77-135)
+__device__ __forceinline__ bool seq_first(const MixParams &P, long row) {
+    return P.first != nullptr ? (P.first[row] != 0) : (row % P.T == 0);
+}
+__device__ __forceinline__ bool seq_last(const MixParams &P, long row, long rows) {
+    return P.first != nullptr ? (row + 1 >= rows || P.first[row + 1] != 0) : ((row + 1) % P.T == 0);
+}
 
 // Each row lane (C/8 threads) walks a CONTIGUOUS range of rows, so the neighbour row a token needs (t-1 in the forward,
 // t+1 and t-1 in the backward) is the row it handled one step earlier / handles next: every element is loaded once.
@@ -122,12 +131,12 @@ __global__ void __launch_bounds__(kMaxThreads) shift_mix_fwd_kernel(const MixPar
     Row8 xp = zero8(), x = zero8(), xn = zero8();
     if (r0 < r1) {
         x = masked(ld8(P.x + r0 * P.C + c0), mask_of(r0));
-        if (r0 % P.T != 0) xp = masked(ld8(P.x + (r0 - 1) * P.C + c0), mask_of(r0 - 1));
+        if (!seq_first(P, r0)) xp = masked(ld8(P.x + (r0 - 1) * P.C + c0), mask_of(r0 - 1));
         if (r0 + 1 < r1) xn = masked(ld8(P.x + (r0 + 1) * P.C + c0), mask_of(r0 + 1));
     }
     for (long row = r0; row < r1; row++) {
         const int t = (int)(row % P.T);
-        if (t == 0) xp = (P.prev != nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
+        if (seq_first(P, row)) xp = (P.prev != nullptr && P.first == nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
         Row8 xn2 = zero8();
         if (row + 2 < r1) xn2 = masked(ld8(P.x + (row + 2) * P.C + c0), mask_of(row + 2));     // two rows ahead, in flight
         Row8 xx;
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kBwdThreads, 2) shift_mix_bwd_kernel(const Mix
     if (r0 < r1) {
         const long last = r1 - 1;
         x = masked(ld8(P.x + last * P.C + c0), mask_of(last));
-        if ((last + 1) % P.T != 0) {        // the row after the range belongs to the same sequence
+        if (!seq_last(P, last, rows)) {        // the row after the range belongs to the same sequence
 #pragma unroll
             for (int s = 0; s < N; s++) dn[s] = *reinterpret_cast<const uint4 *>(P.dout[s] + (last + 1) * P.C + c0);
         }
@@ -180,8 +189,8 @@ __global__ void __launch_bounds__(kBwdThreads, 2) shift_mix_bwd_kernel(const Mix
         Row8 xb = zero8();                    // the row below: this token's shift source and the next step's x
         if (row > 0) xb = masked(ld8(P.x + (row - 1) * P.C + c0), mask_of(row - 1));
         Row8 xp = xb;
-        if (t == 0) xp = (P.prev != nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
-        if (t == P.T - 1) {
+        if (seq_first(P, row)) xp = (P.prev != nullptr && P.first == nullptr) ? ld8(P.prev + (size_t)(row / P.T) * P.C + c0) : zero8();
+        if (seq_last(P, row, rows)) {
 #pragma unroll
             for (int s = 0; s < N; s++) dn[s] = make_uint4(0, 0, 0, 0);
         }
@@ -737,8 +746,10 @@ cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cuda
 }
 
 cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
-                                 const float *mix, void *const *out, void *prev_out, cudaStream_t st) {
+                                 const float *mix, void *const *out, void *prev_out, const unsigned char *first,
+                                 cudaStream_t st) {
     MixParams P{};
+    P.first = first;
     P.x = (const bf16 *)x; P.mask = (const bf16 *)mask; P.prev = (const bf16 *)prev; P.mix = mix;
     P.prev_out = (bf16 *)prev_out;
     for (int i = 0; i < n; i++) P.out[i] = (bf16 *)out[i];
@@ -753,8 +764,9 @@ cudaError_t launch_shift_mix_fwd(int B, int T, int C, int n, const void *x, cons
 
 cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                  const float *mix, const void *const *dout, void *dx, float *dmix, float *part,
-                                 cudaStream_t st) {
+                                 const unsigned char *first, cudaStream_t st) {
     MixParams P{};
+    P.first = first;
     P.x = (const bf16 *)x; P.mask = (const bf16 *)mask; P.prev = (const bf16 *)prev; P.mix = mix;
     for (int i = 0; i < n; i++) P.dout[i] = (const bf16 *)dout[i];
     P.dx = (bf16 *)dx; P.part = part;

@@ -32,6 +32,36 @@ using bf16 = __nv_bfloat16;
 constexpr int kCkFloats = 4096, kCkLbo = 256;
 constexpr int kUFloats = 1024, kULbo = 64;
 
+// What one CTA of the chunked kernels works on: a (batch, head) pair of a dense [B,T,H,64] launch, or a (sequence, head)
+// pair of a packed launch ([1,T_total,H,64] with cu_seqlens: state and token-shift restart at every boundary;
+// data/utils/spark_dataset.py:111-162, utils/multiple_jsonl.py:77-135 build such batches).  `len` need not be a
+// multiple of 16 in the packed case: tokens of the last chunk beyond `len` are loaded as zeros and never stored.
+struct SeqWork {
+    size_t base;     // element offset of token 0, channel 0 of this head
+    size_t ck0;      // index of the sequence's first chunk slot in the scratch tensors (per head)
+    int len, nC;     // tokens, 16-token chunks (ceil)
+    int bh;          // dense: b*H + h (s0 / sT / ds0 index); packed: unused
+};
+__device__ __forceinline__ SeqWork seq_work(int T, int H, const int *cu, const int *cbase) {
+    SeqWork w;
+    const int hh = blockIdx.x % H, bb = blockIdx.x / H;
+    const size_t tok_stride = (size_t)H * kC;
+    if (cu != nullptr) {
+        const int t0 = cu[bb];
+        w.len = cu[bb + 1] - t0;
+        w.nC = (w.len + kChunk - 1) / kChunk;
+        w.base = (size_t)t0 * tok_stride + (size_t)hh * kC;
+        w.ck0 = (size_t)cbase[bb] * H + (size_t)hh * w.nC;
+    } else {
+        w.len = T;
+        w.nC = T / kChunk;
+        w.base = (size_t)bb * T * tok_stride + (size_t)hh * kC;
+        w.ck0 = (size_t)blockIdx.x * w.nC;
+    }
+    w.bh = blockIdx.x;
+    return w;
+}
+
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 

@@ -99,6 +99,7 @@ struct Params {
     bf16 *dw, *dq, *dk, *dv, *da, *db;
     float *ds0;                  // may be null
     long long *dbg;              // phase-cycle counters (profiling builds only), may be null
+    const int *cu, *cbase;       // packed launch (see SeqWork, wkv7_common.cuh), else null
 };
 
 #ifdef RWKVTTS_PROFILE
@@ -136,15 +137,27 @@ __device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
 // raw inputs travel HBM -> shared memory with cp.async into a ring that is private to each thread
 // (the thread that issued the copy reads it back), one chunk ahead: no registers are held across iterations
 
-__device__ __forceinline__ void issue_raw(const Params &P, RawBuf &rb, size_t base, size_t tok_stride, int c, int tp) {
+template <bool kVar>
+__device__ __forceinline__ void issue_raw(const Params &P, RawBuf &rb, size_t base, size_t tok_stride, int c, int tp,
+                                          int len) {
     const int t = tp >> 4, k4 = tp & 15;
-    const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
-    cp_async8(&rb.x[0][tp], P.w + off); cp_async8(&rb.x[1][tp], P.q + off); cp_async8(&rb.x[2][tp], P.k + off);
-    cp_async8(&rb.x[3][tp], P.v + off); cp_async8(&rb.x[4][tp], P.a + off); cp_async8(&rb.x[5][tp], P.b + off);
-    cp_async8(&rb.x[6][tp], P.dy + off);
+    if (!kVar) {
+        const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
+        cp_async8(&rb.x[0][tp], P.w + off); cp_async8(&rb.x[1][tp], P.q + off); cp_async8(&rb.x[2][tp], P.k + off);
+        cp_async8(&rb.x[3][tp], P.v + off); cp_async8(&rb.x[4][tp], P.a + off); cp_async8(&rb.x[5][tp], P.b + off);
+        cp_async8(&rb.x[6][tp], P.dy + off);
+        return;
+    }
+    const bool ok = c * L + t < len;          // beyond the end of a packed sequence: zero-filled, nothing is read
+    const size_t off = base + (ok ? (size_t)(c * L + t) * tok_stride : 0) + k4 * 4;
+    cp_async8_zfill(&rb.x[0][tp], P.w + off, ok); cp_async8_zfill(&rb.x[1][tp], P.q + off, ok);
+    cp_async8_zfill(&rb.x[2][tp], P.k + off, ok); cp_async8_zfill(&rb.x[3][tp], P.v + off, ok);
+    cp_async8_zfill(&rb.x[4][tp], P.a + off, ok); cp_async8_zfill(&rb.x[5][tp], P.b + off, ok);
+    cp_async8_zfill(&rb.x[6][tp], P.dy + off, ok);
 }
 
-__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tp) {
+template <bool kVar>
+__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, size_t ck0, int nC, int len, int tp) {
     long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
     // w of every chunk of the window whose last chunk is c_last: needed when a window is entered from its end,
@@ -153,17 +166,19 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
         const int c0 = (c_last / WIN) * WIN;
 #pragma unroll
         for (int j = 0; j < WIN; j++)
-            if (c0 + j <= c_last) wr[j] = ldg_nc_v2(P.w + base + (size_t)((c0 + j) * L + t) * tok_stride + k4 * 4);
+            if (c0 + j <= c_last)
+                wr[j] = (!kVar || (c0 + j) * L + t < len) ? ldg_nc_v2(P.w + base + (size_t)((c0 + j) * L + t) * tok_stride + k4 * 4)
+                                                : make_uint2(0u, 0u);
     };
     uint2 wr[WIN];
-    issue_raw(P, sm.raw[0], base, tok_stride, nC - 1, tp);      // prologue: chunk of iteration 0
+    issue_raw<kVar>(P, sm.raw[0], base, tok_stride, nC - 1, tp, len);      // prologue: chunk of iteration 0
     cp_async_commit();
     loadw(nC - 1, wr);
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
         Slot &S = sm.slot[si];
         TICK(ta0);
-        if (it + 1 < nC) issue_raw(P, sm.raw[(it + 1) % NRAW], base, tok_stride, c - 1, tp);   // one chunk ahead
+        if (it + 1 < nC) issue_raw<kVar>(P, sm.raw[(it + 1) % NRAW], base, tok_stride, c - 1, tp, len);   // one chunk ahead
         cp_async_commit();
         const bool win_last = (c % WIN == WIN - 1) || (c == nC - 1);
         TICK(ta1);
@@ -233,7 +248,7 @@ __device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_strid
             if (ln == 0) mbar_expect_tx(&sm.blob_full[si], kUFloats * 4);
             __syncwarp();
             if (ln < 16)
-                bulk_g2s(&S.UVn[ln * N32_LBO], P.sa + ((size_t)bh * nC + c) * kUFloats + ln * kULbo, kULbo * 4,
+                bulk_g2s(&S.UVn[ln * N32_LBO], P.sa + (ck0 + c) * kUFloats + ln * kULbo, kULbo * 4,
                          &sm.blob_full[si]);
         }
         {
@@ -387,7 +402,7 @@ __device__ void stage_b(const Params &P, Smem &sm, int nC, int tp) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t kadv(uint64_t d, int kk, int lbo_f) { return d + (uint64_t)((kk * 2 * lbo_f * 4) >> 4); }
 
-__device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
+__device__ void mma_warp(const Params &P, Smem &sm, size_t ck0, int nC) {
     long long *P_dbg = (threadIdx.x & 31) == 0 ? P.dbg : nullptr; (void)P_dbg;
     const uint32_t tb = sm.tmem_base;
     constexpr uint32_t I16 = idesc_tf32(64, 16, false, false);
@@ -436,7 +451,7 @@ __device__ void mma_warp(const Params &P, Smem &sm, int bh, int nC) {
         if (elect_one()) {
             // S0^T of this chunk (the previous chunk's MMAs and, at a window boundary, group C2 are done with the tile)
             mbar_expect_tx(&sm.s0_full, kCkFloats * 4);
-            bulk_g2s(sm.S0c, P.ckT + ((size_t)bh * nC + c) * kCkFloats, kCkFloats * 4, &sm.s0_full);
+            bulk_g2s(sm.S0c, P.ckT + (ck0 + c) * kCkFloats, kCkFloats * 4, &sm.s0_full);
             // R1: Z^T = dY^T Aqb' + dS B'^T
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
@@ -644,7 +659,8 @@ __device__ void group_c1(const Params &P, Smem &sm, int bh, int nC, int tid) {
 // chunk it+1 (the gradient accumulators are double buffered in tensor memory).  Warp (q, hf): q = warp & 3 owns
 // lanes 32q..32q+15 = channel rows 16q..16q+15, hf = warp >> 2 takes tokens 8hf..8hf+7.
 // ---------------------------------------------------------------------------------------------
-__device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+template <bool kVar>
+__device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int len, int tid) {
     long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int wq = tid >> 5, q = wq & 3, hf = wq >> 2, lane = tid & 31;
     const bool act = lane < 16;
@@ -833,7 +849,8 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 const int e = tid + 256 * i, arr = e >> 7, tok = (e >> 3) & 15, part = e & 7;
-                *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v[i];
+                if (!kVar || c * L + tok < len)
+                    *reinterpret_cast<uint4 *>(dst[arr] + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v[i];
             }
         }
         TICK(tc6); ACC(14, tc4, tc5); ACC(15, tc5, tc6);
@@ -842,14 +859,16 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
 
 constexpr int kMmaWarp = 24, kThreads = 32 * (kMmaWarp + 1);
 
+template <bool kVar>
 __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
+    const SeqWork W = seq_work(P.T, P.H, kVar ? P.cu : nullptr, P.cbase);
+    const int bh = W.bh, nC = W.nC;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int nC = P.T / L;
     const size_t tok_stride = (size_t)P.H * kC;
-    const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
+    const size_t base = W.base;
+    if (kVar && nC == 0) return;         // an empty sequence of a packed launch (uniform over the CTA)
 
     if (tid == 0) {
         for (int i = 0; i < NS; i++) {
@@ -868,10 +887,10 @@ __global__ void __launch_bounds__(kThreads, 1) wkv7_tc_bwd_kernel(const Params P
     fence_after_sync();
 
     if (warp < 4) group_c1(P, sm, bh, nC, tid);
-    else if (warp < 12) group_c2(P, sm, base, tok_stride, bh, nC, tid - 128);
-    else if (warp < 20) stage_a(P, sm, base, tok_stride, bh, nC, tid - 384);
+    else if (warp < 12) group_c2<kVar>(P, sm, base, tok_stride, bh, nC, W.len, tid - 128);
+    else if (warp < 20) stage_a<kVar>(P, sm, base, tok_stride, W.ck0, nC, W.len, tid - 384);
     else if (warp < 24) stage_b(P, sm, nC, tid - 640);
-    else mma_warp(P, sm, bh, nC);
+    else mma_warp(P, sm, W.ck0, nC);
 
     fence_before_sync();
     __syncthreads();
@@ -898,21 +917,22 @@ const char *tc_bwd_barrier_name(unsigned off) {
 cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
                           const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
-                          void *db, float *ds0, cudaStream_t st) {
+                          void *db, float *ds0, const int *cu, const int *cbase, cudaStream_t st) {
     using namespace tcbwd;
     static_assert(sizeof(Smem) <= 232448, "shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(wkv7_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(Smem));
+    cudaError_t e = cu ? cudaFuncSetAttribute(wkv7_tc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem))
+                       : cudaFuncSetAttribute(wkv7_tc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
              (const bf16 *)b, (const bf16 *)dy, ckT, sa, sT, dsT, (bf16 *)dw, (bf16 *)dq, (bf16 *)dk, (bf16 *)dv,
-             (bf16 *)da, (bf16 *)db, ds0, g_tcb_dbg};
+             (bf16 *)da, (bf16 *)db, ds0, g_tcb_dbg, cu, cbase};
     if (watchdog_needs_install(1, st)) {
         e = watchdog_install(watchdog_record(), 2);
         if (e != cudaSuccess) return e;
     }
     count_launch();
-    wkv7_tc_bwd_kernel<<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    if (cu) wkv7_tc_bwd_kernel<true><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
+    else wkv7_tc_bwd_kernel<false><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
     return cudaGetLastError();
 }
 

@@ -94,6 +94,8 @@ struct Params {
     const float *s0;     // may be null
     float *sT;           // may be null
     long long *dbg;      // phase-cycle counters (profiling builds only), may be null
+    const int *cu;       // packed launch: cu_seqlens [N+1] (device), else null
+    const int *cbase;    // packed launch: first chunk slot of every sequence [N+1] (exclusive prefix of ceil(len/16))
 };
 
 #ifdef RWKVTTS_PROFILE
@@ -119,9 +121,15 @@ __device__ __forceinline__ uint2 ldg_nc_v2(const void *p) {
 __device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
     f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
 }
-__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int tp,
+template <bool kVar>
+__device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t tok_stride, int c, int tp, int len,
                                          uint2 (&raw)[6]) {
     const int t = tp >> 4, k4 = tp & 15;
+    if (kVar && c * L + t >= len) {          // beyond the end of a packed sequence: a token that changes nothing and is never stored
+#pragma unroll
+        for (int i = 0; i < 6; i++) raw[i] = make_uint2(0u, 0u);
+        return;
+    }
     const size_t off = base + (size_t)(c * L + t) * tok_stride + k4 * 4;
     raw[0] = ldg_nc_v2(P.w + off);
     raw[1] = ldg_nc_v2(P.q + off);
@@ -131,20 +139,21 @@ __device__ __forceinline__ void load_raw(const Params &P, size_t base, size_t to
     raw[5] = ldg_nc_v2(P.b + off);
 }
 
-__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int nC, int tp) {
+template <bool kVar>
+__device__ void stage_a(const Params &P, Smem &sm, size_t base, size_t tok_stride, int nC, int len, int tp) {
     long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
     uint2 raw[6], nxt[6], nx2[6];
     float gpre[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) gpre[j] = 0.f;
-    load_raw(P, base, tok_stride, 0, tp, raw);
-    if (nC > 1) load_raw(P, base, tok_stride, 1, tp, nxt);
+    load_raw<kVar>(P, base, tok_stride, 0, tp, len, raw);
+    if (nC > 1) load_raw<kVar>(P, base, tok_stride, 1, tp, len, nxt);
     for (int c = 0; c < nC; c++) {
         const int si = c % NSLOT, ni = c % NNAT;
         Slot &S = sm.slot[si];
         Nat &N = sm.nat[ni];
-        if (c + 2 < nC) load_raw(P, base, tok_stride, c + 2, tp, nx2);   // two chunks ahead
+        if (c + 2 < nC) load_raw<kVar>(P, base, tok_stride, c + 2, tp, len, nx2);   // two chunks ahead
         float lw[4], gg[4];
         TICK(ta0);
         {
@@ -432,14 +441,15 @@ __device__ void mma_warp(const Params &P, Smem &sm, int nC) {
 // (S^T += B~^T U + K~^T V, one chunk behind the main chain); the chunk-start checkpoint is that copy, read
 // with keys on the lanes, so it leaves as 16-byte pieces of the backward's K-major operand tile.
 // ---------------------------------------------------------------------------------------------
-template <bool kTrain>
-__device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, int nC, int tid) {
+template <bool kTrain, bool kVar>
+__device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stride, int bh, size_t ck0, int nC, int len,
+                         int tid) {
     long long *P_dbg = tid == 0 ? P.dbg : nullptr; (void)P_dbg;
     const int q = tid >> 5, lane = tid & 31;
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16);
-    float *sag = kTrain ? P.sa + (size_t)bh * nC * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
+    float *sag = kTrain ? P.sa + ck0 * kUFloats + (row >> 2) * kULbo + (row & 3) : nullptr;     // value = row
     {   // initial state -> tensor memory
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
@@ -518,7 +528,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
             bar_sync(4, 128);
             const int tok = tid >> 3, part = tid & 7;
             const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
-            *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
+            if (!kVar || c * L + tok < len) *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
         }
         TICK(te2); ACC(13, te0, te1); ACC(14, te1, te2);
     }
@@ -529,12 +539,12 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
 // the transposed state S^T.  After the MMA warp has added chunk c, S^T is the chunk-start checkpoint of chunk c+1:
 // 16-byte pieces of the backward's K-major operand tile, 256 contiguous bytes per warp store.
 // ---------------------------------------------------------------------------------------------
-__device__ void ckpt_group(const Params &P, Smem &sm, int bh, int nC, int tid) {
+__device__ void ckpt_group(const Params &P, Smem &sm, int bh, size_t ck0, int nC, int tid) {
     const int q = (tid >> 5) & 3, lane = tid & 31;
     const bool act = lane < 16;
     const int row = 16 * q + (lane & 15);
     const uint32_t tb = sm.tmem_base + ((uint32_t)(32 * q) << 16) + C_ST;
-    float *ckg = P.ckT + (size_t)bh * nC * kCkFloats + (row >> 3) * 32 + (row & 7) * 4;   // key = row
+    float *ckg = P.ckT + ck0 * kCkFloats + (row >> 3) * 32 + (row & 7) * 4;   // key = row
     auto store_ck = [&](const float (&v)[16], int cb, int cc) {
         if (act) {
             float *dst = ckg + (size_t)cc * kCkFloats + (4 * cb) * kCkLbo;
@@ -582,15 +592,16 @@ __device__ void ckpt_group(const Params &P, Smem &sm, int bh, int nC, int tid) {
 
 constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1), kThreadsTrain = kThreads + 128;
 
-template <bool kTrain>
+template <bool kTrain, bool kVar>
 __global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int bh = blockIdx.x, bb = bh / P.H, hh = bh % P.H;
+    const SeqWork W = seq_work(P.T, P.H, kVar ? P.cu : nullptr, P.cbase);
+    const int bh = W.bh, nC = W.nC;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int nC = P.T / L;
     const size_t tok_stride = (size_t)P.H * kC;
-    const size_t base = (size_t)bb * P.T * tok_stride + (size_t)hh * kC;
+    const size_t base = W.base;
+    if (kVar && nC == 0) return;         // an empty sequence of a packed launch (uniform over the CTA)
 
     if (tid == 0) {
         for (int i = 0; i < NSLOT; i++) { mbar_init(&sm.empty[i], 1); mbar_init(&sm.full[i], 4); }
@@ -605,12 +616,12 @@ __global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_kernel(const Par
     __syncthreads();
     fence_after_sync();
 
-    if (warp < 4) epilogue<kTrain>(P, sm, base, tok_stride, bh, nC, tid);
-    else if (warp < 12) stage_a(P, sm, base, tok_stride, nC, tid - 128);
+    if (warp < 4) epilogue<kTrain, kVar>(P, sm, base, tok_stride, bh, W.ck0, nC, W.len, tid);
+    else if (warp < 12) stage_a<kVar>(P, sm, base, tok_stride, nC, W.len, tid - 128);
     else if (warp < 16) stage_b(P, sm, nC, tid - 384, 0);
     else if (warp < 20) stage_b(P, sm, nC, tid - 512, 1);
     else if (warp == kMmaWarp) mma_warp<kTrain>(P, sm, nC);
-    else if (kTrain) ckpt_group(P, sm, bh, nC, tid);
+    else if (kTrain) ckpt_group(P, sm, bh, W.ck0, nC, tid);
 
     fence_before_sync();
     __syncthreads();
@@ -638,27 +649,26 @@ const char *tc_fwd_barrier_name(unsigned off) {
 // checkpoints (same size as the reference's `s`) and `sa`, consumed by wkv7_tc_bwd.cu.
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
-                          cudaStream_t st) {
+                          const int *cu, const int *cbase, cudaStream_t st) {
     using namespace tcfwd;
     static_assert(sizeof(Smem) <= 232448, "shared memory budget");
     Params P{T, H, (const bf16 *)w, (const bf16 *)q, (const bf16 *)k, (const bf16 *)v, (const bf16 *)a,
-             (const bf16 *)b, (bf16 *)y, ckT, sa, s0, sT, g_tc_dbg};
+             (const bf16 *)b, (bf16 *)y, ckT, sa, s0, sT, g_tc_dbg, cu, cbase};
     if (watchdog_needs_install(0, st)) {
         cudaError_t e = watchdog_install(watchdog_record(), 1);
         if (e != cudaSuccess) return e;
     }
     count_launch();
-    if (ckT != nullptr) {
-        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(Smem));
+    auto go = [&](auto kern, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
         if (e != cudaSuccess) return e;
-        wkv7_tc_fwd_kernel<true><<<dim3(B * H), dim3(kThreadsTrain), sizeof(Smem), st>>>(P);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(wkv7_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(Smem));
-        if (e != cudaSuccess) return e;
-        wkv7_tc_fwd_kernel<false><<<dim3(B * H), dim3(kThreads), sizeof(Smem), st>>>(P);
-    }
+        kern<<<dim3(B * H), dim3(threads), sizeof(Smem), st>>>(P);
+        return cudaSuccess;
+    };
+    cudaError_t e;
+    if (ckT != nullptr) e = cu ? go(wkv7_tc_fwd_kernel<true, true>, kThreadsTrain) : go(wkv7_tc_fwd_kernel<true, false>, kThreadsTrain);
+    else e = cu ? go(wkv7_tc_fwd_kernel<false, true>, kThreads) : go(wkv7_tc_fwd_kernel<false, false>, kThreads);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 

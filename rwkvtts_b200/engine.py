@@ -429,7 +429,8 @@ class Engine:
                         self.exp_avg_sq[so:so + n].data_ptr(), g.data_ptr(), int(g.dtype == torch.bfloat16),
                         pslice.data_ptr(), int(pslice.dtype == torch.bfloat16), n, ends.data_ptr(), gids.data_ptr(),
                         ends.numel(), hp_c, len(hp), b1, b2, eps, self.optimizer.adam_w_mode, self._stat.data_ptr(),
-                        self.gradient_clipping, self._skipped.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+                        self.gradient_clipping, self._skipped.data_ptr() if b == 0 else None,      # one count per step
+                        torch.cuda.current_stream(self.device).cuda_stream)
                 _lib.check(rc, "rwkvtts_adam_multi")
             else:
                 self._cpu_adam(b, g, pslice, hp, b1, b2, eps)

@@ -88,25 +88,26 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
 
 class _ShiftMix(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, mixes, mask, prev):
-        # x [B,T,C] bf16; mixes [n,C] (any float dtype); mask [B,T] bf16 | None; prev [B,C] bf16 | None
-        _need_cuda(x, mixes, mask, prev)
+    def forward(ctx, x, mixes, mask, prev, first=None):
+        # x [B,T,C] bf16; mixes [n,C] (any float dtype); mask [B,T] bf16 | None; prev [B,C] bf16 | None;
+        # first [B*T] uint8 | None: 1 on the first token of every sequence of a packed batch
+        _need_cuda(x, mixes, mask, prev, first)
         B, T, C = x.shape
         n = mixes.shape[0]
         x = x.contiguous()
         mix32 = mixes.detach().to(torch.float32).contiguous()
         outs = [torch.empty_like(x) for _ in range(n)]
         with torch.cuda.device(x.device):
-            rc = _lib.lib().rwkvtts_tmix_shift_mix_forward(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
-                                                           _ptr_array(outs), None, _stream())
+            rc = _lib.lib().rwkvtts_tmix_shift_mix_forward_varlen(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
+                                                                  _ptr_array(outs), None, _ptr(first), _stream())
         _lib.check(rc, "rwkvtts_tmix_shift_mix_forward")
-        ctx.save_for_backward(x, mix32, mask, prev)
+        ctx.save_for_backward(x, mix32, mask, prev, first)
         ctx.mix_dtype = mixes.dtype
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *douts):
-        x, mix32, mask, prev = ctx.saved_tensors
+        x, mix32, mask, prev, first = ctx.saved_tensors
         B, T, C = x.shape
         n = mix32.shape[0]
         douts = [torch.zeros_like(x) if d is None else d.contiguous() for d in douts]
@@ -114,19 +115,21 @@ class _ShiftMix(torch.autograd.Function):
         dmix = torch.empty_like(mix32)
         scratch = _scratch(B, T, C, n, x.device)
         with torch.cuda.device(x.device):
-            rc = _lib.lib().rwkvtts_tmix_shift_mix_backward(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
-                                                            _ptr_array(douts), _ptr(dx), _ptr(dmix), _ptr(scratch), _stream())
+            rc = _lib.lib().rwkvtts_tmix_shift_mix_backward_varlen(B, T, C, n, _ptr(x), _ptr(mask), _ptr(prev), _ptr(mix32),
+                                                                   _ptr_array(douts), _ptr(dx), _ptr(dmix), _ptr(scratch),
+                                                                   _ptr(first), _stream())
         _lib.check(rc, "rwkvtts_tmix_shift_mix_backward")
-        return dx, dmix.to(ctx.mix_dtype), None, None
+        return dx, dmix.to(ctx.mix_dtype), None, None, None
 
 
 def shift_mix(x: torch.Tensor, mixes: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
-              prev: Optional[torch.Tensor] = None):
-    """[x + (shift(x*mask) - x*mask) * m for m in mixes]; mixes broadcastable to [C] (n = 1 or 6)."""
+              prev: Optional[torch.Tensor] = None, seq_first: Optional[torch.Tensor] = None):
+    """[x + (shift(x*mask) - x*mask) * m for m in mixes]; mixes broadcastable to [C] (n = 1 or 6).  seq_first (uint8
+    [B*T], packed batches): the shift restarts with zeros at every flagged token."""
     B, T, C = x.shape
     m = _stack32(mixes)
     prev_ = None if prev is None else prev.detach().to(BF16).contiguous()
-    return _ShiftMix.apply(x, m, _mask2d(mask, B, T), prev_)
+    return _ShiftMix.apply(x, m, _mask2d(mask, B, T), prev_, seq_first)
 
 
 @torch.no_grad()

@@ -18,6 +18,8 @@ PyTorch is only the owner of device memory and streams here.
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -242,6 +244,64 @@ class _Wkv7WithState(torch.autograd.Function):
         wkv7_backward_(w, q, k, v, a, b, dy.contiguous(), s, sa, *grads, s0=s0,
                        dsT=dsT.contiguous() if dsT is not None else None, ds0=ds0, sT=sT.detach())
         return (*grads, ds0)
+
+
+class VarlenPlan:
+    """Device-side description of a packed batch, built once per batch (no host sync): cu_seqlens as int32, the first
+    chunk slot of every sequence inside the scratch tensors, and the per-token `first` flags the token shift needs."""
+
+    def __init__(self, cu_seqlens: torch.Tensor, total: int):
+        cu = cu_seqlens.reshape(-1).to(torch.int32).contiguous()
+        self.cu, self.N, self.total = cu, cu.numel() - 1, int(total)
+        chunks = (cu[1:] - cu[:-1] + (CHUNK_LEN - 1)) // CHUNK_LEN
+        self.cbase = torch.cat([torch.zeros(1, dtype=torch.int32, device=cu.device), chunks.cumsum(0).to(torch.int32)]).contiguous()
+        first = torch.zeros(self.total + 1, dtype=torch.uint8, device=cu.device)
+        first.index_fill_(0, cu.to(torch.long), 1)
+        self.first = first[:self.total].contiguous()
+
+
+class _Wkv7Varlen(torch.autograd.Function):
+    """chunk_rwkv7(..., cu_seqlens=) semantics on one packed [1, T_total, H, 64] tensor: zero state at every boundary."""
+
+    @staticmethod
+    def forward(ctx, w, q, k, v, a, b, plan):
+        _need_cuda(w, q, k, v, a, b)
+        _, T, H, C = w.shape
+        y = torch.empty_like(v)
+        L = _lib.lib()
+        train = any(ctx.needs_input_grad[:6])
+        s = sa = None
+        if train:
+            ns, nsa = ctypes.c_size_t(), ctypes.c_size_t()
+            L.rwkvtts_wkv7_varlen_scratch_floats(T, H, plan.N, ctypes.byref(ns), ctypes.byref(nsa))
+            s = torch.empty(ns.value, dtype=torch.float32, device=w.device)
+            sa = torch.empty(nsa.value, dtype=torch.float32, device=w.device)
+        with torch.cuda.device(w.device), _timed("fwd"):
+            rc = L.rwkvtts_wkv7_forward_varlen(T, H, plan.N, _ptr(plan.cu), _ptr(plan.cbase), _ptr(w), _ptr(q), _ptr(k),
+                                               _ptr(v), _ptr(a), _ptr(b), _ptr(y), _ptr(s), _ptr(sa), _stream())
+        _lib.check(rc, "rwkvtts_wkv7_forward_varlen")
+        if train:
+            ctx.save_for_backward(w, q, k, v, a, b, s, sa)
+            ctx.plan = plan
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        w, q, k, v, a, b, s, sa = ctx.saved_tensors
+        plan = ctx.plan
+        _, T, H, C = w.shape
+        grads = [torch.empty_like(x) for x in (w, q, k, v, a, b)]
+        with torch.cuda.device(w.device), _timed("bwd"):
+            rc = _lib.lib().rwkvtts_wkv7_backward_varlen(T, H, plan.N, _ptr(plan.cu), _ptr(plan.cbase), _ptr(w), _ptr(q),
+                                                         _ptr(k), _ptr(v), _ptr(a), _ptr(b), _ptr(dy.contiguous()), _ptr(s),
+                                                         _ptr(sa), *[_ptr(g) for g in grads], _stream())
+        _lib.check(rc, "rwkvtts_wkv7_backward_varlen")
+        return (*grads, None)
+
+
+def wkv7_varlen(w, q, k, v, a, b, plan: "VarlenPlan"):
+    """y for a packed batch: w,q,k,v,a,b bf16 [1, T_total, H, 64] contiguous (op order), `plan` from VarlenPlan."""
+    return _Wkv7Varlen.apply(w, q, k, v, a, b, plan)
 
 
 def wkv7_with_state(w, q, k, v, a, b, initial_state=None):
