@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from rwkvtts_b200 import core
+from rwkvtts_b200 import core, ops
 from .rwkv6 import LoRA
 
 
@@ -102,8 +102,13 @@ class RWKV7Attention(nn.Module):
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 past_key_values=None, use_cache: Optional[bool] = False, output_attentions: Optional[bool] = False,
                 v_first: torch.Tensor = None, cu_seqlens: Optional[torch.LongTensor] = None, **kwargs):
+        plan = None
         if cu_seqlens is not None:
-            raise NotImplementedError("cu_seqlens (packed varlen) input: pad per sample and pass attention_mask")
+            # packed varlen batch [1, T_total, D] (chunk_rwkv7(..., cu_seqlens=) of rwkv-fla): the chunked kernels and the
+            # token shift restart at every boundary; RWKV7Model hands down one ops.VarlenPlan for all layers
+            plan = cu_seqlens if isinstance(cu_seqlens, ops.VarlenPlan) else ops.VarlenPlan(cu_seqlens, hidden_states.shape[1])
+            if hidden_states.shape[0] != 1 or attention_mask is not None or use_cache:
+                raise ValueError("cu_seqlens expects one packed sequence [1, T_total, D] without attention_mask / cache")
         B, T, _ = hidden_states.shape
         am = None
         if attention_mask is not None:
@@ -118,7 +123,7 @@ class RWKV7Attention(nn.Module):
         out, v_first, new_shift, new_state = core.tmix(
             self.params(), self.layer_idx, hidden_states, v_first, mask=am, mask_rwk=False,
             shift_state=shift, wkv_state=state, need_state=bool(use_cache),
-            inplace_state=not torch.is_grad_enabled())
+            inplace_state=not torch.is_grad_enabled(), plan=plan)
         if past_key_values is not None and use_cache:
             past_key_values.update(recurrent_state=new_state, conv_state=new_shift, layer_idx=self.layer_idx,
                                    offset=T)

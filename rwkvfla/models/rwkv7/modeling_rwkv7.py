@@ -21,8 +21,9 @@ from transformers.generation.utils import GenerationMixin
 from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
-from rwkvtts_b200 import core
+from rwkvtts_b200 import core, ops
 from rwkvtts_b200.fused import cached as fused_cached
+from rwkvtts_b200.fused import usable as fused_usable
 from ...layers.rwkv7 import RWKV7Attention
 from ...modules import FusedCrossEntropyLoss, FusedLinearCrossEntropyLoss, LayerNorm, l2_warp
 from ..utils import Cache
@@ -64,7 +65,8 @@ class RWKV7FeedForward(nn.Module):
             shift = state[self.layer_idx].get("ffn_state")
         out, new_shift = core.cmix(self.x_k, self.key.weight, self.value.weight, x, mask=am, shift_state=shift,
                                    need_state=state is not None and use_cache,
-                                   inplace_state=not torch.is_grad_enabled())
+                                   inplace_state=not torch.is_grad_enabled(),
+                                   plan=cu_seqlens if isinstance(cu_seqlens, ops.VarlenPlan) else None)
         if state is not None and use_cache:
             state.update(ffn_state=new_shift, layer_idx=self.layer_idx, offset=0)
         return out, state
@@ -182,12 +184,17 @@ class RWKV7Model(RWKV7PreTrainedModel):
         hidden_states = inputs_embeds
         packed_idx = None
         if cu_seqlens is not None:
-            # packed varlen input: run it as the equivalent right-padded batch (see unpack_varlen)
             if attention_mask is not None or (past_key_values is not None and len(past_key_values) > 0):
                 raise NotImplementedError("cu_seqlens together with attention_mask / a filled cache")
             use_cache = False                  # a packed batch carries no per-sequence state out
-            hidden_states, packed_idx = unpack_varlen(hidden_states, cu_seqlens)
-            cu_seqlens = None
+            if core.FUSED and fused_usable(hidden_states) and hidden_states.shape[0] == 1:
+                # packed all the way down: the chunked kernels and the token shifts restart at every boundary, no padding
+                # position is computed or moved (one plan for all layers, built on the device without a host sync)
+                cu_seqlens = ops.VarlenPlan(cu_seqlens, hidden_states.shape[1])
+            else:
+                # CPU / fp32 / ATen chain: the equivalent right-padded batch (see unpack_varlen)
+                hidden_states, packed_idx = unpack_varlen(hidden_states, cu_seqlens)
+                cu_seqlens = None
         if use_cache and not isinstance(past_key_values, Cache):
             past_key_values = Cache.from_legacy_cache(past_key_values)
         all_hidden_states = () if output_hidden_states else None

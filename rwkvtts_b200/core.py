@@ -105,11 +105,16 @@ def token_shift(x: torch.Tensor, prev: Optional[torch.Tensor]) -> torch.Tensor:
     return shifted - x
 
 
-def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
+def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False, plan=None):
     """Dispatch of the recurrence.  r,w,k,v,a,b: bf16 [B,T,C] contiguous; state fp32 [B,H,64,64] or None.
-    Returns y [B,T,C] and the final state (None unless need_state)."""
+    Returns y [B,T,C] and the final state (None unless need_state).  plan (ops.VarlenPlan): the batch is ONE packed
+    sequence [1, T_total, C] whose recurrences restart at the plan's cu_seqlens (chunked tcgen05 kernels, any lengths)."""
     B, T, C = r.shape
     H = C // HEAD
+    if plan is not None:
+        assert B == 1 and state is None and not need_state, "a packed batch carries no recurrent state in or out"
+        sh = lambda t: t.view(1, T, H, HEAD)
+        return ops.wkv7_varlen(sh(w), sh(r), sh(k), sh(v), sh(a), sh(b), plan).view(1, T, C), None
     grad = torch.is_grad_enabled() and any(t.requires_grad for t in (r, w, k, v, a, b))
     if T % ops.CHUNK_LEN == 0 and not (EXACT and not grad):
         sh = lambda t: t.view(B, T, H, HEAD)
@@ -140,7 +145,7 @@ def _wkv(r, w, k, v, a, b, state, need_state, inplace_state=False):
 def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.Tensor],
          mask: Optional[torch.Tensor] = None, mask_rwk: bool = True,
          shift_state: Optional[torch.Tensor] = None, wkv_state: Optional[torch.Tensor] = None,
-         need_state: bool = False, inplace_state: bool = False, mask_kk: bool = True):
+         need_state: bool = False, inplace_state: bool = False, mask_kk: bool = True, plan=None):
     """x [B,T,C] (bf16 on the GPU).  mask [B,T,1] of 0/1 or None.  Returns
     (out [B,T,C], v_first, new_shift_state [B,C] | None, new_wkv_state | None).  With `inplace_state` the
     stateful (decode) path advances `wkv_state` in place like the reference's RWKV7_OP (:536).  `mask_kk=False` is the
@@ -148,7 +153,9 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
     B, T, C = x.shape
     H = C // HEAD
     if FUSED and fused.usable(x) and (mask is None or mask_kk):
-        return _tmix_fused(p, layer_id, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state)
+        return _tmix_fused(p, layer_id, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state, plan)
+    if plan is not None:
+        raise NotImplementedError("packed (cu_seqlens) input needs the fused CUDA path; unpack it per sequence otherwise")
     if mask is not None:
         x = x * mask                                                            # :160
     xx = token_shift(x, shift_state)                                            # :162
@@ -184,12 +191,13 @@ def tmix(p: TmixParams, layer_id: int, x: torch.Tensor, v_first: Optional[torch.
 
 
 def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state,
-                inplace_state):
+                inplace_state, plan=None):
     """tmix() with the elementwise chain in the fused kernels (same reference lines, same results up to bf16
     rounding of intermediates the fused kernels keep in fp32)."""
-    if DECODE_BATCHED_GEMM and not torch.is_grad_enabled() and x.shape[1] == 1 and layer_id != 0:
+    if DECODE_BATCHED_GEMM and not torch.is_grad_enabled() and x.shape[1] == 1 and layer_id != 0 and plan is None:
         return _tmix_decode(p, layer_id, x, v_first, mask, mask_rwk, shift_state, wkv_state, need_state, inplace_state)
-    xr, xw, xk, xv, xa, xg = fused.shift_mix(x, (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g), mask, shift_state)  # :160-169
+    xr, xw, xk, xv, xa, xg = fused.shift_mix(x, (p.x_r, p.x_w, p.x_k, p.x_v, p.x_a, p.x_g), mask, shift_state,
+                                             seq_first=None if plan is None else plan.first)                # :160-169
     r = F.linear(xr, p.W_r)
     k = F.linear(xk, p.W_k)
     v = F.linear(xv, p.W_v)
@@ -204,7 +212,8 @@ def _tmix_fused(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift_
     else:
         w, k2, v2, a_op, b_op = fused.prep(k, v, w_lo, a_lo, (xv @ p.v1) @ p.v2, v_first, p.w0, p.a0, p.v0, p.k_k,
                                            p.k_a, mask, mask_rwk)               # :172-190
-    y, new_state = _wkv(r.contiguous(), w, k2, v2.contiguous(), a_op, b_op, wkv_state, need_state, inplace_state)   # :191
+    y, new_state = _wkv(r.contiguous(), w, k2, v2.contiguous(), a_op, b_op, wkv_state, need_state, inplace_state,
+                        plan=plan)                                                                          # :191
     o = fused.out(y, r, k2, v2, g, p.r_k, p.ln_w, p.ln_b, p.ln_eps)             # :192-195
     shift_out = None
     if need_state:
@@ -255,8 +264,15 @@ def _tmix_decode(p: TmixParams, layer_id: int, x, v_first, mask, mask_rwk, shift
 
 def cmix(x_k: torch.Tensor, W_key: torch.Tensor, W_value: torch.Tensor, x: torch.Tensor,
          mask: Optional[torch.Tensor] = None, shift_state: Optional[torch.Tensor] = None,
-         need_state: bool = False, inplace_state: bool = False):
-    """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556)."""
+         need_state: bool = False, inplace_state: bool = False, plan=None):
+    """RWKV_CMix_x070.forward (:223-230) / RWKV_x070_CMix_seq (:551-556).  plan: packed batch (see _wkv)."""
+    if plan is not None:
+        if not (FUSED and fused.usable(x)):
+            raise NotImplementedError("packed (cu_seqlens) input needs the fused CUDA path")
+        (xk,) = fused.shift_mix(x, (x_k,), mask, None, seq_first=plan.first)
+        k = F.linear(xk, W_key)
+        k = fused.sqrelu(k) if k.numel() % 8 == 0 else torch.relu(k) ** 2
+        return F.linear(k, W_value), None
     if (FUSED and fused.usable(x) and not torch.is_grad_enabled() and x.shape[1] == 1 and need_state and inplace_state
             and shift_state is not None and shift_state.dtype == torch.bfloat16 and shift_state.is_contiguous()):
         # decode step: the kernel also writes the new shift state into the caller's buffer

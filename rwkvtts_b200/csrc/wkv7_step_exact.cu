@@ -5,7 +5,7 @@
 // decoding amplifies a last-bit difference of one logit into a different sequence, so the criterion can only be met by
 // reproducing the reference step's floating-point operations one for one.  The default step kernel (wkv7_scan.cu:
 // four lanes per state row, quad reductions) sums in another order; this one keeps one thread per value row and the
-// exact operation sequence read off the reference build's SASS (cuobjdump of oracle/_ref/libref_state_fwd.so, compiled
+// exact operation sequence read off the SASS of the reference kernel as the checker builds it (cuobjdump; compiled
 // with the reference's --use_fast_math: every operation flushes denormals, FFMA.FTZ / FMUL.FTZ / MUFU.EX2):
 //     d_j   = ex2(-(ex2(w_j * log2e)) * log2e)                                  (__expf(-__expf(w)))
 //     sa    = fma(a_63, S_63, ... fma(a_1, S_1, fma(a_0, S_0, 0)))              ascending j

@@ -1,0 +1,143 @@
+"""Packed variable-length batches (cu_seqlens) inside the kernels (round-1 VERDICT missing #2; SURVEY.md section 8 rows
+a10 / b): the chunked tcgen05 pair and the token-shift kernels restart at every sequence boundary, boundaries need not be
+16-aligned, and a packed batch gives what the per-sample runs give -- without computing or moving a padding token."""
+import pytest
+import torch
+
+from oracle import wkv7_oracle as O
+
+pytestmark = pytest.mark.gpu
+ORDER = "wqkvab"
+
+
+def _packed_inputs(lens, H, seed):
+    xs = [O.make_inputs(1, l, H, seed=seed + i) for i, l in enumerate(lens)]
+    packed = {n: torch.cat([x[n] for x in xs], dim=1).contiguous() for n in list(ORDER) + ["dy"]}
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32)
+    return xs, packed, cu
+
+
+@pytest.mark.parametrize("lens,H", [([37, 16, 1, 100, 64, 5], 3), ([512, 300], 2), ([15], 1), ([16, 16, 16], 2),
+                                     ([1, 1, 2, 3, 250], 4)])
+def test_packed_forward_and_backward_equal_the_per_sequence_oracle(lens, H):
+    from rwkvtts_b200 import ops
+    xs, packed, cu = _packed_inputs(lens, H, seed=sum(lens))
+    d = {n: t.cuda() for n, t in packed.items()}
+    plan = ops.VarlenPlan(cu.cuda(), sum(lens))
+    leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
+    y = ops.wkv7_varlen(*leaves, plan)
+    y.backward(d["dy"])
+    torch.cuda.synchronize()
+    y_ng = torch.empty(0)
+    with torch.no_grad():
+        y_ng = ops.wkv7_varlen(*[d[n] for n in ORDER], plan)            # snapshot-free kernel
+    off = 0
+    for x, l in zip(xs, lens):
+        y64, _ = O.wkv7_forward(*[x[n] for n in ORDER])
+        g64 = O.wkv7_backward(*[x[n] for n in ORDER], x["dy"])
+        sl = slice(off, off + l)
+        rows = [("y", y[:, sl].detach().cpu(), y64), ("y_nograd", y_ng[:, sl].cpu(), y64)]
+        rows += [("d" + n, leaf.grad[:, sl].cpu(), g) for n, leaf, g in zip(ORDER, leaves, g64)]
+        for name, got, ref in rows:
+            exc, err, floor = O.excess_rel_l2(got, ref)
+            # short sequences: a handful of elements, the bf16 floor estimate is noisy -> absolute bar next to the excess
+            assert exc <= 1e-3 or err <= 4e-3, f"{name} len={l}: excess {exc:.3e} (err {err:.3e}, floor {floor:.3e})"
+        off += l
+
+
+def test_packed_launch_equals_dense_launch_on_aligned_equal_lengths():
+    """lens all equal and multiples of 16: the packed kernels must reproduce the dense [B,T,H,64] launch bit for bit."""
+    import rwkvtts_b200 as R
+    from rwkvtts_b200 import ops
+    B, T, H = 3, 64, 2
+    x = O.make_inputs(B, T, H, seed=9)
+    d = {n: t.cuda() for n, t in x.items()}
+    leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
+    y = R.WindBackstepping.apply(*leaves)
+    y.backward(d["dy"])
+    pk = {n: t.reshape(1, B * T, H, 64).contiguous() for n, t in d.items()}
+    pl = [pk[n].clone().requires_grad_(True) for n in ORDER]
+    plan = ops.VarlenPlan(torch.arange(0, B * T + 1, T, dtype=torch.int32, device="cuda"), B * T)
+    yp = ops.wkv7_varlen(*pl, plan)
+    yp.backward(pk["dy"])
+    torch.cuda.synchronize()
+    assert torch.equal(yp.view(B, T, H, 64), y)
+    for a, b in zip(pl, leaves):
+        assert torch.equal(a.grad.view(B, T, H, 64), b.grad)
+
+
+def test_shift_mix_restarts_at_sequence_boundaries():
+    from rwkvtts_b200 import fused, ops
+    lens, C = [5, 1, 9, 16, 2], 128
+    tot = sum(lens)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(1, tot, C, device="cuda", generator=g).bfloat16().requires_grad_(True)
+    mixes = [(torch.rand(C, device="cuda", generator=g)).bfloat16().requires_grad_(True) for _ in range(6)]
+    dout = [torch.randn(1, tot, C, device="cuda", generator=g).bfloat16() for _ in range(6)]
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    plan = ops.VarlenPlan(cu, tot)
+    outs = fused.shift_mix(x, mixes, None, None, seq_first=plan.first)
+    torch.autograd.backward(outs, dout)
+    got = [o.detach().clone() for o in outs], x.grad.clone(), [m.grad.clone() for m in mixes]
+    x.grad = None
+    for m in mixes:
+        m.grad = None
+    # the same, sequence by sequence through the dense kernel
+    off, ref_out, = 0, [[] for _ in range(6)]
+    for l in lens:
+        o = fused.shift_mix(x[:, off:off + l], mixes, None, None)
+        torch.autograd.backward(o, [dd[:, off:off + l] for dd in dout])
+        for i in range(6):
+            ref_out[i].append(o[i].detach())
+        off += l
+    for i in range(6):
+        assert torch.equal(got[0][i], torch.cat(ref_out[i], dim=1)), i
+    assert torch.equal(got[1], x.grad)
+    for a, m in zip(got[2], mixes):
+        assert torch.allclose(a.float(), m.grad.float(), rtol=2e-2, atol=2e-2)
+
+
+def test_packed_model_forward_backward_equals_per_sample_runs():
+    """RWKV7ForCausalLM on a packed batch (inputs_embeds + cu_seqlens, what the reference's *_culens collators feed,
+    train_spark_rwkv7speech.py:238-239): hidden states, loss and gradients equal the per-sample runs."""
+    from rwkvfla.models.rwkv7 import RWKV7Config, RWKV7ForCausalLM
+    torch.manual_seed(0)
+    cfg = RWKV7Config(hidden_size=128, num_hidden_layers=2, head_dim=64, vocab_size=97, decay_low_rank_dim=32,
+                      a_low_rank_dim=32, v_low_rank_dim=16, gate_low_rank_dim=32)
+    m = RWKV7ForCausalLM(cfg)
+    with torch.no_grad():
+        for _, p in m.named_parameters():
+            if p.abs().sum() == 0:
+                p.copy_(torch.randn_like(p) * 0.05)
+    m = m.cuda().to(torch.bfloat16).train()
+    lens = [23, 48, 7, 64]
+    tot = sum(lens)
+    emb = (torch.randn(1, tot, 128, device="cuda") * 0.5).bfloat16()
+    labels = torch.randint(0, 97, (1, tot), device="cuda")
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
+    from rwkvtts_b200 import _lib
+    n0 = _lib.lib().rwkvtts_kernel_launches()
+    out = m.model(inputs_embeds=emb, cu_seqlens=cu)
+    hp = out.last_hidden_state
+    assert hp.shape == (1, tot, 128)
+    loss_p = torch.nn.functional.cross_entropy(m.lm_head(hp).float().view(tot, -1), labels.view(-1), reduction="sum")
+    m.zero_grad(set_to_none=True)
+    loss_p.backward()
+    gp = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    # per sample
+    m.zero_grad(set_to_none=True)
+    off, hs, loss_s = 0, [], 0.0
+    for l in lens:
+        h = m.model(inputs_embeds=emb[:, off:off + l]).last_hidden_state
+        hs.append(h.detach())
+        loss_s = loss_s + torch.nn.functional.cross_entropy(m.lm_head(h).float().view(l, -1), labels[:, off:off + l].view(-1),
+                                                            reduction="sum")
+        off += l
+    loss_s.backward()
+    href = torch.cat(hs, dim=1)
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm().clamp(min=1e-6))
+    assert rel(hp.detach(), href) < 1e-2, rel(hp.detach(), href)
+    assert abs(float(loss_p) - float(loss_s)) < 5e-3 * abs(float(loss_s))
+    for n, p in m.named_parameters():
+        if p.grad is not None and float(p.grad.float().norm()) > 1e-4:
+            assert rel(gp[n], p.grad) < 6e-2, (n, rel(gp[n], p.grad))
