@@ -195,11 +195,16 @@ def train_arm(args, rank, local_rank, world):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     log("timed region (%d steps)" % args.steps)
+    prof = os.environ.get("RWKVTTS_BENCH_PROFILE") == "1"        # ncu --profile-from-start off: only the timed region
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         loss = step(dev_batch)
     e1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     launches = lib.rwkvtts_kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     timing, ops.TIMING = ops.TIMING, None

@@ -65,7 +65,7 @@ class FusedLinearCrossEntropyLoss(nn.Module):
         y = target.reshape(-1)
         if core.FUSED and not self.use_l2warp and self.reduction in ("mean", "sum") and fused.linear_ce_usable(h, weight, bias):
             # CUDA bf16: logits GEMM -> CE kernel (loss + gradient in place) -> gradient GEMMs, chunk by chunk
-            return fused.linear_cross_entropy(h, y, weight, self.ignore_index, self.label_smoothing, self.reduction)
+            return fused.linear_cross_entropy(h, y, weight, self.ignore_index, self.label_smoothing, self.reduction, bias=bias)
         n = max(1, min(self.num_chunks, h.shape[0]))
         total = h.new_zeros((), dtype=torch.float32)
         for hc, yc in zip(h.chunk(n), y.chunk(n)):

@@ -399,8 +399,8 @@ def embed_rows(weights, row_src, ids, dst):
 
 
 def linear_ce_usable(h, weight, bias) -> bool:
-    return (h.is_cuda and h.dtype == BF16 and weight.dtype == BF16 and bias is None and h.shape[-1] % 8 == 0
-            and weight.shape[0] <= (1 << 20))
+    return (h.is_cuda and h.dtype == BF16 and weight.dtype == BF16 and (bias is None or bias.dtype == BF16)
+            and h.shape[-1] % 8 == 0 and weight.shape[0] <= (1 << 20))
 
 
 class _LinearCE(torch.autograd.Function):
@@ -409,11 +409,12 @@ class _LinearCE(torch.autograd.Function):
     the forward; the backward only scales by the incoming gradient.  dW accumulates in fp32 across the chunks."""
 
     @staticmethod
-    def forward(ctx, h, labels, weight, ignore_index, label_smoothing, reduction, chunk_rows):
+    def forward(ctx, h, labels, weight, bias, ignore_index, label_smoothing, reduction, chunk_rows):
         N, D = h.shape
         V = weight.shape[0]
         Vp = (V + 7) // 8 * 8
         Wp = weight if Vp == V else torch.nn.functional.pad(weight, (0, 0, 0, Vp - V))       # aligned tensor-core GEMMs
+        bp = None if bias is None else (bias if Vp == V else torch.nn.functional.pad(bias, (0, Vp - V)))
         valid = labels != ignore_index
         if reduction == "mean":
             scale = (1.0 / valid.sum().clamp(min=1).to(torch.float32)).reshape(1)
@@ -423,11 +424,12 @@ class _LinearCE(torch.autograd.Function):
         need = torch.is_grad_enabled() or h.requires_grad or weight.requires_grad
         dh = torch.empty_like(h) if need else None
         dW = torch.zeros(Vp, D, dtype=torch.float32, device=h.device) if need else None
+        db = torch.zeros(Vp, dtype=torch.float32, device=h.device) if (need and bias is not None) else None
         L = _lib.lib()
         for s in range(0, N, chunk_rows):
             e = min(N, s + chunk_rows)
             hc = h[s:e]
-            logits = torch.mm(hc, Wp.t())
+            logits = torch.mm(hc, Wp.t()) if bp is None else torch.addmm(bp, hc, Wp.t())
             with torch.cuda.device(h.device):
                 rc = L.rwkvtts_ce_forward_backward(_ptr(logits), e - s, V, Vp, _ptr(labels[s:e]), int(ignore_index),
                                                    float(label_smoothing), _ptr(scale), _ptr(loss_rows[s:e]), _stream())
@@ -435,20 +437,25 @@ class _LinearCE(torch.autograd.Function):
             if need:
                 torch.mm(logits, Wp, out=dh[s:e])
                 dW += torch.mm(logits.t(), hc, out_dtype=torch.float32)
+                if db is not None:
+                    db += logits.sum(0, dtype=torch.float32)
         loss = loss_rows.sum() * scale[0]
         if need:
-            ctx.save_for_backward(dh, dW[:V].to(BF16))
+            ctx.has_bias = bias is not None
+            ctx.save_for_backward(dh, dW[:V].to(BF16), *([db[:V].to(BF16)] if db is not None else []))
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        dh, dW = ctx.saved_tensors
+        dh, dW = ctx.saved_tensors[:2]
         g = g.to(torch.float32)
-        return (dh * g).to(dh.dtype), None, (dW * g).to(dW.dtype), None, None, None, None
+        dbias = (ctx.saved_tensors[2] * g).to(BF16) if ctx.has_bias else None
+        return (dh * g).to(dh.dtype), None, (dW * g).to(dW.dtype), dbias, None, None, None, None
 
 
-def linear_cross_entropy(h, labels, weight, ignore_index=-100, label_smoothing=0.0, reduction="mean", chunk_rows=4096):
-    """h [N, D] bf16, labels [N] int64, weight [V, D] bf16 -> scalar fp32 loss (see _LinearCE)."""
-    _need_cuda(h, labels, weight)
-    return _LinearCE.apply(h.contiguous(), labels.contiguous(), weight.contiguous(), ignore_index, label_smoothing,
+def linear_cross_entropy(h, labels, weight, ignore_index=-100, label_smoothing=0.0, reduction="mean", chunk_rows=4096,
+                         bias=None):
+    """h [N, D] bf16, labels [N] int64, weight [V, D] bf16 (+ bias [V]) -> scalar fp32 loss (see _LinearCE)."""
+    _need_cuda(h, labels, weight, bias)
+    return _LinearCE.apply(h.contiguous(), labels.contiguous(), weight.contiguous(), bias, ignore_index, label_smoothing,
                            reduction, chunk_rows)

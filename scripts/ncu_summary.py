@@ -60,5 +60,28 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """profiles/r02_wkv_traffic.json: dram bytes per launch of the two training kernels (what bench.py's roofline.traffic
+    reads): python scripts/ncu_summary.py traffic gpurun_out/tc_full.ncu-rep > profiles/r02_wkv_traffic.json"""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res = {"source": f"ncu --set full --clock-control none capture of scripts/run_pair.py at config c2 ({path})"}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+        if "tc_bwd" in name:
+            res["bwd_bytes"] = tot
+        elif "tc_fwd" in name and ("<1" in name or "true" in name or "Lb1" in name):
+            res.setdefault("fwd_bytes", tot)
+        res.setdefault("kernels", []).append({"name": name.split("(")[0], "dram_bytes": tot})
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])

@@ -230,3 +230,94 @@ def test_reference_lr_scheduler_path_on_the_engine(stand_in_blocks):
     want = [args.learning_rate * f for f in (0.5, 1.0, 1.0 - (1 / 8) * (1 - 0.01), 1.0 - (2 / 8) * (1 - 0.01))]
     assert all(abs(a - b) < 1e-12 for a, b in zip(lrs, want)), (lrs, want)
     assert losses[-1] < losses[1]                       # the first step runs at lr = 0 (warm-up from zero)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# this repo's own layout classes (rwkvtts_b200/spark.py, layouts.py: what runs where the reference tree is absent)
+# against the reference's classes: same state-dict keys, same loss / logits on the same batch
+# ---------------------------------------------------------------------------------------------------------------
+def _same(a, b, tol=1e-5):
+    return float((a.float() - b.float()).abs().max()) <= tol * max(1.0, float(b.float().abs().max()))
+
+
+def test_own_layout_classes_are_interchangeable_with_the_reference_classes(stand_in_blocks):
+    import test_batch_builder as tb
+    from rwkvtts_b200 import layouts, spark
+    from rwkvtts_b200.batch import create_inputs_and_labels
+    # Spark
+    mod = _load("ref_spark_llm2", "model/llm/spark_llm.py")
+    torch.manual_seed(0)
+    kw = dict(vocab_size=131, text_vocab_size=500, audio_global_vocab_size=64, fuse_cross_entropy=False, **SMALL)
+    ref = mod.RWKV7ForSpeech(mod.RWKV7SpeechConfig(**kw)).eval()
+    own = spark.RWKV7ForSpeech(spark.RWKV7SpeechConfig(**kw)).eval()
+    assert set(own.state_dict()) == set(ref.state_dict())
+    own.load_state_dict(ref.state_dict(), strict=True)
+    out = create_inputs_and_labels(tb.make_batch(), tb.Tok(), ref, 130, "cpu")
+    with torch.no_grad():
+        a = ref(inputs_embeds=out["input_embs"], attention_mask=out["attention_mask"], labels=out["labels"], return_dict=True)
+        b = own(inputs_embeds=out["input_embs"], attention_mask=out["attention_mask"], labels=out["labels"])
+    assert _same(b.logits, a.logits) and _same(b.loss, a.loss)
+    # Cosy
+    mod = _load("ref_cosy_llm2", "model/llm/cosy_llm.py")
+    kw = dict(vocab_size=100, speech_token_size=50, lsm_weight=0.1, **SMALL)
+    ref = mod.RWKV7CosyLM(mod.RWKV7CosyConfig(**kw)).eval()
+    own = layouts.RWKV7CosyLM(layouts.RWKV7CosyConfig(**kw)).eval()
+    assert set(own.state_dict()) == set(ref.state_dict())
+    own.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(3)
+    batch = {"text_token": torch.randint(0, 100, (3, 7), generator=g), "text_token_len": torch.tensor([7, 2, 5]),
+             "speech_token": torch.randint(0, 50, (3, 11), generator=g), "speech_token_len": torch.tensor([4, 11, 9])}
+    with torch.no_grad():
+        a, b = ref(batch=batch, return_dict=True), own(batch=batch)
+    assert _same(b.logits, a.logits) and _same(b.loss, a.loss)
+    # XY
+    mod = _load("ref_xy_llm2", "model/llm/xy_llm.py")
+    kw = dict(vocab_size=300, speech_vocab_size=40, num_channels=8, text_shift_size=256, **SMALL)
+    ref = mod.RWKV7XYLM(mod.RWKV7XYConfig(**kw)).eval()
+    own = layouts.RWKV7XYLM(layouts.RWKV7XYConfig(**kw)).eval()
+    assert set(own.state_dict()) == set(ref.state_dict())
+    own.load_state_dict(ref.state_dict(), strict=True)
+    ids = torch.cat([torch.randint(0, 299, (2, 9, 1), generator=g), torch.randint(0, 39, (2, 9, 7), generator=g)], dim=2)
+    lab = torch.cat([torch.randint(0, 299, (2, 9, 1), generator=g), torch.randint(0, 39, (2, 9, 7), generator=g)], dim=2)
+    with torch.no_grad():
+        a = ref(input_ids=ids, attention_mask=torch.ones(2, 9, dtype=torch.long), labels=lab, return_dict=True)
+        b = own(input_ids=ids, attention_mask=torch.ones(2, 9, dtype=torch.long), labels=lab)
+    assert _same(b.loss, a.loss) and all(_same(x, y) for x, y in zip(b.logits, a.logits))
+    own.train()
+    c = own(input_ids=ids, attention_mask=torch.ones(2, 9, dtype=torch.long), labels=lab)       # chunked heads, no logits
+    assert c.logits == [] and _same(c.loss.detach(), a.loss, 1e-4)
+
+
+def test_xy_sample_loop_equals_the_reference_sample(stand_in_blocks):
+    """The 8-channel sampling loop (xy_llm.py:39-146) against the reference's `_sample` called directly (HF's generate()
+    of this image's transformers can no longer reach it): same seed -> same tokens on every channel, including the
+    reference's literal stopping rule (reference_termination=True)."""
+    from transformers.generation import GenerationConfig, LogitsProcessorList, StoppingCriteriaList
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper
+    from transformers.generation.stopping_criteria import MaxLengthCriteria
+    from rwkvtts_b200 import layouts
+    mod = _load("ref_xy_llm3", "model/llm/xy_llm.py")
+    torch.manual_seed(0)
+    kw = dict(vocab_size=300, speech_vocab_size=40, num_channels=8, text_shift_size=256, **SMALL)
+    ref = mod.RWKV7XYLM(mod.RWKV7XYConfig(**kw)).eval()
+    own = layouts.RWKV7XYLM(layouts.RWKV7XYConfig(**kw)).eval()
+    own.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(11)
+    ids = torch.cat([torch.randint(0, 255, (2, 5, 1), generator=g), torch.randint(0, 39, (2, 5, 7), generator=g)], dim=2)
+    procs = LogitsProcessorList([TemperatureLogitsWarper(0.8), TopKLogitsWarper(10)])
+    crit = StoppingCriteriaList([MaxLengthCriteria(max_length=12)])
+    gc = GenerationConfig(eos_token_id=299, output_scores=False, return_dict_in_generate=False)
+    # the reference's loop re-feeds the whole sequence through prepare_inputs_for_generation; give it the plain one
+    ref.prepare_inputs_for_generation = lambda input_ids, **kw_: {"input_ids": input_ids}
+    ref._update_model_kwargs_for_generation = lambda outputs, model_kwargs, **kw_: model_kwargs
+    torch.manual_seed(123)
+    want = ref._sample(ids, procs, crit, gc, False, None)
+    torch.manual_seed(123)
+    got = own.sample(ids, max_length=12, eos_token_id=299, temperature=0.8, top_k=10, reference_termination=True)
+    assert got.shape == want.shape and torch.equal(got, want), (got[:, 5:], want[:, 5:])
+    assert got.shape[1] == 6                       # the literal rule: every row stops after its first step
+    assert bool(own.is_audio_token(got[:, 5, 0]).all())
+    # the intended rule runs to max_length here (channel 0 is constrained to audio tokens, so no flush ever starts)
+    torch.manual_seed(123)
+    long = own.sample(ids, max_length=12, eos_token_id=299, temperature=0.8, top_k=10)
+    assert long.shape[1] == 12 and torch.equal(long[:, :6], want)
