@@ -106,7 +106,7 @@ def random_init_0p4b():
     return model.to(torch.bfloat16)
 
 
-def build_engine(world):
+def build_engine(world, fused_p2p=False):
     """Model, optimizer and engine as the reference's script builds them: configure_optimizer
     (train_spark_rwkv7speech.py:178-197: one group, FusedAdam betas (0.9, 0.95), eps 1e-18, adam_w_mode),
     ds_config with bf16 + ZeRO stage 2 + reduce_scatter (:483-516), deepspeed.initialize (:566-572)."""
@@ -120,7 +120,7 @@ def build_engine(world):
                     amsgrad=False, weight_decay=0.01)
     cfg = {"distributed_backend": "nccl", "train_batch_size": B * world, "bf16": {"enabled": True},
            "zero_optimization": {"stage": 2, "allgather_partitions": True, "reduce_scatter": True,
-                                 "overlap_comm": True, "contiguous_gradients": True},
+                                 "overlap_comm": True, "contiguous_gradients": True, "fused_p2p": bool(fused_p2p)},
            "gradient_checkpointing": False, "dump_state": False}
     engine, _, _, _ = deepspeed.initialize(model=model, config=cfg, model_parameters=model.parameters(), optimizer=opt)
     return engine
@@ -149,7 +149,7 @@ def train_arm(args, rank, local_rank, world):
     from rwkvtts_b200.spark import synthetic_spark_batch
     lib = R._lib.lib()
     log("building the 0.4B model and the engine")
-    engine = build_engine(world)
+    engine = build_engine(world, fused_p2p=args.zero_p2p)
     n_params = engine.numel
     host_batch = synthetic_spark_batch(B, T, seed=42 + rank)
     dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
@@ -235,11 +235,12 @@ def train_arm(args, rank, local_rank, world):
     # ---- the exchange in isolation (collective's share of the step) -----------------------------------------------
     comm = engine.profile_comm() if world > 1 else None
     if comm is not None:
-        comm["share_of_step_if_not_overlapped"] = (comm["reduce_scatter_ms"] + comm["all_gather_ms"]) / ms_per_step
+        comm["share_of_step_if_not_overlapped"] = ((comm.get("fused_exchange_and_adam_ms") or 0.0) + comm["reduce_scatter_ms"]
+                                                   + comm["all_gather_ms"]) / ms_per_step
         comm["nccl_nranks"] = dist.get_world_size()
-        comm["what"] = ("per step and rank: reduce-scatter(AVG) of %d buckets of bf16 gradients, one 2-float all-reduce, "
-                        "all-gather of the updated bf16 parameters; timed back to back without the step around them"
-                        % comm["buckets"])
+        comm["what"] = comm.get("mode") or (
+            "per step and rank: reduce-scatter(AVG) of %d buckets of bf16 gradients, one 2-float all-reduce, all-gather of "
+            "the updated bf16 parameters; timed back to back without the step around them" % comm["buckets"])
     if world > 1:
         dist.barrier(device_ids=[local_rank])
     if rank != 0:
@@ -610,6 +611,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--leg", default=None, choices=sorted(LEG_FN))
     ap.add_argument("--no-legs", action="store_true")
+    ap.add_argument("--zero-p2p", action="store_true",
+                    help="N > 1: fuse reduce-scatter + Adam + all-gather into one kernel over NVLink symmetric memory "
+                         "(NVSwitch multicast when available) instead of the overlapped NCCL exchange")
     ap.add_argument("--skip", default=set(), type=lambda s: set(x for x in s.split(",") if x))
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

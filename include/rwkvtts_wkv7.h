@@ -175,6 +175,21 @@ RWKVTTS_API int rwkvtts_adam_multi(float *master, float *exp_avg, float *exp_avg
                        const int *seg_group, int nseg, const float *group_hp, int ngroups, float beta1, float beta2,
                        float eps, int adamw_mode, const float *stat, float clip, unsigned long long *skipped,
                        void *stream);
+/* The whole exchange of the ZeRO-2 step fused with the update, over NVLink / NVSwitch peer memory: for the rank's slice
+ * [flat_off, flat_off + n) of the flat parameter space, reduce-scatter(AVG) of the W ranks' bf16 gradients -> Adam ->
+ * all-gather of the new bf16 parameters, in one kernel and without staging buffers.  grad_ptrs / param_ptrs: HOST
+ * arrays of `world` device pointers, every rank's flat gradient / parameter buffer mapped into this process (symmetric
+ * memory; the reference gets the same exchange from DeepSpeed ZeRO-2's NCCL reduce_scatter + allgather_partitions,
+ * train_spark_rwkv7speech.py:483-516).  mc_grad / mc_param: multicast addresses of the same buffers, or NULL: with them
+ * the reduction happens IN the NVSwitch (multimem.ld_reduce) and the parameter store is broadcast by it (multimem.st).
+ * master / exp_avg / exp_avg_sq, seg_end / seg_group, group_hp as rwkvtts_adam_multi (indices relative to the slice);
+ * stat[1] > 0 skips the step; *norm_sq (device, may be NULL) accumulates the squared norm of the averaged gradient.
+ * The caller orders the launch between two cross-rank barriers.  n, flat_off multiples of 8; world <= 8. */
+RWKVTTS_API int rwkvtts_adam_p2p(float *master, float *exp_avg, float *exp_avg_sq, const void *const *grad_ptrs,
+                     void *const *param_ptrs, const void *mc_grad, void *mc_param, int world, long long flat_off,
+                     long long n, const long long *seg_end, const int *seg_group, int nseg, const float *group_hp,
+                     int ngroups, float beta1, float beta2, float eps, int adamw_mode, const float *stat, float *norm_sq,
+                     unsigned long long *skipped, void *stream);
 /* stat[0] += sum of squares of grad[0..n), stat[1] += 1 if any element is non-finite (device float[2],
  * zeroed by the caller; the engine all-reduces it across ranks before rwkvtts_adam_multi). */
 RWKVTTS_API int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, void *stream);

@@ -57,6 +57,9 @@ SYMBOLS = {
     "rwkvtts_embed_rows": (_i, [ctypes.POINTER(_vp), _i, _vp, ctypes.c_longlong, _i, _vp, _vp]),
     "rwkvtts_ce_forward_backward": (_i, [_vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, ctypes.c_longlong, ctypes.c_float,
                                          _fp, _fp, _vp]),
+    "rwkvtts_adam_p2p": (_i, [_fp, _fp, _fp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, ctypes.c_longlong,
+                              ctypes.c_longlong, _vp, _vp, _i, ctypes.POINTER(ctypes.c_float), _i] + [ctypes.c_float] * 3
+                         + [_i, _fp, _fp, _vp, _vp]),
     "rwkvtts_grad_stat": (_i, [_vp, _i, ctypes.c_longlong, _fp, _vp]),
 }
 

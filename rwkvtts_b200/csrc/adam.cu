@@ -128,6 +128,123 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(float *__restrict__ mas
     }
 }
 
+// ---- the same update fused with BOTH collectives of the ZeRO step over NVLink / NVSwitch --------------------------------
+// reduce-scatter(AVG) of the gradients -> Adam on the rank's slice -> all-gather of the updated parameters, in ONE kernel
+// and without staging buffers: every rank's flat gradient / parameter buffer lives in symmetric memory (same layout on
+// every GPU, mapped into every peer), so for element i of its slice a rank
+//   kMulticast: issues ONE multimem.ld_reduce on the multicast address of the gradient buffers -- the NVSwitch adds the
+//               W ranks' values in flight (fp32 accumulation) and returns the sum -- and ONE multimem.st of the new bf16
+//               parameter, which the switch delivers to all W copies (NVLS: 1x instead of (W-1)x link traffic each way);
+//   otherwise : loads the W peers' gradients through their mapped pointers (16-byte loads, all in flight together) and
+//               stores the parameter into each peer's buffer.
+// The caller brackets the launches with symmetric-memory barriers (all gradients final before, all parameter writes
+// landed after) -- rwkvtts_b200/engine.py.  bf16 gradients and parameters only.  Same segment walk as adam_multi_kernel.
+constexpr int kMaxPeers = 8;
+struct PeerPtrs { const bf16 *grad[kMaxPeers]; bf16 *param[kMaxPeers]; };
+
+__device__ __forceinline__ uint4 ld_peer_v4(const void *p) {       // never cached: the peer rewrites it every step
+    uint4 r;
+    asm volatile("ld.global.cv.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_ld_reduce_bf16x8(const void *mc, float (&x)[8]) {
+    uint32_t r[4];
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(mc) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; i++) { x[2 * i] = bf16_lo(r[i]); x[2 * i + 1] = bf16_hi(r[i]); }
+}
+__device__ __forceinline__ void mc_st_bf16x8(void *mc, const float (&x)[8]) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};"
+                 :: "l"(mc), "r"(pack2(x[0], x[1])), "r"(pack2(x[2], x[3])), "r"(pack2(x[4], x[5])), "r"(pack2(x[6], x[7]))
+                 : "memory");
+}
+
+constexpr int kTileP = 8192;         // elements per CTA tile: 8 per thread and iteration
+template <bool kMulticast>
+__global__ void __launch_bounds__(256) adam_p2p_kernel(float *__restrict__ master, float *__restrict__ m,
+                                                       float *__restrict__ v, PeerPtrs peers, const bf16 *mc_grad,
+                                                       bf16 *mc_param, int world, long long flat_off, long long n,
+                                                       const long long *__restrict__ seg_end,
+                                                       const int *__restrict__ seg_group, int nseg, AdamGroups hps,
+                                                       float b1, float b2, float eps, int adamw,
+                                                       const float *__restrict__ stat, float *__restrict__ norm_sq,
+                                                       unsigned long long *__restrict__ skipped) {
+    if (stat != nullptr && stat[1] > 0.f) {              // a non-finite gradient on some rank: skip the step everywhere
+        if (skipped != nullptr && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(skipped, 1ull);
+        return;
+    }
+    const float inv_w = 1.f / (float)world;
+    float ss = 0.f;
+    const long long ntiles = (n + kTileP - 1) / kTileP;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long t0 = tile * kTileP, t1 = min(n, t0 + (long long)kTileP);
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (seg_end[mid] > t0) hi = mid; else lo = mid + 1;
+        }
+        int seg = lo;
+        for (long long i = t0 + 8 * threadIdx.x; i < t1; i += 8 * 256) {       // n is a multiple of 8 (engine padding)
+            while (seg < nseg - 1 && seg_end[seg] <= i) seg++;
+            const AdamHp hp = hps.g[seg_group[seg]];
+            float g[8];
+            if (kMulticast) {
+                mc_ld_reduce_bf16x8(mc_grad + flat_off + i, g);
+            } else {
+                uint4 raw[kMaxPeers];
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; r++)
+                    if (r < world) raw[r] = ld_peer_v4(peers.grad[r] + flat_off + i);
+#pragma unroll
+                for (int e = 0; e < 8; e++) g[e] = 0.f;
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; r++)
+                    if (r < world) {
+                        float f[8];
+                        unpack8(raw[r], f);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) g[e] += f[e];
+                    }
+            }
+            float w[8], mm[8], vv[8];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float a4[4], b4[4], c4[4];
+                Vec4<float>::load(master + i + 4 * h, a4); Vec4<float>::load(m + i + 4 * h, b4); Vec4<float>::load(v + i + 4 * h, c4);
+#pragma unroll
+                for (int e = 0; e < 4; e++) { w[4 * h + e] = a4[e]; mm[4 * h + e] = b4[e]; vv[4 * h + e] = c4[e]; }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float ge = g[e] * inv_w;
+                ss = fmaf(ge, ge, ss);
+                adam_elem(w[e], mm[e], vv[e], ge, hp, b1, b2, eps, adamw);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float a4[4] = {w[4 * h], w[4 * h + 1], w[4 * h + 2], w[4 * h + 3]};
+                const float b4[4] = {mm[4 * h], mm[4 * h + 1], mm[4 * h + 2], mm[4 * h + 3]};
+                const float c4[4] = {vv[4 * h], vv[4 * h + 1], vv[4 * h + 2], vv[4 * h + 3]};
+                Vec4<float>::store(master + i + 4 * h, a4); Vec4<float>::store(m + i + 4 * h, b4); Vec4<float>::store(v + i + 4 * h, c4);
+            }
+            if (kMulticast) {
+                mc_st_bf16x8(mc_param + flat_off + i, w);
+            } else {
+                const uint4 out = make_uint4(pack2(w[0], w[1]), pack2(w[2], w[3]), pack2(w[4], w[5]), pack2(w[6], w[7]));
+#pragma unroll
+                for (int r = 0; r < kMaxPeers; r++)
+                    if (r < world) *reinterpret_cast<uint4 *>(peers.param[r] + flat_off + i) = out;
+            }
+        }
+    }
+    if (norm_sq != nullptr) {                            // squared norm of the averaged gradient of this slice
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(norm_sq, ss);
+    }
+}
+
 // {sum of squares, any non-finite} of a gradient range, accumulated into stat[0..1] (fp32 atomics; the caller zeroes
 // stat first).  One pass over the gradients: 2 bytes per element.
 template <typename G>
@@ -224,6 +341,31 @@ cudaError_t launch_adam_multi(float *master, float *m, float *v, const void *gra
     }
     return param_is_bf16 ? launch_multi<float, bf16>(master, m, v, grad, param, n, seg_end, seg_group, nseg, hps, b1, b2, eps, adamw, stat, clip, skipped, st)
                          : launch_multi<float, float>(master, m, v, grad, param, n, seg_end, seg_group, nseg, hps, b1, b2, eps, adamw, stat, clip, skipped, st);
+}
+
+cudaError_t launch_adam_p2p(float *master, float *m, float *v, const void *const *grad_ptrs, void *const *param_ptrs,
+                            const void *mc_grad, void *mc_param, int world, long long flat_off, long long n,
+                            const long long *seg_end, const int *seg_group, int nseg, const float *group_hp, int ngroups,
+                            float b1, float b2, float eps, int adamw, const float *stat, float *norm_sq,
+                            unsigned long long *skipped, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    AdamGroups hps{};
+    for (int i = 0; i < ngroups && i < kMaxGroups; i++)
+        hps.g[i] = AdamHp{group_hp[4 * i], group_hp[4 * i + 1], group_hp[4 * i + 2], group_hp[4 * i + 3]};
+    PeerPtrs pp{};
+    for (int r = 0; r < world && r < kMaxPeers; r++) {
+        pp.grad[r] = static_cast<const bf16 *>(grad_ptrs[r]);
+        pp.param[r] = static_cast<bf16 *>(param_ptrs[r]);
+    }
+    count_launch();
+    const unsigned grid = grid_for(n, kTileP);
+    if (mc_grad != nullptr && mc_param != nullptr)
+        adam_p2p_kernel<true><<<grid, 256, 0, st>>>(master, m, v, pp, (const bf16 *)mc_grad, (bf16 *)mc_param, world, flat_off,
+                                                    n, seg_end, seg_group, nseg, hps, b1, b2, eps, adamw, stat, norm_sq, skipped);
+    else
+        adam_p2p_kernel<false><<<grid, 256, 0, st>>>(master, m, v, pp, nullptr, nullptr, world, flat_off, n, seg_end,
+                                                     seg_group, nseg, hps, b1, b2, eps, adamw, stat, norm_sq, skipped);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, cudaStream_t st) {

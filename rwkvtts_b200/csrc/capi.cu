@@ -74,6 +74,11 @@ cudaError_t launch_adam_multi(float *master, float *m, float *v, const void *gra
                               const float *group_hp, int ngroups, float b1, float b2, float eps, int adamw,
                               const float *stat, float clip, unsigned long long *skipped, cudaStream_t st);
 cudaError_t launch_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, cudaStream_t st);
+cudaError_t launch_adam_p2p(float *master, float *m, float *v, const void *const *grad_ptrs, void *const *param_ptrs,
+                            const void *mc_grad, void *mc_param, int world, long long flat_off, long long n,
+                            const long long *seg_end, const int *seg_group, int nseg, const float *group_hp, int ngroups,
+                            float b1, float b2, float eps, int adamw, const float *stat, float *norm_sq,
+                            unsigned long long *skipped, cudaStream_t st);
 cudaError_t launch_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows, int D,
                               void *out, cudaStream_t st);
 cudaError_t launch_ce_fwd_bwd(void *logits, long long rows, int V, long long ld, const long long *labels,
@@ -352,6 +357,25 @@ int rwkvtts_adam_multi(float *master, float *exp_avg, float *exp_avg_sq, const v
     return finish(rwkvtts::launch_adam_multi(master, exp_avg, exp_avg_sq, grad, grad_is_bf16, param, param_is_bf16, n,
                                              seg_end, seg_group, nseg, group_hp, ngroups, beta1, beta2, eps, adamw_mode,
                                              stat, clip, skipped, (cudaStream_t)stream));
+}
+
+int rwkvtts_adam_p2p(float *master, float *exp_avg, float *exp_avg_sq, const void *const *grad_ptrs, void *const *param_ptrs,
+                     const void *mc_grad, void *mc_param, int world, long long flat_off, long long n,
+                     const long long *seg_end, const int *seg_group, int nseg, const float *group_hp, int ngroups, float beta1,
+                     float beta2, float eps, int adamw_mode, const float *stat, float *norm_sq, unsigned long long *skipped,
+                     void *stream) {
+    if (n < 0 || n % 8 != 0 || flat_off < 0 || flat_off % 8 != 0 || nseg <= 0 || ngroups <= 0 || ngroups > 8 || world < 1 ||
+        world > 8)
+        return RWKVTTS_ERR_SHAPE;
+    if (n == 0) return RWKVTTS_OK;
+    if (grad_ptrs == nullptr || param_ptrs == nullptr || group_hp == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({master, exp_avg, exp_avg_sq, seg_end, seg_group})) return rc;
+    for (int r = 0; r < world; r++)
+        if (int rc = check_ptrs({grad_ptrs[r], param_ptrs[r]})) return rc;
+    if ((mc_grad == nullptr) != (mc_param == nullptr)) return RWKVTTS_ERR_NULL;
+    return finish(rwkvtts::launch_adam_p2p(master, exp_avg, exp_avg_sq, grad_ptrs, param_ptrs, mc_grad, mc_param, world,
+                                           flat_off, n, seg_end, seg_group, nseg, group_hp, ngroups, beta1, beta2, eps,
+                                           adamw_mode, stat, norm_sq, skipped, (cudaStream_t)stream));
 }
 
 int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long n, float *stat, void *stream) {

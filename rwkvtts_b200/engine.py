@@ -171,6 +171,16 @@ class Engine:
         self._on_gpu = self.device.type == "cuda"
         self._nccl = self.world_size > 1 and dist.get_backend() == "nccl"
         self._comm_stream = torch.cuda.Stream(device=self.device) if (self._on_gpu and self.world_size > 1) else None
+        # fused exchange over NVLink peer memory (csrc/adam.cu adam_p2p_kernel): one kernel per bucket slice does
+        # reduce-scatter(AVG) + Adam + all-gather on symmetric-memory buffers, in-switch reduction / broadcast when the
+        # fabric offers multicast.  Needs NCCL ranks on one node, bf16, no gradient clipping (the clip factor would need
+        # the reduced norm before the update).  zero_optimization.fused_p2p / RWKVTTS_ZERO_P2P=1 turn it on.
+        want = zo.get("fused_p2p", None)
+        env = os.environ.get("RWKVTTS_ZERO_P2P")
+        self._want_p2p = bool(self._nccl and self.gradient_clipping == 0 and bf16 and self.world_size <= 8
+                              and (env == "1" or (env is None and want)))
+        self._p2p = None
+        self.exchange_events = None
         self._build_flat_buffers()
         self._install_hooks()
 
@@ -213,8 +223,14 @@ class Engine:
                 self.buckets.append((bstart, off))
                 bstart = off
         self.numel, self.padded = sum(p.numel() for p in ordered), off
-        self.flat_param = torch.zeros(off, dtype=dtype, device=self.device)
-        self.flat_grad = torch.zeros(off, dtype=dtype, device=self.device)
+        if self._want_p2p:
+            self._p2p = self._symmetric_buffers(off, dtype)
+        if self._p2p is not None:
+            self.flat_param, self.flat_grad = self._p2p["param"], self._p2p["grad"]
+            self.flat_param.zero_(); self.flat_grad.zero_()
+        else:
+            self.flat_param = torch.zeros(off, dtype=dtype, device=self.device)
+            self.flat_grad = torch.zeros(off, dtype=dtype, device=self.device)
         for p, o in zip(ordered, self._poff):
             n = p.numel()
             self.flat_param[o:o + n].copy_(p.data.reshape(-1))
@@ -236,6 +252,7 @@ class Engine:
         self.grad_shard = torch.zeros(so, dtype=dtype, device=self.device) if W > 1 else None
         self._opt_step = [0] * len(groups)
         self._stat = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._norm2 = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._skipped = torch.zeros(1, dtype=torch.int64, device=self.device)
         # segment tables of the rank's slices: exclusive ends (relative to the slice start) and param group ids
         self._segs = []
@@ -251,6 +268,29 @@ class Engine:
             self._segs.append((torch.tensor(ends, dtype=torch.int64, device=self.device),
                                torch.tensor(gids, dtype=torch.int32, device=self.device), ends, gids))
 
+    def _symmetric_buffers(self, numel, dtype):
+        """Flat parameter and gradient buffers in symmetric memory, mapped into every rank of the node (and bound to a
+        multicast object when the NVSwitch offers it).  Returns None -- on every rank -- if any rank could not set it up."""
+        ok, res = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            bufs, hdls = {}, {}
+            for name in ("param", "grad"):
+                bufs[name] = symm.empty(numel, dtype=dtype, device=self.device)
+                hdls[name] = symm.rendezvous(bufs[name], dist.group.WORLD)
+            res = {"param": bufs["param"], "grad": bufs["grad"], "hp": hdls["param"], "hg": hdls["grad"],
+                   "param_ptrs": [int(x) for x in hdls["param"].buffer_ptrs], "grad_ptrs": [int(x) for x in hdls["grad"].buffer_ptrs],
+                   "mc_param": int(getattr(hdls["param"], "multicast_ptr", 0) or 0),
+                   "mc_grad": int(getattr(hdls["grad"], "multicast_ptr", 0) or 0)}
+            if os.environ.get("RWKVTTS_ZERO_MULTICAST") == "0":
+                res["mc_param"] = res["mc_grad"] = 0
+        except Exception as e:                           # no symmetric memory here: NCCL path
+            ok = 0
+            warnings.warn(f"symmetric memory unavailable ({e!r}); engine uses the NCCL exchange")
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return res if int(flag.item()) == 1 else None
+
     def _install_hooks(self):
         self._hook_handles = []
         self._pending = [0] * len(self.buckets)
@@ -260,7 +300,7 @@ class Engine:
         self._bucket_np = [0] * len(self.buckets)
         for b in self._pbucket:
             self._bucket_np[b] += 1
-        if not (self._nccl and self.overlap_comm):
+        if not (self._nccl and self.overlap_comm) or self._p2p is not None:
             return
         for p, b in zip(self._params, self._pbucket):
             def hook(param, b=b):
@@ -333,6 +373,8 @@ class Engine:
     @property
     def global_grad_norm(self) -> float:
         """Gradient norm of the last step (reads a device scalar: a host sync only when somebody asks)."""
+        if self._p2p is not None:
+            return float(self._norm2[0].sqrt())
         return float(self._stat[0].sqrt())
 
     @property
@@ -389,6 +431,8 @@ class Engine:
             return
         self._rebind_grads()
         W = self.world_size
+        if self._p2p is not None:
+            return self._step_p2p()
         if W > 1:
             self._reduce_gradients()
         # global squared gradient norm and non-finite count: one small all-reduce, consumed on the device
@@ -452,6 +496,52 @@ class Engine:
             self.optimizer._opt_called = True     # the update ran above (on the shard): torch's scheduler order check looks here
             self.lr_scheduler.step()
 
+    def _step_p2p(self):
+        """The optimizer step with the exchange fused into the update kernel (see __init__ / csrc/adam.cu)."""
+        P, L = self._p2p, _lib.lib()
+        W = self.world_size
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        # non-finite check on the LOCAL gradients (a non-finite value on any rank makes the sum non-finite): one pass over
+        # the local buffer + a 2-float all-reduce; the fused kernels read the flag on the device
+        self._stat.zero_()
+        self._norm2.zero_()
+        with torch.cuda.device(self.device):
+            _lib.check(L.rwkvtts_grad_stat(self.flat_grad.data_ptr(), 1, self.flat_grad.numel(), self._stat.data_ptr(), st),
+                       "rwkvtts_grad_stat")
+        dist.all_reduce(self._stat)
+        for gi in range(len(self._opt_step)):
+            self._opt_step[gi] += 1
+        hp = self._group_hp()
+        g0 = self.optimizer.param_groups[0]
+        b1, b2 = g0["betas"]
+        eps = float(g0["eps"])
+        hp_c = (ctypes.c_float * (4 * len(hp)))(*[x for h in hp for x in h])
+        gp = (ctypes.c_void_p * W)(*P["grad_ptrs"])
+        pp = (ctypes.c_void_p * W)(*P["param_ptrs"])
+        _invalidate_param_cache()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        P["hg"].barrier(channel=0)                       # every rank's gradients are final and visible
+        for b, (a, e) in enumerate(self._slice):
+            so, n = self._soff[b], e - a
+            ends, gids, _, _ = self._segs[b]
+            with torch.cuda.device(self.device):
+                rc = L.rwkvtts_adam_p2p(
+                    self.master[so:so + n].data_ptr(), self.exp_avg[so:so + n].data_ptr(), self.exp_avg_sq[so:so + n].data_ptr(),
+                    gp, pp, P["mc_grad"] or None, P["mc_param"] or None, W, a, n, ends.data_ptr(), gids.data_ptr(), ends.numel(),
+                    hp_c, len(hp), b1, b2, eps, self.optimizer.adam_w_mode, self._stat.data_ptr(), self._norm2.data_ptr(),
+                    self._skipped.data_ptr() if b == 0 else None, st)
+            _lib.check(rc, "rwkvtts_adam_p2p")
+        P["hp"].barrier(channel=0)                       # every rank's parameter writes have landed; gradients are free
+        ev1.record()
+        self.exchange_events = (ev0, ev1)
+        dist.all_reduce(self._norm2)                     # reporting only (global_grad_norm); nothing waits for it
+        self.flat_grad.zero_()
+        self.global_steps += 1
+        if self.lr_scheduler is not None:
+            self.optimizer._opt_called = True
+            self.lr_scheduler.step()
+
     def _cpu_adam(self, b, g, pslice, hp, b1, b2, eps):
         """Host-logic twin of rwkvtts_adam_multi (gloo / CPU tests): same segment walk, same skip and clipping rule."""
         norm = float(self._stat[0].sqrt())
@@ -488,6 +578,17 @@ class Engine:
         bench reports it next to the step time as the collective's share.  Leaves gradients zeroed."""
         if not self._nccl:
             self.comm_ms = {"reduce_scatter_ms": 0.0, "all_gather_ms": 0.0, "bytes_per_rank": 0}
+            return self.comm_ms
+        if self._p2p is not None:
+            ms = None
+            if self.exchange_events is not None:
+                torch.cuda.synchronize(self.device)
+                ms = self.exchange_events[0].elapsed_time(self.exchange_events[1])
+            self.comm_ms = {"fused_exchange_and_adam_ms": ms, "reduce_scatter_ms": 0.0, "all_gather_ms": 0.0,
+                            "bytes_per_rank": self.padded * self.flat_grad.element_size(), "buckets": len(self.buckets),
+                            "mode": "one kernel per slice: reduce-scatter + Adam + all-gather over symmetric memory ("
+                                    + ("NVSwitch multicast: multimem.ld_reduce / multimem.st" if self._p2p["mc_grad"] else
+                                       "peer loads / stores") + ")"}
             return self.comm_ms
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         rs = ag = 0.0

@@ -157,6 +157,10 @@ opt = FusedAdam(T._groups(m), lr=1e-2, betas=(T.B1, T.B2), eps=T.EPS)
 eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": True}, "zero_optimization": {"stage": 2}},
                                     model_parameters=m.parameters(), optimizer=opt)
 assert eng.world_size == world and eng._nccl and len(eng.buckets) >= 2
+mode = os.environ.get("TEST_ENGINE_MODE", "nccl")
+if mode != "nccl":
+    assert eng._p2p is not None, "symmetric memory was not set up"
+    assert bool(eng._p2p["mc_grad"]) == (mode == "p2p_multicast") or mode == "p2p", (mode, eng._p2p["mc_grad"])
 g = torch.Generator(device="cuda").manual_seed(1)
 x, y = torch.randn(32, 96, device="cuda", generator=g).bfloat16(), torch.randn(32, 8, device="cuda", generator=g).bfloat16()
 n = 32 // world
@@ -171,15 +175,24 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_ranks_over_nccl_match_single_process():
+@pytest.mark.parametrize("mode", ["nccl", "p2p", "p2p_unicast"])
+def test_two_ranks_over_nccl_match_single_process(mode):
+    """nccl: bucketed reduce-scatter overlapped with backward, Adam, all-gather.  p2p: the exchange fused into the update
+    kernel over symmetric memory (multicast / in-switch reduction when the fabric has it); p2p_unicast: the same kernel
+    with plain peer loads and stores."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, TEST_ENGINE_MODE=mode)
+    if mode != "nccl":
+        env["RWKVTTS_ZERO_P2P"] = "1"
+    if mode == "p2p_unicast":
+        env["RWKVTTS_ZERO_MULTICAST"] = "0"
     with tempfile.TemporaryDirectory() as d:
         script, out = os.path.join(d, "w.py"), os.path.join(d, "o.pt")
         open(script, "w").write(WORKER % {"root": ROOT})
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                             "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), script, out],
-                           capture_output=True, text=True, timeout=300)
+                           capture_output=True, text=True, timeout=300, env=env)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
         got = torch.load(out)
     # the same 4 steps on one process with the full batch, bf16 model / fp32 master weights like the engine
@@ -195,4 +208,7 @@ def test_two_ranks_over_nccl_match_single_process():
         eng.backward(torch.nn.functional.mse_loss(eng(x).float(), y.float())); eng.step()
     for a, b in zip(got["params"], eng.parameters()):
         assert torch.allclose(a, b.detach().float().cpu(), atol=2e-2, rtol=2e-2), (a - b.detach().float().cpu()).abs().max()
-    assert got["comm"]["reduce_scatter_ms"] > 0 and got["comm"]["all_gather_ms"] > 0
+    if mode == "nccl":
+        assert got["comm"]["reduce_scatter_ms"] > 0 and got["comm"]["all_gather_ms"] > 0
+    else:
+        assert got["comm"]["fused_exchange_and_adam_ms"] > 0
