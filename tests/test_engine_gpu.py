@@ -212,3 +212,61 @@ def test_two_ranks_over_nccl_match_single_process(mode):
         assert got["comm"]["reduce_scatter_ms"] > 0 and got["comm"]["all_gather_ms"] > 0
     else:
         assert got["comm"]["fused_exchange_and_adam_ms"] > 0
+
+
+SEQPAR_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+import rwkvtts_b200 as R
+from rwkvtts_b200 import seqpar
+from rwkvtts_b200.synth import make_inputs
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+B, T, H = 2, 256, 4
+x = make_inputs(B, T, H, seed=3)
+tl = T // world
+sl = {n: t[:, rank * tl:(rank + 1) * tl].contiguous().cuda() for n, t in x.items()}
+res = {}
+for hg in (1, 2):
+    leaves = [sl[n].clone().requires_grad_(True) for n in "wqkvab"]
+    y = seqpar.wkv7_sequence_parallel(*leaves, head_groups=hg)
+    y.backward(sl["dy"])
+    res[hg] = [y.detach().cpu()] + [l.grad.cpu() for l in leaves]
+prev = seqpar.shift_boundary(sl["v"][:, -1].reshape(B, -1).float().requires_grad_(True))
+res["prev"] = prev.detach().cpu()
+torch.save(res, sys.argv[1] + f".{rank}")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_sequence_split_across_two_gpus_equals_one_gpu():
+    """rwkvtts_b200.seqpar: T cut across 2 ranks, the recurrent state (and its gradient) handed rank to rank -- y and all
+    six gradients equal the single-GPU run of the whole sequence."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import rwkvtts_b200 as R
+    from rwkvtts_b200.synth import make_inputs
+    with tempfile.TemporaryDirectory() as d:
+        script, out = os.path.join(d, "w.py"), os.path.join(d, "o.pt")
+        open(script, "w").write(SEQPAR_WORKER % {"root": ROOT})
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), script, out],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        parts = [torch.load(out + f".{k}") for k in range(2)]
+    B, T, H = 2, 256, 4
+    x = make_inputs(B, T, H, seed=3)
+    dd = {n: t.cuda() for n, t in x.items()}
+    leaves = [dd[n].clone().requires_grad_(True) for n in "wqkvab"]
+    y = R.WindBackstepping.apply(*leaves)
+    y.backward(dd["dy"])
+    want = [y.detach().cpu()] + [l.grad.cpu() for l in leaves]
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    for hg in (1, 2):
+        for i, name in enumerate(["y", "dw", "dq", "dk", "dv", "da", "db"]):
+            got = torch.cat([parts[0][hg][i], parts[1][hg][i]], dim=1)
+            assert rel(got, want[i]) < 6e-3, (hg, name, rel(got, want[i]))      # two bf16 roundings of equal-precision paths
+    assert float(parts[0]["prev"].abs().sum()) == 0.0
+    assert torch.equal(parts[1]["prev"], x["v"][:, T // 2 - 1].reshape(B, -1).float())
