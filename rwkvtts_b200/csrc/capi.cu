@@ -15,7 +15,7 @@ namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
 
 // ---- watchdog record (see tc05.cuh) -------------------------------------------------------------------------
-constexpr int kWdEntries = 24, kWdWords = 8 + 4 * kWdEntries;      // tc05.cuh: kWatchdogEntries / kWatchdogWords
+constexpr int kWdEntries = 32, kWdWords = 8 + kWdEntries;      // tc05.cuh: kWatchdogEntries / kWatchdogWords
 static unsigned long long *g_wd_host = nullptr;
 static std::once_flag g_wd_once;
 unsigned long long *watchdog_record() {
@@ -201,21 +201,16 @@ int rwkvtts_watchdog_report(char *buf, size_t n) {
         return 0;
     }
     if (buf != nullptr && n > 0) {
-        size_t off = 0;
-        int shown = 0;
-        off += (size_t)snprintf(buf + off, n - off, "rwkvtts watchdog: %llu stuck warp(s) recorded:", r[1]);
+        size_t off = (size_t)snprintf(buf, n, "rwkvtts watchdog: hand-offs that never arrived (one waiter per barrier):");
         for (int i = 0; i < rwkvtts::kWdEntries && off + 1 < n; i++) {
-            const unsigned long long *e = r + 8 + 4 * i;
-            if ((e[0] >> 32) == 0) continue;
-            const unsigned kid = (unsigned)(e[0] & 0xffffffffu);
-            off += (size_t)snprintf(buf + off, n - off,
-                                    "%s %s: %s (smem +%u) parity %u, block %u warp %u, %.2f Gcycles;", shown ? "" : "",
+            const unsigned long long e = r[8 + i];
+            if ((e >> 63) == 0) continue;
+            const unsigned kid = (unsigned)((e >> 60) & 7u), smem_off = (unsigned)(e & 0xffffffu);
+            off += (size_t)snprintf(buf + off, n - off, " %s: %s (smem +%u) parity %u, block %u warp %u;",
                                     kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : "?",
-                                    rwkvtts::watchdog_barrier_name(kid, (unsigned)(e[1] >> 32)), (unsigned)(e[1] >> 32),
-                                    (unsigned)(e[1] & 0xffffffffu), (unsigned)(e[2] >> 32),
-                                    (unsigned)(e[2] & 0xffffffffu) >> 5, (double)e[3] * 2e-9);
+                                    rwkvtts::watchdog_barrier_name(kid, smem_off), smem_off, (unsigned)((e >> 59) & 1u),
+                                    (unsigned)((e >> 24) & 0xffffffu), (unsigned)((e >> 48) & 63u));
             if (off >= n) { off = n - 1; break; }
-            shown++;
         }
         buf[off < n ? off : n - 1] = 0;
     }

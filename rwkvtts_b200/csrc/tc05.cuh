@@ -156,46 +156,39 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 constexpr unsigned long long kWatchdogMagic = 0x57444f4752574b56ull;   // "WDOGRWKV"
 static __device__ unsigned long long *g_wd_rec = nullptr;              // one copy per translation unit
 static __device__ unsigned int g_wd_kernel = 0;
-// record layout (u64 words): [0] magic once any entry exists, [1] number of entries claimed, entries of 4 words from
-// word 8: {kernel id | valid << 32, (barrier offset << 32) | parity, (block << 32) | thread, cycles waited / 2}
-constexpr int kWatchdogEntries = 24, kWatchdogWords = 8 + 4 * kWatchdogEntries;
-static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity, unsigned long long waited) {
-    extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
-    volatile unsigned long long *r = g_wd_rec;
-    if (r != nullptr) {
-        // every stuck warp (one lane each) appends what it was waiting for: a deadlock is a cycle of waits and the
-        // first warp to run out of patience is usually a bystander (first version reported only that one)
-        const unsigned long long idx = atomicAdd_system(g_wd_rec + 1, 1ull);
-        if (idx < (unsigned long long)kWatchdogEntries) {
-            volatile unsigned long long *e = r + 8 + 4 * idx;
-            e[1] = ((unsigned long long)(bar_addr - smem_u32(wd_dyn_smem)) << 32) | parity;
-            e[2] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
-            e[3] = waited;
-            __threadfence_system();
-            e[0] = (unsigned long long)g_wd_kernel | (1ull << 32);          // valid: written last
-            r[0] = kWatchdogMagic;
-            __threadfence_system();
-        }
-        // nobody traps at once: a trap aborts the whole grid, stores in flight included (first version: the record came
-        // back with one field written), and the other stuck warps time out within a few ms of this one
-        const long long t0 = clock64();
-        while (clock64() - t0 < 100000000ll) {}
-    }
-    __trap();
-}
+// record layout (u64 words): [0] magic once any entry exists, entries from word 8: ONE packed word per distinct barrier
+// (barriers are consecutive 8-byte words of the kernel's shared-memory struct, so offset / 8 spreads them over the
+// entries; thousands of warps are stuck at once and a deadlock is a cycle of waits -- the record keeps one waiter of
+// every barrier somebody is stuck on):  valid(1) | kernel(3) | parity(1) | warp(6) | block(24) | smem offset(24)
+constexpr int kWatchdogEntries = 32, kWatchdogWords = 8 + kWatchdogEntries;
+// Everything inline and call-free: a call in these kernels' hot loops costs spills at every call site (measured: the
+// forward lost 40 % to local-memory traffic with an out-of-line report function), so the report is one packed store.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     // hot path = the unbounded loop's first two polls: try_wait suspends the thread in hardware until the phase
-    // completes or its 10 ms hint expires, so a third poll only happens when something is already badly late.  The
-    // bound is counted on the SM's own cycle counter (reading %globaltimer costs ~1 us: taken on every blocking wait it
-    // slowed the forward kernel by 17 %, measured).
+    // completes or its 10 ms hint expires, so a third poll only happens when something is already badly late.  The bound
+    // is counted on the SM's own cycle counter in units of 2^20 cycles (reading %globaltimer costs ~1 us: taken on every
+    // blocking wait it slowed the forward kernel by 17 %, measured).
     if (mbar_try_wait(bar, parity)) return;
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    const uint32_t t0 = (uint32_t)(clock64() >> 20);
     while (!mbar_try_wait(bar, parity)) {
-        const long long dt = clock64() - t0;
-        if (dt > (long long)(RWKVTTS_WATCHDOG_NS) * 2) {
-            if ((threadIdx.x & 31) == 0 || __activemask() != 0xffffffffu) mbar_timeout(smem_u32(bar), parity, (unsigned long long)dt / 2);
-            else { const long long t1 = clock64(); while (clock64() - t1 < 400000000ll) {} __trap(); }
+        if ((uint32_t)(clock64() >> 20) - t0 > (uint32_t)((RWKVTTS_WATCHDOG_NS * 2) >> 20)) {
+            extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
+            unsigned long long *r = g_wd_rec;
+            if (r != nullptr) {
+                const uint32_t off = smem_u32(bar) - smem_u32(wd_dyn_smem);
+                r[8 + ((off >> 3) % kWatchdogEntries)] = (1ull << 63) | ((unsigned long long)g_wd_kernel << 60) |
+                                                         ((unsigned long long)(parity & 1u) << 59) |
+                                                         ((unsigned long long)(threadIdx.x >> 5) << 48) |
+                                                         ((unsigned long long)(blockIdx.x & 0xffffffu) << 24) | (off & 0xffffffu);
+                r[0] = kWatchdogMagic;
+                __threadfence_system();
+            }
+            // nobody traps at once: a trap aborts the grid, stores in flight included, and the other stuck warps
+            // run out of patience within a few ms of this one
+            const uint32_t t1 = (uint32_t)(clock64() >> 20);
+            while ((uint32_t)(clock64() >> 20) - t1 < 100u) {}
+            __trap();
         }
     }
 }

@@ -593,7 +593,7 @@ __device__ void ckpt_group(const Params &P, Smem &sm, int bh, size_t ck0, int nC
 constexpr int kMmaWarp = 20, kThreads = 32 * (kMmaWarp + 1), kThreadsTrain = kThreads + 128;
 
 template <bool kTrain, bool kVar>
-__global__ void __launch_bounds__(kThreadsTrain, 1) wkv7_tc_fwd_kernel(const Params P) {
+__global__ void __launch_bounds__(kTrain ? kThreadsTrain : kThreads, 1) wkv7_tc_fwd_kernel(const Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const SeqWork W = seq_work(P.T, P.H, kVar ? P.cu : nullptr, P.cbase);

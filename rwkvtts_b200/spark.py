@@ -41,7 +41,14 @@ class RWKV7ForSpeech(RWKV7ForCausalLM):
     def forward(self, input_ids=None, attention_mask=None, inputs_embeds=None, **kwargs):
         if self.training and inputs_embeds is not None:
             inputs_embeds = self.dropout(inputs_embeds)
-        return super().forward(input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds, **kwargs)
+        # spark_llm.py:137: `fuse_linear_and_cross_entropy = self.config.fuse_cross_entropy and self.training` -- while
+        # training the head and the loss are one op and no logits come back (:139-158)
+        cfg, prev = self.config, self.config.fuse_linear_cross_entropy
+        cfg.fuse_linear_cross_entropy = bool(prev or (cfg.fuse_cross_entropy and self.training))
+        try:
+            return super().forward(input_ids=input_ids, attention_mask=attention_mask, inputs_embeds=inputs_embeds, **kwargs)
+        finally:
+            cfg.fuse_linear_cross_entropy = prev
 
 
 def spark_0p4b_config(**over) -> RWKV7SpeechConfig:

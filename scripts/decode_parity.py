@@ -5,8 +5,8 @@ The reference loop (model/llm/rwkv_asr_cuda_whisper.py:694-717): forward_batch o
 `emb(next) -> forward_batch(states) -> sample_logits(top_k=1)`, where forward_batch is the eager ATen chain of
 RWKV_Tmix_x070 / RWKV_CMix_x070 / Block (:181-215, :285-326) around the reference's own stateful kernel
 RWKV7_BATCH_OP (rwkv7_state_fwd_fp16.cu:9-57).  Here that loop is rebuilt from the same pieces: this repo's
-restatement of those lines with every fused kernel switched off (core.FUSED = False: plain ATen, bf16 intermediates,
-as the reference) and the WKV op bound to the UNMODIFIED reference kernel compiled in oracle/_ref
+restatement of those lines with every fused kernel switched off and the reference's operation order (core.FUSED = False,
+core.EXACT = True: plain ATen, bf16 intermediates, pinned bit for bit to the reference classes on CPU) and the WKV op bound to the UNMODIFIED reference kernel compiled in oracle/_ref
 (libref_state_fwd.so).  It is driven teacher-forced with the ids the product path produced: at every step the
 reference's argmax must be the id the product path chose next -- if that holds for all steps, the free-running
 reference loop generates the identical sequence (induction), which is the north_star's criterion.
@@ -23,8 +23,10 @@ def reference_step_logits(model, prompt_ids, forced_ids, n_steps):
     from oracle import c_oracle as CO
     from rwkvfla.models.utils import Cache
     from rwkvtts_b200 import core, ops
-    old_fused, old_op = core.FUSED, ops.RWKV7_BATCH_OP
-    core.FUSED = False
+    old_fused, old_exact, old_op = core.FUSED, core.EXACT, ops.RWKV7_BATCH_OP
+    # FUSED off + EXACT on = the reference's eager chain operation for operation (tests/test_forward_batch_cpu.py pins
+    # that chain bit for bit to the reference's own classes); the recurrence itself is the reference kernel
+    core.FUSED, core.EXACT = False, True
     ops.RWKV7_BATCH_OP = lambda state, r, w, k, v, a, b: CO.ref_state_forward(state, r, w, k, v, a, b)
     try:
         with torch.no_grad():
@@ -37,7 +39,7 @@ def reference_step_logits(model, prompt_ids, forced_ids, n_steps):
                 cache = out.past_key_values
                 yield out.logits[:, -1].float()
     finally:
-        core.FUSED, ops.RWKV7_BATCH_OP = old_fused, old_op
+        core.FUSED, core.EXACT, ops.RWKV7_BATCH_OP = old_fused, old_exact, old_op
 
 
 def compare(model, prompt_ids, our_new_ids, n_steps):

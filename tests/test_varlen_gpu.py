@@ -39,6 +39,9 @@ def test_packed_forward_and_backward_equal_the_per_sequence_oracle(lens, H):
         rows = [("y", y[:, sl].detach().cpu(), y64), ("y_nograd", y_ng[:, sl].cpu(), y64)]
         rows += [("d" + n, leaf.grad[:, sl].cpu(), g) for n, leaf, g in zip(ORDER, leaves, g64)]
         for name, got, ref in rows:
+            if float(ref.double().norm()) < 1e-12:               # e.g. dw of a one-token sequence is exactly zero
+                assert float(got.double().norm()) < 1e-6, (name, l)
+                continue
             exc, err, floor = O.excess_rel_l2(got, ref)
             # short sequences: a handful of elements, the bf16 floor estimate is noisy -> absolute bar next to the excess
             assert exc <= 1e-3 or err <= 4e-3, f"{name} len={l}: excess {exc:.3e} (err {err:.3e}, floor {floor:.3e})"
@@ -72,7 +75,7 @@ def test_shift_mix_restarts_at_sequence_boundaries():
     tot = sum(lens)
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(1, tot, C, device="cuda", generator=g).bfloat16().requires_grad_(True)
-    mixes = [(torch.rand(C, device="cuda", generator=g)).bfloat16().requires_grad_(True) for _ in range(6)]
+    mixes = [torch.rand(C, device="cuda", generator=g).requires_grad_(True) for _ in range(6)]     # fp32: exact accumulation
     dout = [torch.randn(1, tot, C, device="cuda", generator=g).bfloat16() for _ in range(6)]
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device="cuda")
     plan = ops.VarlenPlan(cu, tot)
@@ -94,7 +97,7 @@ def test_shift_mix_restarts_at_sequence_boundaries():
         assert torch.equal(got[0][i], torch.cat(ref_out[i], dim=1)), i
     assert torch.equal(got[1], x.grad)
     for a, m in zip(got[2], mixes):
-        assert torch.allclose(a.float(), m.grad.float(), rtol=2e-2, atol=2e-2)
+        assert torch.allclose(a.float(), m.grad.float(), rtol=1e-4, atol=1e-3)
 
 
 def test_packed_model_forward_backward_equals_per_sample_runs():
