@@ -11,7 +11,7 @@ Variants (test infrastructure, built by `--variants` / `build_variants()`):
   librwkvtts_wkv7_delay.so    production protocol + an injected stall of group C2 in the backward
   librwkvtts_wkv7_oldbar.so   round-1 single `out_ready` barrier + the same stall (shows the hazard the
                               per-parity barriers close; scripts/stress_wkv7.py, tests/test_stress_gpu.py)
-Both use a 1 s watchdog.  Select a library with the environment variable RWKVTTS_LIB (rwkvtts_b200/_lib.py).
+Select a library with the environment variable RWKVTTS_LIB (rwkvtts_b200/_lib.py).
 """
 from __future__ import annotations
 
@@ -33,8 +33,8 @@ FILE_FLAGS = {"wkv7_step_exact.cu": ["--use_fast_math"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 VARIANTS = {
-    "delay": ["-DRWKVTTS_BWD_DELAY_C2", "-DRWKVTTS_WATCHDOG_NS=1000000000ull"],
-    "oldbar": ["-DRWKVTTS_BWD_SINGLE_OUT_READY", "-DRWKVTTS_BWD_DELAY_C2", "-DRWKVTTS_WATCHDOG_NS=1000000000ull"],
+    "delay": ["-DRWKVTTS_BWD_DELAY_C2"],
+    "oldbar": ["-DRWKVTTS_BWD_SINGLE_OUT_READY", "-DRWKVTTS_BWD_DELAY_C2"],
 }
 
 

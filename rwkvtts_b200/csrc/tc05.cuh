@@ -146,13 +146,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 
 // ---- watchdog ------------------------------------------------------------------------------------
 // Every mbarrier wait of the chunked kernels is bounded: a hand-off that has not arrived after
-// RWKVTTS_WATCHDOG_NS (default 4 s at a nominal 2 GHz SM clock; a whole launch takes < 2 ms) writes one record
+// 2.2 - 4.4 s (two ticks of the upper word of the SM cycle counter; a whole launch takes < 2 ms) writes one record
 //   {kernel id, barrier offset in dynamic shared memory, parity, block, thread, time waited}   (one per stuck warp)
 // to a pinned host buffer (capi.cu owns it; rwkvtts_watchdog_report() formats it) and traps, so a
 // protocol error surfaces as a CUDA error with a diagnosis instead of a device that spins forever.
-#ifndef RWKVTTS_WATCHDOG_NS
-#define RWKVTTS_WATCHDOG_NS 4000000000ull
-#endif
 constexpr unsigned long long kWatchdogMagic = 0x57444f4752574b56ull;   // "WDOGRWKV"
 static __device__ unsigned long long *g_wd_rec = nullptr;              // one copy per translation unit
 static __device__ unsigned int g_wd_kernel = 0;
@@ -161,35 +158,44 @@ static __device__ unsigned int g_wd_kernel = 0;
 // entries; thousands of warps are stuck at once and a deadlock is a cycle of waits -- the record keeps one waiter of
 // every barrier somebody is stuck on):  valid(1) | kernel(3) | parity(1) | warp(6) | block(24) | smem offset(24)
 constexpr int kWatchdogEntries = 32, kWatchdogWords = 8 + kWatchdogEntries;
-// Everything inline and call-free: a call in these kernels' hot loops costs spills at every call site (measured: the
-// forward lost 40 % to local-memory traffic with an out-of-line report function), so the report is one packed store.
+// The report lives in ONE out-of-line function per translation unit that never returns: a call that does not come back
+// needs no register saved around it (an ordinary out-of-line report function cost the forward 40 % in local-memory
+// traffic at its ~40 call sites, and the fully inlined report 21-24 % more code -- both measured), so a wait site is
+// two polls, one read of the upper clock word and a compare.
+[[noreturn]] static __device__ __noinline__ void mbar_die(uint32_t bar_addr, uint32_t parity) {
+    extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
+    unsigned long long *r = g_wd_rec;
+    if (r != nullptr) {
+        const uint32_t off = bar_addr - smem_u32(wd_dyn_smem);
+        r[8 + ((off >> 3) % kWatchdogEntries)] = (1ull << 63) | ((unsigned long long)g_wd_kernel << 60) |
+                                                 ((unsigned long long)(parity & 1u) << 59) |
+                                                 ((unsigned long long)(threadIdx.x >> 5) << 48) |
+                                                 ((unsigned long long)(blockIdx.x & 0xffffffu) << 24) | (off & 0xffffffu);
+        r[0] = kWatchdogMagic;
+        __threadfence_system();
+    }
+    // nobody traps at once: a trap aborts the grid, stores in flight included, and the other stuck warps run out of
+    // patience within a few ms of this one
+    const long long t1 = clock64();
+    while (clock64() - t1 < 100000000ll) {}
+    __trap();
+    for (;;) {}
+}
+__device__ __forceinline__ uint32_t clock_hi() {        // upper word of the SM cycle counter: one tick = 2^32 cycles ~ 2.2 s
+    uint32_t t;
+    asm volatile("mov.u32 %0, %%clock_hi;" : "=r"(t));
+    return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     // hot path = the unbounded loop's first two polls: try_wait suspends the thread in hardware until the phase
-    // completes or its 10 ms hint expires, so a third poll only happens when something is already badly late.  The bound
-    // is counted on the SM's own cycle counter in units of 2^20 cycles (reading %globaltimer costs ~1 us: taken on every
+    // completes or its 10 ms hint expires, so a third poll only happens when something is already badly late.  Bound:
+    // two ticks of the upper clock word, i.e. 2.2 - 4.4 s (reading %globaltimer instead costs ~1 us: taken on every
     // blocking wait it slowed the forward kernel by 17 %, measured).
     if (mbar_try_wait(bar, parity)) return;
     if (mbar_try_wait(bar, parity)) return;
-    const uint32_t t0 = (uint32_t)(clock64() >> 20);
+    const uint32_t t0 = clock_hi();
     while (!mbar_try_wait(bar, parity)) {
-        if ((uint32_t)(clock64() >> 20) - t0 > (uint32_t)((RWKVTTS_WATCHDOG_NS * 2) >> 20)) {
-            extern __shared__ __align__(128) unsigned char wd_dyn_smem[];
-            unsigned long long *r = g_wd_rec;
-            if (r != nullptr) {
-                const uint32_t off = smem_u32(bar) - smem_u32(wd_dyn_smem);
-                r[8 + ((off >> 3) % kWatchdogEntries)] = (1ull << 63) | ((unsigned long long)g_wd_kernel << 60) |
-                                                         ((unsigned long long)(parity & 1u) << 59) |
-                                                         ((unsigned long long)(threadIdx.x >> 5) << 48) |
-                                                         ((unsigned long long)(blockIdx.x & 0xffffffu) << 24) | (off & 0xffffffu);
-                r[0] = kWatchdogMagic;
-                __threadfence_system();
-            }
-            // nobody traps at once: a trap aborts the grid, stores in flight included, and the other stuck warps
-            // run out of patience within a few ms of this one
-            const uint32_t t1 = (uint32_t)(clock64() >> 20);
-            while ((uint32_t)(clock64() >> 20) - t1 < 100u) {}
-            __trap();
-        }
+        if (clock_hi() - t0 >= 2u) mbar_die(smem_u32(bar), parity);
     }
 }
 // host side: point this translation unit's record pointer at the pinned buffer (once per device)

@@ -85,7 +85,7 @@ struct Smem {
     // one barrier per iteration parity: with a single barrier the MMA warp could commit iteration it+1 before group C2
     // had observed iteration it (nothing on C2's side gates that commit), the 1-bit phase parity would flip twice and
     // C2 would wait for a phase that can only complete after its own ok_free arrival -- a deadlock (found by the
-    // protocol model, proto/bwd_v2_sync_model.py; round-1 VERDICT).  out_ready[p] is committed at iterations of parity
+    // round-1 protocol model and VERDICT; reproduced on the GPU by tests/test_stress_gpu.py).  out_ready[p] is committed at iterations of parity
     // p only, and the next commit on it (it+2) waits for ok_free[p] of iteration `it`, which C2 gives after its wait.
     uint64_t out_ready[2];
     uint32_t tmem_base;
