@@ -22,7 +22,11 @@
  *   - w,q,k,v,z,a,y,dy and the six gradients are bf16, contiguous [B,T,H,64]
  *     ([B,T,H*64] for the stateful op: same memory); argument order at the op boundary is
  *     (w, q=r, k, v, z=a, a=b) (wkv7_op.cpp:7); `w` is the BlinkDL pre-activation,
- *     decay = exp(-exp(w));
+ *     decay = exp(-exp(w)).  RANGE CONTRACT of the default (chunked tensor-core) family: the per-step log-decay
+ *     -exp(w) is clamped at -1.35, i.e. results equal the reference's for w <= ln(1.35) = 0.30 -- every value the models
+ *     produce (w <= -0.5, rwkv_s2s_single_ffn.py:172) and the w = 0 of masked tokens (:176) -- and for larger w the decay
+ *     saturates at exp(-1.35) = 0.26 (dw is not masked there).  The sequential family (rwkvtts_set_impl(0)) and the
+ *     stateful forward accept any w, like the reference kernels;
  *   - recurrent state is fp32 [B,H,64,64], value-major S[b][h][value][key], updated in place;
  *   - `s` and `sa` are the caller-allocated scratch tensors of WindBackstepping
  *     (rwkv_s2s_single_ffn.py:22-25): s  = B*H*(T/16)*64*64 floats, sa = B*T*H*64 floats.
@@ -217,7 +221,8 @@ RWKVTTS_API int rwkvtts_ce_forward_backward(void *logits, long long rows, int V,
  * (model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226).
  * Activations bf16 [B,T,C] contiguous, C = H*64; `mask` bf16 [B,T] of 0/1 or NULL (attention_mask, :160,:175-190);
  * per-channel parameters fp32 [C]; parameter gradients fp32, summed deterministically through `scratch`
- * (rwkvtts_tmix_scratch_floats floats, caller-allocated).  Each *_backward is the exact adjoint of its forward. */
+ * (rwkvtts_tmix_scratch_floats floats, caller-allocated).  Each *_backward is the exact adjoint of its forward.
+ * C <= 4096 for the forward entry points, C <= 2048 for the *_backward ones (RWKVTTS_ERR_SHAPE beyond). */
 
 /* scratch floats for a backward with n_params per-channel parameter vectors (6 / 1 shift_mix, 5 prep, 3 out) */
 RWKVTTS_API size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params);

@@ -407,6 +407,9 @@ int rwkvtts_ce_forward_backward(void *logits, long long rows, int V, long long l
 
 // ---- fused time-mix elementwise kernels ------------------------------------------------------------------------
 static bool tmix_shape_ok(int B, int T, int C) { return B > 0 && T > 0 && C > 0 && C % RWKVTTS_HEAD_SIZE == 0 && C <= 4096; }
+// the adjoint kernels run C/8 threads per row inside CTAs of 256 threads (launch bounds): rows wider than 2048 channels
+// cannot launch -- refuse them here instead of failing in the launch
+static bool tmix_bwd_shape_ok(int B, int T, int C) { return tmix_shape_ok(B, T, C) && C <= 2048; }
 
 size_t rwkvtts_tmix_scratch_floats(int B, int T, int C, int n_params) {
     if (!tmix_shape_ok(B, T, C) || n_params <= 0) return 0;
@@ -436,7 +439,7 @@ int rwkvtts_tmix_shift_mix_forward(int B, int T, int C, int n, const void *x, co
 int rwkvtts_tmix_shift_mix_backward_varlen(int B, int T, int C, int n, const void *x, const void *mask, const void *prev,
                                            const float *mix, const void *const *dout, void *dx, float *dmix, float *scratch,
                                            const unsigned char *seq_first, void *stream) {
-    if (!tmix_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
+    if (!tmix_bwd_shape_ok(B, T, C) || (n != 1 && n != 6)) return RWKVTTS_ERR_SHAPE;
     if (dout == nullptr) return RWKVTTS_ERR_NULL;
     if (int rc = check_ptrs({x, mix, dx, dmix, scratch})) return rc;
     for (int i = 0; i < n; i++)
@@ -472,7 +475,7 @@ int rwkvtts_tmix_prep_backward(int B, int T, int C, const void *k, const void *v
                                const void *dk2, const void *dv2, const void *da_op, const void *db_op, void *dk, void *dv,
                                void *dw_lo, void *da_lo, void *dv_lo, void *dv_first, float *dparams, float *scratch,
                                void *stream) {
-    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (!tmix_bwd_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({k, w_lo, a_lo, w0, a0, k_k, k_a, dw, dk2, da_op, db_op, dk, dw_lo, da_lo, dparams, scratch}))
         return rc;
     if ((v_lo == nullptr) != (v_first == nullptr) || (v_lo != nullptr && v0 == nullptr)) return RWKVTTS_ERR_NULL;
@@ -496,7 +499,7 @@ int rwkvtts_tmix_out_backward(int B, int T, int C, const void *y, const void *r,
                               const void *g, const float *r_k, const float *ln_w, const float *ln_b, float eps,
                               const void *d_o, void *dy, void *dr, void *dk2, void *dv2, void *dg, float *dparams,
                               float *scratch, void *stream) {
-    if (!tmix_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
+    if (!tmix_bwd_shape_ok(B, T, C)) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({y, r, k2, v2, g, r_k, ln_w, ln_b, d_o, dy, dr, dk2, dv2, dg, dparams, scratch})) return rc;
     return finish(rwkvtts::launch_out_bwd(B, T, C, y, r, k2, v2, g, r_k, ln_w, ln_b, eps, d_o, dy, dr, dk2, dv2, dg, dparams,
                                           scratch, (cudaStream_t)stream));
@@ -512,7 +515,7 @@ int rwkvtts_add_layernorm_forward(long long rows, int C, const void *x, const vo
 
 int rwkvtts_add_layernorm_backward(long long rows, int C, const void *sum, const float *stats, const float *w,
                                    const void *dy, const void *ds, void *dx, float *dparams, float *scratch, void *stream) {
-    if (rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 256 != 0 || C > 4096) return RWKVTTS_ERR_SHAPE;
+    if (rows <= 0 || rows > 0x7fffffffLL || C <= 0 || C % 256 != 0 || C > 2048) return RWKVTTS_ERR_SHAPE;
     if (int rc = check_ptrs({sum, stats, w, dy, dx, dparams, scratch})) return rc;
     if (int rc = check_opt({ds})) return rc;
     return finish(rwkvtts::launch_add_ln_bwd((long)rows, C, sum, stats, w, dy, ds, dx, dparams, scratch, (cudaStream_t)stream));

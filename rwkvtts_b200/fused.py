@@ -24,9 +24,16 @@ from .ops import _need_cuda, _ptr, _stream
 BF16 = torch.bfloat16
 
 
+MAX_C_FORWARD, MAX_C_BACKWARD = 4096, 2048     # the adjoint kernels hold C/8 threads per row in CTAs of 256 threads
+
+
 def usable(x: torch.Tensor) -> bool:
-    """The fused kernels cover CUDA bf16 activations with C a multiple of 64 (one head = 8 lanes x 8 channels)."""
-    return x.is_cuda and x.dtype == BF16 and x.shape[-1] % 64 == 0 and x.shape[-1] <= 4096
+    """The fused kernels cover CUDA bf16 activations with C a multiple of 64 (one head = 8 lanes x 8 channels), C <= 4096
+    without autograd and C <= 2048 with it (beyond that the ATen chain runs: ADVICE round 1 -- the adjoint kernels cannot
+    launch a row wider than their 256-thread CTAs)."""
+    if not (x.is_cuda and x.dtype == BF16 and x.shape[-1] % 64 == 0):
+        return False
+    return x.shape[-1] <= (MAX_C_BACKWARD if torch.is_grad_enabled() else MAX_C_FORWARD)
 
 
 # fp32 copies of per-channel parameters.  Under no_grad (prefill / decode: ~14 tiny conversion kernels per layer and
@@ -294,7 +301,8 @@ def sqrelu(x: torch.Tensor) -> torch.Tensor:
 
 
 def ln_usable(x: torch.Tensor) -> bool:
-    return x.is_cuda and x.dtype == BF16 and x.shape[-1] % 256 == 0 and x.shape[-1] <= 4096
+    return (x.is_cuda and x.dtype == BF16 and x.shape[-1] % 256 == 0
+            and x.shape[-1] <= (MAX_C_BACKWARD if torch.is_grad_enabled() else MAX_C_FORWARD))
 
 
 class _AddLayerNorm(torch.autograd.Function):

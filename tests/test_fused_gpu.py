@@ -230,3 +230,34 @@ def test_tmix_fused_matches_aten_path(fused, layer_id, use_mask, mask_rwk):
         # wiring check: the per-kernel tests above pin the math against fp32; the ATen chain rounds every intermediate
         # and every partial parameter gradient to bf16, so the two sides differ by a few per cent on small gradients
         assert rel(res[True][3][n], gr) < 0.15, (n, rel(res[True][3][n], gr))
+
+
+def test_wide_rows_take_the_aten_chain_under_autograd_and_the_abi_refuses_them(fused):
+    """the adjoint kernels cannot launch rows wider than 2048 channels (C/8 threads per row in 256-thread
+    CTAs).  C = 2560: usable() is false under autograd (the ATen chain trains), true without it; the *_backward entry points
+    answer RWKVTTS_ERR_SHAPE instead of failing in the launch."""
+    from rwkvtts_b200 import _lib
+    C = 2560
+    x = torch.randn(2, 8, C, device="cuda").bfloat16()
+    assert not fused.usable(x) and not fused.ln_usable(x)
+    with torch.no_grad():
+        assert fused.usable(x) and fused.ln_usable(x)
+        mixes = [torch.rand(C, device="cuda").bfloat16() for _ in range(6)]
+        outs = fused.shift_mix(x, mixes)                               # forward kernels do cover it
+        want = ref_shift_mix(x, mixes, None, None)
+        for o, w in zip(outs, want):
+            assert rel(o, w) < ACT_TOL
+    L = _lib.lib()
+    f32 = torch.zeros(6 * C, device="cuda")
+    import ctypes
+    dptr = (ctypes.c_void_p * 6)(*[x.data_ptr()] * 6)
+    rc = L.rwkvtts_tmix_shift_mix_backward(2, 8, C, 6, x.data_ptr(), None, None, f32.data_ptr(), dptr, x.data_ptr(),
+                                           f32.data_ptr(), f32.data_ptr(), None)
+    assert rc == -1                                                    # RWKVTTS_ERR_SHAPE
+    # a whole time-mix layer at that width trains (ATen chain around the WKV kernels)
+    from rwkvfla.layers.rwkv7 import RWKV7Attention
+    att = RWKV7Attention(hidden_size=C, head_dim=64, layer_idx=1, num_hidden_layers=2).cuda().to(torch.bfloat16)
+    h = torch.randn(1, 32, C, device="cuda").bfloat16().requires_grad_(True)
+    out, _, _, _ = att(h, v_first=torch.randn(1, 32, C, device="cuda").bfloat16())
+    out.float().square().mean().backward()
+    assert torch.isfinite(h.grad.float()).all()

@@ -297,3 +297,31 @@ def test_full_size_forward_and_backward_slices_vs_oracle(impl, B, T, H, slices):
             # over 4096+ tokens that costs its dw accuracy, exactly as it does the reference kernel
             tol = 5e-3 if (scan and name == "dw") else TOL
             assert exc <= tol, f"{name} b={b} h={h}: excess {exc:.3e} (err {err:.3e}, floor {floor:.3e})"
+
+
+def test_masked_tokens_with_w_zero_vs_oracle(impl):
+    """masked positions reach the op with w = 0 (and r = k = v = 0: `w * mask`, rwkv_s2s_single_ffn.py:
+    175-178), i.e. a per-step log-decay of -1 -- inside the tensor-core family's range contract (clamp at -1.35,
+    include/rwkvtts_wkv7.h).  Runs of masked tokens in the middle and at the end of the sequences, both families, y and
+    all six gradients against the oracle."""
+    R = impl
+    B, T, H = 2, 160, 3
+    x = O.make_inputs(B, T, H, seed=77)
+    m = torch.ones(B, T, 1, 1)
+    m[0, 40:75] = 0
+    m[1, 100:] = 0
+    m[1, 3:5] = 0
+    for n in ("w", "q", "k", "v", "dy"):
+        x[n] = (x[n].float() * m).to(torch.bfloat16)
+    kk = x["a"].float() * m                         # kk is masked too (:188), so a = -kk and b = kk * g vanish
+    x["a"], x["b"] = kk.to(torch.bfloat16), (x["b"].float() * m).to(torch.bfloat16)
+    d = _dev(x)
+    leaves = [d[n].clone().requires_grad_(True) for n in ORDER]
+    y = R.WindBackstepping.apply(*leaves)
+    y.backward(d["dy"])
+    torch.cuda.synchronize()
+    y64, _ = O.wkv7_forward(*[x[n] for n in ORDER])
+    g64 = O.wkv7_backward(*[x[n] for n in ORDER], x["dy"])
+    _check("y", y, y64)
+    for n, leaf, g in zip(ORDER, leaves, g64):
+        _check("d" + n, leaf.grad, g)
