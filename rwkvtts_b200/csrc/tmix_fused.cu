@@ -217,6 +217,98 @@ __global__ void __launch_bounds__(kBwdThreads, 2) shift_mix_bwd_kernel(const Mix
     write_partials<N>(acc, P.part, P.C, tpr, rl, cl, red);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// shift_mix adjoint, second form (C % 128 == 0, 512 <= C <= 2048).  ncu on the first form (profiles/
+// r02_fused_adjoints_full.txt): 128 registers -- 48 d-mix accumulators + 8-channel rows -- leave 16 warps per SM and the
+// compiler cannot keep a row's seven loads in flight together, so every row costs several DRAM round trips (26 % of the
+// HBM roofline, long-scoreboard stalls).  Here a thread owns FOUR channels: 24 accumulators, rows as packed 8-byte words,
+// the next row's loads issued before the current row is consumed, lerp coefficients in shared memory -> ~3 CTAs of C/4
+// threads per SM with 14 loads in flight per thread.  One row lane per CTA: the accumulators are the CTA's partial sums.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack4h(const uint2 &u, float (&f)[4]) {
+    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+}
+template <int N>
+__global__ void __launch_bounds__(512) shift_mix_bwd4_kernel(const MixParams P) {
+    extern __shared__ float smix[];                       // [N][C]
+    const int c0 = threadIdx.x * 4;
+    for (int e = threadIdx.x; e < N * P.C; e += blockDim.x) smix[e] = P.mix[e];
+    __syncthreads();
+    float acc[N][4];
+#pragma unroll
+    for (int s = 0; s < N; s++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[s][i] = 0.f;
+    const long rows = (long)P.B * P.T;
+    const long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    auto mask_of = [&](long row) { return P.mask != nullptr ? __bfloat162float(P.mask[row]) : 1.f; };
+    auto ldx = [&](long row) { return *reinterpret_cast<const uint2 *>(P.x + row * P.C + c0); };
+    const uint2 zero2 = make_uint2(0u, 0u);
+    uint2 dn[N], dc[N], dp[N];                             // d rows: next (row+1), current, prefetched (row-1)
+    uint2 xc = zero2, xb = zero2, xbb = zero2;             // x rows: current, below (row-1), prefetched (row-2)
+#pragma unroll
+    for (int s = 0; s < N; s++) { dn[s] = zero2; dc[s] = zero2; dp[s] = zero2; }
+    if (r0 < r1) {
+        const long last = r1 - 1;
+        xc = ldx(last);
+        if (last > 0) xb = ldx(last - 1);
+#pragma unroll
+        for (int s = 0; s < N; s++) dc[s] = *reinterpret_cast<const uint2 *>(P.dout[s] + last * P.C + c0);
+        if (!seq_last(P, last, rows)) {
+#pragma unroll
+            for (int s = 0; s < N; s++) dn[s] = *reinterpret_cast<const uint2 *>(P.dout[s] + (last + 1) * P.C + c0);
+        }
+    }
+    for (long row = r1 - 1; row >= r0; row--) {
+        // loads of the NEXT iteration first: d[.][row-1] and x[row-2]
+        if (row - 1 >= r0) {
+#pragma unroll
+            for (int s = 0; s < N; s++) dp[s] = *reinterpret_cast<const uint2 *>(P.dout[s] + (row - 1) * P.C + c0);
+        }
+        xbb = (row >= 2) ? ldx(row - 2) : zero2;
+        const float m = mask_of(row), mb = row > 0 ? mask_of(row - 1) : 0.f;
+        float x[4], xp[4];
+        unpack4h(xc, x);
+        unpack4h(xb, xp);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { x[i] *= m; xp[i] *= mb; }
+        if (seq_first(P, row)) {
+            if (P.prev != nullptr && P.first == nullptr) {
+                const uint2 pv = *reinterpret_cast<const uint2 *>(P.prev + (size_t)(row / P.T) * P.C + c0);
+                unpack4h(pv, xp);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) xp[i] = 0.f;
+            }
+        }
+        const bool last_of_seq = seq_last(P, row, rows);
+        float dx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            float d[4], dnx[4];
+            unpack4h(dc[s], d);
+            unpack4h(last_of_seq ? zero2 : dn[s], dnx);
+            const float4 mx = *reinterpret_cast<const float4 *>(smix + s * P.C + c0);
+            const float mixv[4] = {mx.x, mx.y, mx.z, mx.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[s][i] = fmaf(d[i], rbf(xp[i] - x[i]), acc[s][i]);
+                dx[i] += d[i] * (1.f - mixv[i]) + dnx[i] * mixv[i];
+            }
+        }
+        *reinterpret_cast<uint2 *>(P.dx + row * P.C + c0) = make_uint2(pack2(dx[0] * m, dx[1] * m), pack2(dx[2] * m, dx[3] * m));
+#pragma unroll
+        for (int s = 0; s < N; s++) { dn[s] = dc[s]; dc[s] = dp[s]; }
+        xc = xb; xb = xbb;
+    }
+    float *dst = P.part + (size_t)blockIdx.x * N * P.C;
+#pragma unroll
+    for (int s = 0; s < N; s++)
+        *reinterpret_cast<float4 *>(dst + s * P.C + c0) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // prep
 // ------------------------------------------------------------------------------------------------------------------
@@ -677,6 +769,91 @@ __global__ void __launch_bounds__(kBwdThreads, 2) add_ln_bwd_kernel(const LnPara
     write_partials<2>(acc, P.part, P.C, tpr, rl, cl, redp);
 }
 
+
+// residual-add + LayerNorm adjoint, second form (C % 256 == 0, C <= 1024): ONE WARP PER ROW.  The first form reduces each
+// row across a CTA (two __syncthreads per row, two rows in flight per CTA: 42 % of the HBM roofline in the train step);
+// here a lane owns C/256 groups of 8 channels, both row reductions are shuffles, and a warp has all 3 * C/256 loads of a
+// row in flight together.  dw / db partials: per lane in registers, summed over the CTA's warps through shared memory.
+template <int NV>
+__global__ void __launch_bounds__(NV <= 3 ? 256 : 320, NV <= 3 ? 2 : 1) add_ln_bwd_warp_kernel(const LnParams P) {
+    extern __shared__ float redw[];                        // [2][C] per CTA
+    const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float invC = 1.f / P.C;
+    for (int e = threadIdx.x; e < 2 * P.C; e += blockDim.x) redw[e] = 0.f;
+    __syncthreads();
+    float acc[2][NV][kVec];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int j = 0; j < NV; j++)
+#pragma unroll
+            for (int i = 0; i < kVec; i++) acc[s][j][i] = 0.f;
+    const long gw = (long)blockIdx.x * nwarp + wip, nw = (long)gridDim.x * nwarp;
+    for (long row = gw; row < P.rows; row += nw) {
+        uint4 us[NV], ud[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const size_t off = row * P.C + (size_t)(j * 32 + lane) * kVec;
+            us[j] = *reinterpret_cast<const uint4 *>(P.sum + off);
+            ud[j] = *reinterpret_cast<const uint4 *>(P.dy + off);
+        }
+        const float mu = P.stats[2 * row], rstd = P.stats[2 * row + 1];
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            float sv[kVec], dv[kVec];
+            unpack8(us[j], sv);
+            unpack8(ud[j], dv);
+            const Row8 w = ld8f(P.w + (j * 32 + lane) * kVec);
+#pragma unroll
+            for (int i = 0; i < kVec; i++) {
+                const float sh = (sv[i] - mu) * rstd, g = dv[i] * w.v[i];
+                acc[0][j][i] = fmaf(dv[i], sh, acc[0][j][i]);
+                acc[1][j][i] += dv[i];
+                m1 += g;
+                m2 = fmaf(g, sh, m2);
+            }
+        }
+        m1 = warp_sum(m1) * invC;
+        m2 = warp_sum(m2) * invC;
+        // second pass over the row kept packed in registers (sh and g are recomputed: two multiplies instead of 64 registers)
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const size_t off = row * P.C + (size_t)(j * 32 + lane) * kVec;
+            float sv[kVec], dv[kVec], d2[kVec];
+            unpack8(us[j], sv);
+            unpack8(ud[j], dv);
+            if (P.ds != nullptr) unpack8(*reinterpret_cast<const uint4 *>(P.ds + off), d2);
+            else {
+#pragma unroll
+                for (int i = 0; i < kVec; i++) d2[i] = 0.f;
+            }
+            const Row8 w = ld8f(P.w + (j * 32 + lane) * kVec);
+            Row8 o;
+#pragma unroll
+            for (int i = 0; i < kVec; i++) {
+                const float sh = (sv[i] - mu) * rstd, g = dv[i] * w.v[i];
+                o.v[i] = rstd * (g - m1 - sh * m2) + d2[i];
+            }
+            st8(P.dx + off, o);
+        }
+    }
+    // the warps of a CTA add their partials one after the other (fixed order: deterministic)
+    for (int w = 0; w < nwarp; w++) {
+        if (w == wip) {
+#pragma unroll
+            for (int s = 0; s < 2; s++)
+#pragma unroll
+                for (int j = 0; j < NV; j++)
+#pragma unroll
+                    for (int i = 0; i < kVec; i++) redw[s * P.C + (j * 32 + lane) * kVec + i] += acc[s][j][i];
+        }
+        __syncthreads();
+    }
+    float *dst = P.part + (size_t)blockIdx.x * 2 * P.C;
+    for (int e = threadIdx.x; e < 2 * P.C; e += blockDim.x) dst[e] = redw[e];
+}
+
 // launch geometry: threads per row = C/8; rows per CTA so that the CTA has <= 512 threads; grid = multiple of the SM count
 struct Geo { int threads, rows_per_cta, grid; size_t red_bytes(int n, int C) const { return (size_t)rows_per_cta * n * C * 4; } };
 inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm, int max_threads = kMaxThreads) {
@@ -724,10 +901,26 @@ cudaError_t launch_add_ln_bwd(long rows, int C, const void *sum, const float *st
     P.sum = (const bf16 *)sum; P.stats = const_cast<float *>(stats); P.w = w; P.dy = (const bf16 *)dy; P.ds = (const bf16 *)ds;
     P.dx = (bf16 *)dx; P.part = part; P.rows = rows; P.C = C;
     const Geo g = geometry(1, (int)rows, C, 4, 4, kBwdThreads);
+    count_launch(2);
+    if (C % 256 == 0 && C <= 1024 && rows >= 8) {
+        // one warp per row; the grid stays within the scratch the caller sized with rwkvtts_tmix_scratch_floats
+        const int nv = C / 256;
+        int grid = (int)((rows + 7) / 8);
+        if (grid > g.grid) grid = g.grid;
+        if (grid > 148 * (nv <= 3 ? 2 : 1)) grid = 148 * (nv <= 3 ? 2 : 1);       // resident CTAs per SM (registers)
+        const size_t shw = (size_t)2 * C * sizeof(float);
+        switch (nv) {
+            case 1: add_ln_bwd_warp_kernel<1><<<grid, 256, shw, st>>>(P); break;
+            case 2: add_ln_bwd_warp_kernel<2><<<grid, 256, shw, st>>>(P); break;
+            case 3: add_ln_bwd_warp_kernel<3><<<grid, 256, shw, st>>>(P); break;
+            default: add_ln_bwd_warp_kernel<4><<<grid, 320, shw, st>>>(P); break;   // 182 registers: 10 warps, 1 CTA per SM
+        }
+        reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, dparams, grid, 2 * C);
+        return cudaGetLastError();
+    }
     const size_t sh = g.red_bytes(2, C);
     cudaError_t e = cudaFuncSetAttribute(add_ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
-    count_launch(2);
     add_ln_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
     reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, dparams, g.grid, 2 * C);
     return cudaGetLastError();
@@ -775,6 +968,21 @@ cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, cons
     const size_t sh = g.red_bytes(n, C);
     count_launch(2);
     cudaError_t e;
+    if (C % 128 == 0 && C >= 512 && C <= 2048 && (long)B * T >= 64) {
+        // four channels per thread, one row lane per CTA of C/4 threads (see shift_mix_bwd4_kernel)
+        int grid = 148 * 3;
+        if (grid > g.grid) grid = g.grid;             // the caller's scratch holds g.grid partial rows
+        const size_t shm = (size_t)n * C * sizeof(float);
+        if (n == 6) {
+            e = cudaFuncSetAttribute(shift_mix_bwd4_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            if (e != cudaSuccess) return e;
+            shift_mix_bwd4_kernel<6><<<grid, C / 4, shm, st>>>(P);
+        } else if (n == 1) {
+            shift_mix_bwd4_kernel<1><<<grid, C / 4, shm, st>>>(P);
+        } else return cudaErrorInvalidValue;
+        reduce_partials_kernel<<<(n * C + 31) / 32, 256, 0, st>>>(part, dmix, grid, n * C);
+        return cudaGetLastError();
+    }
     if (n == 6) {
         e = cudaFuncSetAttribute(shift_mix_bwd_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
         if (e != cudaSuccess) return e;

@@ -43,7 +43,12 @@ def ref_shift_mix(x, mixes, mask, prev):
 
 @pytest.mark.parametrize("B,T,C,n,use_mask,use_prev", [(2, 37, 192, 6, False, False), (2, 64, 1024, 6, True, False),
                                                        (1, 5, 2048, 1, False, True), (3, 16, 768, 1, True, True),
-                                                       (1, 1, 64, 6, False, True)])
+                                                       (1, 1, 64, 6, False, True),
+                                                       # the four-channel adjoint (C >= 512, >= 64 rows): masks, carried
+                                                       # shift state, every width class, uneven rows per CTA
+                                                       (3, 333, 1024, 6, True, True), (2, 70, 768, 6, False, True),
+                                                       (5, 41, 2048, 6, True, False), (4, 128, 512, 1, True, True),
+                                                       (2, 100, 1024, 1, False, False)])
 def test_shift_mix(fused, B, T, C, n, use_mask, use_prev):
     g = torch.Generator(device="cuda").manual_seed(B * 100 + T)
     x = torch.randn(B, T, C, device="cuda", generator=g).bfloat16().requires_grad_(True)
@@ -146,7 +151,10 @@ def test_out(fused, B, T, C):
 
 
 @pytest.mark.parametrize("B,T,C,use_res,use_bias", [(2, 33, 256, True, True), (8, 64, 1024, True, True), (1, 7, 2048, False, True),
-                                                    (3, 5, 512, True, False)])
+                                                    (3, 5, 512, True, False),
+                                                    # warp-per-row adjoint: every C / 256 class, odd row counts
+                                                    (3, 333, 1024, True, True), (2, 77, 768, True, False), (1, 9, 256, False, True),
+                                                    (5, 41, 512, False, False)])
 def test_add_layernorm(fused, B, T, C, use_res, use_bias):
     g = torch.Generator(device="cuda").manual_seed(C + T)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
