@@ -519,10 +519,26 @@ def leg_decode():
     t_short = time.perf_counter() - t0
     t0 = time.perf_counter(); seq = m.generate(max_new_tokens=NEW, **kw); torch.cuda.synchronize()
     dt = time.perf_counter() - t0 - t_short
+    from rwkvtts_b200.decode import unsupported_reason
     out = {"tokens_per_s": DB * (NEW - short) / dt, "ms_per_step": dt / (NEW - short) * 1e3, "steps": NEW,
+           "step": "one persistent kernel per token over all layers + head + device arg-max (csrc/decode_step.cu)"
+                   if unsupported_reason(m, DB) is None else "CUDA-graph step",
            "prefill_plus_setup_ms": (t_short - short * dt / (NEW - short)) * 1e3,
            "config": "configs[3]: RWKV-7 0.4B random init, batch 32, prompt 163, greedy, EOS suppressed, 2000 new tokens; "
                      "steps timed as the difference of the 2000-token and a 16-token run"}
+    # the step it replaces: the same kernels per layer as ~430 nodes of one CUDA graph
+    kwg = dict(kw, use_megakernel=False)
+    m.generate(max_new_tokens=short, **kwg); torch.cuda.synchronize()
+    t0 = time.perf_counter(); m.generate(max_new_tokens=short, **kwg); torch.cuda.synchronize()
+    tg_short = time.perf_counter() - t0
+    t0 = time.perf_counter(); seqg = m.generate(max_new_tokens=NEW, **kwg); torch.cuda.synchronize()
+    dtg = time.perf_counter() - t0 - tg_short
+    out["graph_step"] = {"tokens_per_s": DB * (NEW - short) / dtg, "ms_per_step": dtg / (NEW - short) * 1e3}
+    # HBM floor of one step: every weight once + every recurrent state in and out
+    wbytes = sum(p.numel() * p.element_size() for n, p in m.named_parameters() if "embed" not in n)
+    sbytes = 2 * DB * 24 * 16 * 64 * 64 * 4
+    out["hbm_floor_ms"] = (wbytes + sbytes) / (peaks()[0] * 1e9) * 1e3
+    out["frac_of_hbm_floor"] = out["hbm_floor_ms"] / out["ms_per_step"]
     try:
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import decode_parity
@@ -539,6 +555,7 @@ def leg_decode():
         # the default fast path (fused kernels, fp32 intermediates): agreement rate and how close the reference's own
         # top-2 logits are wherever it picks another id
         out["fast_path_vs_reference"] = decode_parity.compare(m, ids, seq[:, PROMPT:], NEW)
+        out["graph_step_vs_reference"] = decode_parity.compare(m, ids, seqg[:, PROMPT:], NEW)
     except Exception as e:
         out["greedy_ids_identical_vs_reference"] = {"error": repr(e)}
     return out

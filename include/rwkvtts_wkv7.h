@@ -216,6 +216,52 @@ RWKVTTS_API int rwkvtts_ce_forward_backward(void *logits, long long rows, int V,
                                             long long ignore_index, float label_smoothing, const float *scale_dev,
                                             float *loss_rows, void *stream);
 
+/* ---- whole-model decode step in one persistent kernel -------------------------------------
+ * Replaces, per generated token, the ~25 kernels per layer of the reference decode loop
+ * (inference/rwkv7speech_inference.py; model/llm/spark_llm.py:54-102; per layer model/llm/rwkv_asr_cuda_whisper.py:181-215,
+ * :277-285, :318-326 with the stateful op model/llm/cuda/rwkv7_state_fwd_fp16.cu at T = 1) by ONE cooperative launch that
+ * walks all layers, the final norm and the vocabulary head, and optionally samples greedily on the device.
+ * All tensors bf16 unless noted; projection weights are nn.Linear layout [out, in] with `in` contiguous, LoRA
+ * down-projections [rank, C], LoRA up-projections [C, rank]; per-channel vectors [C].
+ *   dims[RWKVTTS_DEC_NDIM]   : B (<= 32), C (= H * 64, <= 2048), H, L, V, F (channel-mix width, multiple of C, <= 8 C),
+ *                              ranks of the w, a, v, g LoRAs (multiples of 32, sum <= 512)
+ *   eps[2]                   : LayerNorm eps, GroupNorm eps (head_size_divisor^2 * 1e-5 in the reference: 64e-5)
+ *   model_ptrs[RWKVTTS_DEC_NMODEL], layer_ptrs[L][RWKVTTS_DEC_NPTR]: device pointers, indices below.  NULL allowed for
+ *       LN0_* (no pre-norm), every *_B (norm without bias) and V1 / V2 / V0 (layer 0).  STATE fp32 [B,H,64,64] value-major,
+ *       ATT_SHIFT / FFN_SHIFT [B,C]: the recurrent state of the layer, advanced IN PLACE by every step.
+ * rwkvtts_decode_workspace_bytes -> bytes of device workspace (0 = unsupported dims); offsets[3] = byte offsets inside it of
+ *       the fp32 logits [B, V] the step leaves, the int64 next-token buffer [32] and the int32 finished flags [32].
+ * rwkvtts_decode_init   : writes the plan into `workspace` (zeroes it first); call again after any pointer changes.
+ * rwkvtts_decode_step   : one token for all B rows.  tok_in (device int64 [B]) or NULL = the token the previous greedy
+ *       step chose.  greedy != 0: arg-max on the device (lowest index on ties) with the EOS handling of generate():
+ *       ids in eos[n_eos] (host, <= 8) are masked while suppress_eos != 0, rows already finished emit `pad`, a row
+ *       finishes when it emits an EOS id; the chosen ids go to the workspace token buffer and tok_out (device, may be NULL).
+ * rwkvtts_decode_release: forget the plan of `workspace` (the memory is the caller's). */
+enum rwkvtts_decode_dim {
+    RWKVTTS_DEC_B = 0, RWKVTTS_DEC_C, RWKVTTS_DEC_H, RWKVTTS_DEC_L, RWKVTTS_DEC_V, RWKVTTS_DEC_F,
+    RWKVTTS_DEC_DW, RWKVTTS_DEC_DA, RWKVTTS_DEC_DV, RWKVTTS_DEC_DG, RWKVTTS_DEC_NDIM
+};
+enum rwkvtts_decode_model_ptr {
+    RWKVTTS_DEC_EMB = 0, RWKVTTS_DEC_LN0_W, RWKVTTS_DEC_LN0_B, RWKVTTS_DEC_LNF_W, RWKVTTS_DEC_LNF_B, RWKVTTS_DEC_HEAD,
+    RWKVTTS_DEC_NMODEL
+};
+enum rwkvtts_decode_layer_ptr {
+    RWKVTTS_DEC_LN1_W = 0, RWKVTTS_DEC_LN1_B, RWKVTTS_DEC_LN2_W, RWKVTTS_DEC_LN2_B,
+    RWKVTTS_DEC_X_R, RWKVTTS_DEC_X_W, RWKVTTS_DEC_X_K, RWKVTTS_DEC_X_V, RWKVTTS_DEC_X_A, RWKVTTS_DEC_X_G,
+    RWKVTTS_DEC_W_R, RWKVTTS_DEC_W_K, RWKVTTS_DEC_W_V, RWKVTTS_DEC_W_O,
+    RWKVTTS_DEC_W1, RWKVTTS_DEC_W2, RWKVTTS_DEC_W0, RWKVTTS_DEC_A1, RWKVTTS_DEC_A2, RWKVTTS_DEC_A0,
+    RWKVTTS_DEC_V1, RWKVTTS_DEC_V2, RWKVTTS_DEC_V0, RWKVTTS_DEC_G1, RWKVTTS_DEC_G2,
+    RWKVTTS_DEC_K_K, RWKVTTS_DEC_K_A, RWKVTTS_DEC_R_K, RWKVTTS_DEC_GN_W, RWKVTTS_DEC_GN_B,
+    RWKVTTS_DEC_FFN_X_K, RWKVTTS_DEC_FFN_KEY, RWKVTTS_DEC_FFN_VALUE,
+    RWKVTTS_DEC_STATE, RWKVTTS_DEC_ATT_SHIFT, RWKVTTS_DEC_FFN_SHIFT, RWKVTTS_DEC_NPTR
+};
+RWKVTTS_API size_t rwkvtts_decode_workspace_bytes(const int *dims, size_t *offsets);
+RWKVTTS_API int rwkvtts_decode_init(const int *dims, const float *eps, const void *const *model_ptrs,
+                                    const void *const *layer_ptrs, void *workspace, size_t workspace_bytes, void *stream);
+RWKVTTS_API int rwkvtts_decode_step(void *workspace, const long long *tok_in, long long *tok_out, int greedy,
+                                    int suppress_eos, const long long *eos, int n_eos, long long pad, void *stream);
+RWKVTTS_API int rwkvtts_decode_release(void *workspace);
+
 /* ---- fused elementwise kernels of the time-mix around the WKV-7 op ---------------------------------------------
  * Replace the ~30 ATen elementwise kernels RWKV_Tmix_x070.forward runs per layer between its GEMMs
  * (model/llm/rwkv_s2s_single_ffn.py:160-195) and the token-shift lerp of RWKV_CMix_x070.forward (:226).

@@ -22,6 +22,7 @@ from transformers.modeling_outputs import BaseModelOutputWithPast, CausalLMOutpu
 from transformers.modeling_utils import PreTrainedModel
 
 from rwkvtts_b200 import core, ops
+from rwkvtts_b200.decode import MegaDecodeStep, unsupported_reason
 from rwkvtts_b200.fused import cached as fused_cached
 from rwkvtts_b200.fused import usable as fused_usable
 from ...layers.rwkv7 import RWKV7Attention
@@ -385,13 +386,16 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
                  eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
                  use_cache: bool = True, generator: Optional[torch.Generator] = None,
                  return_dict_in_generate: bool = False, use_cuda_graph: Optional[bool] = None,
-                 eos_check_interval: int = 1, exact: bool = False, **kwargs):
+                 eos_check_interval: int = 1, exact: bool = False, use_megakernel: Optional[bool] = None, **kwargs):
         """Autoregressive decode over the recurrent Cache (the call inference/rwkv7speech_inference.py and
         spark_llm.py:54-102 make).  Returns [B, prompt + new] token ids when `input_ids` is given and
         [B, new] when only `inputs_embeds` is given (HF convention); finished rows are padded with
         `pad_token_id`.  On CUDA the per-token step runs as one CUDA graph (`use_cuda_graph`, default on when more than 8
         tokens are requested); `eos_check_interval` > 1 polls the all-finished flag (a host sync) only every that many
-        steps (finished rows are padded either way, so the result does not change)."""
+        steps (finished rows are padded either way, so the result does not change).  `use_megakernel` (default: on
+        whenever the model fits it and neither `exact` nor `use_cuda_graph=False` is asked for): the per-token step is ONE
+        persistent kernel over all layers (rwkvtts_b200/decode.py, csrc/decode_step.cu) instead of the ~430-node graph, and
+        a greedy decode also samples on the device -- n tokens are n launches."""
         if exact:
             # the reference decode step operation for operation (core.exact_mode): greedy ids bit-identical to the
             # reference loop (rwkv_asr_cuda_whisper.py:694-717), at the reference's eager speed plus the CUDA graph
@@ -402,7 +406,8 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
                                      do_sample=do_sample, temperature=temperature, top_k=top_k, top_p=top_p,
                                      eos_token_id=eos_token_id, pad_token_id=pad_token_id, use_cache=use_cache,
                                      generator=generator, return_dict_in_generate=return_dict_in_generate,
-                                     use_cuda_graph=use_cuda_graph, eos_check_interval=eos_check_interval, **kwargs)
+                                     use_cuda_graph=use_cuda_graph, eos_check_interval=eos_check_interval,
+                                     use_megakernel=False, **kwargs)
         if (input_ids is None) == (inputs_embeds is None):
             raise ValueError("pass exactly one of input_ids / inputs_embeds")
         prompt_len = input_ids.shape[1] if input_ids is not None else inputs_embeds.shape[1]
@@ -426,8 +431,13 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
         logits = out.logits[:, -1].float()
         if use_cuda_graph is None:
             use_cuda_graph = dev.type == "cuda" and max_new_tokens > 8
-        graph_step = None
-        if use_cuda_graph and max_new_tokens > 1:
+        graph_step, mega = None, None
+        if use_megakernel is None:
+            use_megakernel = (dev.type == "cuda" and use_cuda_graph and max_new_tokens > 1 and core.FUSED and not core.EXACT
+                              and len(eos) <= 8 and unsupported_reason(self, B) is None)
+        if use_megakernel and max_new_tokens > 1:
+            mega = graph_step = MegaDecodeStep(self, cache, B, dev)       # raises if the model does not fit the kernel
+        elif use_cuda_graph and max_new_tokens > 1:
             try:
                 graph_step = _GraphDecodeStep(self, cache, B, dev)
             except RuntimeError as e:                  # e.g. an op that cannot be captured in a user subclass: decode eagerly
@@ -448,6 +458,26 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
                 done = done | torch.isin(nxt, eos_t)
                 if (step + 1) % max(eos_check_interval, 1) == 0 and bool(done.all()):
                     break
+            if mega is not None and not do_sample and step + 1 < max_new_tokens:
+                # greedy: the rest of the loop runs on the device (arg-max, EOS masking, finished rows, padding), one
+                # launch per token; the host only polls the all-finished flag every 64 tokens
+                left, s0, cur = max_new_tokens - 1 - step, step + 1, nxt
+                while left > 0:
+                    n = min(left, 64) if eos else left
+                    chunk = mega.greedy(cur, n, eos, pad, min_new_tokens, step0=s0, done=done)
+                    new_tokens.extend(chunk.unbind(0))
+                    cur, s0, left = chunk[-1], s0 + n, left - n
+                    if eos and bool(done.all()):
+                        break
+                if eos:       # cut where the host loop would have stopped: the first polled step with every row finished
+                    gen = torch.stack(new_tokens, dim=1)
+                    fin = (torch.isin(gen, eos_t).cumsum(dim=1) > 0).all(dim=0)
+                    k = max(eos_check_interval, 1)
+                    polled = (torch.arange(1, gen.shape[1] + 1, device=dev) % k) == 0
+                    hit = torch.nonzero(fin & polled)
+                    if hit.numel():
+                        new_tokens = new_tokens[: int(hit[0]) + 1]
+                break
             if step + 1 < max_new_tokens:
                 if graph_step is not None:
                     logits = graph_step(nxt).clone()

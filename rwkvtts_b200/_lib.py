@@ -61,6 +61,11 @@ SYMBOLS = {
                               ctypes.c_longlong, _vp, _vp, _i, ctypes.POINTER(ctypes.c_float), _i] + [ctypes.c_float] * 3
                          + [_i, _fp, _fp, _vp, _vp]),
     "rwkvtts_grad_stat": (_i, [_vp, _i, ctypes.c_longlong, _fp, _vp]),
+    "rwkvtts_decode_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_size_t)]),
+    "rwkvtts_decode_init": (_i, [ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                 _vp, ctypes.c_size_t, _vp]),
+    "rwkvtts_decode_step": (_i, [_vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_longlong), _i, ctypes.c_longlong, _vp]),
+    "rwkvtts_decode_release": (_i, [_vp]),
 }
 
 _lib = None

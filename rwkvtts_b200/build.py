@@ -26,7 +26,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "librwkvtts_wkv7.so")
 SOURCES = ["capi.cu", "wkv7_scan.cu", "wkv7_tc_fwd.cu", "wkv7_tc_bwd.cu", "tmix_fused.cu", "adam.cu", "gather.cu",
-           "linear_ce.cu", "wkv7_step_exact.cu"]
+           "linear_ce.cu", "wkv7_step_exact.cu", "decode_step.cu"]
 # per-file flags: the reference-order step kernel must come out with the reference build's flush-to-zero fast-math
 # instructions (model/llm/rwkv_asr_cuda_whisper.py:50) to be bit-identical to it
 FILE_FLAGS = {"wkv7_step_exact.cu": ["--use_fast_math"]}

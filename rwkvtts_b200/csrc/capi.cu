@@ -67,7 +67,8 @@ cudaError_t launch_adam_shard(float *master, float *m, float *v, const void *gra
 const char *tc_fwd_barrier_name(unsigned off);
 const char *tc_bwd_barrier_name(unsigned off);
 inline const char *watchdog_barrier_name(unsigned kernel, unsigned off) {
-    return kernel == 1 ? tc_fwd_barrier_name(off) : kernel == 2 ? tc_bwd_barrier_name(off) : "?";
+    return kernel == 1 ? tc_fwd_barrier_name(off) : kernel == 2 ? tc_bwd_barrier_name(off)
+         : kernel == 3 ? "grid barrier (number = offset)" : "?";
 }
 cudaError_t launch_adam_multi(float *master, float *m, float *v, const void *grad, int grad_is_bf16, void *param,
                               int param_is_bf16, long long n, const long long *seg_end, const int *seg_group, int nseg,
@@ -84,6 +85,13 @@ cudaError_t launch_embed_rows(const void *const *tables, int ntab, const long lo
 cudaError_t launch_ce_fwd_bwd(void *logits, long long rows, int V, long long ld, const long long *labels,
                               long long ignore_index, float label_smoothing, const float *scale_dev, float *loss_rows,
                               cudaStream_t st);
+namespace dec {
+cudaError_t decode_init(const int *dims, const float *eps, const void *const *mp, const void *const *lp, void *ws, cudaStream_t st);
+cudaError_t decode_step(void *ws, const long long *tok_in, long long *tok_out, int greedy, int suppress_eos,
+                        const long long *eos, int n_eos, long long pad, cudaStream_t st);
+void decode_release(void *ws);
+size_t decode_workspace(const int *dims, size_t *offs);
+}  // namespace dec
 int tmix_grid(int B, int T, int C, int which);
 cudaError_t launch_sqrelu(const void *x, const void *dy, void *out, long n, cudaStream_t st);
 cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
@@ -207,7 +215,7 @@ int rwkvtts_watchdog_report(char *buf, size_t n) {
             if ((e >> 63) == 0) continue;
             const unsigned kid = (unsigned)((e >> 60) & 7u), smem_off = (unsigned)(e & 0xffffffu);
             off += (size_t)snprintf(buf + off, n - off, " %s: %s (smem +%u) parity %u, block %u warp %u;",
-                                    kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : "?",
+                                    kid == 1 ? "wkv7_tc_fwd" : kid == 2 ? "wkv7_tc_bwd" : kid == 3 ? "decode_step" : "?",
                                     rwkvtts::watchdog_barrier_name(kid, smem_off), smem_off, (unsigned)((e >> 59) & 1u),
                                     (unsigned)((e >> 24) & 0xffffffu), (unsigned)((e >> 48) & 63u));
             if (off >= n) { off = n - 1; break; }
@@ -403,6 +411,47 @@ int rwkvtts_ce_forward_backward(void *logits, long long rows, int V, long long l
     if (labels == nullptr || scale_dev == nullptr || loss_rows == nullptr) return RWKVTTS_ERR_NULL;
     return finish(rwkvtts::launch_ce_fwd_bwd(logits, rows, V, ld, labels, ignore_index, label_smoothing, scale_dev,
                                              loss_rows, (cudaStream_t)stream));
+}
+
+// ---- whole-model decode step ------------------------------------------------------------------------------------------
+size_t rwkvtts_decode_workspace_bytes(const int *dims, size_t *offsets) {
+    if (dims == nullptr) return 0;
+    return rwkvtts::dec::decode_workspace(dims, offsets);
+}
+
+int rwkvtts_decode_init(const int *dims, const float *eps, const void *const *model_ptrs, const void *const *layer_ptrs,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (dims == nullptr || eps == nullptr || model_ptrs == nullptr || layer_ptrs == nullptr) return RWKVTTS_ERR_NULL;
+    const size_t need = rwkvtts::dec::decode_workspace(dims, nullptr);
+    if (need == 0 || workspace_bytes < need) return RWKVTTS_ERR_SHAPE;
+    if (int rc = check_ptrs({workspace})) return rc;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return RWKVTTS_ERR_ALIGN;
+    for (int i = 0; i < RWKVTTS_DEC_NMODEL; i++) {
+        const bool optional = i == RWKVTTS_DEC_LN0_W || i == RWKVTTS_DEC_LN0_B || i == RWKVTTS_DEC_LNF_B;
+        if (int rc = optional ? check_opt({model_ptrs[i]}) : check_ptrs({model_ptrs[i]})) return rc;
+    }
+    const int L = dims[RWKVTTS_DEC_L];
+    for (int l = 0; l < L; l++)
+        for (int i = 0; i < RWKVTTS_DEC_NPTR; i++) {
+            const void *p = layer_ptrs[(size_t)l * RWKVTTS_DEC_NPTR + i];
+            const bool optional = i == RWKVTTS_DEC_LN1_B || i == RWKVTTS_DEC_LN2_B || i == RWKVTTS_DEC_GN_B ||
+                                  i == RWKVTTS_DEC_V1 || i == RWKVTTS_DEC_V2 || i == RWKVTTS_DEC_V0;
+            if (int rc = optional ? check_opt({p}) : check_ptrs({p})) return rc;
+        }
+    return finish(rwkvtts::dec::decode_init(dims, eps, model_ptrs, layer_ptrs, workspace, (cudaStream_t)stream));
+}
+
+int rwkvtts_decode_step(void *workspace, const long long *tok_in, long long *tok_out, int greedy, int suppress_eos,
+                        const long long *eos, int n_eos, long long pad, void *stream) {
+    if (workspace == nullptr || (n_eos > 0 && eos == nullptr)) return RWKVTTS_ERR_NULL;
+    if (n_eos < 0 || n_eos > 8) return RWKVTTS_ERR_SHAPE;
+    return finish(rwkvtts::dec::decode_step(workspace, tok_in, tok_out, greedy, suppress_eos, eos, n_eos, pad,
+                                            (cudaStream_t)stream));
+}
+
+int rwkvtts_decode_release(void *workspace) {
+    rwkvtts::dec::decode_release(workspace);
+    return RWKVTTS_OK;
 }
 
 // ---- fused time-mix elementwise kernels ------------------------------------------------------------------------

@@ -1,0 +1,702 @@
+// One autoregressive decode step of the whole RWKV-7 model in ONE persistent kernel  [HBM roofline: every weight and
+// every recurrent state read once per token; SURVEY.md section 8 row f3].
+//
+// Reference: the decode loop of inference/rwkv7speech_inference.py / model/llm/spark_llm.py:54-102 runs, per token and
+// layer, ~25 small kernels (token shift, six lerps, eleven skinny projections, the stateful WKV op
+// rwkv7_state_fwd_fp16.cu with T = 1, GroupNorm, gate, output projection, channel mix: rwkv_asr_cuda_whisper.py:181-215,
+// :277-285, :318-326).  At 32 rows each of them moves 0.1-8 MB, so the step is bound by launch count, not by bytes: the
+// CUDA-graph step of this repo (rwkvfla/models/rwkv7/modeling_rwkv7.py::_GraphDecodeStep) needs 1.59 ms for ~430 nodes
+// against 0.19 ms of HBM time for the 0.6 GB of weights + 0.4 GB of state it moves.
+//
+// Here: one cooperative launch of one CTA per SM (512 threads).  The step is a fixed sequence of phases separated by a
+// grid barrier (7 per layer):
+//   ln1    rows      x = residual (+ the previous layer's channel-mix output: its split-K partials are summed here),
+//                    h = LayerNorm1(x), token shift and the six lerps -> X[6]            rwkv_s2s_single_ffn.py:160-169
+//   gemm   columns   r, k, v projections and the four LoRA down-projections (tanh / sigmoid in the epilogue)   :170-184
+//   wkv    (b, head) LoRA up-projections, decay / kk / a / k' / v' (:172-190), the WKV-7 state update and read-out
+//                    (wkv7_cuda.cu:24-40 with T = 1), GroupNorm + bonus + gate (:192-195)
+//   gemm   columns   output projection
+//   ln2    rows      x2 = x + att, LayerNorm2, token shift, one lerp                                             :224-226
+//   gemm   columns   channel-mix key projection, relu^2 in the epilogue                                             :228
+//   gemm   columns   channel-mix value projection, split-K over 1024-wide chunks -> fp32 partials                   :230
+// then the final norm, the vocabulary head, and (greedy) the arg-max with EOS handling on the device.
+//
+// Skinny GEMM (M = 32 rows): a unit is 8 output columns x the whole K; the 16 warps of a CTA split K, each keeps its slice
+// of the activations as mma.sync A fragments in registers (loaded once per phase from L2) and streams the weight rows
+// straight from HBM into B fragments -- W is [N, K] with K contiguous, which IS the "col" operand layout of
+// mma.m16n8k16, so no shared-memory staging: each lane loads 16 contiguous bytes of one row (8 rows x 64 bytes per warp and
+// load) and the k index inside a 32-wide block is permuted identically for A and B.  The 16 partial accumulators are
+// reduced through shared memory; the next unit's weight loads are already in flight while that happens.
+//
+// Rounding points are those of the decode path it replaces (bf16 after every projection, LoRA stage, lerp, norm), so the
+// two agree to the summation order of the projections; `generate(exact=True)` remains the bit-exact reference mode.
+#include "tc05.cuh"
+#include "wkv7_common.cuh"
+#include "../../include/rwkvtts_wkv7.h"
+
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+namespace rwkvtts {
+namespace dec {
+
+using tc05::clock_hi;
+
+constexpr int kThreads = 512, kWarps = 16, kRows = 32, kMaxJobs = 8, kMaxEos = 8, kMaxLora = 512;
+enum { kEpiBf16 = 0, kEpiTanh, kEpiSigmoid, kEpiSqRelu, kEpiF32, kEpiLogits };
+
+struct Job {
+    const bf16 *A;      // [32, lda] activations (rows >= B are zero)
+    const bf16 *W;      // [N, ldw], K contiguous
+    void *out;          // [32, ldo] bf16 or fp32
+    int lda, ldw, ldo, N, K, epi, tile0, pad_;
+};
+struct Phase {
+    Job job[kMaxJobs];
+    int njobs, tiles;
+};
+struct Layer {
+    Phase p2, p4, p6, p7;
+    const bf16 *ln1_w, *ln1_b, *ln2_w, *ln2_b, *mix[6], *ffn_mix;
+    const bf16 *up[4];              // LoRA up-projections [C, D]: w, a, v (null on layer 0), g
+    const bf16 *w0, *a0, *v0, *k_k, *k_a, *r_k, *gn_w, *gn_b;
+    float *state;                   // [B, H, 64, 64] value-major, advanced in place
+    bf16 *att_shift, *ffn_shift;    // [B, C] token-shift states, advanced in place
+};
+struct Desc {
+    int B, C, H, L, V, F, D[4], Dtot, nchunk;
+    float ln_eps, gn_eps;
+    const bf16 *emb, *ln0_w, *ln0_b, *lnf_w, *lnf_b;
+    Phase head;
+    unsigned *bar;                  // [0] arrivals of the grid barrier, [1] exits
+    long long *tok;                 // [32] next input token (written by the arg-max phase)
+    int *done;                      // [32]
+    bf16 *x, *x2, *att, *o, *Xf, *hN, *vfirst, *X, *rkv, *hl, *kf;
+    float *part, *logits;
+    Layer *layers;
+};
+struct StepArgs {
+    const long long *tok_in;        // [B] or null: read Desc::tok
+    long long *tok_out;             // [B] or null
+    long long eos[kMaxEos];
+    long long pad;
+    int n_eos, greedy, suppress_eos;
+};
+
+// ---- small device helpers ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float neg_softplus_neg(float z) {
+    const float y = -z;
+    return (y > 20.f) ? -y : -__logf(1.f + __expf(y));
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+// activations written by other CTAs earlier in this launch: L2 only (an L1 line could be stale)
+__device__ __forceinline__ float ld_act(const bf16 *p) {
+    const unsigned short u = __ldcg(reinterpret_cast<const unsigned short *>(p));
+    return __uint_as_float((unsigned)u << 16);
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+[[noreturn]] static __device__ __noinline__ void grid_die(unsigned epoch) {
+    unsigned long long *r = tc05::g_wd_rec;
+    if (r != nullptr) {
+        r[8 + (epoch % tc05::kWatchdogEntries)] = (1ull << 63) | (3ull << 60) |
+                                                  ((unsigned long long)(blockIdx.x & 0xffffffu) << 24) | (epoch & 0xffffffu);
+        r[0] = tc05::kWatchdogMagic;
+        __threadfence_system();
+    }
+    const long long t1 = clock64();
+    while (clock64() - t1 < 100000000ll) {}
+    __trap();
+    for (;;) {}
+}
+// Grid barrier on a monotonic arrival counter (cooperative launch: all CTAs are resident).  Bounded like the
+// mbarrier waits of the chunked kernels: a CTA that never arrives turns into a trap with a record, not a hung device.
+__device__ __forceinline__ void grid_sync(unsigned *bar, unsigned &epoch) {
+    __syncthreads();
+    epoch++;
+    if (threadIdx.x == 0) {
+        const unsigned target = epoch * gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        if (ld_acquire(bar) < target) {
+            const uint32_t t0 = clock_hi();
+            while (ld_acquire(bar) < target) {
+                if (clock_hi() - t0 >= 2u) grid_die(epoch);
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < kWarps; i++) t += red[i];
+    __syncthreads();
+    return t;
+}
+// LayerNorm of the row in xs[0..C) (each thread owns channels tid, tid + 512, ...): xs <- bf16(LN(xs) * w + b)
+__device__ __forceinline__ void row_layernorm(float *xs, int C, const bf16 *w, const bf16 *b, float eps, float *red) {
+    float s1 = 0.f;
+    for (int c = threadIdx.x; c < C; c += kThreads) s1 += xs[c];
+    const float mu = block_sum(s1, red) / (float)C;
+    float s2 = 0.f;
+    for (int c = threadIdx.x; c < C; c += kThreads) { const float d = xs[c] - mu; s2 = fmaf(d, d, s2); }
+    const float rstd = rsqrtf(block_sum(s2, red) / (float)C + eps);
+    for (int c = threadIdx.x; c < C; c += kThreads)
+        xs[c] = rbf((xs[c] - mu) * rstd * bf2f(w[c]) + (b != nullptr ? bf2f(b[c]) : 0.f));
+}
+
+// ---- row phases ----------------------------------------------------------------------------------------------------
+// sum of the channel-mix value projection's split-K partials, as the bf16 tensor the projection returns
+__device__ __forceinline__ float ffn_out(const Desc &D, int b, int c) {
+    float s = 0.f;
+    for (int kc = 0; kc < D.nchunk; kc++) s += __ldcg(D.part + ((size_t)kc * kRows + b) * D.C + c);
+    return rbf(s);
+}
+
+__device__ __noinline__ void phase_ln1(const Desc &D, const Layer &Ly, int l, const StepArgs &a, float *xs, float *red) {
+    const int C = D.C;
+    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
+        if (l == 0) {
+            const long long t = a.tok_in != nullptr ? a.tok_in[b] : __ldcg(D.tok + b);
+            const bf16 *e = D.emb + (size_t)t * C;
+            for (int c = threadIdx.x; c < C; c += kThreads) xs[c] = bf2f(e[c]);
+            if (D.ln0_w != nullptr) row_layernorm(xs, C, D.ln0_w, D.ln0_b, D.ln_eps, red);
+        } else {
+            for (int c = threadIdx.x; c < C; c += kThreads)
+                xs[c] = rbf(ld_act(D.x2 + (size_t)b * C + c) + ffn_out(D, b, c));
+        }
+        for (int c = threadIdx.x; c < C; c += kThreads) D.x[(size_t)b * C + c] = __float2bfloat16_rn(xs[c]);
+        row_layernorm(xs, C, Ly.ln1_w, Ly.ln1_b, D.ln_eps, red);
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            const float h = xs[c];
+            bf16 *ps = Ly.att_shift + (size_t)b * C + c;
+            const float xx = rbf(ld_act(ps) - h);                 // the reference rounds shift(x) - x to bf16
+#pragma unroll
+            for (int s = 0; s < 6; s++)
+                D.X[((size_t)s * kRows + b) * C + c] = __float2bfloat16_rn(fmaf(xx, bf2f(Ly.mix[s][c]), h));
+            *ps = __float2bfloat16_rn(h);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __noinline__ void phase_ln2(const Desc &D, const Layer &Ly, float *xs, float *red) {
+    const int C = D.C;
+    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            const float s = rbf(ld_act(D.x + (size_t)b * C + c) + ld_act(D.att + (size_t)b * C + c));
+            xs[c] = s;
+            D.x2[(size_t)b * C + c] = __float2bfloat16_rn(s);
+        }
+        row_layernorm(xs, C, Ly.ln2_w, Ly.ln2_b, D.ln_eps, red);
+        for (int c = threadIdx.x; c < C; c += kThreads) {
+            const float h = xs[c];
+            bf16 *ps = Ly.ffn_shift + (size_t)b * C + c;
+            const float xx = rbf(ld_act(ps) - h);
+            D.Xf[(size_t)b * C + c] = __float2bfloat16_rn(fmaf(xx, bf2f(Ly.ffn_mix[c]), h));
+            *ps = __float2bfloat16_rn(h);
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __noinline__ void phase_lnf(const Desc &D, float *xs, float *red) {
+    const int C = D.C;
+    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
+        for (int c = threadIdx.x; c < C; c += kThreads)
+            xs[c] = rbf(ld_act(D.x2 + (size_t)b * C + c) + ffn_out(D, b, c));
+        row_layernorm(xs, C, D.lnf_w, D.lnf_b, D.ln_eps, red);
+        for (int c = threadIdx.x; c < C; c += kThreads) D.hN[(size_t)b * C + c] = __float2bfloat16_rn(xs[c]);
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool is_eos(const StepArgs &a, long long t) {
+    bool e = false;
+#pragma unroll
+    for (int i = 0; i < kMaxEos; i++) e |= (i < a.n_eos && a.eos[i] == t);
+    return e;
+}
+
+// greedy sampling on the device: arg-max (lowest index on ties), EOS ids masked while `suppress_eos`, finished rows
+// padded, the finished flag updated (generate(): logits[:, eos] = -inf; where(done, pad, nxt); done |= isin(nxt, eos))
+__device__ __noinline__ void phase_argmax(const Desc &D, const StepArgs &a, float *red) {
+    int *redi = reinterpret_cast<int *>(red + kWarps);
+    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int n = threadIdx.x; n < D.V; n += kThreads) {
+            const float v = __ldcg(D.logits + (size_t)b * D.V + n);
+            if (a.suppress_eos && is_eos(a, n)) continue;
+            if (v > best || bi == 0x7fffffff) { best = v; bi = n; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; redi[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < kWarps; i++)
+                if (red[i] > best || (red[i] == best && redi[i] < bi)) { best = red[i]; bi = redi[i]; }
+            const int was_done = __ldcg(D.done + b);
+            const long long t = was_done ? a.pad : (long long)bi;
+            D.tok[b] = t;
+            if (a.tok_out != nullptr) a.tok_out[b] = t;
+            if (is_eos(a, t)) D.done[b] = 1;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- (b, head) phase: LoRA ups, decay / kk / a / k' / v', state update, GroupNorm + bonus + gate ---------------------------
+__device__ __forceinline__ void half_bar(int half) { asm volatile("bar.sync %0, 256;" :: "r"(1 + half) : "memory"); }
+
+__device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, int l, float *smem) {
+    const int half = threadIdx.x >> 8, t = threadIdx.x & 255, i = t >> 2, p = t & 3, lane = t & 31;
+    const bool lead = (t >> 5) == 0;                       // first warp of the half: the per-channel work
+    float *hls = smem + half * 1280, *los = hls + kMaxLora, *vec = los + 4 * kC, *ys = vec + 6 * kC;
+    const int C = D.C, H = D.H;
+    for (int u = blockIdx.x * 2 + half; u < D.B * H; u += gridDim.x * 2) {
+        const int b = u / H, h = u % H, c = h * kC + i;
+        float4 *srow = reinterpret_cast<float4 *>(Ly.state + ((size_t)u * kC + i) * kC + 4 * p);
+        float4 s4[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) s4[j] = __ldcg(srow + 4 * j);          // the long-latency loads first
+        for (int j = t; j < D.Dtot; j += 256) hls[j] = ld_act(D.hl + (size_t)b * D.Dtot + j);
+        half_bar(half);
+        int off = 0;
+#pragma unroll
+        for (int L = 0; L < 4; L++) {
+            const int Dl = D.D[L], n = Dl >> 2;
+            float acc = 0.f;
+            if (Ly.up[L] != nullptr) {
+                const bf16 *wrow = Ly.up[L] + (size_t)c * Dl + p * n;
+                const float *hv = hls + off + p * n;
+                for (int e = 0; e < n; e += 8) {
+                    float f[8];
+                    unpack8(ldg_nc_v4(wrow + e), f);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) acc = fmaf(f[q], hv[e + q], acc);
+                }
+            }
+            acc = quad_sum(acc);
+            if (p == 0) los[L * kC + i] = rbf(acc);
+            off += Dl;
+        }
+        half_bar(half);
+        float r2[2] = {0.f, 0.f}, k2[2] = {0.f, 0.f}, v2[2] = {0.f, 0.f}, g2[2] = {0.f, 0.f};
+        if (lead) {
+            float a2[2], u2[2], ss = 0.f;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int ci = 2 * lane + e, ch = h * kC + ci;
+                const size_t at = (size_t)b * C + ch;
+                r2[e] = ld_act(D.rkv + at);
+                k2[e] = ld_act(D.rkv + (size_t)kRows * C + at);
+                v2[e] = ld_act(D.rkv + (size_t)2 * kRows * C + at);
+                g2[e] = los[3 * kC + ci];
+                const float w = rbf(neg_softplus_neg(bf2f(Ly.w0[ch]) + los[ci]) - 0.5f);
+                vec[ci] = expf(-expf(w));                                                   // decay (wkv7_cuda.cu:24)
+                a2[e] = rbf(sigmoidf_(bf2f(Ly.a0[ch]) + los[kC + ci]));
+                u2[e] = k2[e] * bf2f(Ly.k_k[ch]);
+                ss = fmaf(u2[e], u2[e], ss);
+            }
+            ss = warp_sum(ss);
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int ci = 2 * lane + e, ch = h * kC + ci;
+                const float kk = rbf(u2[e] * inv);
+                if (l == 0) {
+                    D.vfirst[(size_t)b * C + ch] = __float2bfloat16_rn(v2[e]);
+                } else {
+                    const float vf = ld_act(D.vfirst + (size_t)b * C + ch);
+                    v2[e] = rbf(v2[e] + (vf - v2[e]) * sigmoidf_(bf2f(Ly.v0[ch]) + los[2 * kC + ci]));
+                }
+                k2[e] = rbf(k2[e] * (1.f + (a2[e] - 1.f) * bf2f(Ly.k_a[ch])));
+                vec[1 * kC + ci] = r2[e];
+                vec[2 * kC + ci] = k2[e];
+                vec[3 * kC + ci] = v2[e];
+                vec[4 * kC + ci] = -kk;
+                vec[5 * kC + ci] = rbf(kk * a2[e]);
+            }
+        }
+        half_bar(half);
+        {
+            float S[16];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { S[4 * j] = s4[j].x; S[4 * j + 1] = s4[j].y; S[4 * j + 2] = s4[j].z; S[4 * j + 3] = s4[j].w; }
+            float sa = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) sa = fmaf(S[j], vec[4 * kC + 16 * (j >> 2) + 4 * p + (j & 3)], sa);
+            sa = quad_sum(sa);
+            const float vi = vec[3 * kC + i];
+            float yy = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int cc = 16 * (j >> 2) + 4 * p + (j & 3);
+                S[j] = fmaf(S[j], vec[cc], fmaf(sa, vec[5 * kC + cc], vec[2 * kC + cc] * vi));
+                yy = fmaf(S[j], vec[1 * kC + cc], yy);
+            }
+            yy = quad_sum(yy);
+#pragma unroll
+            for (int j = 0; j < 4; j++) __stcg(srow + 4 * j, make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]));
+            if (p == 0) ys[i] = rbf(yy);
+        }
+        half_bar(half);
+        if (lead) {
+            const float y0 = ys[2 * lane], y1 = ys[2 * lane + 1];
+            const int ch = h * kC + 2 * lane;
+            const float mu = warp_sum(y0 + y1) * (1.f / kC);
+            const float d0 = y0 - mu, d1 = y1 - mu;
+            const float rstd = rsqrtf(warp_sum(fmaf(d0, d0, d1 * d1)) * (1.f / kC) + D.gn_eps);
+            const float sb = warp_sum(fmaf(r2[0] * k2[0], bf2f(Ly.r_k[ch]), r2[1] * k2[1] * bf2f(Ly.r_k[ch + 1])));
+            const float o0 = (rbf(d0 * rstd * bf2f(Ly.gn_w[ch]) + bf2f(Ly.gn_b[ch])) + sb * v2[0]) * g2[0];
+            const float o1 = (rbf(d1 * rstd * bf2f(Ly.gn_w[ch + 1]) + bf2f(Ly.gn_b[ch + 1])) + sb * v2[1]) * g2[1];
+            *reinterpret_cast<uint32_t *>(D.o + (size_t)b * C + ch) = pack2(o0, o1);
+        }
+    }
+}
+
+// ---- skinny GEMM phase ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+struct TileRef { int job, n0, ntile; };
+__device__ __forceinline__ TileRef locate(const Phase &P, int t, int t1) {
+    TileRef r{0, 0, 0};
+    if (t >= t1) return r;
+    int j = 0;
+    while (j + 1 < P.njobs && t >= P.job[j + 1].tile0) j++;
+    const int lt = t - P.job[j].tile0, jt = (P.job[j].N + 7) >> 3;
+    r.job = j;
+    r.n0 = lt * 8;
+    r.ntile = min(2, min(jt - lt, t1 - t));
+    return r;
+}
+template <int NKB>
+__device__ __forceinline__ void load_w(const Job &J, const TileRef &r, int warp, int g, int q, uint4 (&wv)[2][NKB]) {
+#pragma unroll
+    for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+        for (int kb = 0; kb < NKB; kb++) {
+            const int kblk = warp * NKB + kb, n = r.n0 + tt * 8 + g;
+            const bool ok = tt < r.ntile && n < J.N && kblk * 32 < J.K;
+            wv[tt][kb] = ok ? ldg_nc_v4(J.W + (size_t)n * J.ldw + kblk * 32 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+}
+
+template <int NKB>
+__device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int t0 = (int)((long long)blockIdx.x * P.tiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * P.tiles / gridDim.x);
+    uint32_t af[NKB][2][2][4];      // [k block][m tile][mma of the block][a0..a3], already in the instruction's register order
+    uint4 wv[2][NKB];
+    int a_job = -1, t = t0;
+    TileRef cur = locate(P, t, t1);
+    if (cur.ntile) load_w<NKB>(P.job[cur.job], cur, warp, g, q, wv);
+    while (cur.ntile) {
+        const Job &J = P.job[cur.job];
+        if (cur.job != a_job) {
+            a_job = cur.job;
+#pragma unroll
+            for (int kb = 0; kb < NKB; kb++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    const int kblk = warp * NKB + kb, row = mt * 16 + g;
+                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;          // rows g and g + 8 of the m tile
+                    if (kblk * 32 < J.K) {
+                        const bf16 *src = J.A + (size_t)row * J.lda + kblk * 32 + q * 8;
+                        lo = __ldcg(reinterpret_cast<const uint4 *>(src));
+                        hi = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)8 * J.lda));
+                    }
+                    // physical k = 8q + 4j + {0,1} <-> logical k = 2q + {0,1}; 8q + 4j + {2,3} <-> 2q + 8 + {0,1} (mma j = 0, 1)
+                    af[kb][mt][0][0] = lo.x; af[kb][mt][0][1] = hi.x; af[kb][mt][0][2] = lo.y; af[kb][mt][0][3] = hi.y;
+                    af[kb][mt][1][0] = lo.z; af[kb][mt][1][1] = hi.z; af[kb][mt][1][2] = lo.w; af[kb][mt][1][3] = hi.w;
+                }
+        }
+        float acc[2][2][4];
+#pragma unroll
+        for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[tt][mt][j] = 0.f;
+#pragma unroll
+        for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+            for (int kb = 0; kb < NKB; kb++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    mma_bf16(acc[tt][mt], af[kb][mt][0], wv[tt][kb].x, wv[tt][kb].y);
+                    mma_bf16(acc[tt][mt], af[kb][mt][1], wv[tt][kb].z, wv[tt][kb].w);
+                }
+        const TileRef nxt = locate(P, t + cur.ntile, t1);
+        if (nxt.ntile) load_w<NKB>(P.job[nxt.job], nxt, warp, g, q, wv);          // in flight during the reduction
+#pragma unroll
+        for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+                *reinterpret_cast<float4 *>(red + ((warp * 2 + tt) * 2 + mt) * 128 + lane * 4) =
+                    make_float4(acc[tt][mt][0], acc[tt][mt][1], acc[tt][mt][2], acc[tt][mt][3]);
+        __syncthreads();
+        {
+            const int tt = threadIdx.x >> 8, idx = threadIdx.x & 255;
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) s += red[(w * 2 + tt) * 256 + idx];
+            const int mt = idx >> 7, ln = (idx >> 2) & 31, j = idx & 3;
+            const int row = mt * 16 + (ln >> 2) + ((j >> 1) << 3), n = cur.n0 + tt * 8 + (ln & 3) * 2 + (j & 1);
+            if (tt < cur.ntile && row < B && n < J.N) {
+                const size_t at = (size_t)row * J.ldo + n;
+                if (J.epi == kEpiF32) {
+                    static_cast<float *>(J.out)[at] = s;
+                } else if (J.epi == kEpiLogits) {
+                    static_cast<float *>(J.out)[at] = rbf(s);
+                } else {
+                    float v = rbf(s);
+                    if (J.epi == kEpiTanh) v = tanhf(v);
+                    else if (J.epi == kEpiSigmoid) v = 1.f / (1.f + expf(-v));
+                    else if (J.epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
+                    static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
+                }
+            }
+        }
+        __syncthreads();
+        t += cur.ntile;
+        cur = nxt;
+    }
+}
+
+template <int NKB>
+__global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__restrict__ Dp, const StepArgs a) {
+    __shared__ __align__(16) float smem[kWarps * 512 + 64];
+    const Desc &D = *Dp;
+    float *red_rows = smem + kWarps * 512;      // scratch of the row phases' reductions (xs = smem[0..C))
+    unsigned epoch = 0;
+    for (int l = 0; l < D.L; l++) {
+        const Layer &Ly = D.layers[l];
+        phase_ln1(D, Ly, l, a, smem, red_rows);
+        grid_sync(D.bar, epoch);
+        phase_gemm<NKB>(Ly.p2, D.B, smem);
+        grid_sync(D.bar, epoch);
+        phase_wkv(D, Ly, l, smem);
+        grid_sync(D.bar, epoch);
+        phase_gemm<NKB>(Ly.p4, D.B, smem);
+        grid_sync(D.bar, epoch);
+        phase_ln2(D, Ly, smem, red_rows);
+        grid_sync(D.bar, epoch);
+        phase_gemm<NKB>(Ly.p6, D.B, smem);
+        grid_sync(D.bar, epoch);
+        phase_gemm<NKB>(Ly.p7, D.B, smem);
+        grid_sync(D.bar, epoch);
+    }
+    phase_lnf(D, smem, red_rows);
+    grid_sync(D.bar, epoch);
+    phase_gemm<NKB>(D.head, D.B, smem);
+    if (a.greedy) {
+        grid_sync(D.bar, epoch);
+        phase_argmax(D, a, red_rows);
+    }
+    // the last CTA out resets the counters for the next launch (every CTA has left its last barrier by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(D.bar + 1, 1u) == gridDim.x - 1) {
+            D.bar[0] = 0u;
+            D.bar[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------------
+struct HostInfo { int grid, nkb, device; };
+static std::mutex g_mu;
+static std::unordered_map<void *, HostInfo> g_plans;
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+struct Layout {
+    size_t desc, layers, bar, tok, done, x, x2, att, o, Xf, hN, vfirst, X, rkv, hl, kf, part, logits, total;
+};
+static Layout layout(const int *d) {
+    const size_t B32 = kRows, C = d[RWKVTTS_DEC_C], L = d[RWKVTTS_DEC_L], V = d[RWKVTTS_DEC_V], F = d[RWKVTTS_DEC_F];
+    const size_t Dtot = (size_t)d[RWKVTTS_DEC_DW] + d[RWKVTTS_DEC_DA] + d[RWKVTTS_DEC_DV] + d[RWKVTTS_DEC_DG];
+    Layout o{};
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t r = at; at = align_up(at + bytes); return r; };
+    o.desc = take(sizeof(Desc));
+    o.layers = take(sizeof(Layer) * L);
+    o.bar = take(256);
+    o.tok = take(sizeof(long long) * B32);
+    o.done = take(sizeof(int) * B32);
+    const size_t row = B32 * C * sizeof(bf16);
+    o.x = take(row); o.x2 = take(row); o.att = take(row); o.o = take(row); o.Xf = take(row); o.hN = take(row);
+    o.vfirst = take(row);
+    o.X = take(6 * row);
+    o.rkv = take(3 * row);
+    o.hl = take(B32 * Dtot * sizeof(bf16));
+    o.kf = take(B32 * F * sizeof(bf16));
+    o.part = take((F / C) * B32 * C * sizeof(float));
+    o.logits = take(B32 * V * sizeof(float));
+    o.total = at;
+    return o;
+}
+static bool dims_ok(const int *d) {
+    const int B = d[RWKVTTS_DEC_B], C = d[RWKVTTS_DEC_C], H = d[RWKVTTS_DEC_H], L = d[RWKVTTS_DEC_L], V = d[RWKVTTS_DEC_V],
+              F = d[RWKVTTS_DEC_F];
+    if (B < 1 || B > kRows || H < 1 || C != H * kC || C % 32 != 0 || C > 2048 || L < 1 || V < 1 || F < C || F % C != 0 ||
+        F / C > kMaxJobs)
+        return false;
+    int tot = 0;
+    for (int i = RWKVTTS_DEC_DW; i <= RWKVTTS_DEC_DG; i++) {
+        if (d[i] < 32 || d[i] % 32 != 0) return false;
+        tot += d[i];
+    }
+    return tot <= kMaxLora;
+}
+static void add_job(Phase &P, const void *A, int lda, const void *W, int ldw, void *out, int ldo, int N, int K, int epi) {
+    Job &J = P.job[P.njobs++];
+    J.A = static_cast<const bf16 *>(A); J.W = static_cast<const bf16 *>(W); J.out = out;
+    J.lda = lda; J.ldw = ldw; J.ldo = ldo; J.N = N; J.K = K; J.epi = epi; J.tile0 = P.tiles; J.pad_ = 0;
+    P.tiles += (N + 7) / 8;
+}
+
+cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, const void *const *lp, void *ws, cudaStream_t st) {
+    const Layout lo = layout(d);
+    const int B = d[RWKVTTS_DEC_B], C = d[RWKVTTS_DEC_C], L = d[RWKVTTS_DEC_L], V = d[RWKVTTS_DEC_V], F = d[RWKVTTS_DEC_F];
+    (void)B;
+    char *base = static_cast<char *>(ws);
+    std::vector<char> host(lo.bar, 0);
+    Desc &D = *reinterpret_cast<Desc *>(host.data() + lo.desc);
+    Layer *Ls = reinterpret_cast<Layer *>(host.data() + lo.layers);
+    D.B = d[RWKVTTS_DEC_B]; D.C = C; D.H = d[RWKVTTS_DEC_H]; D.L = L; D.V = V; D.F = F;
+    D.Dtot = 0;
+    for (int i = 0; i < 4; i++) { D.D[i] = d[RWKVTTS_DEC_DW + i]; D.Dtot += D.D[i]; }
+    D.nchunk = F / C;
+    D.ln_eps = eps[0]; D.gn_eps = eps[1];
+    auto bp = [](const void *p) { return static_cast<const bf16 *>(p); };
+    D.emb = bp(mp[RWKVTTS_DEC_EMB]); D.ln0_w = bp(mp[RWKVTTS_DEC_LN0_W]); D.ln0_b = bp(mp[RWKVTTS_DEC_LN0_B]);
+    D.lnf_w = bp(mp[RWKVTTS_DEC_LNF_W]); D.lnf_b = bp(mp[RWKVTTS_DEC_LNF_B]);
+    auto dev = [&](size_t off) { return static_cast<void *>(base + off); };
+    D.bar = static_cast<unsigned *>(dev(lo.bar));
+    D.tok = static_cast<long long *>(dev(lo.tok));
+    D.done = static_cast<int *>(dev(lo.done));
+    D.x = (bf16 *)dev(lo.x); D.x2 = (bf16 *)dev(lo.x2); D.att = (bf16 *)dev(lo.att); D.o = (bf16 *)dev(lo.o);
+    D.Xf = (bf16 *)dev(lo.Xf); D.hN = (bf16 *)dev(lo.hN); D.vfirst = (bf16 *)dev(lo.vfirst); D.X = (bf16 *)dev(lo.X);
+    D.rkv = (bf16 *)dev(lo.rkv); D.hl = (bf16 *)dev(lo.hl); D.kf = (bf16 *)dev(lo.kf);
+    D.part = (float *)dev(lo.part); D.logits = (float *)dev(lo.logits);
+    D.layers = static_cast<Layer *>(dev(lo.layers));
+    const size_t RC = (size_t)kRows * C;
+    for (int l = 0; l < L; l++) {
+        const void *const *p = lp + (size_t)l * RWKVTTS_DEC_NPTR;
+        Layer &Y = Ls[l];
+        Y.ln1_w = bp(p[RWKVTTS_DEC_LN1_W]); Y.ln1_b = bp(p[RWKVTTS_DEC_LN1_B]);
+        Y.ln2_w = bp(p[RWKVTTS_DEC_LN2_W]); Y.ln2_b = bp(p[RWKVTTS_DEC_LN2_B]);
+        for (int s = 0; s < 6; s++) Y.mix[s] = bp(p[RWKVTTS_DEC_X_R + s]);
+        Y.ffn_mix = bp(p[RWKVTTS_DEC_FFN_X_K]);
+        Y.up[0] = bp(p[RWKVTTS_DEC_W2]); Y.up[1] = bp(p[RWKVTTS_DEC_A2]); Y.up[2] = bp(p[RWKVTTS_DEC_V2]); Y.up[3] = bp(p[RWKVTTS_DEC_G2]);
+        Y.w0 = bp(p[RWKVTTS_DEC_W0]); Y.a0 = bp(p[RWKVTTS_DEC_A0]); Y.v0 = bp(p[RWKVTTS_DEC_V0]);
+        Y.k_k = bp(p[RWKVTTS_DEC_K_K]); Y.k_a = bp(p[RWKVTTS_DEC_K_A]); Y.r_k = bp(p[RWKVTTS_DEC_R_K]);
+        Y.gn_w = bp(p[RWKVTTS_DEC_GN_W]); Y.gn_b = bp(p[RWKVTTS_DEC_GN_B]);
+        Y.state = static_cast<float *>(const_cast<void *>(p[RWKVTTS_DEC_STATE]));
+        Y.att_shift = static_cast<bf16 *>(const_cast<void *>(p[RWKVTTS_DEC_ATT_SHIFT]));
+        Y.ffn_shift = static_cast<bf16 *>(const_cast<void *>(p[RWKVTTS_DEC_FFN_SHIFT]));
+        // X slots: 0 r, 1 w, 2 k, 3 v, 4 a, 5 g
+        add_job(Y.p2, D.X + 0 * RC, C, p[RWKVTTS_DEC_W_R], C, D.rkv + 0 * RC, C, C, C, kEpiBf16);
+        add_job(Y.p2, D.X + 2 * RC, C, p[RWKVTTS_DEC_W_K], C, D.rkv + 1 * RC, C, C, C, kEpiBf16);
+        add_job(Y.p2, D.X + 3 * RC, C, p[RWKVTTS_DEC_W_V], C, D.rkv + 2 * RC, C, C, C, kEpiBf16);
+        int off = 0;
+        add_job(Y.p2, D.X + 1 * RC, C, p[RWKVTTS_DEC_W1], C, D.hl + off, D.Dtot, D.D[0], C, kEpiTanh); off += D.D[0];
+        add_job(Y.p2, D.X + 4 * RC, C, p[RWKVTTS_DEC_A1], C, D.hl + off, D.Dtot, D.D[1], C, kEpiBf16); off += D.D[1];
+        if (p[RWKVTTS_DEC_V1] != nullptr)
+            add_job(Y.p2, D.X + 3 * RC, C, p[RWKVTTS_DEC_V1], C, D.hl + off, D.Dtot, D.D[2], C, kEpiBf16);
+        off += D.D[2];
+        add_job(Y.p2, D.X + 5 * RC, C, p[RWKVTTS_DEC_G1], C, D.hl + off, D.Dtot, D.D[3], C, kEpiSigmoid);
+        add_job(Y.p4, D.o, C, p[RWKVTTS_DEC_W_O], C, D.att, C, C, C, kEpiBf16);
+        add_job(Y.p6, D.Xf, C, p[RWKVTTS_DEC_FFN_KEY], C, D.kf, F, F, C, kEpiSqRelu);
+        for (int kc = 0; kc < D.nchunk; kc++)
+            add_job(Y.p7, D.kf + (size_t)kc * C, F, bp(p[RWKVTTS_DEC_FFN_VALUE]) + (size_t)kc * C, F,
+                    D.part + (size_t)kc * RC, C, C, C, kEpiF32);
+    }
+    add_job(D.head, D.hN, C, mp[RWKVTTS_DEC_HEAD], C, D.logits, V, V, C, kEpiLogits);
+
+    cudaError_t e = cudaMemsetAsync(ws, 0, lo.total, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(ws, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    HostInfo hi{};
+    if ((e = cudaGetDevice(&hi.device)) != cudaSuccess) return e;
+    int sms = 0, per_sm = 0;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hi.device)) != cudaSuccess) return e;
+    hi.nkb = C <= 1024 ? 2 : 4;
+    e = hi.nkb == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<2>, kThreads, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<4>, kThreads, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorCooperativeLaunchTooLarge;
+    hi.grid = sms;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_plans[ws] = hi;
+    return cudaSuccess;
+}
+
+cudaError_t decode_step(void *ws, const long long *tok_in, long long *tok_out, int greedy, int suppress_eos,
+                        const long long *eos, int n_eos, long long pad, cudaStream_t st) {
+    HostInfo hi{};
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_plans.find(ws);
+        if (it == g_plans.end()) return cudaErrorInvalidValue;
+        hi = it->second;
+    }
+    if (watchdog_needs_install(2, st)) {
+        cudaError_t e = tc05::watchdog_install(watchdog_record(), 3);
+        if (e != cudaSuccess) return e;
+    }
+    StepArgs a{};
+    a.tok_in = tok_in; a.tok_out = tok_out; a.pad = pad; a.greedy = greedy; a.suppress_eos = suppress_eos;
+    a.n_eos = n_eos < kMaxEos ? n_eos : kMaxEos;
+    for (int i = 0; i < a.n_eos; i++) a.eos[i] = eos[i];
+    const Desc *Dp = static_cast<const Desc *>(ws);
+    void *args[] = {(void *)&Dp, (void *)&a};
+    count_launch();
+    return hi.nkb == 2
+        ? cudaLaunchCooperativeKernel((const void *)decode_step_kernel<2>, dim3(hi.grid), dim3(kThreads), args, 0, st)
+        : cudaLaunchCooperativeKernel((const void *)decode_step_kernel<4>, dim3(hi.grid), dim3(kThreads), args, 0, st);
+}
+
+void decode_release(void *ws) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_plans.erase(ws);
+}
+
+size_t decode_workspace(const int *d, size_t *offs) {
+    if (!dims_ok(d)) return 0;
+    const Layout lo = layout(d);
+    if (offs != nullptr) { offs[0] = lo.logits; offs[1] = lo.tok; offs[2] = lo.done; }
+    return lo.total;
+}
+
+}  // namespace dec
+}  // namespace rwkvtts

@@ -219,14 +219,14 @@ def test_generate_cuda_graph_step_is_bit_exact_with_the_eager_step():
     ids = torch.randint(0, 97, (3, 16), device="cuda")
     a = m.generate(input_ids=ids, max_new_tokens=40, do_sample=False, eos_token_id=None, use_cuda_graph=False)
     b = m.generate(input_ids=ids, max_new_tokens=40, do_sample=False, eos_token_id=None, use_cuda_graph=True,
-                   return_dict_in_generate=True)
+                   use_megakernel=False, return_dict_in_generate=True)
     assert torch.equal(a, b["sequences"])
     assert b["past_key_values"].seen_tokens == 16 + 39
     # eos handling: rows that hit eos are padded, the others keep decoding; polling interval does not change the result
     eos = int(a[0, 20])
     c = m.generate(input_ids=ids, max_new_tokens=40, do_sample=False, eos_token_id=eos, pad_token_id=0, use_cuda_graph=False)
     d = m.generate(input_ids=ids, max_new_tokens=40, do_sample=False, eos_token_id=eos, pad_token_id=0, use_cuda_graph=True,
-                   eos_check_interval=8)
+                   use_megakernel=False, eos_check_interval=8)
     n = min(c.shape[1], d.shape[1])
     assert torch.equal(c[:, :n], d[:, :n]) and bool((d[:, n:] == 0).all() if d.shape[1] > n else True)
 
