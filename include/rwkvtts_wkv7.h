@@ -260,6 +260,13 @@ RWKVTTS_API int rwkvtts_decode_init(const int *dims, const float *eps, const voi
                                     const void *const *layer_ptrs, void *workspace, size_t workspace_bytes, void *stream);
 RWKVTTS_API int rwkvtts_decode_step(void *workspace, const long long *tok_in, long long *tok_out, int greedy,
                                     int suppress_eos, const long long *eos, int n_eos, long long pad, void *stream);
+/* The same step (logits only) with a time line: stamps (device u64 [n * 513 + 128], n = 8 L + 4; the last 128 words: cycle
+ * stamps of CTA 0 at marked points inside layer 1's phases) receives the GPU nanosecond
+ * timer of CTA 0 at kernel start ([0]) and after every grid barrier ([1..7 L + 1]: 7 per layer -- ln1, projections, wkv,
+ * output projection, ln2, channel-mix key, channel-mix value -- then the final norm); then, per barrier e and CTA c < 256,
+ * the arrival time at [n + 256 e + c] and the release time at [257 n + 256 e + c].  A tuning aid: the kernel is bound by
+ * latency per phase, and this separates barrier cost from imbalance between CTAs. */
+RWKVTTS_API int rwkvtts_decode_step_profile(void *workspace, const long long *tok_in, unsigned long long *stamps, void *stream);
 RWKVTTS_API int rwkvtts_decode_release(void *workspace);
 
 /* ---- fused elementwise kernels of the time-mix around the WKV-7 op ---------------------------------------------

@@ -65,6 +65,7 @@ SYMBOLS = {
     "rwkvtts_decode_init": (_i, [ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                  _vp, ctypes.c_size_t, _vp]),
     "rwkvtts_decode_step": (_i, [_vp, _vp, _vp, _i, _i, ctypes.POINTER(ctypes.c_longlong), _i, ctypes.c_longlong, _vp]),
+    "rwkvtts_decode_step_profile": (_i, [_vp, _vp, _vp, _vp]),
     "rwkvtts_decode_release": (_i, [_vp]),
 }
 

@@ -88,7 +88,7 @@ cudaError_t launch_ce_fwd_bwd(void *logits, long long rows, int V, long long ld,
 namespace dec {
 cudaError_t decode_init(const int *dims, const float *eps, const void *const *mp, const void *const *lp, void *ws, cudaStream_t st);
 cudaError_t decode_step(void *ws, const long long *tok_in, long long *tok_out, int greedy, int suppress_eos,
-                        const long long *eos, int n_eos, long long pad, cudaStream_t st);
+                        const long long *eos, int n_eos, long long pad, unsigned long long *prof, cudaStream_t st);
 void decode_release(void *ws);
 size_t decode_workspace(const int *dims, size_t *offs);
 }  // namespace dec
@@ -445,8 +445,13 @@ int rwkvtts_decode_step(void *workspace, const long long *tok_in, long long *tok
                         const long long *eos, int n_eos, long long pad, void *stream) {
     if (workspace == nullptr || (n_eos > 0 && eos == nullptr)) return RWKVTTS_ERR_NULL;
     if (n_eos < 0 || n_eos > 8) return RWKVTTS_ERR_SHAPE;
-    return finish(rwkvtts::dec::decode_step(workspace, tok_in, tok_out, greedy, suppress_eos, eos, n_eos, pad,
+    return finish(rwkvtts::dec::decode_step(workspace, tok_in, tok_out, greedy, suppress_eos, eos, n_eos, pad, nullptr,
                                             (cudaStream_t)stream));
+}
+
+int rwkvtts_decode_step_profile(void *workspace, const long long *tok_in, unsigned long long *stamps, void *stream) {
+    if (workspace == nullptr || stamps == nullptr) return RWKVTTS_ERR_NULL;
+    return finish(rwkvtts::dec::decode_step(workspace, tok_in, nullptr, 0, 0, nullptr, 0, 0, stamps, (cudaStream_t)stream));
 }
 
 int rwkvtts_decode_release(void *workspace) {

@@ -34,6 +34,8 @@
 #include "wkv7_common.cuh"
 #include "../../include/rwkvtts_wkv7.h"
 
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -45,7 +47,9 @@ namespace dec {
 using tc05::clock_hi;
 
 constexpr int kThreads = 512, kWarps = 16, kRows = 32, kMaxJobs = 8, kMaxEos = 8, kMaxLora = 512;
+constexpr int kRedFloats = kWarps * 512;        // 32 KB: GEMM reduction / row buffer / wkv scratch
 enum { kEpiBf16 = 0, kEpiTanh, kEpiSigmoid, kEpiSqRelu, kEpiF32, kEpiLogits };
+enum { kRowLn1 = 0, kRowLn2, kRowFinal };
 
 struct Job {
     const bf16 *A;      // [32, lda] activations (rows >= B are zero)
@@ -57,15 +61,17 @@ struct Phase {
     Job job[kMaxJobs];
     int njobs, tiles;
 };
-struct Layer {
+struct alignas(16) Layer {
     Phase p2, p4, p6, p7;
-    const bf16 *ln1_w, *ln1_b, *ln2_w, *ln2_b, *mix[6], *ffn_mix;
-    const bf16 *up[4];              // LoRA up-projections [C, D]: w, a, v (null on layer 0), g
-    const bf16 *w0, *a0, *v0, *k_k, *k_a, *r_k, *gn_w, *gn_b;
-    float *state;                   // [B, H, 64, 64] value-major, advanced in place
-    bf16 *att_shift, *ffn_shift;    // [B, C] token-shift states, advanced in place
+    const bf16 *ln1_w, *ln1_b, *mix[6];     // what the ln1 phase reads, contiguous with ...
+    bf16 *att_shift;                        // ... its token-shift state [B, C], advanced in place (9 pointers)
+    const bf16 *ln2_w, *ln2_b, *ffn_mix;
+    bf16 *ffn_shift;                        // (4 pointers: the ln2 phase)
+    const bf16 *up[4];                      // LoRA up-projections [C, D]: w, a, v (null on layer 0), g
+    const bf16 *w0, *a0, *v0, *k_k, *k_a, *r_k, *gn_w, *gn_b;      // (8 pointers: per-channel vectors of the wkv phase)
+    float *state;                           // [B, H, 64, 64] value-major, advanced in place
 };
-struct Desc {
+struct alignas(16) Desc {
     int B, C, H, L, V, F, D[4], Dtot, nchunk;
     float ln_eps, gn_eps;
     const bf16 *emb, *ln0_w, *ln0_b, *lnf_w, *lnf_b;
@@ -82,12 +88,20 @@ struct StepArgs {
     long long *tok_out;             // [B] or null
     long long eos[kMaxEos];
     long long pad;
+    unsigned long long *prof;       // null, or the time line described at rwkvtts_decode_step_profile
     int n_eos, greedy, suppress_eos;
+    int debug_skip;                 // tuning experiments only (env RWKVTTS_DECODE_SKIP): 1 skip the row phases, 2 skip wkv
 };
+
+// The kernel runs ~170 short phases per token, each through code the previous phases have pushed out of the 32 KB
+// instruction cache: straight-line code that runs once per phase costs an L2 fetch per 8 instructions, which is what the
+// first form of this kernel spent most of its time on (174 KB of code, 9 us per phase with a 1 us barrier).  So the phases
+// are out-of-line functions with rolled loops (`#pragma unroll 1` wherever a trip count is 1-4 anyway), rare paths (tanh,
+// sigmoid, arg-max, the watchdog) are kept out of the hot code, and loads are batched by hand where a rolled loop would
+// serialise their latencies.
 
 // ---- small device helpers ----------------------------------------------------------------------------------------
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float neg_softplus_neg(float z) {
     const float y = -z;
@@ -98,15 +112,30 @@ __device__ __forceinline__ float warp_sum(float x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
 }
-// activations written by other CTAs earlier in this launch: L2 only (an L1 line could be stale)
+// activations written by other CTAs earlier in this launch: L2 only (an L1 line could be stale); parameters: read-only path
 __device__ __forceinline__ float ld_act(const bf16 *p) {
-    const unsigned short u = __ldcg(reinterpret_cast<const unsigned short *>(p));
-    return __uint_as_float((unsigned)u << 16);
+    return __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short *>(p)) << 16);
 }
+__device__ __forceinline__ float2 ld_act2(const bf16 *p) {
+    const unsigned u = __ldcg(reinterpret_cast<const unsigned *>(p));
+    return make_float2(bf16_lo(u), bf16_hi(u));
+}
+__device__ __forceinline__ float2 ld_par2(const bf16 *p) {
+    const unsigned u = __ldg(reinterpret_cast<const unsigned *>(p));
+    return make_float2(bf16_lo(u), bf16_hi(u));
+}
+__device__ __forceinline__ void st2(bf16 *p, float a, float b) { *reinterpret_cast<uint32_t *>(p) = pack2(a, b); }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// tuning aid: cycle stamps of CTA 0 / thread 0 at marked points of the phases (null = off)
+#define PROF_POINT(fine, k) do { if ((fine) != nullptr && blockIdx.x == 0 && threadIdx.x == 0) (fine)[k] = clock64(); } while (0)
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 [[noreturn]] static __device__ __noinline__ void grid_die(unsigned epoch) {
     unsigned long long *r = tc05::g_wd_rec;
@@ -121,24 +150,32 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     __trap();
     for (;;) {}
 }
-// Grid barrier on a monotonic arrival counter (cooperative launch: all CTAs are resident).  Bounded like the
+// Grid barrier on a monotonic arrival counter (cooperative launch: all CTAs are resident): release-add by one thread
+// (cumulative over what the CTA wrote before the bar.sync), acquire-poll, ~1.0 us from the last arrival to the releases
+// (measured; a per-CTA flag written by the last arriver takes 2.0 us, a poll with back-off the same 1.0).  Bounded like the
 // mbarrier waits of the chunked kernels: a CTA that never arrives turns into a trap with a record, not a hung device.
-__device__ __forceinline__ void grid_sync(unsigned *bar, unsigned &epoch) {
+constexpr int kProfCtas = 256;      // profile layout: [n] CTA 0 after each barrier, then [n][256] arrivals, [n][256] releases
+__device__ __noinline__ unsigned grid_sync(unsigned *bar, unsigned epoch, unsigned long long *prof, int nprof) {
     __syncthreads();
     epoch++;
     if (threadIdx.x == 0) {
+        if (prof != nullptr && blockIdx.x < kProfCtas) prof[nprof + epoch * kProfCtas + blockIdx.x] = globaltimer();
         const unsigned target = epoch * gridDim.x;
-        __threadfence();
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
         if (ld_acquire(bar) < target) {
             const uint32_t t0 = clock_hi();
             while (ld_acquire(bar) < target) {
                 if (clock_hi() - t0 >= 2u) grid_die(epoch);
             }
         }
-        __threadfence();
+        if (prof != nullptr) {
+            const unsigned long long t = globaltimer();
+            if (blockIdx.x == 0) prof[epoch] = t;
+            if (blockIdx.x < kProfCtas) prof[nprof * (1 + kProfCtas) + epoch * kProfCtas + blockIdx.x] = t;
+        }
     }
     __syncthreads();
+    return epoch;
 }
 __device__ __forceinline__ float block_sum(float v, float *red) {
     v = warp_sum(v);
@@ -150,80 +187,93 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     __syncthreads();
     return t;
 }
-// LayerNorm of the row in xs[0..C) (each thread owns channels tid, tid + 512, ...): xs <- bf16(LN(xs) * w + b)
-__device__ __forceinline__ void row_layernorm(float *xs, int C, const bf16 *w, const bf16 *b, float eps, float *red) {
+// LayerNorm of the row in xs[0..C) (each thread owns the channel pairs 2 tid, 2 tid + 1024, ...): xs <- bf16(LN(xs) * w + b)
+__device__ __noinline__ void row_layernorm(float *xs, int C, const bf16 *w, const bf16 *b, float eps, float *red) {
     float s1 = 0.f;
-    for (int c = threadIdx.x; c < C; c += kThreads) s1 += xs[c];
+#pragma unroll 1
+    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) s1 += xs[c] + xs[c + 1];
     const float mu = block_sum(s1, red) / (float)C;
     float s2 = 0.f;
-    for (int c = threadIdx.x; c < C; c += kThreads) { const float d = xs[c] - mu; s2 = fmaf(d, d, s2); }
+#pragma unroll 1
+    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+        const float d0 = xs[c] - mu, d1 = xs[c + 1] - mu;
+        s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+    }
     const float rstd = rsqrtf(block_sum(s2, red) / (float)C + eps);
-    for (int c = threadIdx.x; c < C; c += kThreads)
-        xs[c] = rbf((xs[c] - mu) * rstd * bf2f(w[c]) + (b != nullptr ? bf2f(b[c]) : 0.f));
+#pragma unroll 1
+    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+        const float2 wv = ld_par2(w + c), bv = b != nullptr ? ld_par2(b + c) : make_float2(0.f, 0.f);
+        xs[c] = rbf((xs[c] - mu) * rstd * wv.x + bv.x);
+        xs[c + 1] = rbf((xs[c + 1] - mu) * rstd * wv.y + bv.y);
+    }
 }
 
-// ---- row phases ----------------------------------------------------------------------------------------------------
-// sum of the channel-mix value projection's split-K partials, as the bf16 tensor the projection returns
-__device__ __forceinline__ float ffn_out(const Desc &D, int b, int c) {
-    float s = 0.f;
-    for (int kc = 0; kc < D.nchunk; kc++) s += __ldcg(D.part + ((size_t)kc * kRows + b) * D.C + c);
-    return rbf(s);
-}
-
-__device__ __noinline__ void phase_ln1(const Desc &D, const Layer &Ly, int l, const StepArgs &a, float *xs, float *red) {
+// ---- row phases: ln1 (+ embedding / previous layer's channel-mix sum), ln2, final norm -------------------------------------------
+__device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind, bool first_layer, const StepArgs &a, float *xs,
+                                        float *red) {
     const int C = D.C;
+#pragma unroll 1
     for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
-        if (l == 0) {
+        const size_t rb = (size_t)b * C;
+        if (kind == kRowLn1 && first_layer) {
             const long long t = a.tok_in != nullptr ? a.tok_in[b] : __ldcg(D.tok + b);
             const bf16 *e = D.emb + (size_t)t * C;
-            for (int c = threadIdx.x; c < C; c += kThreads) xs[c] = bf2f(e[c]);
+#pragma unroll 1
+            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+                const float2 v = ld_par2(e + c);
+                xs[c] = v.x; xs[c + 1] = v.y;
+            }
             if (D.ln0_w != nullptr) row_layernorm(xs, C, D.ln0_w, D.ln0_b, D.ln_eps, red);
+        } else if (kind == kRowLn2) {
+#pragma unroll 1
+            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+                const float2 x = ld_act2(D.x + rb + c), t = ld_act2(D.att + rb + c);
+                xs[c] = rbf(x.x + t.x); xs[c + 1] = rbf(x.y + t.y);
+            }
         } else {
-            for (int c = threadIdx.x; c < C; c += kThreads)
-                xs[c] = rbf(ld_act(D.x2 + (size_t)b * C + c) + ffn_out(D, b, c));
-        }
-        for (int c = threadIdx.x; c < C; c += kThreads) D.x[(size_t)b * C + c] = __float2bfloat16_rn(xs[c]);
-        row_layernorm(xs, C, Ly.ln1_w, Ly.ln1_b, D.ln_eps, red);
-        for (int c = threadIdx.x; c < C; c += kThreads) {
-            const float h = xs[c];
-            bf16 *ps = Ly.att_shift + (size_t)b * C + c;
-            const float xx = rbf(ld_act(ps) - h);                 // the reference rounds shift(x) - x to bf16
+            // x2 + the channel-mix value projection: its split-K partials are summed here, as the bf16 tensor it returns
+#pragma unroll 1
+            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+                const float2 x = ld_act2(D.x2 + rb + c);
+                float2 pv[kMaxJobs];
 #pragma unroll
-            for (int s = 0; s < 6; s++)
-                D.X[((size_t)s * kRows + b) * C + c] = __float2bfloat16_rn(fmaf(xx, bf2f(Ly.mix[s][c]), h));
-            *ps = __float2bfloat16_rn(h);
+                for (int kc = 0; kc < kMaxJobs; kc++)
+                    pv[kc] = kc < D.nchunk ? __ldcg(reinterpret_cast<const float2 *>(D.part + ((size_t)kc * kRows + b) * C + c))
+                                           : make_float2(0.f, 0.f);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int kc = 0; kc < kMaxJobs; kc++) { s0 += pv[kc].x; s1 += pv[kc].y; }
+                xs[c] = rbf(x.x + rbf(s0)); xs[c + 1] = rbf(x.y + rbf(s1));
+            }
         }
-        __syncthreads();
-    }
-}
-
-__device__ __noinline__ void phase_ln2(const Desc &D, const Layer &Ly, float *xs, float *red) {
-    const int C = D.C;
-    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
-        for (int c = threadIdx.x; c < C; c += kThreads) {
-            const float s = rbf(ld_act(D.x + (size_t)b * C + c) + ld_act(D.att + (size_t)b * C + c));
-            xs[c] = s;
-            D.x2[(size_t)b * C + c] = __float2bfloat16_rn(s);
+        bf16 *keep = (kind == kRowLn2 ? D.x2 : D.x) + rb;          // the residual stream
+#pragma unroll 1
+        for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) st2(keep + c, xs[c], xs[c + 1]);
+        if (kind == kRowLn1) row_layernorm(xs, C, Ly.ln1_w, Ly.ln1_b, D.ln_eps, red);
+        else if (kind == kRowLn2) row_layernorm(xs, C, Ly.ln2_w, Ly.ln2_b, D.ln_eps, red);
+        else row_layernorm(xs, C, D.lnf_w, D.lnf_b, D.ln_eps, red);
+        if (kind == kRowFinal) {
+#pragma unroll 1
+            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) st2(D.hN + rb + c, xs[c], xs[c + 1]);
+        } else {
+            bf16 *shift = (kind == kRowLn1 ? Ly.att_shift : Ly.ffn_shift) + rb;
+            const bf16 *const *mix = kind == kRowLn1 ? Ly.mix : &Ly.ffn_mix;
+            bf16 *out = (kind == kRowLn1 ? D.X : D.Xf) + rb;
+            const int n = kind == kRowLn1 ? 6 : 1;
+#pragma unroll 1
+            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
+                const float h0 = xs[c], h1 = xs[c + 1];
+                const float2 pr = ld_act2(shift + c);
+                float2 m[6];
+#pragma unroll
+                for (int s = 0; s < 6; s++) m[s] = s < n ? ld_par2(mix[s] + c) : make_float2(0.f, 0.f);
+                const float xx0 = rbf(pr.x - h0), xx1 = rbf(pr.y - h1);      // the reference rounds shift(x) - x to bf16
+#pragma unroll
+                for (int s = 0; s < 6; s++)
+                    if (s < n) st2(out + (size_t)s * kRows * C + c, fmaf(xx0, m[s].x, h0), fmaf(xx1, m[s].y, h1));
+                st2(shift + c, h0, h1);
+            }
         }
-        row_layernorm(xs, C, Ly.ln2_w, Ly.ln2_b, D.ln_eps, red);
-        for (int c = threadIdx.x; c < C; c += kThreads) {
-            const float h = xs[c];
-            bf16 *ps = Ly.ffn_shift + (size_t)b * C + c;
-            const float xx = rbf(ld_act(ps) - h);
-            D.Xf[(size_t)b * C + c] = __float2bfloat16_rn(fmaf(xx, bf2f(Ly.ffn_mix[c]), h));
-            *ps = __float2bfloat16_rn(h);
-        }
-        __syncthreads();
-    }
-}
-
-__device__ __noinline__ void phase_lnf(const Desc &D, float *xs, float *red) {
-    const int C = D.C;
-    for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
-        for (int c = threadIdx.x; c < C; c += kThreads)
-            xs[c] = rbf(ld_act(D.x2 + (size_t)b * C + c) + ffn_out(D, b, c));
-        row_layernorm(xs, C, D.lnf_w, D.lnf_b, D.ln_eps, red);
-        for (int c = threadIdx.x; c < C; c += kThreads) D.hN[(size_t)b * C + c] = __float2bfloat16_rn(xs[c]);
         __syncthreads();
     }
 }
@@ -271,77 +321,113 @@ __device__ __noinline__ void phase_argmax(const Desc &D, const StepArgs &a, floa
 // ---- (b, head) phase: LoRA ups, decay / kk / a / k' / v', state update, GroupNorm + bonus + gate ---------------------------
 __device__ __forceinline__ void half_bar(int half) { asm volatile("bar.sync %0, 256;" :: "r"(1 + half) : "memory"); }
 
-__device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, int l, float *smem) {
+// LoRA up-projection rows of unit u's head (64 rows x rank, contiguous in every [C, rank] matrix) -> shared memory of the
+// calling half, asynchronously: issued BEFORE the grid barrier that precedes the phase (they do not depend on the token)
+__device__ __noinline__ void stage_up(const Desc &D, const Layer &Ly, int u, bf16 *upw) {
+    if (u >= D.B * D.H) return;
+    const int h = u % D.H, t = threadIdx.x & 255;
+    int off = 0;
+#pragma unroll 1
+    for (int L = 0; L < 4; L++) {
+        const int Dl = D.D[L];
+        if (Ly.up[L] != nullptr) {
+            const char *src = reinterpret_cast<const char *>(Ly.up[L] + (size_t)h * kC * Dl);
+            char *dst = reinterpret_cast<char *>(upw + (size_t)kC * off);
+#pragma unroll 1
+            for (int i = t * 16; i < kC * Dl * 2; i += 256 * 16) tc05::cp_async16(dst + i, src + i);
+        }
+        off += Dl;
+    }
+}
+
+__device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool first_layer, float *smem, bf16 *upw_all,
+                                       long long *fine) {
     const int half = threadIdx.x >> 8, t = threadIdx.x & 255, i = t >> 2, p = t & 3, lane = t & 31;
     const bool lead = (t >> 5) == 0;                       // first warp of the half: the per-channel work
     float *hls = smem + half * 1280, *los = hls + kMaxLora, *vec = los + 4 * kC, *ys = vec + 6 * kC;
-    const int C = D.C, H = D.H;
-    for (int u = blockIdx.x * 2 + half; u < D.B * H; u += gridDim.x * 2) {
-        const int b = u / H, h = u % H, c = h * kC + i;
+    bf16 *upw = upw_all + (size_t)half * kC * D.Dtot;
+    const int C = D.C, H = D.H, BH = D.B * D.H;
+#pragma unroll 1
+    for (int u = blockIdx.x * 2 + half; u < BH; u += gridDim.x * 2) {
+        const int b = u / H, h = u % H;
+        PROF_POINT(fine, 0);
         float4 *srow = reinterpret_cast<float4 *>(Ly.state + ((size_t)u * kC + i) * kC + 4 * p);
         float4 s4[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) s4[j] = __ldcg(srow + 4 * j);          // the long-latency loads first
+#pragma unroll 1
         for (int j = t; j < D.Dtot; j += 256) hls[j] = ld_act(D.hl + (size_t)b * D.Dtot + j);
-        half_bar(half);
-        int off = 0;
-#pragma unroll
-        for (int L = 0; L < 4; L++) {
-            const int Dl = D.D[L], n = Dl >> 2;
-            float acc = 0.f;
-            if (Ly.up[L] != nullptr) {
-                const bf16 *wrow = Ly.up[L] + (size_t)c * Dl + p * n;
-                const float *hv = hls + off + p * n;
-                for (int e = 0; e < n; e += 8) {
-                    float f[8];
-                    unpack8(ldg_nc_v4(wrow + e), f);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) acc = fmaf(f[q], hv[e + q], acc);
-                }
-            }
-            acc = quad_sum(acc);
-            if (p == 0) los[L * kC + i] = rbf(acc);
-            off += Dl;
-        }
-        half_bar(half);
-        float r2[2] = {0.f, 0.f}, k2[2] = {0.f, 0.f}, v2[2] = {0.f, 0.f}, g2[2] = {0.f, 0.f};
+        // the lead warp's operands (two channels per lane), all in flight together
+        const size_t at = (size_t)b * C + h * kC + 2 * lane;
+        const int ch = h * kC + 2 * lane;
+        float2 r2, k2, v2, vf, w0, a0, kk_, ka, v0, rk, gw, gb;
         if (lead) {
-            float a2[2], u2[2], ss = 0.f;
+            r2 = ld_act2(D.rkv + at);
+            k2 = ld_act2(D.rkv + (size_t)kRows * C + at);
+            v2 = ld_act2(D.rkv + (size_t)2 * kRows * C + at);
+            vf = first_layer ? make_float2(0.f, 0.f) : ld_act2(D.vfirst + at);
+            w0 = ld_par2(Ly.w0 + ch); a0 = ld_par2(Ly.a0 + ch); kk_ = ld_par2(Ly.k_k + ch); ka = ld_par2(Ly.k_a + ch);
+            v0 = first_layer ? make_float2(0.f, 0.f) : ld_par2(Ly.v0 + ch);
+            rk = ld_par2(Ly.r_k + ch); gw = ld_par2(Ly.gn_w + ch);
+            gb = Ly.gn_b != nullptr ? ld_par2(Ly.gn_b + ch) : make_float2(0.f, 0.f);
+        }
+        PROF_POINT(fine, 1);
+        tc05::cp_async_wait<0>();                                            // this half's up-projection rows
+        half_bar(half);
+        PROF_POINT(fine, 2);
+        {
+            int off = 0;
+#pragma unroll 1
+            for (int L = 0; L < 4; L++) {
+                const int Dl = D.D[L], n = Dl >> 2;
+                float acc = 0.f;
+                if (Ly.up[L] != nullptr) {
+                    const bf16 *wrow = upw + (size_t)kC * off + (size_t)i * Dl + p * n;
+                    const float *hv = hls + off + p * n;
+#pragma unroll 1
+                    for (int e = 0; e < n; e += 8) {
+                        float f[8];
+                        unpack8(*reinterpret_cast<const uint4 *>(wrow + e), f);
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int ci = 2 * lane + e, ch = h * kC + ci;
-                const size_t at = (size_t)b * C + ch;
-                r2[e] = ld_act(D.rkv + at);
-                k2[e] = ld_act(D.rkv + (size_t)kRows * C + at);
-                v2[e] = ld_act(D.rkv + (size_t)2 * kRows * C + at);
-                g2[e] = los[3 * kC + ci];
-                const float w = rbf(neg_softplus_neg(bf2f(Ly.w0[ch]) + los[ci]) - 0.5f);
-                vec[ci] = expf(-expf(w));                                                   // decay (wkv7_cuda.cu:24)
-                a2[e] = rbf(sigmoidf_(bf2f(Ly.a0[ch]) + los[kC + ci]));
-                u2[e] = k2[e] * bf2f(Ly.k_k[ch]);
-                ss = fmaf(u2[e], u2[e], ss);
-            }
-            ss = warp_sum(ss);
-            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const int ci = 2 * lane + e, ch = h * kC + ci;
-                const float kk = rbf(u2[e] * inv);
-                if (l == 0) {
-                    D.vfirst[(size_t)b * C + ch] = __float2bfloat16_rn(v2[e]);
-                } else {
-                    const float vf = ld_act(D.vfirst + (size_t)b * C + ch);
-                    v2[e] = rbf(v2[e] + (vf - v2[e]) * sigmoidf_(bf2f(Ly.v0[ch]) + los[2 * kC + ci]));
+                        for (int q = 0; q < 8; q++) acc = fmaf(f[q], hv[e + q], acc);
+                    }
                 }
-                k2[e] = rbf(k2[e] * (1.f + (a2[e] - 1.f) * bf2f(Ly.k_a[ch])));
-                vec[1 * kC + ci] = r2[e];
-                vec[2 * kC + ci] = k2[e];
-                vec[3 * kC + ci] = v2[e];
-                vec[4 * kC + ci] = -kk;
-                vec[5 * kC + ci] = rbf(kk * a2[e]);
+                acc = quad_sum(acc);
+                if (p == 0) los[L * kC + i] = rbf(acc);
+                off += Dl;
             }
         }
         half_bar(half);
+        PROF_POINT(fine, 3);
+        stage_up(D, Ly, u + gridDim.x * 2, upw);                              // next round's rows, behind the rest of this one
+        tc05::cp_async_commit();
+        PROF_POINT(fine, 4);
+        float g0 = 0.f, g1 = 0.f;
+        if (lead) {
+            const int c0 = 2 * lane, c1 = c0 + 1;
+            g0 = los[3 * kC + c0]; g1 = los[3 * kC + c1];
+            const float wa = rbf(neg_softplus_neg(w0.x + los[c0]) - 0.5f), wb = rbf(neg_softplus_neg(w0.y + los[c1]) - 0.5f);
+            vec[c0] = expf(-expf(wa)); vec[c1] = expf(-expf(wb));                          // decay (wkv7_cuda.cu:24)
+            const float aa = rbf(sigmoidf_(a0.x + los[kC + c0])), ab = rbf(sigmoidf_(a0.y + los[kC + c1]));
+            const float ua = k2.x * kk_.x, ub = k2.y * kk_.y;
+            const float inv = 1.f / fmaxf(sqrtf(warp_sum(fmaf(ua, ua, ub * ub))), 1e-12f);
+            const float kka = rbf(ua * inv), kkb = rbf(ub * inv);
+            if (first_layer) {
+                st2(D.vfirst + at, v2.x, v2.y);
+            } else {
+                v2.x = rbf(v2.x + (vf.x - v2.x) * sigmoidf_(v0.x + los[2 * kC + c0]));
+                v2.y = rbf(v2.y + (vf.y - v2.y) * sigmoidf_(v0.y + los[2 * kC + c1]));
+            }
+            k2.x = rbf(k2.x * (1.f + (aa - 1.f) * ka.x));
+            k2.y = rbf(k2.y * (1.f + (ab - 1.f) * ka.y));
+            vec[1 * kC + c0] = r2.x; vec[1 * kC + c1] = r2.y;
+            vec[2 * kC + c0] = k2.x; vec[2 * kC + c1] = k2.y;
+            vec[3 * kC + c0] = v2.x; vec[3 * kC + c1] = v2.y;
+            vec[4 * kC + c0] = -kka; vec[4 * kC + c1] = -kkb;
+            vec[5 * kC + c0] = rbf(kka * aa); vec[5 * kC + c1] = rbf(kkb * ab);
+        }
+        half_bar(half);
+        PROF_POINT(fine, 5);
         {
             float S[16];
 #pragma unroll
@@ -364,17 +450,17 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, int l, fl
             if (p == 0) ys[i] = rbf(yy);
         }
         half_bar(half);
+        PROF_POINT(fine, 6);
         if (lead) {
             const float y0 = ys[2 * lane], y1 = ys[2 * lane + 1];
-            const int ch = h * kC + 2 * lane;
             const float mu = warp_sum(y0 + y1) * (1.f / kC);
             const float d0 = y0 - mu, d1 = y1 - mu;
             const float rstd = rsqrtf(warp_sum(fmaf(d0, d0, d1 * d1)) * (1.f / kC) + D.gn_eps);
-            const float sb = warp_sum(fmaf(r2[0] * k2[0], bf2f(Ly.r_k[ch]), r2[1] * k2[1] * bf2f(Ly.r_k[ch + 1])));
-            const float o0 = (rbf(d0 * rstd * bf2f(Ly.gn_w[ch]) + bf2f(Ly.gn_b[ch])) + sb * v2[0]) * g2[0];
-            const float o1 = (rbf(d1 * rstd * bf2f(Ly.gn_w[ch + 1]) + bf2f(Ly.gn_b[ch + 1])) + sb * v2[1]) * g2[1];
-            *reinterpret_cast<uint32_t *>(D.o + (size_t)b * C + ch) = pack2(o0, o1);
+            const float sb = warp_sum(fmaf(r2.x * k2.x, rk.x, r2.y * k2.y * rk.y));
+            st2(D.o + at, (rbf(d0 * rstd * gw.x + gb.x) + sb * v2.x) * g0, (rbf(d1 * rstd * gw.y + gb.y) + sb * v2.y) * g1);
         }
+        PROF_POINT(fine, 7);
+        if (fine != nullptr) fine += 8;                                       // next round: next 8 slots
     }
 }
 
@@ -388,6 +474,7 @@ __device__ __forceinline__ TileRef locate(const Phase &P, int t, int t1) {
     TileRef r{0, 0, 0};
     if (t >= t1) return r;
     int j = 0;
+#pragma unroll 1
     while (j + 1 < P.njobs && t >= P.job[j + 1].tile0) j++;
     const int lt = t - P.job[j].tile0, jt = (P.job[j].N + 7) >> 3;
     r.job = j;
@@ -406,17 +493,24 @@ __device__ __forceinline__ void load_w(const Job &J, const TileRef &r, int warp,
             wv[tt][kb] = ok ? ldg_nc_v4(J.W + (size_t)n * J.ldw + kblk * 32 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
         }
 }
+// the LoRA down-projections' activations: rare tiles, kept out of the hot code
+__device__ __noinline__ float epi_act(float v, int epi) {
+    return epi == kEpiTanh ? tanhf(v) : 1.f / (1.f + expf(-v));
+}
 
 template <int NKB>
-__device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red) {
+__device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red, long long *fine) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int t0 = (int)((long long)blockIdx.x * P.tiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * P.tiles / gridDim.x);
     uint32_t af[NKB][2][2][4];      // [k block][m tile][mma of the block][a0..a3], already in the instruction's register order
     uint4 wv[2][NKB];
     int a_job = -1, t = t0;
+    PROF_POINT(fine, 0);
     TileRef cur = locate(P, t, t1);
     if (cur.ntile) load_w<NKB>(P.job[cur.job], cur, warp, g, q, wv);
+#pragma unroll 1
     while (cur.ntile) {
+        PROF_POINT(fine, 1);
         const Job &J = P.job[cur.job];
         if (cur.job != a_job) {
             a_job = cur.job;
@@ -452,6 +546,7 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red) {
                     mma_bf16(acc[tt][mt], af[kb][mt][0], wv[tt][kb].x, wv[tt][kb].y);
                     mma_bf16(acc[tt][mt], af[kb][mt][1], wv[tt][kb].z, wv[tt][kb].w);
                 }
+        PROF_POINT(fine, 2);
         const TileRef nxt = locate(P, t + cur.ntile, t1);
         if (nxt.ntile) load_w<NKB>(P.job[nxt.job], nxt, warp, g, q, wv);          // in flight during the reduction
 #pragma unroll
@@ -461,6 +556,7 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red) {
                 *reinterpret_cast<float4 *>(red + ((warp * 2 + tt) * 2 + mt) * 128 + lane * 4) =
                     make_float4(acc[tt][mt][0], acc[tt][mt][1], acc[tt][mt][2], acc[tt][mt][3]);
         __syncthreads();
+        PROF_POINT(fine, 3);
         {
             const int tt = threadIdx.x >> 8, idx = threadIdx.x & 255;
             float s = 0.f;
@@ -470,53 +566,163 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red) {
             const int row = mt * 16 + (ln >> 2) + ((j >> 1) << 3), n = cur.n0 + tt * 8 + (ln & 3) * 2 + (j & 1);
             if (tt < cur.ntile && row < B && n < J.N) {
                 const size_t at = (size_t)row * J.ldo + n;
-                if (J.epi == kEpiF32) {
+                const int epi = J.epi;
+                if (epi == kEpiF32) {
                     static_cast<float *>(J.out)[at] = s;
-                } else if (J.epi == kEpiLogits) {
+                } else if (epi == kEpiLogits) {
                     static_cast<float *>(J.out)[at] = rbf(s);
                 } else {
                     float v = rbf(s);
-                    if (J.epi == kEpiTanh) v = tanhf(v);
-                    else if (J.epi == kEpiSigmoid) v = 1.f / (1.f + expf(-v));
-                    else if (J.epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
+                    if (epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
+                    else if (epi != kEpiBf16) v = epi_act(v, epi);
                     static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
                 }
             }
         }
         __syncthreads();
+        PROF_POINT(fine, 4);
+        if (fine != nullptr) fine += 4;
         t += cur.ntile;
         cur = nxt;
     }
 }
 
+// ---- L2 prefetch, one to two phases ahead ------------------------------------------------------------------------------
+// What a phase will read from HBM (weights, parameters, recurrent state: nothing of it depends on this token) is pulled
+// into L2 while the phases before it run, so that after a barrier only L2 latencies are left on the critical path.  One
+// bulk-prefetch instruction per contiguous span, executed by the copy engine: a `prefetch.global.L2` per 128-byte line
+// costs the SM ~6 cycles each (measured: 0.4 us per 8-row weight tile), as much as loading the data.
+__device__ __forceinline__ void prefetch_bulk(const void *p, unsigned bytes) {        // 16-byte aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+__device__ __noinline__ void prefetch_gemm(const Phase &P) {
+    const int t0 = (int)((long long)blockIdx.x * P.tiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * P.tiles / gridDim.x);
+    if (threadIdx.x >= 8) return;
+    int j = 0;
+#pragma unroll 1
+    for (int t = t0; t < t1; t++) {
+        while (j + 1 < P.njobs && t >= P.job[j + 1].tile0) j++;
+        const Job &J = P.job[j];
+        const int n0 = (t - J.tile0) * 8, rows = min(8, J.N - n0);
+        if (J.ldw == J.K) {                                                  // the tile's rows are one contiguous span
+            if (threadIdx.x == 0) prefetch_bulk(J.W + (size_t)n0 * J.ldw, (unsigned)(rows * J.K * 2));
+        } else if ((int)threadIdx.x < rows) {
+            prefetch_bulk(J.W + (size_t)(n0 + threadIdx.x) * J.ldw, (unsigned)(J.K * 2));
+        }
+    }
+}
+__device__ __noinline__ void prefetch_wkv(const Desc &D, const Layer &Ly) {
+    const int tid = threadIdx.x;
+    if (tid >= 32) return;
+#pragma unroll 1
+    for (int u = blockIdx.x * 2; u < D.B * D.H; u += gridDim.x * 2) {
+        const int n = min(2, D.B * D.H - u);                             // the two units the halves of the CTA take
+        if (tid == 0) {
+            prefetch_bulk(Ly.state + (size_t)u * kC * kC, (unsigned)(n * kC * kC * sizeof(float)));
+        } else if (tid <= 8) {                                           // (unit, LoRA) pairs
+            const int k = (tid - 1) >> 2, L = (tid - 1) & 3;
+            if (k < n && Ly.up[L] != nullptr)
+                prefetch_bulk(Ly.up[L] + (size_t)((u + k) % D.H) * kC * D.D[L], (unsigned)(kC * D.D[L] * sizeof(bf16)));
+        } else if (tid <= 24) {                                          // (unit, per-channel vector) pairs
+            const int k = (tid - 9) >> 3;
+            const bf16 *q = (&Ly.w0)[(tid - 9) & 7];                     // w0, a0, v0, k_k, k_a, r_k, gn_w, gn_b
+            if (k < n && q != nullptr) prefetch_bulk(q + (size_t)((u + k) % D.H) * kC, kC * sizeof(bf16));
+        }
+    }
+}
+// n per-channel vectors [C] of a row phase (rows b = blockIdx.x, blockIdx.x + grid, ...: only those CTAs read them); the
+// last one is the [B, C] token-shift state when `last_is_rows`: this CTA's row of it
+__device__ __noinline__ void prefetch_vecs(const Desc &D, const bf16 *const *v, int n, bool last_is_rows) {
+    if ((int)blockIdx.x >= D.B || (int)threadIdx.x >= n) return;
+    const bf16 *q = v[threadIdx.x];
+    if (q == nullptr) return;
+    if (last_is_rows && (int)threadIdx.x == n - 1) q += (size_t)blockIdx.x * D.C;
+    prefetch_bulk(q, (unsigned)(D.C * sizeof(bf16)));
+}
+__device__ __forceinline__ void copy_async(void *smem_dst, const void *gsrc, int bytes) {      // bytes % 16 == 0
+#pragma unroll 1
+    for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16)
+        tc05::cp_async16(static_cast<char *>(smem_dst) + i, static_cast<const char *>(gsrc) + i);
+}
+
 template <int NKB>
 __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__restrict__ Dp, const StepArgs a) {
-    __shared__ __align__(16) float smem[kWarps * 512 + 64];
-    const Desc &D = *Dp;
-    float *red_rows = smem + kWarps * 512;      // scratch of the row phases' reductions (xs = smem[0..C))
+    extern __shared__ __align__(16) float smem[];      // [kRedFloats] scratch of the running phase, then the staged LoRA rows
+    __shared__ Desc sD;             // the plan lives in shared memory: a descriptor read from HBM at the head of every
+    __shared__ Layer sL[2];         // phase would put a DRAM round trip in front of each of the 170 phases
+    static_assert(sizeof(Desc) % 16 == 0 && sizeof(Layer) % 16 == 0, "cp.async pieces");
+    static_assert(offsetof(Layer, att_shift) - offsetof(Layer, ln1_w) == 8 * sizeof(void *), "ln1 pointer group");
+    static_assert(offsetof(Layer, ffn_shift) - offsetof(Layer, ln2_w) == 3 * sizeof(void *), "ln2 pointer group");
+    static_assert(offsetof(Layer, gn_b) - offsetof(Layer, w0) == 7 * sizeof(void *), "wkv pointer group");
+    copy_async(&sD, Dp, sizeof(Desc));
+    tc05::cp_async_commit();
+    tc05::cp_async_wait<0>();
+    __syncthreads();
+    const Desc &D = sD;
+    copy_async(&sL[0], D.layers, sizeof(Layer));
+    if (D.L > 1) copy_async(&sL[1], D.layers + 1, sizeof(Layer));
+    tc05::cp_async_commit();
+    tc05::cp_async_wait<0>();
+    __syncthreads();
+    float *red_rows = smem + kRedFloats - 64;   // reductions of the row phases (xs = smem[0..C), C <= 2048)
+    bf16 *upw = reinterpret_cast<bf16 *>(smem + kRedFloats);
+    const int nprof = 8 * D.L + 4, half = threadIdx.x >> 8;
+    // fine stamps of layer 1 (cycles): [0..] main loop marks, [16..] projections, [32..] wkv rounds, [48..] output projection, [64..] key
+    long long *fine = a.prof != nullptr ? reinterpret_cast<long long *>(a.prof + (size_t)nprof * (1 + 2 * kProfCtas)) : nullptr;
     unsigned epoch = 0;
+    if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.prof[0] = globaltimer();
+    prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&sL[0].ln1_w), 9, true);
+    prefetch_vecs(D, &D.ln0_w, 2, false);
+    prefetch_gemm(sL[0].p2);
+#pragma unroll 1
     for (int l = 0; l < D.L; l++) {
-        const Layer &Ly = D.layers[l];
-        phase_ln1(D, Ly, l, a, smem, red_rows);
-        grid_sync(D.bar, epoch);
-        phase_gemm<NKB>(Ly.p2, D.B, smem);
-        grid_sync(D.bar, epoch);
-        phase_wkv(D, Ly, l, smem);
-        grid_sync(D.bar, epoch);
-        phase_gemm<NKB>(Ly.p4, D.B, smem);
-        grid_sync(D.bar, epoch);
-        phase_ln2(D, Ly, smem, red_rows);
-        grid_sync(D.bar, epoch);
-        phase_gemm<NKB>(Ly.p6, D.B, smem);
-        grid_sync(D.bar, epoch);
-        phase_gemm<NKB>(Ly.p7, D.B, smem);
-        grid_sync(D.bar, epoch);
+        const Layer &Ly = sL[l & 1];
+        if (!(a.debug_skip & 1)) phase_rows(D, Ly, kRowLn1, l == 0, a, smem, red_rows);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        if (l == 1) PROF_POINT(fine, 3);
+        if (!(a.debug_skip & 2)) prefetch_wkv(D, Ly);
+        if (l == 1) PROF_POINT(fine, 4);
+        phase_gemm<NKB>(Ly.p2, D.B, smem, (l == 1 && fine != nullptr) ? fine + 16 : nullptr);
+        if (l == 1) PROF_POINT(fine, 5);
+        if (!(a.debug_skip & 2)) stage_up(D, Ly, blockIdx.x * 2 + half, upw + (size_t)half * kC * D.Dtot);      // first round of the wkv phase
+        tc05::cp_async_commit();
+        if (l == 1) PROF_POINT(fine, 6);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        if (l == 1) PROF_POINT(fine, 0);
+        prefetch_gemm(Ly.p4);
+        if (l == 1) PROF_POINT(fine, 1);
+        prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&Ly.ln2_w), 4, true);
+        if (l == 1) PROF_POINT(fine, 2);
+        if (!(a.debug_skip & 2)) phase_wkv(D, Ly, l == 0, smem, upw, (l == 1 && fine != nullptr) ? fine + 32 : nullptr);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        prefetch_gemm(Ly.p6);
+        phase_gemm<NKB>(Ly.p4, D.B, smem, (l == 1 && fine != nullptr) ? fine + 48 : nullptr);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        if (!(a.debug_skip & 1)) phase_rows(D, Ly, kRowLn2, false, a, smem, red_rows);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        prefetch_gemm(Ly.p7);
+        phase_gemm<NKB>(Ly.p6, D.B, smem, (l == 1 && fine != nullptr) ? fine + 64 : nullptr);
+        tc05::cp_async_wait<0>();                        // own pieces of layer l + 1's descriptor; the barrier publishes them
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        if (l + 1 < D.L) {
+            const Layer &Nx = sL[(l + 1) & 1];
+            prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&Nx.ln1_w), 9, true);
+            prefetch_gemm(Nx.p2);
+        } else {
+            prefetch_vecs(D, &D.lnf_w, 2, false);
+            prefetch_gemm(D.head);
+        }
+        phase_gemm<NKB>(Ly.p7, D.B, smem, nullptr);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        // every thread is past its last use of sL[l & 1]: bring in layer l + 2
+        if (l + 2 < D.L) copy_async(&sL[l & 1], D.layers + l + 2, sizeof(Layer));
+        tc05::cp_async_commit();
     }
-    phase_lnf(D, smem, red_rows);
-    grid_sync(D.bar, epoch);
-    phase_gemm<NKB>(D.head, D.B, smem);
+    phase_rows(D, sL[0], kRowFinal, false, a, smem, red_rows);
+    epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+    phase_gemm<NKB>(D.head, D.B, smem, nullptr);
     if (a.greedy) {
-        grid_sync(D.bar, epoch);
+        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
         phase_argmax(D, a, red_rows);
     }
     // the last CTA out resets the counters for the next launch (every CTA has left its last barrier by then)
@@ -532,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------------
-struct HostInfo { int grid, nkb, device; };
+struct HostInfo { int grid, nkb, device; size_t smem; };
 static std::mutex g_mu;
 static std::unordered_map<void *, HostInfo> g_plans;
 
@@ -651,8 +857,12 @@ cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, c
     int sms = 0, per_sm = 0;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hi.device)) != cudaSuccess) return e;
     hi.nkb = C <= 1024 ? 2 : 4;
-    e = hi.nkb == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<2>, kThreads, 0)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<4>, kThreads, 0);
+    // dynamic shared memory: the phase scratch + the staged LoRA up-projection rows of two (b, head) units
+    hi.smem = (size_t)kRedFloats * sizeof(float) + (size_t)2 * kC * D.Dtot * sizeof(bf16);
+    const void *fn = hi.nkb == 2 ? (const void *)decode_step_kernel<2> : (const void *)decode_step_kernel<4>;
+    if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi.smem)) != cudaSuccess) return e;
+    e = hi.nkb == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<2>, kThreads, hi.smem)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<4>, kThreads, hi.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorCooperativeLaunchTooLarge;
     hi.grid = sms;
@@ -662,7 +872,7 @@ cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, c
 }
 
 cudaError_t decode_step(void *ws, const long long *tok_in, long long *tok_out, int greedy, int suppress_eos,
-                        const long long *eos, int n_eos, long long pad, cudaStream_t st) {
+                        const long long *eos, int n_eos, long long pad, unsigned long long *prof, cudaStream_t st) {
     HostInfo hi{};
     {
         std::lock_guard<std::mutex> lk(g_mu);
@@ -675,15 +885,17 @@ cudaError_t decode_step(void *ws, const long long *tok_in, long long *tok_out, i
         if (e != cudaSuccess) return e;
     }
     StepArgs a{};
-    a.tok_in = tok_in; a.tok_out = tok_out; a.pad = pad; a.greedy = greedy; a.suppress_eos = suppress_eos;
+    a.tok_in = tok_in; a.tok_out = tok_out; a.pad = pad; a.greedy = greedy; a.suppress_eos = suppress_eos; a.prof = prof;
+    const char *dbg = getenv("RWKVTTS_DECODE_SKIP");
+    a.debug_skip = dbg != nullptr ? atoi(dbg) : 0;
     a.n_eos = n_eos < kMaxEos ? n_eos : kMaxEos;
     for (int i = 0; i < a.n_eos; i++) a.eos[i] = eos[i];
     const Desc *Dp = static_cast<const Desc *>(ws);
     void *args[] = {(void *)&Dp, (void *)&a};
     count_launch();
     return hi.nkb == 2
-        ? cudaLaunchCooperativeKernel((const void *)decode_step_kernel<2>, dim3(hi.grid), dim3(kThreads), args, 0, st)
-        : cudaLaunchCooperativeKernel((const void *)decode_step_kernel<4>, dim3(hi.grid), dim3(kThreads), args, 0, st);
+        ? cudaLaunchCooperativeKernel((const void *)decode_step_kernel<2>, dim3(hi.grid), dim3(kThreads), args, hi.smem, st)
+        : cudaLaunchCooperativeKernel((const void *)decode_step_kernel<4>, dim3(hi.grid), dim3(kThreads), args, hi.smem, st);
 }
 
 void decode_release(void *ws) {

@@ -176,6 +176,24 @@ class MegaDecodeStep:
         self.cache._seen_tokens += 1
         return self.logits
 
+    def phase_times(self, nxt: torch.Tensor) -> torch.Tensor:
+        """One step with the kernel's time line: float64 [7 L + 1] microseconds spent between consecutive grid barriers
+        (per layer: ln1, projections, wkv, output projection, ln2, channel-mix key, channel-mix value; then the final norm)."""
+        L = len(self.model.model.layers)
+        n = 8 * L + 4
+        stamps = torch.zeros(n * 513 + 128, dtype=torch.int64, device=self.device)
+        tok = nxt.reshape(-1).to(torch.int64).contiguous()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib().rwkvtts_decode_step_profile(ctypes.c_void_p(self._ws_ptr), ctypes.c_void_p(tok.data_ptr()),
+                                                        ctypes.c_void_p(stamps.data_ptr()), self._stream())
+        _lib.check(rc, "rwkvtts_decode_step_profile")
+        self.cache._seen_tokens += 1
+        self.last_arrive = stamps[n: n + 256 * n].view(n, 256)[1: 7 * L + 2]        # [barrier, CTA] ns (0 = no such CTA)
+        self.last_release = stamps[257 * n: 257 * n + 256 * n].view(n, 256)[1: 7 * L + 2]
+        self.last_fine = stamps[n * 513:]                  # cycle stamps inside layer 1's phases (csrc/decode_step.cu)
+        t = stamps[: 7 * L + 2].double()
+        return (t[1:] - t[:-1]) / 1e3
+
     def greedy(self, first: torch.Tensor, steps: int, eos: Sequence[int] = (), pad: int = 0, min_new_tokens: int = 0,
                step0: int = 0, done: Optional[torch.Tensor] = None) -> torch.Tensor:
         """`steps` greedy tokens after `first` [B] (the token the caller sampled from the prefill logits), sampled on the

@@ -33,7 +33,7 @@ def _rel(a, b):
 
 
 def _prefill(m, ids):
-    from rwkvfla.models.rwkv7 import Cache
+    from rwkvfla.models.utils import Cache
     with torch.no_grad():
         out = m(input_ids=ids, past_key_values=Cache(), use_cache=True, logits_to_keep=1)
     return out.past_key_values, out.logits[:, -1].float()
