@@ -73,6 +73,7 @@ struct alignas(16) Layer {
 };
 struct alignas(16) Desc {
     int B, C, H, L, V, F, D[4], Dtot, nchunk;
+    int inv[4], pad_[2];            // ceil(2^20 / (D[i] / 8)): row of a 16-byte piece of a LoRA matrix without a division
     float ln_eps, gn_eps;
     const bf16 *emb, *ln0_w, *ln0_b, *lnf_w, *lnf_b;
     Phase head;
@@ -113,9 +114,6 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 // activations written by other CTAs earlier in this launch: L2 only (an L1 line could be stale); parameters: read-only path
-__device__ __forceinline__ float ld_act(const bf16 *p) {
-    return __uint_as_float((unsigned)__ldcg(reinterpret_cast<const unsigned short *>(p)) << 16);
-}
 __device__ __forceinline__ float2 ld_act2(const bf16 *p) {
     const unsigned u = __ldcg(reinterpret_cast<const unsigned *>(p));
     return make_float2(bf16_lo(u), bf16_hi(u));
@@ -150,28 +148,113 @@ __device__ __forceinline__ unsigned long long globaltimer() {
     __trap();
     for (;;) {}
 }
+
+// ---- L2 prefetch during the barrier waits ------------------------------------------------------------------------------
+// What a later phase will read from HBM (weights, parameters, recurrent state: nothing of it depends on this token) is
+// pulled into L2 one to two phases ahead, so that after a barrier only L2 latencies are left on the critical path.  One
+// bulk-prefetch instruction per contiguous span, run by the copy engine; issuing one costs the warp ~100 cycles and a
+// `prefetch.global.L2` per 128-byte line ~6 cycles of the SM's load pipe each (both measured), so the spans are issued by
+// ONE warp while thread 0 polls the grid barrier -- the ~1 us every CTA waits there anyway.
+__device__ __forceinline__ void prefetch_bulk(const void *p, unsigned bytes) {        // 16-byte aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+struct Ranges { int r[6][2]; };     // this CTA's tile range of: projections (layer 0), projections, out, key, value, head
+enum { kRgP2First = 0, kRgP2, kRgP4, kRgP6, kRgP7, kRgHead };
+enum { kPfNone = 0, kPfWkv, kPfOut, kPfKey, kPfValue, kPfNextProj, kPfHead };
+
+// the weight rows of this CTA's tiles of a GEMM phase: one span per job segment where rows are contiguous (ldw == K),
+// else the first 8 rows only (split-K jobs: every row is its own span)
+__device__ __forceinline__ void prefetch_tiles(const Phase &P, int t0, int t1, int lane) {
+    if (t0 >= t1) return;
+    int j = 0;
+    while (j + 1 < P.njobs && t0 >= P.job[j + 1].tile0) j++;
+    int t = t0;
+#pragma unroll 1
+    while (t < t1) {
+        const Job &J = P.job[j];
+        const int jend = min(t1, J.tile0 + ((J.N + 7) >> 3)), n0 = (t - J.tile0) * 8, rows = min(J.N - n0, (jend - t) * 8);
+        if (J.ldw == J.K) {
+            if (lane == 0) prefetch_bulk(J.W + (size_t)n0 * J.ldw, (unsigned)(rows * J.K * 2));
+        } else if (lane < min(rows, 8)) {
+            prefetch_bulk(J.W + (size_t)(n0 + lane) * J.ldw, (unsigned)(J.K * 2));
+        }
+        t = jend;
+        j++;
+    }
+}
+__device__ __noinline__ void prefetch_plan(int plan, const Desc &D, const Layer &Ly, const Layer &Nx, const Ranges &R, bool first,
+                                           int lane) {
+    if (plan == kPfWkv) {
+        // recurrent state of the two units of each round, and the head's LoRA up-projection rows
+        const int NP = D.H * ((D.B + 1) >> 1);
+#pragma unroll 1
+        for (int q = blockIdx.x; q < NP; q += gridDim.x) {
+            const int h = q % D.H, b0 = 2 * (q / D.H);
+            if (lane < 2) {
+                if (b0 + lane < D.B) prefetch_bulk(Ly.state + (size_t)((b0 + lane) * D.H + h) * kC * kC, kC * kC * sizeof(float));
+            } else if (lane < 6) {
+                const int L = lane - 2;
+                if (Ly.up[L] != nullptr) prefetch_bulk(Ly.up[L] + (size_t)h * kC * D.D[L], (unsigned)(kC * D.D[L] * sizeof(bf16)));
+            }
+        }
+    } else if (plan == kPfOut) {
+        prefetch_tiles(Ly.p4, R.r[kRgP4][0], R.r[kRgP4][1], lane);
+        if ((int)blockIdx.x < D.B && lane >= 8 && lane < 12) {               // ln2_w, ln2_b, ffn_mix, this row of ffn_shift
+            const bf16 *q = (&Ly.ln2_w)[lane - 8];
+            if (q != nullptr) prefetch_bulk(lane == 11 ? q + (size_t)blockIdx.x * D.C : q, (unsigned)(D.C * sizeof(bf16)));
+        }
+    } else if (plan == kPfKey) {
+        prefetch_tiles(Ly.p6, R.r[kRgP6][0], R.r[kRgP6][1], lane);
+    } else if (plan == kPfValue) {
+        prefetch_tiles(Ly.p7, R.r[kRgP7][0], R.r[kRgP7][1], lane);
+    } else if (plan == kPfNextProj) {
+        prefetch_tiles(Nx.p2, R.r[kRgP2][0], R.r[kRgP2][1], lane);
+        if ((int)blockIdx.x < D.B && lane >= 8 && lane < 17) {               // ln1_w, ln1_b, mix[6], this row of att_shift
+            const bf16 *q = (&Nx.ln1_w)[lane - 8];
+            if (q != nullptr) prefetch_bulk(lane == 16 ? q + (size_t)blockIdx.x * D.C : q, (unsigned)(D.C * sizeof(bf16)));
+        }
+    } else if (plan == kPfHead) {
+        prefetch_tiles(D.head, R.r[kRgHead][0], R.r[kRgHead][1], lane);
+        if ((int)blockIdx.x < D.B && lane >= 8 && lane < 10) {
+            const bf16 *q = (&D.lnf_w)[lane - 8];
+            if (q != nullptr) prefetch_bulk(q, (unsigned)(D.C * sizeof(bf16)));
+        }
+    }
+    (void)first;
+}
+
 // Grid barrier on a monotonic arrival counter (cooperative launch: all CTAs are resident): release-add by one thread
 // (cumulative over what the CTA wrote before the bar.sync), acquire-poll, ~1.0 us from the last arrival to the releases
 // (measured; a per-CTA flag written by the last arriver takes 2.0 us, a poll with back-off the same 1.0).  Bounded like the
 // mbarrier waits of the chunked kernels: a CTA that never arrives turns into a trap with a record, not a hung device.
 constexpr int kProfCtas = 256;      // profile layout: [n] CTA 0 after each barrier, then [n][256] arrivals, [n][256] releases
-__device__ __noinline__ unsigned grid_sync(unsigned *bar, unsigned epoch, unsigned long long *prof, int nprof) {
+struct SyncCtx {
+    const Desc *D;
+    const Ranges *R;
+    unsigned long long *prof;
+    int nprof;
+};
+__device__ __noinline__ unsigned grid_sync(const SyncCtx &cx, unsigned epoch, int plan, const Layer *Ly, const Layer *Nx) {
     __syncthreads();
     epoch++;
+    unsigned *bar = cx.D->bar;
     if (threadIdx.x == 0) {
-        if (prof != nullptr && blockIdx.x < kProfCtas) prof[nprof + epoch * kProfCtas + blockIdx.x] = globaltimer();
-        const unsigned target = epoch * gridDim.x;
+        if (cx.prof != nullptr && blockIdx.x < kProfCtas) cx.prof[cx.nprof + epoch * kProfCtas + blockIdx.x] = globaltimer();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
+    }
+    if (plan != kPfNone && (threadIdx.x >> 5) == 1) prefetch_plan(plan, *cx.D, *Ly, *Nx, *cx.R, false, threadIdx.x & 31);
+    if (threadIdx.x == 0) {
+        const unsigned target = epoch * gridDim.x;
         if (ld_acquire(bar) < target) {
             const uint32_t t0 = clock_hi();
             while (ld_acquire(bar) < target) {
                 if (clock_hi() - t0 >= 2u) grid_die(epoch);
             }
         }
-        if (prof != nullptr) {
+        if (cx.prof != nullptr) {
             const unsigned long long t = globaltimer();
-            if (blockIdx.x == 0) prof[epoch] = t;
-            if (blockIdx.x < kProfCtas) prof[nprof * (1 + kProfCtas) + epoch * kProfCtas + blockIdx.x] = t;
+            if (blockIdx.x == 0) cx.prof[epoch] = t;
+            if (blockIdx.x < kProfCtas) cx.prof[cx.nprof * (1 + kProfCtas) + epoch * kProfCtas + blockIdx.x] = t;
         }
     }
     __syncthreads();
@@ -187,94 +270,105 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
     __syncthreads();
     return t;
 }
-// LayerNorm of the row in xs[0..C) (each thread owns the channel pairs 2 tid, 2 tid + 1024, ...): xs <- bf16(LN(xs) * w + b)
-__device__ __noinline__ void row_layernorm(float *xs, int C, const bf16 *w, const bf16 *b, float eps, float *red) {
+
+// ---- row phases: ln1 (+ embedding / previous layer's channel-mix sum), ln2, final norm -------------------------------------------
+// Each thread owns the channel pairs 2 tid (+ 1024): the row never leaves registers, and everything the phase reads that
+// does not depend on the row itself (norm weights, lerp coefficients, shift state) is requested before the first reduction.
+// PP = channel pairs per thread: 1 for C <= 1024, 2 for C <= 2048
+template <int kPP>
+__device__ __forceinline__ void ln_regs(float2 (&x)[kPP], int C, const float2 (&w)[kPP], const float2 (&b)[kPP], float eps, float *red) {
     float s1 = 0.f;
-#pragma unroll 1
-    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) s1 += xs[c] + xs[c + 1];
+#pragma unroll
+    for (int pp = 0; pp < kPP; pp++) s1 += x[pp].x + x[pp].y;           // pairs beyond C hold zeros
     const float mu = block_sum(s1, red) / (float)C;
     float s2 = 0.f;
-#pragma unroll 1
-    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-        const float d0 = xs[c] - mu, d1 = xs[c + 1] - mu;
-        s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-    }
+#pragma unroll
+    for (int pp = 0; pp < kPP; pp++)
+        if (2 * (int)threadIdx.x + pp * 2 * kThreads < C) {
+            const float d0 = x[pp].x - mu, d1 = x[pp].y - mu;
+            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+        }
     const float rstd = rsqrtf(block_sum(s2, red) / (float)C + eps);
-#pragma unroll 1
-    for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-        const float2 wv = ld_par2(w + c), bv = b != nullptr ? ld_par2(b + c) : make_float2(0.f, 0.f);
-        xs[c] = rbf((xs[c] - mu) * rstd * wv.x + bv.x);
-        xs[c + 1] = rbf((xs[c + 1] - mu) * rstd * wv.y + bv.y);
+#pragma unroll
+    for (int pp = 0; pp < kPP; pp++) {
+        x[pp].x = rbf((x[pp].x - mu) * rstd * w[pp].x + b[pp].x);
+        x[pp].y = rbf((x[pp].y - mu) * rstd * w[pp].y + b[pp].y);
     }
 }
 
-// ---- row phases: ln1 (+ embedding / previous layer's channel-mix sum), ln2, final norm -------------------------------------------
-__device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind, bool first_layer, const StepArgs &a, float *xs,
-                                        float *red) {
+template <int kPP>
+__device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind, bool first_layer, const StepArgs &a, float *red) {
     const int C = D.C;
 #pragma unroll 1
     for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
         const size_t rb = (size_t)b * C;
-        if (kind == kRowLn1 && first_layer) {
-            const long long t = a.tok_in != nullptr ? a.tok_in[b] : __ldcg(D.tok + b);
-            const bf16 *e = D.emb + (size_t)t * C;
-#pragma unroll 1
-            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-                const float2 v = ld_par2(e + c);
-                xs[c] = v.x; xs[c + 1] = v.y;
-            }
-            if (D.ln0_w != nullptr) row_layernorm(xs, C, D.ln0_w, D.ln0_b, D.ln_eps, red);
-        } else if (kind == kRowLn2) {
-#pragma unroll 1
-            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-                const float2 x = ld_act2(D.x + rb + c), t = ld_act2(D.att + rb + c);
-                xs[c] = rbf(x.x + t.x); xs[c + 1] = rbf(x.y + t.y);
-            }
-        } else {
-            // x2 + the channel-mix value projection: its split-K partials are summed here, as the bf16 tensor it returns
-#pragma unroll 1
-            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-                const float2 x = ld_act2(D.x2 + rb + c);
+        const bf16 *nw = kind == kRowLn1 ? Ly.ln1_w : kind == kRowLn2 ? Ly.ln2_w : D.lnf_w;
+        const bf16 *nb = kind == kRowLn1 ? Ly.ln1_b : kind == kRowLn2 ? Ly.ln2_b : D.lnf_b;
+        bf16 *shift = (kind == kRowLn1 ? Ly.att_shift : Ly.ffn_shift) + rb;
+        const bf16 *const *mix = kind == kRowLn1 ? Ly.mix : &Ly.ffn_mix;
+        const int n = kind == kRowLn1 ? 6 : kind == kRowLn2 ? 1 : 0;
+        const bool emb = kind == kRowLn1 && first_layer;
+        const bf16 *e = nullptr;
+        if (emb) e = D.emb + (size_t)(a.tok_in != nullptr ? a.tok_in[b] : __ldcg(D.tok + b)) * C;
+        float2 x[kPP], w[kPP], bb[kPP], w0[kPP], b0[kPP], sh[kPP], mx[kPP][6];
+#pragma unroll
+        for (int pp = 0; pp < kPP; pp++) {
+            const int c = 2 * threadIdx.x + pp * 2 * kThreads;
+            const bool ok = c < C;
+            const float2 z = make_float2(0.f, 0.f);
+            // the row
+            if (!ok) {
+                x[pp] = z;
+            } else if (emb) {
+                x[pp] = ld_par2(e + c);
+            } else if (kind == kRowLn2) {
+                const float2 u = ld_act2(D.x + rb + c), t = ld_act2(D.att + rb + c);
+                x[pp] = make_float2(rbf(u.x + t.x), rbf(u.y + t.y));
+            } else {
+                // x2 + the channel-mix value projection: its split-K partials are summed here, as the bf16 tensor it returns
+                const float2 u = ld_act2(D.x2 + rb + c);
                 float2 pv[kMaxJobs];
 #pragma unroll
                 for (int kc = 0; kc < kMaxJobs; kc++)
-                    pv[kc] = kc < D.nchunk ? __ldcg(reinterpret_cast<const float2 *>(D.part + ((size_t)kc * kRows + b) * C + c))
-                                           : make_float2(0.f, 0.f);
+                    pv[kc] = kc < D.nchunk ? __ldcg(reinterpret_cast<const float2 *>(D.part + ((size_t)kc * kRows + b) * C + c)) : z;
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int kc = 0; kc < kMaxJobs; kc++) { s0 += pv[kc].x; s1 += pv[kc].y; }
-                xs[c] = rbf(x.x + rbf(s0)); xs[c + 1] = rbf(x.y + rbf(s1));
+                x[pp] = make_float2(rbf(u.x + rbf(s0)), rbf(u.y + rbf(s1)));
             }
-        }
-        bf16 *keep = (kind == kRowLn2 ? D.x2 : D.x) + rb;          // the residual stream
-#pragma unroll 1
-        for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) st2(keep + c, xs[c], xs[c + 1]);
-        if (kind == kRowLn1) row_layernorm(xs, C, Ly.ln1_w, Ly.ln1_b, D.ln_eps, red);
-        else if (kind == kRowLn2) row_layernorm(xs, C, Ly.ln2_w, Ly.ln2_b, D.ln_eps, red);
-        else row_layernorm(xs, C, D.lnf_w, D.lnf_b, D.ln_eps, red);
-        if (kind == kRowFinal) {
-#pragma unroll 1
-            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) st2(D.hN + rb + c, xs[c], xs[c + 1]);
-        } else {
-            bf16 *shift = (kind == kRowLn1 ? Ly.att_shift : Ly.ffn_shift) + rb;
-            const bf16 *const *mix = kind == kRowLn1 ? Ly.mix : &Ly.ffn_mix;
-            bf16 *out = (kind == kRowLn1 ? D.X : D.Xf) + rb;
-            const int n = kind == kRowLn1 ? 6 : 1;
-#pragma unroll 1
-            for (int c = 2 * threadIdx.x; c < C; c += 2 * kThreads) {
-                const float h0 = xs[c], h1 = xs[c + 1];
-                const float2 pr = ld_act2(shift + c);
-                float2 m[6];
+            // everything else the phase reads
+            w[pp] = ok ? ld_par2(nw + c) : z;
+            bb[pp] = ok && nb != nullptr ? ld_par2(nb + c) : z;
+            w0[pp] = ok && emb && D.ln0_w != nullptr ? ld_par2(D.ln0_w + c) : z;
+            b0[pp] = ok && emb && D.ln0_b != nullptr ? ld_par2(D.ln0_b + c) : z;
+            sh[pp] = ok && n > 0 ? ld_act2(shift + c) : z;
 #pragma unroll
-                for (int s = 0; s < 6; s++) m[s] = s < n ? ld_par2(mix[s] + c) : make_float2(0.f, 0.f);
-                const float xx0 = rbf(pr.x - h0), xx1 = rbf(pr.y - h1);      // the reference rounds shift(x) - x to bf16
+            for (int s = 0; s < 6; s++) mx[pp][s] = ok && s < n ? ld_par2(mix[s] + c) : z;
+        }
+        if (emb && D.ln0_w != nullptr) ln_regs<kPP>(x, C, w0, b0, D.ln_eps, red);
+        bf16 *keep = (kind == kRowLn2 ? D.x2 : D.x) + rb;          // the residual stream
+#pragma unroll
+        for (int pp = 0; pp < kPP; pp++) {
+            const int c = 2 * threadIdx.x + pp * 2 * kThreads;
+            if (c < C) st2(keep + c, x[pp].x, x[pp].y);
+        }
+        ln_regs<kPP>(x, C, w, bb, D.ln_eps, red);
+#pragma unroll
+        for (int pp = 0; pp < kPP; pp++) {
+            const int c = 2 * threadIdx.x + pp * 2 * kThreads;
+            if (c >= C) continue;
+            const float h0 = x[pp].x, h1 = x[pp].y;
+            if (kind == kRowFinal) {
+                st2(D.hN + rb + c, h0, h1);
+            } else {
+                bf16 *out = (kind == kRowLn1 ? D.X : D.Xf) + rb;
+                const float xx0 = rbf(sh[pp].x - h0), xx1 = rbf(sh[pp].y - h1);      // the reference rounds shift(x) - x to bf16
 #pragma unroll
                 for (int s = 0; s < 6; s++)
-                    if (s < n) st2(out + (size_t)s * kRows * C + c, fmaf(xx0, m[s].x, h0), fmaf(xx1, m[s].y, h1));
+                    if (s < n) st2(out + (size_t)s * kRows * C + c, fmaf(xx0, mx[pp][s].x, h0), fmaf(xx1, mx[pp][s].y, h1));
                 st2(shift + c, h0, h1);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -319,44 +413,59 @@ __device__ __noinline__ void phase_argmax(const Desc &D, const StepArgs &a, floa
 }
 
 // ---- (b, head) phase: LoRA ups, decay / kk / a / k' / v', state update, GroupNorm + bonus + gate ---------------------------
+// A CTA takes one head and TWO batch rows per round (one per half of its threads), so the head's LoRA up-projection rows
+// are brought into shared memory once for both.
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void half_bar(int half) { asm volatile("bar.sync %0, 256;" :: "r"(1 + half) : "memory"); }
 
-// LoRA up-projection rows of unit u's head (64 rows x rank, contiguous in every [C, rank] matrix) -> shared memory of the
-// calling half, asynchronously: issued BEFORE the grid barrier that precedes the phase (they do not depend on the token)
-__device__ __noinline__ void stage_up(const Desc &D, const Layer &Ly, int u, bf16 *upw) {
-    if (u >= D.B * D.H) return;
-    const int h = u % D.H, t = threadIdx.x & 255;
+// 64 rows x rank of every LoRA up-projection of head h (contiguous in each [C, rank] matrix) -> shared memory, rows padded
+// by 16 bytes (conflict-free 16-byte reads by the (row, quarter) lanes), asynchronously: for the first round it is issued
+// BEFORE the grid barrier that precedes the phase (the weights do not depend on the token)
+__device__ __noinline__ void stage_up(const Desc &D, const Layer &Ly, int h, bf16 *upw, int tid, int nthreads) {
     int off = 0;
 #pragma unroll 1
     for (int L = 0; L < 4; L++) {
-        const int Dl = D.D[L];
+        const int Dl = D.D[L], S = Dl >> 3, inv = D.inv[L];
         if (Ly.up[L] != nullptr) {
-            const char *src = reinterpret_cast<const char *>(Ly.up[L] + (size_t)h * kC * Dl);
-            char *dst = reinterpret_cast<char *>(upw + (size_t)kC * off);
+            const bf16 *src = Ly.up[L] + (size_t)h * kC * Dl;
 #pragma unroll 1
-            for (int i = t * 16; i < kC * Dl * 2; i += 256 * 16) tc05::cp_async16(dst + i, src + i);
+            for (int idx = tid; idx < kC * S; idx += nthreads) {
+                const int row = (int)(((unsigned)idx * (unsigned)inv) >> 20), seg = idx - row * S;
+                tc05::cp_async16(upw + off + row * (Dl + 8) + seg * 8, src + row * Dl + seg * 8);
+            }
         }
-        off += Dl;
+        off += kC * (Dl + 8);
     }
 }
 
-__device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool first_layer, float *smem, bf16 *upw_all,
-                                       long long *fine) {
+__device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool first_layer, float *smem, bf16 *upw, long long *fine) {
     const int half = threadIdx.x >> 8, t = threadIdx.x & 255, i = t >> 2, p = t & 3, lane = t & 31;
-    const bool lead = (t >> 5) == 0;                       // first warp of the half: the per-channel work
-    float *hls = smem + half * 1280, *los = hls + kMaxLora, *vec = los + 4 * kC, *ys = vec + 6 * kC;
-    bf16 *upw = upw_all + (size_t)half * kC * D.Dtot;
-    const int C = D.C, H = D.H, BH = D.B * D.H;
+    const int warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
+    const bool lead_warp = (t >> 5) == 0;                  // first warp of the half: the per-channel work
+    // scratch: the two rows of LoRA hidden activations as bf16 [2][kMaxLora + 8], then per half los [4][64], vec [6][64], ys [64]
+    constexpr int kHS = kMaxLora + 8;
+    bf16 *hbf = reinterpret_cast<bf16 *>(smem);
+    float *los = smem + kHS + half * 768, *vec = los + 4 * kC, *ys = vec + 6 * kC;
+    const int C = D.C, H = D.H, NP = H * ((D.B + 1) >> 1);
 #pragma unroll 1
-    for (int u = blockIdx.x * 2 + half; u < BH; u += gridDim.x * 2) {
-        const int b = u / H, h = u % H;
+    for (int q = blockIdx.x; q < NP; q += gridDim.x) {
         PROF_POINT(fine, 0);
+        const int h = q % H, b = 2 * (q / H) + half;
+        const bool valid = b < D.B, lead = lead_warp && valid;
+        const int u = b * H + h;
         float4 *srow = reinterpret_cast<float4 *>(Ly.state + ((size_t)u * kC + i) * kC + 4 * p);
         float4 s4[4];
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) s4[j] = __ldcg(srow + 4 * j);          // the long-latency loads first
-#pragma unroll 1
-        for (int j = t; j < D.Dtot; j += 256) hls[j] = ld_act(D.hl + (size_t)b * D.Dtot + j);
+            for (int j = 0; j < 4; j++) s4[j] = __ldcg(srow + 4 * j);          // the long-latency loads first
+        }
+        if (t * 8 < D.Dtot) {                                                  // this half's row of hl, 16 bytes per thread
+            if (valid) tc05::cp_async16(hbf + half * kHS + t * 8, D.hl + (size_t)b * D.Dtot + t * 8);
+            else *reinterpret_cast<uint4 *>(hbf + half * kHS + t * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
         // the lead warp's operands (two channels per lane), all in flight together
         const size_t at = (size_t)b * C + h * kC + 2 * lane;
         const int ch = h * kC + 2 * lane;
@@ -372,39 +481,51 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
             gb = Ly.gn_b != nullptr ? ld_par2(Ly.gn_b + ch) : make_float2(0.f, 0.f);
         }
         PROF_POINT(fine, 1);
-        tc05::cp_async_wait<0>();                                            // this half's up-projection rows
-        half_bar(half);
+        tc05::cp_async_commit();
+        tc05::cp_async_wait<0>();                                            // the head's up-projection rows, the hl rows
+        __syncthreads();
         PROF_POINT(fine, 2);
+        // LoRA up-projections of both rows on the tensor cores: D[16 x 8] = A[16 x K] B[K x 8] with rows 0 / 1 of A the
+        // two halves' hl rows (the other 14 are zero), B = 8 channels of the staged [64, rank] matrix (K contiguous: the
+        // "col" operand as it lies).  Warp w: channels 8 (w & 7) .., LoRAs {w, a} (w < 8) or {v, g}.
         {
-            int off = 0;
+            const int nt = warp & 7, grp = warp >> 3;
+            int off_h = 0, off_w = 0;
 #pragma unroll 1
             for (int L = 0; L < 4; L++) {
-                const int Dl = D.D[L], n = Dl >> 2;
-                float acc = 0.f;
-                if (Ly.up[L] != nullptr) {
-                    const bf16 *wrow = upw + (size_t)kC * off + (size_t)i * Dl + p * n;
-                    const float *hv = hls + off + p * n;
+                const int Dl = D.D[L];
+                if ((L >> 1) == grp && Ly.up[L] != nullptr) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const bf16 *ap = hbf + g * kHS + off_h + 2 * q4;                       // rows >= 2 are zero
+                    const bf16 *bp = upw + off_w + (nt * 8 + g) * (Dl + 8) + 2 * q4;
 #pragma unroll 1
-                    for (int e = 0; e < n; e += 8) {
-                        float f[8];
-                        unpack8(*reinterpret_cast<const uint4 *>(wrow + e), f);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) acc = fmaf(f[q], hv[e + q], acc);
+                    for (int ks = 0; ks < Dl; ks += 16) {
+                        uint32_t af[4];
+                        af[0] = g < 2 ? *reinterpret_cast<const uint32_t *>(ap + ks) : 0u;
+                        af[1] = 0u;
+                        af[2] = g < 2 ? *reinterpret_cast<const uint32_t *>(ap + ks + 8) : 0u;
+                        af[3] = 0u;
+                        mma_bf16(acc, af, *reinterpret_cast<const uint32_t *>(bp + ks), *reinterpret_cast<const uint32_t *>(bp + ks + 8));
+                    }
+                    if (g < 2) {
+                        float *dst = smem + kHS + g * 768 + L * kC + nt * 8 + 2 * q4;          // los of half g
+                        *reinterpret_cast<float2 *>(dst) = make_float2(rbf(acc[0]), rbf(acc[1]));
                     }
                 }
-                acc = quad_sum(acc);
-                if (p == 0) los[L * kC + i] = rbf(acc);
-                off += Dl;
+                off_h += Dl;
+                off_w += kC * (Dl + 8);
             }
         }
-        half_bar(half);
+        __syncthreads();                                                     // los complete; everybody is done with the staged rows
         PROF_POINT(fine, 3);
-        stage_up(D, Ly, u + gridDim.x * 2, upw);                              // next round's rows, behind the rest of this one
+        // next round's rows, issued by the 14 warps that now wait for the two lead warps
+        if (q + (int)gridDim.x < NP && !lead_warp) stage_up(D, Ly, (q + gridDim.x) % H, upw, (int)threadIdx.x - 32 - 32 * half, kThreads - 64);
         tc05::cp_async_commit();
         PROF_POINT(fine, 4);
         float g0 = 0.f, g1 = 0.f;
         if (lead) {
             const int c0 = 2 * lane, c1 = c0 + 1;
+            const bool hv = Ly.up[2] != nullptr;
             g0 = los[3 * kC + c0]; g1 = los[3 * kC + c1];
             const float wa = rbf(neg_softplus_neg(w0.x + los[c0]) - 0.5f), wb = rbf(neg_softplus_neg(w0.y + los[c1]) - 0.5f);
             vec[c0] = expf(-expf(wa)); vec[c1] = expf(-expf(wb));                          // decay (wkv7_cuda.cu:24)
@@ -412,49 +533,59 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
             const float ua = k2.x * kk_.x, ub = k2.y * kk_.y;
             const float inv = 1.f / fmaxf(sqrtf(warp_sum(fmaf(ua, ua, ub * ub))), 1e-12f);
             const float kka = rbf(ua * inv), kkb = rbf(ub * inv);
-            if (first_layer) {
-                st2(D.vfirst + at, v2.x, v2.y);
+            if (first_layer || !hv) {
+                if (first_layer) st2(D.vfirst + at, v2.x, v2.y);
             } else {
                 v2.x = rbf(v2.x + (vf.x - v2.x) * sigmoidf_(v0.x + los[2 * kC + c0]));
                 v2.y = rbf(v2.y + (vf.y - v2.y) * sigmoidf_(v0.y + los[2 * kC + c1]));
             }
             k2.x = rbf(k2.x * (1.f + (aa - 1.f) * ka.x));
             k2.y = rbf(k2.y * (1.f + (ab - 1.f) * ka.y));
-            vec[1 * kC + c0] = r2.x; vec[1 * kC + c1] = r2.y;
-            vec[2 * kC + c0] = k2.x; vec[2 * kC + c1] = k2.y;
-            vec[3 * kC + c0] = v2.x; vec[3 * kC + c1] = v2.y;
-            vec[4 * kC + c0] = -kka; vec[4 * kC + c1] = -kkb;
-            vec[5 * kC + c0] = rbf(kka * aa); vec[5 * kC + c1] = rbf(kkb * ab);
+            *reinterpret_cast<float2 *>(vec + 1 * kC + c0) = r2;
+            *reinterpret_cast<float2 *>(vec + 2 * kC + c0) = k2;
+            *reinterpret_cast<float2 *>(vec + 3 * kC + c0) = v2;
+            *reinterpret_cast<float2 *>(vec + 4 * kC + c0) = make_float2(-kka, -kkb);
+            *reinterpret_cast<float2 *>(vec + 5 * kC + c0) = make_float2(rbf(kka * aa), rbf(kkb * ab));
         }
         half_bar(half);
         PROF_POINT(fine, 5);
-        {
-            float S[16];
-#pragma unroll
-            for (int j = 0; j < 4; j++) { S[4 * j] = s4[j].x; S[4 * j + 1] = s4[j].y; S[4 * j + 2] = s4[j].z; S[4 * j + 3] = s4[j].w; }
+        if (valid) {
+            // thread (i, p) owns value row i and keys 16m + 4p .. + 3, m < 4: same ownership and summation order as the
+            // stand-alone step kernel (wkv7_scan.cu::wkv7_step_kernel); the six 64-vectors are read as 16-byte pieces
             float sa = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; j++) sa = fmaf(S[j], vec[4 * kC + 16 * (j >> 2) + 4 * p + (j & 3)], sa);
+            for (int m = 0; m < 4; m++) {
+                const float4 av = *reinterpret_cast<const float4 *>(vec + 4 * kC + 16 * m + 4 * p);
+                sa = fmaf(s4[m].x, av.x, sa); sa = fmaf(s4[m].y, av.y, sa); sa = fmaf(s4[m].z, av.z, sa); sa = fmaf(s4[m].w, av.w, sa);
+            }
             sa = quad_sum(sa);
             const float vi = vec[3 * kC + i];
             float yy = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int cc = 16 * (j >> 2) + 4 * p + (j & 3);
-                S[j] = fmaf(S[j], vec[cc], fmaf(sa, vec[5 * kC + cc], vec[2 * kC + cc] * vi));
-                yy = fmaf(S[j], vec[1 * kC + cc], yy);
+            for (int m = 0; m < 4; m++) {
+                const int cc = 16 * m + 4 * p;
+                const float4 dv = *reinterpret_cast<const float4 *>(vec + cc), qv = *reinterpret_cast<const float4 *>(vec + 1 * kC + cc),
+                             kv = *reinterpret_cast<const float4 *>(vec + 2 * kC + cc), bv = *reinterpret_cast<const float4 *>(vec + 5 * kC + cc);
+                float4 S = s4[m];
+                S.x = fmaf(S.x, dv.x, fmaf(sa, bv.x, kv.x * vi)); yy = fmaf(S.x, qv.x, yy);
+                S.y = fmaf(S.y, dv.y, fmaf(sa, bv.y, kv.y * vi)); yy = fmaf(S.y, qv.y, yy);
+                S.z = fmaf(S.z, dv.z, fmaf(sa, bv.z, kv.z * vi)); yy = fmaf(S.z, qv.z, yy);
+                S.w = fmaf(S.w, dv.w, fmaf(sa, bv.w, kv.w * vi)); yy = fmaf(S.w, qv.w, yy);
+                s4[m] = S;
             }
             yy = quad_sum(yy);
-#pragma unroll
-            for (int j = 0; j < 4; j++) __stcg(srow + 4 * j, make_float4(S[4 * j], S[4 * j + 1], S[4 * j + 2], S[4 * j + 3]));
             if (p == 0) ys[i] = rbf(yy);
         }
         half_bar(half);
         PROF_POINT(fine, 6);
+        if (valid) {                                                         // the new state leaves behind the barrier
+#pragma unroll
+            for (int m = 0; m < 4; m++) __stcg(srow + 4 * m, s4[m]);
+        }
         if (lead) {
-            const float y0 = ys[2 * lane], y1 = ys[2 * lane + 1];
-            const float mu = warp_sum(y0 + y1) * (1.f / kC);
-            const float d0 = y0 - mu, d1 = y1 - mu;
+            const float2 y = *reinterpret_cast<const float2 *>(ys + 2 * lane);
+            const float mu = warp_sum(y.x + y.y) * (1.f / kC);
+            const float d0 = y.x - mu, d1 = y.y - mu;
             const float rstd = rsqrtf(warp_sum(fmaf(d0, d0, d1 * d1)) * (1.f / kC) + D.gn_eps);
             const float sb = warp_sum(fmaf(r2.x * k2.x, rk.x, r2.y * k2.y * rk.y));
             st2(D.o + at, (rbf(d0 * rstd * gw.x + gb.x) + sb * v2.x) * g0, (rbf(d1 * rstd * gw.y + gb.y) + sb * v2.y) * g1);
@@ -465,32 +596,16 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
 }
 
 // ---- skinny GEMM phase ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-struct TileRef { int job, n0, ntile; };
-__device__ __forceinline__ TileRef locate(const Phase &P, int t, int t1) {
-    TileRef r{0, 0, 0};
-    if (t >= t1) return r;
-    int j = 0;
-#pragma unroll 1
-    while (j + 1 < P.njobs && t >= P.job[j + 1].tile0) j++;
-    const int lt = t - P.job[j].tile0, jt = (P.job[j].N + 7) >> 3;
-    r.job = j;
-    r.n0 = lt * 8;
-    r.ntile = min(2, min(jt - lt, t1 - t));
-    return r;
-}
+// weight fragments of up to two 8-column tiles: wp = this lane's row of the first tile at its k offset; rows_left /
+// k_left bound what exists (last tile of an odd vocabulary, K smaller than the 16 warps' slices)
 template <int NKB>
-__device__ __forceinline__ void load_w(const Job &J, const TileRef &r, int warp, int g, int q, uint4 (&wv)[2][NKB]) {
+__device__ __forceinline__ void load_w(const bf16 *wp, int ldw, int ntile, int rows_left, int k_left, uint4 (&wv)[2][NKB]) {
 #pragma unroll
     for (int tt = 0; tt < 2; tt++)
 #pragma unroll
         for (int kb = 0; kb < NKB; kb++) {
-            const int kblk = warp * NKB + kb, n = r.n0 + tt * 8 + g;
-            const bool ok = tt < r.ntile && n < J.N && kblk * 32 < J.K;
-            wv[tt][kb] = ok ? ldg_nc_v4(J.W + (size_t)n * J.ldw + kblk * 32 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+            const bool ok = tt < ntile && tt * 8 < rows_left && kb * 32 < k_left;
+            wv[tt][kb] = ok ? ldg_nc_v4(wp + (size_t)tt * 8 * ldw + kb * 32) : make_uint4(0u, 0u, 0u, 0u);
         }
 }
 // the LoRA down-projections' activations: rare tiles, kept out of the hot code
@@ -499,146 +614,99 @@ __device__ __noinline__ float epi_act(float v, int epi) {
 }
 
 template <int NKB>
-__device__ __noinline__ void phase_gemm(const Phase &P, int B, float *red, long long *fine) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int t0 = (int)((long long)blockIdx.x * P.tiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * P.tiles / gridDim.x);
-    uint32_t af[NKB][2][2][4];      // [k block][m tile][mma of the block][a0..a3], already in the instruction's register order
-    uint4 wv[2][NKB];
-    int a_job = -1, t = t0;
+__device__ __noinline__ void phase_gemm(const Phase &P, int t0, int t1, int B, float *red, long long *fine) {
+    if (t0 >= t1) return;
     PROF_POINT(fine, 0);
-    TileRef cur = locate(P, t, t1);
-    if (cur.ntile) load_w<NKB>(P.job[cur.job], cur, warp, g, q, wv);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    const int koff = warp * NKB * 32 + q * 8;              // this lane's first k of its warp's slice
+    int j = 0;
+    while (j + 1 < P.njobs && t0 >= P.job[j + 1].tile0) j++;
+    int t = t0;
 #pragma unroll 1
-    while (cur.ntile) {
-        PROF_POINT(fine, 1);
-        const Job &J = P.job[cur.job];
-        if (cur.job != a_job) {
-            a_job = cur.job;
+    while (t < t1) {                                        // one job (projection) at a time: its fields live in registers
+        const Job J = P.job[j];
+        const int jend = min(t1, J.tile0 + ((J.N + 7) >> 3)), k_left = J.K - koff;
+        int n0 = (t - J.tile0) * 8;
+        const bf16 *wp = J.W + (size_t)(n0 + g) * J.ldw + koff;
+        uint4 wv[2][NKB];
+        load_w<NKB>(wp, J.ldw, jend - t, J.N - n0 - g, k_left, wv);
+        uint32_t af[NKB][2][2][4];  // [k block][m tile][mma of the block][a0..a3], already in the instruction's register order
 #pragma unroll
-            for (int kb = 0; kb < NKB; kb++)
+        for (int kb = 0; kb < NKB; kb++)
 #pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    const int kblk = warp * NKB + kb, row = mt * 16 + g;
-                    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;          // rows g and g + 8 of the m tile
-                    if (kblk * 32 < J.K) {
-                        const bf16 *src = J.A + (size_t)row * J.lda + kblk * 32 + q * 8;
-                        lo = __ldcg(reinterpret_cast<const uint4 *>(src));
-                        hi = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)8 * J.lda));
+            for (int mt = 0; mt < 2; mt++) {
+                uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;              // rows g and g + 8 of the m tile
+                if (kb * 32 < k_left) {
+                    const bf16 *src = J.A + (size_t)(mt * 16 + g) * J.lda + koff + kb * 32;
+                    lo = __ldcg(reinterpret_cast<const uint4 *>(src));
+                    hi = __ldcg(reinterpret_cast<const uint4 *>(src + (size_t)8 * J.lda));
+                }
+                // physical k = 8q + 4j + {0,1} <-> logical k = 2q + {0,1}; 8q + 4j + {2,3} <-> 2q + 8 + {0,1} (mma j = 0, 1)
+                af[kb][mt][0][0] = lo.x; af[kb][mt][0][1] = hi.x; af[kb][mt][0][2] = lo.y; af[kb][mt][0][3] = hi.y;
+                af[kb][mt][1][0] = lo.z; af[kb][mt][1][1] = hi.z; af[kb][mt][1][2] = lo.w; af[kb][mt][1][3] = hi.w;
+            }
+#pragma unroll 1
+        while (t < jend) {
+            PROF_POINT(fine, 1);
+            const int ntile = min(2, jend - t);
+            float acc[2][2][4];
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[tt][mt][e] = 0.f;
+#pragma unroll
+            for (int tt = 0; tt < 2; tt++)
+#pragma unroll
+                for (int kb = 0; kb < NKB; kb++)
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) {
+                        mma_bf16(acc[tt][mt], af[kb][mt][0], wv[tt][kb].x, wv[tt][kb].y);
+                        mma_bf16(acc[tt][mt], af[kb][mt][1], wv[tt][kb].z, wv[tt][kb].w);
                     }
-                    // physical k = 8q + 4j + {0,1} <-> logical k = 2q + {0,1}; 8q + 4j + {2,3} <-> 2q + 8 + {0,1} (mma j = 0, 1)
-                    af[kb][mt][0][0] = lo.x; af[kb][mt][0][1] = hi.x; af[kb][mt][0][2] = lo.y; af[kb][mt][0][3] = hi.y;
-                    af[kb][mt][1][0] = lo.z; af[kb][mt][1][1] = hi.z; af[kb][mt][1][2] = lo.w; af[kb][mt][1][3] = hi.w;
-                }
-        }
-        float acc[2][2][4];
+            PROF_POINT(fine, 2);
+            wp += (size_t)16 * J.ldw;
+            if (t + 2 < jend) load_w<NKB>(wp, J.ldw, jend - t - 2, J.N - n0 - 16 - g, k_left, wv);      // in flight during the reduction
 #pragma unroll
-        for (int tt = 0; tt < 2; tt++)
+            for (int tt = 0; tt < 2; tt++)
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
+                for (int mt = 0; mt < 2; mt++)
+                    *reinterpret_cast<float4 *>(red + ((warp * 2 + tt) * 2 + mt) * 128 + lane * 4) =
+                        make_float4(acc[tt][mt][0], acc[tt][mt][1], acc[tt][mt][2], acc[tt][mt][3]);
+            __syncthreads();
+            PROF_POINT(fine, 3);
+            {
+                const int tt = threadIdx.x >> 8, idx = threadIdx.x & 255;
+                float s = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; j++) acc[tt][mt][j] = 0.f;
-#pragma unroll
-        for (int tt = 0; tt < 2; tt++)
-#pragma unroll
-            for (int kb = 0; kb < NKB; kb++)
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    mma_bf16(acc[tt][mt], af[kb][mt][0], wv[tt][kb].x, wv[tt][kb].y);
-                    mma_bf16(acc[tt][mt], af[kb][mt][1], wv[tt][kb].z, wv[tt][kb].w);
-                }
-        PROF_POINT(fine, 2);
-        const TileRef nxt = locate(P, t + cur.ntile, t1);
-        if (nxt.ntile) load_w<NKB>(P.job[nxt.job], nxt, warp, g, q, wv);          // in flight during the reduction
-#pragma unroll
-        for (int tt = 0; tt < 2; tt++)
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-                *reinterpret_cast<float4 *>(red + ((warp * 2 + tt) * 2 + mt) * 128 + lane * 4) =
-                    make_float4(acc[tt][mt][0], acc[tt][mt][1], acc[tt][mt][2], acc[tt][mt][3]);
-        __syncthreads();
-        PROF_POINT(fine, 3);
-        {
-            const int tt = threadIdx.x >> 8, idx = threadIdx.x & 255;
-            float s = 0.f;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) s += red[(w * 2 + tt) * 256 + idx];
-            const int mt = idx >> 7, ln = (idx >> 2) & 31, j = idx & 3;
-            const int row = mt * 16 + (ln >> 2) + ((j >> 1) << 3), n = cur.n0 + tt * 8 + (ln & 3) * 2 + (j & 1);
-            if (tt < cur.ntile && row < B && n < J.N) {
-                const size_t at = (size_t)row * J.ldo + n;
-                const int epi = J.epi;
-                if (epi == kEpiF32) {
-                    static_cast<float *>(J.out)[at] = s;
-                } else if (epi == kEpiLogits) {
-                    static_cast<float *>(J.out)[at] = rbf(s);
-                } else {
-                    float v = rbf(s);
-                    if (epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
-                    else if (epi != kEpiBf16) v = epi_act(v, epi);
-                    static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
+                for (int w = 0; w < kWarps; w++) s += red[(w * 2 + tt) * 256 + idx];
+                __syncthreads();                 // the reduction buffer is free; the store below has no barrier behind it
+                const int mt = idx >> 7, ln = (idx >> 2) & 31, e = idx & 3;
+                const int row = mt * 16 + (ln >> 2) + ((e >> 1) << 3), n = n0 + tt * 8 + (ln & 3) * 2 + (e & 1);
+                if (tt < ntile && row < B && n < J.N) {
+                    const size_t at = (size_t)row * J.ldo + n;
+                    if (J.epi == kEpiF32) {
+                        static_cast<float *>(J.out)[at] = s;
+                    } else if (J.epi == kEpiLogits) {
+                        static_cast<float *>(J.out)[at] = rbf(s);
+                    } else {
+                        float v = rbf(s);
+                        if (J.epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
+                        else if (J.epi != kEpiBf16) v = epi_act(v, J.epi);
+                        static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
+                    }
                 }
             }
+            PROF_POINT(fine, 4);
+            if (fine != nullptr) fine += 4;
+            t += ntile;
+            n0 += 16;
         }
-        __syncthreads();
-        PROF_POINT(fine, 4);
-        if (fine != nullptr) fine += 4;
-        t += cur.ntile;
-        cur = nxt;
+        j++;
     }
 }
 
-// ---- L2 prefetch, one to two phases ahead ------------------------------------------------------------------------------
-// What a phase will read from HBM (weights, parameters, recurrent state: nothing of it depends on this token) is pulled
-// into L2 while the phases before it run, so that after a barrier only L2 latencies are left on the critical path.  One
-// bulk-prefetch instruction per contiguous span, executed by the copy engine: a `prefetch.global.L2` per 128-byte line
-// costs the SM ~6 cycles each (measured: 0.4 us per 8-row weight tile), as much as loading the data.
-__device__ __forceinline__ void prefetch_bulk(const void *p, unsigned bytes) {        // 16-byte aligned, bytes % 16 == 0
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
-__device__ __noinline__ void prefetch_gemm(const Phase &P) {
-    const int t0 = (int)((long long)blockIdx.x * P.tiles / gridDim.x), t1 = (int)((long long)(blockIdx.x + 1) * P.tiles / gridDim.x);
-    if (threadIdx.x >= 8) return;
-    int j = 0;
-#pragma unroll 1
-    for (int t = t0; t < t1; t++) {
-        while (j + 1 < P.njobs && t >= P.job[j + 1].tile0) j++;
-        const Job &J = P.job[j];
-        const int n0 = (t - J.tile0) * 8, rows = min(8, J.N - n0);
-        if (J.ldw == J.K) {                                                  // the tile's rows are one contiguous span
-            if (threadIdx.x == 0) prefetch_bulk(J.W + (size_t)n0 * J.ldw, (unsigned)(rows * J.K * 2));
-        } else if ((int)threadIdx.x < rows) {
-            prefetch_bulk(J.W + (size_t)(n0 + threadIdx.x) * J.ldw, (unsigned)(J.K * 2));
-        }
-    }
-}
-__device__ __noinline__ void prefetch_wkv(const Desc &D, const Layer &Ly) {
-    const int tid = threadIdx.x;
-    if (tid >= 32) return;
-#pragma unroll 1
-    for (int u = blockIdx.x * 2; u < D.B * D.H; u += gridDim.x * 2) {
-        const int n = min(2, D.B * D.H - u);                             // the two units the halves of the CTA take
-        if (tid == 0) {
-            prefetch_bulk(Ly.state + (size_t)u * kC * kC, (unsigned)(n * kC * kC * sizeof(float)));
-        } else if (tid <= 8) {                                           // (unit, LoRA) pairs
-            const int k = (tid - 1) >> 2, L = (tid - 1) & 3;
-            if (k < n && Ly.up[L] != nullptr)
-                prefetch_bulk(Ly.up[L] + (size_t)((u + k) % D.H) * kC * D.D[L], (unsigned)(kC * D.D[L] * sizeof(bf16)));
-        } else if (tid <= 24) {                                          // (unit, per-channel vector) pairs
-            const int k = (tid - 9) >> 3;
-            const bf16 *q = (&Ly.w0)[(tid - 9) & 7];                     // w0, a0, v0, k_k, k_a, r_k, gn_w, gn_b
-            if (k < n && q != nullptr) prefetch_bulk(q + (size_t)((u + k) % D.H) * kC, kC * sizeof(bf16));
-        }
-    }
-}
-// n per-channel vectors [C] of a row phase (rows b = blockIdx.x, blockIdx.x + grid, ...: only those CTAs read them); the
-// last one is the [B, C] token-shift state when `last_is_rows`: this CTA's row of it
-__device__ __noinline__ void prefetch_vecs(const Desc &D, const bf16 *const *v, int n, bool last_is_rows) {
-    if ((int)blockIdx.x >= D.B || (int)threadIdx.x >= n) return;
-    const bf16 *q = v[threadIdx.x];
-    if (q == nullptr) return;
-    if (last_is_rows && (int)threadIdx.x == n - 1) q += (size_t)blockIdx.x * D.C;
-    prefetch_bulk(q, (unsigned)(D.C * sizeof(bf16)));
-}
 __device__ __forceinline__ void copy_async(void *smem_dst, const void *gsrc, int bytes) {      // bytes % 16 == 0
 #pragma unroll 1
     for (int i = threadIdx.x * 16; i < bytes; i += kThreads * 16)
@@ -650,10 +718,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
     extern __shared__ __align__(16) float smem[];      // [kRedFloats] scratch of the running phase, then the staged LoRA rows
     __shared__ Desc sD;             // the plan lives in shared memory: a descriptor read from HBM at the head of every
     __shared__ Layer sL[2];         // phase would put a DRAM round trip in front of each of the 170 phases
+    __shared__ Ranges sR;
     static_assert(sizeof(Desc) % 16 == 0 && sizeof(Layer) % 16 == 0, "cp.async pieces");
     static_assert(offsetof(Layer, att_shift) - offsetof(Layer, ln1_w) == 8 * sizeof(void *), "ln1 pointer group");
     static_assert(offsetof(Layer, ffn_shift) - offsetof(Layer, ln2_w) == 3 * sizeof(void *), "ln2 pointer group");
-    static_assert(offsetof(Layer, gn_b) - offsetof(Layer, w0) == 7 * sizeof(void *), "wkv pointer group");
+    static_assert(offsetof(Desc, lnf_b) - offsetof(Desc, lnf_w) == sizeof(void *), "final norm pointer group");
     copy_async(&sD, Dp, sizeof(Desc));
     tc05::cp_async_commit();
     tc05::cp_async_wait<0>();
@@ -664,65 +733,57 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
     tc05::cp_async_commit();
     tc05::cp_async_wait<0>();
     __syncthreads();
-    float *red_rows = smem + kRedFloats - 64;   // reductions of the row phases (xs = smem[0..C), C <= 2048)
+    if (threadIdx.x < 6) {          // this CTA's share of the tiles of each kind of GEMM phase (the same in every layer > 0)
+        const int k = threadIdx.x;
+        const Phase &P = k == kRgP2First ? sL[0].p2 : k == kRgP2 ? sL[D.L > 1 ? 1 : 0].p2 : k == kRgP4 ? sL[0].p4
+                       : k == kRgP6 ? sL[0].p6 : k == kRgP7 ? sL[0].p7 : D.head;
+        sR.r[k][0] = (int)((unsigned)blockIdx.x * (unsigned)P.tiles / gridDim.x);
+        sR.r[k][1] = (int)((unsigned)(blockIdx.x + 1) * (unsigned)P.tiles / gridDim.x);
+    }
+    __syncthreads();
+    float *red_rows = smem + kRedFloats - 64;   // reductions of the row phases
     bf16 *upw = reinterpret_cast<bf16 *>(smem + kRedFloats);
-    const int nprof = 8 * D.L + 4, half = threadIdx.x >> 8;
-    // fine stamps of layer 1 (cycles): [0..] main loop marks, [16..] projections, [32..] wkv rounds, [48..] output projection, [64..] key
+    const int nprof = 8 * D.L + 4;
+    const SyncCtx cx{&sD, &sR, a.prof, nprof};
+    // fine stamps of layer 1 (cycles): [16..] projections, [32..] wkv rounds, [48..] output projection, [64..] key
     long long *fine = a.prof != nullptr ? reinterpret_cast<long long *>(a.prof + (size_t)nprof * (1 + 2 * kProfCtas)) : nullptr;
     unsigned epoch = 0;
     if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) a.prof[0] = globaltimer();
-    prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&sL[0].ln1_w), 9, true);
-    prefetch_vecs(D, &D.ln0_w, 2, false);
-    prefetch_gemm(sL[0].p2);
+    if ((threadIdx.x >> 5) == 1) {
+        prefetch_tiles(sL[0].p2, sR.r[kRgP2First][0], sR.r[kRgP2First][1], threadIdx.x & 31);
+    }
+    const int NP = D.H * ((D.B + 1) >> 1);
 #pragma unroll 1
     for (int l = 0; l < D.L; l++) {
-        const Layer &Ly = sL[l & 1];
-        if (!(a.debug_skip & 1)) phase_rows(D, Ly, kRowLn1, l == 0, a, smem, red_rows);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        if (l == 1) PROF_POINT(fine, 3);
-        if (!(a.debug_skip & 2)) prefetch_wkv(D, Ly);
-        if (l == 1) PROF_POINT(fine, 4);
-        phase_gemm<NKB>(Ly.p2, D.B, smem, (l == 1 && fine != nullptr) ? fine + 16 : nullptr);
-        if (l == 1) PROF_POINT(fine, 5);
-        if (!(a.debug_skip & 2)) stage_up(D, Ly, blockIdx.x * 2 + half, upw + (size_t)half * kC * D.Dtot);      // first round of the wkv phase
+        const Layer &Ly = sL[l & 1], &Nx = sL[(l + 1) & 1];
+        const bool f1 = l == 1 && fine != nullptr, last = l + 1 == D.L;
+        const int rp2 = l == 0 ? kRgP2First : kRgP2;
+        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn1, l == 0, a, red_rows);
+        epoch = grid_sync(cx, epoch, kPfWkv, &Ly, &Nx);
+        phase_gemm<NKB>(Ly.p2, sR.r[rp2][0], sR.r[rp2][1], D.B, smem, f1 ? fine + 16 : nullptr);
+        if (!(a.debug_skip & 2) && (int)blockIdx.x < NP) stage_up(D, Ly, blockIdx.x % D.H, upw, threadIdx.x, kThreads);      // first round of the wkv phase
         tc05::cp_async_commit();
-        if (l == 1) PROF_POINT(fine, 6);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        if (l == 1) PROF_POINT(fine, 0);
-        prefetch_gemm(Ly.p4);
-        if (l == 1) PROF_POINT(fine, 1);
-        prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&Ly.ln2_w), 4, true);
-        if (l == 1) PROF_POINT(fine, 2);
-        if (!(a.debug_skip & 2)) phase_wkv(D, Ly, l == 0, smem, upw, (l == 1 && fine != nullptr) ? fine + 32 : nullptr);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        prefetch_gemm(Ly.p6);
-        phase_gemm<NKB>(Ly.p4, D.B, smem, (l == 1 && fine != nullptr) ? fine + 48 : nullptr);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        if (!(a.debug_skip & 1)) phase_rows(D, Ly, kRowLn2, false, a, smem, red_rows);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        prefetch_gemm(Ly.p7);
-        phase_gemm<NKB>(Ly.p6, D.B, smem, (l == 1 && fine != nullptr) ? fine + 64 : nullptr);
+        epoch = grid_sync(cx, epoch, kPfOut, &Ly, &Nx);
+        if (!(a.debug_skip & 2)) phase_wkv(D, Ly, l == 0, smem, upw, f1 ? fine + 32 : nullptr);
+        epoch = grid_sync(cx, epoch, kPfKey, &Ly, &Nx);
+        phase_gemm<NKB>(Ly.p4, sR.r[kRgP4][0], sR.r[kRgP4][1], D.B, smem, f1 ? fine + 48 : nullptr);
+        epoch = grid_sync(cx, epoch, kPfValue, &Ly, &Nx);
+        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn2, false, a, red_rows);
         tc05::cp_async_wait<0>();                        // own pieces of layer l + 1's descriptor; the barrier publishes them
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-        if (l + 1 < D.L) {
-            const Layer &Nx = sL[(l + 1) & 1];
-            prefetch_vecs(D, reinterpret_cast<const bf16 *const *>(&Nx.ln1_w), 9, true);
-            prefetch_gemm(Nx.p2);
-        } else {
-            prefetch_vecs(D, &D.lnf_w, 2, false);
-            prefetch_gemm(D.head);
-        }
-        phase_gemm<NKB>(Ly.p7, D.B, smem, nullptr);
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        epoch = grid_sync(cx, epoch, kPfNone, &Ly, &Nx);
+        phase_gemm<NKB>(Ly.p6, sR.r[kRgP6][0], sR.r[kRgP6][1], D.B, smem, f1 ? fine + 64 : nullptr);
+        epoch = grid_sync(cx, epoch, last ? kPfHead : kPfNextProj, &Ly, &Nx);
+        phase_gemm<NKB>(Ly.p7, sR.r[kRgP7][0], sR.r[kRgP7][1], D.B, smem, nullptr);
+        epoch = grid_sync(cx, epoch, kPfNone, &Ly, &Nx);
         // every thread is past its last use of sL[l & 1]: bring in layer l + 2
         if (l + 2 < D.L) copy_async(&sL[l & 1], D.layers + l + 2, sizeof(Layer));
         tc05::cp_async_commit();
     }
-    phase_rows(D, sL[0], kRowFinal, false, a, smem, red_rows);
-    epoch = grid_sync(D.bar, epoch, a.prof, nprof);
-    phase_gemm<NKB>(D.head, D.B, smem, nullptr);
+    phase_rows<NKB / 2>(D, sL[0], kRowFinal, false, a, red_rows);
+    epoch = grid_sync(cx, epoch, kPfNone, &sL[0], &sL[0]);
+    phase_gemm<NKB>(D.head, sR.r[kRgHead][0], sR.r[kRgHead][1], D.B, smem, nullptr);
     if (a.greedy) {
-        epoch = grid_sync(D.bar, epoch, a.prof, nprof);
+        epoch = grid_sync(cx, epoch, kPfNone, &sL[0], &sL[0]);
         phase_argmax(D, a, red_rows);
     }
     // the last CTA out resets the counters for the next launch (every CTA has left its last barrier by then)
@@ -801,6 +862,7 @@ cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, c
     D.Dtot = 0;
     for (int i = 0; i < 4; i++) { D.D[i] = d[RWKVTTS_DEC_DW + i]; D.Dtot += D.D[i]; }
     D.nchunk = F / C;
+    for (int i = 0; i < 4; i++) D.inv[i] = ((1 << 20) + D.D[i] / 8 - 1) / (D.D[i] / 8);
     D.ln_eps = eps[0]; D.gn_eps = eps[1];
     auto bp = [](const void *p) { return static_cast<const bf16 *>(p); };
     D.emb = bp(mp[RWKVTTS_DEC_EMB]); D.ln0_w = bp(mp[RWKVTTS_DEC_LN0_W]); D.ln0_b = bp(mp[RWKVTTS_DEC_LN0_B]);
@@ -858,7 +920,7 @@ cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, c
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hi.device)) != cudaSuccess) return e;
     hi.nkb = C <= 1024 ? 2 : 4;
     // dynamic shared memory: the phase scratch + the staged LoRA up-projection rows of two (b, head) units
-    hi.smem = (size_t)kRedFloats * sizeof(float) + (size_t)2 * kC * D.Dtot * sizeof(bf16);
+    hi.smem = (size_t)kRedFloats * sizeof(float) + (size_t)kC * (D.Dtot + 4 * 8) * sizeof(bf16);
     const void *fn = hi.nkb == 2 ? (const void *)decode_step_kernel<2> : (const void *)decode_step_kernel<4>;
     if ((e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hi.smem)) != cudaSuccess) return e;
     e = hi.nkb == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_step_kernel<2>, kThreads, hi.smem)
