@@ -15,7 +15,10 @@
 // per-channel parameter gradients are accumulated in registers, reduced over the CTA's rows in shared memory and
 // written as one partial per CTA (summed by reduce_partials: deterministic, no atomics).
 // Arithmetic in fp32, one rounding to bf16 at the stores.
+#include "tc05.cuh"
 #include "wkv7_common.cuh"
+
+#include <cstdlib>
 
 namespace rwkvtts {
 namespace tmixf {
@@ -310,6 +313,129 @@ __global__ void __launch_bounds__(512) shift_mix_bwd4_kernel(const MixParams P) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// shift_mix backward, third form: the register pipeline of the form above keeps ONE row (7 x 8 bytes per thread) in flight
+// per warp -- 43 KB per SM against the ~1.5 us of loaded HBM latency is 2 TB/s (Little), which is what it reaches.  Here
+// the rows come in through a shared-memory ring filled with cp.async: 6 slots of (n + 1) rows, three rows (42 KB per CTA,
+// two CTAs per SM) always in flight, independent of the registers; a thread still owns four channels and reads its 8 bytes
+// of each array from the ring.  d[row + 1] and x[row] are carried in registers from the iteration before.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kRing = 6;
+template <int N>
+__global__ void __launch_bounds__(512) shift_mix_bwd_ring_kernel(const MixParams P) {
+    extern __shared__ __align__(16) unsigned char ring_dyn[];
+    float *smix = reinterpret_cast<float *>(ring_dyn);                       // [N][C]
+    bf16 *ring = reinterpret_cast<bf16 *>(smix + (size_t)N * P.C);            // [kRing][N + 1][C]: arrays 0..N-1 = d, N = x
+    const int C = P.C, tid = threadIdx.x, nthr = blockDim.x, c0 = tid * 4;
+    const int S = C / 8, lane_half = tid >= S ? 1 : 0, seg = tid - lane_half * S;      // nthr == 2 S: copy pieces
+    for (int e = tid; e < N * C; e += nthr) smix[e] = P.mix[e];
+    const long rows = (long)P.B * P.T;
+    const long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    if (r0 >= r1) {                                                          // no rows: the partial sums are zeros
+        float *dst = P.part + (size_t)blockIdx.x * N * C;
+        for (int e = tid; e < N * C; e += nthr) dst[e] = 0.f;
+        return;
+    }
+    auto slot = [&](long row, int a) { return ring + ((size_t)((row + kRing) % kRing) * (N + 1) + a) * C; };
+    const long lo = r0 > 0 ? r0 - 1 : 0;                                     // x[r0 - 1] is the lowest row anybody reads
+    auto issue = [&](long row) {                                             // one cp.async group per row, empty if not needed
+        if (row >= lo && row < rows) {
+#pragma unroll
+            for (int a = lane_half; a <= N; a += 2) {
+                const bf16 *src = (a < N ? P.dout[a] : P.x) + row * C + seg * 8;
+                tc05::cp_async16(slot(row, a) + seg * 8, src);
+            }
+        }
+        tc05::cp_async_commit();
+    };
+    auto mask_of = [&](long row) { return (P.mask != nullptr && row >= 0) ? __bfloat162float(P.mask[row]) : 1.f; };
+    long next = r1;
+#pragma unroll 1
+    for (int i = 0; i < 5; i++) issue(next--);                              // rows r1 (for d[row + 1]) .. r1 - 4
+    float acc[N][4], mixv[N][4];
+    __syncthreads();                                                         // smix is complete
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+        const float4 mx = *reinterpret_cast<const float4 *>(smix + s * C + c0);
+        mixv[s][0] = mx.x; mixv[s][1] = mx.y; mixv[s][2] = mx.z; mixv[s][3] = mx.w;
+#pragma unroll
+        for (int i = 0; i < 4; i++) acc[s][i] = 0.f;
+    }
+    const uint2 zero2 = make_uint2(0u, 0u);
+    uint2 xc = zero2;
+    // dx[t] = sum_s d_s[t] (1 - mix_s) + sum_s d_s[t+1] mix_s = A[t] - M[t] + M[t+1] with A = sum_s d_s, M = sum_s d_s mix_s:
+    // only M[t+1] (4 floats) is carried from the iteration before, not the six d rows
+    float mnext[4] = {0.f, 0.f, 0.f, 0.f};
+    float m = mask_of(r1 - 1), mb = mask_of(r1 - 2);
+    bool first_iter = true;
+#pragma unroll 1
+    for (long row = r1 - 1; row >= r0; row--) {
+        const float mb2 = mask_of(row - 2);                                  // used two iterations from now
+        tc05::cp_async_wait<2>();                                            // rows down to row - 1 have landed (own pieces)
+        __syncthreads();                                                     // ... everybody's; slot of row + 2 is free
+        issue(next--);                                                       // row - 4 into it
+        if (first_iter) {
+            first_iter = false;
+            xc = *reinterpret_cast<const uint2 *>(slot(row, N) + c0);
+            if (row + 1 < rows && !seq_last(P, row, rows)) {
+#pragma unroll
+                for (int s = 0; s < N; s++) {
+                    float d[4];
+                    unpack4h(*reinterpret_cast<const uint2 *>(slot(row + 1, s) + c0), d);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) mnext[i] = fmaf(d[i], mixv[s][i], mnext[i]);
+                }
+            }
+        }
+        const uint2 xb = row > 0 ? *reinterpret_cast<const uint2 *>(slot(row - 1, N) + c0) : zero2;
+        float x[4], xp[4];
+        unpack4h(xc, x);
+        unpack4h(xb, xp);
+        const float mbb = row > 0 ? mb : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { x[i] *= m; xp[i] *= mbb; }
+        if (seq_first(P, row)) {
+            if (P.prev != nullptr && P.first == nullptr) {
+                const uint2 pv = *reinterpret_cast<const uint2 *>(P.prev + (size_t)(row / P.T) * C + c0);
+                unpack4h(pv, xp);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) xp[i] = 0.f;
+            }
+        }
+        const bool last_of_seq = seq_last(P, row, rows);
+        float xx[4], asum[4] = {0.f, 0.f, 0.f, 0.f}, msum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; i++) xx[i] = rbf(xp[i] - x[i]);
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            float d[4];
+            unpack4h(*reinterpret_cast<const uint2 *>(slot(row, s) + c0), d);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[s][i] = fmaf(d[i], xx[i], acc[s][i]);
+                asum[i] += d[i];
+                msum[i] = fmaf(d[i], mixv[s][i], msum[i]);
+            }
+        }
+        float dx[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            dx[i] = (asum[i] - msum[i] + (last_of_seq ? 0.f : mnext[i])) * m;
+            mnext[i] = msum[i];
+        }
+        *reinterpret_cast<uint2 *>(P.dx + row * C + c0) = make_uint2(pack2(dx[0], dx[1]), pack2(dx[2], dx[3]));
+        xc = xb;
+        m = mb; mb = mb2;
+    }
+    tc05::cp_async_wait<0>();
+    float *dst = P.part + (size_t)blockIdx.x * N * C;
+#pragma unroll
+    for (int s = 0; s < N; s++)
+        *reinterpret_cast<float4 *>(dst + s * C + c0) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // prep
 // ------------------------------------------------------------------------------------------------------------------
 struct PrepParams {
@@ -497,6 +623,135 @@ __global__ void __launch_bounds__(kBwdThreads, 2) prep_bwd_kernel(const PrepPara
         }
     }
     write_partials<5>(acc, P.part, P.C, tpr, rl, cl, red);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// prep backward, second form: the 11 input rows of a token come in through a shared-memory ring filled with cp.async
+// (3 slots of 11 x C bf16, two rows -- 44 KB per CTA, three CTAs per SM -- in flight independent of the registers; the first
+// form holds one row per warp in registers: 58 % of HBM with its 40 accumulators at 128 registers).  A thread copies exactly
+// the 16-byte pieces it later reads (its 8 channels of every array), so the ring needs no CTA barrier: cp.async.wait_group
+// is all the synchronisation there is.  One row lane per CTA of C/8 threads; rows strided over the grid.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kPrepRing = 3, kPrepArrays = 11;
+__device__ __forceinline__ Row8 ld8s(const bf16 *p) {
+    Row8 r;
+    unpack8(*reinterpret_cast<const uint4 *>(p), r.v);
+    return r;
+}
+__global__ void __launch_bounds__(256) prep_bwd_ring_kernel(const PrepParams P) {
+    extern __shared__ __align__(16) unsigned char prep_dyn[];
+    bf16 *ring = reinterpret_cast<bf16 *>(prep_dyn);                         // [kPrepRing][kPrepArrays][C]
+    const int C = P.C, c0 = threadIdx.x * kVec;
+    const Row8 w0 = ld8f(P.w0 + c0), a0 = ld8f(P.a0 + c0), kk_ = ld8f(P.k_k + c0), ka = ld8f(P.k_a + c0);
+    const bool has_v = P.v_lo != nullptr, want_dv = P.dv != nullptr;
+    const Row8 v0 = has_v ? ld8f(P.v0 + c0) : zero8();
+    // arrays in ring order: k, w_lo, a_lo, dw, dk2, da_op, db_op, dv2, v, v_lo, v_first
+    const bf16 *const src[kPrepArrays] = {P.k, P.w_lo, P.a_lo, P.dw, P.dk2, P.da_op, P.db_op, want_dv ? P.dv2 : nullptr,
+                                          has_v ? P.v : nullptr, has_v ? P.v_lo : nullptr, has_v ? P.v_first : nullptr};
+    const long rows = (long)P.B * P.T;
+    auto issue = [&](long it) {
+        const long row = (long)blockIdx.x + it * gridDim.x;
+        if (row < rows) {
+            bf16 *dst = ring + (size_t)(it % kPrepRing) * kPrepArrays * C + c0;
+#pragma unroll
+            for (int a = 0; a < kPrepArrays; a++)
+                if (src[a] != nullptr) tc05::cp_async16(dst + (size_t)a * C, src[a] + row * C + c0);
+        }
+        tc05::cp_async_commit();
+    };
+    float acc[5][kVec];
+#pragma unroll
+    for (int s = 0; s < 5; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
+    issue(0);
+    issue(1);
+    auto mask_of = [&](long row) { return (P.mask != nullptr && row < rows) ? __bfloat162float(P.mask[row]) : 1.f; };
+    float m_next = mask_of(blockIdx.x);
+#pragma unroll 1
+    for (long it = 0;; it++) {
+        const long row = (long)blockIdx.x + it * gridDim.x;
+        if (row >= rows) break;
+        const float m = m_next, mk = P.mask_rwk ? m : 1.f;
+        m_next = mask_of(row + gridDim.x);
+        tc05::cp_async_wait<1>();                                            // this row's pieces (own) have landed
+        const bf16 *slot = ring + (size_t)(it % kPrepRing) * kPrepArrays * C + c0;
+        const size_t off = row * C + c0;
+        Row8 k = ld8s(slot);
+        const Row8 wl = ld8s(slot + (size_t)1 * C), al = ld8s(slot + (size_t)2 * C), dw = ld8s(slot + (size_t)3 * C),
+                   dk2 = ld8s(slot + (size_t)4 * C), da_op = ld8s(slot + (size_t)5 * C), db_op = ld8s(slot + (size_t)6 * C);
+        Row8 dv2 = zero8(), v = zero8(), vl = zero8(), vf = zero8();
+        if (want_dv) dv2 = ld8s(slot + (size_t)7 * C);
+        if (has_v) { v = ld8s(slot + (size_t)8 * C); vl = ld8s(slot + (size_t)9 * C); vf = ld8s(slot + (size_t)10 * C); }
+        issue(it + 2);                                                       // into the slot read one iteration ago
+        Row8 a, u, o;
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            k.v[i] *= mk;
+            a.v[i] = sigmoidf_(a0.v[i] + al.v[i]);
+            u.v[i] = k.v[i] * kk_.v[i];
+            ss = fmaf(u.v[i], u.v[i], ss);
+        }
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            o.v[i] = dw.v[i] * mk * sigmoidf_(-(w0.v[i] + wl.v[i]));
+            acc[0][i] += o.v[i];
+        }
+        st8(P.dw_lo + off, o);
+        const float n = fmaxf(sqrtf(head_sum(ss)), 1e-12f), inv = 1.f / n;
+        Row8 kk, dkk;
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            kk.v[i] = u.v[i] * inv;
+            dkk.v[i] = (db_op.v[i] * a.v[i] - da_op.v[i]) * m;
+            dot = fmaf(kk.v[i], dkk.v[i], dot);
+        }
+        dot = head_sum(dot);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            const float da = db_op.v[i] * kk.v[i] * m + dk2.v[i] * k.v[i] * ka.v[i];
+            o.v[i] = da * a.v[i] * (1.f - a.v[i]);
+            acc[1][i] += o.v[i];
+        }
+        st8(P.da_lo + off, o);
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            const float du = (dkk.v[i] - kk.v[i] * dot) * inv;
+            acc[3][i] = fmaf(du, k.v[i], acc[3][i]);
+            acc[4][i] = fmaf(dk2.v[i] * k.v[i], a.v[i] - 1.f, acc[4][i]);
+            o.v[i] = (du * kk_.v[i] + dk2.v[i] * (1.f + (a.v[i] - 1.f) * ka.v[i])) * mk;
+        }
+        st8(P.dk + off, o);
+        if (want_dv) {
+            if (has_v) {
+                Row8 dvl, dvf;
+#pragma unroll
+                for (int i = 0; i < kVec; i++) {
+                    const float s = sigmoidf_(v0.v[i] + vl.v[i]), g = dv2.v[i] * m, vm = v.v[i] * mk;
+                    o.v[i] = g * (1.f - s) * mk;
+                    dvf.v[i] = g * s;
+                    dvl.v[i] = g * (vf.v[i] - vm) * s * (1.f - s);
+                    acc[2][i] += dvl.v[i];
+                }
+                st8(P.dv + off, o);
+                st8(P.dv_lo + off, dvl);
+                st8(P.dv_first + off, dvf);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kVec; i++) o.v[i] = dv2.v[i] * m;
+                st8(P.dv + off, o);
+            }
+        }
+    }
+    tc05::cp_async_wait<0>();
+    float *dst = P.part + (size_t)blockIdx.x * 5 * C + c0;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        *reinterpret_cast<float4 *>(dst + (size_t)s * C) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+        *reinterpret_cast<float4 *>(dst + (size_t)s * C + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -968,6 +1223,24 @@ cudaError_t launch_shift_mix_bwd(int B, int T, int C, int n, const void *x, cons
     const size_t sh = g.red_bytes(n, C);
     count_launch(2);
     cudaError_t e;
+    static const int form = [] { const char *e = getenv("RWKVTTS_MIX_BWD"); return e != nullptr ? atoi(e) : 0; }();
+    if (form != 4 && C % 128 == 0 && C >= 512 && C <= 2048 && (long)B * T >= 64 && (n == 6 || n == 1)) {
+        // rows through a cp.async ring in shared memory (see shift_mix_bwd_ring_kernel); two CTAs per SM while they fit
+        const size_t shm = (size_t)n * C * sizeof(float) + (size_t)kRing * (n + 1) * C * sizeof(bf16);
+        int grid = 148 * (shm <= 110 * 1024 ? 2 : 1);
+        if (grid > g.grid) grid = g.grid;             // the caller's scratch holds g.grid partial rows
+        if (n == 6) {
+            e = cudaFuncSetAttribute(shift_mix_bwd_ring_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            if (e != cudaSuccess) return e;
+            shift_mix_bwd_ring_kernel<6><<<grid, C / 4, shm, st>>>(P);
+        } else {
+            e = cudaFuncSetAttribute(shift_mix_bwd_ring_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+            if (e != cudaSuccess) return e;
+            shift_mix_bwd_ring_kernel<1><<<grid, C / 4, shm, st>>>(P);
+        }
+        reduce_partials_kernel<<<(n * C + 31) / 32, 256, 0, st>>>(part, dmix, grid, n * C);
+        return cudaGetLastError();
+    }
     if (C % 128 == 0 && C >= 512 && C <= 2048 && (long)B * T >= 64) {
         // four channels per thread, one row lane per CTA of C/4 threads (see shift_mix_bwd4_kernel)
         int grid = 148 * 3;
@@ -1029,9 +1302,21 @@ cudaError_t launch_prep_bwd(int B, int T, int C, const void *k, const void *v, c
     P.B = B; P.T = T; P.C = C; P.mask_rwk = mask_rwk;
     const Geo g = geometry(B, T, C, 4, 4, kBwdThreads);
     const size_t sh = g.red_bytes(5, C);
+    count_launch(2);
+    static const int form = [] { const char *e = getenv("RWKVTTS_PREP_BWD"); return e != nullptr ? atoi(e) : 0; }();
+    if (form != 1 && C % 256 == 0 && C <= 2048 && (long)B * T >= 64) {
+        // rows through a cp.async ring in shared memory (see prep_bwd_ring_kernel)
+        const size_t shm = (size_t)kPrepRing * kPrepArrays * C * sizeof(bf16);
+        int grid = 148 * (shm <= 72 * 1024 ? 3 : 1);
+        if (grid > g.grid) grid = g.grid;             // the caller's scratch holds g.grid partial rows
+        cudaError_t e2 = cudaFuncSetAttribute(prep_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e2 != cudaSuccess) return e2;
+        prep_bwd_ring_kernel<<<grid, C / kVec, shm, st>>>(P);
+        reduce_partials_kernel<<<(5 * C + 31) / 32, 256, 0, st>>>(part, dparams, grid, 5 * C);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(prep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return e;
-    count_launch(2);
     prep_bwd_kernel<<<g.grid, g.threads, sh, st>>>(P);
     reduce_partials_kernel<<<(5 * C + 31) / 32, 256, 0, st>>>(part, dparams, g.grid, 5 * C);
     return cudaGetLastError();
