@@ -207,6 +207,12 @@ RWKVTTS_API int rwkvtts_grad_stat(const void *grad, int grad_is_bf16, long long 
  * D % 8 == 0. */
 RWKVTTS_API int rwkvtts_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows,
                                    int D, void *out, void *stream);
+/* rwkvtts_multi_copy: `count` contiguous gradient tensors (HOST arrays: device pointers 16-byte aligned, element offsets
+ * into `flat` that are multiples of 16 bytes, element counts) moved into a flat buffer by one launch per 128 tensors;
+ * accumulate[i] != 0 adds to what is there (micro-steps after the first).  elem_bytes 2 (bf16) or 4 (fp32).  What
+ * DeepSpeed's `contiguous_gradients` does per parameter (train_scripts/train_spark_rwkv7speech.py:483-516), per bucket. */
+RWKVTTS_API int rwkvtts_multi_copy(const void *const *srcs, const long long *dst_off, const long long *n, const int *accumulate,
+                                   int count, void *flat, int elem_bytes, void *stream);
 /* rwkvtts_ce_forward_backward: cross-entropy of a chunk of bf16 logits [rows, ld] (V valid columns, ld % 8 == 0),
  * loss and gradient in one pass, IN PLACE: loss_rows[r] (fp32) and logits[r,:] <- d loss / d logits * *scale_dev.
  * Rows with labels[r] == ignore_index give loss 0 and a zero gradient row.  The middle piece of the fused

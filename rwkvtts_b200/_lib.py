@@ -55,6 +55,8 @@ SYMBOLS = {
     "rwkvtts_adam_multi": (_i, [_fp, _fp, _fp, _vp, _i, _vp, _i, ctypes.c_longlong, _vp, _vp, _i,
                                 ctypes.POINTER(ctypes.c_float), _i] + [ctypes.c_float] * 3 + [_i, _fp, ctypes.c_float, _vp, _vp]),
     "rwkvtts_embed_rows": (_i, [ctypes.POINTER(_vp), _i, _vp, ctypes.c_longlong, _i, _vp, _vp]),
+    "rwkvtts_multi_copy": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                ctypes.POINTER(_i), _i, _vp, _i, _vp]),
     "rwkvtts_ce_forward_backward": (_i, [_vp, ctypes.c_longlong, _i, ctypes.c_longlong, _vp, ctypes.c_longlong, ctypes.c_float,
                                          _fp, _fp, _vp]),
     "rwkvtts_adam_p2p": (_i, [_fp, _fp, _fp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _vp, _i, ctypes.c_longlong,

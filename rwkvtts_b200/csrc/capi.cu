@@ -82,6 +82,8 @@ cudaError_t launch_adam_p2p(float *master, float *m, float *v, const void *const
                             unsigned long long *skipped, cudaStream_t st);
 cudaError_t launch_embed_rows(const void *const *tables, int ntab, const long long *row_src, long long rows, int D,
                               void *out, cudaStream_t st);
+cudaError_t launch_multi_copy(const void *const *srcs, const long long *dst_off, const long long *n, const int *accumulate,
+                              int count, void *flat, int elem_bytes, cudaStream_t st);
 cudaError_t launch_ce_fwd_bwd(void *logits, long long rows, int V, long long ld, const long long *labels,
                               long long ignore_index, float label_smoothing, const float *scale_dev, float *loss_rows,
                               cudaStream_t st);
@@ -399,6 +401,19 @@ int rwkvtts_embed_rows(const void *const *tables, int ntab, const long long *row
     if (int rc = check_ptrs({out})) return rc;
     if (row_src == nullptr) return RWKVTTS_ERR_NULL;
     return finish(rwkvtts::launch_embed_rows(tables, ntab, row_src, rows, D, out, (cudaStream_t)stream));
+}
+
+int rwkvtts_multi_copy(const void *const *srcs, const long long *dst_off, const long long *n, const int *accumulate, int count,
+                       void *flat, int elem_bytes, void *stream) {
+    if (count < 0 || (elem_bytes != 2 && elem_bytes != 4)) return RWKVTTS_ERR_SHAPE;
+    if (count == 0) return RWKVTTS_OK;
+    if (srcs == nullptr || dst_off == nullptr || n == nullptr) return RWKVTTS_ERR_NULL;
+    if (int rc = check_ptrs({flat})) return rc;
+    for (int i = 0; i < count; i++) {
+        if (int rc = check_ptrs({srcs[i]})) return rc;
+        if (n[i] <= 0 || n[i] > 0x7fffffffll || dst_off[i] < 0 || (dst_off[i] * elem_bytes) % 16 != 0) return RWKVTTS_ERR_SHAPE;
+    }
+    return finish(rwkvtts::launch_multi_copy(srcs, dst_off, n, accumulate, count, flat, elem_bytes, (cudaStream_t)stream));
 }
 
 int rwkvtts_ce_forward_backward(void *logits, long long rows, int V, long long ld, const long long *labels,

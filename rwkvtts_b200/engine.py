@@ -235,7 +235,11 @@ class Engine:
             n = p.numel()
             self.flat_param[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[o:o + n].view(p.shape)          # parameters alias the flat buffer
-            p.grad = self.flat_grad[o:o + n].view(p.shape)           # autograd accumulates in place
+            p.grad = self.flat_grad[o:o + n].view(p.shape)           # (what a reader of .grad sees; see _collect)
+        self._gviews = [p.grad for p in ordered]
+        self._pindex = {id(p): i for i, p in enumerate(ordered)}
+        self._has = [False] * len(ordered)                           # this window's gradient is in the flat buffer
+        self._stash = [[] for _ in self.buckets]                     # gradients autograd handed over, not yet in it
         # shard space: slice `rank` of every bucket, concatenated
         self._slice, self._soff = [], []
         so = 0
@@ -300,20 +304,65 @@ class Engine:
         self._bucket_np = [0] * len(self.buckets)
         for b in self._pbucket:
             self._bucket_np[b] += 1
-        if not (self._nccl and self.overlap_comm) or self._p2p is not None:
-            return
-        for p, b in zip(self._params, self._pbucket):
-            def hook(param, b=b):
-                if not self.is_gradient_accumulation_boundary():
+        overlap = self._nccl and self.overlap_comm and self._p2p is None
+        self._arrived = [0] * len(self.buckets)
+        for i, (p, b) in enumerate(zip(self._params, self._pbucket)):
+            def hook(param, i=i, b=b):
+                # backward() cleared .grad, so autograd handed over the gradient tensor itself instead of adding it into
+                # the flat buffer with a kernel per parameter: it is parked until its bucket is complete and then moved
+                # with the bucket's other gradients in ONE launch (csrc/gather.cu::multi_copy_kernel)
+                g = param.grad
+                view = self._gviews[i]
+                if g is not None and g.data_ptr() != view.data_ptr():
+                    self._stash[b].append((i, g))
+                    param.grad = view
+                else:
+                    self._has[i] = True                           # accumulated in place (somebody kept .grad bound)
+                self._arrived[b] += 1
+                if self._arrived[b] >= self._bucket_np[b]:
+                    self._flush(b)
+                if not overlap or not self.is_gradient_accumulation_boundary():
                     return
                 if self._launched[b]:
                     self._dirty[b] = True                        # a gradient arrived after its bucket left: redo in step()
                     return
                 self._pending[b] -= 1
                 if self._pending[b] == 0:
+                    self._flush(b)
                     self._launch_reduce(b)
             self._hook_handles.append(p.register_post_accumulate_grad_hook(hook))
         self._pending = list(self._bucket_np)
+
+    def _flush(self, b=None):
+        """Move the parked gradients of bucket b (all buckets if None) into the flat gradient buffer."""
+        for bb in (range(len(self.buckets)) if b is None else (b,)):
+            items = self._stash[bb]
+            if not items:
+                continue
+            self._stash[bb] = []
+            fast, dtype = [], self.flat_grad.dtype
+            for i, g in items:
+                if (self._on_gpu and g.dtype == dtype and g.is_contiguous() and g.data_ptr() % 16 == 0
+                        and g.numel() == self._gviews[i].numel() and dtype in (torch.bfloat16, torch.float32)):
+                    fast.append((i, g))
+                elif self._has[i]:
+                    self._gviews[i].add_(g.to(dtype).view_as(self._gviews[i]))
+                else:
+                    self._gviews[i].copy_(g.view_as(self._gviews[i]))
+                    self._has[i] = True
+            if fast:
+                n = len(fast)
+                srcs = (ctypes.c_void_p * n)(*[g.data_ptr() for _, g in fast])
+                offs = (ctypes.c_longlong * n)(*[self._poff[i] for i, _ in fast])
+                cnts = (ctypes.c_longlong * n)(*[g.numel() for _, g in fast])
+                accs = (ctypes.c_int * n)(*[int(self._has[i]) for i, _ in fast])
+                with torch.cuda.device(self.device):
+                    rc = _lib.lib().rwkvtts_multi_copy(srcs, offs, cnts, accs, n, self.flat_grad.data_ptr(),
+                                                       self.flat_grad.element_size(),
+                                                       torch.cuda.current_stream(self.device).cuda_stream)
+                _lib.check(rc, "rwkvtts_multi_copy")
+                for i, _ in fast:
+                    self._has[i] = True
 
     def _launch_reduce(self, b):
         s, e = self.buckets[b]
@@ -326,13 +375,18 @@ class Engine:
         self._launched[b] = True
 
     def _rebind_grads(self):
-        for p, o in zip(self._params, self._poff):
-            n = p.numel()
-            if p.grad is None or p.grad.data_ptr() != self.flat_grad[o:o + n].data_ptr():
-                g = self.flat_grad[o:o + n].view(p.shape)
-                if p.grad is not None:                   # something replaced .grad (e.g. zero_grad(set_to_none))
-                    g.add_(p.grad)
+        for i, p in enumerate(self._params):
+            g = self._gviews[i]
+            if p.grad is None:
                 p.grad = g
+            elif p.grad.data_ptr() != g.data_ptr():      # something replaced .grad: fold it in
+                g.add_(p.grad)
+                self._has[i] = True
+                p.grad = g
+
+    def _zero_grads(self):
+        self.flat_grad.zero_()
+        self._has = [False] * len(self._params)
 
     # -- module surface ----------------------------------------------------------------------------
     def __call__(self, *args, **kwargs):
@@ -361,7 +415,8 @@ class Engine:
         return self.module.named_parameters(*a, **k)
 
     def zero_grad(self, set_to_none: bool = False):
-        self.flat_grad.zero_()
+        self._stash = [[] for _ in self.buckets]
+        self._zero_grads()
         self._rebind_grads()
 
     def get_lr(self):
@@ -383,10 +438,16 @@ class Engine:
 
     # -- training step --------------------------------------------------------------------------
     def backward(self, loss: torch.Tensor, **kwargs):
+        self._flush()
         self._rebind_grads()
+        for p in self._params:
+            p.grad = None                        # autograd then hands the gradient tensor to the hook (see _install_hooks)
+        self._arrived = [0] * len(self.buckets)
         if self.gradient_accumulation_steps > 1:
             loss = loss / self.gradient_accumulation_steps
         loss.backward()
+        self._flush()                            # buckets with parameters that got no gradient
+        self._rebind_grads()
         return loss
 
     def _reduce_gradients(self):
@@ -429,6 +490,7 @@ class Engine:
         self.micro_steps += 1
         if not boundary:
             return
+        self._flush()
         self._rebind_grads()
         W = self.world_size
         if self._p2p is not None:
@@ -490,7 +552,7 @@ class Engine:
         for w in gathers:
             w.wait()
         _invalidate_param_cache()     # the all-gather rewrote the other ranks' slices of the flat parameter buffer
-        self.flat_grad.zero_()
+        self._zero_grads()
         self.global_steps += 1
         if self.lr_scheduler is not None:
             self.optimizer._opt_called = True     # the update ran above (on the shard): torch's scheduler order check looks here
@@ -536,7 +598,7 @@ class Engine:
         ev1.record()
         self.exchange_events = (ev0, ev1)
         dist.all_reduce(self._norm2)                     # reporting only (global_grad_norm); nothing waits for it
-        self.flat_grad.zero_()
+        self._zero_grads()
         self.global_steps += 1
         if self.lr_scheduler is not None:
             self.optimizer._opt_called = True
@@ -605,7 +667,7 @@ class Engine:
             ev[2].record()
             torch.cuda.synchronize(self.device)
             rs += ev[0].elapsed_time(ev[1]); ag += ev[1].elapsed_time(ev[2])
-        self.flat_grad.zero_()
+        self._zero_grads()
         self.comm_ms = {"reduce_scatter_ms": rs / iters, "all_gather_ms": ag / iters,
                         "bytes_per_rank": self.padded * self.flat_grad.element_size(), "buckets": len(self.buckets)}
         return self.comm_ms

@@ -141,6 +141,60 @@ def test_engine_on_one_gpu_matches_adamw(monkeypatch):
     assert eng.skipped_steps == 1 and all(torch.equal(a, b) for a, b in zip(eng.parameters(), before))
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+def test_multi_copy_moves_and_accumulates_gradients_into_the_flat_buffer(dt):
+    """rwkvtts_multi_copy (csrc/gather.cu): the bucket-wise replacement of one add kernel per parameter."""
+    import ctypes
+    from rwkvtts_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(3)
+    sizes = [1, 7, 8, 64, 1000, 4096 * 3 + 5, 100003] + [33] * 140          # > 128 tensors: two launches
+    srcs = [torch.randn(n, device="cuda").to(dt) for n in sizes]
+    offs, at = [], 0
+    for n in sizes:
+        offs.append(at)
+        at += (n + 7) // 8 * 8
+    flat = torch.randn(at, device="cuda").to(dt)
+    want = flat.clone()
+    acc = [i % 3 == 1 for i in range(len(sizes))]
+    for t, o, a in zip(srcs, offs, acc):
+        want[o:o + t.numel()] = (want[o:o + t.numel()].float() + t.float()).to(dt) if a else t
+    n = len(sizes)
+    rc = L.rwkvtts_multi_copy((ctypes.c_void_p * n)(*[t.data_ptr() for t in srcs]), (ctypes.c_longlong * n)(*offs),
+                              (ctypes.c_longlong * n)(*sizes), (ctypes.c_int * n)(*[int(a) for a in acc]), n, flat.data_ptr(),
+                              flat.element_size(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(flat, want)                       # padding between tensors untouched, sums rounded once
+
+
+def test_engine_gradient_accumulation_on_gpu_equals_the_summed_batch(monkeypatch):
+    """Two micro-steps: the second one's gradients are ADDED to the first one's in the flat buffer (same launch path)."""
+    import deepspeed
+    from deepspeed.ops.adam import FusedAdam
+    monkeypatch.setenv("RWKVTTS_BUCKET_ELEMS", "2000")
+    m = _toy(seed=4)
+    opt = FusedAdam(_groups(m), lr=1e-2, betas=(B1, B2), eps=EPS)
+    eng, _, _, _ = deepspeed.initialize(model=m, config={"bf16": {"enabled": False}, "gradient_accumulation_steps": 2,
+                                                         "zero_optimization": {"stage": 2}},
+                                        model_parameters=m.parameters(), optimizer=opt)
+    ref = _toy(seed=4).cuda()
+    ropt = torch.optim.AdamW([{"params": g["params"], "weight_decay": g["weight_decay"]} for g in _groups(ref)], lr=1e-2,
+                             betas=(B1, B2), eps=EPS)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    xs = [torch.randn(16, 96, device="cuda", generator=g) for _ in range(6)]
+    ys = [torch.randn(16, 8, device="cuda", generator=g) for _ in range(6)]
+    for k in range(0, 6, 2):
+        ropt.zero_grad()
+        for j in (k, k + 1):
+            eng.backward(torch.nn.functional.mse_loss(eng(xs[j]), ys[j])); eng.step()
+            (torch.nn.functional.mse_loss(ref(xs[j]), ys[j]) / 2).backward()
+        ropt.step()
+    assert eng.global_steps == 3
+    for a, b in zip(eng.parameters(), ref.parameters()):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+
+
 WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %(root)r)
