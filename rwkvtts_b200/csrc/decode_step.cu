@@ -91,7 +91,7 @@ struct StepArgs {
     long long pad;
     unsigned long long *prof;       // null, or the time line described at rwkvtts_decode_step_profile
     int n_eos, greedy, suppress_eos;
-    int debug_skip;                 // tuning experiments only (env RWKVTTS_DECODE_SKIP): 1 skip the row phases, 2 skip wkv
+    int debug_skip;                 // tuning experiments only (env RWKVTTS_DECODE_SKIP): 1 skip the row phases, 2 skip wkv, 4 no L2 prefetch
 };
 
 // The kernel runs ~170 short phases per token, each through code the previous phases have pushed out of the 32 KB
@@ -232,7 +232,7 @@ struct SyncCtx {
     const Desc *D;
     const Ranges *R;
     unsigned long long *prof;
-    int nprof;
+    int nprof, no_prefetch;
 };
 __device__ __noinline__ unsigned grid_sync(const SyncCtx &cx, unsigned epoch, int plan, const Layer *Ly, const Layer *Nx) {
     __syncthreads();
@@ -242,7 +242,7 @@ __device__ __noinline__ unsigned grid_sync(const SyncCtx &cx, unsigned epoch, in
         if (cx.prof != nullptr && blockIdx.x < kProfCtas) cx.prof[cx.nprof + epoch * kProfCtas + blockIdx.x] = globaltimer();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(bar) : "memory");
     }
-    if (plan != kPfNone && (threadIdx.x >> 5) == 1) prefetch_plan(plan, *cx.D, *Ly, *Nx, *cx.R, false, threadIdx.x & 31);
+    if (plan != kPfNone && !cx.no_prefetch && (threadIdx.x >> 5) == 1) prefetch_plan(plan, *cx.D, *Ly, *Nx, *cx.R, false, threadIdx.x & 31);
     if (threadIdx.x == 0) {
         const unsigned target = epoch * gridDim.x;
         if (ld_acquire(bar) < target) {
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
     float *red_rows = smem + kRedFloats - 64;   // reductions of the row phases
     bf16 *upw = reinterpret_cast<bf16 *>(smem + kRedFloats);
     const int nprof = 8 * D.L + 4;
-    const SyncCtx cx{&sD, &sR, a.prof, nprof};
+    const SyncCtx cx{&sD, &sR, a.prof, nprof, a.debug_skip & 4};
     // fine stamps of layer 1 (cycles): [16..] projections, [32..] wkv rounds, [48..] output projection, [64..] key
     long long *fine = a.prof != nullptr ? reinterpret_cast<long long *>(a.prof + (size_t)nprof * (1 + 2 * kProfCtas)) : nullptr;
     unsigned epoch = 0;
