@@ -35,6 +35,7 @@
 #include "../../include/rwkvtts_wkv7.h"
 
 #include <cstddef>
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -47,7 +48,7 @@ namespace dec {
 using tc05::clock_hi;
 
 constexpr int kThreads = 512, kWarps = 16, kRows = 32, kMaxJobs = 8, kMaxEos = 8, kMaxLora = 512;
-constexpr int kRedFloats = kWarps * 512;        // 32 KB: GEMM reduction / row buffer / wkv scratch
+constexpr int kRedFloats = kWarps * 512;        // 32 KB: GEMM reduction (16 warps x 2 tiles x 256 partial sums) / wkv scratch
 enum { kEpiBf16 = 0, kEpiTanh, kEpiSigmoid, kEpiSqRelu, kEpiF32, kEpiLogits };
 enum { kRowLn1 = 0, kRowLn2, kRowFinal };
 
@@ -596,12 +597,12 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
 }
 
 // ---- skinny GEMM phase ---------------------------------------------------------------------------------------------------
-// weight fragments of up to two 8-column tiles: wp = this lane's row of the first tile at its k offset; rows_left /
+// weight fragments of up to NT 8-column tiles: wp = this lane's row of the first tile at its k offset; rows_left /
 // k_left bound what exists (last tile of an odd vocabulary, K smaller than the 16 warps' slices)
-template <int NKB>
-__device__ __forceinline__ void load_w(const bf16 *wp, int ldw, int ntile, int rows_left, int k_left, uint4 (&wv)[2][NKB]) {
+template <int NKB, int NT>
+__device__ __forceinline__ void load_w(const bf16 *wp, int ldw, int ntile, int rows_left, int k_left, uint4 (&wv)[NT][NKB]) {
 #pragma unroll
-    for (int tt = 0; tt < 2; tt++)
+    for (int tt = 0; tt < NT; tt++)
 #pragma unroll
         for (int kb = 0; kb < NKB; kb++) {
             const bool ok = tt < ntile && tt * 8 < rows_left && kb * 32 < k_left;
@@ -613,7 +614,10 @@ __device__ __noinline__ float epi_act(float v, int epi) {
     return epi == kEpiTanh ? tanhf(v) : 1.f / (1.f + expf(-v));
 }
 
-template <int NKB>
+// NT = 8-column tiles per pass.  Four per pass (one pass instead of two for the 2.8 - 3.5 tiles a CTA has of the projections
+// and the channel mix) was measured slower: a pass costs instructions in proportion to its tiles, and the phases are bound
+// by instruction issue, not by the number of passes.
+template <int NKB, int NT /* = 2 */>
 __device__ __noinline__ void phase_gemm(const Phase &P, int t0, int t1, int B, float *red, long long *fine) {
     if (t0 >= t1) return;
     PROF_POINT(fine, 0);
@@ -628,8 +632,8 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int t0, int t1, int B, f
         const int jend = min(t1, J.tile0 + ((J.N + 7) >> 3)), k_left = J.K - koff;
         int n0 = (t - J.tile0) * 8;
         const bf16 *wp = J.W + (size_t)(n0 + g) * J.ldw + koff;
-        uint4 wv[2][NKB];
-        load_w<NKB>(wp, J.ldw, jend - t, J.N - n0 - g, k_left, wv);
+        uint4 wv[NT][NKB];
+        load_w<NKB, NT>(wp, J.ldw, jend - t, J.N - n0 - g, k_left, wv);
         uint32_t af[NKB][2][2][4];  // [k block][m tile][mma of the block][a0..a3], already in the instruction's register order
 #pragma unroll
         for (int kb = 0; kb < NKB; kb++)
@@ -645,19 +649,20 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int t0, int t1, int B, f
                 af[kb][mt][0][0] = lo.x; af[kb][mt][0][1] = hi.x; af[kb][mt][0][2] = lo.y; af[kb][mt][0][3] = hi.y;
                 af[kb][mt][1][0] = lo.z; af[kb][mt][1][1] = hi.z; af[kb][mt][1][2] = lo.w; af[kb][mt][1][3] = hi.w;
             }
-#pragma unroll 1
-        while (t < jend) {
+        // one pass of mma -> reduce -> store over TT (compile time) tiles: a single tile (the output projection's one
+        // tile per CTA, the odd tile at the end of a range) runs half the instructions of a pair
+        auto pass = [&](auto tt_const) {
+            constexpr int TT = decltype(tt_const)::value;
             PROF_POINT(fine, 1);
-            const int ntile = min(2, jend - t);
-            float acc[2][2][4];
+            float acc[TT][2][4];
 #pragma unroll
-            for (int tt = 0; tt < 2; tt++)
+            for (int tt = 0; tt < TT; tt++)
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                     for (int e = 0; e < 4; e++) acc[tt][mt][e] = 0.f;
 #pragma unroll
-            for (int tt = 0; tt < 2; tt++)
+            for (int tt = 0; tt < TT; tt++)
 #pragma unroll
                 for (int kb = 0; kb < NKB; kb++)
 #pragma unroll
@@ -666,42 +671,58 @@ __device__ __noinline__ void phase_gemm(const Phase &P, int t0, int t1, int B, f
                         mma_bf16(acc[tt][mt], af[kb][mt][1], wv[tt][kb].z, wv[tt][kb].w);
                     }
             PROF_POINT(fine, 2);
-            wp += (size_t)16 * J.ldw;
-            if (t + 2 < jend) load_w<NKB>(wp, J.ldw, jend - t - 2, J.N - n0 - 16 - g, k_left, wv);      // in flight during the reduction
+            wp += (size_t)NT * 8 * J.ldw;
+            if (t + NT < jend) load_w<NKB, NT>(wp, J.ldw, jend - t - NT, J.N - n0 - NT * 8 - g, k_left, wv);   // in flight during the reduction
 #pragma unroll
-            for (int tt = 0; tt < 2; tt++)
+            for (int tt = 0; tt < TT; tt++)
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
-                    *reinterpret_cast<float4 *>(red + ((warp * 2 + tt) * 2 + mt) * 128 + lane * 4) =
+                    *reinterpret_cast<float4 *>(red + ((warp * NT + tt) * 2 + mt) * 128 + lane * 4) =
                         make_float4(acc[tt][mt][0], acc[tt][mt][1], acc[tt][mt][2], acc[tt][mt][3]);
             __syncthreads();
             PROF_POINT(fine, 3);
-            {
-                const int tt = threadIdx.x >> 8, idx = threadIdx.x & 255;
-                float s = 0.f;
+            // thread -> output (tile tid / 256, element tid % 256) of a pair; a single tile: each half of the CTA sums the
+            // partial tiles of 8 warps, the halves meet in shared memory
+            const int hf = threadIdx.x >> 8, idx = threadIdx.x & 255;
+            float x = 0.f;
+            if (TT == 2) {
 #pragma unroll
-                for (int w = 0; w < kWarps; w++) s += red[(w * 2 + tt) * 256 + idx];
-                __syncthreads();                 // the reduction buffer is free; the store below has no barrier behind it
-                const int mt = idx >> 7, ln = (idx >> 2) & 31, e = idx & 3;
-                const int row = mt * 16 + (ln >> 2) + ((e >> 1) << 3), n = n0 + tt * 8 + (ln & 3) * 2 + (e & 1);
-                if (tt < ntile && row < B && n < J.N) {
-                    const size_t at = (size_t)row * J.ldo + n;
-                    if (J.epi == kEpiF32) {
-                        static_cast<float *>(J.out)[at] = s;
-                    } else if (J.epi == kEpiLogits) {
-                        static_cast<float *>(J.out)[at] = rbf(s);
-                    } else {
-                        float v = rbf(s);
-                        if (J.epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
-                        else if (J.epi != kEpiBf16) v = epi_act(v, J.epi);
-                        static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
-                    }
+                for (int w = 0; w < kWarps; w++) x += red[(w * NT + hf) * 256 + idx];
+            } else {
+#pragma unroll
+                for (int w = 0; w < kWarps / 2; w++) x += red[((w + 8 * hf) * NT) * 256 + idx];
+            }
+            __syncthreads();                     // the reduction buffer is free; the stores below have no barrier behind them
+            if (TT == 1) {
+                if (hf == 1) red[idx] = x;
+                __syncthreads();
+                if (hf == 0) x += red[idx];
+                __syncthreads();
+            }
+            const int mt = idx >> 7, ln = (idx >> 2) & 31, e = idx & 3;
+            const int row = mt * 16 + (ln >> 2) + ((e >> 1) << 3), n = n0 + (TT == 2 ? hf : 0) * 8 + (ln & 3) * 2 + (e & 1);
+            if ((TT == 2 || hf == 0) && row < B && n < J.N) {
+                const size_t at = (size_t)row * J.ldo + n;
+                if (J.epi == kEpiF32) {
+                    static_cast<float *>(J.out)[at] = x;
+                } else if (J.epi == kEpiLogits) {
+                    static_cast<float *>(J.out)[at] = rbf(x);
+                } else {
+                    float v = rbf(x);
+                    if (J.epi == kEpiSqRelu) { v = fmaxf(v, 0.f); v = v * v; }
+                    else if (J.epi != kEpiBf16) v = epi_act(v, J.epi);
+                    static_cast<bf16 *>(J.out)[at] = __float2bfloat16_rn(v);
                 }
             }
             PROF_POINT(fine, 4);
             if (fine != nullptr) fine += 4;
-            t += ntile;
-            n0 += 16;
+            t += TT;
+            n0 += NT * 8;
+        };
+#pragma unroll 1
+        while (t < jend) {
+            if (jend - t >= 2) pass(std::integral_constant<int, 2>{});
+            else pass(std::integral_constant<int, 1>{});
         }
         j++;
     }
@@ -760,20 +781,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
         const int rp2 = l == 0 ? kRgP2First : kRgP2;
         if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn1, l == 0, a, red_rows);
         epoch = grid_sync(cx, epoch, kPfWkv, &Ly, &Nx);
-        phase_gemm<NKB>(Ly.p2, sR.r[rp2][0], sR.r[rp2][1], D.B, smem, f1 ? fine + 16 : nullptr);
+        phase_gemm<NKB, 2>(Ly.p2, sR.r[rp2][0], sR.r[rp2][1], D.B, smem, f1 ? fine + 16 : nullptr);
         if (!(a.debug_skip & 2) && (int)blockIdx.x < NP) stage_up(D, Ly, blockIdx.x % D.H, upw, threadIdx.x, kThreads);      // first round of the wkv phase
         tc05::cp_async_commit();
         epoch = grid_sync(cx, epoch, kPfOut, &Ly, &Nx);
         if (!(a.debug_skip & 2)) phase_wkv(D, Ly, l == 0, smem, upw, f1 ? fine + 32 : nullptr);
         epoch = grid_sync(cx, epoch, kPfKey, &Ly, &Nx);
-        phase_gemm<NKB>(Ly.p4, sR.r[kRgP4][0], sR.r[kRgP4][1], D.B, smem, f1 ? fine + 48 : nullptr);
+        phase_gemm<NKB, 2>(Ly.p4, sR.r[kRgP4][0], sR.r[kRgP4][1], D.B, smem, f1 ? fine + 48 : nullptr);
         epoch = grid_sync(cx, epoch, kPfValue, &Ly, &Nx);
         if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn2, false, a, red_rows);
         tc05::cp_async_wait<0>();                        // own pieces of layer l + 1's descriptor; the barrier publishes them
         epoch = grid_sync(cx, epoch, kPfNone, &Ly, &Nx);
-        phase_gemm<NKB>(Ly.p6, sR.r[kRgP6][0], sR.r[kRgP6][1], D.B, smem, f1 ? fine + 64 : nullptr);
+        phase_gemm<NKB, 2>(Ly.p6, sR.r[kRgP6][0], sR.r[kRgP6][1], D.B, smem, f1 ? fine + 64 : nullptr);
         epoch = grid_sync(cx, epoch, last ? kPfHead : kPfNextProj, &Ly, &Nx);
-        phase_gemm<NKB>(Ly.p7, sR.r[kRgP7][0], sR.r[kRgP7][1], D.B, smem, nullptr);
+        phase_gemm<NKB, 2>(Ly.p7, sR.r[kRgP7][0], sR.r[kRgP7][1], D.B, smem, nullptr);
         epoch = grid_sync(cx, epoch, kPfNone, &Ly, &Nx);
         // every thread is past its last use of sL[l & 1]: bring in layer l + 2
         if (l + 2 < D.L) copy_async(&sL[l & 1], D.layers + l + 2, sizeof(Layer));
@@ -781,7 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
     }
     phase_rows<NKB / 2>(D, sL[0], kRowFinal, false, a, red_rows);
     epoch = grid_sync(cx, epoch, kPfNone, &sL[0], &sL[0]);
-    phase_gemm<NKB>(D.head, sR.r[kRgHead][0], sR.r[kRgHead][1], D.B, smem, nullptr);
+    phase_gemm<NKB, 2>(D.head, sR.r[kRgHead][0], sR.r[kRgHead][1], D.B, smem, nullptr);
     if (a.greedy) {
         epoch = grid_sync(cx, epoch, kPfNone, &sL[0], &sL[0]);
         phase_argmax(D, a, red_rows);
