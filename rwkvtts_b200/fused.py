@@ -36,8 +36,7 @@ def usable(x: torch.Tensor) -> bool:
     return x.shape[-1] <= (MAX_C_BACKWARD if torch.is_grad_enabled() else MAX_C_FORWARD)
 
 
-# fp32 copies of per-channel parameters.  Under no_grad (prefill / decode: ~14 tiny conversion kernels per layer and
-# token otherwise) they are cached per parameter OBJECT (weak references: a freed parameter's address can be reused by
+# fp32 copies of per-channel parameters (~14 tiny conversion kernels per layer and call otherwise): cached per parameter OBJECT (weak references: a freed parameter's address can be reused by
 # another tensor) and version counter.
 _PCACHE: dict = {}       # id(parameter) -> (weakref to it, version key, fp32 copy)
 _EPOCH = [0]
@@ -66,8 +65,9 @@ def _f32(p: Optional[torch.Tensor], C: int) -> Optional[torch.Tensor]:
     if p is None:
         return None
     make = lambda: p.detach().reshape(-1).to(torch.float32).contiguous()
-    if torch.is_grad_enabled():
-        return make()
+    # the copy is detached in either mode (the kernels' adjoints return the parameter gradients themselves), so it is
+    # shared by every call until the parameter changes: in-place updates move `_version`, the engine's raw-pointer Adam
+    # calls invalidate_param_cache() -- ~330 tiny conversion kernels per training step otherwise
     return _cached(p, ("f32", p._version), make)
 
 
