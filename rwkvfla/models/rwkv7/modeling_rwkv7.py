@@ -24,6 +24,7 @@ from transformers.modeling_utils import PreTrainedModel
 from rwkvtts_b200 import core, ops
 from rwkvtts_b200.decode import MegaDecodeStep, unsupported_reason
 from rwkvtts_b200.fused import cached as fused_cached
+from rwkvtts_b200.fused import ln_usable as fused_ln_usable
 from rwkvtts_b200.fused import usable as fused_usable
 from ...layers.rwkv7 import RWKV7Attention
 from ...modules import FusedCrossEntropyLoss, FusedLinearCrossEntropyLoss, LayerNorm, l2_warp
@@ -94,15 +95,25 @@ class RWKV7Block(nn.Module):
 
     def forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                 past_key_values: Optional[Cache] = None, use_cache: Optional[bool] = False,
-                output_attentions: Optional[bool] = False, v_first: torch.Tensor = None, cu_seqlens=None, **kwargs):
-        residual = self.pre_norm(hidden_states) if hasattr(self, "pre_norm") else hidden_states
-        hidden_states = self.attn_norm(residual)
+                output_attentions: Optional[bool] = False, v_first: torch.Tensor = None, cu_seqlens=None,
+                residual_in: Optional[torch.Tensor] = None, defer_add: bool = False, **kwargs):
+        """`residual_in` / `defer_add` (RWKV7Model's own loop): the block's last operation, `residual + ffn(...)`, is left to
+        the NEXT block's attention norm, which adds and normalises in one kernel (`LayerNorm(x, residual, prenorm=True)`: the
+        same bf16 sum, one pass over the activations less in the forward and one accumulation kernel less in the backward
+        per layer).  With defer_add the block returns the pair (ffn output, residual) instead of their sum."""
+        if residual_in is not None:
+            hidden_states, residual = self.attn_norm(hidden_states, residual_in, True)
+        else:
+            residual = self.pre_norm(hidden_states) if hasattr(self, "pre_norm") else hidden_states
+            hidden_states = self.attn_norm(residual)
         hidden_states, attentions, past_key_values, v_first = self.attn(
             hidden_states=hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
             use_cache=use_cache, output_attentions=output_attentions, v_first=v_first, cu_seqlens=cu_seqlens)
         hidden_states, residual = self.ffn_norm(hidden_states, residual, True)
         hidden_states, past_key_values = self.ffn(hidden_states, attention_mask, past_key_values, cu_seqlens,
                                                   use_cache=use_cache)
+        if defer_add:
+            return (hidden_states, residual), attentions, past_key_values, v_first
         hidden_states = residual + hidden_states
         return hidden_states, attentions, past_key_values, v_first
 
@@ -200,7 +211,12 @@ class RWKV7Model(RWKV7PreTrainedModel):
             past_key_values = Cache.from_legacy_cache(past_key_values)
         all_hidden_states = () if output_hidden_states else None
         v_first = torch.zeros_like(hidden_states)
-        for layer in self.layers:
+        # between blocks the residual add is deferred into the next norm (RWKV7Block.forward) unless somebody wants to see
+        # the hidden states of every layer or the fused add+norm kernel does not apply
+        defer = (not output_hidden_states and core.FUSED and fused_ln_usable(hidden_states)
+                 and not (self.gradient_checkpointing and self.training))
+        residual = None
+        for li, layer in enumerate(self.layers):
             if output_hidden_states:
                 all_hidden_states += (hidden_states,)
             if self.gradient_checkpointing and self.training:
@@ -210,8 +226,11 @@ class RWKV7Model(RWKV7PreTrainedModel):
             else:
                 hidden_states, _, past_key_values, v_first = layer(
                     hidden_states, attention_mask=attention_mask, past_key_values=past_key_values,
-                    use_cache=use_cache, output_attentions=False, v_first=v_first, cu_seqlens=cu_seqlens)
-        hidden_states = self.norm(hidden_states)
+                    use_cache=use_cache, output_attentions=False, v_first=v_first, cu_seqlens=cu_seqlens,
+                    residual_in=residual, defer_add=defer)
+                if defer:
+                    hidden_states, residual = hidden_states
+        hidden_states = self.norm(hidden_states, residual) if residual is not None else self.norm(hidden_states)
         if packed_idx is not None:
             hidden_states = repack_varlen(hidden_states, packed_idx)
             if output_hidden_states:
@@ -432,12 +451,18 @@ class RWKV7ForCausalLM(RWKV7PreTrainedModel, GenerationMixin):
         if use_cuda_graph is None:
             use_cuda_graph = dev.type == "cuda" and max_new_tokens > 8
         graph_step, mega = None, None
-        if use_megakernel is None:
+        auto_mega = use_megakernel is None
+        if auto_mega:
             use_megakernel = (dev.type == "cuda" and use_cuda_graph and max_new_tokens > 1 and core.FUSED and not core.EXACT
                               and len(eos) <= 8 and unsupported_reason(self, B) is None)
         if use_megakernel and max_new_tokens > 1:
-            mega = graph_step = MegaDecodeStep(self, cache, B, dev)       # raises if the model does not fit the kernel
-        elif use_cuda_graph and max_new_tokens > 1:
+            try:
+                mega = graph_step = MegaDecodeStep(self, cache, B, dev)   # raises if the model does not fit the kernel
+            except (ValueError, RuntimeError) as e:
+                if not auto_mega:
+                    raise
+                warnings.warn(f"one-kernel decode step unavailable ({e}); using the CUDA-graph step")
+        if mega is None and use_cuda_graph and max_new_tokens > 1:
             try:
                 graph_step = _GraphDecodeStep(self, cache, B, dev)
             except RuntimeError as e:                  # e.g. an op that cannot be captured in a user subclass: decode eagerly

@@ -298,10 +298,12 @@ __device__ __forceinline__ void ln_regs(float2 (&x)[kPP], int C, const float2 (&
 }
 
 template <int kPP>
-__device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind, bool first_layer, const StepArgs &a, float *red) {
+__device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind, bool first_layer, const StepArgs &a, float *red,
+                                        long long *fine) {
     const int C = D.C;
 #pragma unroll 1
     for (int b = blockIdx.x; b < D.B; b += gridDim.x) {
+        PROF_POINT(fine, 0);
         const size_t rb = (size_t)b * C;
         const bf16 *nw = kind == kRowLn1 ? Ly.ln1_w : kind == kRowLn2 ? Ly.ln2_w : D.lnf_w;
         const bf16 *nb = kind == kRowLn1 ? Ly.ln1_b : kind == kRowLn2 ? Ly.ln2_b : D.lnf_b;
@@ -346,6 +348,7 @@ __device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind
 #pragma unroll
             for (int s = 0; s < 6; s++) mx[pp][s] = ok && s < n ? ld_par2(mix[s] + c) : z;
         }
+        PROF_POINT(fine, 1);
         if (emb && D.ln0_w != nullptr) ln_regs<kPP>(x, C, w0, b0, D.ln_eps, red);
         bf16 *keep = (kind == kRowLn2 ? D.x2 : D.x) + rb;          // the residual stream
 #pragma unroll
@@ -353,7 +356,9 @@ __device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind
             const int c = 2 * threadIdx.x + pp * 2 * kThreads;
             if (c < C) st2(keep + c, x[pp].x, x[pp].y);
         }
+        PROF_POINT(fine, 2);
         ln_regs<kPP>(x, C, w, bb, D.ln_eps, red);
+        PROF_POINT(fine, 3);
 #pragma unroll
         for (int pp = 0; pp < kPP; pp++) {
             const int c = 2 * threadIdx.x + pp * 2 * kThreads;
@@ -370,6 +375,7 @@ __device__ __noinline__ void phase_rows(const Desc &D, const Layer &Ly, int kind
                 st2(shift + c, h0, h1);
             }
         }
+        PROF_POINT(fine, 4);
     }
 }
 
@@ -779,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
         const Layer &Ly = sL[l & 1], &Nx = sL[(l + 1) & 1];
         const bool f1 = l == 1 && fine != nullptr, last = l + 1 == D.L;
         const int rp2 = l == 0 ? kRgP2First : kRgP2;
-        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn1, l == 0, a, red_rows);
+        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn1, l == 0, a, red_rows, f1 ? fine + 80 : nullptr);
         epoch = grid_sync(cx, epoch, kPfWkv, &Ly, &Nx);
         phase_gemm<NKB, 2>(Ly.p2, sR.r[rp2][0], sR.r[rp2][1], D.B, smem, f1 ? fine + 16 : nullptr);
         if (!(a.debug_skip & 2) && (int)blockIdx.x < NP) stage_up(D, Ly, blockIdx.x % D.H, upw, threadIdx.x, kThreads);      // first round of the wkv phase
@@ -789,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
         epoch = grid_sync(cx, epoch, kPfKey, &Ly, &Nx);
         phase_gemm<NKB, 2>(Ly.p4, sR.r[kRgP4][0], sR.r[kRgP4][1], D.B, smem, f1 ? fine + 48 : nullptr);
         epoch = grid_sync(cx, epoch, kPfValue, &Ly, &Nx);
-        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn2, false, a, red_rows);
+        if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn2, false, a, red_rows, f1 ? fine + 88 : nullptr);
         tc05::cp_async_wait<0>();                        // own pieces of layer l + 1's descriptor; the barrier publishes them
         epoch = grid_sync(cx, epoch, kPfNone, &Ly, &Nx);
         phase_gemm<NKB, 2>(Ly.p6, sR.r[kRgP6][0], sR.r[kRgP6][1], D.B, smem, f1 ? fine + 64 : nullptr);
@@ -800,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
         if (l + 2 < D.L) copy_async(&sL[l & 1], D.layers + l + 2, sizeof(Layer));
         tc05::cp_async_commit();
     }
-    phase_rows<NKB / 2>(D, sL[0], kRowFinal, false, a, red_rows);
+    phase_rows<NKB / 2>(D, sL[0], kRowFinal, false, a, red_rows, nullptr);
     epoch = grid_sync(cx, epoch, kPfNone, &sL[0], &sL[0]);
     phase_gemm<NKB, 2>(D.head, sR.r[kRgHead][0], sR.r[kRgHead][1], D.B, smem, nullptr);
     if (a.greedy) {
@@ -937,7 +943,9 @@ cudaError_t decode_init(const int *d, const float *eps, const void *const *mp, c
     if (e != cudaSuccess) return e;
     HostInfo hi{};
     if ((e = cudaGetDevice(&hi.device)) != cudaSuccess) return e;
-    int sms = 0, per_sm = 0;
+    int sms = 0, per_sm = 0, coop = 0;
+    if ((e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, hi.device)) != cudaSuccess) return e;
+    if (!coop) return cudaErrorNotSupported;           // the grid barrier needs every CTA resident
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, hi.device)) != cudaSuccess) return e;
     hi.nkb = C <= 1024 ? 2 : 4;
     // dynamic shared memory: the phase scratch + the staged LoRA up-projection rows of two (b, head) units

@@ -69,6 +69,9 @@ for name, base, per, n in (("proj", 16, 4, 4), ("wkv", 32, 8, 2), ("out", 48, 4,
         if f[o + (1 if per == 4 else 0)]:
             pts = [f[o + k] for k in range(per + (1 if per == 4 else 0))]
             print(f"  {name} round {r}: " + " ".join(str(b - a) if a and b else "-" for a, b in zip(pts[:-1], pts[1:])))
+for name, o in (("ln1", 80), ("ln2", 88)):
+    if f[o] and f[o + 4]:
+        print(f"  {name}: loads+row {f[o+1]-f[o]}, store residual {f[o+2]-f[o+1]}, LayerNorm {f[o+3]-f[o+2]}, shift/lerp/stores {f[o+4]-f[o+3]}")
 if "--no-graph" not in sys.argv:
     with torch.no_grad():
         g = _GraphDecodeStep(m, cache, B, dev)
