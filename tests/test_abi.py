@@ -94,3 +94,24 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
                 assert "liboracle" not in src and "oracle/" not in src, f
+
+
+def test_decode_plan_entry_points_validate_on_the_host():
+    """rwkvtts_decode_* (one-kernel decode step): dims are checked without touching a GPU."""
+    import ctypes
+    from rwkvtts_b200 import _lib
+    from rwkvtts_b200.decode import DEC_NDIM
+    L = _lib.lib()
+    ok = (ctypes.c_int * DEC_NDIM)(32, 1024, 16, 24, 8193, 4096, 64, 64, 32, 128)
+    offs = (ctypes.c_size_t * 3)()
+    n = L.rwkvtts_decode_workspace_bytes(ok, offs)
+    assert n > 32 * 8193 * 4 and 0 < offs[0] < n and 0 < offs[1] < n and 0 < offs[2] < n and len({offs[0], offs[1], offs[2]}) == 3
+    for bad in [(33, 1024, 16, 24, 8193, 4096, 64, 64, 32, 128),      # more than 32 rows
+                (32, 1024, 15, 24, 8193, 4096, 64, 64, 32, 128),      # C != H * 64
+                (32, 4096, 64, 24, 8193, 16384, 64, 64, 32, 128),     # hidden size beyond the kernel
+                (32, 1024, 16, 24, 8193, 4096, 64, 64, 16, 128),      # a LoRA rank that is not a multiple of 32
+                (32, 1024, 16, 24, 8193, 5000, 64, 64, 32, 128)]:     # channel-mix width not a multiple of C
+        assert L.rwkvtts_decode_workspace_bytes((ctypes.c_int * DEC_NDIM)(*bad), None) == 0, bad
+    assert L.rwkvtts_decode_init(None, None, None, None, None, 0, None) == -2          # RWKVTTS_ERR_NULL
+    assert L.rwkvtts_decode_step(None, None, None, 1, 0, None, 0, 0, None) == -2
+    assert L.rwkvtts_decode_release(None) == 0
