@@ -186,15 +186,15 @@ __device__ __forceinline__ void prefetch_tiles(const Phase &P, int t0, int t1, i
 __device__ __noinline__ void prefetch_plan(int plan, const Desc &D, const Layer &Ly, const Layer &Nx, const Ranges &R, bool first,
                                            int lane) {
     if (plan == kPfWkv) {
-        // recurrent state of the two units of each round, and the head's LoRA up-projection rows
-        const int NP = D.H * ((D.B + 1) >> 1);
+        // recurrent state of the four units of each round, and the head's LoRA up-projection rows
+        const int NQ = D.H * ((D.B + 3) >> 2);
 #pragma unroll 1
-        for (int q = blockIdx.x; q < NP; q += gridDim.x) {
-            const int h = q % D.H, b0 = 2 * (q / D.H);
-            if (lane < 2) {
+        for (int q = blockIdx.x; q < NQ; q += gridDim.x) {
+            const int h = q % D.H, b0 = 4 * (q / D.H);
+            if (lane < 4) {
                 if (b0 + lane < D.B) prefetch_bulk(Ly.state + (size_t)((b0 + lane) * D.H + h) * kC * kC, kC * kC * sizeof(float));
-            } else if (lane < 6) {
-                const int L = lane - 2;
+            } else if (lane < 8) {
+                const int L = lane - 4;
                 if (Ly.up[L] != nullptr) prefetch_bulk(Ly.up[L] + (size_t)h * kC * D.D[L], (unsigned)(kC * D.D[L] * sizeof(bf16)));
             }
         }
@@ -420,13 +420,16 @@ __device__ __noinline__ void phase_argmax(const Desc &D, const StepArgs &a, floa
 }
 
 // ---- (b, head) phase: LoRA ups, decay / kk / a / k' / v', state update, GroupNorm + bonus + gate ---------------------------
-// A CTA takes one head and TWO batch rows per round (one per half of its threads), so the head's LoRA up-projection rows
-// are brought into shared memory once for both.
+// A CTA takes one head and FOUR batch rows per round (one per quarter of its threads), so the head's LoRA up-projection rows
+// are brought into shared memory once for all four, the up-projections of the four rows are one set of mma tiles, and at
+// batch 32 the 128 (head, four rows) units are ONE round on 148 CTAs (with two rows per round most CTAs ran two rounds,
+// paying load issue, LoRA tiles, per-channel stage and epilogue twice: ~3 us per layer).
 __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void half_bar(int half) { asm volatile("bar.sync %0, 256;" :: "r"(1 + half) : "memory"); }
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;" :: "r"(1 + grp) : "memory"); }
+__device__ __forceinline__ float pair_sum(float x) { return x + __shfl_xor_sync(0xffffffffu, x, 1); }
 
 // 64 rows x rank of every LoRA up-projection of head h (contiguous in each [C, rank] matrix) -> shared memory, rows padded
 // by 16 bytes (conflict-free 16-byte reads by the (row, quarter) lanes), asynchronously: for the first round it is issued
@@ -449,29 +452,30 @@ __device__ __noinline__ void stage_up(const Desc &D, const Layer &Ly, int h, bf1
 }
 
 __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool first_layer, float *smem, bf16 *upw, long long *fine) {
-    const int half = threadIdx.x >> 8, t = threadIdx.x & 255, i = t >> 2, p = t & 3, lane = t & 31;
-    const int warp = threadIdx.x >> 5, g = lane >> 2, q4 = lane & 3;
-    const bool lead_warp = (t >> 5) == 0;                  // first warp of the half: the per-channel work
-    // scratch: the two rows of LoRA hidden activations as bf16 [2][kMaxLora + 8], then per half los [4][64], vec [6][64], ys [64]
-    constexpr int kHS = kMaxLora + 8;
+    const int grp = threadIdx.x >> 7, t = threadIdx.x & 127, i = t >> 1, p = t & 1, lane = t & 31;
+    const int warp = threadIdx.x >> 5, g = (threadIdx.x & 31) >> 2, q4 = threadIdx.x & 3;
+    const bool lead_warp = (t >> 5) == 0;                  // first warp of the group: the per-channel work
+    // scratch: the four rows of LoRA hidden activations as bf16 [4][kMaxLora + 8], then per group los [4][64], vec [6][64], ys [64]
+    constexpr int kHS = kMaxLora + 8, kHB = 2 * kHS;       // floats taken by the four bf16 rows
     bf16 *hbf = reinterpret_cast<bf16 *>(smem);
-    float *los = smem + kHS + half * 768, *vec = los + 4 * kC, *ys = vec + 6 * kC;
-    const int C = D.C, H = D.H, NP = H * ((D.B + 1) >> 1);
+    float *los = smem + kHB + grp * 768, *vec = los + 4 * kC, *ys = vec + 6 * kC;
+    const int C = D.C, H = D.H, NQ = H * ((D.B + 3) >> 2);
 #pragma unroll 1
-    for (int q = blockIdx.x; q < NP; q += gridDim.x) {
+    for (int q = blockIdx.x; q < NQ; q += gridDim.x) {
         PROF_POINT(fine, 0);
-        const int h = q % H, b = 2 * (q / H) + half;
+        const int h = q % H, b = 4 * (q / H) + grp;
         const bool valid = b < D.B, lead = lead_warp && valid;
         const int u = b * H + h;
+        // thread (i, p) owns value row i and the keys 8 m + 4 p .. + 3, m < 8
         float4 *srow = reinterpret_cast<float4 *>(Ly.state + ((size_t)u * kC + i) * kC + 4 * p);
-        float4 s4[4];
+        float4 s4[8];
         if (valid) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) s4[j] = __ldcg(srow + 4 * j);          // the long-latency loads first
+            for (int m = 0; m < 8; m++) s4[m] = __ldcg(srow + 2 * m);          // the long-latency loads first
         }
-        if (t * 8 < D.Dtot) {                                                  // this half's row of hl, 16 bytes per thread
-            if (valid) tc05::cp_async16(hbf + half * kHS + t * 8, D.hl + (size_t)b * D.Dtot + t * 8);
-            else *reinterpret_cast<uint4 *>(hbf + half * kHS + t * 8) = make_uint4(0u, 0u, 0u, 0u);
+        if (t * 8 < D.Dtot) {                                                  // this group's row of hl, 16 bytes per thread
+            if (valid) tc05::cp_async16(hbf + grp * kHS + t * 8, D.hl + (size_t)b * D.Dtot + t * 8);
+            else *reinterpret_cast<uint4 *>(hbf + grp * kHS + t * 8) = make_uint4(0u, 0u, 0u, 0u);
         }
         // the lead warp's operands (two channels per lane), all in flight together
         const size_t at = (size_t)b * C + h * kC + 2 * lane;
@@ -492,30 +496,30 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
         tc05::cp_async_wait<0>();                                            // the head's up-projection rows, the hl rows
         __syncthreads();
         PROF_POINT(fine, 2);
-        // LoRA up-projections of both rows on the tensor cores: D[16 x 8] = A[16 x K] B[K x 8] with rows 0 / 1 of A the
-        // two halves' hl rows (the other 14 are zero), B = 8 channels of the staged [64, rank] matrix (K contiguous: the
+        // LoRA up-projections of the four rows on the tensor cores: D[16 x 8] = A[16 x K] B[K x 8] with rows 0..3 of A the
+        // groups' hl rows (the other 12 are zero), B = 8 channels of the staged [64, rank] matrix (K contiguous: the
         // "col" operand as it lies).  Warp w: channels 8 (w & 7) .., LoRAs {w, a} (w < 8) or {v, g}.
         {
-            const int nt = warp & 7, grp = warp >> 3;
+            const int nt = warp & 7, half = warp >> 3;
             int off_h = 0, off_w = 0;
 #pragma unroll 1
             for (int L = 0; L < 4; L++) {
                 const int Dl = D.D[L];
-                if ((L >> 1) == grp && Ly.up[L] != nullptr) {
+                if ((L >> 1) == half && Ly.up[L] != nullptr) {
                     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                    const bf16 *ap = hbf + g * kHS + off_h + 2 * q4;                       // rows >= 2 are zero
+                    const bf16 *ap = hbf + g * kHS + off_h + 2 * q4;                       // rows >= 4 are zero
                     const bf16 *bp = upw + off_w + (nt * 8 + g) * (Dl + 8) + 2 * q4;
 #pragma unroll 1
                     for (int ks = 0; ks < Dl; ks += 16) {
                         uint32_t af[4];
-                        af[0] = g < 2 ? *reinterpret_cast<const uint32_t *>(ap + ks) : 0u;
+                        af[0] = g < 4 ? *reinterpret_cast<const uint32_t *>(ap + ks) : 0u;
                         af[1] = 0u;
-                        af[2] = g < 2 ? *reinterpret_cast<const uint32_t *>(ap + ks + 8) : 0u;
+                        af[2] = g < 4 ? *reinterpret_cast<const uint32_t *>(ap + ks + 8) : 0u;
                         af[3] = 0u;
                         mma_bf16(acc, af, *reinterpret_cast<const uint32_t *>(bp + ks), *reinterpret_cast<const uint32_t *>(bp + ks + 8));
                     }
-                    if (g < 2) {
-                        float *dst = smem + kHS + g * 768 + L * kC + nt * 8 + 2 * q4;          // los of half g
+                    if (g < 4) {
+                        float *dst = smem + kHB + g * 768 + L * kC + nt * 8 + 2 * q4;          // los of group g
                         *reinterpret_cast<float2 *>(dst) = make_float2(rbf(acc[0]), rbf(acc[1]));
                     }
                 }
@@ -525,8 +529,8 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
         }
         __syncthreads();                                                     // los complete; everybody is done with the staged rows
         PROF_POINT(fine, 3);
-        // next round's rows, issued by the 14 warps that now wait for the two lead warps
-        if (q + (int)gridDim.x < NP && !lead_warp) stage_up(D, Ly, (q + gridDim.x) % H, upw, (int)threadIdx.x - 32 - 32 * half, kThreads - 64);
+        // a next round's rows (more than grid quads: batch > 36 at 16 heads), issued by the 12 warps that now wait for the leads
+        if (q + (int)gridDim.x < NQ && !lead_warp) stage_up(D, Ly, (q + gridDim.x) % H, upw, (int)threadIdx.x - 32 * (grp + 1), kThreads - 128);
         tc05::cp_async_commit();
         PROF_POINT(fine, 4);
         float g0 = 0.f, g1 = 0.f;
@@ -554,23 +558,23 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
             *reinterpret_cast<float2 *>(vec + 4 * kC + c0) = make_float2(-kka, -kkb);
             *reinterpret_cast<float2 *>(vec + 5 * kC + c0) = make_float2(rbf(kka * aa), rbf(kkb * ab));
         }
-        half_bar(half);
+        group_bar(grp);
         PROF_POINT(fine, 5);
         if (valid) {
-            // thread (i, p) owns value row i and keys 16m + 4p .. + 3, m < 4: same ownership and summation order as the
-            // stand-alone step kernel (wkv7_scan.cu::wkv7_step_kernel); the six 64-vectors are read as 16-byte pieces
+            // sa_i = sum_j S_ij a_j ; S_ij <- S_ij d_j + sa_i b_j + k_j v_i ; y_i = sum_j S_ij q_j (wkv7_cuda.cu:27-40, T = 1);
+            // the six 64-vectors are read as 16-byte pieces
             float sa = 0.f;
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const float4 av = *reinterpret_cast<const float4 *>(vec + 4 * kC + 16 * m + 4 * p);
+            for (int m = 0; m < 8; m++) {
+                const float4 av = *reinterpret_cast<const float4 *>(vec + 4 * kC + 8 * m + 4 * p);
                 sa = fmaf(s4[m].x, av.x, sa); sa = fmaf(s4[m].y, av.y, sa); sa = fmaf(s4[m].z, av.z, sa); sa = fmaf(s4[m].w, av.w, sa);
             }
-            sa = quad_sum(sa);
+            sa = pair_sum(sa);
             const float vi = vec[3 * kC + i];
             float yy = 0.f;
 #pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int cc = 16 * m + 4 * p;
+            for (int m = 0; m < 8; m++) {
+                const int cc = 8 * m + 4 * p;
                 const float4 dv = *reinterpret_cast<const float4 *>(vec + cc), qv = *reinterpret_cast<const float4 *>(vec + 1 * kC + cc),
                              kv = *reinterpret_cast<const float4 *>(vec + 2 * kC + cc), bv = *reinterpret_cast<const float4 *>(vec + 5 * kC + cc);
                 float4 S = s4[m];
@@ -580,14 +584,14 @@ __device__ __noinline__ void phase_wkv(const Desc &D, const Layer &Ly, bool firs
                 S.w = fmaf(S.w, dv.w, fmaf(sa, bv.w, kv.w * vi)); yy = fmaf(S.w, qv.w, yy);
                 s4[m] = S;
             }
-            yy = quad_sum(yy);
+            yy = pair_sum(yy);
             if (p == 0) ys[i] = rbf(yy);
         }
-        half_bar(half);
+        group_bar(grp);
         PROF_POINT(fine, 6);
         if (valid) {                                                         // the new state leaves behind the barrier
 #pragma unroll
-            for (int m = 0; m < 4; m++) __stcg(srow + 4 * m, s4[m]);
+            for (int m = 0; m < 8; m++) __stcg(srow + 2 * m, s4[m]);
         }
         if (lead) {
             const float2 y = *reinterpret_cast<const float2 *>(ys + 2 * lane);
@@ -779,7 +783,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
     if ((threadIdx.x >> 5) == 1) {
         prefetch_tiles(sL[0].p2, sR.r[kRgP2First][0], sR.r[kRgP2First][1], threadIdx.x & 31);
     }
-    const int NP = D.H * ((D.B + 1) >> 1);
+    const int NQ = D.H * ((D.B + 3) >> 2);
 #pragma unroll 1
     for (int l = 0; l < D.L; l++) {
         const Layer &Ly = sL[l & 1], &Nx = sL[(l + 1) & 1];
@@ -788,7 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_step_kernel(const Desc *__
         if (!(a.debug_skip & 1)) phase_rows<NKB / 2>(D, Ly, kRowLn1, l == 0, a, red_rows, f1 ? fine + 80 : nullptr);
         epoch = grid_sync(cx, epoch, kPfWkv, &Ly, &Nx);
         phase_gemm<NKB, 2>(Ly.p2, sR.r[rp2][0], sR.r[rp2][1], D.B, smem, f1 ? fine + 16 : nullptr);
-        if (!(a.debug_skip & 2) && (int)blockIdx.x < NP) stage_up(D, Ly, blockIdx.x % D.H, upw, threadIdx.x, kThreads);      // first round of the wkv phase
+        if (!(a.debug_skip & 2) && (int)blockIdx.x < NQ) stage_up(D, Ly, blockIdx.x % D.H, upw, threadIdx.x, kThreads);      // first round of the wkv phase
         tc05::cp_async_commit();
         epoch = grid_sync(cx, epoch, kPfOut, &Ly, &Nx);
         if (!(a.debug_skip & 2)) phase_wkv(D, Ly, l == 0, smem, upw, f1 ? fine + 32 : nullptr);
