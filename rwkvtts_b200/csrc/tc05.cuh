@@ -224,6 +224,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// ---- tensor-map copies (TMA engine, tiled): one box of a [B*T, H, 64] bf16 activation tensor per instruction ----
+// `tmap` is the address of a CUtensorMap that lives in a __grid_constant__ kernel parameter (tma_map.h builds it);
+// the box lands densely ([tokens][64] bf16, 128-byte rows, no swizzle) at `sdst` (128-byte aligned) and its bytes are
+// counted on `bar` (pair with mbar_expect_tx).  Coordinates, innermost first: channel, head, token.  Tokens beyond the
+// tensor's end are filled with zeros (and still counted).
+__device__ __forceinline__ void tma_load_box3(void *sdst, const void *tmap, int c_chan, int c_head, int c_tok, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        :: "r"(smem_u32(sdst)), "l"(tmap), "r"(c_chan), "r"(c_head), "r"(c_tok), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void *tmap) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
+}
+
 // ---- cp.async (LDGSTS): global -> shared without staging registers ------------------------------
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");

@@ -41,6 +41,7 @@ struct SeqWork {
     size_t ck0;      // index of the sequence's first chunk slot in the scratch tensors (per head)
     int len, nC;     // tokens, 16-token chunks (ceil)
     int bh;          // dense: b*H + h (s0 / sT / ds0 index); packed: unused
+    int h, tok0;     // head and index of the sequence's first token in the [tokens, H, 64] view (tensor-map coordinates)
 };
 __device__ __forceinline__ SeqWork seq_work(int T, int H, const int *cu, const int *cbase) {
     SeqWork w;
@@ -52,13 +53,16 @@ __device__ __forceinline__ SeqWork seq_work(int T, int H, const int *cu, const i
         w.nC = (w.len + kChunk - 1) / kChunk;
         w.base = (size_t)t0 * tok_stride + (size_t)hh * kC;
         w.ck0 = (size_t)cbase[bb] * H + (size_t)hh * w.nC;
+        w.tok0 = t0;
     } else {
         w.len = T;
         w.nC = T / kChunk;
         w.base = (size_t)bb * T * tok_stride + (size_t)hh * kC;
         w.ck0 = (size_t)blockIdx.x * w.nC;
+        w.tok0 = bb * T;
     }
     w.bh = blockIdx.x;
+    w.h = hh;
     return w;
 }
 
