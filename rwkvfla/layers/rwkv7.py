@@ -113,7 +113,7 @@ class RWKV7Attention(nn.Module):
         am = None
         if attention_mask is not None:
             assert attention_mask.dim() == 2, "Expected attention_mask as a 0-1 matrix [batch_size, seq_len]"
-            am = attention_mask.narrow(1, attention_mask.size(1) - T, T).unsqueeze(-1).to(hidden_states.dtype)
+            am = core.mask3(attention_mask, T, hidden_states.dtype)
         last = None
         if past_key_values is not None and len(past_key_values) > self.layer_idx:
             last = past_key_values[self.layer_idx]

@@ -61,7 +61,7 @@ class RWKV7FeedForward(nn.Module):
                 cu_seqlens=None, use_cache: bool = False, **kwargs):
         am = None
         if attention_mask is not None:
-            am = attention_mask.narrow(1, attention_mask.size(1) - x.shape[1], x.shape[1]).unsqueeze(-1).to(x.dtype)
+            am = core.mask3(attention_mask, x.shape[1], x.dtype)
         shift = None
         if state is not None and len(state) > self.layer_idx:
             shift = state[self.layer_idx].get("ffn_state")

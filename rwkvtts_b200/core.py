@@ -95,6 +95,33 @@ class TmixParams:
     ln_eps: float = 64e-5      # 1e-5 * head_size_divisor**2 (:145) == head_dim * norm_eps (rwkvfla)
 
 
+_MASK_CACHE: list = [None]     # (weakref to the [B, T_all] mask, key, the [B, T, 1] result)
+
+
+def mask3(attention_mask: Optional[torch.Tensor], T: int, dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """The last T columns of a 0/1 `attention_mask` [B, T_all] as a [B, T, 1] tensor of the activations' dtype.  Every
+    layer of a model asks for the same one: the conversion runs once per forward (one entry, keyed on the mask object,
+    its version counter and the autograd / inference mode) instead of twice per layer.  Not cached while a CUDA graph is
+    being captured (the result would live in the graph's private pool)."""
+    if attention_mask is None:
+        return None
+    convert = lambda: attention_mask.narrow(1, attention_mask.size(1) - T, T).unsqueeze(-1).to(dtype)
+    if attention_mask.is_cuda and torch.cuda.is_current_stream_capturing():
+        return convert()
+    import weakref
+    try:
+        ver = attention_mask._version
+    except RuntimeError:                        # an inference tensor tracks no version: nothing to key the entry on
+        return convert()
+    key = (ver, T, dtype, torch.is_inference_mode_enabled(), attention_mask.device)
+    hit = _MASK_CACHE[0]
+    if hit is not None and hit[0]() is attention_mask and hit[1] == key:
+        return hit[2]
+    am = convert()
+    _MASK_CACHE[0] = (weakref.ref(attention_mask), key, am)
+    return am
+
+
 def token_shift(x: torch.Tensor, prev: Optional[torch.Tensor]) -> torch.Tensor:
     """time_shift(x) - x with time_shift = ZeroPad2d((0,0,1,-1)) (:162); `prev` [B,C] is the last
     token of the previous call (:511), zeros if None."""

@@ -1109,6 +1109,85 @@ __global__ void __launch_bounds__(NV <= 3 ? 256 : 320, NV <= 3 ? 2 : 1) add_ln_b
     for (int e = threadIdx.x; e < 2 * P.C; e += blockDim.x) dst[e] = redw[e];
 }
 
+// residual-add + LayerNorm adjoint, third form (C % 256 == 0, C <= 2048): the three input rows of a token (sum, dy, ds)
+// come in through a shared-memory ring filled with cp.async, like prep_bwd_ring_kernel: four rows in flight per CTA
+// independent of the registers (the warp-per-row form holds 64 accumulators per lane -- 182 registers, 10 warps per SM --
+// and fetches ds only after the row reduction: 46 % of the HBM roofline in the train step).  One row lane per CTA of C/8
+// threads, rows strided over the grid; a thread copies exactly the 16-byte pieces it reads later, so the ring needs no
+// barrier; the row reduction is one __syncthreads per row (scratch double buffered by row parity); 16 accumulators per thread.
+constexpr int kLnRing = 5;
+__global__ void __launch_bounds__(256) add_ln_bwd_ring_kernel(const LnParams P) {
+    extern __shared__ __align__(16) unsigned char ln_dyn[];
+    const int C = P.C, c0 = threadIdx.x * kVec, lane = threadIdx.x & 31, wip = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    bf16 *ring = reinterpret_cast<bf16 *>(ln_dyn);                                          // [kLnRing][3][C]
+    float *red = reinterpret_cast<float *>(ln_dyn + (size_t)kLnRing * 3 * C * sizeof(bf16));  // [2 parities][2][8 warps]
+    const Row8 w = ld8f(P.w + c0);
+    const bool has_ds = P.ds != nullptr;
+    const float invC = 1.f / C;
+    auto issue = [&](long it) {
+        const long row = (long)blockIdx.x + it * gridDim.x;
+        if (row < P.rows) {
+            bf16 *dst = ring + (size_t)(it % kLnRing) * 3 * C + c0;
+            tc05::cp_async16(dst, P.sum + row * C + c0);
+            tc05::cp_async16(dst + C, P.dy + row * C + c0);
+            if (has_ds) tc05::cp_async16(dst + 2 * (size_t)C, P.ds + row * C + c0);
+        }
+        tc05::cp_async_commit();
+    };
+    float acc[2][kVec];
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+#pragma unroll
+        for (int i = 0; i < kVec; i++) acc[s][i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnRing - 1; i++) issue(i);
+    auto stats_of = [&](long row) {
+        return row < P.rows ? *reinterpret_cast<const float2 *>(P.stats + 2 * row) : make_float2(0.f, 0.f);
+    };
+    float2 st_next = stats_of(blockIdx.x);
+#pragma unroll 1
+    for (long it = 0;; it++) {
+        const long row = (long)blockIdx.x + it * gridDim.x;
+        if (row >= P.rows) break;
+        const float mu = st_next.x, rstd = st_next.y;
+        st_next = stats_of(row + gridDim.x);
+        tc05::cp_async_wait<kLnRing - 2>();                                  // this row's pieces (own) have landed
+        const bf16 *slot = ring + (size_t)(it % kLnRing) * 3 * C + c0;
+        const Row8 sm_ = ld8s(slot), dy = ld8s(slot + C);
+        const Row8 d2 = has_ds ? ld8s(slot + 2 * (size_t)C) : zero8();
+        issue(it + kLnRing - 1);                                             // into the slot read one iteration ago
+        Row8 sh, g;
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) {
+            sh.v[i] = (sm_.v[i] - mu) * rstd;
+            g.v[i] = dy.v[i] * w.v[i];
+            acc[0][i] = fmaf(dy.v[i], sh.v[i], acc[0][i]);
+            acc[1][i] += dy.v[i];
+            m1 += g.v[i];
+            m2 = fmaf(g.v[i], sh.v[i], m2);
+        }
+        m1 = warp_sum(m1); m2 = warp_sum(m2);
+        float *rp = red + (it & 1) * 16;
+        if (lane == 0) { rp[wip] = m1; rp[8 + wip] = m2; }
+        __syncthreads();
+        m1 = 0.f; m2 = 0.f;
+        for (int j = 0; j < nwarp; j++) { m1 += rp[j]; m2 += rp[8 + j]; }
+        m1 *= invC; m2 *= invC;
+        Row8 o;
+#pragma unroll
+        for (int i = 0; i < kVec; i++) o.v[i] = rstd * (g.v[i] - m1 - sh.v[i] * m2) + d2.v[i];
+        st8(P.dx + row * C + c0, o);
+    }
+    tc05::cp_async_wait<0>();
+    float *dst = P.part + (size_t)blockIdx.x * 2 * C + c0;
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        *reinterpret_cast<float4 *>(dst + (size_t)s * C) = make_float4(acc[s][0], acc[s][1], acc[s][2], acc[s][3]);
+        *reinterpret_cast<float4 *>(dst + (size_t)s * C + 4) = make_float4(acc[s][4], acc[s][5], acc[s][6], acc[s][7]);
+    }
+}
+
 // launch geometry: threads per row = C/8; rows per CTA so that the CTA has <= 512 threads; grid = multiple of the SM count
 struct Geo { int threads, rows_per_cta, grid; size_t red_bytes(int n, int C) const { return (size_t)rows_per_cta * n * C * 4; } };
 inline Geo geometry(int B, int T, int C, int max_rows, int ctas_per_sm, int max_threads = kMaxThreads) {
@@ -1136,7 +1215,7 @@ static bool shape_ok(int B, int T, int C) { return B > 0 && T > 0 && C > 0 && C 
 int tmix_grid(int B, int T, int C, int which) {
     if (!shape_ok(B, T, C)) return 0;
     (void)which;
-    return geometry(B, T, C, 4, 4, kBwdThreads).grid;
+    return geometry(B, T, C, 4, 8, kBwdThreads).grid;       // partial rows the adjoints' scratch holds: up to 8 CTAs per SM
 }
 
 cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, const float *w, const float *b, float eps,
@@ -1157,7 +1236,23 @@ cudaError_t launch_add_ln_bwd(long rows, int C, const void *sum, const float *st
     P.dx = (bf16 *)dx; P.part = part; P.rows = rows; P.C = C;
     const Geo g = geometry(1, (int)rows, C, 4, 4, kBwdThreads);
     count_launch(2);
-    if (C % 256 == 0 && C <= 1024 && rows >= 8) {
+    static const int form = [] { const char *e = getenv("RWKVTTS_LN_BWD"); return e != nullptr ? atoi(e) : 0; }();
+    if (form == 0 && C % 256 == 0 && C <= 2048 && rows >= 64) {
+        // rows through a cp.async ring in shared memory (see add_ln_bwd_ring_kernel); the grid stays within the scratch the
+        // caller sized with rwkvtts_tmix_scratch_floats
+        const size_t shm = (size_t)kLnRing * 3 * C * sizeof(bf16) + 2 * 16 * sizeof(float);
+        int per_sm = (int)((227 * 1024) / (shm + 1024));                 // resident CTAs per SM by shared memory
+        if (per_sm > 8) per_sm = 8;
+        const int cap = geometry(1, (int)rows, C, 4, 8, kBwdThreads).grid;   // = tmix_grid(): rows of the caller's scratch
+        int grid = 148 * per_sm;
+        if (grid > cap) grid = cap;
+        cudaError_t e2 = cudaFuncSetAttribute(add_ln_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm);
+        if (e2 != cudaSuccess) return e2;
+        add_ln_bwd_ring_kernel<<<grid, C / kVec, shm, st>>>(P);
+        reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(part, dparams, grid, 2 * C);
+        return cudaGetLastError();
+    }
+    if (form != 2 && C % 256 == 0 && C <= 1024 && rows >= 8) {
         // one warp per row; the grid stays within the scratch the caller sized with rwkvtts_tmix_scratch_floats
         const int nv = C / 256;
         int grid = (int)((rows + 7) / 8);
