@@ -973,6 +973,59 @@ __global__ void __launch_bounds__(kMaxThreads) add_ln_fwd_kernel(const LnParams 
     }
 }
 
+// residual add + LayerNorm forward, second form (C % 256 == 0, C <= 1024): ONE WARP PER ROW.  A lane owns C/256 groups of 8
+// channels, both row reductions are shuffles (the first form crosses the CTA through shared memory with two barriers per
+// reduction: 55 % of the HBM roofline), and a warp has all 2 * C/256 loads of a row in flight together.
+template <int NV>
+__global__ void __launch_bounds__(256) add_ln_fwd_warp_kernel(const LnParams P) {
+    const int lane = threadIdx.x & 31, wip = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float invC = 1.f / P.C;
+    const bool has_res = P.res != nullptr;
+    const long gw = (long)blockIdx.x * nwarp + wip, nw = (long)gridDim.x * nwarp;
+    for (long row = gw; row < P.rows; row += nw) {
+        uint4 ux[NV], ur[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const size_t off = row * P.C + (size_t)(j * 32 + lane) * kVec;
+            ux[j] = *reinterpret_cast<const uint4 *>(P.x + off);
+            if (has_res) ur[j] = *reinterpret_cast<const uint4 *>(P.res + off);
+        }
+        float xs[NV][kVec];
+        float s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            unpack8(ux[j], xs[j]);
+            if (has_res) {
+                float r[kVec];
+                unpack8(ur[j], r);
+                Row8 t;
+#pragma unroll
+                for (int i = 0; i < kVec; i++) { xs[j][i] = rbf(xs[j][i] + r[i]); t.v[i] = xs[j][i]; }   // the sum is a bf16 tensor in the reference
+                if (P.s != nullptr) st8(P.s + row * P.C + (size_t)(j * 32 + lane) * kVec, t);
+            }
+#pragma unroll
+            for (int i = 0; i < kVec; i++) s1 += xs[j][i];
+        }
+        const float mu = warp_sum(s1) * invC;
+        float s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; j++)
+#pragma unroll
+            for (int i = 0; i < kVec; i++) { const float d = xs[j][i] - mu; s2 = fmaf(d, d, s2); }
+        const float rstd = rsqrtf(warp_sum(s2) * invC + P.eps);
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            const int c0 = (j * 32 + lane) * kVec;
+            const Row8 w = ld8f(P.w + c0), b = P.b != nullptr ? ld8f(P.b + c0) : zero8();
+            Row8 o;
+#pragma unroll
+            for (int i = 0; i < kVec; i++) o.v[i] = (xs[j][i] - mu) * rstd * w.v[i] + b.v[i];
+            st8(P.y + row * P.C + c0, o);
+        }
+        if (P.stats != nullptr && lane == 0) { P.stats[2 * row] = mu; P.stats[2 * row + 1] = rstd; }
+    }
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 2) add_ln_bwd_kernel(const LnParams P) {
     extern __shared__ float redp[];
     __shared__ float red[2 * kBwdThreads / 32];
@@ -1225,6 +1278,19 @@ cudaError_t launch_add_ln_fwd(long rows, int C, const void *x, const void *res, 
     P.eps = eps; P.rows = rows; P.C = C;
     const Geo g = geometry(1, (int)rows, C, 4, 4);
     count_launch();
+    static const int form = [] { const char *e = getenv("RWKVTTS_LN_FWD"); return e != nullptr ? atoi(e) : 0; }();
+    if (form == 0 && C % 256 == 0 && C <= 1024 && rows >= 64) {
+        // one warp per row, 8 rows per CTA, the CTAs that are resident together (73 registers at C = 1024: three per SM)
+        const long need = (rows + 7) / 8, cap = 148L * (C <= 512 ? 4 : 3);
+        const int grid = (int)(need < cap ? need : cap);
+        switch (C / 256) {
+            case 1: add_ln_fwd_warp_kernel<1><<<grid, 256, 0, st>>>(P); break;
+            case 2: add_ln_fwd_warp_kernel<2><<<grid, 256, 0, st>>>(P); break;
+            case 3: add_ln_fwd_warp_kernel<3><<<grid, 256, 0, st>>>(P); break;
+            default: add_ln_fwd_warp_kernel<4><<<grid, 256, 0, st>>>(P); break;
+        }
+        return cudaGetLastError();
+    }
     add_ln_fwd_kernel<<<g.grid, g.threads, 0, st>>>(P);
     return cudaGetLastError();
 }

@@ -53,7 +53,11 @@ constexpr int N32_LBO = 132, N16_LBO = 68, N_SBO = 32;   // [32|16 rows (tokens)
 constexpr int T_SBO = 36, T_LBO = 288;                   // [64 rows (channels)][16 tokens]
 constexpr int G_LBO = 296;   // same tiles when stage B also reads them as mma.sync fragments (Q~, A~, B~, K~): = 8 mod 32, so the
                              // 64-bit fragment loads of a half-warp hit 32 different banks
-constexpr int S32_LBO = 128, S16_LBO = 64, S_SBO = 32;   // [32|16 rows][16]
+// [32|16 rows][16].  The 16-row tiles (stage B's Gram / column stores) and the transposed gradient-Gram tiles are padded by one
+// 16-byte piece per K block: with the dense strides (64 / 128 floats = 0 mod 32 banks) the fragment stores were 8-way / 4-way /
+// 2-way bank conflicted (ncu: 64 wavefronts per tile and chunk where 8-16 are needed); 68 makes the Gram stores 2-way and the
+// column stores conflict-free, 132 the transposed stores conflict-free (the natural ones stay 2-way for any legal stride)
+constexpr int S32_LBO = 128, S32T_LBO = 132, S16_LBO = 68, S_SBO = 32;
 
 struct Slot {
     float UVn[16 * N32_LBO];      // rows 0-15 U (sa), 16-31 V          [.][value]
@@ -63,8 +67,11 @@ struct Slot {
     float dYt[4 * T_LBO], Qt[4 * G_LBO], At[4 * G_LBO], Bt[4 * G_LBO], Kt[4 * G_LBO];   // [channel][token]
     float Gt[4 * T_LBO];          // G (fp32, not an MMA operand), same layout
     float AqbpT[4 * S16_LBO], AqkT[4 * S16_LBO], AakT[4 * S16_LBO];   // [n=s][k=t]          (stage B)
-    float Gs[kC];                 // G at the chunk start
+    // (G at the chunk start lives in the padding of Gt: gs_off())
 };
+// G at the chunk start, one float per channel row, kept in the 16-byte gaps the T_SBO = 36 stride leaves after every core
+// matrix of the Gt tile (outside what any tile access touches)
+__host__ __device__ constexpr int gs_off(int row) { return (row >> 3) * T_SBO + ((row & 7) >> 1) * T_LBO + 32 + (row & 1); }
 constexpr int NRAW = 2;
 // the seven raw input tiles of one chunk as the TMA engine lands them: [16 tokens][64 channels] bf16, 128-byte rows;
 // x[i][16 * t + k4] is the 8-byte piece (channels 4*k4 .. 4*k4+3 of token t) that stage-A thread tp = 16 * t + k4 expands
@@ -74,8 +81,8 @@ struct Smem {
     float ZT[4 * T_LBO];          // Z^T [value][t]
     float QB_N[4 * S32_LBO];      // rows 0-15 dAqb [t][s], 16-31 dN [t][s]
     float QK_AK[4 * S32_LBO];     // rows 0-15 dAqk, 16-31 dAak
-    float NT_AKT[4 * S32_LBO];    // rows 0-15 dN^T [s][t], 16-31 dAak^T
-    float QBT_QKT[4 * S32_LBO];   // rows 0-15 dAqb^T, 16-31 dAqk^T
+    float NT_AKT[4 * S32T_LBO];   // rows 0-15 dN^T [s][t], 16-31 dAak^T
+    float QBT_QKT[4 * S32T_LBO];  // rows 0-15 dAqb^T, 16-31 dAqk^T
     __align__(128) RawBuf raw[NRAW];   // stage A: landing buffers of the tensor-map copies, one chunk ahead
     __align__(128) float S0c[kCkFloats];   // checkpoint S0^T of the chunk in flight: K-major operand tile [key][value],
                                            // brought in by the MMA warp with one bulk copy per chunk
@@ -285,7 +292,10 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
             st4(&S.DYZn[on32], f[0], f[1], f[2], f[3]);
 #pragma unroll
             for (int j = 0; j < 4; j++) S.Gt[ot + 4 * j] = gg[j];
-            if (t == 0) st4(&S.Gs[k4 * 4], gg[0] - lw[0], gg[1] - lw[1], gg[2] - lw[2], gg[3] - lw[3]);
+            if (t == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) S.Gt[gs_off(4 * k4 + j)] = gg[j] - lw[j];
+            }
         }
         fence_proxy_async();
         mbar_arrive_warp(&sm.a_done[si]);
@@ -410,8 +420,8 @@ __device__ void mma_warp(const Params &P, Smem &sm, size_t ck0, int nC) {
     const uint64_t dZT = smem_desc(smem_u32(sm.ZT), T_LBO * 4, T_SBO * 4);
     const uint64_t dQBN = smem_desc(smem_u32(sm.QB_N), S32_LBO * 4, S_SBO * 4);
     const uint64_t dQKAK = smem_desc(smem_u32(sm.QK_AK), S32_LBO * 4, S_SBO * 4);
-    const uint64_t dNTAKT = smem_desc(smem_u32(sm.NT_AKT), S32_LBO * 4, S_SBO * 4);
-    const uint64_t dQBTQKT = smem_desc(smem_u32(sm.QBT_QKT), S32_LBO * 4, S_SBO * 4);
+    const uint64_t dNTAKT = smem_desc(smem_u32(sm.NT_AKT), S32T_LBO * 4, S_SBO * 4);
+    const uint64_t dQBTQKT = smem_desc(smem_u32(sm.QBT_QKT), S32T_LBO * 4, S_SBO * 4);
     int nw = 0;
     for (int it = 0; it < nC; it++) {
         const int c = nC - 1 - it, si = it % NS;
@@ -506,10 +516,10 @@ __device__ void mma_warp(const Params &P, Smem &sm, size_t ck0, int nC) {
             // P2b: [dB~^T | dK~^T] += A~^T [dN^T;dAak^T]^T + Q~^T [dAqb^T;dAqk^T]^T
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok + 32, kadv(dAt, kk, G_LBO), kadv(dNTAKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dAt, kk, G_LBO), kadv(dNTAKT, kk, S32T_LBO), I32, true);
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
-                mma_tf32_ss(ok + 32, kadv(dQt, kk, G_LBO), kadv(dQBTQKT, kk, S32_LBO), I32, true);
+                mma_tf32_ss(ok + 32, kadv(dQt, kk, G_LBO), kadv(dQBTQKT, kk, S32T_LBO), I32, true);
             // P3b: dV^T += dY^T Aqk + Z^T Aak
 #pragma unroll
             for (int kk = 0; kk < 2; kk++)
@@ -643,7 +653,7 @@ __device__ void group_c1(const Params &P, Smem &sm, int bh, int nC, int tid) {
                         float x = acc[nt][2 * hh + e];
                         x = ((q & 1) ? (col < r) : (col <= r)) ? tf32r(x) : 0.f;
                         nat[kmajor_off(nrow + r, col, S32_LBO, S_SBO)] = x;
-                        trn[kmajor_off(trow_ + col, r, S32_LBO, S_SBO)] = x;
+                        trn[kmajor_off(trow_ + col, r, S32T_LBO, S_SBO)] = x;
                     }
                 }
         }
@@ -713,7 +723,7 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
             float G[8], lwv[8], gsum[8], acc_[8], op[8];
             tile8(S.Gt, G, T_LBO);
             {
-                const float gprev = (hf == 0) ? S.Gs[row] : S.Gt[trow + T_LBO + 3];   // G of token 7
+                const float gprev = (hf == 0) ? S.Gt[gs_off(row)] : S.Gt[trow + T_LBO + 3];   // G of token 7
                 lwv[0] = G[0] - gprev;
 #pragma unroll
                 for (int i = 1; i < 8; i++) lwv[i] = G[i] - G[i - 1];
@@ -722,8 +732,9 @@ __device__ void group_c2(const Params &P, Smem &sm, size_t base, size_t tok_stri
             // gradients are staged [array][token][channel] in tiles of this slot that are dead once the chunk's MMAs
             // have completed (UVn + DYZn), then leave as 128-byte rows (2-byte global stores straight from the
             // registers were measured 1.6x slower for the whole stage)
-            const int orow = act ? row : 64 + (lane & 7);          // idle lanes write into the padding columns
-            auto put = [&](int arr, int i, float x) { obuf[arr][8 * hf + i][orow] = __float2bfloat16_rn(x); };
+            // (idle lanes used to write into the padding columns: for the warps of rows 0-15 those share banks with the
+            // live columns -- 20 % more wavefronts on the stage's hottest line, ncu; the stores are predicated instead)
+            auto put = [&](int arr, int i, float x) { if (act) obuf[arr][8 * hf + i][row] = __float2bfloat16_rn(x); };
             float E[8], iE[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) {
