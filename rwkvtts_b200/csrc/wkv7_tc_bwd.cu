@@ -143,7 +143,13 @@ __device__ __forceinline__ void unpack4(const uint2 &u, float *f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage A: tp in [0,256); token t = tp>>4, channels 4*k4 .. 4*k4+3
+// stage A: tp in [0,256); thread = (token t, channels 4*k4 .. 4*k4+3).  Warp wp holds the token group 4*(wp>>1) .. +3:
+// lane = 8*tt + k4l is token 4*(wp>>1) + tt and channel quad k4 = k4l + 8*((tt ^ wp) & 1) -- the two warps of a token group
+// take opposite halves of the channels on odd / even tokens.  With it (bank model + ncu) every access of the stage is
+// conflict-free: a half-warp reads 16 different channel quads of the raw tiles, a scalar store into a transposed
+// [channel][token] operand tile hits 8 row groups x 4 tokens = 32 banks (two tokens x 16 quads per warp, the first mapping,
+// made all six of them 2-way conflicted: 6 % of the kernel's wavefronts), the 16-byte stores into the [token][channel]
+// tiles stay 8 consecutive quads per quarter-warp.
 // ---------------------------------------------------------------------------------------------
 // raw inputs travel HBM -> shared memory as tensor-map boxes (cp.async.bulk.tensor: one 16-token x 64-channel tile of
 // this head per tensor and chunk, no register and no LSU instruction on the way), one chunk ahead; one elected thread
@@ -160,7 +166,8 @@ template <bool kVar>
 __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base, size_t tok_stride, size_t ck0, int h, int tok0,
                         int nC, int len, int tp) {
     long long *P_dbg = tp == 0 ? P.dbg : nullptr; (void)P_dbg;
-    const int t = tp >> 4, k4 = tp & 15, wp = tp >> 5;
+    const int wp = tp >> 5, lane = tp & 31, tt = lane >> 3;
+    const int t = 4 * (wp >> 1) + tt, k4 = (lane & 7) + 8 * ((tt ^ wp) & 1);
     // w of every chunk of the window whose last chunk is c_last: needed when a window is entered from its end,
     // fetched one window ahead
     auto loadw = [&](int c_last, uint2 (&wr)[WIN]) {
@@ -185,7 +192,8 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
         TICK(ta1);
         if (it >= NS) mbar_wait(&sm.empty[si], ((it / NS) - 1) & 1);
         TICK(ta2);
-        float(&wt)[8][kC] = *reinterpret_cast<float(*)[8][kC]>(S.Bpn);          // scratch: stage B writes the tile later
+        float(&lwt)[L][kC] = *reinterpret_cast<float(*)[L][kC]>(S.Bpn);         // scratch: stage B writes the tile later
+        static_assert(sizeof(float) * L * kC <= sizeof(S.Bpn), "scan scratch fits in the B' tile");
         if (win_last) {
             // entering a window (from its end): G at the start of each of its chunks
             float(&wtw)[WIN][8][kC] = *reinterpret_cast<float(*)[WIN][8][kC]>(S.DYZn);   // scratch: dY rows come below
@@ -198,9 +206,9 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     s4[e] = fmaxf(-__expf(f[e]), kMinLogDecay);
-                    s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);
+                    s4[e] += __shfl_xor_sync(0xffffffffu, s4[e], 16);      // lanes tt and tt ^ 2: same channel quad
                 }
-                if (t & 1) st4(&wtw[j][wp][k4 * 4], s4[0], s4[1], s4[2], s4[3]);
+                if (lane & 16) st4(&wtw[j][wp][k4 * 4], s4[0], s4[1], s4[2], s4[3]);   // this warp's two tokens of the quad
             }
             if (c0 > 0) loadw(c0 - 1, wr);        // the window below
             bar_sync(1, 256);
@@ -222,7 +230,7 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
             // end): a token that changes nothing and is never stored
             const bool live = !kVar || c * L + t < len;
 #pragma unroll
-            for (int i = 0; i < 7; i++) raw.x[i] = live ? rb.x[i][tp] : make_uint2(0u, 0u);
+            for (int i = 0; i < 7; i++) raw.x[i] = live ? rb.x[i][16 * t + k4] : make_uint2(0u, 0u);
         }
         float lw[4], gg[4];
         {
@@ -231,23 +239,23 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
 #pragma unroll
             for (int j = 0; j < 4; j++) { lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay); gg[j] = lw[j]; }
         }
+        // G_t = G at the chunk start + inclusive sum of the log-decays over the chunk's tokens: every thread parks its four
+        // values, 64 threads (one per channel) run the prefix over the 16 tokens (independent loads, sums in registers) and
+        // put G back, every thread takes its own
+        st4(&lwt[t][k4 * 4], lw[0], lw[1], lw[2], lw[3]);
+        bar_sync(1, 256);
+        if (tp < kC) {
+            float v[L];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float x = __shfl_up_sync(0xffffffffu, gg[j], 16);
-            if (t & 1) gg[j] += x;
+            for (int i = 0; i < L; i++) v[i] = lwt[i][tp];
+            float run = sm.gst[c % WIN][tp];
+#pragma unroll
+            for (int i = 0; i < L; i++) { run += v[i]; lwt[i][tp] = run; }
         }
-        if (t & 1) st4(&wt[wp][k4 * 4], gg[0], gg[1], gg[2], gg[3]);
         bar_sync(1, 256);
         {
-            const float4 g0 = *reinterpret_cast<const float4 *>(&sm.gst[c % WIN][k4 * 4]);
-            gg[0] += g0.x; gg[1] += g0.y; gg[2] += g0.z; gg[3] += g0.w;
-        }
-#pragma unroll
-        for (int ww = 0; ww < 8; ww++) {
-            if (ww < wp) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(&wt[ww][k4 * 4]);
-                gg[0] += x0.x; gg[1] += x0.y; gg[2] += x0.z; gg[3] += x0.w;
-            }
+            const float4 g0 = *reinterpret_cast<const float4 *>(&lwt[t][k4 * 4]);
+            gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w;
         }
         if (wp == 0) {   // U of this chunk: operand tile rows, HBM -> slot, bulk copies
             const int ln = tp & 31;
