@@ -496,6 +496,8 @@ def leg_fused():
     fb("shift_mix6", lambda: FU.shift_mix(fxg, mixes), [fxg] + mixes, fdo, 7, 8)
     fb("prep", lambda: FU.prep(k_, v_, wl_, al_, vl_, vf_, *pp), [k_, v_, wl_, al_, vl_, vf_] + pp, fdo, 11, 17)
     fb("out", lambda: FU.out(y_, r_, k_, v_, g_, rk_, lw_, lb_, 64e-5), [y_, r_, k_, v_, g_, rk_, lw_, lb_], fdo, 6, 11)
+    lx_, lr_ = act().requires_grad_(True), act().requires_grad_(True)
+    fb("add_layernorm", lambda: FU.add_layernorm(lx_, lr_, lw_, lb_, 1e-5), [lx_, lr_, lw_, lb_], fdo, 4, 4)
     res["note"] = "algorithmic [B,T,C] bf16 arrays moved per call / CUDA-event time of the autograd call; frac of measured HBM peak"
     return res
 

@@ -7,13 +7,16 @@
 #include <cuda_bf16.h>
 namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
+unsigned long long *watchdog_record() { return nullptr; }
+bool watchdog_needs_install(int, cudaStream_t) { return false; }
 extern long long *g_tc_dbg, *g_tcb_dbg;
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT, cudaStream_t st);
+                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
+                          const int *cu, const int *cbase, cudaStream_t st);
 cudaError_t launch_tc_bwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
                           const void *a, const void *b, const void *dy, const float *ckT, const float *sa,
                           const float *sT, const float *dsT, void *dw, void *dq, void *dk, void *dv, void *da,
-                          void *db, float *ds0, cudaStream_t st);
+                          void *db, float *ds0, const int *cu, const int *cbase, cudaStream_t st);
 }
 int main() {
     int B = 8, T = 4096, H = 16; size_t n = (size_t)B * T * H * 64;
@@ -25,9 +28,9 @@ int main() {
     cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
     for (int r = 0; r < 3; r++) {
         cudaMemset(dbg, 0, 128); cudaMemset(dbg2, 0, 128); cudaEventRecord(e0);
-        rwkvtts::launch_tc_fwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[6], s, sa, nullptr, nullptr, 0);
+        rwkvtts::launch_tc_fwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[6], s, sa, nullptr, nullptr, nullptr, nullptr, 0);
         cudaEventRecord(e1);
-        rwkvtts::launch_tc_bwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[7], s, sa, nullptr, nullptr, t[8], t[9], t[10], t[11], t[12], t[13], nullptr, 0);
+        rwkvtts::launch_tc_bwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[7], s, sa, nullptr, nullptr, t[8], t[9], t[10], t[11], t[12], t[13], nullptr, nullptr, nullptr, 0);
         cudaEventRecord(e2); cudaDeviceSynchronize();
     }
     float ms1, ms2; cudaEventElapsedTime(&ms1, e0, e1); cudaEventElapsedTime(&ms2, e1, e2);

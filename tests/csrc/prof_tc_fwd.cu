@@ -7,9 +7,12 @@
 #include <cuda_bf16.h>
 namespace rwkvtts {
 std::atomic<long long> g_kernel_launches{0};
+unsigned long long *watchdog_record() { return nullptr; }
+bool watchdog_needs_install(int, cudaStream_t) { return false; }
 extern long long *g_tc_dbg;
 cudaError_t launch_tc_fwd(int B, int T, int H, const void *w, const void *q, const void *k, const void *v,
-                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT, cudaStream_t st);
+                          const void *a, const void *b, void *y, float *ckT, float *sa, const float *s0, float *sT,
+                          const int *cu, const int *cbase, cudaStream_t st);
 }
 int main() {
     int B = 8, T = 4096, H = 16; size_t n = (size_t)B * T * H * 64;
@@ -19,7 +22,7 @@ int main() {
     long long *dbg; cudaMalloc(&dbg, 16 * 8);
     rwkvtts::g_tc_dbg = dbg;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int r = 0; r < 3; r++) { cudaMemset(dbg, 0, 128); cudaEventRecord(e0); rwkvtts::launch_tc_fwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[6], nullptr, nullptr, nullptr, nullptr, 0); cudaEventRecord(e1); cudaDeviceSynchronize(); }
+    for (int r = 0; r < 3; r++) { cudaMemset(dbg, 0, 128); cudaEventRecord(e0); rwkvtts::launch_tc_fwd(B, T, H, t[0], t[1], t[2], t[3], t[4], t[5], t[6], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0); cudaEventRecord(e1); cudaDeviceSynchronize(); }
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     long long hd[16]; cudaMemcpy(hd, dbg, 128, cudaMemcpyDeviceToHost);
     const char *nm[16] = {"A scan+prefix", "A wait slot empty", "A wait nat empty", "A scale+write+load", "B wait a_done", "B gram", "B solve+write",
