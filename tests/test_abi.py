@@ -115,3 +115,30 @@ def test_decode_plan_entry_points_validate_on_the_host():
     assert L.rwkvtts_decode_init(None, None, None, None, None, 0, None) == -2          # RWKVTTS_ERR_NULL
     assert L.rwkvtts_decode_step(None, None, None, 1, 0, None, 0, 0, None) == -2
     assert L.rwkvtts_decode_release(None) == 0
+
+
+def test_chunked_kernels_are_blackwell_native_in_the_shipped_sass(built):
+    """What the shipped library's machine code contains (no GPU needed: cuobjdump reads the .so): tcgen05 MMAs with
+    tensor-memory loads / stores in both chunked kernels, and the backward's inputs staged by tensor-map copies
+    (cp.async.bulk.tensor -> UTMALDG; north_star: "TMA-staged (B,T,H,D) tiles"), not by per-thread copies."""
+    import shutil
+    import subprocess
+    from rwkvtts_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.lib()._name], capture_output=True, text=True, check=True).stdout
+    per = {}
+    fn = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            fn = line.split("Function :")[1].strip()
+            per[fn] = {"UTCHMMA": 0, "LDTM": 0, "UTMALDG": 0, "LDGSTS": 0}
+        elif fn is not None:
+            for m in per[fn]:
+                if m in line:
+                    per[fn][m] += 1
+    fwd = [v for k, v in per.items() if "wkv7_tc_fwd_kernel" in k]
+    bwd = [v for k, v in per.items() if "wkv7_tc_bwd_kernel" in k]
+    assert len(fwd) == 4 and len(bwd) == 2
+    assert all(v["UTCHMMA"] >= 16 and v["LDTM"] >= 5 for v in fwd + bwd)
+    assert all(v["UTMALDG"] == 14 and v["LDGSTS"] == 0 for v in bwd)      # 7 tiles, issued in the prologue and in the loop
