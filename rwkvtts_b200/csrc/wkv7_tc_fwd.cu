@@ -505,6 +505,7 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
         fence_before_sync();
         mbar_arrive_warp(&sm.y_free[u]);
         if (win_end) mbar_arrive_warp(&sm.win_scaled);
+        TICK(te1a);
         {   // Y tile: [value lanes][16 tokens] -> shared [token][value] bf16 -> 128-byte rows to HBM
             bf16(&yb)[L][72] = sm.ybuf[u];
             if (act) {
@@ -521,11 +522,18 @@ __device__ void epilogue(const Params &P, Smem &sm, size_t base, size_t tok_stri
                     for (int j = 0; j < 16; j++) sap[(j >> 3) * 32 + (j & 7) * 4] = uv[j];
                 }
             }
+            TICK(te1b);
+            // (handing the U^T tile over BEFORE the Y staging and the 16 strided stores of U was measured: the hand-off
+            // comes 750 cycles earlier and the kernel takes the same time -- the training variant is slower than the no-grad
+            // one in every role by the same 40 %, not on this chain; profiles/r02_tc_pair_roles.txt)
             if (kTrain) {
                 fence_proxy_async();
                 mbar_arrive_warp(&sm.ut_ready);
             }
+            TICK(te1c);
             bar_sync(4, 128);
+            TICK(te1d);
+            ACC(16, te1, te1a); ACC(17, te1a, te1b); ACC(18, te1b, te1c); ACC(19, te1c, te1d);
             const int tok = tid >> 3, part = tid & 7;
             const uint4 v = *reinterpret_cast<const uint4 *>(&yb[tok][part * 8]);
             if (!kVar || c * L + tok < len) *reinterpret_cast<uint4 *>(P.y + base + (size_t)(c * L + tok) * tok_stride + part * 8) = v;
