@@ -154,7 +154,9 @@ def test_out(fused, B, T, C):
                                                     (3, 5, 512, True, False),
                                                     # warp-per-row adjoint: every C / 256 class, odd row counts
                                                     (3, 333, 1024, True, True), (2, 77, 768, True, False), (1, 9, 256, False, True),
-                                                    (5, 41, 512, False, False)])
+                                                    (5, 41, 512, False, False),
+                                                    # ring adjoint at its widest row (3 CTAs per SM by shared memory)
+                                                    (2, 96, 2048, True, True)])
 def test_add_layernorm(fused, B, T, C, use_res, use_bias):
     g = torch.Generator(device="cuda").manual_seed(C + T)
     rn = lambda *s: torch.randn(*s, device="cuda", generator=g).bfloat16()
