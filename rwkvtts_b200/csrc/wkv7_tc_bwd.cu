@@ -30,12 +30,13 @@
 //   warps  4-11  group C2 (off the chain): output epilogue of chunk `it` while chunk `it+1` is in flight -- gradient
 //                accumulators double buffered in tensor memory; scaling, dw suffix scan, bf16, staging in slot tiles
 //                that are dead by then, 128-byte rows; window-boundary term sum_v dS.S
-//   warps 12-19  stage A: cp.async ring of the 7 bf16 inputs (one chunk ahead), the window's decays (one window ahead),
-//                decay scan, ten operand tiles; U (`sa`) arrives by bulk copy straight into its operand tile
+//   warps 12-19  stage A: the 7 bf16 input tiles of a chunk land by tensor-map copies (cp.async.bulk.tensor, one chunk
+//                ahead), the window's decays (one window ahead), decay prefix, ten operand tiles; U (`sa`) arrives by bulk
+//                copy straight into its operand tile
 //   warps 20-23  stage B: forward Gram blocks (64-bit conflict-free fragment loads), back substitution
 //   warp   24    MMA issuer; also brings S0^T (the checkpoint, already in operand layout) in with one bulk copy per chunk
 // Three operand slots; scan scratch, stage-B scratch and the output staging alias slot tiles that are written later /
-// already consumed.  Bound by the shared-memory data pipe (~80 % of peak on the SMs that hold a CTA, ncu).
+// already consumed.  Bound by shared memory (bytes through the banks + the dependent hand-offs of a chunk: DESIGN.md 4).
 #include "mma_tf32.cuh"
 #include "tc05.cuh"
 #include "tma_map.h"
@@ -74,7 +75,7 @@ struct Slot {
 __host__ __device__ constexpr int gs_off(int row) { return (row >> 3) * T_SBO + ((row & 7) >> 1) * T_LBO + 32 + (row & 1); }
 constexpr int NRAW = 2;
 // the seven raw input tiles of one chunk as the TMA engine lands them: [16 tokens][64 channels] bf16, 128-byte rows;
-// x[i][16 * t + k4] is the 8-byte piece (channels 4*k4 .. 4*k4+3 of token t) that stage-A thread tp = 16 * t + k4 expands
+// x[i][16 * t + k4] is the 8-byte piece (channels 4*k4 .. 4*k4+3 of token t) one stage-A thread expands
 struct RawBuf { uint2 x[7][256]; };
 struct Smem {
     Slot slot[NS];
@@ -237,7 +238,7 @@ __device__ void stage_a(const Params &P, const TmaMaps &M, Smem &sm, size_t base
             float f[4];
             unpack4(raw.x[0], f);
 #pragma unroll
-            for (int j = 0; j < 4; j++) { lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay); gg[j] = lw[j]; }
+            for (int j = 0; j < 4; j++) lw[j] = fmaxf(-__expf(f[j]), kMinLogDecay);
         }
         // G_t = G at the chunk start + inclusive sum of the log-decays over the chunk's tokens: every thread parks its four
         // values, 64 threads (one per channel) run the prefix over the 16 tokens (independent loads, sums in registers) and
